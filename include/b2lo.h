@@ -1,0 +1,187 @@
+/* b2lo.h — C ABI of the B200-native scan-to-map registration engine.
+ *
+ * This is the drop-in boundary underneath three C++ classes of SiarheiHerasiuta/lidar_odometry
+ * (the reference has no FFI layer of its own; every entry point cites the class member it replaces):
+ *
+ *   lidar_slam::map::FastVoxelFilter                      src/database/VoxelMap.h:53-143
+ *   lidar_slam::map::VoxelMap                             src/database/VoxelMap.h:188-332, VoxelMap.cpp
+ *   lidar_slam::optimization::IterativeClosestPointOptimizer::optimize
+ *                                                         src/optimization/IterativeClosestPointOptimizer.h:158-225, .cpp:255-463
+ *   lidar_slam::optimization::AdaptiveMEstimator (PKO)    src/optimization/AdaptiveMEstimator.h:58-143  (runs on the device inside optimize)
+ *
+ * Conventions: plain pointers and sizes, POD structs, no C++/torch types.  Host pointers unless the
+ * name ends in _dev.  Point clouds are AoS float32 xyz with a caller-given stride in floats (3 for
+ * util::Point3D, 4 for KITTI .bin xyzI).  Poses are row-major 4x4 float32 (util::SE3::Matrix()).
+ * Every function returns an int: 0 = ok, < 0 = error (B2LO_E_*), > 0 = soft outcome (B2LO_S_*).
+ * No exception crosses this boundary.  All work of a context is issued on its own CUDA stream; a
+ * context and the maps created from it must be used from one thread at a time, except the const
+ * readers b2lo_map_counts / b2lo_map_export_surfels which take the map's internal mutex
+ * (VoxelMap::m_mutex, VoxelMap.h:331).  There is NO CPU fallback: without a CUDA device every
+ * call fails with B2LO_E_CUDA.
+ */
+#ifndef B2LO_H
+#define B2LO_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2LO_OK 0
+#define B2LO_S_INSUFFICIENT 1 /* optimize(): correspondences < min_correspondence_points (ICP.cpp:298-302) -> reference returns false */
+#define B2LO_S_EMPTY 2        /* empty input / empty map: nothing done */
+#define B2LO_E_CUDA (-1)
+#define B2LO_E_ARG (-2)
+#define B2LO_E_RANGE (-3)     /* a voxel key left the 21-bit-per-axis Z-order domain (|coord| >= 2^20 voxels) */
+#define B2LO_E_CAPACITY (-4)
+#define B2LO_E_NOMEM (-5)
+
+typedef struct b2lo_ctx b2lo_ctx;
+typedef struct b2lo_map b2lo_map;
+typedef struct b2lo_odom b2lo_odom;
+
+/* optimization::ICPConfig (ICP.h:55-76) + optimization::AdaptiveMEstimatorConfig (AdaptiveMEstimator.h:28-45),
+ * with the values Estimator.cpp:49-70 wires in as defaults (b2lo_default_icp_cfg). */
+typedef struct {
+  int max_iterations;
+  double translation_tolerance, rotation_tolerance;
+  double max_correspondence_distance;
+  int min_correspondence_points;
+  int use_robust_loss;
+  double robust_loss_delta;
+  int use_surfel_correspondence; /* 1: O(1) surfel lookup, 0: exact 5-NN + plane fit ("KDTree" mode) */
+  int use_adaptive_m_estimator;
+  int loss_type;                 /* 0 huber, 1 cauchy (GN weight, ICP.cpp:394-403) */
+  double min_scale_factor, max_scale_factor;
+  int num_alpha_segments;        /* <= 128 */
+  double truncated_threshold;
+  int gmm_components;            /* == 3 */
+  int gmm_sample_size;           /* 1..128 */
+  int pko_kernel_type;           /* 0 huber, 1 cauchy */
+} b2lo_icp_cfg;
+
+/* OptimizationStats (ICP.h:203-210) + per-iteration taps used by the parity tests. */
+#define B2LO_MAX_ITERS 16
+typedef struct {
+  int n_corr;
+  double scale, delta;
+  double H[36], g[6], cost; /* f64 block-tree accumulation of the f32 terms (row-major 6x6; full symmetric) */
+  float dx[6];
+  float T_in[16], T_out[16];
+  int em_iters, kmeans_iters;
+} b2lo_iter_trace;
+typedef struct {
+  int status;               /* B2LO_OK or B2LO_S_INSUFFICIENT */
+  int num_iterations;
+  int num_correspondences;  /* of the last iteration */
+  int converged;            /* tolerance met (the reference reports true whenever it returns true) */
+  double initial_cost, final_cost;
+  float device_ms;          /* CUDA-event time of the optimize call on the context stream */
+  b2lo_iter_trace it[B2LO_MAX_ITERS];
+} b2lo_icp_stats;
+
+void b2lo_default_icp_cfg(b2lo_icp_cfg* cfg);
+const char* b2lo_version(void);
+const char* b2lo_last_error(void);
+void b2lo_struct_sizes(size_t out[5]); /* sizeof icp_cfg, iter_trace, icp_stats, odom_cfg, odom_result: lets a binding verify its mirrors */
+
+/* ---- context ------------------------------------------------------------------------------------ */
+int b2lo_ctx_create(int device, b2lo_ctx** out);
+int b2lo_ctx_destroy(b2lo_ctx* ctx);
+int b2lo_ctx_sync(b2lo_ctx* ctx);
+void* b2lo_ctx_stream(b2lo_ctx* ctx);          /* cudaStream_t */
+long long b2lo_ctx_launch_count(b2lo_ctx* ctx); /* kernels launched by this library on ctx since creation */
+int b2lo_ctx_io_bytes(b2lo_ctx* ctx, unsigned long long* h2d, unsigned long long* d2h); /* PCIe bytes moved by this library on ctx */
+
+/* optional per-kernel CUDA-event timing on the context stream (adds event records; keep it off when timing whole scans).
+ * slots: 0 K1 downsample (5 kernels), 1 K2 surfel correspondence, 2 K4 PKO fit, 3 K4 PKO arg-min, 4 K5 normal equations + solve,
+ * 5 K6 map update (all kernels), 6 cloud transform, 7 K3 kNN + plane fit (3 kernels) */
+int b2lo_ctx_profile(b2lo_ctx* ctx, int enable);
+int b2lo_ctx_profile_read(b2lo_ctx* ctx, int slot, double* total_ms, long long* launches);
+
+/* ---- FastVoxelFilter::filter (VoxelMap.h:73-104) ------------------------------------------------ */
+/* out_xyz: capacity >= ceil(n/stride) points (packed xyz); *m receives the voxel count (getVoxelCount). */
+int b2lo_filter(b2lo_ctx* ctx, const float* xyz, size_t n, size_t stride_floats, int stride, float voxel_size, float* out_xyz,
+                uint64_t* out_keys /* nullable: Morton key of every output voxel */, size_t* m);
+/* device-resident variant: raw scan already in HBM, result stays in the context's feature buffer */
+int b2lo_filter_dev(b2lo_ctx* ctx, const float* xyz_dev, size_t n, size_t stride_floats, int stride, float voxel_size);
+int b2lo_ctx_features(b2lo_ctx* ctx, float* out_xyz, size_t cap, size_t* m); /* copy the feature buffer to the host */
+
+/* ---- VoxelMap ------------------------------------------------------------------------------------ */
+int b2lo_map_create(b2lo_ctx* ctx, float voxel_size, int hierarchy_factor, float planarity_threshold, int compute_surfels,
+                    size_t l0_capacity_hint, b2lo_map** out);                         /* VoxelMap(), Set* (VoxelMap.h:195-209) */
+int b2lo_map_destroy(b2lo_map* map);
+int b2lo_map_clear(b2lo_map* map);                                                    /* Clear (VoxelMap.cpp:122-126) */
+int b2lo_map_set_planarity_threshold(b2lo_map* map, float thr);
+int b2lo_map_set_compute_surfels(b2lo_map* map, int on);
+/* UpdateVoxelMap(cloud, sensor_position, max_distance, is_keyframe=true) (VoxelMap.cpp:128-262) */
+int b2lo_map_update(b2lo_map* map, const float* world_xyz, size_t m, size_t stride_floats, const double sensor[3], double max_distance);
+int b2lo_map_counts(b2lo_map* map, size_t* l0, size_t* l1, size_t* surfels);          /* GetVoxelCount/GetL1VoxelCount/GetSurfelCount */
+int b2lo_map_lookup(b2lo_map* map, const float p[3], float n[3], float c[3]);         /* GetSurfelAtPoint: 1 found, 0 not */
+/* GetPointCloud (VoxelMap.cpp:388-403): L0 centroids in the reference's dense (insertion/swap-erase) order */
+int b2lo_map_export_l0(b2lo_map* map, float* xyz, int* keys /*nullable, 3 per voxel*/, int* counts /*nullable*/, size_t cap, size_t* n);
+/* GetL1Surfels (VoxelMap.cpp:405-418); order unspecified (the reference's L1 order is unobservable elsewhere) */
+int b2lo_map_export_surfels(b2lo_map* map, float* centroid, float* normal, float* planarity, int* l1keys /*nullable*/, size_t cap, size_t* n);
+/* full L1 dump for parity tests: children as L0 keys in the reference's child-set order */
+int b2lo_map_export_l1(b2lo_map* map, int* keys, int* nchild, int* children /*27*3 per L1*/, int* has_surfel, float* normal,
+                       float* centroid, float* planarity, int* last_child_count, size_t cap, size_t* n);
+int b2lo_map_rebuild_knn(b2lo_map* map);                                              /* RebuildKdTree (VoxelMap.cpp:420-438) */
+int b2lo_map_has_knn(b2lo_map* map);                                                  /* HasKdTree (VoxelMap.h:268) */
+int b2lo_map_transform_rehash(b2lo_map* map, const float T16[16]);                    /* ApplyTransformAndRehash (:264-302) */
+
+/* ---- IterativeClosestPointOptimizer ------------------------------------------------------------- */
+/* find_correspondences (ICP.cpp:587-645) at a fixed pose; per-query taps for bit-exact parity:
+ * state 0 no surfel / 1 gated out / 2 accepted; l1key 3 ints; morton = VoxelKeyHash; residual f64. */
+int b2lo_icp_correspondences(b2lo_map* map, const float* local_xyz, size_t m, size_t stride_floats, const float T16[16],
+                             double max_distance, int* state, int* l1key, uint64_t* morton, float* normal, float* centroid,
+                             double* residual, size_t* n_accepted);
+/* find_correspondences_kdtree (ICP.cpp:647-767) at a fixed pose: knn = m*5 indices into the b2lo_map_export_l0 order
+ * (-1 when fewer were found), d2 = m*5 f32 squared distances, found per query, state 0 (<5 / collinear) / 1 gated / 2 accepted;
+ * normal/centroid are the f32 casts the Gauss-Newton loop consumes; *n_scanned = queries that needed the exact full scan. */
+int b2lo_icp_correspondences_knn(b2lo_map* map, const float* local_xyz, size_t m, size_t stride_floats, const float T16[16],
+                                 double max_distance, int* knn, float* d2, int* found, int* state, float* normal, float* centroid,
+                                 double* residual, size_t* n_accepted, size_t* n_scanned);
+/* optimize (ICP.cpp:255-463).  T_init is used verbatim (SE3f initial_transform); on B2LO_S_INSUFFICIENT
+ * T_out = T_init, as the reference leaves optimized_transform. */
+int b2lo_icp_optimize(b2lo_map* map, const float* local_xyz, size_t m, size_t stride_floats, const float T_init[16],
+                      const b2lo_icp_cfg* cfg, float T_out[16], b2lo_icp_stats* stats /*nullable*/);
+/* same, query cloud = the context's feature buffer left by b2lo_filter / b2lo_filter_dev */
+int b2lo_icp_optimize_features(b2lo_map* map, const float T_init[16], const b2lo_icp_cfg* cfg, float T_out[16], b2lo_icp_stats* stats);
+
+/* ---- pose algebra used at the boundary (util::SE3 / SO3, MathUtils.h:57-168) --------------------- */
+void b2lo_se3_mul(const float A16[16], const float B16[16], float C16[16]);  /* SE3::operator*, re-projects the rotation */
+void b2lo_se3_inv(const float A16[16], float C16[16]);                       /* SE3::Inverse */
+void b2lo_se3_from_rt(const float T16_in[16], float T16_out[16]);            /* SE3(Matrix3f, Vector3f) ctor re-projection */
+void b2lo_so3_log(const float T16[16], float w[3]);                          /* SO3::Log of the rotation block */
+void b2lo_so3_exp(const float w[3], float R9[9]);                            /* SO3::Exp (MathUtils.cpp:23-39), row-major 3x3 */
+/* the engine's small dense numerics, exposed so parity tests can pin them on the host (same inline code the kernels run) */
+void b2lo_svd3(const float A9[9], float U9[9], float S3[3], float V9[9]);    /* JacobiSVD<Matrix3f> (VoxelMap.cpp:239, MathUtils.cpp:88) */
+void b2lo_ldlt6_solve(const float H36[36], const float b6[6], float x6[6]);  /* Matrix<float,6,6>::ldlt().solve (ICP.cpp:418) */
+void b2lo_fit_plane(const float* pts, int n, float mu[3], float normal[3], float* planarity); /* surfel PCA (VoxelMap.cpp:223-242) */
+uint64_t b2lo_voxel_key_hash(int x, int y, int z);                           /* VoxelKeyHash (VoxelMap.h:166-183) */
+
+/* ---- per-scan driver kept on the device (Estimator.cpp:116-233, 349-368, 449-470) -- */
+typedef struct {
+  float voxel_size; int point_stride; float map_voxel_size; double max_range;
+  float surfel_planarity_threshold; double keyframe_distance_threshold, keyframe_rotation_threshold;
+  b2lo_icp_cfg icp;
+} b2lo_odom_cfg;
+typedef struct {
+  float pose[16];
+  int keyframe, icp_status, n_features, n_corr, n_iters;
+  float device_ms;       /* whole scan, CUDA events */
+  size_t l0, l1;
+} b2lo_odom_result;
+void b2lo_default_odom_cfg(b2lo_odom_cfg* cfg, int mid360);
+int b2lo_odom_create(b2lo_ctx* ctx, const b2lo_odom_cfg* cfg, b2lo_odom** out);
+int b2lo_odom_destroy(b2lo_odom* od);
+int b2lo_odom_reset(b2lo_odom* od);   /* clear the map and the pose state (new sequence) */
+b2lo_map* b2lo_odom_map(b2lo_odom* od);
+/* process_frame on a host scan (H2D inside) or on a scan already resident in HBM */
+int b2lo_odom_process(b2lo_odom* od, const float* xyz, size_t n, size_t stride_floats, b2lo_odom_result* res);
+int b2lo_odom_process_dev(b2lo_odom* od, const float* xyz_dev, size_t n, size_t stride_floats, b2lo_odom_result* res);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2LO_H */

@@ -1,0 +1,161 @@
+// b2lo_filter.cu — K1: stride + Z-order voxel downsample on the device.
+//
+// Replaces map::FastVoxelFilter::filter (/root/reference/src/database/VoxelMap.h:73-104) with its
+// computeMortonKey (:124-135) / expandBits (:114-122).  Contract reproduced bit-for-bit:
+//   * every `stride`-th point, non-finite points skipped;
+//   * key = Z-order of clamp(floor(x * (1/voxel)) + 2^20, 0, 2^21-1) per axis;
+//   * per voxel the f32 sums run SEQUENTIALLY in input order, centroid = sum * (1/(float)count);
+//   * output order = first-seen order of the voxels (unordered_dense iteration order).
+// Device algorithm (no sort, five small kernels on the context stream):
+//   F1 insert   : sampled point -> key -> claim/find a slot in a scratch hash; count and min-index per voxel
+//   F2 scan     : one CTA; voxel rank = prefix count of "leaders" (first point of each voxel) in input
+//                 order, segment offsets = prefix sum of the per-voxel counts in that order
+//   F3 fill     : every point drops its index into its voxel's segment (arbitrary slot)
+//   F4 rank     : every point counts the smaller indices of its segment -> position in input order
+//   F5 reduce   : one thread per voxel adds its points in input order and writes the centroid
+// Algorithmic bytes: 16 B read per sampled point + 16 B written per voxel.
+#include <climits>
+#include "b2lo_internal.h"
+
+namespace b2 {
+
+__device__ __forceinline__ long long x86_f2ll(float f) {
+  // static_cast<int64_t>(float) as cvttss2si does it: out-of-range -> INT64_MIN ("integer indefinite")
+  if (!(f < 9223372036854775808.0f) || f < -9223372036854775808.0f) return LLONG_MIN;
+  return (long long)f;
+}
+__device__ __forceinline__ unsigned long long filter_key(float x, float y, float z, float inv) {
+  const long long OFF = 1ll << 20, HI = (1ll << 21) - 1;
+  long long ix = x86_f2ll(floorf(x * inv)) + OFF;
+  long long iy = x86_f2ll(floorf(y * inv)) + OFF;
+  long long iz = x86_f2ll(floorf(z * inv)) + OFF;
+  ix = ix < 0 ? 0 : (ix > HI ? HI : ix);
+  iy = iy < 0 ? 0 : (iy > HI ? HI : iy);
+  iz = iz < 0 ? 0 : (iz > HI ? HI : iz);
+  return expand21((uint64_t)ix) | (expand21((uint64_t)iy) << 1) | (expand21((uint64_t)iz) << 2);
+}
+
+__global__ void k_flt_insert(const float* __restrict__ src, int n_samples, size_t sample_stride, float inv, FEntry* tab, int log2cap,
+                             float4* samp, int* slot_of) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_samples; j += gridDim.x * blockDim.x) {
+    const float* p = src + (size_t)j * sample_stride;
+    float x = p[0], y = p[1], z = p[2];
+    samp[j] = make_float4(x, y, z, 0.0f);
+    int s = -1;
+    if (isfinite(x) && isfinite(y) && isfinite(z)) {
+      unsigned long long key = filter_key(x, y, z, inv);
+      uint32_t mask = (1u << log2cap) - 1u;
+      uint32_t h = hash_slot(key, log2cap);
+      for (;;) {
+        unsigned long long k = *((volatile unsigned long long*)&tab[h].key);
+        if (k == key) break;
+        if (k == KEY_EMPTY) {
+          unsigned long long old = atomicCAS(&tab[h].key, KEY_EMPTY, key);
+          if (old == KEY_EMPTY || old == key) break;
+        }
+        h = (h + 1) & mask;
+      }
+      s = (int)h;
+      atomicAdd(&tab[h].cnt, 1);                 // starts at -1 (memset 0xFF): holds count-1
+      atomicMin(&tab[h].first, (unsigned)j);     // starts at 0xFFFFFFFF
+    }
+    slot_of[j] = s;
+  }
+}
+
+// one CTA of 1024 threads walks the samples in input order
+__global__ void __launch_bounds__(1024) k_flt_scan(const FEntry* __restrict__ tab, const int* __restrict__ slot_of, int n_samples,
+                                                    int* vid_of_point, int* seg_start, int* seg_cnt, int* lead_of_vid, int* d_nvox) {
+  __shared__ int sm[40];
+  int base_v = 0, base_c = 0;
+  for (int t0 = 0; t0 < n_samples; t0 += blockDim.x) {
+    int j = t0 + threadIdx.x;
+    int lead = 0, cnt = 0;
+    if (j < n_samples) {
+      int s = slot_of[j];
+      if (s >= 0 && tab[s].first == (unsigned)j) { lead = 1; cnt = tab[s].cnt + 1; }
+    }
+    int tv, tc;
+    int ev = block_excl_scan(lead, &tv, sm);
+    int ec = block_excl_scan(cnt, &tc, sm);
+    if (lead) {
+      int v = base_v + ev;
+      vid_of_point[j] = v;
+      seg_start[v] = base_c + ec;
+      seg_cnt[v] = cnt;
+      lead_of_vid[v] = j;
+    }
+    base_v += tv; base_c += tc;
+  }
+  if (threadIdx.x == 0) { *d_nvox = base_v; seg_start[base_v] = base_c; }
+}
+
+__global__ void k_flt_fill(FEntry* tab, const int* __restrict__ slot_of, int n_samples, const int* __restrict__ vid_of_point,
+                           const int* __restrict__ seg_start, int* bucket) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_samples; j += gridDim.x * blockDim.x) {
+    int s = slot_of[j];
+    if (s < 0) continue;
+    int v = vid_of_point[tab[s].first];
+    int t = atomicSub(&tab[s].cnt, 1);  // count-1, count-2, ..., 0 : a unique ticket in [0, count)
+    bucket[seg_start[v] + t] = j;
+  }
+}
+
+__global__ void k_flt_rank(const FEntry* __restrict__ tab, const int* __restrict__ slot_of, int n_samples,
+                           const int* __restrict__ vid_of_point, const int* __restrict__ seg_start, const int* __restrict__ seg_cnt,
+                           const int* __restrict__ bucket, int* ordered) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_samples; j += gridDim.x * blockDim.x) {
+    int s = slot_of[j];
+    if (s < 0) continue;
+    int v = vid_of_point[tab[s].first];
+    int b = seg_start[v], m = seg_cnt[v], r = 0;
+    for (int q = 0; q < m; ++q) r += (bucket[b + q] < j);
+    ordered[b + r] = j;
+  }
+}
+
+__global__ void k_flt_reduce(const int* __restrict__ d_nvox, const int* __restrict__ seg_start, const int* __restrict__ seg_cnt,
+                             const int* __restrict__ ordered, const int* __restrict__ lead_of_vid, const int* __restrict__ slot_of,
+                             const FEntry* __restrict__ tab, const float4* __restrict__ samp, float4* out, unsigned long long* out_key) {
+  int nv = *d_nvox;
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
+    int b = seg_start[v], m = seg_cnt[v];
+    float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+    for (int q = 0; q < m; ++q) {
+      float4 p = samp[ordered[b + q]];
+      sx += p.x; sy += p.y; sz += p.z;
+    }
+    float ic = 1.0f / (float)(unsigned)m;
+    out[v] = make_float4(sx * ic, sy * ic, sz * ic, 0.0f);
+    out_key[v] = tab[slot_of[lead_of_vid[v]]].key;
+  }
+}
+
+int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sample_stride_floats, float voxel) {
+  if (n_samples == 0) { ctx->feat_cap_hint = 0; B2_CUDA(cudaMemsetAsync(ctx->d_nfeat, 0, sizeof(int), ctx->stream)); return B2LO_OK; }
+  if (n_samples > (size_t)INT_MAX / 4) { set_error("filter: too many samples"); return B2LO_E_CAPACITY; }
+  int rc = ctx_reserve_points(ctx, n_samples);
+  if (rc) return rc;
+  int log2cap = 4;
+  while ((1ull << log2cap) < 2 * n_samples) ++log2cap;
+  if (log2cap > ctx->f_log2cap) { set_error("filter: scratch hash too small"); return B2LO_E_CAPACITY; }
+  ctx->feat_cap_hint = n_samples;
+  cudaStream_t st = ctx->stream;
+  B2_CUDA(cudaMemsetAsync(ctx->f_tab, 0xFF, sizeof(FEntry) << log2cap, st));
+  float inv = 1.0f / voxel;  // m_inv_voxel_size (VoxelMap.h:57)
+  int ns = (int)n_samples;
+  int blocks = (ns + 255) / 256; if (blocks > 1184) blocks = 1184;
+  prof_begin(ctx, PS_FILTER);
+  k_flt_insert<<<blocks, 256, 0, st>>>(src_dev, ns, sample_stride_floats, inv, ctx->f_tab, log2cap, ctx->f_samp, ctx->f_slot);
+  k_flt_scan<<<1, 1024, 0, st>>>(ctx->f_tab, ctx->f_slot, ns, ctx->f_vid, ctx->f_segstart, ctx->f_segcnt, ctx->f_lead, ctx->d_nfeat);
+  k_flt_fill<<<blocks, 256, 0, st>>>(ctx->f_tab, ctx->f_slot, ns, ctx->f_vid, ctx->f_segstart, ctx->f_bucket);
+  k_flt_rank<<<blocks, 256, 0, st>>>(ctx->f_tab, ctx->f_slot, ns, ctx->f_vid, ctx->f_segstart, ctx->f_segcnt, ctx->f_bucket, ctx->f_ordered);
+  k_flt_reduce<<<blocks, 256, 0, st>>>(ctx->d_nfeat, ctx->f_segstart, ctx->f_segcnt, ctx->f_ordered, ctx->f_lead, ctx->f_slot, ctx->f_tab,
+                                       ctx->f_samp, ctx->d_feat, ctx->d_feat_key);
+  prof_end(ctx);
+  ctx->launches += 5;
+  B2_CUDA(cudaGetLastError());
+  return B2LO_OK;
+}
+
+}  // namespace b2

@@ -1,0 +1,834 @@
+// b2lo_icp.cu — K2/K4/K5: scan-to-map ICP with the Gauss-Newton loop resident on the device.
+//
+// Replaces IterativeClosestPointOptimizer::optimize (/root/reference/src/optimization/IterativeClosestPointOptimizer.cpp:255-463)
+// with find_correspondences (:587-645), VoxelMap::GetSurfelAtPoint (src/database/VoxelMap.cpp:368-386),
+// the residual normalisation (:304-316), AdaptiveMEstimator::calculate_scale_factor
+// (src/optimization/AdaptiveMEstimator.cpp:243-291, 294-485, 710-787), the normal equations (:345-410)
+// and the solve + SE(3) right update (:417-448).
+//
+// One Gauss-Newton iteration = four launches on the context stream, no host round trip:
+//   k_icp_corr   : per query: T*p (f32, no FMA) -> L1 key -> one 32 B hash-sector probe -> f64 residual gate;
+//                  per 256-query tile: compacted accepted-query list + count            (48 B / query algorithmic)
+//   k_icp_pko1   : one CTA: tile-count scan, C < min check, iteration-0 sigma/6 scale, libstdc++-exact
+//                  sample draw from the hit tables, k-means, EM (3-component GMM)
+//   k_icp_pko2   : one CTA per alpha candidate: JS divergence; last CTA takes the arg-min -> Huber delta
+//   k_icp_gn     : per accepted query: residual, Jacobian, weight, 28 unique sums; warp-shuffle + shared-memory
+//                  block reduction in f64; the last CTA adds the block partials in fixed order, solves the 6x6
+//                  system (pivoted LDL^T, f32), applies T <- T * (Exp(dw), dt) and sets the convergence flag.
+// Later iterations turn into no-ops once the state's `done` flag is set.
+#include <climits>
+#include <cstring>
+#include "b2lo_internal.h"
+#include "b2lo_knn.cuh"
+
+namespace b2 {
+
+constexpr int TILE = 256;
+constexpr int PKO_THREADS = 256;
+constexpr int MAXS = 128;  // max GMM sample size / alpha candidates handled
+
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void transform_point(const float* R, const float* t, float x, float y, float z, float* w) {
+  // Matrix4f * (x,y,z,1): ((c0*x + c1*y) + c2*z) + c3*1   (src/util/PointCloudUtils.cpp:120-121)
+  w[0] = ((R[0] * x + R[1] * y) + R[2] * z) + t[0] * 1.0f;
+  w[1] = ((R[3] * x + R[4] * y) + R[5] * z) + t[1] * 1.0f;
+  w[2] = ((R[6] * x + R[7] * y) + R[8] * z) + t[2] * 1.0f;
+}
+
+// returns slot (>=0) if the L1 voxel of w holds a surfel; fills n, c and the key taps
+__device__ __forceinline__ int surfel_probe(const MapDev& M, const float* w, float* n, float* c, int* key3, unsigned long long* morton) {
+  int kx = voxel_coord(w[0], M.scale1), ky = voxel_coord(w[1], M.scale1), kz = voxel_coord(w[2], M.scale1);
+  if (key3) { key3[0] = kx; key3[1] = ky; key3[2] = kz; }
+  unsigned long long key = key_morton(kx, ky, kz);
+  if (morton) *morton = key;
+  if (!key_in_range(kx, ky, kz)) return -1;
+  uint32_t mask = (1u << M.l1_log2cap) - 1u;
+  uint32_t s = hash_slot(key, M.l1_log2cap);
+  for (uint32_t probe = 0; probe <= mask; ++probe) {
+    const float4* e = reinterpret_cast<const float4*>(&M.l1_tab[s]);
+    float4 a = __ldg(e);  // key (8 B), n.x, n.y
+    unsigned long long k = ((unsigned long long)__float_as_uint(a.y) << 32) | (unsigned long long)__float_as_uint(a.x);
+    if (k == KEY_EMPTY) return -1;
+    if (k != KEY_TOMB && (k & KEY_MASK) == key) {
+      if (!(k & SURFEL_BIT)) return -1;
+      float4 b = __ldg(e + 1);  // n.z, c.x, c.y, c.z
+      n[0] = a.z; n[1] = a.w; n[2] = b.x; c[0] = b.y; c[1] = b.z; c[2] = b.w;
+      return (int)s;
+    }
+    s = (s + 1) & mask;
+  }
+  return -1;
+}
+
+__device__ __forceinline__ double gate_residual(const float* n, const float* c, const float* w) {
+  // |normal.dot(p_world_d - plane_point)| in f64 (ICP.cpp:623-628); Vector3d dot reduces as (a + b) + c
+  double d0 = (double)w[0] - (double)c[0], d1 = (double)w[1] - (double)c[1], d2 = (double)w[2] - (double)c[2];
+  return fabs(((double)n[0] * d0 + (double)n[1] * d1) + (double)n[2] * d2);
+}
+
+__global__ void __launch_bounds__(TILE) k_icp_corr(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, IcpState* st,
+                                                   IcpParams prm, double* res, int* slot_out, int* cidx, int* tilecnt) {
+  if (st->done) return;
+  __shared__ int sm[40];
+  __shared__ float sR[9], sT[3];
+  if (threadIdx.x < 9) sR[threadIdx.x] = st->R[threadIdx.x];
+  if (threadIdx.x < 3) sT[threadIdx.x] = st->t[threadIdx.x];
+  __syncthreads();
+  const int npts = *d_npts;
+  const int ntiles = (npts + TILE - 1) / TILE;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int i = tile * TILE + threadIdx.x;
+    int ok = 0, s = -1;
+    double r = 0.0;
+    if (i < npts) {
+      float4 p = pts[i];
+      float w[3], n[3], c[3];
+      transform_point(sR, sT, p.x, p.y, p.z, w);
+      s = surfel_probe(M, w, n, c, nullptr, nullptr);
+      if (s >= 0) {
+        r = gate_residual(n, c, w);
+        if (r > prm.max_dist) s = -1; else ok = 1;
+      }
+      slot_out[i] = s;
+      res[i] = r;
+    }
+    int total;
+    int off = block_excl_scan(ok, &total, sm);
+    if (ok) cidx[tile * TILE + off] = i;
+    if (threadIdx.x == 0) tilecnt[tile] = total;
+  }
+}
+
+// ---- KDTree-mode correspondence (K3) ----------------------------------------------------------------
+// search: one thread per query walks the cell shells of the L0 hash; unresolved queries are queued
+__global__ void __launch_bounds__(TILE) k_knn_search(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, IcpState* st,
+                                                     int* knn_idx, int* knn_n, int* unres, int* n_unres) {
+  if (st->done) return;
+  __shared__ float sR[9], sT[3];
+  if (threadIdx.x < 9) sR[threadIdx.x] = st->R[threadIdx.x];
+  if (threadIdx.x < 3) sT[threadIdx.x] = st->t[threadIdx.x];
+  __syncthreads();
+  const int npts = *d_npts;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += gridDim.x * blockDim.x) {
+    float4 p = pts[i];
+    float w[3];
+    transform_point(sR, sT, p.x, p.y, p.z, w);
+    Top5 top;
+    bool exact = knn_rings(M, w, top);
+    if (exact) {
+      for (int k = 0; k < KNN_K; ++k) knn_idx[i * KNN_K + k] = top.id[k];
+      knn_n[i] = top.n;
+    } else {
+      knn_n[i] = -1;
+      unres[atomicAdd(n_unres, 1)] = i;
+    }
+  }
+}
+// exact scan for the queued queries: one warp per query over the dense L0 centroid stream
+__global__ void __launch_bounds__(256) k_knn_brute(MapDev M, const float4* __restrict__ pts, IcpState* st, int* knn_idx, int* knn_n,
+                                                   const int* __restrict__ unres, const int* __restrict__ n_unres) {
+  if (st->done) return;
+  const int nu = *n_unres;
+  const int n0 = M.ctr[0];
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int u = warp; u < nu; u += nwarps) {
+    int i = unres[u];
+    float4 p = pts[i];
+    float w[3];
+    transform_point(st->R, st->t, p.x, p.y, p.z, w);
+    Top5 top;
+    knn_brute_warp(M, n0, w, top);
+    if ((threadIdx.x & 31) == 0) {
+      for (int k = 0; k < KNN_K; ++k) knn_idx[i * KNN_K + k] = top.id[k];
+      knn_n[i] = top.n;
+    }
+  }
+}
+// plane fit + gate + per-tile compaction (same outputs as k_icp_corr, plus the per-query plane)
+__global__ void __launch_bounds__(TILE) k_knn_gate(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, IcpState* st, IcpParams prm,
+                                                   const int* __restrict__ knn_idx, const int* __restrict__ knn_n, int* n_unres, double* res,
+                                                   int* slot_out, int* cidx, int* tilecnt, float4* plane) {
+  if (st->done) return;
+  __shared__ int sm[40];
+  __shared__ float sR[9], sT[3];
+  if (threadIdx.x < 9) sR[threadIdx.x] = st->R[threadIdx.x];
+  if (threadIdx.x < 3) sT[threadIdx.x] = st->t[threadIdx.x];
+  if (blockIdx.x == 0 && threadIdx.x == 0) *n_unres = 0;  // k_knn_brute of this iteration has finished
+  __syncthreads();
+  const int npts = *d_npts;
+  const int ntiles = (npts + TILE - 1) / TILE;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int i = tile * TILE + threadIdx.x;
+    int ok = 0;
+    if (i < npts) {
+      float4 p = pts[i];
+      float w[3], n[3] = {0, 0, 0}, c[3] = {0, 0, 0};
+      transform_point(sR, sT, p.x, p.y, p.z, w);
+      Top5 top;
+      top.init();
+      top.n = knn_n[i] < 0 ? 0 : knn_n[i];
+      for (int k = 0; k < top.n; ++k) top.id[k] = knn_idx[i * KNN_K + k];
+      double r = 0.0;
+      int state = knn_fit(M, top, w, prm.max_dist, n, c, &r);
+      ok = (state == 2);
+      slot_out[i] = ok ? 0 : -1;
+      res[i] = r;
+      plane[2 * i] = make_float4(n[0], n[1], n[2], c[0]);
+      plane[2 * i + 1] = make_float4(c[1], c[2], 0.0f, 0.0f);
+    }
+    int total;
+    int off = block_excl_scan(ok, &total, sm);
+    if (ok) cidx[tile * TILE + off] = i;
+    if (threadIdx.x == 0) tilecnt[tile] = total;
+  }
+}
+// parity tap of the KDTree-mode correspondence at the pose held in st
+__global__ void k_knn_taps(MapDev M, const float4* __restrict__ pts, int npts, IcpState* st, double max_dist, const int* __restrict__ knn_idx,
+                           const int* __restrict__ knn_n, int* idx_out, float* d2_out, int* found, int* state, float* nout, float* cout, double* res) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npts) return;
+  float4 p = pts[i];
+  float w[3], n[3] = {0, 0, 0}, c[3] = {0, 0, 0};
+  transform_point(st->R, st->t, p.x, p.y, p.z, w);
+  Top5 top;
+  top.init();
+  top.n = knn_n[i] < 0 ? 0 : knn_n[i];
+  for (int k = 0; k < KNN_K; ++k) {
+    int id = k < top.n ? knn_idx[i * KNN_K + k] : -1;
+    top.id[k] = id;
+    idx_out[i * KNN_K + k] = id;
+    float d2 = 0.0f;
+    if (id >= 0) { float4 cc = M.l0_cent[id]; d2 = knn_dist2(w, cc.x, cc.y, cc.z); }
+    d2_out[i * KNN_K + k] = d2;
+  }
+  found[i] = top.n;
+  double r = 0.0;
+  int stt = knn_fit(M, top, w, max_dist, n, c, &r);
+  state[i] = stt; res[i] = r;
+  for (int a = 0; a < 3; ++a) { nout[i * 3 + a] = n[a]; cout[i * 3 + a] = c[a]; }
+}
+
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum_d(double v, double* smd /*>=33*/) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) smd[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    int nw = (blockDim.x + 31) >> 5;
+    double x = lane < nw ? smd[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) smd[32] = x;
+  }
+  __syncthreads();
+  double r = smd[32];
+  __syncthreads();
+  return r;
+}
+
+__device__ __forceinline__ double pko_kernel(int type, double r, double delta) {
+  if (type == 0) { double a = fabs(r); return a <= delta ? 1.0 : delta / a; }
+  double e2 = r * r, d2 = delta * delta;
+  return d2 / (d2 + e2);
+}
+__device__ __forceinline__ double gauss_pdf(double x, double mean, double var) {
+  if (var <= 0.0) return 0.0;
+  double diff = x - mean;
+  double ex = -0.5 * (diff * diff) / var;
+  double nrm = 1.0 / sqrt(2.0 * 3.14159265358979323846 * var);
+  return nrm * exp(ex);
+}
+
+// sample position j of std::shuffle(iota(n), mt19937(42)) from the hit tables (see b2lo_pko_host.cpp)
+__device__ int shuffled_head(const PkoTables* T, const int* hits, int n, int j) {
+  int mode = n >= 65536 ? 2 : ((n & 1) ? 1 : 0);
+  int lo = T->hit_off[mode][j], hi = T->hit_off[mode][j + 1];
+  // largest hit < n (lists are ascending and short)
+  int best = -1;
+  for (int q = lo; q < hi; ++q) { int v = hits[q]; if (v < n) best = v; else break; }
+  if (best >= 0) return best;
+  int pos = j;
+  int top = n - 1 < 127 ? n - 1 : 127;
+  for (int i = top; i >= 1; --i) {
+    int r = T->head_r[mode][i];
+    if (pos == i) pos = r; else if (pos == r) pos = i;
+  }
+  return pos;
+}
+
+// One CTA.  Every floating-point SUM of the reference's fit_gmm is a sequential left-to-right loop over the
+// (<=128) samples; those loops are replayed here by single lanes in the same order, so k-means, the EM
+// fixed point and its iteration count agree with the CPU path bit for bit (up to libm exp/log rounding).
+// The embarrassingly parallel parts (sample gather, cluster assignment, responsibilities) use one thread
+// per sample.
+__global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict__ d_npts, IcpState* st, IcpParams prm, const double* __restrict__ res,
+                                                           const int* __restrict__ slot, const int* __restrict__ cidx, const int* __restrict__ tilecnt,
+                                                           int* tileoff, const PkoTables* __restrict__ T, const int* __restrict__ hits, double* gmm_out) {
+  if (st->done) return;
+  __shared__ int sm[40];
+  __shared__ double smd[40];
+  __shared__ double s_x[MAXS];
+  __shared__ double s_r[3][MAXS];
+  __shared__ int s_cl[MAXS];
+  __shared__ double s_mean[3], s_var[3], s_w[3], s_sum[8];
+  __shared__ int s_cnt[3];
+  __shared__ int s_flag;
+  const int tid = threadIdx.x;
+  const int npts = *d_npts;
+  const int ntiles = (npts + TILE - 1) / TILE;
+  // 1. exclusive scan of the per-tile accepted counts
+  int base = 0;
+  for (int t0 = 0; t0 < ntiles; t0 += blockDim.x) {
+    int t = t0 + tid;
+    int c = t < ntiles ? tilecnt[t] : 0;
+    int tot;
+    int e = block_excl_scan(c, &tot, sm);
+    if (t < ntiles) tileoff[t] = base + e;
+    base += tot;
+  }
+  const int C = base;
+  if (tid == 0) { st->n_corr = C; st->n_blocks = ntiles; }
+  if (C < prm.min_corr) {  // ICP.cpp:298-302
+    if (tid == 0) { st->done = 2; st->status = B2LO_S_INSUFFICIENT; }
+    return;
+  }
+  // 2. residual normalisation scale, first iteration only (ICP.cpp:304-316)
+  double scale = st->scale;
+  if (st->iter == 0) {
+    double acc = 0.0;
+    for (int i = tid; i < npts; i += blockDim.x) if (slot[i] >= 0) acc += res[i];
+    double mean = block_sum_d(acc, smd) / (double)C;
+    acc = 0.0;
+    for (int i = tid; i < npts; i += blockDim.x) if (slot[i] >= 0) { double d = res[i] - mean; acc += d * d; }
+    double var = block_sum_d(acc, smd) / (double)C;
+    scale = sqrt(var) / 6.0;
+    if (tid == 0) st->scale = scale;
+  }
+  if (!prm.use_pko) { if (tid == 0) { st->delta = prm.robust_delta; st->em_iters = 0; st->kmeans_iters = 0; } return; }
+  const double sdiv = fmax(scale, 1e-6);
+  // 3. the sample: residuals[idx[0..ns)] of the shuffled index vector (AdaptiveMEstimator.cpp:319-331)
+  const int ns = T->sample_size < C ? T->sample_size : C;
+  if (tid < ns) {
+    int ci = shuffled_head(T, hits, C, tid);
+    int lo = 0, hi = ntiles - 1;  // last tile with tileoff <= ci
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (tileoff[mid] <= ci) lo = mid; else hi = mid - 1; }
+    int q = cidx[lo * TILE + (ci - tileoff[lo])];
+    s_x[tid] = res[q] / sdiv;
+  }
+  __syncthreads();
+  // 4. k-means (:336-389): mean0 = 0, mean1/2 = sample[dis(gen)]
+  if (tid == 0) { s_mean[0] = 0.0; s_mean[1] = s_x[T->kmeans_seed[ns][0]]; s_mean[2] = s_x[T->kmeans_seed[ns][1]]; }
+  __syncthreads();
+  int km_iters = 0;
+  for (;;) {
+    ++km_iters;
+    if (tid < ns) {
+      double x = s_x[tid];
+      double md = 1.7976931348623157e308;
+      int cl = 0;
+      for (int j = 0; j < 3; ++j) { double d = fabs(x - s_mean[j]); if (d < md) { md = d; cl = j; } }
+      s_cl[tid] = cl;
+    }
+    __syncthreads();
+    if (tid < 3) {  // lane j replays new_means[j] += s[i] over i ascending
+      double sum = 0.0; int cnt = 0;
+      for (int i = 0; i < ns; ++i) if (s_cl[i] == tid) { sum += s_x[i]; ++cnt; }
+      s_sum[tid] = sum; s_cnt[tid] = cnt;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double nm[3];
+      nm[0] = 0.0;
+      for (int j = 1; j < 3; ++j) nm[j] = s_cnt[j] > 0 ? s_sum[j] / (double)s_cnt[j] : s_sum[j];
+      int same = (nm[0] == s_mean[0] && nm[1] == s_mean[1] && nm[2] == s_mean[2]);
+      s_flag = same;
+      if (!same) { s_mean[0] = 0.0; s_mean[1] = nm[1]; s_mean[2] = nm[2]; }
+    }
+    __syncthreads();
+    if (s_flag || km_iters >= 100000) break;
+  }
+  // 5. initial variance = population variance of the sample (:392-399); weights = cluster fractions (:402-410)
+  if (tid == 0) {
+    double acc = 0.0;
+    for (int i = 0; i < ns; ++i) acc += s_x[i];
+    double mean = acc / (double)ns;
+    double v = 0.0;
+    for (int i = 0; i < ns; ++i) { double d = s_x[i] - mean; v += d * d; }
+    v /= (double)ns;
+    for (int j = 0; j < 3; ++j) { s_var[j] = v; s_w[j] = (double)s_cnt[j] / (double)ns; }
+  }
+  __syncthreads();
+  // 6. EM (:418-484)
+  int em_iters = 0;
+  for (int it = 0; it < 100; ++it) {
+    ++em_iters;
+    if (tid < ns) {
+      double x = s_x[tid], r[3], sum = 0.0;
+      for (int j = 0; j < 3; ++j) { r[j] = s_w[j] * gauss_pdf(x, s_mean[j], s_var[j]); sum += r[j]; }
+      for (int j = 0; j < 3; ++j) s_r[j][tid] = r[j] / sum;
+    }
+    __syncthreads();
+    if (tid < 5) {  // Nk[0..2]; sum_i resp[i][j] * s[i] for j = 1, 2
+      double acc = 0.0;
+      if (tid < 3) for (int i = 0; i < ns; ++i) acc += s_r[tid][i];
+      else { const int j = tid - 2; for (int i = 0; i < ns; ++i) acc += s_r[j][i] * s_x[i]; }
+      s_sum[tid] = acc;
+    }
+    __syncthreads();
+    double nk[3] = {s_sum[0], s_sum[1], s_sum[2]};
+    double nm[3] = {0.0, s_sum[3] / nk[1], s_sum[4] / nk[2]};
+    if (tid < 3) {
+      double acc = 0.0;
+      const double mj = nm[tid];
+      for (int i = 0; i < ns; ++i) { double diff = s_x[i] - mj; acc += s_r[tid][i] * diff * diff; }
+      s_sum[5 + tid] = fmax(acc / nk[tid], 1e-6);
+    }
+    double change = fabs(nm[1] - s_mean[1]) + fabs(nm[2] - s_mean[2]);
+    __syncthreads();
+    if (tid == 0) {
+      for (int j = 0; j < 3; ++j) { s_w[j] = nk[j] / (double)ns; s_mean[j] = nm[j]; s_var[j] = s_sum[5 + j]; }
+    }
+    __syncthreads();
+    if (change < 1e-6) break;
+  }
+  if (tid == 0) {
+    for (int j = 0; j < 3; ++j) { gmm_out[j] = s_mean[j]; gmm_out[3 + j] = s_var[j]; gmm_out[6 + j] = s_w[j]; }
+    st->em_iters = em_iters; st->kmeans_iters = km_iters;
+  }
+  // 7. P(r_k) of the fitted mixture on the JS grid r_k = dr * (1 + k) (:741-752), shared by all alpha candidates
+  if (tid < 100) {
+    const double dr = T->trunc / 100.0;
+    double r = dr * (1.0 + (double)tid);
+    double Pr = 0.0;
+    for (int m = 0; m < 3; ++m) Pr += s_w[m] * gauss_pdf(r, s_mean[m], s_var[m]);
+    gmm_out[16 + tid] = Pr + 1e-10;
+  }
+}
+
+// one CTA per alpha candidate i = 1..S (blockIdx.x + 1); thread k handles r_k = dr * (1 + k)
+__global__ void __launch_bounds__(128) k_icp_pko2(IcpState* st, IcpParams prm, const PkoTables* __restrict__ T, const double* __restrict__ gmm,
+                                                   double* js, unsigned int* ticket) {
+  if (st->done || !prm.use_pko) return;
+  __shared__ double term[128];
+  __shared__ int s_last;
+  const int k = threadIdx.x;
+  const int ai = blockIdx.x + 1;
+  const double alpha = T->alpha[ai];
+  const double pf = T->Z[ai];
+  const double dr = T->trunc / 100.0;
+  double v = __longlong_as_double(0x7ff8000000000000ll);
+  if (k < 100) {
+    double r = dr * (1.0 + (double)k);
+    double Pr = gmm[16 + k];
+    double Q = pko_kernel(T->kernel_type, r, alpha) / (pf + 1e-10) + 1e-10;
+    double Mx = 0.5 * (Pr + Q);
+    v = 0.5 * (Pr * log(Pr / Mx) + Q * log(Q / Mx));
+  }
+  term[k] = v;
+  __syncthreads();
+  if (k == 0) {
+    double cost = 0.0, cnt = 0.0;
+    for (int q = 0; q < 100; ++q) { double tq = term[q]; if (tq == tq) { cost += tq; cnt += 1.0; } }
+    double out = (pf < 1e-10 || cnt == 0.0) ? 1.7976931348623157e308 : cost / cnt;
+    js[ai] = out;
+    __threadfence();
+    unsigned int old = atomicAdd(ticket, 1u);
+    s_last = (old == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && k == 0) {
+    __threadfence();
+    double best_alpha = T->min_sf, best = 1.7976931348623157e308;
+    for (int i = 1; i < T->n_alpha; ++i) { double c = ((volatile double*)js)[i]; if (c < best) { best = c; best_alpha = T->alpha[i]; } }
+    st->delta = best_alpha;
+    *ticket = 0u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+__device__ void gn_finish(IcpState* st, const IcpParams& prm, const double* acc /*28*/) {
+  // unpack: 21 lower-triangle entries (row-major a>=b), 6 g, 1 cost
+  float H[36], g[6];
+  double H64[36];
+  int q = 0;
+  for (int a = 0; a < 6; ++a)
+    for (int b = 0; b <= a; ++b) { double v = acc[q++]; H64[a * 6 + b] = v; H64[b * 6 + a] = v; H[a * 6 + b] = (float)v; H[b * 6 + a] = (float)v; }
+  for (int a = 0; a < 6; ++a) g[a] = (float)acc[21 + a];
+  const int it = st->iter;
+  b2lo_iter_trace* tr = (it < B2LO_MAX_ITERS) ? &st->trace[it] : nullptr;
+  Pose cur;
+  for (int i = 0; i < 9; ++i) cur.R.m[i] = st->R[i];
+  for (int i = 0; i < 3; ++i) cur.t[i] = st->t[i];
+  if (tr) {
+    tr->n_corr = st->n_corr; tr->scale = st->scale; tr->delta = st->delta;
+    for (int i = 0; i < 36; ++i) tr->H[i] = H64[i];
+    for (int i = 0; i < 6; ++i) tr->g[i] = acc[21 + i];
+    tr->cost = acc[27];
+    pose_to_T16(cur, tr->T_in);
+    tr->em_iters = st->em_iters; tr->kmeans_iters = st->kmeans_iters;
+  }
+  float mg[6], dx[6];
+  for (int a = 0; a < 6; ++a) mg[a] = -g[a];
+  ldlt6_solve(H, mg, dx);
+  float dt[3] = {dx[0], dx[1], dx[2]}, dw[3] = {dx[3], dx[4], dx[5]};
+  Pose d;
+  float wn = sqrtf(sqn3(dw));
+  if (wn < 1e-10f) d.R = so3_project(mat3_identity()); else d.R = so3_exp(dw);
+  d.t[0] = dt[0]; d.t[1] = dt[1]; d.t[2] = dt[2];
+  Pose nxt = pose_mul(cur, d);
+  for (int i = 0; i < 9; ++i) st->R[i] = nxt.R.m[i];
+  for (int i = 0; i < 3; ++i) st->t[i] = nxt.t[i];
+  if (tr) { for (int i = 0; i < 6; ++i) tr->dx[i] = dx[i]; pose_to_T16(nxt, tr->T_out); }
+  float tn = sqrtf(sqn3(dt));
+  bool conv = ((double)tn < prm.tol_t) && ((double)wn < prm.tol_r);
+  if (it == 0) st->initial_cost = (double)(float)acc[27];
+  st->final_cost = (double)(float)acc[27];
+  st->num_iterations = it + 1;
+  st->iter = it + 1;
+  if (conv) { st->done = 1; st->converged = 1; }
+  else if (it + 1 >= prm.max_iterations) st->done = 1;
+}
+
+template <bool SURFEL>
+__global__ void __launch_bounds__(TILE) k_icp_gn(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, IcpState* st, IcpParams prm,
+                                                 const double* __restrict__ res, const int* __restrict__ slot, const float4* __restrict__ plane,
+                                                 double* partial) {
+  if (st->done) return;
+  __shared__ double red[8][28];
+  __shared__ float sR[9], sT[3];
+  __shared__ int s_last;
+  if (threadIdx.x < 9) sR[threadIdx.x] = st->R[threadIdx.x];
+  if (threadIdx.x < 3) sT[threadIdx.x] = st->t[threadIdx.x];
+  __syncthreads();
+  const int npts = *d_npts;
+  const double sdiv = fmax(st->scale, 1e-6);
+  const float delta = (float)st->delta;
+  double acc[28];
+#pragma unroll
+  for (int k = 0; k < 28; ++k) acc[k] = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += gridDim.x * blockDim.x) {
+    int s = slot[i];
+    if (s < 0) continue;
+    float4 P = pts[i];
+    float n[3], qc[3];
+    if (SURFEL) {
+      const float4* e = reinterpret_cast<const float4*>(&M.l1_tab[s]);
+      float4 ea = __ldg(e), eb = __ldg(e + 1);
+      n[0] = ea.z; n[1] = ea.w; n[2] = eb.x; qc[0] = eb.y; qc[1] = eb.z; qc[2] = eb.w;
+    } else {
+      float4 ea = plane[2 * i], eb = plane[2 * i + 1];
+      n[0] = ea.x; n[1] = ea.y; n[2] = ea.z; qc[0] = ea.w; qc[1] = eb.x; qc[2] = eb.y;
+    }
+    float p[3] = {P.x, P.y, P.z};
+    // p_world = R * p + t ; residual = n . (p_world - q)            (ICP.cpp:368-371)
+    float Rp[3]; mat3_vec(sR, p, Rp);
+    float d[3] = {(Rp[0] + sT[0]) - qc[0], (Rp[1] + sT[1]) - qc[1], (Rp[2] + sT[2]) - qc[2]};
+    float r = dot3(n, d);
+    float J[6];
+    for (int j = 0; j < 3; ++j) J[j] = add3(n[0] * sR[j], n[1] * sR[3 + j], n[2] * sR[6 + j]);               // n^T R
+    float u[3];
+    for (int j = 0; j < 3; ++j) u[j] = add3((-n[0]) * sR[j], (-n[1]) * sR[3 + j], (-n[2]) * sR[6 + j]);      // (-n)^T R
+    J[3] = add3(u[0] * 0.0f, u[1] * p[2], u[2] * (-p[1]));                                                   // ... * [p]x
+    J[4] = add3(u[0] * (-p[2]), u[1] * 0.0f, u[2] * p[0]);
+    J[5] = add3(u[0] * p[1], u[1] * (-p[0]), u[2] * 0.0f);
+    float w = 1.0f;
+    if (prm.use_robust) {  // ICP.cpp:388-404
+      float an = fabsf((float)(res[i] / sdiv));
+      if (prm.loss_type == 1) { float ratio = an / delta; w = 1.0f / (1.0f + ratio * ratio); }
+      else if (an > delta) w = delta / an;
+    }
+    int q = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      float wJ = w * J[a];
+#pragma unroll
+      for (int b = 0; b <= a; ++b) acc[q++] += (double)(wJ * J[b]);
+    }
+    float wr = w * r;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) acc[21 + a] += (double)(wr * J[a]);
+    acc[27] += (double)(wr * r);
+  }
+  // block reduction: warp shuffle, then shared memory across the 8 warps
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 28; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[wid][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 28) {
+    double v = 0.0;
+    for (int w8 = 0; w8 < 8; ++w8) v += red[w8][threadIdx.x];
+    partial[blockIdx.x * 28 + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) { unsigned int old = atomicAdd(&st->ticket, 1u); s_last = (old == gridDim.x - 1); }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < 28) {
+    double v = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) v += ((volatile double*)partial)[b * 28 + threadIdx.x];
+    red[0][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { st->ticket = 0u; gn_finish(st, prm, red[0]); }
+}
+
+struct Init16 { float m[16]; };
+__global__ void k_icp_begin(IcpState* st, Init16 T, int from_state /*1: st->T_init was written by an earlier kernel*/) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (!from_state) for (int i = 0; i < 16; ++i) st->T_init[i] = T.m[i];
+    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) st->R[i * 3 + j] = st->T_init[i * 4 + j]; st->t[i] = st->T_init[i * 4 + 3]; }
+    st->iter = 0; st->done = 0; st->status = B2LO_OK; st->n_corr = 0; st->scale = 1.0; st->delta = 0.0; st->ticket = 0u;
+    st->num_iterations = 0; st->converged = 0; st->initial_cost = 0.0; st->final_cost = 0.0; st->em_iters = 0; st->kmeans_iters = 0;
+  }
+}
+// on failure the reference leaves optimized_transform = initial (ICP.cpp:266,301)
+__global__ void k_icp_end(IcpState* st) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && st->done == 2) {
+    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) st->R[i * 3 + j] = st->T_init[i * 4 + j]; st->t[i] = st->T_init[i * 4 + 3]; }
+  }
+}
+
+// parity tap: per-query correspondence state at a fixed pose
+__global__ void k_icp_taps(MapDev M, const float4* __restrict__ pts, int npts, const float* __restrict__ T16, double max_dist, int* state,
+                           int* key3, unsigned long long* morton, float* nout, float* cout, double* res) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npts) return;
+  float R[9], t[3];
+  for (int a = 0; a < 3; ++a) { for (int b = 0; b < 3; ++b) R[a * 3 + b] = T16[a * 4 + b]; t[a] = T16[a * 4 + 3]; }
+  float4 p = pts[i];
+  float w[3], n[3] = {0, 0, 0}, c[3] = {0, 0, 0};
+  transform_point(R, t, p.x, p.y, p.z, w);
+  int s = surfel_probe(M, w, n, c, key3 + i * 3, morton + i);
+  int stt = 0; double r = 0.0;
+  if (s >= 0) { r = gate_residual(n, c, w); stt = (r > max_dist) ? 1 : 2; }
+  state[i] = stt; res[i] = r;
+  for (int a = 0; a < 3; ++a) { nout[i * 3 + a] = n[a]; cout[i * 3 + a] = c[a]; }
+}
+
+// ---------------------------------------------------------------------------------------------------
+static int knn_reserve(b2lo_ctx* ctx) {
+  if (ctx->k_cap >= ctx->pts_cap) return B2LO_OK;
+  B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  void* old[] = {ctx->k_idx, ctx->k_n, ctx->k_unres, ctx->k_plane};
+  for (void* p : old) if (p) cudaFree(p);
+  size_t cap = ctx->pts_cap;
+  B2_CUDA(cudaMalloc((void**)&ctx->k_idx, cap * KNN_K * sizeof(int)));
+  B2_CUDA(cudaMalloc((void**)&ctx->k_n, cap * sizeof(int)));
+  B2_CUDA(cudaMalloc((void**)&ctx->k_unres, cap * sizeof(int)));
+  B2_CUDA(cudaMalloc((void**)&ctx->k_plane, cap * 2 * sizeof(float4)));
+  if (!ctx->k_nunres) { B2_CUDA(cudaMalloc((void**)&ctx->k_nunres, sizeof(int))); B2_CUDA(cudaMemsetAsync(ctx->k_nunres, 0, sizeof(int), ctx->stream)); }
+  ctx->k_cap = cap;
+  return B2LO_OK;
+}
+
+int icp_build_pko(b2lo_ctx* ctx, const b2lo_icp_cfg* cfg) {
+  if (cfg->num_alpha_segments < 1 || cfg->num_alpha_segments > 128 || cfg->gmm_sample_size < 1 || cfg->gmm_sample_size > 128 ||
+      cfg->gmm_components != 3 || cfg->pko_kernel_type < 0 || cfg->pko_kernel_type > 1) {
+    set_error("PKO config outside the supported domain (segments<=128, sample<=128, 3 components, huber|cauchy kernel)");
+    return B2LO_E_ARG;
+  }
+  const b2lo_icp_cfg& o = ctx->pko_cfg_built;
+  if (ctx->pko_built && o.num_alpha_segments == cfg->num_alpha_segments && o.gmm_sample_size == cfg->gmm_sample_size &&
+      o.pko_kernel_type == cfg->pko_kernel_type && o.min_scale_factor == cfg->min_scale_factor && o.max_scale_factor == cfg->max_scale_factor &&
+      o.truncated_threshold == cfg->truncated_threshold)
+    return B2LO_OK;
+  bool first = ctx->h_pko_hits.empty();
+  if (first) pko_build_host(cfg, &ctx->h_pko, &ctx->h_pko_hits);
+  else { std::vector<int> tmp; pko_build_host(cfg, &ctx->h_pko, &tmp); }
+  if (!ctx->d_pko) B2_CUDA(cudaMalloc(&ctx->d_pko, sizeof(PkoTables)));
+  if (!ctx->d_pko_hits) B2_CUDA(cudaMalloc(&ctx->d_pko_hits, sizeof(int) * (ctx->h_pko_hits.size() + 1)));
+  B2_CUDA(cudaMemcpyAsync(ctx->d_pko, &ctx->h_pko, sizeof(PkoTables), cudaMemcpyHostToDevice, ctx->stream));
+  B2_CUDA(cudaMemcpyAsync(ctx->d_pko_hits, ctx->h_pko_hits.data(), sizeof(int) * ctx->h_pko_hits.size(), cudaMemcpyHostToDevice, ctx->stream));
+  B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->pko_cfg_built = *cfg;
+  ctx->pko_built = true;
+  return B2LO_OK;
+}
+
+// enqueue a whole optimize() on the context stream.  T_init16 (host) is copied through the pinned state
+// block unless init_pose_on_device (then st->T_init was written by a previous kernel).
+int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_cap, const float* T_init16, const b2lo_icp_cfg* cfg,
+            bool init_pose_on_device) {
+  b2lo_ctx* ctx = map->ctx;
+  if (cfg->max_iterations < 1 || cfg->max_iterations > B2LO_MAX_ITERS) { set_error("max_iterations must be in [1,%d]", B2LO_MAX_ITERS); return B2LO_E_ARG; }
+  int rc = icp_build_pko(ctx, cfg);
+  if (rc) return rc;
+  const bool surfel = cfg->use_surfel_correspondence != 0;
+  if (!surfel && (rc = knn_reserve(ctx))) return rc;
+  cudaStream_t s = ctx->stream;
+  IcpParams prm;
+  prm.max_iterations = cfg->max_iterations; prm.min_corr = cfg->min_correspondence_points; prm.use_robust = cfg->use_robust_loss;
+  prm.loss_type = cfg->loss_type; prm.use_pko = cfg->use_adaptive_m_estimator; prm.use_surfel = cfg->use_surfel_correspondence;
+  prm.tol_t = cfg->translation_tolerance; prm.tol_r = cfg->rotation_tolerance; prm.max_dist = cfg->max_correspondence_distance;
+  prm.robust_delta = cfg->robust_loss_delta;
+  Init16 Ti;
+  for (int i = 0; i < 16; ++i) Ti.m[i] = init_pose_on_device ? 0.0f : T_init16[i];
+  k_icp_begin<<<1, 32, 0, s>>>(ctx->d_icp, Ti, init_pose_on_device ? 1 : 0);
+  int ntiles_cap = (int)((npts_cap + TILE - 1) / TILE);
+  int grid = ntiles_cap < 1 ? 1 : (ntiles_cap > ctx->i_max_blocks ? ctx->i_max_blocks : ntiles_cap);
+  double* gmm = ctx->i_partial + (size_t)ctx->i_max_blocks * 28;      // 9 GMM doubles, then P(r_k) at [16, 116)
+  double* js = gmm + 120;                                             // 129 doubles
+  unsigned int* tk = reinterpret_cast<unsigned int*>(js + 132);       // PKO arg-min ticket (zeroed at context creation)
+  for (int it = 0; it < cfg->max_iterations; ++it) {
+    if (surfel) {
+      prof_begin(ctx, PS_CORR);
+      k_icp_corr<<<grid, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt);
+      prof_end(ctx);
+    } else {
+      prof_begin(ctx, PS_KNN);
+      k_knn_search<<<grid, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, ctx->k_idx, ctx->k_n, ctx->k_unres, ctx->k_nunres);
+      k_knn_brute<<<ctx->sm_count * 2, 256, 0, s>>>(map->d, d_pts, ctx->d_icp, ctx->k_idx, ctx->k_n, ctx->k_unres, ctx->k_nunres);
+      k_knn_gate<<<grid, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->k_idx, ctx->k_n, ctx->k_nunres, ctx->i_res, ctx->i_slot,
+                                       ctx->i_cidx, ctx->i_blkcnt, ctx->k_plane);
+      prof_end(ctx);
+      ctx->launches += 2;
+    }
+    prof_begin(ctx, PS_PKO1);
+    k_icp_pko1<<<1, PKO_THREADS, 0, s>>>(d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff, ctx->d_pko,
+                                         ctx->d_pko_hits, gmm);
+    prof_end(ctx);
+    if (cfg->use_adaptive_m_estimator) {
+      prof_begin(ctx, PS_PKO2);
+      k_icp_pko2<<<cfg->num_alpha_segments, 128, 0, s>>>(ctx->d_icp, prm, ctx->d_pko, gmm, js, tk);
+      prof_end(ctx);
+    }
+    prof_begin(ctx, PS_GN);
+    if (surfel) k_icp_gn<true><<<grid, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, nullptr, ctx->i_partial);
+    else k_icp_gn<false><<<grid, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->k_plane, ctx->i_partial);
+    prof_end(ctx);
+    ctx->launches += cfg->use_adaptive_m_estimator ? 4 : 3;
+  }
+  k_icp_end<<<1, 32, 0, s>>>(ctx->d_icp);
+  ctx->launches += 2;
+  B2_CUDA(cudaGetLastError());
+  return B2LO_OK;
+}
+
+__global__ void k_lookup(MapDev M, float px, float py, float pz, float* out7) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float w[3] = {px, py, pz}, n[3] = {0, 0, 0}, c[3] = {0, 0, 0};
+  int s = surfel_probe(M, w, n, c, nullptr, nullptr);
+  out7[0] = s >= 0 ? 1.0f : 0.0f;
+  for (int a = 0; a < 3; ++a) { out7[1 + a] = n[a]; out7[4 + a] = c[a]; }
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int b2lo_icp_correspondences(b2lo_map* map, const float* local_xyz, size_t m, size_t stride_floats, const float T16[16],
+                                        double max_distance, int* state, int* l1key, uint64_t* morton, float* normal, float* centroid,
+                                        double* residual, size_t* n_accepted) {
+  if (!map || !T16 || !state || !l1key || !morton || !normal || !centroid || !residual) return B2LO_E_ARG;
+  if (stride_floats < 3) return B2LO_E_ARG;
+  if (n_accepted) *n_accepted = 0;
+  if (!local_xyz || m == 0) return B2LO_S_EMPTY;
+  std::lock_guard<std::recursive_mutex> lk(map->mu);
+  b2lo_ctx* ctx = map->ctx;
+  std::lock_guard<std::mutex> lk2(ctx->mu);
+  cudaSetDevice(ctx->device);
+  int rc = ctx_stage_h2d(ctx, local_xyz, m, stride_floats, 1, ctx->d_query, ctx->d_nquery);
+  if (rc) return rc;
+  int* d_state = nullptr; int* d_key = nullptr; unsigned long long* d_mor = nullptr; float* d_n = nullptr; float* d_c = nullptr; double* d_r = nullptr;
+  float* d_T = nullptr;
+  B2_CUDA(cudaMalloc(&d_state, m * sizeof(int)));
+  B2_CUDA(cudaMalloc(&d_key, m * 3 * sizeof(int)));
+  B2_CUDA(cudaMalloc(&d_mor, m * sizeof(unsigned long long)));
+  B2_CUDA(cudaMalloc(&d_n, m * 3 * sizeof(float)));
+  B2_CUDA(cudaMalloc(&d_c, m * 3 * sizeof(float)));
+  B2_CUDA(cudaMalloc(&d_r, m * sizeof(double)));
+  B2_CUDA(cudaMalloc(&d_T, 16 * sizeof(float)));
+  B2_CUDA(cudaMemcpyAsync(d_T, T16, 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  k_icp_taps<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(map->d, ctx->d_query, (int)m, d_T, max_distance, d_state, d_key, d_mor, d_n, d_c, d_r);
+  ctx->launches++;
+  B2_CUDA(cudaGetLastError());
+  B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  B2_CUDA(cudaMemcpy(state, d_state, m * sizeof(int), cudaMemcpyDeviceToHost));
+  B2_CUDA(cudaMemcpy(l1key, d_key, m * 3 * sizeof(int), cudaMemcpyDeviceToHost));
+  B2_CUDA(cudaMemcpy(morton, d_mor, m * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  B2_CUDA(cudaMemcpy(normal, d_n, m * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+  B2_CUDA(cudaMemcpy(centroid, d_c, m * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+  B2_CUDA(cudaMemcpy(residual, d_r, m * sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(d_state); cudaFree(d_key); cudaFree(d_mor); cudaFree(d_n); cudaFree(d_c); cudaFree(d_r); cudaFree(d_T);
+  if (n_accepted) { size_t c = 0; for (size_t i = 0; i < m; ++i) c += (state[i] == 2); *n_accepted = c; }
+  return B2LO_OK;
+}
+
+extern "C" int b2lo_map_lookup(b2lo_map* map, const float p[3], float n[3], float c[3]) {
+  if (!map || !p || !n || !c) return B2LO_E_ARG;
+  b2lo_ctx* ctx = map->ctx;
+  std::lock_guard<std::recursive_mutex> lk(map->mu);
+  cudaSetDevice(ctx->device);
+  float* d_out = reinterpret_cast<float*>(ctx->i_partial + (size_t)ctx->i_max_blocks * 28 + 260);
+  k_lookup<<<1, 32, 0, ctx->stream>>>(map->d, p[0], p[1], p[2], d_out);
+  ctx->launches++;
+  float h[8];
+  B2_CUDA(cudaMemcpyAsync(ctx->h_counts + 24, d_out, 7 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::memcpy(h, ctx->h_counts + 24, 7 * sizeof(float));
+  if (h[0] == 0.0f) return 0;
+  n[0] = h[1]; n[1] = h[2]; n[2] = h[3]; c[0] = h[4]; c[1] = h[5]; c[2] = h[6];
+  return 1;
+}
+
+
+// KDTree-mode parity tap: exact 5-NN (indices into the b2lo_map_export_l0 order), found count, plane, gate
+extern "C" int b2lo_icp_correspondences_knn(b2lo_map* map, const float* local_xyz, size_t m, size_t stride_floats, const float T16[16],
+                                            double max_distance, int* knn, float* d2, int* found, int* state, float* normal, float* centroid,
+                                            double* residual, size_t* n_accepted, size_t* n_scanned) {
+  if (!map || !T16 || !knn || !d2 || !found || !state || !normal || !centroid || !residual) return B2LO_E_ARG;
+  if (stride_floats < 3) return B2LO_E_ARG;
+  if (n_accepted) *n_accepted = 0;
+  if (n_scanned) *n_scanned = 0;
+  if (!local_xyz || m == 0) return B2LO_S_EMPTY;
+  std::lock_guard<std::recursive_mutex> lk(map->mu);
+  b2lo_ctx* ctx = map->ctx;
+  std::lock_guard<std::mutex> lk2(ctx->mu);
+  cudaSetDevice(ctx->device);
+  int rc = ctx_stage_h2d(ctx, local_xyz, m, stride_floats, 1, ctx->d_query, ctx->d_nquery);
+  if (rc) return rc;
+  if ((rc = knn_reserve(ctx))) return rc;
+  cudaStream_t s = ctx->stream;
+  Init16 Ti;
+  for (int i = 0; i < 16; ++i) Ti.m[i] = T16[i];
+  k_icp_begin<<<1, 32, 0, s>>>(ctx->d_icp, Ti, 0);
+  int grid = (int)((m + TILE - 1) / TILE);
+  if (grid > ctx->i_max_blocks) grid = ctx->i_max_blocks;
+  k_knn_search<<<grid, TILE, 0, s>>>(map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, ctx->k_idx, ctx->k_n, ctx->k_unres, ctx->k_nunres);
+  B2_CUDA(cudaMemcpyAsync(ctx->h_counts + 40, ctx->k_nunres, sizeof(int), cudaMemcpyDeviceToHost, s));
+  k_knn_brute<<<ctx->sm_count * 2, 256, 0, s>>>(map->d, ctx->d_query, ctx->d_icp, ctx->k_idx, ctx->k_n, ctx->k_unres, ctx->k_nunres);
+  B2_CUDA(cudaMemsetAsync(ctx->k_nunres, 0, sizeof(int), s));
+  int *d_idx = nullptr, *d_found = nullptr, *d_state = nullptr; float *d_d2 = nullptr, *d_n = nullptr, *d_c = nullptr; double* d_r = nullptr;
+  B2_CUDA(cudaMalloc(&d_idx, m * KNN_K * sizeof(int)));
+  B2_CUDA(cudaMalloc(&d_d2, m * KNN_K * sizeof(float)));
+  B2_CUDA(cudaMalloc(&d_found, m * sizeof(int)));
+  B2_CUDA(cudaMalloc(&d_state, m * sizeof(int)));
+  B2_CUDA(cudaMalloc(&d_n, m * 3 * sizeof(float)));
+  B2_CUDA(cudaMalloc(&d_c, m * 3 * sizeof(float)));
+  B2_CUDA(cudaMalloc(&d_r, m * sizeof(double)));
+  k_knn_taps<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(map->d, ctx->d_query, (int)m, ctx->d_icp, max_distance, ctx->k_idx, ctx->k_n, d_idx, d_d2, d_found,
+                                                         d_state, d_n, d_c, d_r);
+  ctx->launches += 4;
+  B2_CUDA(cudaGetLastError());
+  B2_CUDA(cudaStreamSynchronize(s));
+  B2_CUDA(cudaMemcpy(knn, d_idx, m * KNN_K * sizeof(int), cudaMemcpyDeviceToHost));
+  B2_CUDA(cudaMemcpy(d2, d_d2, m * KNN_K * sizeof(float), cudaMemcpyDeviceToHost));
+  B2_CUDA(cudaMemcpy(found, d_found, m * sizeof(int), cudaMemcpyDeviceToHost));
+  B2_CUDA(cudaMemcpy(state, d_state, m * sizeof(int), cudaMemcpyDeviceToHost));
+  B2_CUDA(cudaMemcpy(normal, d_n, m * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+  B2_CUDA(cudaMemcpy(centroid, d_c, m * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+  B2_CUDA(cudaMemcpy(residual, d_r, m * sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(d_idx); cudaFree(d_d2); cudaFree(d_found); cudaFree(d_state); cudaFree(d_n); cudaFree(d_c); cudaFree(d_r);
+  if (n_accepted) { size_t c = 0; for (size_t i = 0; i < m; ++i) c += (state[i] == 2); *n_accepted = c; }
+  if (n_scanned) *n_scanned = (size_t)ctx->h_counts[40];
+  return B2LO_OK;
+}

@@ -1,0 +1,150 @@
+// b2lo_internal.h — host-side objects behind the opaque handles of include/b2lo.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "../../include/b2lo.h"
+#include "b2lo_dev.cuh"
+
+namespace b2 {
+
+void set_error(const char* fmt, ...);
+#define B2_CUDA(expr)                                                                               \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) {                                                                        \
+      b2::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);    \
+      return B2LO_E_CUDA;                                                                           \
+    }                                                                                               \
+  } while (0)
+
+// ---- device-side state blocks ------------------------------------------------------------------------
+struct FEntry { unsigned long long key; int cnt; unsigned int first; };  // filter scratch hash, 16 B
+
+struct PkoTables {                // built on the host once per context (b2lo_pko_host.cpp)
+  double alpha[129], Z[129];      // alpha candidates and partition functions (AdaptiveMEstimator.cpp:218-241)
+  int n_alpha;                    // num_alpha_segments + 1
+  int kmeans_seed[129][2];        // uniform_int_distribution(0, ns-1)(mt19937(42)) draws for sample size ns
+  int head_r[3][128];             // first swaps r_i (i < 128) of std::shuffle per mode (even, odd, large n)
+  int hit_off[3][129];            // per mode, per head position j: [hit_off[j], hit_off[j+1]) into hits
+  int hit_n;
+  // config scalars
+  double min_sf, max_sf, trunc;
+  int sample_size, kernel_type;
+};
+
+struct IcpState {                 // lives in device memory, one per context
+  float R[9], t[3];               // current pose
+  float T_init[16];
+  int iter, done, status;         // done: 1 converged / max reached, 2 failed
+  int n_corr, n_blocks;
+  double scale, delta;
+  int em_iters, kmeans_iters;
+  unsigned int ticket;            // last-block election of the GN reduction
+  int num_iterations; int converged; double initial_cost, final_cost;
+  b2lo_iter_trace trace[B2LO_MAX_ITERS];
+};
+
+struct IcpParams {                // kernel-argument POD
+  int max_iterations, min_corr, use_robust, loss_type, use_pko, use_surfel;
+  double tol_t, tol_r, max_dist, robust_delta;
+};
+
+}  // namespace b2
+
+namespace b2 {
+// optional per-kernel CUDA-event timing on the context stream (bench.py roofline leg); off by default
+enum ProfSlot { PS_FILTER = 0, PS_CORR = 1, PS_PKO1 = 2, PS_PKO2 = 3, PS_GN = 4, PS_MAP = 5, PS_XFORM = 6, PS_KNN = 7, PS_COUNT = 8 };
+struct Prof {
+  bool on = false;
+  static constexpr int POOL = 512;
+  cudaEvent_t a[POOL], b[POOL]; int slot[POOL]; int used = 0; bool created = false;
+  double ms[PS_COUNT] = {0}; long long n[PS_COUNT] = {0};
+};
+}  // namespace b2
+
+
+struct b2lo_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  long long launches = 0;
+  unsigned long long h2d_bytes = 0, d2h_bytes = 0;   // bytes moved over PCIe by this context (bench accounting)
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_stage = nullptr;
+  bool stage_busy = false;
+  int sm_count = 148;
+  size_t feat_cap_hint = 0;        // host-known upper bound of *d_nfeat (samples of the last filter run)
+  cudaGraphExec_t icp_graph_exec = nullptr; unsigned long long icp_graph_sig = 0;
+  b2::MapDev* d_mapdev = nullptr;
+  // capacities (points)
+  size_t pts_cap = 0;
+  // pinned staging + device staging for host clouds
+  float* h_stage = nullptr; size_t h_stage_floats = 0;
+  float* d_stage = nullptr; size_t d_stage_floats = 0;
+  // feature cloud (output of the filter, input of ICP / transform)
+  float4* d_feat = nullptr; unsigned long long* d_feat_key = nullptr; int* d_nfeat = nullptr;
+  // ICP query cloud uploaded from the host
+  float4* d_query = nullptr; int* d_nquery = nullptr;
+  float4* d_world = nullptr;       // transformed cloud (map update input)
+  // filter scratch
+  b2::FEntry* f_tab = nullptr; int f_log2cap = 0;
+  float4* f_samp = nullptr; int* f_slot = nullptr; int* f_vid = nullptr; int* f_segstart = nullptr; int* f_segcnt = nullptr;
+  int* f_lead = nullptr; int* f_bucket = nullptr; int* f_ordered = nullptr;
+  // ICP scratch
+  double* i_res = nullptr; int* i_slot = nullptr; int* i_cidx = nullptr; int* i_blkcnt = nullptr; int* i_blkoff = nullptr;
+  double* i_partial = nullptr;     // per-block 28 doubles
+  int i_max_blocks = 0;
+  b2::IcpState* d_icp = nullptr; b2::IcpState* h_icp = nullptr /*pinned*/;
+  b2::PkoTables* d_pko = nullptr; int* d_pko_hits = nullptr; b2::PkoTables h_pko; std::vector<int> h_pko_hits;
+  b2lo_icp_cfg pko_cfg_built{}; bool pko_built = false;
+  // KDTree-mode scratch (b2lo_knn.cuh): 5 neighbour ids + found count per query, unresolved queue, fitted planes
+  int* k_idx = nullptr; int* k_n = nullptr; int* k_unres = nullptr; int* k_nunres = nullptr; float4* k_plane = nullptr; size_t k_cap = 0;
+  // parity taps scratch
+  int* d_tap_state = nullptr; int* d_tap_key = nullptr; unsigned long long* d_tap_morton = nullptr; float* d_tap_n = nullptr; float* d_tap_c = nullptr;
+  int* h_counts = nullptr;         // pinned small readback area (64 ints)
+  b2::Prof* prof = nullptr;
+  std::mutex mu;
+};
+
+struct b2lo_map {
+  b2lo_ctx* ctx = nullptr;
+  b2::MapDev d{};                  // device pointers + params (passed by value to kernels)
+  size_t tcap0 = 0, tcap1 = 0;
+  // update scratch sized by the number of new points
+  size_t upd_cap = 0;
+  float4* u_pts = nullptr; int* u_pslot = nullptr; int* u_next = nullptr; int* u_isnew = nullptr; int* u_newrank = nullptr;
+  int* u_l1slot = nullptr; int* u_next1 = nullptr;
+  b2::FEntry* a_tab = nullptr; int a_log2cap = 0;   // affected-L1 set of the current update
+  int* a_list = nullptr;                            // compacted affected slots / purge list
+  // cull scratch (sized by dense capacity)
+  uint8_t* c_flag = nullptr; int* c_blkcnt = nullptr; int* c_blkoff = nullptr; int* c_removed = nullptr; int* c_surv = nullptr;
+  int* c_l1work = nullptr;
+  // purge scratch
+  int* p_seq = nullptr; int* p_aux = nullptr; size_t p_cap = 0;
+  int* u_state = nullptr;          // small device int block of per-update scalars
+  // host mirrors
+  size_t n0 = 0, n1 = 0, tomb0 = 0, tomb1 = 0;
+  bool knn_ready = false;
+  std::recursive_mutex mu;
+};
+
+namespace b2 {
+void prof_begin(b2lo_ctx* ctx, int slot);
+void prof_end(b2lo_ctx* ctx);
+void prof_drain(b2lo_ctx* ctx);
+// implemented across the .cu files
+int ctx_reserve_points(b2lo_ctx* ctx, size_t n);
+int ctx_stage_h2d(b2lo_ctx* ctx, const float* xyz, size_t n, size_t stride_floats, size_t take_every, float4* dst, int* d_count);
+int ctx_transform(b2lo_ctx* ctx, const float4* src, const int* d_n, size_t n_cap, const float T16[16], float4* dst);
+int ctx_read_cloud(b2lo_ctx* ctx, const float4* src, const int* d_n, size_t n_cap, float* out_xyz, size_t out_cap, size_t* n_out);
+int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sample_stride_floats, float voxel);
+int icp_build_pko(b2lo_ctx* ctx, const b2lo_icp_cfg* cfg);
+int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_cap, const float* T_init16, const b2lo_icp_cfg* cfg, bool init_pose_on_device);
+int map_update_dev(b2lo_map* map, const float4* d_world, const int* d_n, size_t n_cap, const float sensor_f[3], float radius_sq, int rehash = 0);
+int map_reserve(b2lo_map* map, size_t need_l0, size_t need_upd);
+int map_refresh_counts(b2lo_map* map);
+int map_rebuild_knn_locked(b2lo_map* map);
+void pko_build_host(const b2lo_icp_cfg* cfg, PkoTables* t, std::vector<int>* hits);
+}  // namespace b2

@@ -1,0 +1,212 @@
+// b2lo_odom.cu — per-scan driver that keeps the scan on the device between the hot-path stages.
+//
+// Mirrors the in-scope part of processing::Estimator (/root/reference/src/processing/Estimator.cpp):
+//   process_frame :116-233, initialize_first_frame :235-269, estimate_motion_dual_frame :271-320,
+//   should_create_keyframe :349-368, create_keyframe (map part) :449-470, preprocess_frame :561-589.
+// Per scan: K1 downsample -> K2..K5 ICP (device-resident Gauss-Newton loop) -> one small read-back
+// (pose + counters) -> host keyframe decision -> K6 map update on keyframes.  The feature cloud never
+// leaves HBM; only the 16-float pose and a few counters cross PCIe (plus the strided scan upload for
+// b2lo_odom_process).  Loop closure / PGO / viewer stay with the host Estimator and are out of scope.
+#include <cstring>
+#include "b2lo_internal.h"
+
+using namespace b2;
+
+struct b2lo_odom {
+  b2lo_ctx* ctx = nullptr;
+  b2lo_map* map = nullptr;
+  b2lo_odom_cfg cfg{};
+  Pose pose, prev_pose, velocity, last_kf_pose;
+  bool initialized = false;
+  int n_keyframes = 0;
+};
+
+static Pose pose_identity() {
+  Pose p;
+  p.R = mat3_identity();
+  p.t[0] = p.t[1] = p.t[2] = 0.0f;
+  return p;
+}
+static Pose pose_reproject(const Pose& a) {  // SE3f(R.matrix, t): the SO3(Matrix3f) ctor re-projects (MathUtils.h:116-117)
+  Pose r = a;
+  r.R = so3_project(a.R);
+  return r;
+}
+
+extern "C" void b2lo_default_odom_cfg(b2lo_odom_cfg* c, int mid360) {  // config/kitti.yaml / config/mid360.yaml
+  if (!c) return;
+  c->voxel_size = mid360 ? 0.4f : 0.5f;
+  c->point_stride = mid360 ? 4 : 8;
+  c->map_voxel_size = mid360 ? 0.4f : 0.5f;
+  c->max_range = 100.0;
+  c->surfel_planarity_threshold = 0.1f;
+  c->keyframe_distance_threshold = 1.0;
+  c->keyframe_rotation_threshold = 0.3;
+  b2lo_default_icp_cfg(&c->icp);
+  if (mid360) c->icp.use_surfel_correspondence = 0;
+}
+
+extern "C" int b2lo_odom_create(b2lo_ctx* ctx, const b2lo_odom_cfg* cfg, b2lo_odom** out) {
+  if (!ctx || !cfg || !out) return B2LO_E_ARG;
+  *out = nullptr;
+  b2lo_odom* od = new b2lo_odom();
+  od->ctx = ctx;
+  od->cfg = *cfg;
+  // Estimator.cpp:78-81: VoxelMap(map_voxel_size), hierarchy factor 3, planarity threshold, surfels iff surfel correspondence
+  int rc = b2lo_map_create(ctx, cfg->map_voxel_size, 3, cfg->surfel_planarity_threshold, cfg->icp.use_surfel_correspondence, 1u << 17, &od->map);
+  if (rc) { delete od; return rc; }
+  od->pose = od->prev_pose = od->velocity = od->last_kf_pose = pose_identity();
+  *out = od;
+  return B2LO_OK;
+}
+extern "C" int b2lo_odom_destroy(b2lo_odom* od) {
+  if (!od) return B2LO_E_ARG;
+  if (od->map) b2lo_map_destroy(od->map);
+  delete od;
+  return B2LO_OK;
+}
+extern "C" b2lo_map* b2lo_odom_map(b2lo_odom* od) { return od ? od->map : nullptr; }
+
+static bool should_create_keyframe(const b2lo_odom* od, const Pose& cur) {  // Estimator.cpp:349-368
+  if (od->n_keyframes == 0) return true;
+  float d[3] = {cur.t[0] - od->last_kf_pose.t[0], cur.t[1] - od->last_kf_pose.t[1], cur.t[2] - od->last_kf_pose.t[2]};
+  double distance = (double)sqrtf(sqn3(d));
+  Mat3 rd = so3_project(mat3_mul(so3_project(mat3_t(od->last_kf_pose.R)), cur.R));
+  float lg[3];
+  so3_log(rd, lg);
+  double angle = (double)sqrtf(sqn3(lg));
+  return distance > od->cfg.keyframe_distance_threshold || angle > od->cfg.keyframe_rotation_threshold;
+}
+
+// create_keyframe, map part (Estimator.cpp:449-470): feature cloud at the optimised pose -> UpdateVoxelMap
+static int create_keyframe(b2lo_odom* od, size_t n_cap) {
+  b2lo_ctx* ctx = od->ctx;
+  float T16[16];
+  pose_to_T16(od->pose, T16);
+  int rc = ctx_transform(ctx, ctx->d_feat, ctx->d_nfeat, n_cap, T16, ctx->d_world);
+  if (rc) return rc;
+  float sensor[3] = {od->pose.t[0], od->pose.t[1], od->pose.t[2]};
+  double md = od->cfg.max_range * 1.2;  // Estimator.cpp:455
+  rc = map_update_dev(od->map, ctx->d_world, ctx->d_nfeat, n_cap, sensor, (float)(md * md));
+  if (rc < 0) return rc;
+  if (!od->cfg.icp.use_surfel_correspondence) { rc = map_rebuild_knn_locked(od->map); if (rc < 0) return rc; }
+  od->last_kf_pose = od->pose;
+  od->n_keyframes++;
+  return B2LO_OK;
+}
+
+static int process_common(b2lo_odom* od, const float* src_dev, size_t ns, size_t sample_stride_floats, b2lo_odom_result* res) {
+  b2lo_ctx* ctx = od->ctx;
+  b2lo_map* map = od->map;
+  cudaStream_t st = ctx->stream;
+  std::memset(res, 0, sizeof *res);
+  int rc = filter_run(ctx, src_dev, ns, sample_stride_floats, od->cfg.voxel_size);
+  if (rc) return rc;
+  int* hc = ctx->h_counts + 32;
+  if (!od->initialized) {  // initialize_first_frame
+    B2_CUDA(cudaMemcpyAsync(hc, ctx->d_nfeat, sizeof(int), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    ctx->d2h_bytes += sizeof(int);
+    res->n_features = hc[0];
+    if (hc[0] == 0) return B2LO_S_EMPTY;  // Estimator.cpp:131-134
+    od->pose = pose_identity();
+    od->velocity = pose_identity();
+    rc = create_keyframe(od, ns);
+    if (rc) return rc;
+    od->prev_pose = od->pose;
+    od->initialized = true;
+    res->keyframe = 1;
+    res->icp_status = B2LO_S_EMPTY;
+  } else {
+    Pose guess = pose_mul(od->prev_pose, od->velocity);  // Estimator.cpp:154
+    Pose result = guess;
+    bool ran_icp = false;
+    if (map->n0 > 0) {  // keyframe->get_local_map() non-empty (Estimator.cpp:279-285)
+      Pose init = pose_reproject(guess);
+      float T16[16];
+      pose_to_T16(init, T16);
+      rc = icp_run(map, ctx->d_feat, ctx->d_nfeat, ns, T16, &od->cfg.icp, false);
+      if (rc) return rc;
+      B2_CUDA(cudaMemcpyAsync(ctx->h_icp, ctx->d_icp, offsetof(IcpState, trace), cudaMemcpyDeviceToHost, st));
+      ctx->d2h_bytes += offsetof(IcpState, trace);
+      ran_icp = true;
+    }
+    B2_CUDA(cudaMemcpyAsync(hc, ctx->d_nfeat, sizeof(int), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    ctx->d2h_bytes += sizeof(int);
+    res->n_features = hc[0];
+    if (hc[0] == 0) return B2LO_S_EMPTY;
+    res->icp_status = B2LO_S_EMPTY;
+    if (ran_icp) {
+      const IcpState* h = ctx->h_icp;
+      res->icp_status = h->status; res->n_corr = h->n_corr; res->n_iters = h->num_iterations;
+      if (h->status == B2LO_OK) {
+        Pose opt;
+        for (int i = 0; i < 9; ++i) opt.R.m[i] = h->R[i];
+        for (int i = 0; i < 3; ++i) opt.t[i] = h->t[i];
+        result = pose_reproject(opt);  // Estimator.cpp:300-302
+      }
+    }
+    od->pose = result;
+    od->velocity = pose_mul(pose_inv(od->prev_pose), od->pose);  // :177
+    if (should_create_keyframe(od, od->pose)) {
+      rc = create_keyframe(od, ns);
+      if (rc) return rc;
+      res->keyframe = 1;
+    }
+    od->prev_pose = od->pose;
+  }
+  pose_to_T16(od->pose, res->pose);
+  res->l0 = map->n0; res->l1 = map->n1;
+  return B2LO_OK;
+}
+
+static int process_timed(b2lo_odom* od, const float* src_dev, size_t ns, size_t sstride, b2lo_odom_result* res, bool ev0_recorded) {
+  b2lo_ctx* ctx = od->ctx;
+  if (!ev0_recorded) B2_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  int rc = process_common(od, src_dev, ns, sstride, res);
+  if (rc < 0) return rc;
+  B2_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  B2_CUDA(cudaEventSynchronize(ctx->ev1));
+  cudaEventElapsedTime(&res->device_ms, ctx->ev0, ctx->ev1);
+  return rc;
+}
+
+extern "C" int b2lo_odom_process(b2lo_odom* od, const float* xyz, size_t n, size_t stride_floats, b2lo_odom_result* res) {
+  if (!od || !res) return B2LO_E_ARG;
+  if (stride_floats < 3) return B2LO_E_ARG;
+  if (!xyz || n == 0) { std::memset(res, 0, sizeof *res); return B2LO_S_EMPTY; }
+  b2lo_ctx* ctx = od->ctx;
+  std::lock_guard<std::recursive_mutex> lk(od->map->mu);
+  std::lock_guard<std::mutex> lk2(ctx->mu);
+  cudaSetDevice(ctx->device);
+  const size_t S = (size_t)(od->cfg.point_stride < 1 ? 1 : od->cfg.point_stride);
+  const size_t ns = (n + S - 1) / S;
+  B2_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  // only every S-th point is ever read by the filter (VoxelMap.h:81): gather those into pinned memory, one H2D
+  int rc = ctx_stage_h2d(ctx, xyz, n, stride_floats, S, nullptr, nullptr);
+  if (rc) return rc;
+  return process_timed(od, ctx->d_stage, ns, 3, res, true);
+}
+
+extern "C" int b2lo_odom_process_dev(b2lo_odom* od, const float* xyz_dev, size_t n, size_t stride_floats, b2lo_odom_result* res) {
+  if (!od || !res) return B2LO_E_ARG;
+  if (stride_floats < 3) return B2LO_E_ARG;
+  if (!xyz_dev || n == 0) { std::memset(res, 0, sizeof *res); return B2LO_S_EMPTY; }
+  b2lo_ctx* ctx = od->ctx;
+  std::lock_guard<std::recursive_mutex> lk(od->map->mu);
+  std::lock_guard<std::mutex> lk2(ctx->mu);
+  cudaSetDevice(ctx->device);
+  const size_t S = (size_t)(od->cfg.point_stride < 1 ? 1 : od->cfg.point_stride);
+  const size_t ns = (n + S - 1) / S;
+  return process_timed(od, xyz_dev, ns, stride_floats * S, res, false);
+}
+
+extern "C" int b2lo_odom_reset(b2lo_odom* od) {
+  if (!od) return B2LO_E_ARG;
+  int rc = b2lo_map_clear(od->map);
+  od->pose = od->prev_pose = od->velocity = od->last_kf_pose = pose_identity();
+  od->initialized = false;
+  od->n_keyframes = 0;
+  return rc;
+}

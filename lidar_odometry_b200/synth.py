@@ -71,6 +71,54 @@ class Scene:
         return t
 
 
+def _cast_torch(scene, o, d, max_range, device):
+    """Same ray casting as Scene.cast, evaluated with torch (float64) on `device` - used by bench.py to build
+    full-size sequences quickly.  Plumbing for synthetic data only; not part of the registration path."""
+    import torch
+    dt = torch.float64
+    d_t = torch.as_tensor(d, dtype=dt, device=device)
+    o_t = torch.as_tensor(np.asarray(o, np.float64), dtype=dt, device=device)
+    inf = torch.tensor(float("inf"), dtype=dt, device=device)
+    n = d_t.shape[0]
+    t = torch.full((n,), float("inf"), dtype=dt, device=device)
+    inv = 1.0 / d_t
+    if scene.ground_z is not None:
+        tg = (scene.ground_z - o_t[2]) * inv[:, 2]
+        tg = torch.where(tg > 1e-6, tg, inf)
+        t = torch.minimum(t, tg)
+    if scene.room is not None:
+        lo = torch.as_tensor(scene.room[:3], dtype=dt, device=device); hi = torch.as_tensor(scene.room[3:], dtype=dt, device=device)
+        t1 = (lo - o_t) * inv; t2 = (hi - o_t) * inv
+        tfar = torch.maximum(t1, t2).min(dim=1).values
+        tfar = torch.where(tfar > 1e-6, tfar, inf)
+        t = torch.minimum(t, tfar)
+    if len(scene.boxes):
+        c = 0.5 * (scene.boxes[:, :3] + scene.boxes[:, 3:])
+        rad = 0.5 * np.linalg.norm(scene.boxes[:, 3:] - scene.boxes[:, :3], axis=1)
+        near = np.linalg.norm(c - np.asarray(o), axis=1) - rad < max_range
+        for b in scene.boxes[near]:
+            bt = torch.as_tensor(b, dtype=dt, device=device)
+            t1 = (bt[:3] - o_t) * inv; t2 = (bt[3:] - o_t) * inv
+            tn = torch.minimum(t1, t2).max(dim=1).values
+            tf = torch.maximum(t1, t2).min(dim=1).values
+            hit = (tn <= tf) & (tn > 1e-6) & (tn < t)
+            t = torch.where(hit, tn, t)
+    for cx, cy, r, z0, z1 in scene.cylinders:
+        if np.hypot(cx - o[0], cy - o[1]) - r > max_range:
+            continue
+        ox, oy = float(o[0] - cx), float(o[1] - cy)
+        a = d_t[:, 0] ** 2 + d_t[:, 1] ** 2
+        bq = 2.0 * (ox * d_t[:, 0] + oy * d_t[:, 1])
+        cq = ox * ox + oy * oy - r * r
+        disc = bq * bq - 4 * a * cq
+        ok = (disc > 0) & (a > 1e-12)
+        tc = (-bq - torch.sqrt(torch.where(ok, disc, torch.zeros_like(disc)))) / (2 * torch.where(ok, a, torch.ones_like(a)))
+        z = o_t[2] + tc * d_t[:, 2]
+        hit = ok & (tc > 1e-6) & (z >= z0) & (z <= z1) & (tc < t)
+        t = torch.where(hit, tc, t)
+    return t.cpu().numpy()
+
+
 def pose_matrix(x, y, z, yaw, pitch=0.0, roll=0.0):
     cy, sy, cp, sp, cr, sr = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch), np.cos(roll), np.sin(roll)
     Rz = np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1]])
@@ -135,10 +183,10 @@ def kitti_trajectory(n_scans, step=1.2, seed=42):
     return poses
 
 
-def _scan(scene, T, dirs_local, max_range, sigma, rng, dropout=0.0):
+def _scan(scene, T, dirs_local, max_range, sigma, rng, dropout=0.0, device=None):
     o = T[:3, 3]
     d = dirs_local @ T[:3, :3].T
-    t = scene.cast(o, d, max_range)
+    t = scene.cast(o, d, max_range) if device is None else _cast_torch(scene, o, d, max_range, device)
     keep = np.isfinite(t) & (t < max_range) & (t > 0.5)
     if dropout > 0:
         keep &= rng.uniform(size=t.shape) >= dropout
@@ -150,13 +198,13 @@ def _scan(scene, T, dirs_local, max_range, sigma, rng, dropout=0.0):
     return out
 
 
-def kitti_sequence(n_scans=100, seed=42, n_rings=64, n_az=1900, max_range=100.0, sigma=0.02):
+def kitti_sequence(n_scans=100, seed=42, n_rings=64, n_az=1900, max_range=100.0, sigma=0.02, device=None):
     """Returns (list of (N_i,4) float32 xyzI scans in the sensor frame, list of 4x4 ground-truth poses)."""
     scene = kitti_scene(seed)
     dirs = _hdl64_dirs(n_rings, n_az)
     poses = kitti_trajectory(n_scans, seed=seed)
     rng = np.random.default_rng(seed + 7)
-    scans = [_scan(scene, T, dirs, max_range, sigma, rng, dropout=0.01) for T in poses]
+    scans = [_scan(scene, T, dirs, max_range, sigma, rng, dropout=0.01, device=device) for T in poses]
     return scans, poses
 
 
@@ -191,7 +239,7 @@ def _mid360_dirs(n, k, seed):
     return np.stack([ce * np.cos(az), ce * np.sin(az), se], axis=-1)
 
 
-def mid360_sequence(n_scans=100, seed=42, n_pts=20000, max_range=40.0, sigma=0.01):
+def mid360_sequence(n_scans=100, seed=42, n_pts=20000, max_range=40.0, sigma=0.01, device=None):
     scene = mid360_scene(seed)
     rng = np.random.default_rng(seed + 7)
     scans, poses = [], []
@@ -201,6 +249,6 @@ def mid360_sequence(n_scans=100, seed=42, n_pts=20000, max_range=40.0, sigma=0.0
         # ~0.1 m / scan along a slow arc
         T[:3, 3] = (0.1 * k * np.cos(0.2 * ang), 0.1 * k * np.sin(0.2 * ang) * 0.3, 0.0)
         dirs = _mid360_dirs(n_pts, k, seed)
-        scans.append(_scan(scene, T, dirs, max_range, sigma, rng))
+        scans.append(_scan(scene, T, dirs, max_range, sigma, rng, device=device))
         poses.append(T)
     return scans, poses

@@ -92,6 +92,9 @@ void orc_se3_mul(const float* A16, const float* B16, float* C16);
 void orc_se3_inv(const float* A16, float* C16);
 void orc_fit_plane(const float* cents, int n, float* mu, float* normal, float* planarity);
 
+/* container semantics probe: iteration order of the restated dense map under (op, key) pairs, op 0 = operator[], 1 = erase */
+size_t orc_dense_order(const int64_t* ops, size_t n_ops, uint64_t* out_keys);
+
 /* pipeline (Estimator-lite) */
 void* orc_pipe_create(const orc_pipe_cfg* cfg);
 void orc_pipe_destroy(void* h);

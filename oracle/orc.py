@@ -344,6 +344,15 @@ class Pipeline:
         return out
 
 
+def dense_order(ops):
+    """Iteration order of the oracle's restated dense map under (op, key) pairs (op 0 = operator[], 1 = erase)."""
+    ops = np.ascontiguousarray(ops, np.int64)
+    out = np.zeros(len(ops) + 1, np.uint64)
+    lib().orc_dense_order.restype = C.c_size_t
+    n = lib().orc_dense_order(_p(ops), C.c_size_t(len(ops)), _p(out))
+    return out[:n].copy()
+
+
 # ---- the REAL reference pieces (oracle/_ref) -------------------------------------------------------
 def ref_pko_available():
     return os.path.exists(REF_PKO)

@@ -275,4 +275,18 @@ size_t orc_pipe_features(void* h, float* xyz, size_t cap) {
   return p->feature_cloud.size();
 }
 
+// ops: (op, key) pairs; op 0 = operator[] (insert if absent), 1 = erase.  Iteration order of the restated DenseMap
+// (pinned against the real ankerl::unordered_dense in tests/test_oracle_pins.py)
+size_t orc_dense_order(const int64_t* ops, size_t n_ops, uint64_t* out_keys) {
+  struct H { uint64_t operator()(uint64_t k) const { return k; } };
+  orc::DenseMap<uint64_t, int, H> m;
+  for (size_t i = 0; i < n_ops; ++i) {
+    uint64_t k = (uint64_t)ops[i * 2 + 1];
+    if (ops[i * 2] == 0) m[k] += 1; else m.erase(k);
+  }
+  size_t j = 0;
+  for (const auto& kv : m.values) out_keys[j++] = kv.first;
+  return j;
+}
+
 }  // extern "C"

@@ -1,0 +1,390 @@
+"""GPU parity: the CUDA path (through the C ABI, via lidar_odometry_b200.api) against the CPU oracle on the same
+seeded inputs.  Integer / key / index / order work must be bit-exact; f32 results that depend only on exact
+inputs are compared bit-for-bit too; Hessian/gradient within 1e-5 relative; poses within 1e-6 m / 1e-6 rad per
+teacher-forced iteration (BASELINE.json north_star tolerances)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view(np.uint32) if a.dtype == np.float32 else a.view(np.uint64)
+
+
+def T32(T):
+    return np.asarray(T, np.float64).astype(np.float32)
+
+
+def world_cloud(orc, feat, T):
+    """transform_point_cloud with the oracle's arithmetic (PointCloudUtils.cpp:102-125)."""
+    T = T32(T)
+    x, y, z = feat[:, 0], feat[:, 1], feat[:, 2]
+    out = np.empty_like(feat)
+    for r in range(3):
+        out[:, r] = ((T[r, 0] * x + T[r, 1] * y) + T[r, 2] * z) + T[r, 3] * np.float32(1.0)
+    return out
+
+
+def l1_dict(d):
+    out = {}
+    for i in range(len(d["keys"])):
+        k = tuple(int(v) for v in d["keys"][i])
+        nc = int(d["nchild"][i])
+        out[k] = dict(nchild=nc, children=[tuple(int(v) for v in c) for c in d["children"][i][:nc]], has=int(d["has_surfel"][i]),
+                      normal=bits(d["normal"][i]).tolist(), centroid=bits(d["centroid"][i]).tolist(),
+                      planarity=int(bits(d["planarity"][i:i + 1])[0]), last=int(d["last_child_count"][i]))
+    return out
+
+
+def assert_maps_equal(omap, gmap, tag=""):
+    ok, oc, on = omap.export_l0()
+    gc, gk, gn = gmap.export_l0()
+    assert len(ok) == len(gk), f"{tag}: L0 count oracle {len(ok)} vs gpu {len(gk)}"
+    assert np.array_equal(ok, gk), f"{tag}: L0 dense-order keys differ at {np.nonzero((ok != gk).any(axis=1))[0][:5]}"
+    assert np.array_equal(on, gn), f"{tag}: L0 point counts differ"
+    assert np.array_equal(bits(oc), bits(gc)), f"{tag}: L0 centroid bits differ at {np.nonzero((bits(oc) != bits(gc)).any(axis=1))[0][:5]}"
+    o1, g1 = l1_dict(omap.export_l1()), l1_dict(gmap.export_l1())
+    assert set(o1) == set(g1), f"{tag}: L1 key sets differ: only-oracle {list(set(o1) - set(g1))[:3]} only-gpu {list(set(g1) - set(o1))[:3]}"
+    for k in o1:
+        a, b = o1[k], g1[k]
+        assert a["nchild"] == b["nchild"] and a["children"] == b["children"], f"{tag}: L1 {k} child set/order differs\n{a}\n{b}"
+        assert a["has"] == b["has"], f"{tag}: L1 {k} has_surfel differs {a} {b}"
+        assert a["last"] == b["last"], f"{tag}: L1 {k} last_child_count {a['last']} vs {b['last']}"
+        if a["has"]:
+            assert a["normal"] == b["normal"] and a["centroid"] == b["centroid"] and a["planarity"] == b["planarity"], f"{tag}: L1 {k} surfel bits differ"
+
+
+# ---- K1 ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("stride,voxel", [(8, 0.5), (1, 0.5), (4, 0.4), (3, 0.25)])
+def test_filter_bit_exact(orc, b2, small_kitti, stride, voxel):
+    scans, _ = small_kitti
+    f = b2.FastVoxelFilter(voxel)
+    for s in scans[:2]:
+        ref, rkeys = orc.voxel_filter(s[:, :3], stride, voxel)
+        got = f.filter(s, stride, want_keys=True)   # xyzI input, stride_floats = 4
+        assert f.getVoxelCount() == len(ref)
+        assert np.array_equal(rkeys, f.last_keys)
+        assert np.array_equal(bits(ref), bits(got))
+        got3 = f.filter(np.ascontiguousarray(s[:, :3]), stride)  # packed xyz input
+        assert np.array_equal(bits(ref), bits(got3))
+
+
+def test_filter_edge_cases(orc, b2):
+    f = b2.FastVoxelFilter(0.5)
+    assert f.filter(np.zeros((0, 3), np.float32)).shape == (0, 3) and f.getVoxelCount() == 0
+    rng = np.random.default_rng(3)
+    pts = (rng.standard_normal((5000, 3)) * 20).astype(np.float32)
+    pts[7] = [np.nan, 1, 2]; pts[100] = [1, np.inf, 2]; pts[200] = [1, 2, -np.inf]       # skipped (VoxelMap.h:83)
+    pts[300] = [3e9, -3e9, 1e30]; pts[301] = [2e6, 0, 0]; pts[302] = [-2e6, 5, 5]          # clamp to the 21-bit range (:127-131)
+    pts[400:600] = pts[400] + (rng.uniform(0, 1e-3, (200, 3))).astype(np.float32)          # many points in one voxel: sequential f32 sum
+    ref, rk = orc.voxel_filter(pts, 1, 0.5)
+    got = f.filter(pts, 1, want_keys=True)
+    assert np.array_equal(rk, f.last_keys) and np.array_equal(bits(ref), bits(got))
+    one = np.tile(np.array([[0.1, 0.2, 0.3]], np.float32), (3000, 1))
+    ref, _ = orc.voxel_filter(one, 1, 0.5)
+    assert np.array_equal(bits(ref), bits(f.filter(one, 1)))
+    with pytest.raises(Exception):
+        b2.FastVoxelFilter(-1.0).filter(pts, 1)
+
+
+# ---- K6 / K7 ------------------------------------------------------------------------------------------------------
+def _keyframes(orc, scans, poses, stride=8, voxel=0.5):
+    out = []
+    for s, T in zip(scans, poses):
+        feat, _ = orc.voxel_filter(s[:, :3], stride, voxel)
+        out.append((feat, world_cloud(orc, feat, T), T32(T)[:3, 3].astype(np.float64)))
+    return out
+
+
+def test_map_update_sequence_bit_exact(orc, b2, small_kitti):
+    scans, poses = small_kitti
+    omap = orc.VoxelMap(0.5, 3, 0.1, True)
+    gmap = b2.VoxelMap(0.5)
+    gmap.SetPlanarityThreshold(0.1)
+    purged = culled = 0
+    for i, (feat, world, sensor) in enumerate(_keyframes(orc, scans, poses)):
+        before = omap.counts()[0]
+        radius = 25.0 if i >= 3 else 120.0  # small radius on later keyframes forces the cull path
+        omap.update(world, sensor, radius)
+        gmap.UpdateVoxelMap(world, sensor, radius, True)
+        assert_maps_equal(omap, gmap, f"keyframe {i}")
+        assert gmap.GetSurfelCount() == omap.counts()[2]
+        if i >= 3 and omap.counts()[0] < before:
+            culled += 1
+    assert culled > 0, "test did not exercise the radius cull"
+    # lookups at every L0 centroid
+    cent = omap.export_l0()[1]
+    for p in cent[:: max(1, len(cent) // 50)]:
+        fo, no, co = omap.lookup(p)
+        fg, ng, cg = gmap.GetSurfelAtPoint(p)
+        assert fo == fg
+        if fo:
+            assert np.array_equal(bits(no), bits(ng)) and np.array_equal(bits(co), bits(cg))
+
+
+def test_map_purge_path(orc, b2):
+    """Non-planar parents are purged with all their children (VoxelMap.cpp:244-253); the dense L0 order after the
+    swap-erases must still match."""
+    rng = np.random.default_rng(5)
+    omap = orc.VoxelMap(0.5, 3, 0.1, True)
+    gmap = b2.VoxelMap(0.5)
+    n_before = 0
+    for k in range(4):
+        plane = np.c_[rng.uniform(-20, 20, (4000, 2)), rng.normal(0, 0.01, 4000)]
+        blob = rng.uniform(-1, 1, (3000, 3)) * [15, 15, 3] + [0, 0, 5 + k]   # volumetric clutter -> non-planar L1 cells
+        cloud = np.r_[plane, blob].astype(np.float32)
+        rng.shuffle(cloud)
+        omap.update(cloud, [0, 0, 0], 120.0)
+        gmap.UpdateVoxelMap(cloud, [0, 0, 0], 120.0)
+        assert_maps_equal(omap, gmap, f"purge step {k}")
+        n_before += len(cloud)
+    l0, l1, ns = omap.counts()
+    assert ns > 0 and l1 > 0
+
+
+def test_map_edge_cases(orc, b2):
+    gmap = b2.VoxelMap(0.5)
+    assert gmap.empty() and gmap.GetVoxelCount() == 0 and gmap.GetL1VoxelCount() == 0 and gmap.GetSurfelCount() == 0
+    gmap.UpdateVoxelMap(np.zeros((0, 3), np.float32), [0, 0, 0], 10.0)
+    assert gmap.empty()
+    found, _, _ = gmap.GetSurfelAtPoint([0, 0, 0])
+    assert not found
+    with pytest.raises(ValueError):
+        gmap.SetVoxelSize(0.0)
+    omap = orc.VoxelMap(0.5, 3, 0.1, True)
+    # negative coordinates: floor-division parents (VoxelMap.cpp:60-67) vs float-division lookup key (:50-58)
+    rng = np.random.default_rng(9)
+    cloud = (rng.uniform(-6, 6, (6000, 3)) * [1, 1, 0.02]).astype(np.float32)
+    omap.update(cloud, [0, 0, 0], 50.0)
+    gmap.UpdateVoxelMap(cloud, [0, 0, 0], 50.0)
+    assert_maps_equal(omap, gmap, "negative coords")
+    # everything culled, then refilled in the same update
+    far = cloud + np.float32(500.0)
+    omap.update(far, [500, 500, 500], 5.0)
+    gmap.UpdateVoxelMap(far, [500, 500, 500], 5.0)
+    assert_maps_equal(omap, gmap, "cull all + refill")
+    gmap.Clear(); omap.clear()
+    assert gmap.empty()
+    omap.update(cloud, [0, 0, 0], 50.0); gmap.UpdateVoxelMap(cloud, [0, 0, 0], 50.0)
+    assert_maps_equal(omap, gmap, "after clear")
+    gmap.SetVoxelSize(0.4)  # clears on change
+    assert gmap.empty()
+
+
+def test_map_transform_rehash(orc, b2, small_kitti):
+    scans, poses = small_kitti
+    omap = orc.VoxelMap(0.5, 3, 0.1, True)
+    gmap = b2.VoxelMap(0.5)
+    for feat, world, sensor in _keyframes(orc, scans[:3], poses[:3]):
+        omap.update(world, sensor, 120.0); gmap.UpdateVoxelMap(world, sensor, 120.0)
+    from lidar_odometry_b200 import synth
+    T = T32(synth.pose_matrix(0.31, -0.22, 0.05, 0.02, 0.003, -0.004))
+    omap.transform_rehash(T); gmap.ApplyTransformAndRehash(T)
+    assert_maps_equal(omap, gmap, "rehash")
+
+
+# ---- K2 ---------------------------------------------------------------------------------------------------------
+def _built_maps(orc, b2, scans, poses, n=3):
+    omap = orc.VoxelMap(0.5, 3, 0.1, True)
+    gmap = b2.VoxelMap(0.5)
+    kfs = _keyframes(orc, scans, poses)
+    for feat, world, sensor in kfs[:n]:
+        omap.update(world, sensor, 120.0); gmap.UpdateVoxelMap(world, sensor, 120.0)
+    return omap, gmap, kfs
+
+
+def test_correspondences_bit_exact(orc, b2, small_kitti):
+    scans, poses = small_kitti
+    omap, gmap, kfs = _built_maps(orc, b2, scans, poses)
+    icp = b2.IterativeClosestPointOptimizer(b2.ICPConfig())
+    for k in (2, 3, 4):
+        feat = kfs[k][0]
+        for T in (T32(poses[k]), T32(poses[k - 1])):
+            ref = orc.icp_correspondences(omap, feat, T, 1.0)
+            got = icp.find_correspondences(gmap, feat, T)
+            assert np.array_equal(ref["l1key"], got["l1key"])
+            assert np.array_equal(ref["morton"], got["morton"])
+            assert np.array_equal(ref["state"], got["state"]) and ref["n_accepted"] == got["n_accepted"]
+            hit = ref["state"] > 0
+            assert np.array_equal(bits(ref["normal"][hit]), bits(got["normal"][hit]))
+            assert np.array_equal(bits(ref["centroid"][hit]), bits(got["centroid"][hit]))
+            assert np.array_equal(bits(ref["residual"][hit]), bits(got["residual"][hit]))
+            assert ref["n_accepted"] > 100
+
+
+# ---- K4 / K5 ------------------------------------------------------------------------------------------------------
+def _rel(a, b):
+    return np.linalg.norm(np.asarray(a, np.float64) - np.asarray(b, np.float64)) / max(np.linalg.norm(np.asarray(b, np.float64)), 1e-300)
+
+
+def _rot_angle(Ra, Rb):
+    c = (np.trace(Ra.astype(np.float64).T @ Rb.astype(np.float64)) - 1) / 2
+    return float(np.arccos(np.clip(c, -1, 1)))
+
+
+def test_icp_teacher_forced_iterations(orc, b2, small_kitti):
+    scans, poses = small_kitti
+    omap, gmap, kfs = _built_maps(orc, b2, scans, poses)
+    ame = b2.AdaptiveMEstimator()
+    icp = b2.IterativeClosestPointOptimizer(b2.ICPConfig(), ame)
+    checked = flips = 0
+    for k in (3, 4, 5):
+        feat = kfs[k][0]
+        init = T32(poses[k - 1])  # a realistic ~1.2 m off initial guess
+        ok_o, T_o, tr_o = orc.icp_optimize(omap, feat, init)
+        ok_g, T_g = icp.optimize(gmap, feat, init)
+        tr_g = icp.get_last_stats().iterations
+        assert ok_o == ok_g and len(tr_o) == len(tr_g) == icp.get_last_stats().num_iterations
+        for it, (a, b) in enumerate(zip(tr_o, tr_g)):
+            same_in = np.array_equal(bits(a["T_in"]), bits(b["T_in"]))
+            if it == 0:
+                assert same_in
+            if not same_in:
+                continue  # later iterations are only comparable when the incoming pose is identical
+            checked += 1
+            assert a["n_corr"] == b["n_corr"]
+            assert abs(a["scale"] - b["scale"]) <= 1e-12 * abs(a["scale"])
+            if a["delta"] != b["delta"]:
+                flips += 1
+                continue
+            assert a["em_iters"] == b["em_iters"] and a["kmeans_iters"] == b["kmeans_iters"]
+            assert _rel(b["H"], a["H64"]) < 1e-5 and _rel(b["g"], a["g64"]) < 1e-5   # Hessian / gradient within 1e-5 relative
+            assert _rel(b["H"], a["H"]) < 1e-5 and _rel(b["g"], a["g"]) < 1e-5       # also vs the faithful sequential-f32 sums
+            assert np.linalg.norm(a["T_out"][:3, 3].astype(np.float64) - b["T_out"][:3, 3]) < 1e-6
+            assert _rot_angle(a["T_out"][:3, :3], b["T_out"][:3, :3]) < 1e-6
+        assert np.linalg.norm(T_o[:3, 3].astype(np.float64) - T_g[:3, 3]) < 1e-4
+    assert checked >= 3
+    assert flips == 0, f"PKO alpha differs from the oracle in {flips} teacher-forced iterations"
+
+
+def test_icp_variants_and_failure(orc, b2, small_kitti):
+    scans, poses = small_kitti
+    omap, gmap, kfs = _built_maps(orc, b2, scans, poses)
+    feat = kfs[3][0]
+    init = T32(poses[2])
+    # no adaptive estimator: fixed Huber delta (ICP.cpp:319)
+    cfg_o = orc.default_icp_cfg(); cfg_o.use_adaptive_m_estimator = 0
+    ok_o, T_o, tr_o = orc.icp_optimize(omap, feat, init, cfg_o)
+    icp = b2.IterativeClosestPointOptimizer(b2.ICPConfig(), None)
+    ok_g, T_g = icp.optimize(gmap, feat, init)
+    tr_g = icp.get_last_stats().iterations
+    assert ok_o and ok_g and tr_o[0]["n_corr"] == tr_g[0]["n_corr"] and tr_g[0]["delta"] == 0.1
+    assert _rel(tr_g[0]["H"], tr_o[0]["H64"]) < 1e-5
+    # cauchy GN weights
+    cfg_o = orc.default_icp_cfg(); cfg_o.loss_type = 1
+    ok_o, T_o, tr_o = orc.icp_optimize(omap, feat, init, cfg_o)
+    icp = b2.IterativeClosestPointOptimizer(b2.ICPConfig(), b2.AdaptiveMEstimator(b2.AdaptiveMEstimatorConfig(loss_type="cauchy")))
+    ok_g, T_g = icp.optimize(gmap, feat, init)
+    tr_g = icp.get_last_stats().iterations
+    assert tr_o[0]["delta"] == tr_g[0]["delta"] and _rel(tr_g[0]["H"], tr_o[0]["H64"]) < 1e-5
+    # too few correspondences -> false, output = initial (ICP.cpp:298-302)
+    far = init.copy(); far[:3, 3] += np.float32(900.0)
+    ok_o, T_o, _ = orc.icp_optimize(omap, feat, far)
+    ok_g, T_g = b2.IterativeClosestPointOptimizer(b2.ICPConfig(), b2.AdaptiveMEstimator()).optimize(gmap, feat, far)
+    assert not ok_o and not ok_g and np.array_equal(bits(T_g), bits(far))
+    # empty map / empty cloud
+    empty = b2.VoxelMap(0.5)
+    ok_g, T_g = icp.optimize(empty, feat, init)
+    assert not ok_g and np.array_equal(bits(T_g), bits(init))
+    ok_g, T_g = icp.optimize(gmap, np.zeros((0, 3), np.float32), init)
+    assert not ok_g
+
+
+# ---- K3 ---------------------------------------------------------------------------------------------------------
+def test_knn_mode_parity(orc, b2, small_mid360):
+    scans, poses = small_mid360
+    omap = orc.VoxelMap(0.4, 3, 0.1, False)
+    gmap = b2.VoxelMap(0.4)
+    gmap.SetComputeSurfels(False)
+    kfs = _keyframes(orc, scans, poses, stride=4, voxel=0.4)
+    for feat, world, sensor in kfs[:3]:
+        omap.update(world, sensor, 120.0); gmap.UpdateVoxelMap(world, sensor, 120.0)
+    gmap.RebuildKdTree()
+    assert gmap.HasKdTree()
+    assert_maps_equal(omap, gmap, "knn map")
+    cloud = omap.export_l0()[1]
+    icp = b2.IterativeClosestPointOptimizer(b2.ICPConfig(use_surfel_correspondence=False), b2.AdaptiveMEstimator())
+    feat = kfs[3][0]
+    # queries far from the map as well (exact full scan path)
+    extra = feat[:50] * np.float32(3.0) + np.float32(40.0)
+    q = np.r_[feat, extra].astype(np.float32)
+    for T in (T32(poses[3]), T32(poses[2])):
+        ref = orc.kdtree_correspondences(cloud, q, T, 1.0)
+        got = icp.find_correspondences_kdtree(gmap, q, T)
+        assert got["n_scanned"] >= 50
+        # distance ties are the only legitimate source of index differences
+        diff = (ref["knn"] != got["knn"]).any(axis=1)
+        world = world_cloud(orc, q, T)
+        for i in np.nonzero(diff)[0]:
+            d_ref = np.sort(((world[i] - cloud[ref["knn"][i]]) ** 2).sum(axis=1))
+            assert np.allclose(d_ref, np.sort(got["d2"][i]), rtol=1e-6), f"query {i}: knn sets differ beyond ties"
+        assert diff.sum() <= 2
+        same = ~diff
+        assert np.array_equal(ref["state"][same], got["state"][same])
+        acc = same & (ref["state"] > 0)
+        assert np.array_equal(bits(ref["residual"][acc]), bits(got["residual"][acc]))
+        assert np.array_equal(bits(ref["centroid"][acc]), bits(got["centroid"][acc]))
+        assert np.array_equal(bits(ref["normal"][acc]), bits(got["normal"][acc]))
+    # full optimize in KDTree mode
+    cfg_o = orc.default_icp_cfg(); cfg_o.use_surfel_correspondence = 0
+    init = T32(poses[2])
+    ok_o, T_o, tr_o = orc.icp_optimize_kdtree(cloud, feat, init, cfg_o)
+    ok_g, T_g = icp.optimize(gmap, feat, init)
+    tr_g = icp.get_last_stats().iterations
+    assert ok_o and ok_g
+    assert tr_o[0]["n_corr"] == tr_g[0]["n_corr"] and tr_o[0]["delta"] == tr_g[0]["delta"]
+    assert _rel(tr_g[0]["H"], tr_o[0]["H64"]) < 1e-5 and _rel(tr_g[0]["g"], tr_o[0]["g64"]) < 1e-5
+    assert np.linalg.norm(T_o[:3, 3].astype(np.float64) - T_g[:3, 3]) < 1e-4
+
+
+# ---- whole pipeline -----------------------------------------------------------------------------------------------
+def _run_sequences(orc, b2, scans, mid360):
+    pipe = orc.Pipeline(orc.default_pipe_cfg(mid360))
+    odo = b2.Odometry(mid360=mid360)
+    rows = []
+    for k, s in enumerate(scans):
+        a = pipe.process(s)
+        b = odo.process(s)
+        rows.append((a, b))
+    return pipe, odo, rows
+
+
+def test_odometry_sequence_kitti(orc, b2, small_kitti):
+    scans, poses = small_kitti
+    pipe, odo, rows = _run_sequences(orc, b2, scans, False)
+    path = 0.0
+    for k, (a, b) in enumerate(rows):
+        assert a["ok"] == b["ok"] and a["n_features"] == b["n_features"], f"scan {k}"
+        assert a["keyframe"] == b["keyframe"] and a["icp_ok"] == b["icp_ok"], f"scan {k}"
+        err = np.linalg.norm(a["pose"][:3, 3].astype(np.float64) - b["pose"][:3, 3])
+        if k:
+            path += np.linalg.norm(rows[k][0]["pose"][:3, 3] - rows[k - 1][0]["pose"][:3, 3])
+        assert err <= max(1e-3 * path, 1e-5), f"scan {k}: drift {err} m after {path} m"   # 0.1 % of the path length
+        assert _rot_angle(a["pose"][:3, :3], b["pose"][:3, :3]) < 1e-4
+    # feature cloud of the last scan stayed on the device and is bit-identical
+    assert np.array_equal(bits(pipe.features()), bits(odo.ctx.features()))
+    l0o, l1o, _ = pipe.map().counts()
+    assert abs(l0o - rows[-1][1]["l0"]) <= max(3, l0o // 500)
+
+
+def test_odometry_sequence_mid360(orc, b2, small_mid360):
+    scans, poses = small_mid360
+    pipe, odo, rows = _run_sequences(orc, b2, scans, True)
+    for k, (a, b) in enumerate(rows):
+        assert a["ok"] == b["ok"] and a["n_features"] == b["n_features"] and a["keyframe"] == b["keyframe"] and a["icp_ok"] == b["icp_ok"], f"scan {k}"
+        assert np.linalg.norm(a["pose"][:3, 3].astype(np.float64) - b["pose"][:3, 3]) < 1e-3, f"scan {k}"
+
+
+def test_device_resident_scan_matches_host_scan(b2, small_kitti):
+    import torch
+    scans, _ = small_kitti
+    a, b = b2.Odometry(), b2.Odometry()
+    for s in scans[:4]:
+        ra = a.process(s)
+        t = torch.from_numpy(np.ascontiguousarray(s)).cuda()
+        torch.cuda.synchronize()
+        rb = b.process_dev(t.data_ptr(), s.shape[0], s.shape[1])
+        assert np.array_equal(bits(ra["pose"]), bits(rb["pose"])) and ra["n_features"] == rb["n_features"] and ra["n_corr"] == rb["n_corr"]
+    assert a.ctx.launch_count > 0
