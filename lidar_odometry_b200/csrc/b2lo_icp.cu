@@ -258,23 +258,46 @@ __device__ int shuffled_head(const PkoTables* T, const int* hits, int n, int j) 
   return pos;
 }
 
-// One CTA.  Every floating-point SUM of the reference's fit_gmm is a sequential left-to-right loop over the
-// (<=128) samples; those loops are replayed here by single lanes in the same order, so k-means, the EM
-// fixed point and its iteration count agree with the CPU path bit for bit (up to libm exp/log rounding).
-// The embarrassingly parallel parts (sample gather, cluster assignment, responsibilities) use one thread
-// per sample.
+// Block-wide sum of V doubles at once: warp shuffles, one shared-memory exchange, ONE barrier (double-buffered).
+// Every thread receives the totals, accumulated in a fixed order (deterministic run to run).
+template <int V>
+__device__ __forceinline__ void block_sum_multi(double (&v)[V], double (*buf)[8][8], int& phase) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) buf[phase][w][i] = v[i];
+  }
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    double acc = buf[phase][0][i];
+    for (int ww = 1; ww < nw; ++ww) acc += buf[phase][ww][i];
+    v[i] = acc;
+  }
+  phase ^= 1;
+}
+
+// One CTA: accepted-count scan, the C < min test, the iteration-0 residual scale, the libstdc++-exact sample draw,
+// k-means and the 3-component EM of AdaptiveMEstimator::fit_gmm (AdaptiveMEstimator.cpp:294-485) with one thread per
+// sample and block-tree sums (the reference sums left to right; the two orders agree to ~1e-16 relative, which moves
+// the discrete outputs - iteration counts, arg-min alpha - only on exact ties; tests/ assert they match the oracle).
 __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict__ d_npts, IcpState* st, IcpParams prm, const double* __restrict__ res,
                                                            const int* __restrict__ slot, const int* __restrict__ cidx, const int* __restrict__ tilecnt,
                                                            int* tileoff, const PkoTables* __restrict__ T, const int* __restrict__ hits, double* gmm_out) {
   if (st->done) return;
   __shared__ int sm[40];
   __shared__ double smd[40];
+  __shared__ double s_buf[2][8][8];
   __shared__ double s_x[MAXS];
-  __shared__ double s_r[3][MAXS];
-  __shared__ int s_cl[MAXS];
-  __shared__ double s_mean[3], s_var[3], s_w[3], s_sum[8];
-  __shared__ int s_cnt[3];
+  __shared__ double s_mean[3], s_var[3], s_w[3], s_norm[3];
   __shared__ int s_flag;
+  int phase = 0;
   const int tid = threadIdx.x;
   const int npts = *d_npts;
   const int ntiles = (npts + TILE - 1) / TILE;
@@ -310,99 +333,83 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
   const double sdiv = fmax(scale, 1e-6);
   // 3. the sample: residuals[idx[0..ns)] of the shuffled index vector (AdaptiveMEstimator.cpp:319-331)
   const int ns = T->sample_size < C ? T->sample_size : C;
-  if (tid < ns) {
+  const bool act = tid < ns;
+  double x = 0.0;
+  if (act) {
     int ci = shuffled_head(T, hits, C, tid);
     int lo = 0, hi = ntiles - 1;  // last tile with tileoff <= ci
     while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (tileoff[mid] <= ci) lo = mid; else hi = mid - 1; }
     int q = cidx[lo * TILE + (ci - tileoff[lo])];
-    s_x[tid] = res[q] / sdiv;
+    x = res[q] / sdiv;
+    s_x[tid] = x;
   }
   __syncthreads();
   // 4. k-means (:336-389): mean0 = 0, mean1/2 = sample[dis(gen)]
-  if (tid == 0) { s_mean[0] = 0.0; s_mean[1] = s_x[T->kmeans_seed[ns][0]]; s_mean[2] = s_x[T->kmeans_seed[ns][1]]; }
-  __syncthreads();
+  double m1 = s_x[T->kmeans_seed[ns][0]], m2 = s_x[T->kmeans_seed[ns][1]];
   int km_iters = 0;
+  double cnt_d[3] = {0.0, 0.0, 0.0};
   for (;;) {
     ++km_iters;
-    if (tid < ns) {
-      double x = s_x[tid];
-      double md = 1.7976931348623157e308;
-      int cl = 0;
-      for (int j = 0; j < 3; ++j) { double d = fabs(x - s_mean[j]); if (d < md) { md = d; cl = j; } }
-      s_cl[tid] = cl;
+    int cl = 0;
+    if (act) {
+      double md = fabs(x);  // |x - mean0|, mean0 = 0
+      double d1 = fabs(x - m1), d2 = fabs(x - m2);
+      if (d1 < md) { md = d1; cl = 1; }
+      if (d2 < md) { md = d2; cl = 2; }
     }
-    __syncthreads();
-    if (tid < 3) {  // lane j replays new_means[j] += s[i] over i ascending
-      double sum = 0.0; int cnt = 0;
-      for (int i = 0; i < ns; ++i) if (s_cl[i] == tid) { sum += s_x[i]; ++cnt; }
-      s_sum[tid] = sum; s_cnt[tid] = cnt;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      double nm[3];
-      nm[0] = 0.0;
-      for (int j = 1; j < 3; ++j) nm[j] = s_cnt[j] > 0 ? s_sum[j] / (double)s_cnt[j] : s_sum[j];
-      int same = (nm[0] == s_mean[0] && nm[1] == s_mean[1] && nm[2] == s_mean[2]);
-      s_flag = same;
-      if (!same) { s_mean[0] = 0.0; s_mean[1] = nm[1]; s_mean[2] = nm[2]; }
-    }
-    __syncthreads();
-    if (s_flag || km_iters >= 100000) break;
+    double v[5] = {(act && cl == 1) ? x : 0.0, (act && cl == 2) ? x : 0.0, (act && cl == 0) ? 1.0 : 0.0, (act && cl == 1) ? 1.0 : 0.0,
+                   (act && cl == 2) ? 1.0 : 0.0};
+    block_sum_multi<5>(v, s_buf, phase);
+    double n1 = v[3] > 0.0 ? v[0] / v[3] : v[0];
+    double n2 = v[4] > 0.0 ? v[1] / v[4] : v[1];
+    cnt_d[0] = v[2]; cnt_d[1] = v[3]; cnt_d[2] = v[4];
+    bool same = (n1 == m1 && n2 == m2);
+    if (same || km_iters >= 100000) break;
+    m1 = n1; m2 = n2;
   }
   // 5. initial variance = population variance of the sample (:392-399); weights = cluster fractions (:402-410)
-  if (tid == 0) {
-    double acc = 0.0;
-    for (int i = 0; i < ns; ++i) acc += s_x[i];
-    double mean = acc / (double)ns;
-    double v = 0.0;
-    for (int i = 0; i < ns; ++i) { double d = s_x[i] - mean; v += d * d; }
-    v /= (double)ns;
-    for (int j = 0; j < 3; ++j) { s_var[j] = v; s_w[j] = (double)s_cnt[j] / (double)ns; }
+  double mean[3] = {0.0, m1, m2}, var[3], wgt[3];
+  {
+    double v1[1] = {act ? x : 0.0};
+    block_sum_multi<1>(v1, s_buf, phase);
+    double mu = v1[0] / (double)ns;
+    double d = act ? (x - mu) : 0.0;
+    double v2[1] = {d * d};
+    block_sum_multi<1>(v2, s_buf, phase);
+    double iv = v2[0] / (double)ns;
+    for (int j = 0; j < 3; ++j) { var[j] = iv; wgt[j] = cnt_d[j] / (double)ns; }
   }
-  __syncthreads();
-  // 6. EM (:418-484)
+  // 6. EM (:418-484); every thread carries the (identical) mixture parameters in registers
   int em_iters = 0;
   for (int it = 0; it < 100; ++it) {
     ++em_iters;
-    if (tid < ns) {
-      double x = s_x[tid], r[3], sum = 0.0;
-      for (int j = 0; j < 3; ++j) { r[j] = s_w[j] * gauss_pdf(x, s_mean[j], s_var[j]); sum += r[j]; }
-      for (int j = 0; j < 3; ++j) s_r[j][tid] = r[j] / sum;
+    double r[3] = {0.0, 0.0, 0.0};
+    if (act) {
+      double sum = 0.0;
+      for (int j = 0; j < 3; ++j) { r[j] = wgt[j] * gauss_pdf(x, mean[j], var[j]); sum += r[j]; }
+      for (int j = 0; j < 3; ++j) r[j] /= sum;
     }
-    __syncthreads();
-    if (tid < 5) {  // Nk[0..2]; sum_i resp[i][j] * s[i] for j = 1, 2
-      double acc = 0.0;
-      if (tid < 3) for (int i = 0; i < ns; ++i) acc += s_r[tid][i];
-      else { const int j = tid - 2; for (int i = 0; i < ns; ++i) acc += s_r[j][i] * s_x[i]; }
-      s_sum[tid] = acc;
-    }
-    __syncthreads();
-    double nk[3] = {s_sum[0], s_sum[1], s_sum[2]};
-    double nm[3] = {0.0, s_sum[3] / nk[1], s_sum[4] / nk[2]};
-    if (tid < 3) {
-      double acc = 0.0;
-      const double mj = nm[tid];
-      for (int i = 0; i < ns; ++i) { double diff = s_x[i] - mj; acc += s_r[tid][i] * diff * diff; }
-      s_sum[5 + tid] = fmax(acc / nk[tid], 1e-6);
-    }
-    double change = fabs(nm[1] - s_mean[1]) + fabs(nm[2] - s_mean[2]);
-    __syncthreads();
-    if (tid == 0) {
-      for (int j = 0; j < 3; ++j) { s_w[j] = nk[j] / (double)ns; s_mean[j] = nm[j]; s_var[j] = s_sum[5 + j]; }
-    }
-    __syncthreads();
+    double a5[5] = {r[0], r[1], r[2], r[1] * x, r[2] * x};
+    block_sum_multi<5>(a5, s_buf, phase);
+    double nk[3] = {a5[0], a5[1], a5[2]};
+    double nm[3] = {0.0, a5[3] / nk[1], a5[4] / nk[2]};
+    double b3[3];
+    for (int j = 0; j < 3; ++j) { double diff = x - nm[j]; b3[j] = act ? r[j] * diff * diff : 0.0; }
+    block_sum_multi<3>(b3, s_buf, phase);
+    double change = fabs(nm[1] - mean[1]) + fabs(nm[2] - mean[2]);
+    for (int j = 0; j < 3; ++j) { wgt[j] = nk[j] / (double)ns; mean[j] = nm[j]; var[j] = fmax(b3[j] / nk[j], 1e-6); }
     if (change < 1e-6) break;
   }
   if (tid == 0) {
-    for (int j = 0; j < 3; ++j) { gmm_out[j] = s_mean[j]; gmm_out[3 + j] = s_var[j]; gmm_out[6 + j] = s_w[j]; }
+    for (int j = 0; j < 3; ++j) { gmm_out[j] = mean[j]; gmm_out[3 + j] = var[j]; gmm_out[6 + j] = wgt[j]; }
     st->em_iters = em_iters; st->kmeans_iters = km_iters;
   }
   // 7. P(r_k) of the fitted mixture on the JS grid r_k = dr * (1 + k) (:741-752), shared by all alpha candidates
   if (tid < 100) {
     const double dr = T->trunc / 100.0;
-    double r = dr * (1.0 + (double)tid);
+    double rr = dr * (1.0 + (double)tid);
     double Pr = 0.0;
-    for (int m = 0; m < 3; ++m) Pr += s_w[m] * gauss_pdf(r, s_mean[m], s_var[m]);
+    for (int m = 0; m < 3; ++m) Pr += wgt[m] * gauss_pdf(rr, mean[m], var[m]);
     gmm_out[16 + tid] = Pr + 1e-10;
   }
 }

@@ -73,7 +73,7 @@ struct b2lo_ctx {
   long long launches = 0;
   unsigned long long h2d_bytes = 0, d2h_bytes = 0;   // bytes moved over PCIe by this context (bench accounting)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_stage = nullptr;
-  bool stage_busy = false;
+  bool stage_busy = false; bool sim_attr_set = false;
   int sm_count = 148;
   size_t feat_cap_hint = 0;        // host-known upper bound of *d_nfeat (samples of the last filter run)
   cudaGraphExec_t icp_graph_exec = nullptr; unsigned long long icp_graph_sig = 0;
@@ -119,7 +119,7 @@ struct b2lo_map {
   b2::FEntry* a_tab = nullptr; int a_log2cap = 0;   // affected-L1 set of the current update
   int* a_list = nullptr;                            // compacted affected slots / purge list
   // cull scratch (sized by dense capacity)
-  uint8_t* c_flag = nullptr; int* c_blkcnt = nullptr; int* c_blkoff = nullptr; int* c_removed = nullptr; int* c_surv = nullptr;
+  uint8_t* c_flag = nullptr; int* c_blkcnt = nullptr; int* c_blkoff = nullptr; int* c_removed = nullptr; int* c_aux = nullptr;
   int* c_l1work = nullptr;
   // purge scratch
   int* p_seq = nullptr; int* p_aux = nullptr; size_t p_cap = 0;

@@ -8,8 +8,9 @@
 // The reference is sequential and its containers leak their ORDER into the results (SURVEY.md hard
 // part 4): L0 iteration order (= GetPointCloud order, = cull order) and each L1's child-set order
 // (= summation order of the surfel fit).  The kernels below reproduce those orders exactly, in parallel:
-//   cull    : mark -> scan -> closed form of "erase ascending positions with swap-with-last":
-//             the i-th hole below the new size receives the i-th LAST surviving tail element;
+//   cull    : mark -> scan -> replay of "erase in ascending position order, swap-with-last" on indices only
+//             (closed form hole_t <- element n-t when no tail voxel is culled, the usual case; otherwise one
+//             thread replays the k erases in shared memory), then the moves are applied in parallel;
 //             per affected parent one thread replays its child-set swap-erases in removal order.
 //   insert  : per-voxel lists of the new points (atomicExch) sorted by point index -> running mean
 //             c = (c*n + p)/(n+1) replayed in input order; new voxels ranked by first-seen index with a
@@ -57,11 +58,10 @@ __global__ void __launch_bounds__(1024) k_cull_scan(int n0, const int* blkcnt, i
   }
   if (threadIdx.x == 0) { us[US_K] = base; us[US_S] = n0 - base; us[US_N0] = n0 - base; us[US_NWORK] = 0; }
 }
-__global__ void __launch_bounds__(1024) k_cull_lists(MapDev M, int n0, const uint8_t* flag, const int* blkoff, int* us, int* removed, int* surv, int* l1work) {
+__global__ void __launch_bounds__(1024) k_cull_lists(MapDev M, int n0, const uint8_t* flag, const int* blkoff, int* us, int* removed, int* l1work) {
   __shared__ int sm[40];
   const int k = us[US_K];
   if (k == 0) return;
-  const int s = us[US_S];
   int ntiles = (n0 + 1023) / 1024;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     int pos = tile * 1024 + threadIdx.x;
@@ -75,8 +75,6 @@ __global__ void __launch_bounds__(1024) k_cull_lists(MapDev M, int n0, const uin
       unsigned long long pk = key_morton(parent_coord(x, M.factor), parent_coord(y, M.factor), parent_coord(z, M.factor));
       int s1 = l1_find(M, pk);
       if (s1 >= 0 && atomicCAS(&M.t1_first[s1], INT_MAX, pre) == INT_MAX) l1work[atomicAdd(&us[US_NWORK], 1)] = s1;
-    } else if (pos >= s) {
-      surv[(n0 - 1 - pos) - (k - pre)] = pos;
     }
   }
 }
@@ -116,14 +114,15 @@ __global__ void k_cull_unregister(MapDev M, const uint8_t* flag, int* us, const 
     M.l1_tab[s1].key = k1;
   }
 }
-__global__ void k_cull_move(MapDev M, int* us, const int* removed, const int* surv) {
+__global__ void k_cull_move(MapDev M, int* us, const int* removed, const int* aux) {
   const int k = us[US_K];
   const int s = us[US_S];
+  const int* fill = aux + 3 * k + 1;  // fill[t], t = 1..k (k_swap_erase_sim)
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < k; r += gridDim.x * blockDim.x) {
     int pos = removed[r];
     M.l0_tab[M.l0_slot[pos]].key = KEY_TOMB;
     if (pos < s) {
-      int src = surv[r];
+      int src = fill[r + 1];
       uint32_t sl = M.l0_slot[src];
       M.l0_cent[pos] = M.l0_cent[src];
       M.l0_key[pos] = M.l0_key[src];
@@ -417,16 +416,24 @@ __global__ void k_purge_seq(MapDev M, int* us, const int* pord, const int* poff,
     atomicSub(&M.ctr[CT_N1], 1); atomicAdd(&M.ctr[CT_TOMB1], 1);
   }
 }
-// Replay of k arbitrary-order swap-with-last erases on a dense vector of size n, on indices only.
-// loc[t]  : where the t-th erased element currently sits (>= s: tail position; < 0: hole -h of erase h)
-// occ*[q-s]: current occupant of tail position q (original position id, erase time or 0)
-// fill[h] : original position of the survivor that finally lands in the hole left by erase h (P_h < s)
-__global__ void k_purge_sim(int* us, const int* seq_pos, int* aux, int aux_cap_k) {
+// Replay of k swap-with-last erases (in the given order) on a dense vector of size n, on indices only.
+// seq_pos[t-1]: ORIGINAL position of the t-th erased element.  Output fill[t] (at aux[3k+1+t]): original position of
+// the survivor that finally sits in the hole the t-th erase leaves below the new size s = n - k.
+//   loc[t]   : where the t-th erased element currently sits (>= s: tail position; -h: in the hole of erase h)
+//   occ*[q-s]: current occupant of tail position q (original position id, its erase time or 0)
+// Fast path (no erased element lives in the tail [s, n)): erase t moves original element n-t into hole t.
+__global__ void k_swap_erase_sim(const int* us, int k_slot, int n_fixed, const int* seq_pos, int* aux, int aux_cap_k) {
   extern __shared__ int smem[];
-  const int k = us[US_KPURGE];
+  const int k = us[k_slot];
   if (k == 0) return;
-  const int n = us[US_N0] + us[US_NNEW];
+  const int n = n_fixed >= 0 ? n_fixed : us[US_N0] + us[US_NNEW];
   const int s = n - k;
+  int tail = 0;
+  for (int t = threadIdx.x; t < k; t += blockDim.x) tail |= (seq_pos[t] >= s);
+  if (!__syncthreads_or(tail)) {
+    for (int t = 1 + threadIdx.x; t <= k; t += blockDim.x) aux[3 * k + 1 + t] = n - t;
+    return;
+  }
   const bool in_smem = (k <= aux_cap_k);
   int* loc = in_smem ? smem : aux;               // k+1
   int* occ_id = loc + (k + 1);                   // k
@@ -629,7 +636,7 @@ int map_reserve(b2lo_map* m, size_t need_l0, size_t need_upd) {
     B2_CUDA(cudaStreamSynchronize(st));
     cudaFree(d.l0_cent); cudaFree(d.l0_key); cudaFree(d.l0_slot);
     d.l0_cent = nc; d.l0_key = nk; d.l0_slot = ns; d.l0_cap = (uint32_t)ncap;
-    if ((rc = dmalloc(&m->c_flag, ncap)) || (rc = dmalloc(&m->c_removed, ncap)) || (rc = dmalloc(&m->c_surv, ncap)) ||
+    if ((rc = dmalloc(&m->c_flag, ncap)) || (rc = dmalloc(&m->c_removed, ncap)) || (rc = dmalloc(&m->c_aux, 4 * ncap + 16)) ||
         (rc = dmalloc(&m->c_l1work, ncap)) || (rc = dmalloc(&m->c_blkcnt, ncap / 1024 + 2)) || (rc = dmalloc(&m->c_blkoff, ncap / 1024 + 2)))
       return rc;
   }
@@ -678,6 +685,9 @@ static int grid_for(size_t n, int threads) { size_t b = (n + threads - 1) / thre
 
 // UpdateVoxelMap on a world-frame cloud already on the device (float4 stream).  n_cap = host-known upper
 // bound of *d_n.  Ends with a counter read-back (one synchronisation).
+constexpr int SIM_SMEM_K = 12000;  // (4k+2) ints <= 192 KB of dynamic shared memory
+constexpr int SIM_SMEM_BYTES = (4 * SIM_SMEM_K + 2) * (int)sizeof(int);
+
 int map_update_dev(b2lo_map* m, const float4* d_world, const int* d_n, size_t n_cap, const float sensor[3], float radius_sq, int rehash) {
   b2lo_ctx* ctx = m->ctx;
   if (n_cap == 0) return B2LO_S_EMPTY;
@@ -686,6 +696,10 @@ int map_update_dev(b2lo_map* m, const float4* d_world, const int* d_n, size_t n_
   MapDev& d = m->d;
   cudaStream_t st = ctx->stream;
   int* us = m->u_state;
+  if (!ctx->sim_attr_set) {
+    B2_CUDA(cudaFuncSetAttribute(k_swap_erase_sim, cudaFuncAttributeMaxDynamicSharedMemorySize, SIM_SMEM_BYTES));
+    ctx->sim_attr_set = true;
+  }
   prof_begin(ctx, PS_MAP);
   B2_CUDA(cudaMemsetAsync(us, 0, US_COUNT * sizeof(int), st));
   const int n0 = (int)m->n0;
@@ -694,10 +708,11 @@ int map_update_dev(b2lo_map* m, const float4* d_world, const int* d_n, size_t n_
     int g = tiles > 1184 ? 1184 : tiles;
     k_cull_mark<<<g, 1024, 0, st>>>(d, n0, sensor[0], sensor[1], sensor[2], radius_sq, m->c_flag, m->c_blkcnt);
     k_cull_scan<<<1, 1024, 0, st>>>(n0, m->c_blkcnt, m->c_blkoff, us);
-    k_cull_lists<<<g, 1024, 0, st>>>(d, n0, m->c_flag, m->c_blkoff, us, m->c_removed, m->c_surv, m->c_l1work);
+    k_cull_lists<<<g, 1024, 0, st>>>(d, n0, m->c_flag, m->c_blkoff, us, m->c_removed, m->c_l1work);
     k_cull_unregister<<<grid_for(n0 / 8 + 1, 128), 128, 0, st>>>(d, m->c_flag, us, m->c_l1work);
-    k_cull_move<<<grid_for(n0 / 4 + 1, 256), 256, 0, st>>>(d, us, m->c_removed, m->c_surv);
-    ctx->launches += 5;
+    k_swap_erase_sim<<<1, 256, SIM_SMEM_BYTES, st>>>(us, US_K, n0, m->c_removed, m->c_aux, SIM_SMEM_K);
+    k_cull_move<<<grid_for(n0 / 4 + 1, 256), 256, 0, st>>>(d, us, m->c_removed, m->c_aux);
+    ctx->launches += 6;
   }
   B2_CUDA(cudaMemsetAsync(m->a_tab, 0xFF, sizeof(FEntry) << m->a_log2cap, st));
   int gm = grid_for(n_cap, 256);
@@ -719,10 +734,7 @@ int map_update_dev(b2lo_map* m, const float4* d_world, const int* d_n, size_t n_
     k_surfel<<<grid_for((size_t)1 << m->a_log2cap, 128), 128, 0, st>>>(d, m->a_tab, m->a_log2cap, us, plist, pfirst);
     k_purge_order<<<1, 1024, 0, st>>>(d, us, plist, pfirst, pord, poff);
     k_purge_seq<<<grid_for(n_cap, 128), 128, 0, st>>>(d, us, pord, poff, m->p_seq);
-    const int smem_k = 12000;  // (4k+2) ints <= 192 KB
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_purge_sim, cudaFuncAttributeMaxDynamicSharedMemorySize, (4 * smem_k + 2) * (int)sizeof(int)); attr_set = true; }
-    k_purge_sim<<<1, 256, (4 * smem_k + 2) * sizeof(int), st>>>(us, m->p_seq, m->p_aux, smem_k);
+    k_swap_erase_sim<<<1, 256, SIM_SMEM_BYTES, st>>>(us, US_KPURGE, -1, m->p_seq, m->p_aux, SIM_SMEM_K);
     k_purge_apply<<<grid_for(n_cap, 256), 256, 0, st>>>(d, us, m->p_seq, m->p_aux);
     ctx->launches += 5;
   }
@@ -774,7 +786,7 @@ extern "C" int b2lo_map_destroy(b2lo_map* m) {
   MapDev& d = m->d;
   void* ptrs[] = {d.l0_cent, d.l0_key, d.l0_slot, d.l0_tab, d.l1_tab, d.l1_meta, d.t0_first, d.t0_cnt, d.t0_head, d.t1_first, d.t1_head, d.ctr,
                   m->u_pts, m->u_pslot, m->u_next, m->u_isnew, m->u_newrank, m->u_l1slot, m->u_next1, m->a_tab, m->a_list, m->c_flag, m->c_blkcnt,
-                  m->c_blkoff, m->c_removed, m->c_surv, m->c_l1work, m->p_seq, m->p_aux, m->u_state};
+                  m->c_blkoff, m->c_removed, m->c_aux, m->c_l1work, m->p_seq, m->p_aux, m->u_state};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete m;
   return B2LO_OK;
