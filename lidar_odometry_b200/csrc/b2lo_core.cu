@@ -281,6 +281,12 @@ extern "C" int b2lo_ctx_profile_read(b2lo_ctx* ctx, int slot, double* total_ms, 
   if (launches) *launches = ctx->prof->n[slot];
   return B2LO_OK;
 }
+extern "C" int b2lo_ctx_debug_clocks(b2lo_ctx* ctx, long long out[32]) {  // clock64 phase stamps of the last optimize (debug aid)
+  if (!ctx || !out) return B2LO_E_ARG;
+  B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  B2_CUDA(cudaMemcpy(out, ctx->d_icp->dbg, 32 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return B2LO_OK;
+}
 extern "C" int b2lo_ctx_io_bytes(b2lo_ctx* ctx, unsigned long long* h2d, unsigned long long* d2h) {
   if (!ctx) return B2LO_E_ARG;
   if (h2d) *h2d = ctx->h2d_bytes;

@@ -6,7 +6,8 @@
 //     l0_cent[pos]  float4  (cx, cy, cz, point_count as int bits)          16 B  <- cull scan / export stream
 //     l0_key[pos]   u64     63-bit Z-order code of the voxel key             8 B
 //     l0_slot[pos]  u32     index of the voxel's entry in the L0 hash        4 B
-//   L0 hash: open addressing, linear probing, 16 B entries {u64 key, u32 pos, u32 pad}.
+//   L0 hash: open addressing, linear probing, 32 B entries = one sector: {u64 key, u32 pos, per-update scratch
+//            (first point, point count - 1, list head, creation rank)}; the scratch is self-cleaning (all 0xFF when idle).
 //   L1 ("parent voxels with surfels", VoxelMap.h:312-324) — the hash entry IS the storage:
 //     l1_tab[slot]  32 B = one sector: {u64 key | has_surfel<<63, float n[3], float c[3]}   <- K2 probe = 1 sector
 //     l1_meta[slot] 40 B: child list (<=27 five-bit codes in the reference's child-set order), counts, planarity
@@ -25,9 +26,9 @@ constexpr uint64_t KEY_MASK = 0x7FFFFFFFFFFFFFFFull;
 constexpr uint64_t SURFEL_BIT = 0x8000000000000000ull;
 constexpr uint32_t POS_PENDING = 0xFFFFFFFFu;
 
-struct L0Entry { unsigned long long key; uint32_t pos; uint32_t pad; };              // 16 B
+struct __align__(32) L0Entry { unsigned long long key; uint32_t pos; unsigned int first; int cnt; int head; int rank; int pad; };  // 32 B
 struct __align__(32) L1Entry { unsigned long long key; float n[3]; float c[3]; };    // 32 B
-struct L1Meta { uint8_t child[27]; uint8_t nchild; float planarity; int last_child_count; int pad; };  // 40 B
+struct L1Meta { uint8_t child[27]; uint8_t nchild; float planarity; int last_child_count; int mark; };  // 40 B (mark: per-update dedupe flag)
 
 __host__ __device__ __forceinline__ uint64_t expand21(uint64_t v) {
   v &= 0x1FFFFFull;
@@ -87,9 +88,6 @@ struct MapDev {
   L0Entry* l0_tab; int l0_log2cap; uint32_t l0_cap;   // dense capacity
   // L1
   L1Entry* l1_tab; L1Meta* l1_meta; int l1_log2cap;
-  // self-cleaning per-update scratch, indexed by L0 / L1 hash slot
-  int* t0_first; int* t0_cnt; int* t0_head;
-  int* t1_first; int* t1_head;
   // counters (device): [0]=n0, [1]=n1, [2]=l0 tombstones, [3]=l1 tombstones, [4]=error flags, [5]=surfel count
   int* ctr;
 };
@@ -121,7 +119,7 @@ __device__ __forceinline__ int l0_find_or_insert(const MapDev& M, uint64_t key, 
       (void)first_tomb;
     } else if (k == KEY_EMPTY) {
       unsigned long long old = atomicCAS(&M.l0_tab[s].key, KEY_EMPTY, (unsigned long long)key);
-      if (old == KEY_EMPTY) { M.l0_tab[s].pos = POS_PENDING; *inserted = true; return (int)s; }
+      if (old == KEY_EMPTY) { *inserted = true; return (int)s; }  // pos is POS_PENDING (0xFFFFFFFF) in a cleared entry
       if (old == key) return (int)s;
     }
     s = (s + 1) & mask;

@@ -63,31 +63,64 @@ __global__ void k_flt_insert(const float* __restrict__ src, int n_samples, size_
   }
 }
 
-// one CTA of 1024 threads walks the samples in input order
+// exclusive scan of one u64 per thread across the block; *total = block sum (smem: >= 33 u64)
+__device__ __forceinline__ unsigned long long block_excl_scan64(unsigned long long v, unsigned long long* total, unsigned long long* smem) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned long long inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { unsigned long long n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
+  if (lane == 31) smem[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int nw = (blockDim.x + 31) >> 5;
+    unsigned long long x = lane < nw ? smem[lane] : 0ull, xi = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned long long n = __shfl_up_sync(0xffffffffu, xi, o); if (lane >= o) xi += n; }
+    smem[lane] = xi - x;
+    if (lane == 31) smem[32] = xi;
+  }
+  __syncthreads();
+  unsigned long long res = smem[w] + inc - v;
+  *total = smem[32];
+  __syncthreads();
+  return res;
+}
+
+// one CTA of 1024 threads walks the samples in input order, 4 per thread; the voxel rank (count of earlier leaders) and
+// the segment offset (sum of earlier leaders' point counts) ride one packed 64-bit scan: leaders << 32 | points
 __global__ void __launch_bounds__(1024) k_flt_scan(const FEntry* __restrict__ tab, const int* __restrict__ slot_of, int n_samples,
                                                     int* vid_of_point, int* seg_start, int* seg_cnt, int* lead_of_vid, int* d_nvox) {
-  __shared__ int sm[40];
-  int base_v = 0, base_c = 0;
-  for (int t0 = 0; t0 < n_samples; t0 += blockDim.x) {
-    int j = t0 + threadIdx.x;
-    int lead = 0, cnt = 0;
-    if (j < n_samples) {
-      int s = slot_of[j];
-      if (s >= 0 && tab[s].first == (unsigned)j) { lead = 1; cnt = tab[s].cnt + 1; }
+  __shared__ unsigned long long sm[40];
+  unsigned long long base = 0ull;
+  for (int t0 = 0; t0 < n_samples; t0 += 4 * blockDim.x) {
+    const int j0 = t0 + 4 * threadIdx.x;
+    unsigned long long p[4], sum = 0ull;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int j = j0 + k;
+      p[k] = 0ull;
+      if (j < n_samples) {
+        int s = slot_of[j];
+        if (s >= 0 && tab[s].first == (unsigned)j) p[k] = (1ull << 32) | (unsigned long long)(unsigned)(tab[s].cnt + 1);
+      }
+      sum += p[k];
     }
-    int tv, tc;
-    int ev = block_excl_scan(lead, &tv, sm);
-    int ec = block_excl_scan(cnt, &tc, sm);
-    if (lead) {
-      int v = base_v + ev;
-      vid_of_point[j] = v;
-      seg_start[v] = base_c + ec;
-      seg_cnt[v] = cnt;
-      lead_of_vid[v] = j;
+    unsigned long long tot;
+    unsigned long long ex = base + block_excl_scan64(sum, &tot, sm);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (p[k]) {
+        int v = (int)(ex >> 32), off = (int)(ex & 0xffffffffull), cnt = (int)(p[k] & 0xffffffffull);
+        vid_of_point[j0 + k] = v;
+        seg_start[v] = off;
+        seg_cnt[v] = cnt;
+        lead_of_vid[v] = j0 + k;
+      }
+      ex += p[k];
     }
-    base_v += tv; base_c += tc;
+    base += tot;
   }
-  if (threadIdx.x == 0) { *d_nvox = base_v; seg_start[base_v] = base_c; }
+  if (threadIdx.x == 0) { *d_nvox = (int)(base >> 32); seg_start[(int)(base >> 32)] = (int)(base & 0xffffffffull); }
 }
 
 __global__ void k_flt_fill(FEntry* tab, const int* __restrict__ slot_of, int n_samples, const int* __restrict__ vid_of_point,

@@ -258,47 +258,71 @@ __device__ int shuffled_head(const PkoTables* T, const int* hits, int n, int j) 
   return pos;
 }
 
-// Block-wide sum of V doubles at once: warp shuffles, one shared-memory exchange, ONE barrier (double-buffered).
-// Every thread receives the totals, accumulated in a fixed order (deterministic run to run).
-template <int V>
-__device__ __forceinline__ void block_sum_multi(double (&v)[V], double (*buf)[8][8], int& phase) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+// exp(x) for the Gaussian terms of the EM (x <= 0).  Branch-free: the argument is clamped at -708 (exp = 3e-308, an
+// additive nothing next to the O(1) mixture sums), rounding to the nearest multiple of ln 2 uses the 1.5*2^52 trick
+// (no float->int conversion), Cody-Waite reduction, degree-13 Taylor polynomial in Estrin form.  The EM fixed point
+// is one long chain of dependent f64 operations, so DEPTH is what costs: ~11 dependent operations here against the
+// ~25-deep Horner chain of the library routine.  Relative error ~2e-16 (truncation 4e-18).
+__device__ __forceinline__ double em_exp(double x) {
+  x = fmax(x, -708.0);
+  const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
+  const double tm = x * 1.4426950408889634 + MAGIC;
+  const double kd = tm - MAGIC;
+  const int k = __double2loint(tm);          // low word of the biased sum = round(x * log2 e) in two's complement
+  double r = fma(-kd, 6.93147180369123816490e-01, x);
+  r = fma(-kd, 1.90821492927058770002e-10, r);
+  const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+  const double p01 = 1.0 + r;
+  const double p23 = fma(r, 1.0 / 6.0, 0.5);
+  const double p45 = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+  const double p67 = fma(r, 1.0 / 5040.0, 1.0 / 720.0);
+  const double p89 = fma(r, 1.0 / 362880.0, 1.0 / 40320.0);
+  const double pab = fma(r, 1.0 / 39916800.0, 1.0 / 3628800.0);
+  const double pcd = fma(r, 1.0 / 6227020800.0, 1.0 / 479001600.0);
+  const double q0 = fma(p23, r2, p01), q1 = fma(p67, r2, p45), q2 = fma(pab, r2, p89);
+  const double s0 = fma(q1, r4, q0), s1 = fma(pcd, r4, q2);
+  const double pr = fma(s1, r8, s0);
+  return __hiloint2double(__double2hiint(pr) + k * 1048576, __double2loint(pr));
+}
+
+constexpr int EM_SPL = MAXS / 32;   // samples per lane in the EM (4): sample index = lane + 32 k
+static_assert(MAXS % 32 == 0, "EM layout needs a multiple of 32 samples");
+
+template <int V> __device__ __forceinline__ void warp_sum_multi(double (&v)[V]) {
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
+  for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+    for (int i = 0; i < V; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
   }
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < V; ++i) buf[phase][w][i] = v[i];
-  }
-  __syncthreads();
-  const int nw = (blockDim.x + 31) >> 5;
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    double acc = buf[phase][0][i];
-    for (int ww = 1; ww < nw; ++ww) acc += buf[phase][ww][i];
-    v[i] = acc;
-  }
-  phase ^= 1;
 }
 
 // One CTA: accepted-count scan, the C < min test, the iteration-0 residual scale, the libstdc++-exact sample draw,
-// k-means and the 3-component EM of AdaptiveMEstimator::fit_gmm (AdaptiveMEstimator.cpp:294-485) with one thread per
-// sample and block-tree sums (the reference sums left to right; the two orders agree to ~1e-16 relative, which moves
-// the discrete outputs - iteration counts, arg-min alpha - only on exact ties; tests/ assert they match the oracle).
+// k-means and the 3-component EM of AdaptiveMEstimator::fit_gmm (AdaptiveMEstimator.cpp:294-485).
+// The EM fixed point is a chain of dependent f64 operations (30-100 iterations per call, capped at 100), so the
+// kernel is laid out for LATENCY (measured on B200: DFMA 8.5, SHFL64+DADD 36, f64 rcp/rsqrt ~75, bar.sync ~45 cycles):
+//   * warp c owns mixture component c; each lane carries 4 samples (independent chains hide the exp latency);
+//   * per iteration ONE shared-memory exchange + ONE named barrier: the three warps publish their unnormalised
+//     densities p_c(x_i) (and the mean shift of their previous M-step), then every warp normalises its own
+//     responsibilities and reduces its own three sums with warp shuffles only;
+//   * the convergence test of iteration t rides the exchange of iteration t+1 (the speculative E-step is dropped);
+//   * the variance update uses sum r x^2 / nk - mean^2 (algebraically the reference's second pass), reciprocals are
+//     computed once per component, and responsibilities are p * rcp(sum) (a true f64 divide of the tiny far-component
+//     terms takes the slow denormal path).
+// The reference sums left to right and divides; the two evaluation orders agree to ~1e-14 relative, which can move
+// the discrete outputs (iteration counts, arg-min alpha) only on near-exact ties - tests/ assert they match the oracle.
 __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict__ d_npts, IcpState* st, IcpParams prm, const double* __restrict__ res,
                                                            const int* __restrict__ slot, const int* __restrict__ cidx, const int* __restrict__ tilecnt,
                                                            int* tileoff, const PkoTables* __restrict__ T, const int* __restrict__ hits, double* gmm_out) {
   if (st->done) return;
   __shared__ int sm[40];
   __shared__ double smd[40];
-  __shared__ double s_buf[2][8][8];
   __shared__ double s_x[MAXS];
-  __shared__ double s_mean[3], s_var[3], s_w[3], s_norm[3];
-  __shared__ int s_flag;
-  int phase = 0;
+  __shared__ int s_head[MAXS];
+  __shared__ double s_p[2][3][MAXS];
+  __shared__ double s_dm[2][4];
+  __shared__ double s_par[3][4];
   const int tid = threadIdx.x;
+  const long long c0 = clock64();
   const int npts = *d_npts;
   const int ntiles = (npts + TILE - 1) / TILE;
   // 1. exclusive scan of the per-tile accepted counts
@@ -318,6 +342,7 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
     return;
   }
   // 2. residual normalisation scale, first iteration only (ICP.cpp:304-316)
+  const long long c1 = clock64();
   double scale = st->scale;
   if (st->iter == 0) {
     double acc = 0.0;
@@ -331,125 +356,188 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
   }
   if (!prm.use_pko) { if (tid == 0) { st->delta = prm.robust_delta; st->em_iters = 0; st->kmeans_iters = 0; } return; }
   const double sdiv = fmax(scale, 1e-6);
+  const long long c2 = clock64();
   // 3. the sample: residuals[idx[0..ns)] of the shuffled index vector (AdaptiveMEstimator.cpp:319-331)
   const int ns = T->sample_size < C ? T->sample_size : C;
-  const bool act = tid < ns;
-  double x = 0.0;
-  if (act) {
-    int ci = shuffled_head(T, hits, C, tid);
-    int lo = 0, hi = ntiles - 1;  // last tile with tileoff <= ci
-    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (tileoff[mid] <= ci) lo = mid; else hi = mid - 1; }
-    int q = cidx[lo * TILE + (ci - tileoff[lo])];
-    x = res[q] / sdiv;
-    s_x[tid] = x;
+  const int mode = C >= 65536 ? 2 : ((C & 1) ? 1 : 0);
+  if (tid < MAXS) s_head[tid] = T->head_r[mode][tid];
+  __syncthreads();
+  if (tid < ns) {
+    // position tid of std::shuffle(iota(C), mt19937(42)): the LARGEST swap partner i in [128, C) that hit position tid
+    // (ascending hit list), else a backward trace through the first min(C,128)-1 swaps
+    const int lo = T->hit_off[mode][tid], hi = T->hit_off[mode][tid + 1];
+    int best = -1;
+    for (int q0 = lo; q0 < hi; q0 += 8) {
+      int v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = (q0 + u < hi) ? hits[q0 + u] : 0x7fffffff;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) if (v[u] < C) best = v[u];
+      if (v[7] >= C) break;
+    }
+    int ci = best;
+    if (best < 0) {
+      int pos = tid;
+      const int top = C - 1 < MAXS - 1 ? C - 1 : MAXS - 1;
+      for (int i = top; i >= 1; --i) { int r = s_head[i]; pos = (pos == i) ? r : ((pos == r) ? i : pos); }
+      ci = pos;
+    }
+    int tl = 0, th = ntiles - 1;  // last tile with tileoff <= ci
+    while (tl < th) { int mid = (tl + th + 1) >> 1; if (tileoff[mid] <= ci) tl = mid; else th = mid - 1; }
+    int q = cidx[tl * TILE + (ci - tileoff[tl])];
+    s_x[tid] = res[q] / sdiv;
   }
   __syncthreads();
-  // 4. k-means (:336-389): mean0 = 0, mean1/2 = sample[dis(gen)]
+  const long long c3 = clock64();
+  if (tid >= 96) return;
+  const int lane = tid & 31, c = tid >> 5;   // warp c <-> mixture component / k-means cluster c
+  double x[EM_SPL], xx[EM_SPL];
+  bool act[EM_SPL];
+#pragma unroll
+  for (int k = 0; k < EM_SPL; ++k) { const int i = lane + 32 * k; act[k] = i < ns; x[k] = act[k] ? s_x[i] : 0.0; xx[k] = x[k] * x[k]; }
+  const double inv_ns = 1.0 / (double)ns;
+  // 4. k-means (:336-389): mean0 = 0, mean1/2 = sample[dis(gen)]; every warp runs it redundantly (no exchange needed)
   double m1 = s_x[T->kmeans_seed[ns][0]], m2 = s_x[T->kmeans_seed[ns][1]];
   int km_iters = 0;
-  double cnt_d[3] = {0.0, 0.0, 0.0};
+  double cnt[3] = {0.0, 0.0, 0.0};
   for (;;) {
     ++km_iters;
-    int cl = 0;
-    if (act) {
-      double md = fabs(x);  // |x - mean0|, mean0 = 0
-      double d1 = fabs(x - m1), d2 = fabs(x - m2);
+    double v[4] = {0.0, 0.0, 0.0, 0.0};   // sum1, sum2, count1, count2
+#pragma unroll
+    for (int k = 0; k < EM_SPL; ++k) {
+      double md = fabs(x[k]);  // |x - mean0|, mean0 = 0
+      const double d1 = fabs(x[k] - m1), d2 = fabs(x[k] - m2);
+      int cl = 0;
       if (d1 < md) { md = d1; cl = 1; }
       if (d2 < md) { md = d2; cl = 2; }
+      if (act[k]) { v[0] += (cl == 1) ? x[k] : 0.0; v[1] += (cl == 2) ? x[k] : 0.0; v[2] += (cl == 1) ? 1.0 : 0.0; v[3] += (cl == 2) ? 1.0 : 0.0; }
     }
-    double v[5] = {(act && cl == 1) ? x : 0.0, (act && cl == 2) ? x : 0.0, (act && cl == 0) ? 1.0 : 0.0, (act && cl == 1) ? 1.0 : 0.0,
-                   (act && cl == 2) ? 1.0 : 0.0};
-    block_sum_multi<5>(v, s_buf, phase);
-    double n1 = v[3] > 0.0 ? v[0] / v[3] : v[0];
-    double n2 = v[4] > 0.0 ? v[1] / v[4] : v[1];
-    cnt_d[0] = v[2]; cnt_d[1] = v[3]; cnt_d[2] = v[4];
-    bool same = (n1 == m1 && n2 == m2);
+    warp_sum_multi<4>(v);
+    const double n1 = v[2] > 0.0 ? v[0] / v[2] : v[0];
+    const double n2 = v[3] > 0.0 ? v[1] / v[3] : v[1];
+    cnt[1] = v[2]; cnt[2] = v[3]; cnt[0] = (double)ns - v[2] - v[3];
+    const bool same = (n1 == m1 && n2 == m2);
     if (same || km_iters >= 100000) break;
     m1 = n1; m2 = n2;
   }
+  const long long c4 = clock64();
   // 5. initial variance = population variance of the sample (:392-399); weights = cluster fractions (:402-410)
-  double mean[3] = {0.0, m1, m2}, var[3], wgt[3];
+  double mean = (c == 1) ? m1 : ((c == 2) ? m2 : 0.0), var, wgt = cnt[c] * inv_ns;
   {
-    double v1[1] = {act ? x : 0.0};
-    block_sum_multi<1>(v1, s_buf, phase);
-    double mu = v1[0] / (double)ns;
-    double d = act ? (x - mu) : 0.0;
-    double v2[1] = {d * d};
-    block_sum_multi<1>(v2, s_buf, phase);
-    double iv = v2[0] / (double)ns;
-    for (int j = 0; j < 3; ++j) { var[j] = iv; wgt[j] = cnt_d[j] / (double)ns; }
+    double v2[2] = {0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < EM_SPL; ++k) if (act[k]) { v2[0] += x[k]; v2[1] += xx[k]; }
+    warp_sum_multi<2>(v2);
+    const double mu = v2[0] * inv_ns;
+    var = v2[1] * inv_ns - mu * mu;   // population variance
   }
-  // 6. EM (:418-484); every thread carries the (identical) mixture parameters in registers
-  int em_iters = 0;
+  // 6. EM (:418-484)
+  int em_iters = 100, ph = 0;
+  double dm = 1.0;   // |mean shift| of this component in the previous M-step
   for (int it = 0; it < 100; ++it) {
-    ++em_iters;
-    double r[3] = {0.0, 0.0, 0.0};
-    if (act) {
-      double sum = 0.0;
-      for (int j = 0; j < 3; ++j) { r[j] = wgt[j] * gauss_pdf(x, mean[j], var[j]); sum += r[j]; }
-      for (int j = 0; j < 3; ++j) r[j] /= sum;
+    // E-step, own component: p_c(x_i) = w_c N(x_i; mean_c, var_c)   (gaussian_pdf :675-685: 0 for variance <= 0)
+    const bool ok = var > 0.0;
+    const double sq = ok ? rsqrt(6.283185307179586 * var) : 0.0;     // one rsqrt feeds the normalisation and 1/var = 2 pi sq^2
+    const double hiv = -0.5 * (6.283185307179586 * (sq * sq));
+    const double coef = wgt * sq;
+    double p[EM_SPL];
+#pragma unroll
+    for (int k = 0; k < EM_SPL; ++k) {
+      const double d = x[k] - mean;
+      p[k] = coef * em_exp((d * d) * hiv);
+      s_p[ph][c][lane + 32 * k] = p[k];
     }
-    double a5[5] = {r[0], r[1], r[2], r[1] * x, r[2] * x};
-    block_sum_multi<5>(a5, s_buf, phase);
-    double nk[3] = {a5[0], a5[1], a5[2]};
-    double nm[3] = {0.0, a5[3] / nk[1], a5[4] / nk[2]};
-    double b3[3];
-    for (int j = 0; j < 3; ++j) { double diff = x - nm[j]; b3[j] = act ? r[j] * diff * diff : 0.0; }
-    block_sum_multi<3>(b3, s_buf, phase);
-    double change = fabs(nm[1] - mean[1]) + fabs(nm[2] - mean[2]);
-    for (int j = 0; j < 3; ++j) { wgt[j] = nk[j] / (double)ns; mean[j] = nm[j]; var[j] = fmax(b3[j] / nk[j], 1e-6); }
-    if (change < 1e-6) break;
+    if (lane == 0) s_dm[ph][c] = dm;
+    asm volatile("bar.sync 1, 96;" ::: "memory");
+    if (it > 0) {  // convergence test of the previous iteration (:476-482); this iteration's E-step was speculative
+      const double change = s_dm[ph][1] + s_dm[ph][2];
+      if (change < 1e-6) { em_iters = it; break; }
+    }
+    double a3[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < EM_SPL; ++k) {
+      const int i = lane + 32 * k;
+      const double sum = (s_p[ph][0][i] + s_p[ph][1][i]) + s_p[ph][2][i];
+      const double r = act[k] ? p[k] * __drcp_rn(sum) : 0.0;   // sum 0 -> inf * 0 = NaN propagates as in the reference
+      a3[0] += r; a3[1] += r * x[k]; a3[2] += r * xx[k];
+    }
+    warp_sum_multi<3>(a3);
+    // M-step, own component (:436-474); mean0 stays pinned at 0
+    const double rnk = 1.0 / a3[0];
+    const double nm = (c == 0) ? 0.0 : a3[1] * rnk;
+    const double nv = fmax(a3[2] * rnk - 2.0 * nm * (a3[1] * rnk) + nm * nm, 1e-6);   // sum r (x - nm)^2 / nk
+    dm = fabs(nm - mean);
+    wgt = a3[0] * inv_ns; mean = nm; var = nv;
+    ph ^= 1;
   }
+  if (lane == 0) { s_par[c][0] = mean; s_par[c][1] = var; s_par[c][2] = wgt; }
+  asm volatile("bar.sync 1, 96;" ::: "memory");
   if (tid == 0) {
-    for (int j = 0; j < 3; ++j) { gmm_out[j] = mean[j]; gmm_out[3 + j] = var[j]; gmm_out[6 + j] = wgt[j]; }
+    for (int j = 0; j < 3; ++j) { gmm_out[j] = s_par[j][0]; gmm_out[3 + j] = s_par[j][1]; gmm_out[6 + j] = s_par[j][2]; }
     st->em_iters = em_iters; st->kmeans_iters = km_iters;
+    const long long c5 = clock64();
+    long long* dg = st->dbg + 8 * (st->iter & 1);
+    dg[0] = c1 - c0; dg[1] = c2 - c1; dg[2] = c3 - c2; dg[3] = c4 - c3; dg[4] = c5 - c4; dg[5] = em_iters; dg[6] = km_iters;
   }
   // 7. P(r_k) of the fitted mixture on the JS grid r_k = dr * (1 + k) (:741-752), shared by all alpha candidates
-  if (tid < 100) {
-    const double dr = T->trunc / 100.0;
-    double rr = dr * (1.0 + (double)tid);
+  for (int k = tid; k < 100; k += 96) {
+    const double rr = (T->trunc / 100.0) * (1.0 + (double)k);
     double Pr = 0.0;
-    for (int m = 0; m < 3; ++m) Pr += wgt[m] * gauss_pdf(rr, mean[m], var[m]);
-    gmm_out[16 + tid] = Pr + 1e-10;
+    for (int m = 0; m < 3; ++m) Pr += s_par[m][2] * gauss_pdf(rr, s_par[m][0], s_par[m][1]);
+    gmm_out[16 + k] = Pr + 1e-10;
   }
 }
 
-// one CTA per alpha candidate i = 1..S (blockIdx.x + 1); thread k handles r_k = dr * (1 + k)
+// one CTA per alpha candidate i = 1..S (blockIdx.x + 1); thread k handles r_k = dr * (1 + k); the last CTA takes the arg-min
 __global__ void __launch_bounds__(128) k_icp_pko2(IcpState* st, IcpParams prm, const PkoTables* __restrict__ T, const double* __restrict__ gmm,
                                                    double* js, unsigned int* ticket) {
   if (st->done || !prm.use_pko) return;
-  __shared__ double term[128];
+  __shared__ double s_c[4], s_n[4];
+  __shared__ int s_i[4];
   __shared__ int s_last;
-  const int k = threadIdx.x;
+  const int k = threadIdx.x, lane = k & 31, w = k >> 5;
   const int ai = blockIdx.x + 1;
   const double alpha = T->alpha[ai];
   const double pf = T->Z[ai];
   const double dr = T->trunc / 100.0;
-  double v = __longlong_as_double(0x7ff8000000000000ll);
+  double v = 0.0, c = 0.0;
   if (k < 100) {
     double r = dr * (1.0 + (double)k);
     double Pr = gmm[16 + k];
     double Q = pko_kernel(T->kernel_type, r, alpha) / (pf + 1e-10) + 1e-10;
     double Mx = 0.5 * (Pr + Q);
-    v = 0.5 * (Pr * log(Pr / Mx) + Q * log(Q / Mx));
+    double jsd = 0.5 * (Pr * log(Pr / Mx) + Q * log(Q / Mx));
+    if (jsd == jsd) { v = jsd; c = 1.0; }   // NaN terms are skipped (:777-779)
   }
-  term[k] = v;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+  if (lane == 0) { s_c[w] = v; s_n[w] = c; }
   __syncthreads();
   if (k == 0) {
-    double cost = 0.0, cnt = 0.0;
-    for (int q = 0; q < 100; ++q) { double tq = term[q]; if (tq == tq) { cost += tq; cnt += 1.0; } }
-    double out = (pf < 1e-10 || cnt == 0.0) ? 1.7976931348623157e308 : cost / cnt;
-    js[ai] = out;
+    double cost = (s_c[0] + s_c[1]) + (s_c[2] + s_c[3]), cnt = (s_n[0] + s_n[1]) + (s_n[2] + s_n[3]);
+    js[ai] = (pf < 1e-10 || cnt == 0.0) ? 1.7976931348623157e308 : cost / cnt;
     __threadfence();
     unsigned int old = atomicAdd(ticket, 1u);
     s_last = (old == gridDim.x - 1);
   }
   __syncthreads();
-  if (s_last && k == 0) {
-    __threadfence();
-    double best_alpha = T->min_sf, best = 1.7976931348623157e308;
-    for (int i = 1; i < T->n_alpha; ++i) { double c = ((volatile double*)js)[i]; if (c < best) { best = c; best_alpha = T->alpha[i]; } }
-    st->delta = best_alpha;
+  if (!s_last) return;
+  __threadfence();
+  // arg-min with strict '<' in candidate order (:259-275): smallest cost, lowest index on ties
+  const int na = T->n_alpha;
+  double best = 1.7976931348623157e308; int bi = 0x7fffffff;
+  for (int i = 1 + k; i < na; i += blockDim.x) { double cc = ((volatile double*)js)[i]; if (cc < best) { best = cc; bi = i; } }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ob = __shfl_xor_sync(0xffffffffu, best, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if (lane == 0) { s_c[w] = best; s_i[w] = bi; }
+  __syncthreads();
+  if (k == 0) {
+    for (int ww = 1; ww < 4; ++ww) if (s_c[ww] < best || (s_c[ww] == best && s_i[ww] < bi)) { best = s_c[ww]; bi = s_i[ww]; }
+    // best_cost starts at DBL_MAX and only a strictly smaller cost replaces min_scale_factor
+    st->delta = (bi != 0x7fffffff && best < 1.7976931348623157e308) ? T->alpha[bi] : T->min_sf;
     *ticket = 0u;
   }
 }
@@ -578,14 +666,29 @@ __global__ void __launch_bounds__(TILE) k_icp_gn(MapDev M, const float4* __restr
   if (threadIdx.x == 0) { unsigned int old = atomicAdd(&st->ticket, 1u); s_last = (old == gridDim.x - 1); }
   __syncthreads();
   if (!s_last) return;
+  const long long g0 = clock64();
   __threadfence();
-  if (threadIdx.x < 28) {
+  // fixed-order sum of the per-block partials: 8 warps x 28 lanes take every 8th block (independent L2 loads in flight),
+  // then the 8 warp totals are added in order -> bit-reproducible from run to run
+  {
     double v = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) v += ((volatile double*)partial)[b * 28 + threadIdx.x];
-    red[0][threadIdx.x] = v;
+    if (lane < 28) for (unsigned b = wid; b < gridDim.x; b += 8) v += __ldcg(&partial[b * 28 + lane]);
+    __syncthreads();
+    if (lane < 28) red[wid][lane] = v;
+    __syncthreads();
+    if (threadIdx.x < 28) {
+      double t = red[0][threadIdx.x];
+      for (int w8 = 1; w8 < 8; ++w8) t += red[w8][threadIdx.x];
+      red[0][threadIdx.x] = t;
+    }
   }
   __syncthreads();
-  if (threadIdx.x == 0) { st->ticket = 0u; gn_finish(st, prm, red[0]); }
+  if (threadIdx.x == 0) {
+    const long long g1 = clock64();
+    st->ticket = 0u;
+    gn_finish(st, prm, red[0]);
+    st->dbg[16] = g1 - g0; st->dbg[17] = clock64() - g1;
+  }
 }
 
 struct Init16 { float m[16]; };

@@ -46,6 +46,7 @@ struct IcpState {                 // lives in device memory, one per context
   unsigned int ticket;            // last-block election of the GN reduction
   int num_iterations; int converged; double initial_cost, final_cost;
   b2lo_iter_trace trace[B2LO_MAX_ITERS];
+  long long dbg[32];                // clock64 stamps of the single-CTA phases (tools/gpu_phase_clocks.py)
 };
 
 struct IcpParams {                // kernel-argument POD
@@ -115,9 +116,9 @@ struct b2lo_map {
   // update scratch sized by the number of new points
   size_t upd_cap = 0;
   float4* u_pts = nullptr; int* u_pslot = nullptr; int* u_next = nullptr; int* u_isnew = nullptr; int* u_newrank = nullptr;
-  int* u_l1slot = nullptr; int* u_next1 = nullptr;
   b2::FEntry* a_tab = nullptr; int a_log2cap = 0;   // affected-L1 set of the current update
-  int* a_list = nullptr;                            // compacted affected slots / purge list
+  int* a_list = nullptr;                            // purge lists (4 x upd_cap)
+  int* a_slots = nullptr;                           // compacted slots of the affected-L1 set
   // cull scratch (sized by dense capacity)
   uint8_t* c_flag = nullptr; int* c_blkcnt = nullptr; int* c_blkoff = nullptr; int* c_removed = nullptr; int* c_aux = nullptr;
   int* c_l1work = nullptr;

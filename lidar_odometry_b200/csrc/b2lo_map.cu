@@ -24,13 +24,78 @@
 
 namespace b2 {
 
-enum { US_K = 0, US_S = 1, US_NWORK = 2, US_NNEW = 3, US_NAFF = 4, US_NPURGE = 5, US_KPURGE = 6, US_N0 = 7, US_ERR = 8, US_COUNT = 16 };
+enum { US_K = 0, US_S = 1, US_NWORK = 2, US_NNEW = 3, US_NAFF = 4, US_NPURGE = 5, US_KPURGE = 6, US_N0 = 7, US_ERR = 8, US_TICKET = 9, US_COUNT = 16 };
 enum { CT_N0 = 0, CT_N1 = 1, CT_TOMB0 = 2, CT_TOMB1 = 3, CT_ERR = 4, CT_SURF = 5 };
 constexpr int ERR_RANGE = 1, ERR_CAP = 2, ERR_INTERNAL = 4;
+constexpr int SIM_SMEM_K = 12000;  // (4k+2) ints <= 192 KB of dynamic shared memory
+constexpr int SIM_SMEM_BYTES = (4 * SIM_SMEM_K + 2) * (int)sizeof(int);
+
+__device__ __forceinline__ unsigned long long child_key(int px, int py, int pz, int f, int code) {
+  return key_morton(px * f + code % 3, py * f + (code / 3) % 3, pz * f + code / 9);
+}
+
+// Replay of k swap-with-last erases (in the given order) on a dense vector of size n, on indices only; whole CTA.
+// seq_pos[t-1]: ORIGINAL position of the t-th erased element.  Output fill[t] (at aux[3k+1+t]): original position of
+// the survivor that finally sits in the hole the t-th erase leaves below the new size s = n - k.
+//   loc[t]   : where the t-th erased element currently sits (>= s: tail position; -h: in the hole of erase h)
+//   occ*[q-s]: current occupant of tail position q (original position id, its erase time or 0)
+// Fast path (no erased element lives in the tail [s, n)): erase t moves original element n-t into hole t.
+__device__ void swap_erase_sim(int k, int n, const int* seq_pos, int* aux, int* smem, int smem_cap_k) {
+  const int s = n - k;
+  int tail = 0;
+  for (int t = threadIdx.x; t < k; t += blockDim.x) tail |= (seq_pos[t] >= s);
+  if (!__syncthreads_or(tail)) {
+    for (int t = 1 + threadIdx.x; t <= k; t += blockDim.x) aux[3 * k + 1 + t] = n - t;
+    __syncthreads();
+    return;
+  }
+  const bool in_smem = (k <= smem_cap_k);
+  int* loc = in_smem ? smem : aux;               // k+1
+  int* occ_id = loc + (k + 1);                   // k
+  int* occ_t = occ_id + k;                       // k
+  int* fill = occ_t + k;                         // k+1
+  for (int q = threadIdx.x; q < k; q += blockDim.x) { occ_id[q] = s + q; occ_t[q] = 0; }
+  __syncthreads();
+  for (int t = 1 + threadIdx.x; t <= k; t += blockDim.x) {
+    int P = seq_pos[t - 1];
+    if (P >= s) { loc[t] = P; occ_t[P - s] = t; } else loc[t] = -t;
+    fill[t] = -1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int t = 1; t <= k; ++t) {
+      int b = n - t;
+      int l = loc[t];
+      int yid = occ_id[b - s], yt = occ_t[b - s];
+      if (l >= 0) { if (l != b) { occ_id[l - s] = yid; occ_t[l - s] = yt; if (yt) loc[yt] = l; } }
+      else { fill[-l] = yid; if (yt) loc[yt] = l; }
+    }
+  }
+  __syncthreads();
+  if (in_smem) for (int t = 1 + threadIdx.x; t <= k; t += blockDim.x) aux[3 * k + 1 + t] = fill[t];
+  __syncthreads();
+}
+// apply the moves of a replay: hole seq_pos[t-1] (< s) <- element fill[t]; whole CTA
+__device__ void swap_erase_apply(const MapDev& M, int k, int s, const int* seq_pos, const int* aux) {
+  const int* fill = aux + 3 * k + 1;
+  for (int t = 1 + threadIdx.x; t <= k; t += blockDim.x) {
+    int dst = seq_pos[t - 1];
+    if (dst < 0 || dst >= s) continue;
+    int src = fill[t];
+    uint32_t sl = M.l0_slot[src];
+    M.l0_cent[dst] = M.l0_cent[src];
+    M.l0_key[dst] = M.l0_key[src];
+    M.l0_slot[dst] = sl;
+    M.l0_tab[sl].pos = (uint32_t)dst;
+  }
+}
 
 // ---- cull ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_cull_mark(MapDev M, int n0, float sx, float sy, float sz, float r2, uint8_t* flag, int* blkcnt) {
+// mark: ||c - sensor||^2 > r^2 (VoxelMap.cpp:146-158), per-tile counts; the last CTA scans the tile counts
+__global__ void __launch_bounds__(1024) k_cull_mark(MapDev M, int n0, float sx, float sy, float sz, float r2, uint8_t* flag, int* blkcnt, int* blkoff,
+                                                    int* us) {
   __shared__ int sm[40];
+  __shared__ int s_last;
   int ntiles = (n0 + 1023) / 1024;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     int pos = tile * 1024 + threadIdx.x;
@@ -45,19 +110,23 @@ __global__ void __launch_bounds__(1024) k_cull_mark(MapDev M, int n0, float sx, 
     block_excl_scan(mk, &tot, sm);
     if (threadIdx.x == 0) blkcnt[tile] = tot;
   }
-}
-__global__ void __launch_bounds__(1024) k_cull_scan(int n0, const int* blkcnt, int* blkoff, int* us) {
-  __shared__ int sm[40];
-  int ntiles = (n0 + 1023) / 1024, base = 0;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&us[US_TICKET], 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  int base = 0;
   for (int t0 = 0; t0 < ntiles; t0 += blockDim.x) {
     int t = t0 + threadIdx.x;
-    int c = t < ntiles ? blkcnt[t] : 0, tot;
+    int c = t < ntiles ? ((volatile int*)blkcnt)[t] : 0, tot;
     int e = block_excl_scan(c, &tot, sm);
     if (t < ntiles) blkoff[t] = base + e;
     base += tot;
   }
-  if (threadIdx.x == 0) { us[US_K] = base; us[US_S] = n0 - base; us[US_N0] = n0 - base; us[US_NWORK] = 0; }
+  if (threadIdx.x == 0) { us[US_K] = base; us[US_S] = n0 - base; us[US_N0] = n0 - base; us[US_NWORK] = 0; us[US_TICKET] = 0; }
 }
+// removed[] (ascending dense position) and the list of parents that lose children
 __global__ void __launch_bounds__(1024) k_cull_lists(MapDev M, int n0, const uint8_t* flag, const int* blkoff, int* us, int* removed, int* l1work) {
   __shared__ int sm[40];
   const int k = us[US_K];
@@ -67,74 +136,76 @@ __global__ void __launch_bounds__(1024) k_cull_lists(MapDev M, int n0, const uin
     int pos = tile * 1024 + threadIdx.x;
     int mk = (pos < n0) ? flag[pos] : 0, tot;
     int pre = blkoff[tile] + block_excl_scan(mk, &tot, sm);
-    if (pos >= n0) continue;
-    if (mk) {
-      removed[pre] = pos;
-      int x, y, z;
-      morton_key(M.l0_key[pos], x, y, z);
-      unsigned long long pk = key_morton(parent_coord(x, M.factor), parent_coord(y, M.factor), parent_coord(z, M.factor));
-      int s1 = l1_find(M, pk);
-      if (s1 >= 0 && atomicCAS(&M.t1_first[s1], INT_MAX, pre) == INT_MAX) l1work[atomicAdd(&us[US_NWORK], 1)] = s1;
-    }
+    if (pos >= n0 || !mk) continue;
+    removed[pre] = pos;
+    int x, y, z;
+    morton_key(M.l0_key[pos], x, y, z);
+    unsigned long long pk = key_morton(parent_coord(x, M.factor), parent_coord(y, M.factor), parent_coord(z, M.factor));
+    int s1 = l1_find(M, pk);
+    if (s1 >= 0 && atomicCAS(&M.l1_meta[s1].mark, 0, 1) == 0) l1work[atomicAdd(&us[US_NWORK], 1)] = s1;
   }
 }
-// one thread per parent that lost children: replay occupied_children.erase() in removal (= L0 dense) order
-__global__ void k_cull_unregister(MapDev M, const uint8_t* flag, int* us, const int* l1work) {
+// one CTA: (1) per affected parent replay occupied_children.erase() in removal (= L0 dense) order, one warp per parent,
+// one lane per child; (2) replay the k dense-vector erases on indices; (3) apply the moves, drop the hash entries
+__global__ void __launch_bounds__(1024) k_cull_fix(MapDev M, const uint8_t* flag, int* us, const int* l1work, const int* removed, int* aux, int n0) {
+  extern __shared__ int smem[];
+  const int k = us[US_K];
+  if (k == 0) return;
+  const int s = us[US_S];
   const int nwork = us[US_NWORK];
-  for (int wi = blockIdx.x * blockDim.x + threadIdx.x; wi < nwork; wi += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int wi = warp; wi < nwork; wi += nwarps) {
     int s1 = l1work[wi];
-    M.t1_first[s1] = INT_MAX;
     L1Meta* mt = &M.l1_meta[s1];
     unsigned long long k1 = M.l1_tab[s1].key;
     int px, py, pz;
     morton_key(k1 & KEY_MASK, px, py, pz);
     int n = mt->nchild;
-    int rpos[27]; uint8_t rcode[27]; int nr = 0;
-    for (int ci = 0; ci < n; ++ci) {
-      int code = mt->child[ci];
-      int cx = px * M.factor + code % 3, cy = py * M.factor + (code / 3) % 3, cz = pz * M.factor + code / 9;
-      int s0 = l0_find(M, key_morton(cx, cy, cz));
-      if (s0 < 0) continue;
-      int pos = (int)M.l0_tab[s0].pos;
-      if (flag[pos]) { rpos[nr] = pos; rcode[nr] = (uint8_t)code; ++nr; }
+    int code = lane < n ? mt->child[lane] : -1;
+    int rp = INT_MAX;  // dense position of this lane's child if it is being removed
+    if (code >= 0) {
+      int s0 = l0_find(M, child_key(px, py, pz, M.factor, code));
+      if (s0 >= 0) { int pos = (int)M.l0_tab[s0].pos; if (flag[pos]) rp = pos; }
     }
-    for (int a = 1; a < nr; ++a) {  // ascending dense position = removal order
-      int p = rpos[a]; uint8_t c = rcode[a]; int b = a - 1;
-      while (b >= 0 && rpos[b] > p) { rpos[b + 1] = rpos[b]; rcode[b + 1] = rcode[b]; --b; }
-      rpos[b + 1] = p; rcode[b + 1] = c;
-    }
+    unsigned rem = __ballot_sync(0xffffffffu, rp != INT_MAX);
+    int nr = __popc(rem);
+    // removal order = ascending dense position: rank of this lane's child among the removed ones
+    int myrank = 0;
+    for (int l = 0; l < 32; ++l) { int op = __shfl_sync(0xffffffffu, rp, l); if (op < rp) ++myrank; }
+    // gather the removed codes in removal order into lane 0 by rank
+    int ord_code[27];
     for (int a = 0; a < nr; ++a) {
-      int idx = 0;
-      while (idx < n && mt->child[idx] != rcode[a]) ++idx;
-      if (idx < n) { mt->child[idx] = mt->child[n - 1]; --n; }
+      unsigned m = __ballot_sync(0xffffffffu, rp != INT_MAX && myrank == a);
+      int src = __ffs(m) - 1;
+      ord_code[a] = __shfl_sync(0xffffffffu, code, src);
     }
-    mt->nchild = (uint8_t)n;
-    if (n < 5) k1 &= ~SURFEL_BIT;  // has_surfel = false, last_child_count kept (VoxelMap.cpp:90-92)
-    if (n == 0) { k1 = KEY_TOMB; atomicSub(&M.ctr[CT_N1], 1); atomicAdd(&M.ctr[CT_TOMB1], 1); }
-    M.l1_tab[s1].key = k1;
-  }
-}
-__global__ void k_cull_move(MapDev M, int* us, const int* removed, const int* aux) {
-  const int k = us[US_K];
-  const int s = us[US_S];
-  const int* fill = aux + 3 * k + 1;  // fill[t], t = 1..k (k_swap_erase_sim)
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < k; r += gridDim.x * blockDim.x) {
-    int pos = removed[r];
-    M.l0_tab[M.l0_slot[pos]].key = KEY_TOMB;
-    if (pos < s) {
-      int src = fill[r + 1];
-      uint32_t sl = M.l0_slot[src];
-      M.l0_cent[pos] = M.l0_cent[src];
-      M.l0_key[pos] = M.l0_key[src];
-      M.l0_slot[pos] = sl;
-      M.l0_tab[sl].pos = (uint32_t)pos;
+    if (lane == 0) {
+      for (int a = 0; a < nr; ++a) {
+        int idx = 0;
+        while (idx < n && mt->child[idx] != (uint8_t)ord_code[a]) ++idx;
+        if (idx < n) { mt->child[idx] = mt->child[n - 1]; --n; }
+      }
+      mt->nchild = (uint8_t)n;
+      mt->mark = 0;
+      if (n < 5) k1 &= ~SURFEL_BIT;  // has_surfel = false, last_child_count kept (VoxelMap.cpp:90-92)
+      if (n == 0) { k1 = KEY_TOMB; mt->last_child_count = 0; atomicSub(&M.ctr[CT_N1], 1); atomicAdd(&M.ctr[CT_TOMB1], 1); }
+      M.l1_tab[s1].key = k1;
     }
-    if (r == 0) atomicAdd(&M.ctr[CT_TOMB0], k);
   }
+  __syncthreads();
+  swap_erase_sim(k, n0, removed, aux, smem, SIM_SMEM_K);
+  for (int r = threadIdx.x; r < k; r += blockDim.x) {  // drop the hash entries of the removed voxels (before slots move)
+    L0Entry* e = &M.l0_tab[M.l0_slot[removed[r]]];
+    e->key = KEY_TOMB;
+  }
+  __syncthreads();
+  swap_erase_apply(M, k, s, removed, aux);
+  if (threadIdx.x == 0) atomicAdd(&M.ctr[CT_TOMB0], k);
 }
 
 // ---- insert ---------------------------------------------------------------------------------------------
-__global__ void k_ins_probe(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_m, int* us, int* pslot, int* nxt, FEntry* atab, int alog2) {
+__global__ void k_ins_probe(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_m, int* us, int* pslot, int* nxt, FEntry* atab, int alog2,
+                            int* alist) {
   const int m = *d_m;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
     float4 p = pts[i];
@@ -144,9 +215,10 @@ __global__ void k_ins_probe(MapDev M, const float4* __restrict__ pts, const int*
     bool ins;
     int s0 = l0_find_or_insert(M, key_morton(x, y, z), &ins);
     if (s0 < 0) { atomicOr(&us[US_ERR], ERR_CAP); pslot[i] = -1; continue; }
-    atomicMin(&M.t0_first[s0], i);
-    atomicAdd(&M.t0_cnt[s0], 1);
-    nxt[i] = atomicExch(&M.t0_head[s0], i);
+    L0Entry* e = &M.l0_tab[s0];
+    atomicMin(&e->first, (unsigned)i);
+    atomicAdd(&e->cnt, 1);                 // idle value -1: holds count - 1
+    nxt[i] = atomicExch(&e->head, i);      // idle value -1
     pslot[i] = s0;
     // affected_L1.insert(PointToVoxelKey(point, 1))  (VoxelMap.cpp:178-179) — float division by voxel*3
     unsigned long long ak = key_morton(ax, ay, az);
@@ -154,7 +226,11 @@ __global__ void k_ins_probe(MapDev M, const float4* __restrict__ pts, const int*
     for (;;) {
       unsigned long long kk = *((volatile unsigned long long*)&atab[h].key);
       if (kk == ak) break;
-      if (kk == KEY_EMPTY) { unsigned long long old = atomicCAS(&atab[h].key, KEY_EMPTY, ak); if (old == KEY_EMPTY || old == ak) break; }
+      if (kk == KEY_EMPTY) {
+        unsigned long long old = atomicCAS(&atab[h].key, KEY_EMPTY, ak);
+        if (old == KEY_EMPTY) { alist[atomicAdd(&us[US_NAFF], 1)] = (int)h; break; }
+        if (old == ak) break;
+      }
       h = (h + 1) & mask;
     }
     atomicMin(&atab[h].first, (unsigned)i);
@@ -167,9 +243,11 @@ __global__ void k_ins_apply(MapDev M, const float4* __restrict__ pts, const int*
   const int m = *d_m;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
     int s0 = pslot[i];
-    if (s0 < 0 || M.t0_first[s0] != i) { isnew[i] = 0; continue; }
-    int cnt = M.t0_cnt[s0];
-    uint32_t pos = M.l0_tab[s0].pos;
+    if (s0 < 0) { isnew[i] = 0; continue; }
+    L0Entry* e = &M.l0_tab[s0];
+    if (e->first != (unsigned)i) { isnew[i] = 0; continue; }
+    int cnt = e->cnt + 1;
+    uint32_t pos = e->pos;
     float cx, cy, cz; int n;
     if (pos == POS_PENDING) { n = 0; cx = cy = cz = 0.0f; }
     else { float4 c = M.l0_cent[pos]; cx = c.x; cy = c.y; cz = c.z; n = __float_as_int(c.w); }
@@ -194,32 +272,43 @@ __global__ void k_ins_apply(MapDev M, const float4* __restrict__ pts, const int*
     if (cnt == 1) add(i);
     else if (cnt <= 32) {
       int idx[32]; int q = 0;
-      for (int j = M.t0_head[s0]; j >= 0 && q < 32; j = nxt[j]) idx[q++] = j;
+      for (int j = e->head; j >= 0 && q < 32; j = nxt[j]) idx[q++] = j;
       for (int a = 1; a < q; ++a) { int v = idx[a], b = a - 1; while (b >= 0 && idx[b] > v) { idx[b + 1] = idx[b]; --b; } idx[b + 1] = v; }
       for (int a = 0; a < q; ++a) add(idx[a]);
     } else {
       int last = -1;
       for (int a = 0; a < cnt; ++a) {  // selection by repeated list walks (pathological multiplicities only)
         int best = INT_MAX;
-        for (int j = M.t0_head[s0]; j >= 0; j = nxt[j]) if (j > last && j < best) best = j;
+        for (int j = e->head; j >= 0; j = nxt[j]) if (j > last && j < best) best = j;
         add(best); last = best;
       }
     }
     float4 out = make_float4(cx, cy, cz, __int_as_float(n));
     if (pos == POS_PENDING) { newc[i] = out; isnew[i] = 1; }
     else { M.l0_cent[pos] = out; isnew[i] = 0; }
-    M.t0_first[s0] = INT_MAX; M.t0_cnt[s0] = 0; M.t0_head[s0] = -1;
+    e->first = 0xFFFFFFFFu; e->cnt = -1; e->head = -1;  // scratch back to idle
   }
 }
-__global__ void __launch_bounds__(1024) k_ins_scan(MapDev M, const int* __restrict__ d_m, const int* isnew, int* newrank, int* us) {
+// one CTA: rank of every new voxel in first-seen order (4 points per thread); the rank is also left in the voxel's
+// hash entry so that siblings can order themselves (k_ins_place)
+__global__ void __launch_bounds__(1024) k_ins_scan(MapDev M, const int* __restrict__ d_m, const int* isnew, const int* pslot, int* newrank, int* us) {
   __shared__ int sm[40];
   const int m = *d_m;
   int base = 0;
-  for (int t0 = 0; t0 < m; t0 += blockDim.x) {
-    int i = t0 + threadIdx.x;
-    int f = i < m ? isnew[i] : 0, tot;
-    int e = block_excl_scan(f, &tot, sm);
-    if (i < m) newrank[i] = base + e;
+  for (int t0 = 0; t0 < m; t0 += 4 * blockDim.x) {
+    const int i0 = t0 + 4 * threadIdx.x;
+    int f[4], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { f[k] = (i0 + k < m) ? isnew[i0 + k] : 0; sum += f[k]; }
+    int tot;
+    int e = base + block_excl_scan(sum, &tot, sm);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i0 + k < m) {
+        newrank[i0 + k] = e;
+        if (f[k]) { M.l0_tab[pslot[i0 + k]].rank = e; ++e; }
+      }
+    }
     base += tot;
   }
   if (threadIdx.x == 0) {
@@ -227,99 +316,102 @@ __global__ void __launch_bounds__(1024) k_ins_scan(MapDev M, const int* __restri
     if ((long long)us[US_N0] + base > (long long)M.l0_cap) atomicOr(&us[US_ERR], ERR_CAP);
   }
 }
-__global__ void k_ins_place(MapDev M, const int* __restrict__ d_m, int* us, const int* pslot, const int* isnew, const int* newrank, const float4* newc,
-                            int* l1slot, int* nxt1) {
+// one warp per new voxel: append it to the dense vector, find-or-create its parent and place it in the parent's child
+// list in creation order (RegisterToParent, VoxelMap.cpp:77-80).  Lane c probes sibling cell c of the parent: the
+// position is (#siblings that already existed) + (#new siblings created earlier), so nobody has to read nchild while
+// it is being updated; the first new sibling writes the new count.
+__global__ void __launch_bounds__(256) k_ins_place(MapDev M, const int* __restrict__ d_m, int* us, const int* pslot, const int* isnew,
+                                                   const int* newrank, const float4* newc) {
   const int m = *d_m;
   if (us[US_ERR] & ERR_CAP) return;
   const int base = us[US_N0];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = warp; i < m; i += nwarps) {
     if (!isnew[i]) continue;
-    int s0 = pslot[i];
-    int pos = base + newrank[i];
-    unsigned long long key = M.l0_tab[s0].key;
-    M.l0_cent[pos] = newc[i];
-    M.l0_key[pos] = key;
-    M.l0_slot[pos] = (uint32_t)s0;
-    M.l0_tab[s0].pos = (uint32_t)pos;
+    const int s0 = pslot[i];
+    const int myrank = newrank[i];
+    const int pos = base + myrank;
+    const unsigned long long key = M.l0_tab[s0].key;
     int x, y, z;
     morton_key(key, x, y, z);
-    bool ins;
-    int s1 = l1_find_or_insert(M, key_morton(parent_coord(x, M.factor), parent_coord(y, M.factor), parent_coord(z, M.factor)), &ins);
-    l1slot[i] = s1;
-    if (s1 < 0) { atomicOr(&us[US_ERR], ERR_CAP); continue; }
-    if (ins) {
+    const int px = parent_coord(x, M.factor), py = parent_coord(y, M.factor), pz = parent_coord(z, M.factor);
+    const int mycode = (x - px * M.factor) + 3 * (y - py * M.factor) + 9 * (z - pz * M.factor);
+    int s1 = -1;
+    if (lane == 0) {
+      M.l0_cent[pos] = newc[i];
+      M.l0_key[pos] = key;
+      M.l0_slot[pos] = (uint32_t)s0;
+      M.l0_tab[s0].pos = (uint32_t)pos;
+      bool ins;
+      s1 = l1_find_or_insert(M, key_morton(px, py, pz), &ins);  // a fresh slot has zeroed meta: no children, no surfel
+      if (s1 < 0) atomicOr(&us[US_ERR], ERR_CAP);
+      else if (ins) atomicAdd(&M.ctr[CT_N1], 1);
+    }
+    s1 = __shfl_sync(0xffffffffu, s1, 0);
+    if (s1 < 0) continue;
+    int is_old = 0, is_new = 0, earlier = 0;
+    if (lane < 27 && lane != mycode) {
+      int sc = l0_find(M, child_key(px, py, pz, M.factor, lane));
+      if (sc >= 0) {
+        int rk = M.l0_tab[sc].rank;
+        if (rk < 0) is_old = 1; else { is_new = 1; earlier = rk < myrank; }
+      }
+    }
+    const int n_old = __popc(__ballot_sync(0xffffffffu, is_old));
+    const int n_new = __popc(__ballot_sync(0xffffffffu, is_new)) + 1;
+    const int n_before = __popc(__ballot_sync(0xffffffffu, earlier));
+    if (lane == 0) {
       L1Meta* mt = &M.l1_meta[s1];
-      mt->nchild = 0; mt->planarity = 1.0f; mt->last_child_count = 0;
-      M.l1_tab[s1].n[0] = 0.0f; M.l1_tab[s1].n[1] = 0.0f; M.l1_tab[s1].n[2] = 0.0f;
-      M.l1_tab[s1].c[0] = 0.0f; M.l1_tab[s1].c[1] = 0.0f; M.l1_tab[s1].c[2] = 0.0f;
-      atomicAdd(&M.ctr[CT_N1], 1);
+      if (n_old + n_before < 27) mt->child[n_old + n_before] = (uint8_t)mycode;
+      if (n_before == 0) mt->nchild = (uint8_t)(n_old + n_new);
     }
-    atomicMin(&M.t1_first[s1], newrank[i]);
-    nxt1[i] = atomicExch(&M.t1_head[s1], i);
   }
 }
-// per parent: append the new children in creation order (RegisterToParent, VoxelMap.cpp:77-80)
-__global__ void k_reg_children(MapDev M, const int* __restrict__ d_m, int* us, const int* pslot, const int* isnew, const int* newrank, const int* l1slot,
-                               const int* nxt1) {
-  const int m = *d_m;
-  if (us[US_ERR] & ERR_CAP) return;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
-    if (!isnew[i]) continue;
-    int s1 = l1slot[i];
-    if (s1 < 0 || M.t1_first[s1] != newrank[i]) continue;
-    int px, py, pz;
-    morton_key(M.l1_tab[s1].key & KEY_MASK, px, py, pz);
-    int rk[27]; uint8_t code[27]; int q = 0;
-    for (int j = M.t1_head[s1]; j >= 0 && q < 27; j = nxt1[j]) {
-      int x, y, z;
-      morton_key(M.l0_tab[pslot[j]].key, x, y, z);
-      rk[q] = newrank[j];
-      code[q] = (uint8_t)((x - px * M.factor) + 3 * (y - py * M.factor) + 9 * (z - pz * M.factor));
-      ++q;
-    }
-    for (int a = 1; a < q; ++a) {
-      int v = rk[a]; uint8_t c = code[a]; int b = a - 1;
-      while (b >= 0 && rk[b] > v) { rk[b + 1] = rk[b]; code[b + 1] = code[b]; --b; }
-      rk[b + 1] = v; code[b + 1] = c;
-    }
-    L1Meta* mt = &M.l1_meta[s1];
-    int n = mt->nchild;
-    for (int a = 0; a < q && n < 27; ++a) mt->child[n++] = code[a];
-    mt->nchild = (uint8_t)n;
-    M.t1_first[s1] = INT_MAX; M.t1_head[s1] = -1;
-  }
-}
-
 // ---- surfels ----------------------------------------------------------------------------------------------
-__global__ void k_surfel(MapDev M, const FEntry* __restrict__ atab, int alog2, int* us, int* plist, unsigned int* pfirst) {
-  if (us[US_ERR] & ERR_CAP) return;
-  const int acap = 1 << alog2;
-  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < acap; a += gridDim.x * blockDim.x) {
-    unsigned long long ak = atab[a].key;
-    if (ak == KEY_EMPTY) continue;
+// one warp per affected L1 (VoxelMap.cpp:187-261): lane c fetches child c of the child set; lane 0 sums in child-set
+// order (f32, as the reference), runs the Jacobi SVD and applies the planarity gate.  Non-planar parents are queued
+// for the purge.  The affected-set entry is cleared on the way out (the set is self-cleaning).
+__global__ void __launch_bounds__(256) k_surfel(MapDev M, FEntry* atab, const int* __restrict__ alist, int* us, int* plist, unsigned int* pfirst) {
+  const int naff = us[US_NAFF];
+  const bool skip = (us[US_ERR] & ERR_CAP) || !M.compute_surfels;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int a = warp; a < naff; a += nwarps) {
+    const int h = alist[a];
+    const unsigned long long ak = atab[h].key;
+    const unsigned int first = atab[h].first;
+    __syncwarp();
+    if (lane == 0) { atab[h].key = KEY_EMPTY; atab[h].first = 0xFFFFFFFFu; atab[h].cnt = -1; }
+    if (skip) continue;
     int s1 = l1_find(M, ak);
     if (s1 < 0) continue;
     L1Meta* mt = &M.l1_meta[s1];
-    unsigned long long k1 = M.l1_tab[s1].key;
-    int N = mt->nchild;
-    if (N < 5) { M.l1_tab[s1].key = k1 & ~SURFEL_BIT; continue; }
+    const unsigned long long k1 = M.l1_tab[s1].key;
+    const int N = mt->nchild;
+    if (N < 5) { if (lane == 0) M.l1_tab[s1].key = k1 & ~SURFEL_BIT; continue; }
     if ((k1 & SURFEL_BIT) && mt->last_child_count == N) continue;  // incremental skip (VoxelMap.cpp:202-205)
     int px, py, pz;
     morton_key(k1 & KEY_MASK, px, py, pz);
-    float cents[27 * 3]; int nc = 0;
-    for (int ci = 0; ci < N; ++ci) {
-      int code = mt->child[ci];
-      int s0 = l0_find(M, key_morton(px * M.factor + code % 3, py * M.factor + (code / 3) % 3, pz * M.factor + code / 9));
-      if (s0 < 0) continue;
-      float4 c = M.l0_cent[M.l0_tab[s0].pos];
-      cents[nc * 3] = c.x; cents[nc * 3 + 1] = c.y; cents[nc * 3 + 2] = c.z; ++nc;
+    float cx = 0.0f, cy = 0.0f, cz = 0.0f;
+    int have = 0;
+    if (lane < N) {
+      int s0 = l0_find(M, child_key(px, py, pz, M.factor, mt->child[lane]));
+      if (s0 >= 0) { float4 c = M.l0_cent[M.l0_tab[s0].pos]; cx = c.x; cy = c.y; cz = c.z; have = 1; }
     }
+    const unsigned hm = __ballot_sync(0xffffffffu, have);
+    float cents[27 * 3]; int nc = 0;
+    for (int c = 0; c < N; ++c) {  // uniform loop: every lane takes part in the shuffles
+      float vx = __shfl_sync(0xffffffffu, cx, c), vy = __shfl_sync(0xffffffffu, cy, c), vz = __shfl_sync(0xffffffffu, cz, c);
+      if ((hm >> c) & 1u) { cents[nc * 3] = vx; cents[nc * 3 + 1] = vy; cents[nc * 3 + 2] = vz; ++nc; }
+    }
+    if (lane != 0) continue;
     if (nc < 3) { M.l1_tab[s1].key = k1 & ~SURFEL_BIT; continue; }
     float mu[3], nrm[3], plan;
     fit_plane(cents, nc, mu, nrm, &plan);
     if (plan > M.planarity_thr) {  // not planar: the parent and all its children go (VoxelMap.cpp:244-253)
       int idx = atomicAdd(&us[US_NPURGE], 1);
-      plist[idx] = s1; pfirst[idx] = atab[a].first;
+      plist[idx] = s1; pfirst[idx] = first;
       continue;
     }
     L1Entry* e = &M.l1_tab[s1];
@@ -344,8 +436,7 @@ __global__ void k_surfel_all(MapDev M) {
     morton_key(k1 & KEY_MASK, px, py, pz);
     float cents[27 * 3]; int nc = 0;
     for (int ci = 0; ci < N; ++ci) {
-      int code = mt->child[ci];
-      int s0 = l0_find(M, key_morton(px * M.factor + code % 3, py * M.factor + (code / 3) % 3, pz * M.factor + code / 9));
+      int s0 = l0_find(M, child_key(px, py, pz, M.factor, mt->child[ci]));
       if (s0 < 0) continue;
       float4 c = M.l0_cent[M.l0_tab[s0].pos];
       cents[nc * 3] = c.x; cents[nc * 3 + 1] = c.y; cents[nc * 3 + 2] = c.z; ++nc;
@@ -373,12 +464,25 @@ __global__ void k_xform_l0(MapDev M, int n0, Rt12 T, float4* out, int* d_n) {
   if (blockIdx.x == 0 && threadIdx.x == 0) *d_n = n0;
 }
 
-// order the purged parents by the position of their key in affected_L1 (= first touching point), lay out
-// the erase sequence (children in child-set order) and drop the hash entries
-__global__ void __launch_bounds__(1024) k_purge_order(MapDev M, int* us, const int* plist, const unsigned int* pfirst, int* pord, int* poff) {
+// one CTA closes the update: order the purged parents by the position of their key in affected_L1 (= first touching
+// point), lay out the erase sequence (children in child-set order, one warp per parent), replay the swap-erases on
+// indices, apply the moves, publish the counters.
+__global__ void __launch_bounds__(1024) k_upd_close(MapDev M, int* us, const int* plist, const unsigned int* pfirst, int* pord, int* poff, int* seq_pos,
+                                                    int* aux, int purge_ran, const int* __restrict__ d_m, const int* __restrict__ pslot,
+                                                    const int* __restrict__ isnew) {
+  extern __shared__ int smem[];
   __shared__ int sm[40];
-  const int P = us[US_NPURGE];
-  if (P == 0) { if (threadIdx.x == 0) us[US_KPURGE] = 0; return; }
+  __shared__ int s_k;
+  {  // creation ranks are only meaningful inside one update: back to idle
+    const int m = *d_m;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) if (isnew[i]) M.l0_tab[pslot[i]].rank = -1;
+  }
+  const int P = purge_ran ? us[US_NPURGE] : 0;
+  const int n_all = us[US_N0] + ((us[US_ERR] & ERR_CAP) ? 0 : us[US_NNEW]);
+  if (P == 0) {
+    if (threadIdx.x == 0) { M.ctr[CT_N0] = n_all; M.ctr[CT_ERR] = us[US_ERR]; }
+    return;
+  }
   for (int t = threadIdx.x; t < P; t += blockDim.x) {
     unsigned int f = pfirst[t]; int r = 0;
     for (int u = 0; u < P; ++u) r += (pfirst[u] < f);
@@ -393,97 +497,39 @@ __global__ void __launch_bounds__(1024) k_purge_order(MapDev M, int* us, const i
     if (t < P) poff[t] = base + e;
     base += tot;
   }
-  if (threadIdx.x == 0) us[US_KPURGE] = base;
-}
-__global__ void k_purge_seq(MapDev M, int* us, const int* pord, const int* poff, int* seq_pos) {
-  const int P = us[US_NPURGE];
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < P; t += gridDim.x * blockDim.x) {
+  if (threadIdx.x == 0) s_k = base;
+  __syncthreads();
+  const int k = s_k;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int t = warp; t < P; t += nwarps) {
     int s1 = pord[t];
     L1Meta* mt = &M.l1_meta[s1];
     int px, py, pz;
     morton_key(M.l1_tab[s1].key & KEY_MASK, px, py, pz);
     int N = mt->nchild, o = poff[t];
-    for (int ci = 0; ci < N; ++ci) {
-      int code = mt->child[ci];
-      int s0 = l0_find(M, key_morton(px * M.factor + code % 3, py * M.factor + (code / 3) % 3, pz * M.factor + code / 9));
+    if (lane < N) {
+      int s0 = l0_find(M, child_key(px, py, pz, M.factor, mt->child[lane]));
       int pos = -1;
       if (s0 >= 0) { pos = (int)M.l0_tab[s0].pos; M.l0_tab[s0].key = KEY_TOMB; }
       else atomicOr(&us[US_ERR], ERR_INTERNAL);
-      seq_pos[o + ci] = pos;
+      seq_pos[o + lane] = pos;
     }
-    M.l1_tab[s1].key = KEY_TOMB;
-    mt->nchild = 0;
-    atomicSub(&M.ctr[CT_N1], 1); atomicAdd(&M.ctr[CT_TOMB1], 1);
-  }
-}
-// Replay of k swap-with-last erases (in the given order) on a dense vector of size n, on indices only.
-// seq_pos[t-1]: ORIGINAL position of the t-th erased element.  Output fill[t] (at aux[3k+1+t]): original position of
-// the survivor that finally sits in the hole the t-th erase leaves below the new size s = n - k.
-//   loc[t]   : where the t-th erased element currently sits (>= s: tail position; -h: in the hole of erase h)
-//   occ*[q-s]: current occupant of tail position q (original position id, its erase time or 0)
-// Fast path (no erased element lives in the tail [s, n)): erase t moves original element n-t into hole t.
-__global__ void k_swap_erase_sim(const int* us, int k_slot, int n_fixed, const int* seq_pos, int* aux, int aux_cap_k) {
-  extern __shared__ int smem[];
-  const int k = us[k_slot];
-  if (k == 0) return;
-  const int n = n_fixed >= 0 ? n_fixed : us[US_N0] + us[US_NNEW];
-  const int s = n - k;
-  int tail = 0;
-  for (int t = threadIdx.x; t < k; t += blockDim.x) tail |= (seq_pos[t] >= s);
-  if (!__syncthreads_or(tail)) {
-    for (int t = 1 + threadIdx.x; t <= k; t += blockDim.x) aux[3 * k + 1 + t] = n - t;
-    return;
-  }
-  const bool in_smem = (k <= aux_cap_k);
-  int* loc = in_smem ? smem : aux;               // k+1
-  int* occ_id = loc + (k + 1);                   // k
-  int* occ_t = occ_id + k;                       // k
-  int* fill = occ_t + k;                         // k+1
-  for (int q = threadIdx.x; q < k; q += blockDim.x) { occ_id[q] = s + q; occ_t[q] = 0; }
-  __syncthreads();
-  for (int t = 1 + threadIdx.x; t <= k; t += blockDim.x) {
-    int P = seq_pos[t - 1];
-    if (P >= s) { loc[t] = P; occ_t[P - s] = t; } else loc[t] = -t;
-    fill[t] = -1;
+    __syncwarp();
+    if (lane == 0) {
+      M.l1_tab[s1].key = KEY_TOMB;
+      mt->nchild = 0; mt->last_child_count = 0;
+      atomicSub(&M.ctr[CT_N1], 1); atomicAdd(&M.ctr[CT_TOMB1], 1);
+    }
   }
   __syncthreads();
+  swap_erase_sim(k, n_all, seq_pos, aux, smem, SIM_SMEM_K);
+  swap_erase_apply(M, k, n_all - k, seq_pos, aux);
   if (threadIdx.x == 0) {
-    for (int t = 1; t <= k; ++t) {
-      int b = n - t;
-      int l = loc[t];
-      int yid = occ_id[b - s], yt = occ_t[b - s];
-      if (l >= 0) { if (l != b) { occ_id[l - s] = yid; occ_t[l - s] = yt; if (yt) loc[yt] = l; } }
-      else { fill[-l] = yid; if (yt) loc[yt] = l; }
-    }
+    M.ctr[CT_N0] = n_all - k;
+    atomicAdd(&M.ctr[CT_TOMB0], k);
+    M.ctr[CT_ERR] = us[US_ERR];
+    us[US_KPURGE] = k;
   }
-  __syncthreads();
-  if (in_smem) for (int t = 1 + threadIdx.x; t <= k; t += blockDim.x) aux[3 * k + 1 + t] = fill[t];
-}
-__global__ void k_purge_apply(MapDev M, int* us, const int* seq_pos, const int* aux) {
-  const int k = us[US_KPURGE];
-  if (k == 0) { if (blockIdx.x == 0 && threadIdx.x == 0) us[US_N0] = us[US_N0] + us[US_NNEW]; return; }
-  const int n = us[US_N0] + us[US_NNEW];
-  const int s = n - k;
-  const int* fill = aux + 3 * k + 1;
-  for (int t = 1 + blockIdx.x * blockDim.x + threadIdx.x; t <= k; t += gridDim.x * blockDim.x) {
-    int dst = seq_pos[t - 1];
-    if (dst < 0 || dst >= s) continue;
-    int src = fill[t];
-    uint32_t sl = M.l0_slot[src];
-    M.l0_cent[dst] = M.l0_cent[src];
-    M.l0_key[dst] = M.l0_key[src];
-    M.l0_slot[dst] = sl;
-    M.l0_tab[sl].pos = (uint32_t)dst;
-  }
-}
-__global__ void k_upd_finish(MapDev M, int* us, int purge_ran) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  int n;
-  if (us[US_ERR] & ERR_CAP) n = us[US_N0];
-  else if (purge_ran) { int k = us[US_KPURGE]; n = (k == 0) ? us[US_N0] : us[US_N0] + us[US_NNEW] - k; if (k) atomicAdd(&M.ctr[CT_TOMB0], k); }
-  else n = us[US_N0] + us[US_NNEW];
-  M.ctr[CT_N0] = n;
-  M.ctr[CT_ERR] = us[US_ERR];
 }
 
 // ---- table maintenance --------------------------------------------------------------------------------------
@@ -579,15 +625,9 @@ static int alloc_l0_table(b2lo_map* m, int log2cap) {
   int rc;
   size_t cap = 1ull << log2cap;
   if ((rc = dmalloc(&d.l0_tab, cap))) return rc;
-  if ((rc = dmalloc(&d.t0_first, cap))) return rc;
-  if ((rc = dmalloc(&d.t0_cnt, cap))) return rc;
-  if ((rc = dmalloc(&d.t0_head, cap))) return rc;
   d.l0_log2cap = log2cap; m->tcap0 = cap;
   cudaStream_t st = m->ctx->stream;
-  B2_CUDA(cudaMemsetAsync(d.l0_tab, 0xFF, cap * sizeof(L0Entry), st));
-  m->ctx->launches += fill_int(st, d.t0_first, cap, INT_MAX);
-  B2_CUDA(cudaMemsetAsync(d.t0_cnt, 0, cap * sizeof(int), st));
-  B2_CUDA(cudaMemsetAsync(d.t0_head, 0xFF, cap * sizeof(int), st));
+  B2_CUDA(cudaMemsetAsync(d.l0_tab, 0xFF, cap * sizeof(L0Entry), st));  // key EMPTY, pos PENDING, scratch idle
   return B2LO_OK;
 }
 static int alloc_l1_table(b2lo_map* m, int log2cap) {
@@ -596,14 +636,10 @@ static int alloc_l1_table(b2lo_map* m, int log2cap) {
   size_t cap = 1ull << log2cap;
   if ((rc = dmalloc(&d.l1_tab, cap))) return rc;
   if ((rc = dmalloc(&d.l1_meta, cap))) return rc;
-  if ((rc = dmalloc(&d.t1_first, cap))) return rc;
-  if ((rc = dmalloc(&d.t1_head, cap))) return rc;
   d.l1_log2cap = log2cap; m->tcap1 = cap;
   cudaStream_t st = m->ctx->stream;
   B2_CUDA(cudaMemsetAsync(d.l1_tab, 0xFF, cap * sizeof(L1Entry), st));
   B2_CUDA(cudaMemsetAsync(d.l1_meta, 0, cap * sizeof(L1Meta), st));
-  m->ctx->launches += fill_int(st, d.t1_first, cap, INT_MAX);
-  B2_CUDA(cudaMemsetAsync(d.t1_head, 0xFF, cap * sizeof(int), st));
   return B2LO_OK;
 }
 
@@ -669,10 +705,11 @@ int map_reserve(b2lo_map* m, size_t need_l0, size_t need_upd) {
     while (ncap < need_upd) ncap *= 2;
     B2_CUDA(cudaStreamSynchronize(st));
     if ((rc = dmalloc(&m->u_pts, ncap)) || (rc = dmalloc(&m->u_pslot, ncap)) || (rc = dmalloc(&m->u_next, ncap)) || (rc = dmalloc(&m->u_isnew, ncap)) ||
-        (rc = dmalloc(&m->u_newrank, ncap)) || (rc = dmalloc(&m->u_l1slot, ncap)) || (rc = dmalloc(&m->u_next1, ncap)))
+        (rc = dmalloc(&m->u_newrank, ncap)))
       return rc;
     m->a_log2cap = ceil_log2(ncap * 2);
-    if ((rc = dmalloc(&m->a_tab, (size_t)1 << m->a_log2cap)) || (rc = dmalloc(&m->a_list, ncap * 4 + 16))) return rc;
+    if ((rc = dmalloc(&m->a_tab, (size_t)1 << m->a_log2cap)) || (rc = dmalloc(&m->a_list, ncap * 4 + 16)) || (rc = dmalloc(&m->a_slots, ncap + 16))) return rc;
+    B2_CUDA(cudaMemsetAsync(m->a_tab, 0xFF, sizeof(FEntry) << m->a_log2cap, st));  // the affected set cleans itself afterwards (k_surfel)
     // purge scratch: up to 27 children per affected parent
     m->p_cap = ncap * 27;
     if ((rc = dmalloc(&m->p_seq, m->p_cap + 16)) || (rc = dmalloc(&m->p_aux, m->p_cap * 4 + 16))) return rc;
@@ -685,9 +722,6 @@ static int grid_for(size_t n, int threads) { size_t b = (n + threads - 1) / thre
 
 // UpdateVoxelMap on a world-frame cloud already on the device (float4 stream).  n_cap = host-known upper
 // bound of *d_n.  Ends with a counter read-back (one synchronisation).
-constexpr int SIM_SMEM_K = 12000;  // (4k+2) ints <= 192 KB of dynamic shared memory
-constexpr int SIM_SMEM_BYTES = (4 * SIM_SMEM_K + 2) * (int)sizeof(int);
-
 int map_update_dev(b2lo_map* m, const float4* d_world, const int* d_n, size_t n_cap, const float sensor[3], float radius_sq, int rehash) {
   b2lo_ctx* ctx = m->ctx;
   if (n_cap == 0) return B2LO_S_EMPTY;
@@ -697,7 +731,8 @@ int map_update_dev(b2lo_map* m, const float4* d_world, const int* d_n, size_t n_
   cudaStream_t st = ctx->stream;
   int* us = m->u_state;
   if (!ctx->sim_attr_set) {
-    B2_CUDA(cudaFuncSetAttribute(k_swap_erase_sim, cudaFuncAttributeMaxDynamicSharedMemorySize, SIM_SMEM_BYTES));
+    B2_CUDA(cudaFuncSetAttribute(k_cull_fix, cudaFuncAttributeMaxDynamicSharedMemorySize, SIM_SMEM_BYTES));
+    B2_CUDA(cudaFuncSetAttribute(k_upd_close, cudaFuncAttributeMaxDynamicSharedMemorySize, SIM_SMEM_BYTES));
     ctx->sim_attr_set = true;
   }
   prof_begin(ctx, PS_MAP);
@@ -705,40 +740,35 @@ int map_update_dev(b2lo_map* m, const float4* d_world, const int* d_n, size_t n_
   const int n0 = (int)m->n0;
   if (n0 > 0 && !rehash) {
     int tiles = (n0 + 1023) / 1024;
-    int g = tiles > 1184 ? 1184 : tiles;
-    k_cull_mark<<<g, 1024, 0, st>>>(d, n0, sensor[0], sensor[1], sensor[2], radius_sq, m->c_flag, m->c_blkcnt);
-    k_cull_scan<<<1, 1024, 0, st>>>(n0, m->c_blkcnt, m->c_blkoff, us);
+    int g = tiles > ctx->sm_count ? ctx->sm_count : tiles;
+    k_cull_mark<<<g, 1024, 0, st>>>(d, n0, sensor[0], sensor[1], sensor[2], radius_sq, m->c_flag, m->c_blkcnt, m->c_blkoff, us);
     k_cull_lists<<<g, 1024, 0, st>>>(d, n0, m->c_flag, m->c_blkoff, us, m->c_removed, m->c_l1work);
-    k_cull_unregister<<<grid_for(n0 / 8 + 1, 128), 128, 0, st>>>(d, m->c_flag, us, m->c_l1work);
-    k_swap_erase_sim<<<1, 256, SIM_SMEM_BYTES, st>>>(us, US_K, n0, m->c_removed, m->c_aux, SIM_SMEM_K);
-    k_cull_move<<<grid_for(n0 / 4 + 1, 256), 256, 0, st>>>(d, us, m->c_removed, m->c_aux);
-    ctx->launches += 6;
+    k_cull_fix<<<1, 1024, SIM_SMEM_BYTES, st>>>(d, m->c_flag, us, m->c_l1work, m->c_removed, m->c_aux, n0);
+    ctx->launches += 3;
   }
-  B2_CUDA(cudaMemsetAsync(m->a_tab, 0xFF, sizeof(FEntry) << m->a_log2cap, st));
   int gm = grid_for(n_cap, 256);
+  int gw = grid_for(n_cap * 32, 256);   // one warp per point
   int* plist = m->a_list; unsigned int* pfirst = reinterpret_cast<unsigned int*>(m->a_list + m->upd_cap);
   int* pord = m->a_list + 2 * m->upd_cap; int* poff = m->a_list + 3 * m->upd_cap;
-  k_ins_probe<<<gm, 256, 0, st>>>(d, d_world, d_n, us, m->u_pslot, m->u_next, m->a_tab, m->a_log2cap);
+  k_ins_probe<<<gm, 256, 0, st>>>(d, d_world, d_n, us, m->u_pslot, m->u_next, m->a_tab, m->a_log2cap, m->a_slots);
   k_ins_apply<<<gm, 256, 0, st>>>(d, d_world, d_n, m->u_pslot, m->u_next, m->u_isnew, m->u_pts, rehash);
-  k_ins_scan<<<1, 1024, 0, st>>>(d, d_n, m->u_isnew, m->u_newrank, us);
-  k_ins_place<<<gm, 256, 0, st>>>(d, d_n, us, m->u_pslot, m->u_isnew, m->u_newrank, m->u_pts, m->u_l1slot, m->u_next1);
-  k_reg_children<<<gm, 256, 0, st>>>(d, d_n, us, m->u_pslot, m->u_isnew, m->u_newrank, m->u_l1slot, m->u_next1);
-  ctx->launches += 5;
+  k_ins_scan<<<1, 1024, 0, st>>>(d, d_n, m->u_isnew, m->u_pslot, m->u_newrank, us);
+  k_ins_place<<<gw, 256, 0, st>>>(d, d_n, us, m->u_pslot, m->u_isnew, m->u_newrank, m->u_pts);
+  ctx->launches += 4;
   int purge = 0;
   if (rehash) {
-    // ApplyTransformAndRehash always ends in RecomputeAllSurfels (VoxelMap.cpp:301), whatever compute_surfels says
+    // ApplyTransformAndRehash always ends in RecomputeAllSurfels (VoxelMap.cpp:301), whatever compute_surfels says;
+    // the affected set is still drained (skip = !compute_surfels is overridden by passing through k_surfel with surfels off)
+    MapDev dd = d; dd.compute_surfels = 0;
+    k_surfel<<<gw, 256, 0, st>>>(dd, m->a_tab, m->a_slots, us, plist, pfirst);
     k_surfel_all<<<grid_for(m->tcap1, 128), 128, 0, st>>>(d);
+    ctx->launches += 2;
+  } else {
+    purge = d.compute_surfels;
+    k_surfel<<<gw, 256, 0, st>>>(d, m->a_tab, m->a_slots, us, plist, pfirst);
     ctx->launches += 1;
-  } else if (d.compute_surfels) {
-    purge = 1;
-    k_surfel<<<grid_for((size_t)1 << m->a_log2cap, 128), 128, 0, st>>>(d, m->a_tab, m->a_log2cap, us, plist, pfirst);
-    k_purge_order<<<1, 1024, 0, st>>>(d, us, plist, pfirst, pord, poff);
-    k_purge_seq<<<grid_for(n_cap, 128), 128, 0, st>>>(d, us, pord, poff, m->p_seq);
-    k_swap_erase_sim<<<1, 256, SIM_SMEM_BYTES, st>>>(us, US_KPURGE, -1, m->p_seq, m->p_aux, SIM_SMEM_K);
-    k_purge_apply<<<grid_for(n_cap, 256), 256, 0, st>>>(d, us, m->p_seq, m->p_aux);
-    ctx->launches += 5;
   }
-  k_upd_finish<<<1, 32, 0, st>>>(d, us, purge);
+  k_upd_close<<<1, 1024, SIM_SMEM_BYTES, st>>>(d, us, plist, pfirst, pord, poff, m->p_seq, m->p_aux, purge, d_n, m->u_pslot, m->u_isnew);
   prof_end(ctx);
   ctx->launches += 1;
   B2_CUDA(cudaGetLastError());
@@ -784,8 +814,8 @@ extern "C" int b2lo_map_destroy(b2lo_map* m) {
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
   MapDev& d = m->d;
-  void* ptrs[] = {d.l0_cent, d.l0_key, d.l0_slot, d.l0_tab, d.l1_tab, d.l1_meta, d.t0_first, d.t0_cnt, d.t0_head, d.t1_first, d.t1_head, d.ctr,
-                  m->u_pts, m->u_pslot, m->u_next, m->u_isnew, m->u_newrank, m->u_l1slot, m->u_next1, m->a_tab, m->a_list, m->c_flag, m->c_blkcnt,
+  void* ptrs[] = {d.l0_cent, d.l0_key, d.l0_slot, d.l0_tab, d.l1_tab, d.l1_meta, d.ctr,
+                  m->u_pts, m->u_pslot, m->u_next, m->u_isnew, m->u_newrank, m->a_tab, m->a_list, m->a_slots, m->c_flag, m->c_blkcnt,
                   m->c_blkoff, m->c_removed, m->c_aux, m->c_l1work, m->p_seq, m->p_aux, m->u_state};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete m;

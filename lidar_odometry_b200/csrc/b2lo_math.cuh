@@ -55,15 +55,9 @@ B2_HD float mat3_det(const Mat3& A) {
 }
 
 // ---- two-sided Jacobi SVD of a 3x3 f32 matrix (Eigen 3.4 JacobiSVD semantics) ----------------------
+// All indices are compile-time constants after unrolling, so W/U/V stay in registers on the device
+// (the Gauss-Newton finish and the surfel refit run this on a single thread: latency matters).
 struct Rot2 { float c, s; };
-B2_HD void plane_rot(float* x, int sx, float* y, int sy, int n, Rot2 j) {
-  if (j.c == 1.0f && j.s == 0.0f) return;
-  for (int i = 0; i < n; ++i) {
-    float xi = x[i * sx], yi = y[i * sy];
-    x[i * sx] = j.c * xi + j.s * yi;
-    y[i * sy] = j.c * yi - j.s * xi;
-  }
-}
 B2_HD Rot2 sym_jacobi(float x, float y, float z) {
   Rot2 j;
   float deno = 2.0f * fabsf(y);
@@ -77,72 +71,107 @@ B2_HD Rot2 sym_jacobi(float x, float y, float z) {
   j.c = n;
   return j;
 }
-B2_HD void svd2x2(const float* W, int p, int q, Rot2& jl, Rot2& jr) {
-  float a = W[p * 3 + p], b = W[p * 3 + q], c = W[q * 3 + p], d = W[q * 3 + q];
+// real_2x2_jacobi_svd on the (p,q) sub-block [[a b],[c d]] = [[Wpp Wpq],[Wqp Wqq]]
+B2_HD void svd2x2(float a, float b, float c, float d, Rot2& jl, Rot2& jr) {
   Rot2 r1;
   float t = a + d, dd = c - b;
   if (fabsf(dd) < FLT_MIN) { r1.s = 0.0f; r1.c = 1.0f; }
   else { float u = t / dd; float tmp = sqrtf(1.0f + u * u); r1.s = 1.0f / tmp; r1.c = u / tmp; }
   if (!(r1.c == 1.0f && r1.s == 0.0f)) {
     float na = r1.c * a + r1.s * c, nb = r1.c * b + r1.s * d;
-    float nc = r1.c * c - r1.s * a, nd = r1.c * d - r1.s * b;
-    a = na; b = nb; c = nc; d = nd;
+    float nd = r1.c * d - r1.s * b;
+    a = na; b = nb; d = nd;
   }
-  (void)c;
   jr = sym_jacobi(a, b, d);
   Rot2 jrt{jr.c, -jr.s};
   jl.c = r1.c * jrt.c - r1.s * jrt.s;
   jl.s = r1.c * jrt.s + r1.s * jrt.c;
 }
+// apply_rotation_in_the_plane on (x, y): x' = c x + s y ; y' = c y - s x
+#define B2_ROT(X, Y, J)                                   \
+  do {                                                    \
+    float _x = (X), _y = (Y);                             \
+    (X) = (J).c * _x + (J).s * _y;                        \
+    (Y) = (J).c * _y - (J).s * _x;                        \
+  } while (0)
+// one (p,q) step of the sweep; P, Q are literal indices
+#define B2_SVD_PAIR(P, Q)                                                                           \
+  do {                                                                                              \
+    float thr = fmaxf(FLT_MIN, precision * maxd);                                                   \
+    if (fabsf(W[P * 3 + Q]) > thr || fabsf(W[Q * 3 + P]) > thr) {                                   \
+      done = false;                                                                                 \
+      Rot2 jl, jr;                                                                                  \
+      svd2x2(W[P * 3 + P], W[P * 3 + Q], W[Q * 3 + P], W[Q * 3 + Q], jl, jr);                       \
+      if (!(jl.c == 1.0f && jl.s == 0.0f)) {                                                        \
+        B2_ROT(W[P * 3 + 0], W[Q * 3 + 0], jl); B2_ROT(W[P * 3 + 1], W[Q * 3 + 1], jl); B2_ROT(W[P * 3 + 2], W[Q * 3 + 2], jl); \
+        B2_ROT(Um[0 * 3 + P], Um[0 * 3 + Q], jl); B2_ROT(Um[1 * 3 + P], Um[1 * 3 + Q], jl); B2_ROT(Um[2 * 3 + P], Um[2 * 3 + Q], jl); \
+      }                                                                                             \
+      Rot2 jrt{jr.c, -jr.s};                                                                        \
+      if (!(jrt.c == 1.0f && jrt.s == 0.0f)) {                                                      \
+        B2_ROT(W[0 * 3 + P], W[0 * 3 + Q], jrt); B2_ROT(W[1 * 3 + P], W[1 * 3 + Q], jrt); B2_ROT(W[2 * 3 + P], W[2 * 3 + Q], jrt); \
+        B2_ROT(Vm[0 * 3 + P], Vm[0 * 3 + Q], jrt); B2_ROT(Vm[1 * 3 + P], Vm[1 * 3 + Q], jrt); B2_ROT(Vm[2 * 3 + P], Vm[2 * 3 + Q], jrt); \
+      }                                                                                             \
+      maxd = fmaxf(maxd, fmaxf(fabsf(W[P * 3 + P]), fabsf(W[Q * 3 + Q])));                          \
+    }                                                                                               \
+  } while (0)
+#define B2_SWAP_COL(A, I, J)                                                                        \
+  do {                                                                                              \
+    float _t;                                                                                       \
+    _t = A[0 * 3 + I]; A[0 * 3 + I] = A[0 * 3 + J]; A[0 * 3 + J] = _t;                              \
+    _t = A[1 * 3 + I]; A[1 * 3 + I] = A[1 * 3 + J]; A[1 * 3 + J] = _t;                              \
+    _t = A[2 * 3 + I]; A[2 * 3 + I] = A[2 * 3 + J]; A[2 * 3 + J] = _t;                              \
+  } while (0)
 // A = U diag(S) V^T, S descending.
 B2_HD void svd3(const Mat3& A, Mat3& U, float* S, Mat3& V) {
   const float precision = 2.0f * FLT_EPSILON;
   float scale = 0.0f;
   bool bad = false;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
   for (int i = 0; i < 9; ++i) { float a = fabsf(A.m[i]); if (!(a == a) || a > FLT_MAX) bad = true; if (a > scale) scale = a; }
-  U = mat3_identity(); V = mat3_identity();
-  if (bad) { S[0] = S[1] = S[2] = 0.0f; return; }
-  if (scale == 0.0f) scale = 1.0f;
-  float W[9];
-  for (int i = 0; i < 9; ++i) W[i] = A.m[i] / scale;
-  float maxd = fmaxf(fabsf(W[0]), fmaxf(fabsf(W[4]), fabsf(W[8])));
-  bool done = false;
-  while (!done) {
-    done = true;
-    for (int p = 1; p < 3; ++p)
-      for (int q = 0; q < p; ++q) {
-        float thr = fmaxf(FLT_MIN, precision * maxd);
-        if (fabsf(W[p * 3 + q]) > thr || fabsf(W[q * 3 + p]) > thr) {
-          done = false;
-          Rot2 jl, jr;
-          svd2x2(W, p, q, jl, jr);
-          plane_rot(&W[p * 3], 1, &W[q * 3], 1, 3, jl);
-          plane_rot(&U.m[p], 3, &U.m[q], 3, 3, jl);
-          Rot2 jrt{jr.c, -jr.s};
-          plane_rot(&W[p], 3, &W[q], 3, 3, jrt);
-          plane_rot(&V.m[p], 3, &V.m[q], 3, 3, jrt);
-          maxd = fmaxf(maxd, fmaxf(fabsf(W[p * 3 + p]), fabsf(W[q * 3 + q])));
-        }
-      }
-  }
-  for (int i = 0; i < 3; ++i) {
-    float a = W[i * 4];
-    S[i] = fabsf(a);
-    if (a < 0.0f) for (int r = 0; r < 3; ++r) U.m[r * 3 + i] = -U.m[r * 3 + i];
-  }
-  for (int i = 0; i < 3; ++i) S[i] *= scale;
-  for (int i = 0; i < 3; ++i) {
-    int pos = i; float mx = S[i];
-    for (int k = i + 1; k < 3; ++k) if (S[k] > mx) { mx = S[k]; pos = k; }
-    if (mx == 0.0f) break;
-    if (pos != i) {
-      float ts = S[i]; S[i] = S[pos]; S[pos] = ts;
-      for (int r = 0; r < 3; ++r) {
-        float tu = U.m[r * 3 + i]; U.m[r * 3 + i] = U.m[r * 3 + pos]; U.m[r * 3 + pos] = tu;
-        float tv = V.m[r * 3 + i]; V.m[r * 3 + i] = V.m[r * 3 + pos]; V.m[r * 3 + pos] = tv;
-      }
+  float Um[9] = {1.0f, 0.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f, 0.0f, 1.0f};
+  float Vm[9] = {1.0f, 0.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f, 0.0f, 1.0f};
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
+  if (!bad) {
+    if (scale == 0.0f) scale = 1.0f;
+    float W[9];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 9; ++i) W[i] = A.m[i] / scale;
+    float maxd = fmaxf(fabsf(W[0]), fmaxf(fabsf(W[4]), fabsf(W[8])));
+    bool done = false;
+    while (!done) {
+      done = true;
+      B2_SVD_PAIR(1, 0);
+      B2_SVD_PAIR(2, 0);
+      B2_SVD_PAIR(2, 1);
+    }
+    s0 = fabsf(W[0]); s1 = fabsf(W[4]); s2 = fabsf(W[8]);
+    if (W[0] < 0.0f) { Um[0] = -Um[0]; Um[3] = -Um[3]; Um[6] = -Um[6]; }
+    if (W[4] < 0.0f) { Um[1] = -Um[1]; Um[4] = -Um[4]; Um[7] = -Um[7]; }
+    if (W[8] < 0.0f) { Um[2] = -Um[2]; Um[5] = -Um[5]; Um[8] = -Um[8]; }
+    s0 *= scale; s1 *= scale; s2 *= scale;
+    // selection sort, descending, first maximum wins ties, stop at an all-zero tail (Eigen)
+    bool stop = false;
+    {
+      int pos = 0; float mx = s0;
+      if (s1 > mx) { mx = s1; pos = 1; }
+      if (s2 > mx) { mx = s2; pos = 2; }
+      if (mx == 0.0f) stop = true;
+      else if (pos == 1) { float t = s0; s0 = s1; s1 = t; B2_SWAP_COL(Um, 0, 1); B2_SWAP_COL(Vm, 0, 1); }
+      else if (pos == 2) { float t = s0; s0 = s2; s2 = t; B2_SWAP_COL(Um, 0, 2); B2_SWAP_COL(Vm, 0, 2); }
+    }
+    if (!stop) {
+      if (s2 > s1) { float t = s1; s1 = s2; s2 = t; B2_SWAP_COL(Um, 1, 2); B2_SWAP_COL(Vm, 1, 2); }
     }
   }
+  S[0] = s0; S[1] = s1; S[2] = s2;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 9; ++i) { U.m[i] = Um[i]; V.m[i] = Vm[i]; }
 }
 
 // nearest rotation: SO3::SO3(const Matrix3f&)
@@ -164,16 +193,44 @@ B2_HD Mat3 hat(const float* w) {
   K.m[6] = -w[1]; K.m[7] = w[0]; K.m[8] = 0.0f;
   return K;
 }
+// sinf / cosf as glibc computes them (correctly rounded in practice): on the device the f64 value rounded to f32.
+// Gauss-Newton steps are small angles, so |x| < 0.5 takes a Taylor series in f64 (error < 2e-17, then one rounding)
+// instead of libdevice's full-range routines, whose ~40-deep f64 chains sit on the single-thread finish path.
 B2_HD float sin_f32(float x) {
 #if defined(__CUDA_ARCH__)
-  return (float)sin((double)x);  // correctly rounded in practice, as glibc's sinf is
+  const double xd = (double)x;
+  if (fabs(xd) < 0.5) {
+    const double z = xd * xd;
+    double p = -1.0 / 1307674368000.0;            // x^15
+    p = p * z + 1.0 / 6227020800.0;               // x^13
+    p = p * z - 1.0 / 39916800.0;
+    p = p * z + 1.0 / 362880.0;
+    p = p * z - 1.0 / 5040.0;
+    p = p * z + 1.0 / 120.0;
+    p = p * z - 1.0 / 6.0;
+    return (float)(xd + xd * (z * p));
+  }
+  return (float)sin(xd);
 #else
   return sinf(x);
 #endif
 }
 B2_HD float cos_f32(float x) {
 #if defined(__CUDA_ARCH__)
-  return (float)cos((double)x);
+  const double xd = (double)x;
+  if (fabs(xd) < 0.5) {
+    const double z = xd * xd;
+    double p = 1.0 / 20922789888000.0;            // x^16
+    p = p * z - 1.0 / 87178291200.0;              // x^14
+    p = p * z + 1.0 / 479001600.0;
+    p = p * z - 1.0 / 3628800.0;
+    p = p * z + 1.0 / 40320.0;
+    p = p * z - 1.0 / 720.0;
+    p = p * z + 1.0 / 24.0;
+    p = p * z - 0.5;
+    return (float)(1.0 + z * p);
+  }
+  return (float)cos(xd);
 #else
   return cosf(x);
 #endif
@@ -249,44 +306,94 @@ B2_HD Pose pose_inv(const Pose& a) {
 }
 
 // ---- pivoted LDL^T (lower) solve of a 6x6 f32 system: x = H.ldlt().solve(b) -------------------------
+// Eigen's unblocked LDLT with largest-|diagonal| pivoting.  Every index below is a compile-time constant once the
+// loops are unrolled (the dynamic pivot only selects between statically indexed swap blocks), so the matrix lives in
+// registers on the device: this runs on ONE thread at the end of every Gauss-Newton iteration.
+#if defined(__CUDA_ARCH__)
+#define B2_UNROLL _Pragma("unroll")
+#else
+#define B2_UNROLL
+#endif
+#define B2_FSWAP(a, b) do { float _t = (a); (a) = (b); (b) = _t; } while (0)
 B2_HD void ldlt6_solve(const float* Hin, const float* b, float* x) {
   float A[36];
+  B2_UNROLL
   for (int i = 0; i < 36; ++i) A[i] = Hin[i];
-  int perm[6];
+  int perm[6] = {0, 1, 2, 3, 4, 5};
   float tmp[6];
+  bool all_zero = false;
+  B2_UNROLL
   for (int k = 0; k < 6; ++k) {
+    if (all_zero) continue;
     int piv = k; float best = fabsf(A[k * 7]);
+    B2_UNROLL
     for (int i = k + 1; i < 6; ++i) { float a = fabsf(A[i * 7]); if (a > best) { best = a; piv = i; } }
     perm[k] = piv;
-    if (piv != k) {
-      for (int c = 0; c < k; ++c) { float t = A[k * 6 + c]; A[k * 6 + c] = A[piv * 6 + c]; A[piv * 6 + c] = t; }
-      for (int r = piv + 1; r < 6; ++r) { float t = A[r * 6 + k]; A[r * 6 + k] = A[r * 6 + piv]; A[r * 6 + piv] = t; }
-      { float t = A[k * 7]; A[k * 7] = A[piv * 7]; A[piv * 7] = t; }
-      for (int i = k + 1; i < piv; ++i) { float t = A[i * 6 + k]; A[i * 6 + k] = A[piv * 6 + i]; A[piv * 6 + i] = t; }
+    B2_UNROLL
+    for (int p = k + 1; p < 6; ++p) {
+      if (piv == p) {
+        B2_UNROLL
+        for (int c = 0; c < k; ++c) B2_FSWAP(A[k * 6 + c], A[p * 6 + c]);
+        B2_UNROLL
+        for (int r = p + 1; r < 6; ++r) B2_FSWAP(A[r * 6 + k], A[r * 6 + p]);
+        B2_FSWAP(A[k * 7], A[p * 7]);
+        B2_UNROLL
+        for (int i = k + 1; i < p; ++i) B2_FSWAP(A[i * 6 + k], A[p * 6 + i]);
+      }
     }
     if (k > 0) {
+      B2_UNROLL
       for (int c = 0; c < k; ++c) tmp[c] = A[c * 7] * A[k * 6 + c];
       float acc = A[k * 6] * tmp[0];
+      B2_UNROLL
       for (int c = 1; c < k; ++c) acc = acc + A[k * 6 + c] * tmp[c];
       A[k * 7] -= acc;
+      B2_UNROLL
       for (int r = k + 1; r < 6; ++r) {
         float a2 = A[r * 6] * tmp[0];
+        B2_UNROLL
         for (int c = 1; c < k; ++c) a2 = a2 + A[r * 6 + c] * tmp[c];
         A[r * 6 + k] -= a2;
       }
     }
-    float akk = A[k * 7];
-    bool valid = fabsf(akk) > 0.0f;
-    if (k == 0 && !valid) { for (int j = 0; j < 6; ++j) perm[j] = j; break; }
-    if (valid) for (int r = k + 1; r < 6; ++r) A[r * 6 + k] /= akk;
+    const float akk = A[k * 7];
+    const bool valid = fabsf(akk) > 0.0f;
+    if (k == 0 && !valid) { all_zero = true; B2_UNROLL for (int j = 0; j < 6; ++j) perm[j] = j; continue; }
+    if (valid) {
+      B2_UNROLL
+      for (int r = k + 1; r < 6; ++r) A[r * 6 + k] /= akk;
+    }
   }
   float y[6];
+  B2_UNROLL
   for (int i = 0; i < 6; ++i) y[i] = b[i];
-  for (int k = 0; k < 6; ++k) if (perm[k] != k) { float t = y[k]; y[k] = y[perm[k]]; y[perm[k]] = t; }
-  for (int i = 0; i < 6; ++i) { float acc = y[i]; for (int c = 0; c < i; ++c) acc -= A[i * 6 + c] * y[c]; y[i] = acc; }
+  B2_UNROLL
+  for (int k = 0; k < 6; ++k) {
+    B2_UNROLL
+    for (int p = k + 1; p < 6; ++p) if (perm[k] == p) B2_FSWAP(y[k], y[p]);
+  }
+  B2_UNROLL
+  for (int i = 0; i < 6; ++i) {
+    float acc = y[i];
+    B2_UNROLL
+    for (int c = 0; c < i; ++c) acc -= A[i * 6 + c] * y[c];
+    y[i] = acc;
+  }
+  B2_UNROLL
   for (int i = 0; i < 6; ++i) { if (fabsf(A[i * 7]) > FLT_MIN) y[i] /= A[i * 7]; else y[i] = 0.0f; }
-  for (int i = 5; i >= 0; --i) { float acc = y[i]; for (int c = i + 1; c < 6; ++c) acc -= A[c * 6 + i] * y[c]; y[i] = acc; }
-  for (int k = 5; k >= 0; --k) if (perm[k] != k) { float t = y[k]; y[k] = y[perm[k]]; y[perm[k]] = t; }
+  B2_UNROLL
+  for (int i = 5; i >= 0; --i) {
+    float acc = y[i];
+    B2_UNROLL
+    for (int c = i + 1; c < 6; ++c) acc -= A[c * 6 + i] * y[c];
+    y[i] = acc;
+  }
+  B2_UNROLL
+  for (int k = 5; k >= 0; --k) {
+    B2_UNROLL
+    for (int p = k + 1; p < 6; ++p) if (perm[k] == p) B2_FSWAP(y[k], y[p]);
+  }
+  B2_UNROLL
   for (int i = 0; i < 6; ++i) x[i] = y[i];
 }
 
