@@ -66,6 +66,12 @@ __device__ __forceinline__ double gate_residual(const float* n, const float* c, 
   return fabs(((double)n[0] * d0 + (double)n[1] * d1) + (double)n[2] * d2);
 }
 
+// K2.  One thread takes QPT consecutive queries (64 B of the float4 query stream), issues their QPT first hash probes
+// back to back (independent 32 B sectors in flight), then gates and compacts.  Accepted queries are written in
+// ascending query order per CT-query tile (cidx) with the tile count (tilecnt); k_icp_pko1 scans the tile counts.
+// Algorithmic traffic per query: 16 B query + 32 B surfel sector (+ 12 B of per-query results: slot, f64 residual).
+constexpr int QPT = 4;
+constexpr int CT = TILE * QPT;   // queries per compaction tile
 __global__ void __launch_bounds__(TILE) k_icp_corr(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, IcpState* st,
                                                    IcpParams prm, double* res, int* slot_out, int* cidx, int* tilecnt) {
   if (st->done) return;
@@ -75,26 +81,57 @@ __global__ void __launch_bounds__(TILE) k_icp_corr(MapDev M, const float4* __res
   if (threadIdx.x < 3) sT[threadIdx.x] = st->t[threadIdx.x];
   __syncthreads();
   const int npts = *d_npts;
-  const int ntiles = (npts + TILE - 1) / TILE;
+  const int ntiles = (npts + CT - 1) / CT;
+  const uint32_t mask = (1u << M.l1_log2cap) - 1u;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    int i = tile * TILE + threadIdx.x;
-    int ok = 0, s = -1;
-    double r = 0.0;
-    if (i < npts) {
-      float4 p = pts[i];
-      float w[3], n[3], c[3];
-      transform_point(sR, sT, p.x, p.y, p.z, w);
-      s = surfel_probe(M, w, n, c, nullptr, nullptr);
-      if (s >= 0) {
-        r = gate_residual(n, c, w);
-        if (r > prm.max_dist) s = -1; else ok = 1;
+    const int i0 = tile * CT + threadIdx.x * QPT;
+    float w[QPT][3];
+    unsigned long long key[QPT];
+    uint32_t hs[QPT];
+    float4 ea[QPT];
+#pragma unroll
+    for (int u = 0; u < QPT; ++u) {
+      const int i = i0 + u;
+      float4 p = (i < npts) ? pts[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      transform_point(sR, sT, p.x, p.y, p.z, w[u]);
+      int kx = voxel_coord(w[u][0], M.scale1), ky = voxel_coord(w[u][1], M.scale1), kz = voxel_coord(w[u][2], M.scale1);
+      key[u] = (i < npts && key_in_range(kx, ky, kz)) ? key_morton(kx, ky, kz) : KEY_TOMB;   // TOMB never matches: no surfel
+      hs[u] = hash_slot(key[u], M.l1_log2cap);
+    }
+#pragma unroll
+    for (int u = 0; u < QPT; ++u) ea[u] = __ldg(reinterpret_cast<const float4*>(&M.l1_tab[hs[u]]));   // QPT sectors in flight
+    int okm = 0, nok = 0;
+#pragma unroll
+    for (int u = 0; u < QPT; ++u) {
+      const int i = i0 + u;
+      int s = -1;
+      double r = 0.0;
+      if (key[u] != KEY_TOMB) {
+        uint32_t h = hs[u];
+        float4 a = ea[u];
+        for (uint32_t probe = 0; probe <= mask; ++probe) {
+          unsigned long long k = ((unsigned long long)__float_as_uint(a.y) << 32) | (unsigned long long)__float_as_uint(a.x);
+          if (k == KEY_EMPTY) break;
+          if (k != KEY_TOMB && (k & KEY_MASK) == key[u]) {
+            if (k & SURFEL_BIT) {
+              float4 b = __ldg(reinterpret_cast<const float4*>(&M.l1_tab[h]) + 1);   // same 32 B sector
+              float n[3] = {a.z, a.w, b.x}, c[3] = {b.y, b.z, b.w};
+              r = gate_residual(n, c, w[u]);
+              if (!(r > prm.max_dist)) s = (int)h;
+            }
+            break;
+          }
+          h = (h + 1) & mask;
+          a = __ldg(reinterpret_cast<const float4*>(&M.l1_tab[h]));
+        }
       }
-      slot_out[i] = s;
-      res[i] = r;
+      if (i < npts) { slot_out[i] = s; res[i] = r; }
+      if (s >= 0) { okm |= 1 << u; ++nok; }
     }
     int total;
-    int off = block_excl_scan(ok, &total, sm);
-    if (ok) cidx[tile * TILE + off] = i;
+    int off = tile * CT + block_excl_scan(nok, &total, sm);
+#pragma unroll
+    for (int u = 0; u < QPT; ++u) if (okm & (1 << u)) cidx[off++] = i0 + u;
     if (threadIdx.x == 0) tilecnt[tile] = total;
   }
 }
@@ -324,7 +361,8 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
   const int tid = threadIdx.x;
   const long long c0 = clock64();
   const int npts = *d_npts;
-  const int ntiles = (npts + TILE - 1) / TILE;
+  const int ctile = prm.ctile;
+  const int ntiles = (npts + ctile - 1) / ctile;
   // 1. exclusive scan of the per-tile accepted counts
   int base = 0;
   for (int t0 = 0; t0 < ntiles; t0 += blockDim.x) {
@@ -384,7 +422,7 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
     }
     int tl = 0, th = ntiles - 1;  // last tile with tileoff <= ci
     while (tl < th) { int mid = (tl + th + 1) >> 1; if (tileoff[mid] <= ci) tl = mid; else th = mid - 1; }
-    int q = cidx[tl * TILE + (ci - tileoff[tl])];
+    int q = cidx[tl * ctile + (ci - tileoff[tl])];
     s_x[tid] = res[q] / sdiv;
   }
   __syncthreads();
@@ -770,9 +808,9 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
             bool init_pose_on_device) {
   b2lo_ctx* ctx = map->ctx;
   if (cfg->max_iterations < 1 || cfg->max_iterations > B2LO_MAX_ITERS) { set_error("max_iterations must be in [1,%d]", B2LO_MAX_ITERS); return B2LO_E_ARG; }
+  const bool surfel = cfg->use_surfel_correspondence != 0;
   int rc = icp_build_pko(ctx, cfg);
   if (rc) return rc;
-  const bool surfel = cfg->use_surfel_correspondence != 0;
   if (!surfel && (rc = knn_reserve(ctx))) return rc;
   cudaStream_t s = ctx->stream;
   IcpParams prm;
@@ -780,9 +818,12 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
   prm.loss_type = cfg->loss_type; prm.use_pko = cfg->use_adaptive_m_estimator; prm.use_surfel = cfg->use_surfel_correspondence;
   prm.tol_t = cfg->translation_tolerance; prm.tol_r = cfg->rotation_tolerance; prm.max_dist = cfg->max_correspondence_distance;
   prm.robust_delta = cfg->robust_loss_delta;
+  prm.ctile = surfel ? CT : TILE;
   Init16 Ti;
   for (int i = 0; i < 16; ++i) Ti.m[i] = init_pose_on_device ? 0.0f : T_init16[i];
   k_icp_begin<<<1, 32, 0, s>>>(ctx->d_icp, Ti, init_pose_on_device ? 1 : 0);
+  int ctiles_cap = (int)((npts_cap + CT - 1) / CT);
+  int grid_corr = ctiles_cap < 1 ? 1 : (ctiles_cap > ctx->sm_count * 8 ? ctx->sm_count * 8 : ctiles_cap);
   int ntiles_cap = (int)((npts_cap + TILE - 1) / TILE);
   int grid = ntiles_cap < 1 ? 1 : (ntiles_cap > ctx->i_max_blocks ? ctx->i_max_blocks : ntiles_cap);
   double* gmm = ctx->i_partial + (size_t)ctx->i_max_blocks * 28;      // 9 GMM doubles, then P(r_k) at [16, 116)
@@ -791,7 +832,7 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
   for (int it = 0; it < cfg->max_iterations; ++it) {
     if (surfel) {
       prof_begin(ctx, PS_CORR);
-      k_icp_corr<<<grid, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt);
+      k_icp_corr<<<grid_corr, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt);
       prof_end(ctx);
     } else {
       prof_begin(ctx, PS_KNN);

@@ -50,7 +50,7 @@ struct IcpState {                 // lives in device memory, one per context
 };
 
 struct IcpParams {                // kernel-argument POD
-  int max_iterations, min_corr, use_robust, loss_type, use_pko, use_surfel;
+  int max_iterations, min_corr, use_robust, loss_type, use_pko, use_surfel, ctile;
   double tol_t, tol_r, max_dist, robust_delta;
 };
 
@@ -58,7 +58,7 @@ struct IcpParams {                // kernel-argument POD
 
 namespace b2 {
 // optional per-kernel CUDA-event timing on the context stream (bench.py roofline leg); off by default
-enum ProfSlot { PS_FILTER = 0, PS_CORR = 1, PS_PKO1 = 2, PS_PKO2 = 3, PS_GN = 4, PS_MAP = 5, PS_XFORM = 6, PS_KNN = 7, PS_COUNT = 8 };
+enum ProfSlot { PS_FILTER = 0, PS_CORR = 1, PS_PKO1 = 2, PS_PKO2 = 3, PS_GN = 4, PS_MAP = 5, PS_XFORM = 6, PS_KNN = 7, PS_CULL = 8, PS_COUNT = 9 };
 struct Prof {
   bool on = false;
   static constexpr int POOL = 512;

@@ -97,18 +97,23 @@ __global__ void __launch_bounds__(1024) k_cull_mark(MapDev M, int n0, float sx, 
   __shared__ int sm[40];
   __shared__ int s_last;
   int ntiles = (n0 + 1023) / 1024;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    int pos = tile * 1024 + threadIdx.x;
-    int mk = 0;
-    if (pos < n0) {
-      float4 c = M.l0_cent[pos];
-      float d[3] = {c.x - sx, c.y - sy, c.z - sz};
-      mk = sqn3(d) > r2;  // (centroid - sensor).squaredNorm() > radius_sq  (VoxelMap.cpp:149-150)
-      flag[pos] = (uint8_t)mk;
+  // 4 tiles per trip: four independent 16 B loads in flight per thread (the scan streams 16 B / voxel from HBM)
+  for (int tile0 = blockIdx.x * 4; tile0 < ntiles; tile0 += gridDim.x * 4) {
+    float4 c[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int pos = (tile0 + u) * 1024 + threadIdx.x;
+      c[u] = (pos < n0) ? M.l0_cent[pos] : make_float4(sx, sy, sz, 0.0f);
     }
-    int tot;
-    block_excl_scan(mk, &tot, sm);
-    if (threadIdx.x == 0) blkcnt[tile] = tot;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int pos = (tile0 + u) * 1024 + threadIdx.x;
+      float d[3] = {c[u].x - sx, c[u].y - sy, c[u].z - sz};
+      int mk = (pos < n0) && (sqn3(d) > r2);  // (centroid - sensor).squaredNorm() > radius_sq  (VoxelMap.cpp:149-150)
+      if (pos < n0) flag[pos] = (uint8_t)mk;
+      int tot = __syncthreads_count(mk);
+      if (threadIdx.x == 0 && tile0 + u < ntiles) blkcnt[tile0 + u] = tot;
+    }
   }
   __threadfence();
   __syncthreads();
@@ -741,7 +746,12 @@ int map_update_dev(b2lo_map* m, const float4* d_world, const int* d_n, size_t n_
   if (n0 > 0 && !rehash) {
     int tiles = (n0 + 1023) / 1024;
     int g = tiles > ctx->sm_count ? ctx->sm_count : tiles;
-    k_cull_mark<<<g, 1024, 0, st>>>(d, n0, sensor[0], sensor[1], sensor[2], radius_sq, m->c_flag, m->c_blkcnt, m->c_blkoff, us);
+    int g4 = (tiles + 3) / 4; if (g4 > 2 * ctx->sm_count) g4 = 2 * ctx->sm_count;
+    prof_end(ctx);
+    prof_begin(ctx, PS_CULL);
+    k_cull_mark<<<g4, 1024, 0, st>>>(d, n0, sensor[0], sensor[1], sensor[2], radius_sq, m->c_flag, m->c_blkcnt, m->c_blkoff, us);
+    prof_end(ctx);
+    prof_begin(ctx, PS_MAP);
     k_cull_lists<<<g, 1024, 0, st>>>(d, n0, m->c_flag, m->c_blkoff, us, m->c_removed, m->c_l1work);
     k_cull_fix<<<1, 1024, SIM_SMEM_BYTES, st>>>(d, m->c_flag, us, m->c_l1work, m->c_removed, m->c_aux, n0);
     ctx->launches += 3;
