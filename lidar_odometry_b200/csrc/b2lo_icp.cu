@@ -70,8 +70,8 @@ __device__ __forceinline__ double gate_residual(const float* n, const float* c, 
 // back to back (independent 32 B sectors in flight), then gates and compacts.  Accepted queries are written in
 // ascending query order per CT-query tile (cidx) with the tile count (tilecnt); k_icp_pko1 scans the tile counts.
 // Algorithmic traffic per query: 16 B query + 32 B surfel sector (+ 12 B of per-query results: slot, f64 residual).
-constexpr int QPT = 4;
-constexpr int CT = TILE * QPT;   // queries per compaction tile
+// QPT = 1 for scan-sized clouds (more threads, shortest chain), 4 for dense clouds (more probes in flight per thread).
+template <int QPT>
 __global__ void __launch_bounds__(TILE) k_icp_corr(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, IcpState* st,
                                                    IcpParams prm, double* res, int* slot_out, int* cidx, int* tilecnt) {
   if (st->done) return;
@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(TILE) k_icp_corr(MapDev M, const float4* __res
   if (threadIdx.x < 9) sR[threadIdx.x] = st->R[threadIdx.x];
   if (threadIdx.x < 3) sT[threadIdx.x] = st->t[threadIdx.x];
   __syncthreads();
+  constexpr int CT = TILE * QPT;   // queries per compaction tile
   const int npts = *d_npts;
   const int ntiles = (npts + CT - 1) / CT;
   const uint32_t mask = (1u << M.l1_log2cap) - 1u;
@@ -818,11 +819,12 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
   prm.loss_type = cfg->loss_type; prm.use_pko = cfg->use_adaptive_m_estimator; prm.use_surfel = cfg->use_surfel_correspondence;
   prm.tol_t = cfg->translation_tolerance; prm.tol_r = cfg->rotation_tolerance; prm.max_dist = cfg->max_correspondence_distance;
   prm.robust_delta = cfg->robust_loss_delta;
-  prm.ctile = surfel ? CT : TILE;
+  const int qpt = (npts_cap >= 65536) ? 4 : 1;
+  prm.ctile = surfel ? TILE * qpt : TILE;
   Init16 Ti;
   for (int i = 0; i < 16; ++i) Ti.m[i] = init_pose_on_device ? 0.0f : T_init16[i];
   k_icp_begin<<<1, 32, 0, s>>>(ctx->d_icp, Ti, init_pose_on_device ? 1 : 0);
-  int ctiles_cap = (int)((npts_cap + CT - 1) / CT);
+  int ctiles_cap = (int)((npts_cap + prm.ctile - 1) / prm.ctile);
   int grid_corr = ctiles_cap < 1 ? 1 : (ctiles_cap > ctx->sm_count * 8 ? ctx->sm_count * 8 : ctiles_cap);
   int ntiles_cap = (int)((npts_cap + TILE - 1) / TILE);
   int grid = ntiles_cap < 1 ? 1 : (ntiles_cap > ctx->i_max_blocks ? ctx->i_max_blocks : ntiles_cap);
@@ -832,7 +834,8 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
   for (int it = 0; it < cfg->max_iterations; ++it) {
     if (surfel) {
       prof_begin(ctx, PS_CORR);
-      k_icp_corr<<<grid_corr, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt);
+      if (qpt == 4) k_icp_corr<4><<<grid_corr, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt);
+      else k_icp_corr<1><<<grid_corr, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt);
       prof_end(ctx);
     } else {
       prof_begin(ctx, PS_KNN);
