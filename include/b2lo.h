@@ -149,6 +149,19 @@ int b2lo_icp_optimize(b2lo_map* map, const float* local_xyz, size_t m, size_t st
 /* same, query cloud = the context's feature buffer left by b2lo_filter / b2lo_filter_dev */
 int b2lo_icp_optimize_features(b2lo_map* map, const float T_init[16], const b2lo_icp_cfg* cfg, float T_out[16], b2lo_icp_stats* stats);
 
+/* ---- point-sharded scan-to-map ICP for dense scans: this rank holds a contiguous slice of the query cloud, the map
+ * is replicated.  One Gauss-Newton iteration = shard_corr -> [all-gather 3 doubles: C_r, sum r, sum r^2] -> shard_sample ->
+ * [all-reduce gmm_sample_size doubles] -> shard_accumulate -> [all-reduce 28 doubles: 21 lower-triangle H, 6 g, cost] ->
+ * shard_finish (every rank solves the identical 6x6 system).  The *_dev buffers are DEVICE pointers owned by the caller (the
+ * tensors handed to NCCL); every call enqueues on the context stream, only shard_finish synchronises.  scale = the residual
+ * normalisation sqrt(var)/6 of iteration 0 (ICP.cpp:304-316) computed by the caller from the gathered moments. */
+int b2lo_icp_shard_begin(b2lo_map* map, const float* local_xyz, size_t m, size_t stride_floats, const float T_init[16], const b2lo_icp_cfg* cfg);
+int b2lo_icp_shard_corr(b2lo_map* map, const b2lo_icp_cfg* cfg, double* stats3_dev);
+int b2lo_icp_shard_sample(b2lo_map* map, const b2lo_icp_cfg* cfg, long long offset, long long c_total, double scale, double* sample_dev /*128 doubles*/);
+int b2lo_icp_shard_accumulate(b2lo_map* map, const b2lo_icp_cfg* cfg, long long c_total, double scale, const double* sample_dev, double* acc28_dev);
+int b2lo_icp_shard_finish(b2lo_map* map, const b2lo_icp_cfg* cfg, const double* acc28_dev, float T_out[16], int* done /*0 go on, 1 finished, 2 failed*/,
+                          b2lo_icp_stats* stats /*nullable*/);
+
 /* ---- pose algebra used at the boundary (util::SE3 / SO3, MathUtils.h:57-168) --------------------- */
 void b2lo_se3_mul(const float A16[16], const float B16[16], float C16[16]);  /* SE3::operator*, re-projects the rotation */
 void b2lo_se3_inv(const float A16[16], float C16[16]);                       /* SE3::Inverse */

@@ -22,7 +22,7 @@ import numpy as np
 from . import capi
 from .capi import B2LO_OK, B2LO_S_EMPTY, B2LO_S_INSUFFICIENT, IcpCfg, IcpStats, OdomCfg, OdomResult, check
 
-__all__ = ["Context", "default_context", "FastVoxelFilter", "FastVoxelGrid", "VoxelMap", "ICPConfig", "AdaptiveMEstimatorConfig",
+__all__ = ["PointShardedICP", "Context", "default_context", "FastVoxelFilter", "FastVoxelGrid", "VoxelMap", "ICPConfig", "AdaptiveMEstimatorConfig",
            "AdaptiveMEstimator", "OptimizationStats", "IterativeClosestPointOptimizer", "Odometry", "SE3"]
 
 
@@ -470,6 +470,89 @@ class IterativeClosestPointOptimizer:
         out["n_accepted"] = na.value
         out["n_scanned"] = nsc.value
         return out
+
+
+class PointShardedICP:
+    """optimize() for a dense scan whose queries are split across ranks; the map is replicated.
+    Collectives (3 tiny ones per Gauss-Newton iteration) go through torch.distributed on the caller's process group;
+    with ``group=None`` and an uninitialised torch.distributed the exchange is the identity (single rank)."""
+
+    def __init__(self, config: ICPConfig | None = None, adaptive_estimator: AdaptiveMEstimator | None = None, group=None):
+        self.m_config = config or ICPConfig()
+        self.m_adaptive_estimator = adaptive_estimator
+        self.group = group
+        self.m_last_stats = OptimizationStats()
+        self.collective_seconds = 0.0
+
+    def get_last_stats(self):
+        return self.m_last_stats
+
+    def optimize(self, voxel_map: VoxelMap, cloud_shard, initial_transform):
+        import time
+        import torch
+        import torch.distributed as dist
+        from . import sharding
+        L = capi.lib()
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+        rank = dist.get_rank(self.group) if multi else 0
+        world = dist.get_world_size(self.group) if multi else 1
+        a, n, sf = _cloud(cloud_shard)
+        T0 = _f32(initial_transform).reshape(16)
+        ame = self.m_adaptive_estimator.get_config() if self.m_adaptive_estimator else None
+        cfg = _icp_cfg(self.m_config, ame)
+        dev = torch.device("cuda", voxel_map.ctx.device)
+        stats3 = torch.zeros(3, dtype=torch.float64, device=dev)
+        sample = torch.zeros(128, dtype=torch.float64, device=dev)
+        acc28 = torch.zeros(28, dtype=torch.float64, device=dev)
+        torch.cuda.synchronize(dev)
+        check(L.b2lo_icp_shard_begin(voxel_map.h, _p(a), n, sf, _p(T0), C.byref(cfg)))
+        Tout = np.zeros(16, np.float32)
+        st = IcpStats()
+        scale = 1.0
+        self.collective_seconds = 0.0
+        ok = True
+        for it in range(self.m_config.max_iterations):
+            check(L.b2lo_icp_shard_corr(voxel_map.h, C.byref(cfg), C.c_void_p(stats3.data_ptr())))
+            voxel_map.ctx.sync()
+            t0 = time.perf_counter()
+            if multi:
+                gathered = [torch.zeros_like(stats3) for _ in range(world)]
+                dist.all_gather(gathered, stats3, group=self.group)
+                g = torch.stack(gathered).cpu().numpy()
+            else:
+                g = stats3.cpu().numpy()[None, :]
+            self.collective_seconds += time.perf_counter() - t0
+            offset, total = sharding.shard_plan(g[:, 0], rank)
+            if total < self.m_config.min_correspondence_points:   # ICP.cpp:298-302: false, output = initial
+                ok = False
+                break
+            if it == 0:
+                scale = sharding.scale_from_moments(total, float(g[:, 1].sum()), float(g[:, 2].sum()))
+            check(L.b2lo_icp_shard_sample(voxel_map.h, C.byref(cfg), offset, total, C.c_double(scale), C.c_void_p(sample.data_ptr())))
+            voxel_map.ctx.sync()
+            t0 = time.perf_counter()
+            if multi:
+                dist.all_reduce(sample, group=self.group)
+                torch.cuda.synchronize(dev)
+            self.collective_seconds += time.perf_counter() - t0
+            check(L.b2lo_icp_shard_accumulate(voxel_map.h, C.byref(cfg), total, C.c_double(scale), C.c_void_p(sample.data_ptr()),
+                                              C.c_void_p(acc28.data_ptr())))
+            voxel_map.ctx.sync()
+            t0 = time.perf_counter()
+            if multi:
+                dist.all_reduce(acc28, group=self.group)
+                torch.cuda.synchronize(dev)
+            self.collective_seconds += time.perf_counter() - t0
+            done = C.c_int(0)
+            check(L.b2lo_icp_shard_finish(voxel_map.h, C.byref(cfg), C.c_void_p(acc28.data_ptr()), _p(Tout), C.byref(done), C.byref(st)))
+            if done.value:
+                break
+        if not ok:
+            self.m_last_stats = OptimizationStats()
+            return False, T0.reshape(4, 4).copy()
+        self.m_last_stats = OptimizationStats(num_iterations=st.num_iterations, num_correspondences=st.num_correspondences,
+                                              initial_cost=st.initial_cost, final_cost=st.final_cost, converged=True, iterations=_trace(st))
+        return True, Tout.reshape(4, 4).copy()
 
 
 # ---- per-scan driver (SURVEY §8f rank 1) ---------------------------------------------------------------------------------

@@ -118,6 +118,11 @@ SIGNATURES = {
     "b2lo_icp_correspondences_knn": (_i, [_vp, _vp, _sz, _sz, _vp, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_sz), C.POINTER(_sz)]),
     "b2lo_icp_optimize": (_i, [_vp, _vp, _sz, _sz, _vp, C.POINTER(IcpCfg), _vp, C.POINTER(IcpStats)]),
     "b2lo_icp_optimize_features": (_i, [_vp, _vp, C.POINTER(IcpCfg), _vp, C.POINTER(IcpStats)]),
+    "b2lo_icp_shard_begin": (_i, [_vp, _vp, _sz, _sz, _vp, C.POINTER(IcpCfg)]),
+    "b2lo_icp_shard_corr": (_i, [_vp, C.POINTER(IcpCfg), _vp]),
+    "b2lo_icp_shard_sample": (_i, [_vp, C.POINTER(IcpCfg), C.c_longlong, C.c_longlong, _d, _vp]),
+    "b2lo_icp_shard_accumulate": (_i, [_vp, C.POINTER(IcpCfg), C.c_longlong, _d, _vp, _vp]),
+    "b2lo_icp_shard_finish": (_i, [_vp, C.POINTER(IcpCfg), _vp, _vp, C.POINTER(_i), C.POINTER(IcpStats)]),
     "b2lo_se3_mul": (None, [_vp, _vp, _vp]),
     "b2lo_se3_inv": (None, [_vp, _vp]),
     "b2lo_se3_from_rt": (None, [_vp, _vp]),

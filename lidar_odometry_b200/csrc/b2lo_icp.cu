@@ -350,7 +350,8 @@ template <int V> __device__ __forceinline__ void warp_sum_multi(double (&v)[V]) 
 // the discrete outputs (iteration counts, arg-min alpha) only on near-exact ties - tests/ assert they match the oracle.
 __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict__ d_npts, IcpState* st, IcpParams prm, const double* __restrict__ res,
                                                            const int* __restrict__ slot, const int* __restrict__ cidx, const int* __restrict__ tilecnt,
-                                                           int* tileoff, const PkoTables* __restrict__ T, const int* __restrict__ hits, double* gmm_out) {
+                                                           int* tileoff, const PkoTables* __restrict__ T, const int* __restrict__ hits, double* gmm_out,
+                                                           const double* __restrict__ ext_sample, int ext_C, double ext_scale) {
   if (st->done) return;
   __shared__ int sm[40];
   __shared__ double smd[40];
@@ -361,6 +362,16 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
   __shared__ double s_par[3][4];
   const int tid = threadIdx.x;
   const long long c0 = clock64();
+  long long c1 = c0, c2 = c0;
+  int ns;
+  if (ext_sample) {
+    // point-sharded mode: the globally drawn, already normalised sample arrives from the all-reduce (b2lo_icp_shard_*)
+    if (!prm.use_pko) { if (tid == 0) { st->delta = prm.robust_delta; st->em_iters = 0; st->kmeans_iters = 0; st->scale = ext_scale; st->n_corr = ext_C; } return; }
+    ns = T->sample_size < ext_C ? T->sample_size : ext_C;
+    if (tid < ns) s_x[tid] = ext_sample[tid];
+    if (tid == 0) { st->scale = ext_scale; st->n_corr = ext_C; }
+    __syncthreads();
+  } else {
   const int npts = *d_npts;
   const int ctile = prm.ctile;
   const int ntiles = (npts + ctile - 1) / ctile;
@@ -381,7 +392,7 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
     return;
   }
   // 2. residual normalisation scale, first iteration only (ICP.cpp:304-316)
-  const long long c1 = clock64();
+  c1 = clock64();
   double scale = st->scale;
   if (st->iter == 0) {
     double acc = 0.0;
@@ -395,9 +406,9 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
   }
   if (!prm.use_pko) { if (tid == 0) { st->delta = prm.robust_delta; st->em_iters = 0; st->kmeans_iters = 0; } return; }
   const double sdiv = fmax(scale, 1e-6);
-  const long long c2 = clock64();
+  c2 = clock64();
   // 3. the sample: residuals[idx[0..ns)] of the shuffled index vector (AdaptiveMEstimator.cpp:319-331)
-  const int ns = T->sample_size < C ? T->sample_size : C;
+  ns = T->sample_size < C ? T->sample_size : C;
   const int mode = C >= 65536 ? 2 : ((C & 1) ? 1 : 0);
   if (tid < MAXS) s_head[tid] = T->head_r[mode][tid];
   __syncthreads();
@@ -427,6 +438,7 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
     s_x[tid] = res[q] / sdiv;
   }
   __syncthreads();
+  }
   const long long c3 = clock64();
   if (tid >= 96) return;
   const int lane = tid & 31, c = tid >> 5;   // warp c <-> mixture component / k-means cluster c
@@ -628,7 +640,7 @@ __device__ void gn_finish(IcpState* st, const IcpParams& prm, const double* acc 
 template <bool SURFEL>
 __global__ void __launch_bounds__(TILE) k_icp_gn(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, IcpState* st, IcpParams prm,
                                                  const double* __restrict__ res, const int* __restrict__ slot, const float4* __restrict__ plane,
-                                                 double* partial) {
+                                                 double* partial, double* ext_out) {
   if (st->done) return;
   __shared__ double red[8][28];
   __shared__ float sR[9], sT[3];
@@ -722,6 +734,11 @@ __global__ void __launch_bounds__(TILE) k_icp_gn(MapDev M, const float4* __restr
     }
   }
   __syncthreads();
+  if (ext_out) {  // point-sharded mode: hand this rank's 28 partial sums to the all-reduce; b2lo_icp_shard_finish solves
+    if (threadIdx.x < 28) ext_out[threadIdx.x] = red[0][threadIdx.x];
+    if (threadIdx.x == 0) st->ticket = 0u;
+    return;
+  }
   if (threadIdx.x == 0) {
     const long long g1 = clock64();
     st->ticket = 0u;
@@ -848,7 +865,7 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
     }
     prof_begin(ctx, PS_PKO1);
     k_icp_pko1<<<1, PKO_THREADS, 0, s>>>(d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff, ctx->d_pko,
-                                         ctx->d_pko_hits, gmm);
+                                         ctx->d_pko_hits, gmm, nullptr, 0, 0.0);
     prof_end(ctx);
     if (cfg->use_adaptive_m_estimator) {
       prof_begin(ctx, PS_PKO2);
@@ -856,8 +873,8 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
       prof_end(ctx);
     }
     prof_begin(ctx, PS_GN);
-    if (surfel) k_icp_gn<true><<<grid, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, nullptr, ctx->i_partial);
-    else k_icp_gn<false><<<grid, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->k_plane, ctx->i_partial);
+    if (surfel) k_icp_gn<true><<<grid, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, nullptr, ctx->i_partial, nullptr);
+    else k_icp_gn<false><<<grid, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->k_plane, ctx->i_partial, nullptr);
     prof_end(ctx);
     ctx->launches += cfg->use_adaptive_m_estimator ? 4 : 3;
   }
@@ -865,6 +882,74 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
   ctx->launches += 2;
   B2_CUDA(cudaGetLastError());
   return B2LO_OK;
+}
+
+// ---- point-sharded mode: queries split across ranks, map replicated ---------------------------------------
+// local statistics of this rank's shard after K2: tile offsets, accepted count, sum r, sum r^2
+__global__ void __launch_bounds__(256) k_shard_stats(const int* __restrict__ d_npts, IcpState* st, IcpParams prm, const double* __restrict__ res,
+                                                      const int* __restrict__ slot, const int* __restrict__ tilecnt, int* tileoff, double* stats3) {
+  __shared__ int sm[40];
+  __shared__ double smd[40];
+  const int tid = threadIdx.x;
+  const int npts = *d_npts;
+  const int ntiles = (npts + prm.ctile - 1) / prm.ctile;
+  int base = 0;
+  for (int t0 = 0; t0 < ntiles; t0 += blockDim.x) {
+    int t = t0 + tid;
+    int c = t < ntiles ? tilecnt[t] : 0, tot;
+    int e = block_excl_scan(c, &tot, sm);
+    if (t < ntiles) tileoff[t] = base + e;
+    base += tot;
+  }
+  double a1 = 0.0, a2 = 0.0;
+  for (int i = tid; i < npts; i += blockDim.x) if (slot[i] >= 0) { double r = res[i]; a1 += r; a2 += r * r; }
+  a1 = block_sum_d(a1, smd);
+  a2 = block_sum_d(a2, smd);
+  if (tid == 0) { st->n_blocks = base; stats3[0] = (double)base; stats3[1] = a1; stats3[2] = a2; }
+}
+// this rank's contribution to the global GMM sample: position j of shuffle(iota(C_total)) is a global compacted index;
+// the rank owning it ([offset, offset + C_local)) writes the normalised residual, everybody else writes 0
+__global__ void __launch_bounds__(MAXS) k_shard_sample(const int* __restrict__ d_npts, IcpState* st, IcpParams prm, const double* __restrict__ res,
+                                                        const int* __restrict__ cidx, const int* __restrict__ tileoff, const PkoTables* __restrict__ T,
+                                                        const int* __restrict__ hits, long long offset, long long c_total, double scale, double* sample) {
+  __shared__ int s_head[MAXS];
+  const int tid = threadIdx.x;
+  const int C = (int)c_total;
+  const int c_local = st->n_blocks;  // accepted count of this shard (k_shard_stats)
+  const int npts = *d_npts;
+  const int ntiles = (npts + prm.ctile - 1) / prm.ctile;
+  const int mode = C >= 65536 ? 2 : ((C & 1) ? 1 : 0);
+  s_head[tid] = T->head_r[mode][tid];
+  __syncthreads();
+  const int ns = T->sample_size < C ? T->sample_size : C;
+  double out = 0.0;
+  if (tid < ns) {
+    const int lo = T->hit_off[mode][tid], hi = T->hit_off[mode][tid + 1];
+    int best = -1;
+    for (int q = lo; q < hi; ++q) { int v = hits[q]; if (v < C) best = v; else break; }
+    long long ci = best;
+    if (best < 0) {
+      int pos = tid;
+      const int top = C - 1 < MAXS - 1 ? C - 1 : MAXS - 1;
+      for (int i = top; i >= 1; --i) { int r = s_head[i]; pos = (pos == i) ? r : ((pos == r) ? i : pos); }
+      ci = pos;
+    }
+    ci -= offset;
+    if (ci >= 0 && ci < c_local) {
+      int tl = 0, th = ntiles - 1;
+      while (tl < th) { int mid = (tl + th + 1) >> 1; if (tileoff[mid] <= (int)ci) tl = mid; else th = mid - 1; }
+      int q = cidx[tl * prm.ctile + ((int)ci - tileoff[tl])];
+      out = res[q] / fmax(scale, 1e-6);
+    }
+  }
+  if (tid < MAXS) sample[tid] = out;
+}
+__global__ void k_shard_finish(IcpState* st, IcpParams prm, const double* __restrict__ acc28) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && !st->done) {
+    double acc[28];
+    for (int i = 0; i < 28; ++i) acc[i] = acc28[i];
+    gn_finish(st, prm, acc);
+  }
 }
 
 __global__ void k_lookup(MapDev M, float px, float py, float pz, float* out7) {
@@ -984,5 +1069,131 @@ extern "C" int b2lo_icp_correspondences_knn(b2lo_map* map, const float* local_xy
   cudaFree(d_idx); cudaFree(d_d2); cudaFree(d_found); cudaFree(d_state); cudaFree(d_n); cudaFree(d_c); cudaFree(d_r);
   if (n_accepted) { size_t c = 0; for (size_t i = 0; i < m; ++i) c += (state[i] == 2); *n_accepted = c; }
   if (n_scanned) *n_scanned = (size_t)ctx->h_counts[40];
+  return B2LO_OK;
+}
+
+// ---- point-sharded scan-to-map ICP: per-phase entry points, the collectives run between them on the caller's side -------------
+static void shard_params(const b2lo_icp_cfg* cfg, size_t npts_cap, IcpParams& prm, int& qpt) {
+  prm.max_iterations = cfg->max_iterations; prm.min_corr = cfg->min_correspondence_points; prm.use_robust = cfg->use_robust_loss;
+  prm.loss_type = cfg->loss_type; prm.use_pko = cfg->use_adaptive_m_estimator; prm.use_surfel = 1;
+  prm.tol_t = cfg->translation_tolerance; prm.tol_r = cfg->rotation_tolerance; prm.max_dist = cfg->max_correspondence_distance;
+  prm.robust_delta = cfg->robust_loss_delta;
+  qpt = (npts_cap >= 65536) ? 4 : 1;
+  prm.ctile = TILE * qpt;
+}
+static int shard_check(b2lo_map* map, const b2lo_icp_cfg* cfg) {
+  if (!map || !cfg) return B2LO_E_ARG;
+  if (!cfg->use_surfel_correspondence) { set_error("the point-sharded mode supports surfel correspondence only"); return B2LO_E_ARG; }
+  if (cfg->max_iterations < 1 || cfg->max_iterations > B2LO_MAX_ITERS) { set_error("max_iterations must be in [1,%d]", B2LO_MAX_ITERS); return B2LO_E_ARG; }
+  return B2LO_OK;
+}
+extern "C" int b2lo_icp_shard_begin(b2lo_map* map, const float* local_xyz, size_t m, size_t stride_floats, const float T_init[16], const b2lo_icp_cfg* cfg) {
+  int rc = shard_check(map, cfg);
+  if (rc) return rc;
+  if (!T_init || stride_floats < 3) return B2LO_E_ARG;
+  std::lock_guard<std::recursive_mutex> lk(map->mu);
+  b2lo_ctx* ctx = map->ctx;
+  std::lock_guard<std::mutex> lk2(ctx->mu);
+  cudaSetDevice(ctx->device);
+  if ((rc = icp_build_pko(ctx, cfg))) return rc;
+  if ((rc = ctx_stage_h2d(ctx, local_xyz, m, stride_floats, 1, ctx->d_query, ctx->d_nquery))) return rc;
+  ctx->shard_m = m;
+  Init16 Ti;
+  for (int i = 0; i < 16; ++i) Ti.m[i] = T_init[i];
+  k_icp_begin<<<1, 32, 0, ctx->stream>>>(ctx->d_icp, Ti, 0);
+  ctx->launches++;
+  B2_CUDA(cudaGetLastError());
+  return B2LO_OK;
+}
+extern "C" int b2lo_icp_shard_corr(b2lo_map* map, const b2lo_icp_cfg* cfg, double* stats3_dev) {
+  int rc = shard_check(map, cfg);
+  if (rc) return rc;
+  if (!stats3_dev) return B2LO_E_ARG;
+  std::lock_guard<std::recursive_mutex> lk(map->mu);
+  b2lo_ctx* ctx = map->ctx;
+  cudaSetDevice(ctx->device);
+  IcpParams prm; int qpt;
+  const size_t m = ctx->shard_m ? ctx->shard_m : 1;
+  shard_params(cfg, m, prm, qpt);
+  int ctiles = (int)((m + prm.ctile - 1) / prm.ctile);
+  int grid = ctiles > ctx->sm_count * 8 ? ctx->sm_count * 8 : ctiles;
+  cudaStream_t s = ctx->stream;
+  prof_begin(ctx, PS_CORR);
+  if (qpt == 4) k_icp_corr<4><<<grid, TILE, 0, s>>>(map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt);
+  else k_icp_corr<1><<<grid, TILE, 0, s>>>(map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt);
+  prof_end(ctx);
+  k_shard_stats<<<1, 256, 0, s>>>(ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_blkcnt, ctx->i_blkoff, stats3_dev);
+  ctx->launches += 2;
+  B2_CUDA(cudaGetLastError());
+  return B2LO_OK;
+}
+extern "C" int b2lo_icp_shard_sample(b2lo_map* map, const b2lo_icp_cfg* cfg, long long offset, long long c_total, double scale, double* sample_dev) {
+  int rc = shard_check(map, cfg);
+  if (rc) return rc;
+  if (!sample_dev || c_total < 1 || c_total > (1ll << 22)) { set_error("shard_sample: total correspondence count outside [1, 2^22]"); return B2LO_E_ARG; }
+  std::lock_guard<std::recursive_mutex> lk(map->mu);
+  b2lo_ctx* ctx = map->ctx;
+  cudaSetDevice(ctx->device);
+  IcpParams prm; int qpt;
+  shard_params(cfg, ctx->shard_m ? ctx->shard_m : 1, prm, qpt);
+  k_shard_sample<<<1, MAXS, 0, ctx->stream>>>(ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_cidx, ctx->i_blkoff, ctx->d_pko, ctx->d_pko_hits, offset, c_total,
+                                              scale, sample_dev);
+  ctx->launches++;
+  B2_CUDA(cudaGetLastError());
+  return B2LO_OK;
+}
+extern "C" int b2lo_icp_shard_accumulate(b2lo_map* map, const b2lo_icp_cfg* cfg, long long c_total, double scale, const double* sample_dev, double* acc28_dev) {
+  int rc = shard_check(map, cfg);
+  if (rc) return rc;
+  if (!sample_dev || !acc28_dev) return B2LO_E_ARG;
+  std::lock_guard<std::recursive_mutex> lk(map->mu);
+  b2lo_ctx* ctx = map->ctx;
+  cudaSetDevice(ctx->device);
+  IcpParams prm; int qpt;
+  const size_t m = ctx->shard_m ? ctx->shard_m : 1;
+  shard_params(cfg, m, prm, qpt);
+  cudaStream_t s = ctx->stream;
+  double* gmm = ctx->i_partial + (size_t)ctx->i_max_blocks * 28;
+  double* js = gmm + 120;
+  unsigned int* tk = reinterpret_cast<unsigned int*>(js + 132);
+  int ntiles = (int)((m + TILE - 1) / TILE);
+  int grid = ntiles < 1 ? 1 : (ntiles > ctx->i_max_blocks ? ctx->i_max_blocks : ntiles);
+  prof_begin(ctx, PS_PKO1);
+  k_icp_pko1<<<1, PKO_THREADS, 0, s>>>(ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff, ctx->d_pko,
+                                       ctx->d_pko_hits, gmm, sample_dev, (int)c_total, scale);
+  prof_end(ctx);
+  if (cfg->use_adaptive_m_estimator) { k_icp_pko2<<<cfg->num_alpha_segments, 128, 0, s>>>(ctx->d_icp, prm, ctx->d_pko, gmm, js, tk); ctx->launches++; }
+  prof_begin(ctx, PS_GN);
+  k_icp_gn<true><<<grid, TILE, 0, s>>>(map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, nullptr, ctx->i_partial, acc28_dev);
+  prof_end(ctx);
+  ctx->launches += 2;
+  B2_CUDA(cudaGetLastError());
+  return B2LO_OK;
+}
+extern "C" int b2lo_icp_shard_finish(b2lo_map* map, const b2lo_icp_cfg* cfg, const double* acc28_dev, float T_out[16], int* done, b2lo_icp_stats* stats) {
+  int rc = shard_check(map, cfg);
+  if (rc) return rc;
+  if (!acc28_dev || !T_out || !done) return B2LO_E_ARG;
+  std::lock_guard<std::recursive_mutex> lk(map->mu);
+  b2lo_ctx* ctx = map->ctx;
+  cudaSetDevice(ctx->device);
+  IcpParams prm; int qpt;
+  shard_params(cfg, ctx->shard_m ? ctx->shard_m : 1, prm, qpt);
+  k_shard_finish<<<1, 32, 0, ctx->stream>>>(ctx->d_icp, prm, acc28_dev);
+  ctx->launches++;
+  B2_CUDA(cudaMemcpyAsync(ctx->h_icp, ctx->d_icp, sizeof(IcpState), cudaMemcpyDeviceToHost, ctx->stream));
+  B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->d2h_bytes += sizeof(IcpState);
+  const IcpState* h = ctx->h_icp;
+  Pose p;
+  for (int i = 0; i < 9; ++i) p.R.m[i] = h->R[i];
+  for (int i = 0; i < 3; ++i) p.t[i] = h->t[i];
+  pose_to_T16(p, T_out);
+  *done = h->done;
+  if (stats) {
+    stats->status = h->status; stats->num_iterations = h->num_iterations; stats->num_correspondences = h->n_corr; stats->converged = h->converged;
+    stats->initial_cost = h->initial_cost; stats->final_cost = h->final_cost; stats->device_ms = 0.0f;
+    std::memcpy(stats->it, h->trace, sizeof(stats->it));
+  }
   return B2LO_OK;
 }

@@ -76,6 +76,7 @@ struct b2lo_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_stage = nullptr;
   bool stage_busy = false; bool sim_attr_set = false;
   int sm_count = 148;
+  size_t shard_m = 0;              // query count of the current point-sharded optimize (b2lo_icp_shard_begin)
   size_t feat_cap_hint = 0;        // host-known upper bound of *d_nfeat (samples of the last filter run)
   cudaGraphExec_t icp_graph_exec = nullptr; unsigned long long icp_graph_sig = 0;
   b2::MapDev* d_mapdev = nullptr;

@@ -390,3 +390,73 @@ def test_device_resident_scan_matches_host_scan(b2, small_kitti):
         rb = b.process_dev(t.data_ptr(), s.shape[0], s.shape[1])
         assert np.array_equal(bits(ra["pose"]), bits(rb["pose"])) and ra["n_features"] == rb["n_features"] and ra["n_corr"] == rb["n_corr"]
     assert a.ctx.launch_count > 0
+
+
+# ---- point-sharded mode ----------------------------------------------------------------------------------
+def test_point_sharded_single_rank_matches_fused(orc, b2, small_kitti):
+    """World size 1: the phase-split path (K2 | stats | sample | PKO + partial sums | finish) must reproduce the fused
+    device-resident loop: same C, same alpha, same iteration count, pose within the per-iteration tolerance."""
+    scans, poses = small_kitti
+    omap, gmap, kfs = _built_maps(orc, b2, scans, poses)
+    ame = b2.AdaptiveMEstimator()
+    fused = b2.IterativeClosestPointOptimizer(b2.ICPConfig(), ame)
+    shard = b2.PointShardedICP(b2.ICPConfig(), ame)
+    for k in (3, 4):
+        feat, init = kfs[k][0], T32(poses[k - 1])
+        ok_f, T_f = fused.optimize(gmap, feat, init)
+        tr_f = fused.get_last_stats().iterations
+        ok_s, T_s = shard.optimize(gmap, feat, init)
+        tr_s = shard.get_last_stats().iterations
+        assert ok_f and ok_s and len(tr_f) == len(tr_s)
+        assert tr_f[0]["n_corr"] == tr_s[0]["n_corr"] and tr_f[0]["delta"] == tr_s[0]["delta"]
+        assert abs(tr_f[0]["scale"] - tr_s[0]["scale"]) <= 1e-9 * tr_f[0]["scale"]
+        assert _rel(tr_s[0]["H"], tr_f[0]["H"]) < 1e-9 and _rel(tr_s[0]["g"], tr_f[0]["g"]) < 1e-9
+        assert np.linalg.norm(T_f[:3, 3].astype(np.float64) - T_s[:3, 3]) < 1e-5
+    # too few correspondences -> false, output = initial
+    far = T32(poses[3]).copy(); far[:3, 3] += np.float32(900.0)
+    ok_s, T_s = shard.optimize(gmap, kfs[3][0], far)
+    assert not ok_s and np.array_equal(bits(T_s), bits(far))
+
+
+def _sharded_worker(rank, world, port, out):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from lidar_odometry_b200 import api, sharding, synth
+    scans, poses = synth.kitti_sequence(n_scans=4, seed=7, n_rings=64, n_az=600)
+    ctx = api.Context(rank)
+    f = api.FastVoxelFilter(0.5, ctx)
+    gmap = api.VoxelMap(0.5, ctx)
+    feats = [f.filter(s, 8) for s in scans]
+    for k in range(3):   # identical keyframe updates on every rank: the map replica is deterministic
+        T = np.asarray(poses[k], np.float64).astype(np.float32)
+        world_pts = (feats[k] @ T[:3, :3].T + T[:3, 3]).astype(np.float32)
+        gmap.UpdateVoxelMap(world_pts, T[:3, 3].astype(np.float64), 120.0)
+    init = np.asarray(poses[2], np.float64).astype(np.float32)
+    ame = api.AdaptiveMEstimator()
+    lo, hi = sharding.shard_bounds(len(feats[3]), world, rank)
+    shard = api.PointShardedICP(api.ICPConfig(), ame)
+    ok_s, T_s = shard.optimize(gmap, feats[3][lo:hi], init)
+    ok_f, T_f = api.IterativeClosestPointOptimizer(api.ICPConfig(), ame).optimize(gmap, feats[3], init)
+    if rank == 0:
+        np.savez(out, ok_s=ok_s, ok_f=ok_f, T_s=T_s, T_f=T_f, n_s=shard.get_last_stats().iterations[0]["n_corr"],
+                 d_s=shard.get_last_stats().iterations[0]["delta"], coll=shard.collective_seconds)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_point_sharded_two_gpus(tmp_path):
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    out = str(tmp_path / "r0.npz")
+    mp.spawn(_sharded_worker, args=(2, port, out), nprocs=2, join=True)
+    z = np.load(out)
+    assert bool(z["ok_s"]) and bool(z["ok_f"])
+    assert np.linalg.norm(z["T_s"][:3, 3].astype(np.float64) - z["T_f"][:3, 3]) < 1e-5
