@@ -108,7 +108,8 @@ int ctx_reserve_points(b2lo_ctx* ctx, size_t n) {
       (rc = dev_alloc(&ctx->f_lead, cap)) || (rc = dev_alloc(&ctx->f_bucket, cap)) || (rc = dev_alloc(&ctx->f_ordered, cap)))
     return rc;
   if ((rc = dev_alloc(&ctx->i_res, cap)) || (rc = dev_alloc(&ctx->i_slot, cap)) || (rc = dev_alloc(&ctx->i_cidx, cap + 1024)) ||
-      (rc = dev_alloc(&ctx->i_blkcnt, cap / 256 + 8)) || (rc = dev_alloc(&ctx->i_blkoff, cap / 256 + 8)))
+      (rc = dev_alloc(&ctx->i_blkcnt, cap / 256 + 8)) || (rc = dev_alloc(&ctx->i_blkoff, cap / 256 + 8)) ||
+      (rc = dev_alloc(&ctx->i_tilesum, 2 * (cap / 256 + 8))))
     return rc;
   if (ctx->h_stage) { cudaFreeHost(ctx->h_stage); ctx->h_stage = nullptr; }
   ctx->h_stage_floats = cap * 6 + 64;
@@ -241,7 +242,7 @@ extern "C" int b2lo_ctx_destroy(b2lo_ctx* ctx) {
   if (ctx->icp_graph_exec) cudaGraphExecDestroy(ctx->icp_graph_exec);
   void* dptrs[] = {ctx->d_stage, ctx->d_feat, ctx->d_feat_key, ctx->d_nfeat, ctx->d_query, ctx->d_nquery, ctx->d_world, ctx->f_tab, ctx->f_samp,
                    ctx->f_slot, ctx->f_vid, ctx->f_segstart, ctx->f_segcnt, ctx->f_lead, ctx->f_bucket, ctx->f_ordered, ctx->i_res, ctx->i_slot,
-                   ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff, ctx->i_partial, ctx->d_icp, ctx->d_pko, ctx->d_pko_hits, ctx->d_tap_state,
+                   ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff, ctx->i_tilesum, ctx->i_partial, ctx->d_icp, ctx->d_pko, ctx->d_pko_hits, ctx->d_tap_state,
                    ctx->d_tap_key, ctx->d_tap_morton, ctx->d_tap_n, ctx->d_tap_c, ctx->d_mapdev, ctx->k_idx, ctx->k_n, ctx->k_unres, ctx->k_nunres,
                    ctx->k_plane};
   for (void* p : dptrs) if (p) cudaFree(p);
@@ -386,6 +387,7 @@ extern "C" int b2lo_icp_optimize(b2lo_map* map, const float* local_xyz, size_t m
     if (stats) { std::memset(stats, 0, sizeof *stats); stats->status = B2LO_S_INSUFFICIENT; }
     return B2LO_S_INSUFFICIENT;
   }
+  { int rr = ctx_reserve_points(ctx, m); if (rr) return rr; }  // may reallocate d_query: reserve before taking the pointer
   int rc = ctx_stage_h2d(ctx, local_xyz, m, stride_floats, 1, ctx->d_query, ctx->d_nquery);
   if (rc) return rc;
   return icp_optimize_common(map, ctx->d_query, ctx->d_nquery, m, T_init, cfg, T_out, stats);

@@ -66,6 +66,22 @@ __device__ __forceinline__ double gate_residual(const float* n, const float* c, 
   return fabs(((double)n[0] * d0 + (double)n[1] * d1) + (double)n[2] * d2);
 }
 
+// block-wide sums of two doubles (warp shuffles + one shared exchange); result valid in thread 0
+__device__ __forceinline__ void block_sum2_t0(double& a, double& b, double* smd /*>= 16*/) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  if (lane == 0) { smd[2 * w] = a; smd[2 * w + 1] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    double sa = 0.0, sb = 0.0;
+    for (int i = 0; i < nw; ++i) { sa += smd[2 * i]; sb += smd[2 * i + 1]; }
+    a = sa; b = sb;
+  }
+  __syncthreads();
+}
+
 // K2.  One thread takes QPT consecutive queries (64 B of the float4 query stream), issues their QPT first hash probes
 // back to back (independent 32 B sectors in flight), then gates and compacts.  Accepted queries are written in
 // ascending query order per CT-query tile (cidx) with the tile count (tilecnt); k_icp_pko1 scans the tile counts.
@@ -73,9 +89,10 @@ __device__ __forceinline__ double gate_residual(const float* n, const float* c, 
 // QPT = 1 for scan-sized clouds (more threads, shortest chain), 4 for dense clouds (more probes in flight per thread).
 template <int QPT>
 __global__ void __launch_bounds__(TILE) k_icp_corr(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, IcpState* st,
-                                                   IcpParams prm, double* res, int* slot_out, int* cidx, int* tilecnt) {
+                                                   IcpParams prm, double* res, int* slot_out, int* cidx, int* tilecnt, double* tilesum) {
   if (st->done) return;
   __shared__ int sm[40];
+  __shared__ double smd2[16];
   __shared__ float sR[9], sT[3];
   if (threadIdx.x < 9) sR[threadIdx.x] = st->R[threadIdx.x];
   if (threadIdx.x < 3) sT[threadIdx.x] = st->t[threadIdx.x];
@@ -102,6 +119,7 @@ __global__ void __launch_bounds__(TILE) k_icp_corr(MapDev M, const float4* __res
 #pragma unroll
     for (int u = 0; u < QPT; ++u) ea[u] = __ldg(reinterpret_cast<const float4*>(&M.l1_tab[hs[u]]));   // QPT sectors in flight
     int okm = 0, nok = 0;
+    double a1 = 0.0, a2 = 0.0;   // sum r, sum r^2 over the accepted queries of this tile (residual scale, ICP.cpp:304-316)
 #pragma unroll
     for (int u = 0; u < QPT; ++u) {
       const int i = i0 + u;
@@ -127,13 +145,14 @@ __global__ void __launch_bounds__(TILE) k_icp_corr(MapDev M, const float4* __res
         }
       }
       if (i < npts) { slot_out[i] = s; res[i] = r; }
-      if (s >= 0) { okm |= 1 << u; ++nok; }
+      if (s >= 0) { okm |= 1 << u; ++nok; a1 += r; a2 += r * r; }
     }
     int total;
     int off = tile * CT + block_excl_scan(nok, &total, sm);
 #pragma unroll
     for (int u = 0; u < QPT; ++u) if (okm & (1 << u)) cidx[off++] = i0 + u;
-    if (threadIdx.x == 0) tilecnt[tile] = total;
+    block_sum2_t0(a1, a2, smd2);
+    if (threadIdx.x == 0) { tilecnt[tile] = total; tilesum[2 * tile] = a1; tilesum[2 * tile + 1] = a2; }
   }
 }
 
@@ -185,9 +204,10 @@ __global__ void __launch_bounds__(256) k_knn_brute(MapDev M, const float4* __res
 // plane fit + gate + per-tile compaction (same outputs as k_icp_corr, plus the per-query plane)
 __global__ void __launch_bounds__(TILE) k_knn_gate(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, IcpState* st, IcpParams prm,
                                                    const int* __restrict__ knn_idx, const int* __restrict__ knn_n, int* n_unres, double* res,
-                                                   int* slot_out, int* cidx, int* tilecnt, float4* plane) {
+                                                   int* slot_out, int* cidx, int* tilecnt, float4* plane, double* tilesum) {
   if (st->done) return;
   __shared__ int sm[40];
+  __shared__ double smd2[16];
   __shared__ float sR[9], sT[3];
   if (threadIdx.x < 9) sR[threadIdx.x] = st->R[threadIdx.x];
   if (threadIdx.x < 3) sT[threadIdx.x] = st->t[threadIdx.x];
@@ -198,6 +218,7 @@ __global__ void __launch_bounds__(TILE) k_knn_gate(MapDev M, const float4* __res
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     int i = tile * TILE + threadIdx.x;
     int ok = 0;
+    double a1 = 0.0, a2 = 0.0;
     if (i < npts) {
       float4 p = pts[i];
       float w[3], n[3] = {0, 0, 0}, c[3] = {0, 0, 0};
@@ -209,6 +230,7 @@ __global__ void __launch_bounds__(TILE) k_knn_gate(MapDev M, const float4* __res
       double r = 0.0;
       int state = knn_fit(M, top, w, prm.max_dist, n, c, &r);
       ok = (state == 2);
+      if (ok) { a1 = r; a2 = r * r; }
       slot_out[i] = ok ? 0 : -1;
       res[i] = r;
       plane[2 * i] = make_float4(n[0], n[1], n[2], c[0]);
@@ -217,7 +239,8 @@ __global__ void __launch_bounds__(TILE) k_knn_gate(MapDev M, const float4* __res
     int total;
     int off = block_excl_scan(ok, &total, sm);
     if (ok) cidx[tile * TILE + off] = i;
-    if (threadIdx.x == 0) tilecnt[tile] = total;
+    block_sum2_t0(a1, a2, smd2);
+    if (threadIdx.x == 0) { tilecnt[tile] = total; tilesum[2 * tile] = a1; tilesum[2 * tile + 1] = a2; }
   }
 }
 // parity tap of the KDTree-mode correspondence at the pose held in st
@@ -351,7 +374,8 @@ template <int V> __device__ __forceinline__ void warp_sum_multi(double (&v)[V]) 
 __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict__ d_npts, IcpState* st, IcpParams prm, const double* __restrict__ res,
                                                            const int* __restrict__ slot, const int* __restrict__ cidx, const int* __restrict__ tilecnt,
                                                            int* tileoff, const PkoTables* __restrict__ T, const int* __restrict__ hits, double* gmm_out,
-                                                           const double* __restrict__ ext_sample, int ext_C, double ext_scale) {
+                                                           const double* __restrict__ ext_sample, int ext_C, double ext_scale,
+                                                           const double* __restrict__ tilesum) {
   if (st->done) return;
   __shared__ int sm[40];
   __shared__ double smd[40];
@@ -395,12 +419,13 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
   c1 = clock64();
   double scale = st->scale;
   if (st->iter == 0) {
-    double acc = 0.0;
-    for (int i = tid; i < npts; i += blockDim.x) if (slot[i] >= 0) acc += res[i];
-    double mean = block_sum_d(acc, smd) / (double)C;
-    acc = 0.0;
-    for (int i = tid; i < npts; i += blockDim.x) if (slot[i] >= 0) { double d = res[i] - mean; acc += d * d; }
-    double var = block_sum_d(acc, smd) / (double)C;
+    // population sigma / 6 from the per-tile raw moments K2 left behind (var = E[r^2] - mean^2)
+    double a1 = 0.0, a2 = 0.0;
+    for (int t = tid; t < ntiles; t += blockDim.x) { a1 += tilesum[2 * t]; a2 += tilesum[2 * t + 1]; }
+    a1 = block_sum_d(a1, smd);
+    a2 = block_sum_d(a2, smd);
+    const double mean = a1 / (double)C;
+    const double var = fmax(a2 / (double)C - mean * mean, 0.0);
     scale = sqrt(var) / 6.0;
     if (tid == 0) st->scale = scale;
   }
@@ -851,21 +876,21 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
   for (int it = 0; it < cfg->max_iterations; ++it) {
     if (surfel) {
       prof_begin(ctx, PS_CORR);
-      if (qpt == 4) k_icp_corr<4><<<grid_corr, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt);
-      else k_icp_corr<1><<<grid_corr, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt);
+      if (qpt == 4) k_icp_corr<4><<<grid_corr, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum);
+      else k_icp_corr<1><<<grid_corr, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum);
       prof_end(ctx);
     } else {
       prof_begin(ctx, PS_KNN);
       k_knn_search<<<grid, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, ctx->k_idx, ctx->k_n, ctx->k_unres, ctx->k_nunres);
       k_knn_brute<<<ctx->sm_count * 2, 256, 0, s>>>(map->d, d_pts, ctx->d_icp, ctx->k_idx, ctx->k_n, ctx->k_unres, ctx->k_nunres);
       k_knn_gate<<<grid, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->k_idx, ctx->k_n, ctx->k_nunres, ctx->i_res, ctx->i_slot,
-                                       ctx->i_cidx, ctx->i_blkcnt, ctx->k_plane);
+                                       ctx->i_cidx, ctx->i_blkcnt, ctx->k_plane, ctx->i_tilesum);
       prof_end(ctx);
       ctx->launches += 2;
     }
     prof_begin(ctx, PS_PKO1);
     k_icp_pko1<<<1, PKO_THREADS, 0, s>>>(d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff, ctx->d_pko,
-                                         ctx->d_pko_hits, gmm, nullptr, 0, 0.0);
+                                         ctx->d_pko_hits, gmm, nullptr, 0, 0.0, ctx->i_tilesum);
     prof_end(ctx);
     if (cfg->use_adaptive_m_estimator) {
       prof_begin(ctx, PS_PKO2);
@@ -887,7 +912,8 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
 // ---- point-sharded mode: queries split across ranks, map replicated ---------------------------------------
 // local statistics of this rank's shard after K2: tile offsets, accepted count, sum r, sum r^2
 __global__ void __launch_bounds__(256) k_shard_stats(const int* __restrict__ d_npts, IcpState* st, IcpParams prm, const double* __restrict__ res,
-                                                      const int* __restrict__ slot, const int* __restrict__ tilecnt, int* tileoff, double* stats3) {
+                                                      const int* __restrict__ slot, const int* __restrict__ tilecnt, int* tileoff, double* stats3,
+                                                      const double* __restrict__ tilesum) {
   __shared__ int sm[40];
   __shared__ double smd[40];
   const int tid = threadIdx.x;
@@ -902,7 +928,7 @@ __global__ void __launch_bounds__(256) k_shard_stats(const int* __restrict__ d_n
     base += tot;
   }
   double a1 = 0.0, a2 = 0.0;
-  for (int i = tid; i < npts; i += blockDim.x) if (slot[i] >= 0) { double r = res[i]; a1 += r; a2 += r * r; }
+  for (int t = tid; t < ntiles; t += blockDim.x) { a1 += tilesum[2 * t]; a2 += tilesum[2 * t + 1]; }
   a1 = block_sum_d(a1, smd);
   a2 = block_sum_d(a2, smd);
   if (tid == 0) { st->n_blocks = base; stats3[0] = (double)base; stats3[1] = a1; stats3[2] = a2; }
@@ -975,6 +1001,7 @@ extern "C" int b2lo_icp_correspondences(b2lo_map* map, const float* local_xyz, s
   b2lo_ctx* ctx = map->ctx;
   std::lock_guard<std::mutex> lk2(ctx->mu);
   cudaSetDevice(ctx->device);
+  { int rr = ctx_reserve_points(ctx, m); if (rr) return rr; }  // may reallocate d_query: reserve before taking the pointer
   int rc = ctx_stage_h2d(ctx, local_xyz, m, stride_floats, 1, ctx->d_query, ctx->d_nquery);
   if (rc) return rc;
   int* d_state = nullptr; int* d_key = nullptr; unsigned long long* d_mor = nullptr; float* d_n = nullptr; float* d_c = nullptr; double* d_r = nullptr;
@@ -1033,6 +1060,7 @@ extern "C" int b2lo_icp_correspondences_knn(b2lo_map* map, const float* local_xy
   b2lo_ctx* ctx = map->ctx;
   std::lock_guard<std::mutex> lk2(ctx->mu);
   cudaSetDevice(ctx->device);
+  { int rr = ctx_reserve_points(ctx, m); if (rr) return rr; }  // may reallocate d_query: reserve before taking the pointer
   int rc = ctx_stage_h2d(ctx, local_xyz, m, stride_floats, 1, ctx->d_query, ctx->d_nquery);
   if (rc) return rc;
   if ((rc = knn_reserve(ctx))) return rc;
@@ -1096,6 +1124,7 @@ extern "C" int b2lo_icp_shard_begin(b2lo_map* map, const float* local_xyz, size_
   std::lock_guard<std::mutex> lk2(ctx->mu);
   cudaSetDevice(ctx->device);
   if ((rc = icp_build_pko(ctx, cfg))) return rc;
+  { int rr = ctx_reserve_points(ctx, m); if (rr) return rr; }  // may reallocate d_query: reserve before taking the pointer
   if ((rc = ctx_stage_h2d(ctx, local_xyz, m, stride_floats, 1, ctx->d_query, ctx->d_nquery))) return rc;
   ctx->shard_m = m;
   Init16 Ti;
@@ -1119,10 +1148,10 @@ extern "C" int b2lo_icp_shard_corr(b2lo_map* map, const b2lo_icp_cfg* cfg, doubl
   int grid = ctiles > ctx->sm_count * 8 ? ctx->sm_count * 8 : ctiles;
   cudaStream_t s = ctx->stream;
   prof_begin(ctx, PS_CORR);
-  if (qpt == 4) k_icp_corr<4><<<grid, TILE, 0, s>>>(map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt);
-  else k_icp_corr<1><<<grid, TILE, 0, s>>>(map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt);
+  if (qpt == 4) k_icp_corr<4><<<grid, TILE, 0, s>>>(map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum);
+  else k_icp_corr<1><<<grid, TILE, 0, s>>>(map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum);
   prof_end(ctx);
-  k_shard_stats<<<1, 256, 0, s>>>(ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_blkcnt, ctx->i_blkoff, stats3_dev);
+  k_shard_stats<<<1, 256, 0, s>>>(ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_blkcnt, ctx->i_blkoff, stats3_dev, ctx->i_tilesum);
   ctx->launches += 2;
   B2_CUDA(cudaGetLastError());
   return B2LO_OK;
@@ -1160,7 +1189,7 @@ extern "C" int b2lo_icp_shard_accumulate(b2lo_map* map, const b2lo_icp_cfg* cfg,
   int grid = ntiles < 1 ? 1 : (ntiles > ctx->i_max_blocks ? ctx->i_max_blocks : ntiles);
   prof_begin(ctx, PS_PKO1);
   k_icp_pko1<<<1, PKO_THREADS, 0, s>>>(ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff, ctx->d_pko,
-                                       ctx->d_pko_hits, gmm, sample_dev, (int)c_total, scale);
+                                       ctx->d_pko_hits, gmm, sample_dev, (int)c_total, scale, ctx->i_tilesum);
   prof_end(ctx);
   if (cfg->use_adaptive_m_estimator) { k_icp_pko2<<<cfg->num_alpha_segments, 128, 0, s>>>(ctx->d_icp, prm, ctx->d_pko, gmm, js, tk); ctx->launches++; }
   prof_begin(ctx, PS_GN);

@@ -96,6 +96,7 @@ struct b2lo_ctx {
   int* f_lead = nullptr; int* f_bucket = nullptr; int* f_ordered = nullptr;
   // ICP scratch
   double* i_res = nullptr; int* i_slot = nullptr; int* i_cidx = nullptr; int* i_blkcnt = nullptr; int* i_blkoff = nullptr;
+  double* i_tilesum = nullptr;     // per compaction tile: sum r, sum r^2 of the accepted queries
   double* i_partial = nullptr;     // per-block 28 doubles
   int i_max_blocks = 0;
   b2::IcpState* d_icp = nullptr; b2::IcpState* h_icp = nullptr /*pinned*/;
