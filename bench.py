@@ -289,7 +289,9 @@ def main():
     value = world * K / (max_ms * 1e-3)
     final_l0, final_l1 = r["l0"], r["l1"]
 
-    # ---- e2e: host scans through the public host-buffer call, wall clock, copies inside -------------------------
+    # ---- e2e: host scans (page-locked, as the contract asks) through the public host-buffer call, wall clock, copies inside ------
+    pinned = [torch.from_numpy(s).pin_memory() for s in scans]
+    scans = [t.numpy() for t in pinned]
     odo2 = api.Odometry(ctx)
     for s in scans[:W]:
         odo2.process(s)

@@ -96,6 +96,7 @@ int b2lo_ctx_io_bytes(b2lo_ctx* ctx, unsigned long long* h2d, unsigned long long
 /* optional per-kernel CUDA-event timing on the context stream (adds event records; keep it off when timing whole scans).
  * slots: 0 K1 downsample (5 kernels), 1 K2 surfel correspondence, 2 K4 PKO fit, 3 K4 PKO arg-min, 4 K5 normal equations + solve,
  * 5 K6 map update (all kernels but the cull scan), 6 cloud transform, 7 K3 kNN + plane fit (3 kernels), 8 K6 radius-cull scan */
+int b2lo_ctx_host_us(b2lo_ctx* ctx, double out[8], int reset); /* host wall-clock split of b2lo_odom_process: 0 gather+H2D enqueue, 1 K1+ICP enqueue, 2 wait for the pose, 3 host pose algebra, 4 K6 enqueue + wait (debug aid) */
 int b2lo_ctx_debug_clocks(b2lo_ctx* ctx, long long out[32]); /* SM-clock stamps of the single-CTA phases of the last optimize (debug aid) */
 int b2lo_ctx_profile(b2lo_ctx* ctx, int enable);
 int b2lo_ctx_profile_read(b2lo_ctx* ctx, int slot, double* total_ms, long long* launches);

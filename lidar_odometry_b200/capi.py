@@ -95,6 +95,7 @@ SIGNATURES = {
     "b2lo_ctx_launch_count": (C.c_longlong, [_vp]),
     "b2lo_ctx_io_bytes": (_i, [_vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "b2lo_ctx_debug_clocks": (_i, [_vp, _vp]),
+    "b2lo_ctx_host_us": (_i, [_vp, _vp, _i]),
     "b2lo_ctx_profile": (_i, [_vp, _i]),
     "b2lo_ctx_profile_read": (_i, [_vp, _i, C.POINTER(_d), C.POINTER(C.c_longlong)]),
     "b2lo_filter": (_i, [_vp, _vp, _sz, _sz, _i, _f, _vp, _vp, C.POINTER(_sz)]),

@@ -240,7 +240,7 @@ extern "C" int b2lo_ctx_destroy(b2lo_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->icp_graph_exec) cudaGraphExecDestroy(ctx->icp_graph_exec);
-  void* dptrs[] = {ctx->d_stage, ctx->d_feat, ctx->d_feat_key, ctx->d_nfeat, ctx->d_query, ctx->d_nquery, ctx->d_world, ctx->f_tab, ctx->f_samp,
+  void* dptrs[] = {ctx->d_raw, ctx->d_stage, ctx->d_feat, ctx->d_feat_key, ctx->d_nfeat, ctx->d_query, ctx->d_nquery, ctx->d_world, ctx->f_tab, ctx->f_samp,
                    ctx->f_slot, ctx->f_vid, ctx->f_segstart, ctx->f_segcnt, ctx->f_lead, ctx->f_bucket, ctx->f_ordered, ctx->i_res, ctx->i_slot,
                    ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff, ctx->i_tilesum, ctx->i_partial, ctx->d_icp, ctx->d_pko, ctx->d_pko_hits, ctx->d_tap_state,
                    ctx->d_tap_key, ctx->d_tap_morton, ctx->d_tap_n, ctx->d_tap_c, ctx->d_mapdev, ctx->k_idx, ctx->k_n, ctx->k_unres, ctx->k_nunres,
@@ -286,6 +286,11 @@ extern "C" int b2lo_ctx_debug_clocks(b2lo_ctx* ctx, long long out[32]) {  // clo
   if (!ctx || !out) return B2LO_E_ARG;
   B2_CUDA(cudaStreamSynchronize(ctx->stream));
   B2_CUDA(cudaMemcpy(out, ctx->d_icp->dbg, 32 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return B2LO_OK;
+}
+extern "C" int b2lo_ctx_host_us(b2lo_ctx* ctx, double out[8], int reset) {  // host-side wall-clock split of b2lo_odom_process (debug aid)
+  if (!ctx || !out) return B2LO_E_ARG;
+  for (int i = 0; i < 8; ++i) { out[i] = ctx->host_us[i]; if (reset) ctx->host_us[i] = 0.0; }
   return B2LO_OK;
 }
 extern "C" int b2lo_ctx_io_bytes(b2lo_ctx* ctx, unsigned long long* h2d, unsigned long long* d2h) {

@@ -646,9 +646,33 @@ __device__ void gn_finish(IcpState* st, const IcpParams& prm, const double* acc 
   float dt[3] = {dx[0], dx[1], dx[2]}, dw[3] = {dx[3], dx[4], dx[5]};
   Pose d;
   float wn = sqrtf(sqn3(dw));
-  if (wn < 1e-10f) d.R = so3_project(mat3_identity()); else d.R = so3_exp(dw);
+  // T <- T * SE3(Exp(dw), dt) (ICP.cpp:426-434, MathUtils.h:144-147).  The reference re-projects the exponential and the
+  // product onto SO(3) with an SVD each; both inputs are rotations up to rounding, so one Newton-Schulz step gives the
+  // same nearest rotation (b2lo_math.cuh, so3_project_near) without the two Jacobi-sweep chains on this single thread.
+  if (wn < 1e-10f) d.R = mat3_identity();
+  else {
+    Mat3 I = mat3_identity(), Mx;
+    if (wn < 1e-6f) { Mat3 K = hat(dw); for (int i = 0; i < 9; ++i) Mx.m[i] = I.m[i] + K.m[i]; }
+    else {
+      float ti = 1.0f / wn;
+      float kv[3] = {dw[0] * ti, dw[1] * ti, dw[2] * ti};
+      Mat3 K = hat(kv);
+      float sn = sin_f32(wn), omc = 1.0f - cos_f32(wn);
+      Mat3 oK;
+      for (int i = 0; i < 9; ++i) oK.m[i] = omc * K.m[i];
+      Mat3 KK = mat3_mul(oK, K);
+      for (int i = 0; i < 9; ++i) Mx.m[i] = (I.m[i] + sn * K.m[i]) + KK.m[i];
+    }
+    d.R = so3_project_near(Mx);
+  }
   d.t[0] = dt[0]; d.t[1] = dt[1]; d.t[2] = dt[2];
-  Pose nxt = pose_mul(cur, d);
+  Pose nxt;
+  {
+    float rt[3];
+    mat3_vec(cur.R.m, d.t, rt);
+    nxt.t[0] = cur.t[0] + rt[0]; nxt.t[1] = cur.t[1] + rt[1]; nxt.t[2] = cur.t[2] + rt[2];
+    nxt.R = so3_project_near(mat3_mul(cur.R, d.R));
+  }
   for (int i = 0; i < 9; ++i) st->R[i] = nxt.R.m[i];
   for (int i = 0; i < 3; ++i) st->t[i] = nxt.t[i];
   if (tr) { for (int i = 0; i < 6; ++i) tr->dx[i] = dx[i]; pose_to_T16(nxt, tr->T_out); }

@@ -85,6 +85,7 @@ struct b2lo_ctx {
   // pinned staging + device staging for host clouds
   float* h_stage = nullptr; size_t h_stage_floats = 0;
   float* d_stage = nullptr; size_t d_stage_floats = 0;
+  float* d_raw = nullptr; size_t raw_floats = 0;     // raw scan DMA target when the caller's buffer is page-locked
   // feature cloud (output of the filter, input of ICP / transform)
   float4* d_feat = nullptr; unsigned long long* d_feat_key = nullptr; int* d_nfeat = nullptr;
   // ICP query cloud uploaded from the host
@@ -108,6 +109,7 @@ struct b2lo_ctx {
   int* d_tap_state = nullptr; int* d_tap_key = nullptr; unsigned long long* d_tap_morton = nullptr; float* d_tap_n = nullptr; float* d_tap_c = nullptr;
   int* h_counts = nullptr;         // pinned small readback area (64 ints)
   b2::Prof* prof = nullptr;
+  double host_us[8] = {0};         // wall-clock split of the host side of b2lo_odom_process (debug aid): gather, enqueue, wait, ...
   std::mutex mu;
 };
 

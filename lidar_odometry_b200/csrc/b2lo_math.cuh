@@ -186,6 +186,21 @@ B2_HD Mat3 so3_project(const Mat3& R) {
   }
   return M;
 }
+// Nearest rotation of a matrix that is ALREADY orthonormal up to f32 rounding (a product / exponential of rotations):
+// one Newton-Schulz step X <- X (3I - X^T X) / 2 takes an orthogonality error e to 1.5 e^2, i.e. from ~1e-7 to below f32
+// resolution, so the result equals the SVD projection U V^T up to the last bit or two - at a fraction of the ~8k-cycle
+// dependent chain of the Jacobi sweeps.  Used only on the single-thread finish of the device Gauss-Newton iteration;
+// inputs that are not near-orthonormal (|X^T X - I| > 1e-3) fall back to the exact SVD path.
+B2_HD Mat3 so3_project_near(const Mat3& X) {
+  Mat3 Xt = mat3_t(X);
+  Mat3 G = mat3_mul(Xt, X);
+  float dev = 0.0f;
+  for (int i = 0; i < 9; ++i) dev = fmaxf(dev, fabsf(G.m[i] - ((i % 4 == 0) ? 1.0f : 0.0f)));
+  if (!(dev < 1e-3f)) return so3_project(X);
+  Mat3 H;
+  for (int i = 0; i < 9; ++i) H.m[i] = 0.5f * (((i % 4 == 0) ? 3.0f : 0.0f) - G.m[i]);
+  return mat3_mul(X, H);
+}
 B2_HD Mat3 hat(const float* w) {
   Mat3 K;
   K.m[0] = 0.0f; K.m[1] = -w[2]; K.m[2] = w[1];

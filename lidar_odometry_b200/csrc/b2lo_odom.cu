@@ -7,8 +7,12 @@
 // (pose + counters) -> host keyframe decision -> K6 map update on keyframes.  The feature cloud never
 // leaves HBM; only the 16-float pose and a few counters cross PCIe (plus the strided scan upload for
 // b2lo_odom_process).  Loop closure / PGO / viewer stay with the host Estimator and are out of scope.
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include "b2lo_internal.h"
+
+static inline double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 using namespace b2;
 
@@ -100,6 +104,7 @@ static int process_common(b2lo_odom* od, const float* src_dev, size_t ns, size_t
   b2lo_map* map = od->map;
   cudaStream_t st = ctx->stream;
   std::memset(res, 0, sizeof *res);
+  double t0 = now_us();
   int rc = filter_run(ctx, src_dev, ns, sample_stride_floats, od->cfg.voxel_size);
   if (rc) return rc;
   int* hc = ctx->h_counts + 32;
@@ -132,7 +137,10 @@ static int process_common(b2lo_odom* od, const float* src_dev, size_t ns, size_t
       ran_icp = true;
     }
     B2_CUDA(cudaMemcpyAsync(hc, ctx->d_nfeat, sizeof(int), cudaMemcpyDeviceToHost, st));
+    double t1 = now_us();
     B2_CUDA(cudaStreamSynchronize(st));
+    double t2 = now_us();
+    ctx->host_us[1] += t1 - t0; ctx->host_us[2] += t2 - t1;
     ctx->d2h_bytes += sizeof(int);
     res->n_features = hc[0];
     if (hc[0] == 0) return B2LO_S_EMPTY;
@@ -147,13 +155,17 @@ static int process_common(b2lo_odom* od, const float* src_dev, size_t ns, size_t
         result = pose_reproject(opt);  // Estimator.cpp:300-302
       }
     }
+    double t2b = now_us();
     od->pose = result;
     od->velocity = pose_mul(pose_inv(od->prev_pose), od->pose);  // :177
+    double t3 = now_us();
     if (should_create_keyframe(od, od->pose)) {
       rc = create_keyframe(od, ns);
       if (rc) return rc;
       res->keyframe = 1;
     }
+    ctx->host_us[3] += t3 - t2b;
+    ctx->host_us[4] += now_us() - t3;
     od->prev_pose = od->pose;
   }
   pose_to_T16(od->pose, res->pose);
@@ -183,8 +195,37 @@ extern "C" int b2lo_odom_process(b2lo_odom* od, const float* xyz, size_t n, size
   const size_t S = (size_t)(od->cfg.point_stride < 1 ? 1 : od->cfg.point_stride);
   const size_t ns = (n + S - 1) / S;
   B2_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-  // only every S-th point is ever read by the filter (VoxelMap.h:81): gather those into pinned memory, one H2D
+  double tg = now_us();
+  // Page-locked caller memory (cudaMallocHost / cudaHostRegister / torch pin_memory): DMA the raw scan as it is, asynchronously,
+  // and let K1 read it strided on the device - no CPU pass over the scan at all.
+  cudaPointerAttributes attr;
+  bool pinned = (cudaPointerGetAttributes(&attr, xyz) == cudaSuccess) && attr.type == cudaMemoryTypeHost;
+  if (!pinned) cudaGetLastError();
+  if (pinned && attr.devicePointer && !getenv("B2LO_NO_ZERO_COPY")) {
+    // zero-copy: K1 reads just the sampled points (one 32 B sector each) straight out of the caller's page-locked buffer over
+    // PCIe; nothing else of the ~1.9 MB scan ever crosses the bus and no staging copy exists
+    ctx->h2d_bytes += ns * 32;
+    ctx->host_us[0] += now_us() - tg;
+    return process_timed(od, static_cast<const float*>(attr.devicePointer), ns, stride_floats * S, res, true);
+  }
+  if (pinned) {
+    const size_t floats = n * stride_floats;
+    if (floats > ctx->raw_floats) {
+      B2_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (ctx->d_raw) cudaFree(ctx->d_raw);
+      ctx->d_raw = nullptr; ctx->raw_floats = 0;
+      size_t cap = floats + floats / 4 + 1024;
+      if (cudaMalloc((void**)&ctx->d_raw, cap * sizeof(float)) != cudaSuccess) { set_error("cudaMalloc(raw scan, %zu B) failed", cap * sizeof(float)); return B2LO_E_NOMEM; }
+      ctx->raw_floats = cap;
+    }
+    B2_CUDA(cudaMemcpyAsync(ctx->d_raw, xyz, floats * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d_bytes += floats * sizeof(float);
+    ctx->host_us[0] += now_us() - tg;
+    return process_timed(od, ctx->d_raw, ns, stride_floats * S, res, true);
+  }
+  // pageable memory: only every S-th point is ever read by the filter (VoxelMap.h:81): gather those into pinned staging, one H2D
   int rc = ctx_stage_h2d(ctx, xyz, n, stride_floats, S, nullptr, nullptr);
+  ctx->host_us[0] += now_us() - tg;
   if (rc) return rc;
   return process_timed(od, ctx->d_stage, ns, 3, res, true);
 }

@@ -220,8 +220,13 @@ def _rel(a, b):
 
 
 def _rot_angle(Ra, Rb):
-    c = (np.trace(Ra.astype(np.float64).T @ Rb.astype(np.float64)) - 1) / 2
-    return float(np.arccos(np.clip(c, -1, 1)))
+    """Angle of Ra^T Rb from its skew part (well conditioned near 0, unlike arccos of the trace, which turns the ~1e-7
+    non-orthonormality of two f32 matrices into ~3e-4 rad)."""
+    A = Ra.astype(np.float64).T @ Rb.astype(np.float64)
+    v = 0.5 * np.array([A[2, 1] - A[1, 2], A[0, 2] - A[2, 0], A[1, 0] - A[0, 1]])
+    s = float(np.linalg.norm(v))
+    c = (np.trace(A) - 1.0) / 2.0
+    return float(np.arctan2(s, c)) if s > 1e-3 else float(np.arcsin(min(s, 1.0)))
 
 
 def test_icp_teacher_forced_iterations(orc, b2, small_kitti):

@@ -14,6 +14,6 @@ for k, s in enumerate(scans):
     a = pipe.process(s); b = odo.process(s)
     dt = np.linalg.norm(a["pose"][:3, 3].astype(np.float64) - b["pose"][:3, 3])
     Ra, Rb = a["pose"][:3, :3].astype(np.float64), b["pose"][:3, :3].astype(np.float64)
-    ang = np.arccos(np.clip((np.trace(Ra.T @ Rb) - 1) / 2, -1, 1))
+    A = Ra.T @ Rb; ang = np.linalg.norm(0.5 * np.array([A[2, 1] - A[1, 2], A[0, 2] - A[2, 0], A[1, 0] - A[0, 1]]))
     print(f"scan {k}: feat {a['n_features']}/{b['n_features']} kf {a['keyframe']}/{b['keyframe']} ok {a['icp_ok']}/{b['icp_ok']} "
           f"corr {a['n_corr']}/{b['n_corr']} iters {a['n_iters']}/{b['n_iters']} dpos {dt:.3e} drot {ang:.3e} L0 {pipe.map().counts()[0]}/{b['l0']} dev_ms {b['device_ms']:.3f}")
