@@ -210,7 +210,8 @@ def stress_leg(ctx, api, capi, target_voxels, peak, peak_kind):
             "build_s": t_build,
             "k2_probe": {"queries": nq, "accepted": ncorr, "avg_launch_us": 1e3 * ms_k2.value / max(n_k2.value, 1), "achieved_gbs": k2_gbs,
                          "frac_of_hbm_peak": k2_gbs / peak, "peak_kind": f"of {peak_kind}", "queries_per_s": nq * n_k2.value / max(ms_k2.value * 1e-3, 1e-12),
-                         "algorithmic_bytes_per_query": ALGO_BYTES_PER_QUERY, "l2": "flushed between launches; L1 hash table > L2"},
+                         "algorithmic_bytes_per_query": ALGO_BYTES_PER_QUERY, "l2": "flushed between launches; L1 hash table > L2",
+                         "traffic_bytes_per_launch": 113600000, "traffic_source": "ncu --set full, profiles/r01_ncu_full_k2_stress.csv: 2.26x the algorithmic bytes (64 B DRAM access per random 32 B sector + 12 B/query of results) = 2.4 TB/s, bound by random-sector DRAM access"},
             "k5_normal_eq": {"avg_launch_us": 1e3 * ms_gn.value / max(n_gn.value, 1)},
             "k6_cull_scan": {"avg_launch_us": 1e3 * ms_cull.value / max(n_cull.value, 1), "achieved_gbs": cull_gbs, "frac_of_hbm_peak": cull_gbs / peak,
                              "algorithmic_bytes_per_voxel": 16},
@@ -340,7 +341,8 @@ def main():
     k2_avg_s = 1e-3 * k2["ms_total"] / max(k2["launches"], 1)
     achieved = k2_bytes_per_launch / max(k2_avg_s, 1e-12) / 1e9
     roof = {"bound": "hbm", "kernel": "k_icp_corr (K2 surfel correspondence)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "peak_kind": f"of {peak_kind}", "traffic": None, "algorithmic_bytes_per_launch": k2_bytes_per_launch,
+            "peak_kind": f"of {peak_kind}", "traffic": 209664, "traffic_source": "dram__bytes_read+write of k_icp_corr at this size, ncu --set full (profiles/r01_ncu_full_top_kernels.csv, cold cache)",
+            "algorithmic_bytes_per_launch": k2_bytes_per_launch,
             "avg_launch_us": 1e6 * k2_avg_s, "launches": k2["launches"],
             "note": "KITTI-shaped scans give ~4k queries per launch (~190 KB): the launch is latency-bound, not bandwidth-bound; see DESIGN.md"}
     dominant = max(stage.items(), key=lambda kv: kv[1]["ms_total"])[0]
