@@ -237,6 +237,7 @@ def main():
                     help="sequences: one independent sequence per GPU (the contract line); sharded: one dense ~1M-point scan, queries split across ranks")
     ap.add_argument("--no-stress", action="store_true", help="skip the 10^7-voxel map leg (BASELINE.json configs[3])")
     ap.add_argument("--stress-voxels", type=float, default=1.0e7)
+    ap.add_argument("--stress-only", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
@@ -254,6 +255,10 @@ def main():
     if args.mode == "sharded":
         return run_point_sharded(args, rank, world, local, api, torch, dist)
     K, W = args.steps, args.warmup
+    if args.stress_only:
+        peak, peak_kind = peaks()
+        print(json.dumps(stress_leg(api.Context(local), api, capi, int(args.stress_voxels), peak, peak_kind)["k2_probe"]))
+        return
     scans, _ = make_scans(K + W, 42 + rank, f"cuda:{local}")
     ctx = api.Context(local)
     dev_scans = [torch.from_numpy(s).cuda() for s in scans]

@@ -81,6 +81,21 @@ __global__ void k_transform(const float4* __restrict__ src, const int* __restric
   }
 }
 
+__global__ void k_transform_dev(const float4* __restrict__ src, const int* __restrict__ d_n, const float* __restrict__ T, const int* __restrict__ gate,
+                                float4* dst) {
+  if (gate && !*gate) return;
+  const int n = *d_n;
+  float m[12];
+  for (int i = 0; i < 12; ++i) m[i] = T[i];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 p = src[i];
+    float x = ((m[0] * p.x + m[1] * p.y) + m[2] * p.z) + m[3] * 1.0f;
+    float y = ((m[4] * p.x + m[5] * p.y) + m[6] * p.z) + m[7] * 1.0f;
+    float z = ((m[8] * p.x + m[9] * p.y) + m[10] * p.z) + m[11] * 1.0f;
+    dst[i] = make_float4(x, y, z, 0.0f);
+  }
+}
+
 static int grid_of(size_t n, int threads) { size_t b = (n + threads - 1) / threads; if (b < 1) b = 1; if (b > 1184) b = 1184; return (int)b; }
 
 int ctx_reserve_points(b2lo_ctx* ctx, size_t n) {
@@ -148,6 +163,15 @@ int ctx_transform(b2lo_ctx* ctx, const float4* src, const int* d_n, size_t n_cap
   std::memcpy(T.m, T16, sizeof T.m);
   prof_begin(ctx, PS_XFORM);
   k_transform<<<grid_of(n_cap, 256), 256, 0, ctx->stream>>>(src, d_n, T, dst);
+  prof_end(ctx);
+  ctx->launches++;
+  B2_CUDA(cudaGetLastError());
+  return B2LO_OK;
+}
+
+int ctx_transform_dev(b2lo_ctx* ctx, const float4* src, const int* d_n, size_t n_cap, const float* T16_dev, const int* gate, float4* dst) {
+  prof_begin(ctx, PS_XFORM);
+  k_transform_dev<<<grid_of(n_cap, 256), 256, 0, ctx->stream>>>(src, d_n, T16_dev, gate, dst);
   prof_end(ctx);
   ctx->launches++;
   B2_CUDA(cudaGetLastError());

@@ -88,6 +88,10 @@ struct MapDev {
   L0Entry* l0_tab; int l0_log2cap; uint32_t l0_cap;   // dense capacity
   // L1
   L1Entry* l1_tab; L1Meta* l1_meta; int l1_log2cap;
+  // optional device-side gate of a speculatively enqueued update (odometry: keyframe decided on the device): when non-null and
+  // *gate == 0 every update kernel returns at once; sensor_dev (row-major 4x4 pose, translation = sensor position) then replaces the
+  // host-passed sensor position
+  const int* gate; const float* sensor_dev;
   // counters (device): [0]=n0, [1]=n1, [2]=l0 tombstones, [3]=l1 tombstones, [4]=error flags, [5]=surfel count
   int* ctr;
 };

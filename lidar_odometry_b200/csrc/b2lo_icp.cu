@@ -17,6 +17,7 @@
 //                  system (pivoted LDL^T, f32), applies T <- T * (Exp(dw), dt) and sets the convergence flag.
 // Later iterations turn into no-ops once the state's `done` flag is set.
 #include <climits>
+#include <cstdlib>
 #include <cstring>
 #include "b2lo_internal.h"
 #include "b2lo_knn.cuh"
@@ -346,6 +347,26 @@ __device__ __forceinline__ double em_exp(double x) {
   return __hiloint2double(__double2hiint(pr) + k * 1048576, __double2loint(pr));
 }
 
+// Reciprocal / reciprocal square root for the EM chain: hardware seed (rcp/rsqrt.approx.ftz.f64, ~2^-20) + two Newton steps
+// (error ~1e-16, not correctly rounded).  5 / 9 dependent f64 operations instead of the ~20-40 instructions of the IEEE
+// library routines; the EM only needs the ~1e-14 agreement discussed at k_icp_pko1.
+__device__ __forceinline__ double em_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+__device__ __forceinline__ double em_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  y = fma(y, fma(-hx * y, y, 0.5), y);   // y += y (1/2 - x y^2 / 2)
+  y = fma(y, fma(-hx * y, y, 0.5), y);
+  return y;
+}
+
 constexpr int EM_SPL = MAXS / 32;   // samples per lane in the EM (4): sample index = lane + 32 k
 static_assert(MAXS % 32 == 0, "EM layout needs a multiple of 32 samples");
 
@@ -470,7 +491,9 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
   double x[EM_SPL], xx[EM_SPL];
   bool act[EM_SPL];
 #pragma unroll
-  for (int k = 0; k < EM_SPL; ++k) { const int i = lane + 32 * k; act[k] = i < ns; x[k] = act[k] ? s_x[i] : 0.0; xx[k] = x[k] * x[k]; }
+  double msk[EM_SPL];
+#pragma unroll
+  for (int k = 0; k < EM_SPL; ++k) { const int i = lane + 32 * k; act[k] = i < ns; x[k] = act[k] ? s_x[i] : 0.0; xx[k] = x[k] * x[k]; msk[k] = act[k] ? 1.0 : 0.0; }
   const double inv_ns = 1.0 / (double)ns;
   // 4. k-means (:336-389): mean0 = 0, mean1/2 = sample[dis(gen)]; every warp runs it redundantly (no exchange needed)
   double m1 = s_x[T->kmeans_seed[ns][0]], m2 = s_x[T->kmeans_seed[ns][1]];
@@ -513,7 +536,7 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
   for (int it = 0; it < 100; ++it) {
     // E-step, own component: p_c(x_i) = w_c N(x_i; mean_c, var_c)   (gaussian_pdf :675-685: 0 for variance <= 0)
     const bool ok = var > 0.0;
-    const double sq = ok ? rsqrt(6.283185307179586 * var) : 0.0;     // one rsqrt feeds the normalisation and 1/var = 2 pi sq^2
+    const double sq = ok ? em_rsqrt(6.283185307179586 * var) : 0.0;  // one rsqrt feeds the normalisation and 1/var = 2 pi sq^2
     const double hiv = -0.5 * (6.283185307179586 * (sq * sq));
     const double coef = wgt * sq;
     double p[EM_SPL];
@@ -529,17 +552,24 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
       const double change = s_dm[ph][1] + s_dm[ph][2];
       if (change < 1e-6) { em_iters = it; break; }
     }
-    double a3[3] = {0.0, 0.0, 0.0};
+    // branch-free so that the four reciprocal chains of this lane interleave: idle samples normalise by 1 and are masked by 0
+    double sum[EM_SPL], a3[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int k = 0; k < EM_SPL; ++k) {
       const int i = lane + 32 * k;
-      const double sum = (s_p[ph][0][i] + s_p[ph][1][i]) + s_p[ph][2][i];
-      const double r = act[k] ? p[k] * __drcp_rn(sum) : 0.0;   // sum 0 -> inf * 0 = NaN propagates as in the reference
+      const double t = (s_p[ph][0][i] + s_p[ph][1][i]) + s_p[ph][2][i];
+      sum[k] = act[k] ? t : 1.0;
+    }
+#pragma unroll
+    for (int k = 0; k < EM_SPL; ++k) sum[k] = em_rcp(sum[k]);   // sum 0 -> NaN propagates as in the reference
+#pragma unroll
+    for (int k = 0; k < EM_SPL; ++k) {
+      const double r = (p[k] * sum[k]) * msk[k];
       a3[0] += r; a3[1] += r * x[k]; a3[2] += r * xx[k];
     }
     warp_sum_multi<3>(a3);
     // M-step, own component (:436-474); mean0 stays pinned at 0
-    const double rnk = 1.0 / a3[0];
+    const double rnk = em_rcp(a3[0]);
     const double nm = (c == 0) ? 0.0 : a3[1] * rnk;
     const double nv = fmax(a3[2] * rnk - 2.0 * nm * (a3[1] * rnk) + nm * nm, 1e-6);   // sum r (x - nm)^2 / nk
     dm = fabs(nm - mean);
@@ -885,7 +915,8 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
   prm.loss_type = cfg->loss_type; prm.use_pko = cfg->use_adaptive_m_estimator; prm.use_surfel = cfg->use_surfel_correspondence;
   prm.tol_t = cfg->translation_tolerance; prm.tol_r = cfg->rotation_tolerance; prm.max_dist = cfg->max_correspondence_distance;
   prm.robust_delta = cfg->robust_loss_delta;
-  const int qpt = (npts_cap >= 65536) ? 4 : 1;
+  int qpt = 1;   // measured on the 10^7-voxel map: 1 query/thread (32 regs, 8 CTAs/SM) 45.5 us, 2: 47.7 us, 4: 52.4 us per 2^20 probes
+  if (const char* e = getenv("B2LO_QPT")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) qpt = v; }
   prm.ctile = surfel ? TILE * qpt : TILE;
   Init16 Ti;
   for (int i = 0; i < 16; ++i) Ti.m[i] = init_pose_on_device ? 0.0f : T_init16[i];
@@ -901,6 +932,7 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
     if (surfel) {
       prof_begin(ctx, PS_CORR);
       if (qpt == 4) k_icp_corr<4><<<grid_corr, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum);
+      else if (qpt == 2) k_icp_corr<2><<<grid_corr, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum);
       else k_icp_corr<1><<<grid_corr, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum);
       prof_end(ctx);
     } else {
@@ -1130,7 +1162,8 @@ static void shard_params(const b2lo_icp_cfg* cfg, size_t npts_cap, IcpParams& pr
   prm.loss_type = cfg->loss_type; prm.use_pko = cfg->use_adaptive_m_estimator; prm.use_surfel = 1;
   prm.tol_t = cfg->translation_tolerance; prm.tol_r = cfg->rotation_tolerance; prm.max_dist = cfg->max_correspondence_distance;
   prm.robust_delta = cfg->robust_loss_delta;
-  qpt = (npts_cap >= 65536) ? 4 : 1;
+  qpt = 1;
+  (void)npts_cap;
   prm.ctile = TILE * qpt;
 }
 static int shard_check(b2lo_map* map, const b2lo_icp_cfg* cfg) {

@@ -143,11 +143,14 @@ void prof_drain(b2lo_ctx* ctx);
 int ctx_reserve_points(b2lo_ctx* ctx, size_t n);
 int ctx_stage_h2d(b2lo_ctx* ctx, const float* xyz, size_t n, size_t stride_floats, size_t take_every, float4* dst, int* d_count);
 int ctx_transform(b2lo_ctx* ctx, const float4* src, const int* d_n, size_t n_cap, const float T16[16], float4* dst);
+int ctx_transform_dev(b2lo_ctx* ctx, const float4* src, const int* d_n, size_t n_cap, const float* T16_dev, const int* gate, float4* dst);
 int ctx_read_cloud(b2lo_ctx* ctx, const float4* src, const int* d_n, size_t n_cap, float* out_xyz, size_t out_cap, size_t* n_out);
 int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sample_stride_floats, float voxel);
 int icp_build_pko(b2lo_ctx* ctx, const b2lo_icp_cfg* cfg);
 int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_cap, const float* T_init16, const b2lo_icp_cfg* cfg, bool init_pose_on_device);
-int map_update_dev(b2lo_map* map, const float4* d_world, const int* d_n, size_t n_cap, const float sensor_f[3], float radius_sq, int rehash = 0);
+int map_update_dev(b2lo_map* map, const float4* d_world, const int* d_n, size_t n_cap, const float sensor_f[3], float radius_sq, int rehash = 0,
+                   const int* gate = nullptr, const float* sensor_dev = nullptr);
+int map_absorb_counts(b2lo_map* map);
 int map_reserve(b2lo_map* map, size_t need_l0, size_t need_upd);
 int map_refresh_counts(b2lo_map* map);
 int map_rebuild_knn_locked(b2lo_map* map);

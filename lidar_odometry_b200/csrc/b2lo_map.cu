@@ -94,8 +94,10 @@ __device__ void swap_erase_apply(const MapDev& M, int k, int s, const int* seq_p
 // mark: ||c - sensor||^2 > r^2 (VoxelMap.cpp:146-158), per-tile counts; the last CTA scans the tile counts
 __global__ void __launch_bounds__(1024) k_cull_mark(MapDev M, int n0, float sx, float sy, float sz, float r2, uint8_t* flag, int* blkcnt, int* blkoff,
                                                     int* us) {
+  if (M.gate && !*M.gate) return;
   __shared__ int sm[40];
   __shared__ int s_last;
+  if (M.sensor_dev) { sx = M.sensor_dev[3]; sy = M.sensor_dev[7]; sz = M.sensor_dev[11]; }   // translation of a row-major 4x4 pose
   int ntiles = (n0 + 1023) / 1024;
   // 4 tiles per trip: four independent 16 B loads in flight per thread (the scan streams 16 B / voxel from HBM)
   for (int tile0 = blockIdx.x * 4; tile0 < ntiles; tile0 += gridDim.x * 4) {
@@ -133,6 +135,7 @@ __global__ void __launch_bounds__(1024) k_cull_mark(MapDev M, int n0, float sx, 
 }
 // removed[] (ascending dense position) and the list of parents that lose children
 __global__ void __launch_bounds__(1024) k_cull_lists(MapDev M, int n0, const uint8_t* flag, const int* blkoff, int* us, int* removed, int* l1work) {
+  if (M.gate && !*M.gate) return;
   __shared__ int sm[40];
   const int k = us[US_K];
   if (k == 0) return;
@@ -153,6 +156,7 @@ __global__ void __launch_bounds__(1024) k_cull_lists(MapDev M, int n0, const uin
 // one CTA: (1) per affected parent replay occupied_children.erase() in removal (= L0 dense) order, one warp per parent,
 // one lane per child; (2) replay the k dense-vector erases on indices; (3) apply the moves, drop the hash entries
 __global__ void __launch_bounds__(1024) k_cull_fix(MapDev M, const uint8_t* flag, int* us, const int* l1work, const int* removed, int* aux, int n0) {
+  if (M.gate && !*M.gate) return;
   extern __shared__ int smem[];
   const int k = us[US_K];
   if (k == 0) return;
@@ -211,6 +215,7 @@ __global__ void __launch_bounds__(1024) k_cull_fix(MapDev M, const uint8_t* flag
 // ---- insert ---------------------------------------------------------------------------------------------
 __global__ void k_ins_probe(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_m, int* us, int* pslot, int* nxt, FEntry* atab, int alog2,
                             int* alist) {
+  if (M.gate && !*M.gate) return;
   const int m = *d_m;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
     float4 p = pts[i];
@@ -245,6 +250,7 @@ __global__ void k_ins_probe(MapDev M, const float4* __restrict__ pts, const int*
 // weighted = 1: the "points" are voxels of a re-hash (w = point_count), merged as in ApplyTransformAndRehash (VoxelMap.cpp:283-297)
 __global__ void k_ins_apply(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_m, const int* pslot, const int* nxt, int* isnew,
                             float4* newc, int weighted) {
+  if (M.gate && !*M.gate) return;
   const int m = *d_m;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
     int s0 = pslot[i];
@@ -297,6 +303,7 @@ __global__ void k_ins_apply(MapDev M, const float4* __restrict__ pts, const int*
 // one CTA: rank of every new voxel in first-seen order (4 points per thread); the rank is also left in the voxel's
 // hash entry so that siblings can order themselves (k_ins_place)
 __global__ void __launch_bounds__(1024) k_ins_scan(MapDev M, const int* __restrict__ d_m, const int* isnew, const int* pslot, int* newrank, int* us) {
+  if (M.gate && !*M.gate) return;
   __shared__ int sm[40];
   const int m = *d_m;
   int base = 0;
@@ -327,6 +334,7 @@ __global__ void __launch_bounds__(1024) k_ins_scan(MapDev M, const int* __restri
 // it is being updated; the first new sibling writes the new count.
 __global__ void __launch_bounds__(256) k_ins_place(MapDev M, const int* __restrict__ d_m, int* us, const int* pslot, const int* isnew,
                                                    const int* newrank, const float4* newc) {
+  if (M.gate && !*M.gate) return;
   const int m = *d_m;
   if (us[US_ERR] & ERR_CAP) return;
   const int base = us[US_N0];
@@ -378,6 +386,7 @@ __global__ void __launch_bounds__(256) k_ins_place(MapDev M, const int* __restri
 // order (f32, as the reference), runs the Jacobi SVD and applies the planarity gate.  Non-planar parents are queued
 // for the purge.  The affected-set entry is cleared on the way out (the set is self-cleaning).
 __global__ void __launch_bounds__(256) k_surfel(MapDev M, FEntry* atab, const int* __restrict__ alist, int* us, int* plist, unsigned int* pfirst) {
+  if (M.gate && !*M.gate) return;
   const int naff = us[US_NAFF];
   const bool skip = (us[US_ERR] & ERR_CAP) || !M.compute_surfels;
   const int lane = threadIdx.x & 31;
@@ -475,6 +484,7 @@ __global__ void k_xform_l0(MapDev M, int n0, Rt12 T, float4* out, int* d_n) {
 __global__ void __launch_bounds__(1024) k_upd_close(MapDev M, int* us, const int* plist, const unsigned int* pfirst, int* pord, int* poff, int* seq_pos,
                                                     int* aux, int purge_ran, const int* __restrict__ d_m, const int* __restrict__ pslot,
                                                     const int* __restrict__ isnew) {
+  if (M.gate && !*M.gate) return;
   extern __shared__ int smem[];
   __shared__ int sm[40];
   __shared__ int s_k;
@@ -648,6 +658,18 @@ static int alloc_l1_table(b2lo_map* m, int log2cap) {
   return B2LO_OK;
 }
 
+// take over counters the caller has already copied into ctx->h_counts[0..8) and synchronised
+int map_absorb_counts(b2lo_map* m) {
+  b2lo_ctx* ctx = m->ctx;
+  m->n0 = (size_t)ctx->h_counts[CT_N0]; m->n1 = (size_t)ctx->h_counts[CT_N1];
+  m->tomb0 = (size_t)ctx->h_counts[CT_TOMB0]; m->tomb1 = (size_t)ctx->h_counts[CT_TOMB1];
+  int err = ctx->h_counts[CT_ERR];
+  if (err & ERR_CAP) { set_error("voxel map capacity exceeded during update"); return B2LO_E_CAPACITY; }
+  if (err & ERR_INTERNAL) { set_error("voxel map internal inconsistency (child without L0 voxel)"); return B2LO_E_CAPACITY; }
+  if (err & ERR_RANGE) { set_error("point outside the 21-bit voxel key domain was skipped"); return B2LO_E_RANGE; }
+  return B2LO_OK;
+}
+
 int map_refresh_counts(b2lo_map* m) {
   b2lo_ctx* ctx = m->ctx;
   B2_CUDA(cudaMemcpyAsync(ctx->h_counts, m->d.ctr, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -727,12 +749,15 @@ static int grid_for(size_t n, int threads) { size_t b = (n + threads - 1) / thre
 
 // UpdateVoxelMap on a world-frame cloud already on the device (float4 stream).  n_cap = host-known upper
 // bound of *d_n.  Ends with a counter read-back (one synchronisation).
-int map_update_dev(b2lo_map* m, const float4* d_world, const int* d_n, size_t n_cap, const float sensor[3], float radius_sq, int rehash) {
+int map_update_dev(b2lo_map* m, const float4* d_world, const int* d_n, size_t n_cap, const float sensor[3], float radius_sq, int rehash,
+                   const int* gate, const float* sensor_dev) {
   b2lo_ctx* ctx = m->ctx;
   if (n_cap == 0) return B2LO_S_EMPTY;
   int rc = map_reserve(m, m->n0 + n_cap, n_cap);
   if (rc) return rc;
-  MapDev& d = m->d;
+  m->d.gate = gate; m->d.sensor_dev = sensor_dev;   // passed by value with every launch below
+  MapDev d = m->d;
+  m->d.gate = nullptr; m->d.sensor_dev = nullptr;
   cudaStream_t st = ctx->stream;
   int* us = m->u_state;
   if (!ctx->sim_attr_set) {
@@ -782,6 +807,7 @@ int map_update_dev(b2lo_map* m, const float4* d_world, const int* d_n, size_t n_
   prof_end(ctx);
   ctx->launches += 1;
   B2_CUDA(cudaGetLastError());
+  if (gate) return B2LO_OK;   // speculative: the caller reads the counters back with its own batch (map_absorb_counts)
   rc = map_refresh_counts(m);
   if (rc) return rc;
   int err = ctx->h_counts[CT_ERR];

@@ -16,6 +16,7 @@ static inline double now_us() { return std::chrono::duration<double, std::micro>
 
 using namespace b2;
 
+struct OdomDev;
 struct b2lo_odom {
   b2lo_ctx* ctx = nullptr;
   b2lo_map* map = nullptr;
@@ -23,6 +24,8 @@ struct b2lo_odom {
   Pose pose, prev_pose, velocity, last_kf_pose;
   bool initialized = false;
   int n_keyframes = 0;
+  OdomDev* d_out = nullptr;        // device result block of k_odom_decide
+  OdomDev* h_out = nullptr;        // pinned mirror
 };
 
 static Pose pose_identity() {
@@ -35,6 +38,42 @@ static Pose pose_reproject(const Pose& a) {  // SE3f(R.matrix, t): the SO3(Matri
   Pose r = a;
   r.R = so3_project(a.R);
   return r;
+}
+
+// Device-side tail of estimate_motion + should_create_keyframe (Estimator.cpp:300-302, 349-368), so that the keyframe
+// update can be enqueued behind the ICP without a host round trip: one thread turns the ICP state into the scan's pose
+// and decides whether the (already enqueued, gated) map update runs.
+struct OdomDev { float pose[16]; int keyframe; int icp_status; int pad[2]; };
+struct DecideArgs { float guess[16]; float last_kf[16]; int ran_icp; int n_keyframes; double kf_dist, kf_rot; };
+__global__ void k_odom_decide(const IcpState* st, DecideArgs a, const int* __restrict__ d_nfeat, OdomDev* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Pose result = pose_from_T16(a.guess);
+  int status = B2LO_S_EMPTY;
+  if (a.ran_icp) {
+    status = st->status;
+    if (st->status == B2LO_OK) {
+      Pose opt;
+      for (int i = 0; i < 9; ++i) opt.R.m[i] = st->R[i];
+      for (int i = 0; i < 3; ++i) opt.t[i] = st->t[i];
+      opt.R = so3_project(opt.R);   // SE3f(optimized.RotationMatrix(), ...) re-projects (Estimator.cpp:300-302)
+      result = opt;
+    }
+  }
+  int kf = 1;
+  if (a.n_keyframes > 0) {
+    Pose last = pose_from_T16(a.last_kf);
+    float d[3] = {result.t[0] - last.t[0], result.t[1] - last.t[1], result.t[2] - last.t[2]};
+    double distance = (double)sqrtf(sqn3(d));
+    Mat3 rd = so3_project(mat3_mul(so3_project(mat3_t(last.R)), result.R));
+    float lg[3];
+    so3_log(rd, lg);
+    double angle = (double)sqrtf(sqn3(lg));
+    kf = (distance > a.kf_dist || angle > a.kf_rot) ? 1 : 0;
+  }
+  if (*d_nfeat == 0) kf = 0;   // empty feature cloud: process_frame returns before touching anything (Estimator.cpp:131-134)
+  pose_to_T16(result, out->pose);
+  out->keyframe = kf;
+  out->icp_status = status;
 }
 
 extern "C" void b2lo_default_odom_cfg(b2lo_odom_cfg* c, int mid360) {  // config/kitti.yaml / config/mid360.yaml
@@ -60,11 +99,17 @@ extern "C" int b2lo_odom_create(b2lo_ctx* ctx, const b2lo_odom_cfg* cfg, b2lo_od
   int rc = b2lo_map_create(ctx, cfg->map_voxel_size, 3, cfg->surfel_planarity_threshold, cfg->icp.use_surfel_correspondence, 1u << 17, &od->map);
   if (rc) { delete od; return rc; }
   od->pose = od->prev_pose = od->velocity = od->last_kf_pose = pose_identity();
+  if (cudaMalloc((void**)&od->d_out, sizeof(OdomDev)) != cudaSuccess || cudaMallocHost((void**)&od->h_out, sizeof(OdomDev)) != cudaSuccess) {
+    b2lo_odom_destroy(od);
+    return B2LO_E_NOMEM;
+  }
   *out = od;
   return B2LO_OK;
 }
 extern "C" int b2lo_odom_destroy(b2lo_odom* od) {
   if (!od) return B2LO_E_ARG;
+  if (od->d_out) cudaFree(od->d_out);
+  if (od->h_out) cudaFreeHost(od->h_out);
   if (od->map) b2lo_map_destroy(od->map);
   delete od;
   return B2LO_OK;
@@ -124,7 +169,6 @@ static int process_common(b2lo_odom* od, const float* src_dev, size_t ns, size_t
     res->icp_status = B2LO_S_EMPTY;
   } else {
     Pose guess = pose_mul(od->prev_pose, od->velocity);  // Estimator.cpp:154
-    Pose result = guess;
     bool ran_icp = false;
     if (map->n0 > 0) {  // keyframe->get_local_map() non-empty (Estimator.cpp:279-285)
       Pose init = pose_reproject(guess);
@@ -132,39 +176,69 @@ static int process_common(b2lo_odom* od, const float* src_dev, size_t ns, size_t
       pose_to_T16(init, T16);
       rc = icp_run(map, ctx->d_feat, ctx->d_nfeat, ns, T16, &od->cfg.icp, false);
       if (rc) return rc;
-      B2_CUDA(cudaMemcpyAsync(ctx->h_icp, ctx->d_icp, offsetof(IcpState, trace), cudaMemcpyDeviceToHost, st));
-      ctx->d2h_bytes += offsetof(IcpState, trace);
       ran_icp = true;
     }
+    // pose + keyframe decision on the device; when the motion model says a keyframe is likely, the whole map update is
+    // enqueued right behind it, gated by the device flag - the host then synchronises ONCE per scan
+    DecideArgs da;
+    pose_to_T16(guess, da.guess);
+    pose_to_T16(od->last_kf_pose, da.last_kf);
+    da.ran_icp = ran_icp ? 1 : 0; da.n_keyframes = od->n_keyframes;
+    da.kf_dist = od->cfg.keyframe_distance_threshold; da.kf_rot = od->cfg.keyframe_rotation_threshold;
+    k_odom_decide<<<1, 32, 0, st>>>(ctx->d_icp, da, ctx->d_nfeat, od->d_out);
+    ctx->launches++;
+    bool speculate = od->n_keyframes == 0;
+    if (!speculate) {
+      float d[3] = {guess.t[0] - od->last_kf_pose.t[0], guess.t[1] - od->last_kf_pose.t[1], guess.t[2] - od->last_kf_pose.t[2]};
+      Mat3 rd = mat3_mul(mat3_t(od->last_kf_pose.R), guess.R);
+      float lg[3];
+      so3_log(rd, lg);
+      speculate = (double)sqrtf(sqn3(d)) > 0.6 * od->cfg.keyframe_distance_threshold || (double)sqrtf(sqn3(lg)) > 0.6 * od->cfg.keyframe_rotation_threshold;
+    }
+    const double md = od->cfg.max_range * 1.2;  // Estimator.cpp:455
+    const float r2 = (float)(md * md);
+    const float zero3[3] = {0.0f, 0.0f, 0.0f};
+    if (speculate) {
+      rc = ctx_transform_dev(ctx, ctx->d_feat, ctx->d_nfeat, ns, od->d_out->pose, &od->d_out->keyframe, ctx->d_world);
+      if (rc) return rc;
+      // sensor position = translation of the device pose: elements 3, 7, 11 are not contiguous -> a tiny strided view is avoided by
+      // letting the cull kernel read them through sensor_dev = pose + 3 with stride 4 (see k_cull_mark)
+      rc = map_update_dev(map, ctx->d_world, ctx->d_nfeat, ns, zero3, r2, 0, &od->d_out->keyframe, od->d_out->pose);
+      if (rc < 0) return rc;
+    }
+    if (ran_icp) {
+      B2_CUDA(cudaMemcpyAsync(ctx->h_icp, ctx->d_icp, offsetof(IcpState, trace), cudaMemcpyDeviceToHost, st));
+      ctx->d2h_bytes += offsetof(IcpState, trace);
+    }
+    B2_CUDA(cudaMemcpyAsync(od->h_out, od->d_out, sizeof(OdomDev), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaMemcpyAsync(ctx->h_counts, map->d.ctr, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaMemcpyAsync(hc, ctx->d_nfeat, sizeof(int), cudaMemcpyDeviceToHost, st));
     double t1 = now_us();
     B2_CUDA(cudaStreamSynchronize(st));
     double t2 = now_us();
     ctx->host_us[1] += t1 - t0; ctx->host_us[2] += t2 - t1;
-    ctx->d2h_bytes += sizeof(int);
+    ctx->d2h_bytes += sizeof(int) + sizeof(OdomDev) + 8 * sizeof(int);
     res->n_features = hc[0];
-    if (hc[0] == 0) return B2LO_S_EMPTY;
-    res->icp_status = B2LO_S_EMPTY;
-    if (ran_icp) {
-      const IcpState* h = ctx->h_icp;
-      res->icp_status = h->status; res->n_corr = h->n_corr; res->n_iters = h->num_iterations;
-      if (h->status == B2LO_OK) {
-        Pose opt;
-        for (int i = 0; i < 9; ++i) opt.R.m[i] = h->R[i];
-        for (int i = 0; i < 3; ++i) opt.t[i] = h->t[i];
-        result = pose_reproject(opt);  // Estimator.cpp:300-302
-      }
-    }
-    double t2b = now_us();
-    od->pose = result;
+    if (hc[0] == 0) return B2LO_S_EMPTY;   // nothing was changed: the gated update saw an empty cloud, the pose state is untouched
+    res->icp_status = od->h_out->icp_status;
+    if (ran_icp) { res->n_corr = ctx->h_icp->n_corr; res->n_iters = ctx->h_icp->num_iterations; }
+    od->pose = pose_from_T16(od->h_out->pose);
     od->velocity = pose_mul(pose_inv(od->prev_pose), od->pose);  // :177
     double t3 = now_us();
-    if (should_create_keyframe(od, od->pose)) {
-      rc = create_keyframe(od, ns);
-      if (rc) return rc;
+    if (od->h_out->keyframe) {
+      if (speculate) {
+        rc = map_absorb_counts(map);
+        if (rc < 0) return rc;
+        if (!od->cfg.icp.use_surfel_correspondence) map_rebuild_knn_locked(map);
+        od->last_kf_pose = od->pose;
+        od->n_keyframes++;
+      } else {  // mispredicted: run the update now (one more round trip, rare)
+        rc = create_keyframe(od, ns);
+        if (rc) return rc;
+      }
       res->keyframe = 1;
     }
-    ctx->host_us[3] += t3 - t2b;
+    ctx->host_us[3] += t3 - t2;
     ctx->host_us[4] += now_us() - t3;
     od->prev_pose = od->pose;
   }

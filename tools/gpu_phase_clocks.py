@@ -10,4 +10,4 @@ for k, s in enumerate(scans):
     out = (C.c_longlong * 32)()
     capi.lib().b2lo_ctx_debug_clocks(odo.ctx.h, out)
     v = list(out)
-    print(k, r["n_iters"], r["n_corr"], "pko1[scan,scale,sample,kmeans,em,em_it,km_it] a:", v[0:7], "b:", v[8:15], "gn[partial_sum,finish]:", v[16:18],  f"dev_ms {r['device_ms']:.3f}")
+    print(k, r["n_iters"], r["n_corr"], "pko1[scan,scale,sample,kmeans,em,em_it,km_it] a:", v[0:7], "b:", v[8:15], "gn[partial_sum,finish]:", v[16:18],   f"dev_ms {r['device_ms']:.3f}")
