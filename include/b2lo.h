@@ -190,7 +190,10 @@ typedef struct {
 void b2lo_default_odom_cfg(b2lo_odom_cfg* cfg, int mid360);
 int b2lo_odom_create(b2lo_ctx* ctx, const b2lo_odom_cfg* cfg, b2lo_odom** out);
 int b2lo_odom_destroy(b2lo_odom* od);
-int b2lo_odom_reset(b2lo_odom* od);   /* clear the map and the pose state (new sequence) */
+int b2lo_odom_reset(b2lo_odom* od);
+/* steady-state scans replay one captured CUDA graph (K1 -> ICP -> pose/keyframe decision -> gated K6 -> read-backs); how often it was
+ * replayed / rebuilt (buffers grew) and how many kernels one replay holds.  B2LO_NO_GRAPH=1 in the environment disables the capture. */
+int b2lo_odom_graph_stats(b2lo_odom* od, long long* replays, long long* builds, long long* kernels_per_replay);   /* clear the map and the pose state (new sequence) */
 b2lo_map* b2lo_odom_map(b2lo_odom* od);
 /* process_frame on a host scan (H2D inside) or on a scan already resident in HBM */
 int b2lo_odom_process(b2lo_odom* od, const float* xyz, size_t n, size_t stride_floats, b2lo_odom_result* res);

@@ -578,6 +578,11 @@ class Odometry:
     def reset(self):
         check(capi.lib().b2lo_odom_reset(self.h))
 
+    def graph_stats(self):
+        a, b, c = C.c_longlong(), C.c_longlong(), C.c_longlong()
+        check(capi.lib().b2lo_odom_graph_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(replays=a.value, builds=b.value, kernels_per_replay=c.value)
+
     @staticmethod
     def _result(rc, r: OdomResult):
         return dict(ok=rc == B2LO_OK, pose=np.array(r.pose, np.float32).reshape(4, 4), keyframe=bool(r.keyframe), icp_ok=r.icp_status == B2LO_OK,

@@ -137,6 +137,7 @@ SIGNATURES = {
     "b2lo_odom_create": (_i, [_vp, C.POINTER(OdomCfg), C.POINTER(_vp)]),
     "b2lo_odom_destroy": (_i, [_vp]),
     "b2lo_odom_reset": (_i, [_vp]),
+    "b2lo_odom_graph_stats": (_i, [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "b2lo_odom_map": (_vp, [_vp]),
     "b2lo_odom_process": (_i, [_vp, _vp, _sz, _sz, C.POINTER(OdomResult)]),
     "b2lo_odom_process_dev": (_i, [_vp, _vp, _sz, _sz, C.POINTER(OdomResult)]),

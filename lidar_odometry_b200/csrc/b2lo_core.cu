@@ -132,6 +132,7 @@ int ctx_reserve_points(b2lo_ctx* ctx, size_t n) {
   ctx->d_stage_floats = cap * 4 + 64;
   if ((rc = dev_alloc(&ctx->d_stage, ctx->d_stage_floats))) return rc;
   ctx->pts_cap = cap;
+  ctx->alloc_epoch++;
   return B2LO_OK;
 }
 
@@ -155,6 +156,17 @@ int ctx_stage_h2d(b2lo_ctx* ctx, const float* xyz, size_t n, size_t stride_float
     k_pack4<<<grid_of(nt, 256), 256, 0, ctx->stream>>>(ctx->d_stage, (int)nt, dst, d_count);
     ctx->launches++;
   }
+  return B2LO_OK;
+}
+
+int sp_begin_write(b2lo_ctx* ctx) {
+  if (ctx->sp_busy) { B2_CUDA(cudaEventSynchronize(ctx->ev_sp)); ctx->sp_busy = false; }
+  return B2LO_OK;
+}
+int sp_upload(b2lo_ctx* ctx, size_t offset, size_t bytes) {
+  B2_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(ctx->d_sp) + offset, reinterpret_cast<const char*>(ctx->h_sp) + offset, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  B2_CUDA(cudaEventRecord(ctx->ev_sp, ctx->stream));
+  ctx->sp_busy = true;
   return B2LO_OK;
 }
 
@@ -244,7 +256,8 @@ extern "C" int b2lo_ctx_create(int device, b2lo_ctx** out) {
   if (cudaMalloc((void**)&ctx->d_nfeat, sizeof(int)) != cudaSuccess || cudaMalloc((void**)&ctx->d_nquery, sizeof(int)) != cudaSuccess ||
       cudaMalloc((void**)&ctx->d_icp, sizeof(IcpState)) != cudaSuccess ||
       cudaMalloc((void**)&ctx->i_partial, ((size_t)ctx->i_max_blocks * 28 + 320) * sizeof(double)) != cudaSuccess ||
-      cudaMallocHost((void**)&ctx->h_icp, sizeof(IcpState)) != cudaSuccess || cudaMallocHost((void**)&ctx->h_counts, 64 * sizeof(int)) != cudaSuccess)
+      cudaMallocHost((void**)&ctx->h_icp, sizeof(IcpState)) != cudaSuccess || cudaMalloc((void**)&ctx->d_sp, sizeof(ScanParams)) != cudaSuccess ||
+      cudaMallocHost((void**)&ctx->h_sp, sizeof(ScanParams)) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_sp, cudaEventDisableTiming) != cudaSuccess || cudaMallocHost((void**)&ctx->h_counts, 64 * sizeof(int)) != cudaSuccess)
     rc = B2LO_E_NOMEM;
   if (!rc) {
     cudaMemsetAsync(ctx->d_nfeat, 0, sizeof(int), ctx->stream);
@@ -273,6 +286,9 @@ extern "C" int b2lo_ctx_destroy(b2lo_ctx* ctx) {
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->h_icp) cudaFreeHost(ctx->h_icp);
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+  if (ctx->h_sp) cudaFreeHost(ctx->h_sp);
+  if (ctx->d_sp) cudaFree(ctx->d_sp);
+  if (ctx->ev_sp) cudaEventDestroy(ctx->ev_sp);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ev_stage) cudaEventDestroy(ctx->ev_stage);

@@ -35,8 +35,12 @@ __device__ __forceinline__ unsigned long long filter_key(float x, float y, float
   return expand21((uint64_t)ix) | (expand21((uint64_t)iy) << 1) | (expand21((uint64_t)iz) << 2);
 }
 
-__global__ void k_flt_insert(const float* __restrict__ src, int n_samples, size_t sample_stride, float inv, FEntry* tab, int log2cap,
+__global__ void k_flt_insert(const ScanParams* __restrict__ sp, FEntry* tab, int log2cap,
                              float4* samp, int* slot_of) {
+  const float* __restrict__ src = sp->flt_src;
+  const int n_samples = sp->flt_ns;
+  const size_t sample_stride = (size_t)sp->flt_stride;
+  const float inv = sp->flt_inv;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_samples; j += gridDim.x * blockDim.x) {
     const float* p = src + (size_t)j * sample_stride;
     float x = p[0], y = p[1], z = p[2];
@@ -88,9 +92,10 @@ __device__ __forceinline__ unsigned long long block_excl_scan64(unsigned long lo
 
 // one CTA of 1024 threads walks the samples in input order, 4 per thread; the voxel rank (count of earlier leaders) and
 // the segment offset (sum of earlier leaders' point counts) ride one packed 64-bit scan: leaders << 32 | points
-__global__ void __launch_bounds__(1024) k_flt_scan(const FEntry* __restrict__ tab, const int* __restrict__ slot_of, int n_samples,
+__global__ void __launch_bounds__(1024) k_flt_scan(const FEntry* __restrict__ tab, const int* __restrict__ slot_of, const ScanParams* __restrict__ sp,
                                                     int* vid_of_point, int* seg_start, int* seg_cnt, int* lead_of_vid, int* d_nvox) {
   __shared__ unsigned long long sm[40];
+  const int n_samples = sp->flt_ns;
   unsigned long long base = 0ull;
   for (int t0 = 0; t0 < n_samples; t0 += 4 * blockDim.x) {
     const int j0 = t0 + 4 * threadIdx.x;
@@ -123,8 +128,9 @@ __global__ void __launch_bounds__(1024) k_flt_scan(const FEntry* __restrict__ ta
   if (threadIdx.x == 0) { *d_nvox = (int)(base >> 32); seg_start[(int)(base >> 32)] = (int)(base & 0xffffffffull); }
 }
 
-__global__ void k_flt_fill(FEntry* tab, const int* __restrict__ slot_of, int n_samples, const int* __restrict__ vid_of_point,
+__global__ void k_flt_fill(FEntry* tab, const int* __restrict__ slot_of, const ScanParams* __restrict__ sp, const int* __restrict__ vid_of_point,
                            const int* __restrict__ seg_start, int* bucket) {
+  const int n_samples = sp->flt_ns;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_samples; j += gridDim.x * blockDim.x) {
     int s = slot_of[j];
     if (s < 0) continue;
@@ -134,9 +140,10 @@ __global__ void k_flt_fill(FEntry* tab, const int* __restrict__ slot_of, int n_s
   }
 }
 
-__global__ void k_flt_rank(const FEntry* __restrict__ tab, const int* __restrict__ slot_of, int n_samples,
+__global__ void k_flt_rank(const FEntry* __restrict__ tab, const int* __restrict__ slot_of, const ScanParams* __restrict__ sp,
                            const int* __restrict__ vid_of_point, const int* __restrict__ seg_start, const int* __restrict__ seg_cnt,
                            const int* __restrict__ bucket, int* ordered) {
+  const int n_samples = sp->flt_ns;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_samples; j += gridDim.x * blockDim.x) {
     int s = slot_of[j];
     if (s < 0) continue;
@@ -169,20 +176,28 @@ int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sam
   if (n_samples > (size_t)INT_MAX / 4) { set_error("filter: too many samples"); return B2LO_E_CAPACITY; }
   int rc = ctx_reserve_points(ctx, n_samples);
   if (rc) return rc;
-  int log2cap = 4;
-  while ((1ull << log2cap) < 2 * n_samples) ++log2cap;
+  // launch geometry and scratch size depend on the CAPACITY only, the actual count travels in the parameter block:
+  // the launch sequence is identical from scan to scan (graph-replayable)
+  int log2cap = 12;
+  while ((1ull << log2cap) < 2 * n_samples) ++log2cap;   // constant while the sample count stays in one power-of-two bucket
   if (log2cap > ctx->f_log2cap) { set_error("filter: scratch hash too small"); return B2LO_E_CAPACITY; }
+  ctx->f_log2_last = log2cap;
   ctx->feat_cap_hint = n_samples;
   cudaStream_t st = ctx->stream;
+  if (!ctx->sp_preloaded) {
+    if ((rc = sp_begin_write(ctx))) return rc;
+    ctx->h_sp->flt_src = src_dev; ctx->h_sp->flt_ns = (int)n_samples; ctx->h_sp->flt_stride = sample_stride_floats;
+    ctx->h_sp->flt_inv = 1.0f / voxel;  // m_inv_voxel_size (VoxelMap.h:57)
+    if ((rc = sp_upload(ctx, 0, offsetof(ScanParams, T_init)))) return rc;
+  }
   B2_CUDA(cudaMemsetAsync(ctx->f_tab, 0xFF, sizeof(FEntry) << log2cap, st));
-  float inv = 1.0f / voxel;  // m_inv_voxel_size (VoxelMap.h:57)
-  int ns = (int)n_samples;
-  int blocks = (ns + 255) / 256; if (blocks > 1184) blocks = 1184;
+  int blocks = (int)((ctx->pts_cap + 255) / 256); if (blocks > 1184) blocks = 1184;
+  const ScanParams* sp = ctx->d_sp;
   prof_begin(ctx, PS_FILTER);
-  k_flt_insert<<<blocks, 256, 0, st>>>(src_dev, ns, sample_stride_floats, inv, ctx->f_tab, log2cap, ctx->f_samp, ctx->f_slot);
-  k_flt_scan<<<1, 1024, 0, st>>>(ctx->f_tab, ctx->f_slot, ns, ctx->f_vid, ctx->f_segstart, ctx->f_segcnt, ctx->f_lead, ctx->d_nfeat);
-  k_flt_fill<<<blocks, 256, 0, st>>>(ctx->f_tab, ctx->f_slot, ns, ctx->f_vid, ctx->f_segstart, ctx->f_bucket);
-  k_flt_rank<<<blocks, 256, 0, st>>>(ctx->f_tab, ctx->f_slot, ns, ctx->f_vid, ctx->f_segstart, ctx->f_segcnt, ctx->f_bucket, ctx->f_ordered);
+  k_flt_insert<<<blocks, 256, 0, st>>>(sp, ctx->f_tab, log2cap, ctx->f_samp, ctx->f_slot);
+  k_flt_scan<<<1, 1024, 0, st>>>(ctx->f_tab, ctx->f_slot, sp, ctx->f_vid, ctx->f_segstart, ctx->f_segcnt, ctx->f_lead, ctx->d_nfeat);
+  k_flt_fill<<<blocks, 256, 0, st>>>(ctx->f_tab, ctx->f_slot, sp, ctx->f_vid, ctx->f_segstart, ctx->f_bucket);
+  k_flt_rank<<<blocks, 256, 0, st>>>(ctx->f_tab, ctx->f_slot, sp, ctx->f_vid, ctx->f_segstart, ctx->f_segcnt, ctx->f_bucket, ctx->f_ordered);
   k_flt_reduce<<<blocks, 256, 0, st>>>(ctx->d_nfeat, ctx->f_segstart, ctx->f_segcnt, ctx->f_ordered, ctx->f_lead, ctx->f_slot, ctx->f_tab,
                                        ctx->f_samp, ctx->d_feat, ctx->d_feat_key);
   prof_end(ctx);

@@ -826,10 +826,9 @@ __global__ void __launch_bounds__(TILE) k_icp_gn(MapDev M, const float4* __restr
   }
 }
 
-struct Init16 { float m[16]; };
-__global__ void k_icp_begin(IcpState* st, Init16 T, int from_state /*1: st->T_init was written by an earlier kernel*/) {
+__global__ void k_icp_begin(IcpState* st, const ScanParams* __restrict__ sp) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    if (!from_state) for (int i = 0; i < 16; ++i) st->T_init[i] = T.m[i];
+    for (int i = 0; i < 16; ++i) st->T_init[i] = sp->T_init[i];
     for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) st->R[i * 3 + j] = st->T_init[i * 4 + j]; st->t[i] = st->T_init[i * 4 + 3]; }
     st->iter = 0; st->done = 0; st->status = B2LO_OK; st->n_corr = 0; st->scale = 1.0; st->delta = 0.0; st->ticket = 0u;
     st->num_iterations = 0; st->converged = 0; st->initial_cost = 0.0; st->final_cost = 0.0; st->em_iters = 0; st->kmeans_iters = 0;
@@ -872,6 +871,7 @@ static int knn_reserve(b2lo_ctx* ctx) {
   B2_CUDA(cudaMalloc((void**)&ctx->k_plane, cap * 2 * sizeof(float4)));
   if (!ctx->k_nunres) { B2_CUDA(cudaMalloc((void**)&ctx->k_nunres, sizeof(int))); B2_CUDA(cudaMemsetAsync(ctx->k_nunres, 0, sizeof(int), ctx->stream)); }
   ctx->k_cap = cap;
+  ctx->alloc_epoch++;
   return B2LO_OK;
 }
 
@@ -899,6 +899,13 @@ int icp_build_pko(b2lo_ctx* ctx, const b2lo_icp_cfg* cfg) {
   return B2LO_OK;
 }
 
+// everything icp_run may have to allocate or upload, done ahead of a stream capture
+int icp_prepare(b2lo_ctx* ctx, const b2lo_icp_cfg* cfg) {
+  int rc = icp_build_pko(ctx, cfg);
+  if (!rc && !cfg->use_surfel_correspondence) rc = knn_reserve(ctx);
+  return rc;
+}
+
 // enqueue a whole optimize() on the context stream.  T_init16 (host) is copied through the pinned state
 // block unless init_pose_on_device (then st->T_init was written by a previous kernel).
 int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_cap, const float* T_init16, const b2lo_icp_cfg* cfg,
@@ -918,9 +925,13 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
   int qpt = 1;   // measured on the 10^7-voxel map: 1 query/thread (32 regs, 8 CTAs/SM) 45.5 us, 2: 47.7 us, 4: 52.4 us per 2^20 probes
   if (const char* e = getenv("B2LO_QPT")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) qpt = v; }
   prm.ctile = surfel ? TILE * qpt : TILE;
-  Init16 Ti;
-  for (int i = 0; i < 16; ++i) Ti.m[i] = init_pose_on_device ? 0.0f : T_init16[i];
-  k_icp_begin<<<1, 32, 0, s>>>(ctx->d_icp, Ti, init_pose_on_device ? 1 : 0);
+  (void)init_pose_on_device;
+  if (!ctx->sp_preloaded) {
+    if ((rc = sp_begin_write(ctx))) return rc;
+    for (int i = 0; i < 16; ++i) ctx->h_sp->T_init[i] = T_init16[i];
+    if ((rc = sp_upload(ctx, offsetof(ScanParams, T_init), sizeof(float) * 16))) return rc;
+  }
+  k_icp_begin<<<1, 32, 0, s>>>(ctx->d_icp, ctx->d_sp);
   int ctiles_cap = (int)((npts_cap + prm.ctile - 1) / prm.ctile);
   int grid_corr = ctiles_cap < 1 ? 1 : (ctiles_cap > ctx->sm_count * 8 ? ctx->sm_count * 8 : ctiles_cap);
   int ntiles_cap = (int)((npts_cap + TILE - 1) / TILE);
@@ -1121,9 +1132,10 @@ extern "C" int b2lo_icp_correspondences_knn(b2lo_map* map, const float* local_xy
   if (rc) return rc;
   if ((rc = knn_reserve(ctx))) return rc;
   cudaStream_t s = ctx->stream;
-  Init16 Ti;
-  for (int i = 0; i < 16; ++i) Ti.m[i] = T16[i];
-  k_icp_begin<<<1, 32, 0, s>>>(ctx->d_icp, Ti, 0);
+  if ((rc = sp_begin_write(ctx))) return rc;
+  for (int i = 0; i < 16; ++i) ctx->h_sp->T_init[i] = T16[i];
+  if ((rc = sp_upload(ctx, offsetof(ScanParams, T_init), sizeof(float) * 16))) return rc;
+  k_icp_begin<<<1, 32, 0, s>>>(ctx->d_icp, ctx->d_sp);
   int grid = (int)((m + TILE - 1) / TILE);
   if (grid > ctx->i_max_blocks) grid = ctx->i_max_blocks;
   k_knn_search<<<grid, TILE, 0, s>>>(map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, ctx->k_idx, ctx->k_n, ctx->k_unres, ctx->k_nunres);
@@ -1184,9 +1196,10 @@ extern "C" int b2lo_icp_shard_begin(b2lo_map* map, const float* local_xyz, size_
   { int rr = ctx_reserve_points(ctx, m); if (rr) return rr; }  // may reallocate d_query: reserve before taking the pointer
   if ((rc = ctx_stage_h2d(ctx, local_xyz, m, stride_floats, 1, ctx->d_query, ctx->d_nquery))) return rc;
   ctx->shard_m = m;
-  Init16 Ti;
-  for (int i = 0; i < 16; ++i) Ti.m[i] = T_init[i];
-  k_icp_begin<<<1, 32, 0, ctx->stream>>>(ctx->d_icp, Ti, 0);
+  if ((rc = sp_begin_write(ctx))) return rc;
+  for (int i = 0; i < 16; ++i) ctx->h_sp->T_init[i] = T_init[i];
+  if ((rc = sp_upload(ctx, offsetof(ScanParams, T_init), sizeof(float) * 16))) return rc;
+  k_icp_begin<<<1, 32, 0, ctx->stream>>>(ctx->d_icp, ctx->d_sp);
   ctx->launches++;
   B2_CUDA(cudaGetLastError());
   return B2LO_OK;

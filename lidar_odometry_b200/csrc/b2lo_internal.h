@@ -49,6 +49,16 @@ struct IcpState {                 // lives in device memory, one per context
   long long dbg[32];                // clock64 stamps of the single-CTA phases (tools/gpu_phase_clocks.py)
 };
 
+// Per-call scalars that change from scan to scan live in ONE device block, refreshed by a single H2D copy from its pinned
+// mirror: the kernels read them through a pointer, so the launch sequence of a scan has constant arguments and can be
+// replayed as a CUDA graph (b2lo_odom.cu).
+struct DecideArgs { float guess[16]; float last_kf[16]; int ran_icp; int n_keyframes; double kf_dist, kf_rot; };
+struct ScanParams {
+  const float* flt_src; unsigned long long flt_stride; int flt_ns; float flt_inv;   // K1
+  float T_init[16];                                                                   // ICP initial pose
+  DecideArgs decide;                                                                  // odometry tail
+};
+
 struct IcpParams {                // kernel-argument POD
   int max_iterations, min_corr, use_robust, loss_type, use_pko, use_surfel, ctile;
   double tol_t, tol_r, max_dist, robust_delta;
@@ -75,6 +85,7 @@ struct b2lo_ctx {
   unsigned long long h2d_bytes = 0, d2h_bytes = 0;   // bytes moved over PCIe by this context (bench accounting)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_stage = nullptr;
   bool stage_busy = false; bool sim_attr_set = false;
+  unsigned long long alloc_epoch = 1;   // bumped whenever a device buffer of the context is reallocated (invalidates captured graphs)
   int sm_count = 148;
   size_t shard_m = 0;              // query count of the current point-sharded optimize (b2lo_icp_shard_begin)
   size_t feat_cap_hint = 0;        // host-known upper bound of *d_nfeat (samples of the last filter run)
@@ -92,7 +103,7 @@ struct b2lo_ctx {
   float4* d_query = nullptr; int* d_nquery = nullptr;
   float4* d_world = nullptr;       // transformed cloud (map update input)
   // filter scratch
-  b2::FEntry* f_tab = nullptr; int f_log2cap = 0;
+  b2::FEntry* f_tab = nullptr; int f_log2cap = 0; int f_log2_last = 0;
   float4* f_samp = nullptr; int* f_slot = nullptr; int* f_vid = nullptr; int* f_segstart = nullptr; int* f_segcnt = nullptr;
   int* f_lead = nullptr; int* f_bucket = nullptr; int* f_ordered = nullptr;
   // ICP scratch
@@ -108,6 +119,8 @@ struct b2lo_ctx {
   // parity taps scratch
   int* d_tap_state = nullptr; int* d_tap_key = nullptr; unsigned long long* d_tap_morton = nullptr; float* d_tap_n = nullptr; float* d_tap_c = nullptr;
   int* h_counts = nullptr;         // pinned small readback area (64 ints)
+  b2::ScanParams* d_sp = nullptr; b2::ScanParams* h_sp = nullptr /*pinned*/; cudaEvent_t ev_sp = nullptr; bool sp_busy = false;
+  bool sp_preloaded = false;       // the caller has already uploaded the whole parameter block for this launch sequence
   b2::Prof* prof = nullptr;
   double host_us[8] = {0};         // wall-clock split of the host side of b2lo_odom_process (debug aid): gather, enqueue, wait, ...
   std::mutex mu;
@@ -132,6 +145,8 @@ struct b2lo_map {
   // host mirrors
   size_t n0 = 0, n1 = 0, tomb0 = 0, tomb1 = 0;
   bool knn_ready = false;
+  bool graph_mode = false;              // update kernels read the live voxel count from the device, grids come from capacities
+  unsigned long long alloc_epoch = 1;   // bumped whenever a device buffer of the map is reallocated
   std::recursive_mutex mu;
 };
 
@@ -139,6 +154,8 @@ namespace b2 {
 void prof_begin(b2lo_ctx* ctx, int slot);
 void prof_end(b2lo_ctx* ctx);
 void prof_drain(b2lo_ctx* ctx);
+int sp_begin_write(b2lo_ctx* ctx);                                   // host may now write ctx->h_sp
+int sp_upload(b2lo_ctx* ctx, size_t offset, size_t bytes);           // enqueue the H2D copy of [offset, offset + bytes) of the block
 // implemented across the .cu files
 int ctx_reserve_points(b2lo_ctx* ctx, size_t n);
 int ctx_stage_h2d(b2lo_ctx* ctx, const float* xyz, size_t n, size_t stride_floats, size_t take_every, float4* dst, int* d_count);
@@ -147,6 +164,7 @@ int ctx_transform_dev(b2lo_ctx* ctx, const float4* src, const int* d_n, size_t n
 int ctx_read_cloud(b2lo_ctx* ctx, const float4* src, const int* d_n, size_t n_cap, float* out_xyz, size_t out_cap, size_t* n_out);
 int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sample_stride_floats, float voxel);
 int icp_build_pko(b2lo_ctx* ctx, const b2lo_icp_cfg* cfg);
+int icp_prepare(b2lo_ctx* ctx, const b2lo_icp_cfg* cfg);
 int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_cap, const float* T_init16, const b2lo_icp_cfg* cfg, bool init_pose_on_device);
 int map_update_dev(b2lo_map* map, const float4* d_world, const int* d_n, size_t n_cap, const float sensor_f[3], float radius_sq, int rehash = 0,
                    const int* gate = nullptr, const float* sensor_dev = nullptr);

@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(1024) k_cull_mark(MapDev M, int n0, float sx, 
   __shared__ int sm[40];
   __shared__ int s_last;
   if (M.sensor_dev) { sx = M.sensor_dev[3]; sy = M.sensor_dev[7]; sz = M.sensor_dev[11]; }   // translation of a row-major 4x4 pose
+  if (n0 < 0) n0 = M.ctr[CT_N0];   // replayed launch sequence: the live voxel count is on the device
   int ntiles = (n0 + 1023) / 1024;
   // 4 tiles per trip: four independent 16 B loads in flight per thread (the scan streams 16 B / voxel from HBM)
   for (int tile0 = blockIdx.x * 4; tile0 < ntiles; tile0 += gridDim.x * 4) {
@@ -139,6 +140,7 @@ __global__ void __launch_bounds__(1024) k_cull_lists(MapDev M, int n0, const uin
   __shared__ int sm[40];
   const int k = us[US_K];
   if (k == 0) return;
+  if (n0 < 0) n0 = us[US_K] + us[US_S];   // voxel count before the cull (k_cull_mark)
   int ntiles = (n0 + 1023) / 1024;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     int pos = tile * 1024 + threadIdx.x;
@@ -161,6 +163,7 @@ __global__ void __launch_bounds__(1024) k_cull_fix(MapDev M, const uint8_t* flag
   const int k = us[US_K];
   if (k == 0) return;
   const int s = us[US_S];
+  if (n0 < 0) n0 = k + s;
   const int nwork = us[US_NWORK];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int wi = warp; wi < nwork; wi += nwarps) {
@@ -687,6 +690,7 @@ int map_reserve(b2lo_map* m, size_t need_l0, size_t need_upd) {
   cudaStream_t st = ctx->stream;
   int rc;
   if (need_l0 > d.l0_cap) {  // grow the dense vectors (copy live prefix)
+    m->alloc_epoch++;
     size_t ncap = d.l0_cap ? d.l0_cap : 1024;
     while (ncap < need_l0) ncap *= 2;
     float4* nc = nullptr; unsigned long long* nk = nullptr; uint32_t* ns = nullptr;
@@ -705,6 +709,7 @@ int map_reserve(b2lo_map* m, size_t need_l0, size_t need_upd) {
   }
   // L0 hash: keep (live + tombstones + incoming) under half the table
   if ((m->n0 + m->tomb0 + need_upd) * 2 > m->tcap0) {
+    m->alloc_epoch++;
     int l2 = ceil_log2((m->n0 + need_upd) * 4);
     if (l2 < d.l0_log2cap) l2 = d.l0_log2cap;
     B2_CUDA(cudaStreamSynchronize(st));
@@ -714,6 +719,7 @@ int map_reserve(b2lo_map* m, size_t need_l0, size_t need_upd) {
     m->tomb0 = 0;
   }
   if ((m->n1 + m->tomb1 + need_upd) * 2 > m->tcap1) {
+    m->alloc_epoch++;
     int l2 = ceil_log2((m->n1 + need_upd) * 4);
     if (l2 < d.l1_log2cap) l2 = d.l1_log2cap;
     B2_CUDA(cudaStreamSynchronize(st));
@@ -728,6 +734,7 @@ int map_reserve(b2lo_map* m, size_t need_l0, size_t need_upd) {
     m->tomb1 = 0;
   }
   if (need_upd > m->upd_cap) {
+    m->alloc_epoch++;
     size_t ncap = m->upd_cap ? m->upd_cap : 4096;
     while (ncap < need_upd) ncap *= 2;
     B2_CUDA(cudaStreamSynchronize(st));
@@ -767,9 +774,9 @@ int map_update_dev(b2lo_map* m, const float4* d_world, const int* d_n, size_t n_
   }
   prof_begin(ctx, PS_MAP);
   B2_CUDA(cudaMemsetAsync(us, 0, US_COUNT * sizeof(int), st));
-  const int n0 = (int)m->n0;
-  if (n0 > 0 && !rehash) {
-    int tiles = (n0 + 1023) / 1024;
+  const int n0 = m->graph_mode ? -1 : (int)m->n0;
+  if ((n0 > 0 || m->graph_mode) && !rehash) {
+    int tiles = (int)(((m->graph_mode ? (size_t)d.l0_cap : m->n0) + 1023) / 1024);
     int g = tiles > ctx->sm_count ? ctx->sm_count : tiles;
     int g4 = (tiles + 3) / 4; if (g4 > 2 * ctx->sm_count) g4 = 2 * ctx->sm_count;
     prof_end(ctx);

@@ -24,6 +24,10 @@ struct b2lo_odom {
   Pose pose, prev_pose, velocity, last_kf_pose;
   bool initialized = false;
   int n_keyframes = 0;
+  cudaGraphExec_t gexec = nullptr;  // replayable launch sequence of one steady-state scan
+  unsigned long long gsig[4] = {0, 0, 0, 0};
+  bool allow_graph = true;
+  long long graph_launches = 0, graph_builds = 0, launches_per_graph = 0;
   OdomDev* d_out = nullptr;        // device result block of k_odom_decide
   OdomDev* h_out = nullptr;        // pinned mirror
 };
@@ -44,9 +48,9 @@ static Pose pose_reproject(const Pose& a) {  // SE3f(R.matrix, t): the SO3(Matri
 // update can be enqueued behind the ICP without a host round trip: one thread turns the ICP state into the scan's pose
 // and decides whether the (already enqueued, gated) map update runs.
 struct OdomDev { float pose[16]; int keyframe; int icp_status; int pad[2]; };
-struct DecideArgs { float guess[16]; float last_kf[16]; int ran_icp; int n_keyframes; double kf_dist, kf_rot; };
-__global__ void k_odom_decide(const IcpState* st, DecideArgs a, const int* __restrict__ d_nfeat, OdomDev* out) {
+__global__ void k_odom_decide(const IcpState* st, const ScanParams* __restrict__ sp, const int* __restrict__ d_nfeat, OdomDev* out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const DecideArgs a = sp->decide;
   Pose result = pose_from_T16(a.guess);
   int status = B2LO_S_EMPTY;
   if (a.ran_icp) {
@@ -55,7 +59,7 @@ __global__ void k_odom_decide(const IcpState* st, DecideArgs a, const int* __res
       Pose opt;
       for (int i = 0; i < 9; ++i) opt.R.m[i] = st->R[i];
       for (int i = 0; i < 3; ++i) opt.t[i] = st->t[i];
-      opt.R = so3_project(opt.R);   // SE3f(optimized.RotationMatrix(), ...) re-projects (Estimator.cpp:300-302)
+      opt.R = so3_project_near(opt.R);   // SE3f(optimized.RotationMatrix(), ...) re-projects (Estimator.cpp:300-302)
       result = opt;
     }
   }
@@ -64,7 +68,7 @@ __global__ void k_odom_decide(const IcpState* st, DecideArgs a, const int* __res
     Pose last = pose_from_T16(a.last_kf);
     float d[3] = {result.t[0] - last.t[0], result.t[1] - last.t[1], result.t[2] - last.t[2]};
     double distance = (double)sqrtf(sqn3(d));
-    Mat3 rd = so3_project(mat3_mul(so3_project(mat3_t(last.R)), result.R));
+    Mat3 rd = so3_project_near(mat3_mul(mat3_t(last.R), result.R));
     float lg[3];
     so3_log(rd, lg);
     double angle = (double)sqrtf(sqn3(lg));
@@ -99,6 +103,7 @@ extern "C" int b2lo_odom_create(b2lo_ctx* ctx, const b2lo_odom_cfg* cfg, b2lo_od
   int rc = b2lo_map_create(ctx, cfg->map_voxel_size, 3, cfg->surfel_planarity_threshold, cfg->icp.use_surfel_correspondence, 1u << 17, &od->map);
   if (rc) { delete od; return rc; }
   od->pose = od->prev_pose = od->velocity = od->last_kf_pose = pose_identity();
+  od->allow_graph = getenv("B2LO_NO_GRAPH") == nullptr;
   if (cudaMalloc((void**)&od->d_out, sizeof(OdomDev)) != cudaSuccess || cudaMallocHost((void**)&od->h_out, sizeof(OdomDev)) != cudaSuccess) {
     b2lo_odom_destroy(od);
     return B2LO_E_NOMEM;
@@ -108,6 +113,7 @@ extern "C" int b2lo_odom_create(b2lo_ctx* ctx, const b2lo_odom_cfg* cfg, b2lo_od
 }
 extern "C" int b2lo_odom_destroy(b2lo_odom* od) {
   if (!od) return B2LO_E_ARG;
+  if (od->gexec) cudaGraphExecDestroy(od->gexec);
   if (od->d_out) cudaFree(od->d_out);
   if (od->h_out) cudaFreeHost(od->h_out);
   if (od->map) b2lo_map_destroy(od->map);
@@ -144,16 +150,131 @@ static int create_keyframe(b2lo_odom* od, size_t n_cap) {
   return B2LO_OK;
 }
 
+// the launch sequence of one steady-state scan on the context stream: K1 -> ICP -> pose/keyframe decision -> gated K6 -> read-backs.
+// Everything that changes from scan to scan sits in the parameter block, so the very same sequence is what the CUDA graph replays.
+static int enqueue_scan(b2lo_odom* od, size_t ns, size_t cap, bool in_graph) {
+  b2lo_ctx* ctx = od->ctx;
+  b2lo_map* map = od->map;
+  cudaStream_t st = ctx->stream;
+  int rc;
+  if (in_graph) B2_CUDA(cudaMemcpyAsync(ctx->d_sp, ctx->h_sp, sizeof(ScanParams), cudaMemcpyHostToDevice, st));
+  ctx->sp_preloaded = true;
+  rc = filter_run(ctx, ctx->h_sp->flt_src, ns, (size_t)ctx->h_sp->flt_stride, od->cfg.voxel_size);
+  if (!rc) rc = icp_run(map, ctx->d_feat, ctx->d_nfeat, cap, ctx->h_sp->T_init, &od->cfg.icp, false);
+  ctx->sp_preloaded = false;
+  if (rc) return rc;
+  k_odom_decide<<<1, 32, 0, st>>>(ctx->d_icp, ctx->d_sp, ctx->d_nfeat, od->d_out);
+  ctx->launches++;
+  rc = ctx_transform_dev(ctx, ctx->d_feat, ctx->d_nfeat, cap, od->d_out->pose, &od->d_out->keyframe, ctx->d_world);
+  if (rc) return rc;
+  const double md = od->cfg.max_range * 1.2;  // Estimator.cpp:455
+  const float zero3[3] = {0.0f, 0.0f, 0.0f};
+  map->graph_mode = true;   // cull kernels take the live voxel count from the device counter, grids from the capacity
+  rc = map_update_dev(map, ctx->d_world, ctx->d_nfeat, cap, zero3, (float)(md * md), 0, &od->d_out->keyframe, od->d_out->pose);
+  map->graph_mode = false;
+  if (rc < 0) return rc;
+  B2_CUDA(cudaMemcpyAsync(ctx->h_icp, ctx->d_icp, offsetof(IcpState, trace), cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaMemcpyAsync(od->h_out, od->d_out, sizeof(OdomDev), cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaMemcpyAsync(ctx->h_counts, map->d.ctr, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaMemcpyAsync(ctx->h_counts + 32, ctx->d_nfeat, sizeof(int), cudaMemcpyDeviceToHost, st));
+  return B2LO_OK;
+}
+
+static int steady_scan(b2lo_odom* od, const float* src_dev, size_t ns, size_t sample_stride_floats, b2lo_odom_result* res, double t0) {
+  b2lo_ctx* ctx = od->ctx;
+  b2lo_map* map = od->map;
+  cudaStream_t st = ctx->stream;
+  int* hc = ctx->h_counts + 32;
+  int rc;
+  if (map->n0 == 0) {  // no local map yet (Estimator.cpp:279-285): the motion model alone; cannot happen after the first keyframe
+    set_error("odometry: the map is empty after initialisation");
+    return B2LO_E_ARG;
+  }
+  // capacities first (may reallocate and synchronise): nothing below allocates
+  if ((rc = ctx_reserve_points(ctx, ns))) return rc;
+  const size_t cap = ctx->pts_cap;
+  if ((rc = map_reserve(map, map->n0 + cap, cap))) return rc;
+  if ((rc = icp_prepare(ctx, &od->cfg.icp))) return rc;
+  // the parameter block of this scan
+  Pose guess = pose_mul(od->prev_pose, od->velocity);  // Estimator.cpp:154
+  Pose init = pose_reproject(guess);
+  if ((rc = sp_begin_write(ctx))) return rc;
+  ScanParams* sp = ctx->h_sp;
+  sp->flt_src = src_dev; sp->flt_ns = (int)ns; sp->flt_stride = sample_stride_floats; sp->flt_inv = 1.0f / od->cfg.voxel_size;
+  pose_to_T16(init, sp->T_init);
+  pose_to_T16(guess, sp->decide.guess);
+  pose_to_T16(od->last_kf_pose, sp->decide.last_kf);
+  sp->decide.ran_icp = 1; sp->decide.n_keyframes = od->n_keyframes;
+  sp->decide.kf_dist = od->cfg.keyframe_distance_threshold; sp->decide.kf_rot = od->cfg.keyframe_rotation_threshold;
+  int l2 = 12;
+  while ((1ull << l2) < 2 * ns) ++l2;
+  const unsigned long long sig[4] = {ctx->alloc_epoch, map->alloc_epoch, (unsigned long long)l2, (unsigned long long)cap};
+  const bool profiling = ctx->prof && ctx->prof->on;
+  bool use_graph = od->allow_graph && !profiling && od->n_keyframes >= 2;
+  if (use_graph && (!od->gexec || std::memcmp(sig, od->gsig, sizeof sig) != 0)) {
+    if (od->gexec) { cudaGraphExecDestroy(od->gexec); od->gexec = nullptr; }
+    cudaGraph_t g = nullptr;
+    long long launches0 = ctx->launches;
+    B2_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    rc = enqueue_scan(od, ns, cap, true);
+    cudaError_t ce = cudaStreamEndCapture(st, &g);
+    const long long in_capture = ctx->launches - launches0;
+    ctx->launches = launches0;
+    if (rc || ce != cudaSuccess || !g) {
+      if (g) cudaGraphDestroy(g);
+      cudaGetLastError();
+      od->allow_graph = false;  // fall back to plain stream launches for good
+      use_graph = false;
+    } else {
+      ce = cudaGraphInstantiate(&od->gexec, g, 0);
+      cudaGraphDestroy(g);
+      if (ce != cudaSuccess) { od->gexec = nullptr; od->allow_graph = false; use_graph = false; cudaGetLastError(); }
+      else { std::memcpy(od->gsig, sig, sizeof sig); od->graph_builds++; od->launches_per_graph = in_capture; }
+    }
+  }
+  if (use_graph) {
+    B2_CUDA(cudaGraphLaunch(od->gexec, st));
+    ctx->launches += od->launches_per_graph;
+    od->graph_launches++;
+  } else {
+    if ((rc = sp_upload(ctx, 0, sizeof(ScanParams)))) return rc;
+    if ((rc = enqueue_scan(od, ns, cap, false))) return rc;
+  }
+  double t1 = now_us();
+  B2_CUDA(cudaStreamSynchronize(st));
+  double t2 = now_us();
+  ctx->host_us[1] += t1 - t0; ctx->host_us[2] += t2 - t1;
+  ctx->d2h_bytes += offsetof(IcpState, trace) + sizeof(int) + sizeof(OdomDev) + 8 * sizeof(int);
+  res->n_features = hc[0];
+  if (hc[0] == 0) return B2LO_S_EMPTY;   // nothing was changed: the gated update was switched off, the pose state is untouched
+  res->icp_status = od->h_out->icp_status;
+  res->n_corr = ctx->h_icp->n_corr; res->n_iters = ctx->h_icp->num_iterations;
+  od->pose = pose_from_T16(od->h_out->pose);
+  od->velocity = pose_mul(pose_inv(od->prev_pose), od->pose);  // :177
+  if (od->h_out->keyframe) {
+    rc = map_absorb_counts(map);
+    if (rc < 0) return rc;
+    if (!od->cfg.icp.use_surfel_correspondence) map_rebuild_knn_locked(map);
+    od->last_kf_pose = od->pose;
+    od->n_keyframes++;
+    res->keyframe = 1;
+  }
+  ctx->host_us[3] += now_us() - t2;
+  od->prev_pose = od->pose;
+  return B2LO_OK;
+}
+
 static int process_common(b2lo_odom* od, const float* src_dev, size_t ns, size_t sample_stride_floats, b2lo_odom_result* res) {
   b2lo_ctx* ctx = od->ctx;
   b2lo_map* map = od->map;
   cudaStream_t st = ctx->stream;
   std::memset(res, 0, sizeof *res);
   double t0 = now_us();
-  int rc = filter_run(ctx, src_dev, ns, sample_stride_floats, od->cfg.voxel_size);
-  if (rc) return rc;
+  int rc = B2LO_OK;
   int* hc = ctx->h_counts + 32;
   if (!od->initialized) {  // initialize_first_frame
+    rc = filter_run(ctx, src_dev, ns, sample_stride_floats, od->cfg.voxel_size);
+    if (rc) return rc;
     B2_CUDA(cudaMemcpyAsync(hc, ctx->d_nfeat, sizeof(int), cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
     ctx->d2h_bytes += sizeof(int);
@@ -168,79 +289,8 @@ static int process_common(b2lo_odom* od, const float* src_dev, size_t ns, size_t
     res->keyframe = 1;
     res->icp_status = B2LO_S_EMPTY;
   } else {
-    Pose guess = pose_mul(od->prev_pose, od->velocity);  // Estimator.cpp:154
-    bool ran_icp = false;
-    if (map->n0 > 0) {  // keyframe->get_local_map() non-empty (Estimator.cpp:279-285)
-      Pose init = pose_reproject(guess);
-      float T16[16];
-      pose_to_T16(init, T16);
-      rc = icp_run(map, ctx->d_feat, ctx->d_nfeat, ns, T16, &od->cfg.icp, false);
-      if (rc) return rc;
-      ran_icp = true;
-    }
-    // pose + keyframe decision on the device; when the motion model says a keyframe is likely, the whole map update is
-    // enqueued right behind it, gated by the device flag - the host then synchronises ONCE per scan
-    DecideArgs da;
-    pose_to_T16(guess, da.guess);
-    pose_to_T16(od->last_kf_pose, da.last_kf);
-    da.ran_icp = ran_icp ? 1 : 0; da.n_keyframes = od->n_keyframes;
-    da.kf_dist = od->cfg.keyframe_distance_threshold; da.kf_rot = od->cfg.keyframe_rotation_threshold;
-    k_odom_decide<<<1, 32, 0, st>>>(ctx->d_icp, da, ctx->d_nfeat, od->d_out);
-    ctx->launches++;
-    bool speculate = od->n_keyframes == 0;
-    if (!speculate) {
-      float d[3] = {guess.t[0] - od->last_kf_pose.t[0], guess.t[1] - od->last_kf_pose.t[1], guess.t[2] - od->last_kf_pose.t[2]};
-      Mat3 rd = mat3_mul(mat3_t(od->last_kf_pose.R), guess.R);
-      float lg[3];
-      so3_log(rd, lg);
-      speculate = (double)sqrtf(sqn3(d)) > 0.6 * od->cfg.keyframe_distance_threshold || (double)sqrtf(sqn3(lg)) > 0.6 * od->cfg.keyframe_rotation_threshold;
-    }
-    const double md = od->cfg.max_range * 1.2;  // Estimator.cpp:455
-    const float r2 = (float)(md * md);
-    const float zero3[3] = {0.0f, 0.0f, 0.0f};
-    if (speculate) {
-      rc = ctx_transform_dev(ctx, ctx->d_feat, ctx->d_nfeat, ns, od->d_out->pose, &od->d_out->keyframe, ctx->d_world);
-      if (rc) return rc;
-      // sensor position = translation of the device pose: elements 3, 7, 11 are not contiguous -> a tiny strided view is avoided by
-      // letting the cull kernel read them through sensor_dev = pose + 3 with stride 4 (see k_cull_mark)
-      rc = map_update_dev(map, ctx->d_world, ctx->d_nfeat, ns, zero3, r2, 0, &od->d_out->keyframe, od->d_out->pose);
-      if (rc < 0) return rc;
-    }
-    if (ran_icp) {
-      B2_CUDA(cudaMemcpyAsync(ctx->h_icp, ctx->d_icp, offsetof(IcpState, trace), cudaMemcpyDeviceToHost, st));
-      ctx->d2h_bytes += offsetof(IcpState, trace);
-    }
-    B2_CUDA(cudaMemcpyAsync(od->h_out, od->d_out, sizeof(OdomDev), cudaMemcpyDeviceToHost, st));
-    B2_CUDA(cudaMemcpyAsync(ctx->h_counts, map->d.ctr, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    B2_CUDA(cudaMemcpyAsync(hc, ctx->d_nfeat, sizeof(int), cudaMemcpyDeviceToHost, st));
-    double t1 = now_us();
-    B2_CUDA(cudaStreamSynchronize(st));
-    double t2 = now_us();
-    ctx->host_us[1] += t1 - t0; ctx->host_us[2] += t2 - t1;
-    ctx->d2h_bytes += sizeof(int) + sizeof(OdomDev) + 8 * sizeof(int);
-    res->n_features = hc[0];
-    if (hc[0] == 0) return B2LO_S_EMPTY;   // nothing was changed: the gated update saw an empty cloud, the pose state is untouched
-    res->icp_status = od->h_out->icp_status;
-    if (ran_icp) { res->n_corr = ctx->h_icp->n_corr; res->n_iters = ctx->h_icp->num_iterations; }
-    od->pose = pose_from_T16(od->h_out->pose);
-    od->velocity = pose_mul(pose_inv(od->prev_pose), od->pose);  // :177
-    double t3 = now_us();
-    if (od->h_out->keyframe) {
-      if (speculate) {
-        rc = map_absorb_counts(map);
-        if (rc < 0) return rc;
-        if (!od->cfg.icp.use_surfel_correspondence) map_rebuild_knn_locked(map);
-        od->last_kf_pose = od->pose;
-        od->n_keyframes++;
-      } else {  // mispredicted: run the update now (one more round trip, rare)
-        rc = create_keyframe(od, ns);
-        if (rc) return rc;
-      }
-      res->keyframe = 1;
-    }
-    ctx->host_us[3] += t3 - t2;
-    ctx->host_us[4] += now_us() - t3;
-    od->prev_pose = od->pose;
+    rc = steady_scan(od, src_dev, ns, sample_stride_floats, res, t0);
+    if (rc) return rc;
   }
   pose_to_T16(od->pose, res->pose);
   res->l0 = map->n0; res->l1 = map->n1;
@@ -315,6 +365,14 @@ extern "C" int b2lo_odom_process_dev(b2lo_odom* od, const float* xyz_dev, size_t
   const size_t S = (size_t)(od->cfg.point_stride < 1 ? 1 : od->cfg.point_stride);
   const size_t ns = (n + S - 1) / S;
   return process_timed(od, xyz_dev, ns, stride_floats * S, res, false);
+}
+
+extern "C" int b2lo_odom_graph_stats(b2lo_odom* od, long long* replays, long long* builds, long long* kernels_per_replay) {
+  if (!od) return B2LO_E_ARG;
+  if (replays) *replays = od->graph_launches;
+  if (builds) *builds = od->graph_builds;
+  if (kernels_per_replay) *kernels_per_replay = od->launches_per_graph;
+  return B2LO_OK;
 }
 
 extern "C" int b2lo_odom_reset(b2lo_odom* od) {
