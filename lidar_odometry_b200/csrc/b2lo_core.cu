@@ -120,7 +120,8 @@ int ctx_reserve_points(b2lo_ctx* ctx, size_t n) {
   ctx->f_log2cap = l2;
   if ((rc = dev_alloc(&ctx->f_tab, (size_t)1 << l2)) || (rc = dev_alloc(&ctx->f_samp, cap)) || (rc = dev_alloc(&ctx->f_slot, cap)) ||
       (rc = dev_alloc(&ctx->f_vid, cap)) || (rc = dev_alloc(&ctx->f_segstart, cap + 1)) || (rc = dev_alloc(&ctx->f_segcnt, cap)) ||
-      (rc = dev_alloc(&ctx->f_lead, cap)) || (rc = dev_alloc(&ctx->f_bucket, cap)) || (rc = dev_alloc(&ctx->f_ordered, cap)))
+      (rc = dev_alloc(&ctx->f_lead, cap)) || (rc = dev_alloc(&ctx->f_bucket, cap)) || (rc = dev_alloc(&ctx->f_ordered, cap)) ||
+      (rc = dev_alloc(&ctx->f_packed, cap)) || (rc = dev_alloc(&ctx->f_sorted, cap)))
     return rc;
   if ((rc = dev_alloc(&ctx->i_res, cap)) || (rc = dev_alloc(&ctx->i_slot, cap)) || (rc = dev_alloc(&ctx->i_cidx, cap + 1024)) ||
       (rc = dev_alloc(&ctx->i_blkcnt, cap / 256 + 8)) || (rc = dev_alloc(&ctx->i_blkoff, cap / 256 + 8)) ||
@@ -278,7 +279,7 @@ extern "C" int b2lo_ctx_destroy(b2lo_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->icp_graph_exec) cudaGraphExecDestroy(ctx->icp_graph_exec);
   void* dptrs[] = {ctx->d_raw, ctx->d_stage, ctx->d_feat, ctx->d_feat_key, ctx->d_nfeat, ctx->d_query, ctx->d_nquery, ctx->d_world, ctx->f_tab, ctx->f_samp,
-                   ctx->f_slot, ctx->f_vid, ctx->f_segstart, ctx->f_segcnt, ctx->f_lead, ctx->f_bucket, ctx->f_ordered, ctx->i_res, ctx->i_slot,
+                   ctx->f_slot, ctx->f_vid, ctx->f_segstart, ctx->f_segcnt, ctx->f_lead, ctx->f_bucket, ctx->f_ordered, ctx->f_packed, ctx->f_sorted, ctx->i_res, ctx->i_slot,
                    ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff, ctx->i_tilesum, ctx->i_partial, ctx->d_icp, ctx->d_pko, ctx->d_pko_hits, ctx->d_tap_state,
                    ctx->d_tap_key, ctx->d_tap_morton, ctx->d_tap_n, ctx->d_tap_c, ctx->d_mapdev, ctx->k_idx, ctx->k_n, ctx->k_unres, ctx->k_nunres,
                    ctx->k_plane};

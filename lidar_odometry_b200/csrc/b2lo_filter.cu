@@ -6,13 +6,14 @@
 //   * key = Z-order of clamp(floor(x * (1/voxel)) + 2^20, 0, 2^21-1) per axis;
 //   * per voxel the f32 sums run SEQUENTIALLY in input order, centroid = sum * (1/(float)count);
 //   * output order = first-seen order of the voxels (unordered_dense iteration order).
-// Device algorithm (no sort, five small kernels on the context stream):
+// Device algorithm (no global sort, six small kernels on the context stream):
 //   F1 insert   : sampled point -> key -> claim/find a slot in a scratch hash; count and min-index per voxel
-//   F2 scan     : one CTA; voxel rank = prefix count of "leaders" (first point of each voxel) in input
-//                 order, segment offsets = prefix sum of the per-voxel counts in that order
-//   F3 fill     : every point drops its index into its voxel's segment (arbitrary slot)
-//   F4 rank     : every point counts the smaller indices of its segment -> position in input order
-//   F5 reduce   : one thread per voxel adds its points in input order and writes the centroid
+//   F2 flags    : per point, packed (is-leader << 32 | points of its voxel) - the dependent table look-ups, spread over the grid
+//   F3 scan     : one CTA, coalesced; voxel rank = prefix count of leaders (first point of each voxel) in input order,
+//                 segment offsets = prefix sum of the per-voxel counts in that order (one packed 64-bit scan)
+//   F4 fill     : every point drops its index into its voxel's segment (arbitrary slot)
+//   F5 rank     : every point counts the smaller indices of its segment and drops its coordinates at that position
+//   F6 reduce   : one thread per voxel streams its (now ordered, contiguous) points, adds them in input order, writes the centroid
 // Algorithmic bytes: 16 B read per sampled point + 16 B written per voxel.
 #include <climits>
 #include "b2lo_internal.h"
@@ -90,9 +91,19 @@ __device__ __forceinline__ unsigned long long block_excl_scan64(unsigned long lo
   return res;
 }
 
-// one CTA of 1024 threads walks the samples in input order, 4 per thread; the voxel rank (count of earlier leaders) and
+__global__ void k_flt_flags(const FEntry* __restrict__ tab, const int* __restrict__ slot_of, const ScanParams* __restrict__ sp,
+                            unsigned long long* __restrict__ packed) {
+  const int n_samples = sp->flt_ns;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_samples; j += gridDim.x * blockDim.x) {
+    const int s = slot_of[j];
+    unsigned long long p = 0ull;
+    if (s >= 0) { const FEntry e = tab[s]; if (e.first == (unsigned)j) p = (1ull << 32) | (unsigned long long)(unsigned)(e.cnt + 1); }
+    packed[j] = p;
+  }
+}
+// one CTA of 1024 threads walks the packed flags in input order, 4 per thread; the voxel rank (count of earlier leaders) and
 // the segment offset (sum of earlier leaders' point counts) ride one packed 64-bit scan: leaders << 32 | points
-__global__ void __launch_bounds__(1024) k_flt_scan(const FEntry* __restrict__ tab, const int* __restrict__ slot_of, const ScanParams* __restrict__ sp,
+__global__ void __launch_bounds__(1024) k_flt_scan(const unsigned long long* __restrict__ packed, const ScanParams* __restrict__ sp,
                                                     int* vid_of_point, int* seg_start, int* seg_cnt, int* lead_of_vid, int* d_nvox) {
   __shared__ unsigned long long sm[40];
   const int n_samples = sp->flt_ns;
@@ -101,15 +112,7 @@ __global__ void __launch_bounds__(1024) k_flt_scan(const FEntry* __restrict__ ta
     const int j0 = t0 + 4 * threadIdx.x;
     unsigned long long p[4], sum = 0ull;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      int j = j0 + k;
-      p[k] = 0ull;
-      if (j < n_samples) {
-        int s = slot_of[j];
-        if (s >= 0 && tab[s].first == (unsigned)j) p[k] = (1ull << 32) | (unsigned long long)(unsigned)(tab[s].cnt + 1);
-      }
-      sum += p[k];
-    }
+    for (int k = 0; k < 4; ++k) { p[k] = (j0 + k < n_samples) ? packed[j0 + k] : 0ull; sum += p[k]; }
     unsigned long long tot;
     unsigned long long ex = base + block_excl_scan64(sum, &tot, sm);
 #pragma unroll
@@ -140,9 +143,12 @@ __global__ void k_flt_fill(FEntry* tab, const int* __restrict__ slot_of, const S
   }
 }
 
+// every point counts the smaller indices of its voxel's segment -> its position in input order; it drops its COORDINATES
+// there, so that the reduction below streams contiguous float4s (the O(m^2) ordering work of a crowded voxel is spread
+// over its m points' threads instead of serialising on one)
 __global__ void k_flt_rank(const FEntry* __restrict__ tab, const int* __restrict__ slot_of, const ScanParams* __restrict__ sp,
                            const int* __restrict__ vid_of_point, const int* __restrict__ seg_start, const int* __restrict__ seg_cnt,
-                           const int* __restrict__ bucket, int* ordered) {
+                           const int* __restrict__ bucket, const float4* __restrict__ samp, float4* __restrict__ sorted) {
   const int n_samples = sp->flt_ns;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_samples; j += gridDim.x * blockDim.x) {
     int s = slot_of[j];
@@ -150,22 +156,28 @@ __global__ void k_flt_rank(const FEntry* __restrict__ tab, const int* __restrict
     int v = vid_of_point[tab[s].first];
     int b = seg_start[v], m = seg_cnt[v], r = 0;
     for (int q = 0; q < m; ++q) r += (bucket[b + q] < j);
-    ordered[b + r] = j;
+    sorted[b + r] = samp[j];
   }
 }
 
+// one thread per voxel adds its points in input order (sequential f32, VoxelMap.h:88-91) and writes centroid and key
 __global__ void k_flt_reduce(const int* __restrict__ d_nvox, const int* __restrict__ seg_start, const int* __restrict__ seg_cnt,
-                             const int* __restrict__ ordered, const int* __restrict__ lead_of_vid, const int* __restrict__ slot_of,
-                             const FEntry* __restrict__ tab, const float4* __restrict__ samp, float4* out, unsigned long long* out_key) {
-  int nv = *d_nvox;
+                             const float4* __restrict__ sorted, const int* __restrict__ lead_of_vid, const int* __restrict__ slot_of,
+                             const FEntry* __restrict__ tab, float4* out, unsigned long long* out_key) {
+  const int nv = *d_nvox;
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
-    int b = seg_start[v], m = seg_cnt[v];
+    const int b = seg_start[v], m = seg_cnt[v];
     float sx = 0.0f, sy = 0.0f, sz = 0.0f;
-    for (int q = 0; q < m; ++q) {
-      float4 p = samp[ordered[b + q]];
-      sx += p.x; sy += p.y; sz += p.z;
+    int q = 0;
+    for (; q + 4 <= m; q += 4) {  // four independent loads in flight, adds stay in order
+      float4 p0 = sorted[b + q], p1 = sorted[b + q + 1], p2 = sorted[b + q + 2], p3 = sorted[b + q + 3];
+      sx += p0.x; sy += p0.y; sz += p0.z;
+      sx += p1.x; sy += p1.y; sz += p1.z;
+      sx += p2.x; sy += p2.y; sz += p2.z;
+      sx += p3.x; sy += p3.y; sz += p3.z;
     }
-    float ic = 1.0f / (float)(unsigned)m;
+    for (; q < m; ++q) { float4 p = sorted[b + q]; sx += p.x; sy += p.y; sz += p.z; }
+    const float ic = 1.0f / (float)(unsigned)m;
     out[v] = make_float4(sx * ic, sy * ic, sz * ic, 0.0f);
     out_key[v] = tab[slot_of[lead_of_vid[v]]].key;
   }
@@ -195,13 +207,14 @@ int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sam
   const ScanParams* sp = ctx->d_sp;
   prof_begin(ctx, PS_FILTER);
   k_flt_insert<<<blocks, 256, 0, st>>>(sp, ctx->f_tab, log2cap, ctx->f_samp, ctx->f_slot);
-  k_flt_scan<<<1, 1024, 0, st>>>(ctx->f_tab, ctx->f_slot, sp, ctx->f_vid, ctx->f_segstart, ctx->f_segcnt, ctx->f_lead, ctx->d_nfeat);
+  k_flt_flags<<<blocks, 256, 0, st>>>(ctx->f_tab, ctx->f_slot, sp, ctx->f_packed);
+  k_flt_scan<<<1, 1024, 0, st>>>(ctx->f_packed, sp, ctx->f_vid, ctx->f_segstart, ctx->f_segcnt, ctx->f_lead, ctx->d_nfeat);
   k_flt_fill<<<blocks, 256, 0, st>>>(ctx->f_tab, ctx->f_slot, sp, ctx->f_vid, ctx->f_segstart, ctx->f_bucket);
-  k_flt_rank<<<blocks, 256, 0, st>>>(ctx->f_tab, ctx->f_slot, sp, ctx->f_vid, ctx->f_segstart, ctx->f_segcnt, ctx->f_bucket, ctx->f_ordered);
-  k_flt_reduce<<<blocks, 256, 0, st>>>(ctx->d_nfeat, ctx->f_segstart, ctx->f_segcnt, ctx->f_ordered, ctx->f_lead, ctx->f_slot, ctx->f_tab,
-                                       ctx->f_samp, ctx->d_feat, ctx->d_feat_key);
+  k_flt_rank<<<blocks, 256, 0, st>>>(ctx->f_tab, ctx->f_slot, sp, ctx->f_vid, ctx->f_segstart, ctx->f_segcnt, ctx->f_bucket, ctx->f_samp, ctx->f_sorted);
+  k_flt_reduce<<<blocks, 256, 0, st>>>(ctx->d_nfeat, ctx->f_segstart, ctx->f_segcnt, ctx->f_sorted, ctx->f_lead, ctx->f_slot, ctx->f_tab,
+                                       ctx->d_feat, ctx->d_feat_key);
   prof_end(ctx);
-  ctx->launches += 5;
+  ctx->launches += 6;
   B2_CUDA(cudaGetLastError());
   return B2LO_OK;
 }

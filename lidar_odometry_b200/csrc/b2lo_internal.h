@@ -105,7 +105,7 @@ struct b2lo_ctx {
   // filter scratch
   b2::FEntry* f_tab = nullptr; int f_log2cap = 0; int f_log2_last = 0;
   float4* f_samp = nullptr; int* f_slot = nullptr; int* f_vid = nullptr; int* f_segstart = nullptr; int* f_segcnt = nullptr;
-  int* f_lead = nullptr; int* f_bucket = nullptr; int* f_ordered = nullptr;
+  int* f_lead = nullptr; int* f_bucket = nullptr; int* f_ordered = nullptr; unsigned long long* f_packed = nullptr; float4* f_sorted = nullptr;
   // ICP scratch
   double* i_res = nullptr; int* i_slot = nullptr; int* i_cidx = nullptr; int* i_blkcnt = nullptr; int* i_blkoff = nullptr;
   double* i_tilesum = nullptr;     // per compaction tile: sum r, sum r^2 of the accepted queries

@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(1024) k_upd_close(MapDev M, int* us, const int
   const int P = purge_ran ? us[US_NPURGE] : 0;
   const int n_all = us[US_N0] + ((us[US_ERR] & ERR_CAP) ? 0 : us[US_NNEW]);
   if (P == 0) {
-    if (threadIdx.x == 0) { M.ctr[CT_N0] = n_all; M.ctr[CT_ERR] = us[US_ERR]; }
+    if (threadIdx.x == 0) { M.ctr[CT_N0] = n_all; M.ctr[CT_ERR] = us[US_ERR]; M.ctr[6] = 0; M.ctr[7] = 0; }
     return;
   }
   for (int t = threadIdx.x; t < P; t += blockDim.x) {
@@ -546,6 +546,7 @@ __global__ void __launch_bounds__(1024) k_upd_close(MapDev M, int* us, const int
     M.ctr[CT_N0] = n_all - k;
     atomicAdd(&M.ctr[CT_TOMB0], k);
     M.ctr[CT_ERR] = us[US_ERR];
+    M.ctr[6] = k; M.ctr[7] = P;   // purge size of this update (debug / statistics)
     us[US_KPURGE] = k;
   }
 }

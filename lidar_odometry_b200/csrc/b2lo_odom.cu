@@ -252,6 +252,7 @@ static int steady_scan(b2lo_odom* od, const float* src_dev, size_t ns, size_t sa
   od->pose = pose_from_T16(od->h_out->pose);
   od->velocity = pose_mul(pose_inv(od->prev_pose), od->pose);  // :177
   if (od->h_out->keyframe) {
+    ctx->host_us[5] += ctx->h_counts[6]; ctx->host_us[6] += ctx->h_counts[7]; ctx->host_us[7] += 1.0;   // purge statistics
     rc = map_absorb_counts(map);
     if (rc < 0) return rc;
     if (!od->cfg.icp.use_surfel_correspondence) map_rebuild_knn_locked(map);

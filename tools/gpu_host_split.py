@@ -16,4 +16,4 @@ for s in scans[5:]:
 wall = time.perf_counter() - t0
 capi.lib().b2lo_ctx_host_us(odo.ctx.h, out, 1)
 n = len(scans) - 5
-print(odo.graph_stats()); print("per scan: wall %.1f us, device events %.1f us; host split [gather+h2d, enqueue K1+ICP, wait pose, host algebra, K6 enqueue+wait]:" % (1e6 * wall / n, 1e3 * dev / n), [round(v / n, 1) for v in list(out)[:5]])
+print(odo.graph_stats()); print("per scan: wall %.1f us, device events %.1f us; host split [gather+h2d, enqueue K1+ICP, wait pose, host algebra, K6 enqueue+wait]:" % (1e6 * wall / n, 1e3 * dev / n), [round(v / n, 1) for v in list(out)[:5]], "purge per keyframe: voxels %.1f parents %.1f" % (out[5] / max(out[7], 1), out[6] / max(out[7], 1)))
