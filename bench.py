@@ -153,6 +153,51 @@ def run_point_sharded(args, rank, world, local, api, torch, dist):
         dist.destroy_process_group()
 
 
+def mid360_leg(ctx, api, capi, flush, torch):
+    """BASELINE.json configs[2]: KDTree-mode correspondence (exact 5-NN over the L0 hash + per-query plane fit) on MID360-shaped
+    non-repetitive scans (20 k points, stride 4, 0.4 m voxels), whole scan-to-map pipeline, next to the CPU oracle on the same scans."""
+    import ctypes as C
+    from lidar_odometry_b200 import synth
+    from oracle import orc
+    L = capi.lib()
+    scans, _ = synth.mid360_sequence(n_scans=45, seed=42, device="cuda")
+    scans = [torch.from_numpy(np.ascontiguousarray(s)).pin_memory().numpy() for s in scans]
+    odo = api.Odometry(ctx, mid360=True)
+    for s in scans[:5]:
+        odo.process(s)
+    dev_ms = 0.0; wall = 0.0; nq = 0; kf = 0
+    for s in scans[5:]:
+        flush.zero_(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = odo.process(s)
+        wall += time.perf_counter() - t0
+        dev_ms += r["device_ms"]; nq += r["n_features"] * r["n_iters"]; kf += int(r["keyframe"])
+    n = len(scans) - 5
+    # K3 alone, CUDA events (plain launches)
+    odo2 = api.Odometry(ctx, mid360=True)
+    for s in scans[:5]:
+        odo2.process(s)
+    L.b2lo_ctx_profile(ctx.h, 1)
+    q2 = 0
+    for s in scans[5:]:
+        r = odo2.process(s); q2 += r["n_features"] * r["n_iters"]
+    ms, cnt = C.c_double(), C.c_longlong()
+    L.b2lo_ctx_profile_read(ctx.h, 7, C.byref(ms), C.byref(cnt))
+    L.b2lo_ctx_profile(ctx.h, 0)
+    pipe = orc.Pipeline(orc.default_pipe_cfg(True))
+    for s in scans[:5]:
+        pipe.process(s)
+    t0 = time.perf_counter()
+    for s in scans[5:]:
+        pipe.process(s)
+    cpu = time.perf_counter() - t0
+    return {"workload": "MID360-shaped rosette, 20 k pts/scan, stride 4, voxel 0.4 m, KDTree correspondence (5-NN + plane fit), 0.1 m/scan",
+            "scans": n, "keyframes": kf, "ms_per_scan_device": dev_ms / n, "e2e_scans_per_s": n / wall, "queries_per_scan_iteration": nq / max(n, 1),
+            "k3_knn_plane_fit": {"avg_us_per_iteration": 1e3 * ms.value / max(cnt.value, 1), "queries_per_s": q2 / max(ms.value * 1e-3, 1e-12),
+                                 "algorithmic_bytes_per_query": 96},
+            "cpu_oracle_scans_per_s": n / cpu}
+
+
 def stress_leg(ctx, api, capi, target_voxels, peak, peak_kind):
     """BASELINE.json configs[3]: ~10^7-voxel hierarchical hash (a stack of planar slabs filling the 120 m cull sphere's
     bounding square), keyframe updates on top of it, and the K2 surfel probe on a table far larger than the 126 MB L2.
@@ -373,8 +418,9 @@ def main():
                "sample": f"the same {K} scans after {W} warm-up scans, single thread (the reference hot path is single-threaded)",
                "ms_per_scan": 1e3 * dt / K, "stage_ms_per_scan": {"preprocess": st[0] / K, "icp": st[1] / K, "map_update": st[2] / K}}
 
-    stress = None
+    stress = mid360 = None
     if world == 1 and not args.no_stress:
+        mid360 = mid360_leg(ctx, api, capi, flush, torch)
         stress = stress_leg(ctx, api, capi, int(args.stress_voxels), peak, peak_kind)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": max_ms / K,
@@ -389,7 +435,7 @@ def main():
                     "d2h_bytes_per_step": (d1 - d0) / K},
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "stage_ms_per_scan": {k: v["ms_total"] / K for k, v in stage.items()},
             "dominant_kernel_group": dominant, "cpu_baseline": cpu,
-            "large_map_stress": stress}
+            "large_map_stress": stress, "kdtree_mid360": mid360}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -113,14 +113,12 @@ __device__ __forceinline__ int l0_find_or_insert(const MapDev& M, uint64_t key, 
   uint32_t mask = (1u << M.l0_log2cap) - 1u;
   uint32_t s = hash_slot(key, M.l0_log2cap);
   *inserted = false;
-  int first_tomb = -1;
   for (uint32_t probe = 0; probe <= mask; ++probe) {
     unsigned long long k = *((volatile unsigned long long*)&M.l0_tab[s].key);
     if (k == key) return (int)s;
     if (k == KEY_TOMB) {
       // tombstones are never recycled inside an update (another thread may be inserting the same key
       // further down the chain); they are dropped by the periodic rebuild.
-      (void)first_tomb;
     } else if (k == KEY_EMPTY) {
       unsigned long long old = atomicCAS(&M.l0_tab[s].key, KEY_EMPTY, (unsigned long long)key);
       if (old == KEY_EMPTY) { *inserted = true; return (int)s; }  // pos is POS_PENDING (0xFFFFFFFF) in a cleared entry
