@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(TILE) k_icp_corr(MapDev M, const float4* __res
 }
 
 // ---- KDTree-mode correspondence (K3) ----------------------------------------------------------------
-// search: one thread per query walks the cell shells of the L0 hash; unresolved queries are queued
+// search: one warp per query probes the cell shells of the L0 hash (27, then 98 cells, one lane per cell); unresolved queries are queued
 __global__ void __launch_bounds__(TILE) k_knn_search(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, IcpState* st,
                                                      int* knn_idx, int* knn_n, int* unres, int* n_unres) {
   if (st->done) return;
@@ -167,18 +167,22 @@ __global__ void __launch_bounds__(TILE) k_knn_search(MapDev M, const float4* __r
   if (threadIdx.x < 3) sT[threadIdx.x] = st->t[threadIdx.x];
   __syncthreads();
   const int npts = *d_npts;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = warp; i < npts; i += nwarps) {
     float4 p = pts[i];
     float w[3];
     transform_point(sR, sT, p.x, p.y, p.z, w);
     Top5 top;
-    bool exact = knn_rings(M, w, top);
-    if (exact) {
-      for (int k = 0; k < KNN_K; ++k) knn_idx[i * KNN_K + k] = top.id[k];
-      knn_n[i] = top.n;
-    } else {
-      knn_n[i] = -1;
-      unres[atomicAdd(n_unres, 1)] = i;
+    bool exact = knn_rings_warp(M, w, top);
+    if (lane == 0) {
+      if (exact) {
+        for (int k = 0; k < KNN_K; ++k) knn_idx[i * KNN_K + k] = top.id[k];
+        knn_n[i] = top.n;
+      } else {
+        knn_n[i] = -1;
+        unres[atomicAdd(n_unres, 1)] = i;
+      }
     }
   }
 }
@@ -932,6 +936,9 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
     if ((rc = sp_upload(ctx, offsetof(ScanParams, T_init), sizeof(float) * 16))) return rc;
   }
   k_icp_begin<<<1, 32, 0, s>>>(ctx->d_icp, ctx->d_sp);
+  int grid_knn = (int)((npts_cap + 7) / 8);   // one warp per query, 8 per CTA
+  if (grid_knn > ctx->sm_count * 8) grid_knn = ctx->sm_count * 8;
+  if (grid_knn < 1) grid_knn = 1;
   int ctiles_cap = (int)((npts_cap + prm.ctile - 1) / prm.ctile);
   int grid_corr = ctiles_cap < 1 ? 1 : (ctiles_cap > ctx->sm_count * 8 ? ctx->sm_count * 8 : ctiles_cap);
   int ntiles_cap = (int)((npts_cap + TILE - 1) / TILE);
@@ -948,7 +955,7 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
       prof_end(ctx);
     } else {
       prof_begin(ctx, PS_KNN);
-      k_knn_search<<<grid, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, ctx->k_idx, ctx->k_n, ctx->k_unres, ctx->k_nunres);
+      k_knn_search<<<grid_knn, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, ctx->k_idx, ctx->k_n, ctx->k_unres, ctx->k_nunres);
       k_knn_brute<<<ctx->sm_count * 2, 256, 0, s>>>(map->d, d_pts, ctx->d_icp, ctx->k_idx, ctx->k_n, ctx->k_unres, ctx->k_nunres);
       k_knn_gate<<<grid, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->k_idx, ctx->k_n, ctx->k_nunres, ctx->i_res, ctx->i_slot,
                                        ctx->i_cidx, ctx->i_blkcnt, ctx->k_plane, ctx->i_tilesum);
@@ -1136,8 +1143,8 @@ extern "C" int b2lo_icp_correspondences_knn(b2lo_map* map, const float* local_xy
   for (int i = 0; i < 16; ++i) ctx->h_sp->T_init[i] = T16[i];
   if ((rc = sp_upload(ctx, offsetof(ScanParams, T_init), sizeof(float) * 16))) return rc;
   k_icp_begin<<<1, 32, 0, s>>>(ctx->d_icp, ctx->d_sp);
-  int grid = (int)((m + TILE - 1) / TILE);
-  if (grid > ctx->i_max_blocks) grid = ctx->i_max_blocks;
+  int grid = (int)((m + 7) / 8);
+  if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
   k_knn_search<<<grid, TILE, 0, s>>>(map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, ctx->k_idx, ctx->k_n, ctx->k_unres, ctx->k_nunres);
   B2_CUDA(cudaMemcpyAsync(ctx->h_counts + 40, ctx->k_nunres, sizeof(int), cudaMemcpyDeviceToHost, s));
   k_knn_brute<<<ctx->sm_count * 2, 256, 0, s>>>(map->d, ctx->d_query, ctx->d_icp, ctx->k_idx, ctx->k_n, ctx->k_unres, ctx->k_nunres);

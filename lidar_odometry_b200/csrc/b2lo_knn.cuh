@@ -74,15 +74,8 @@ __device__ __forceinline__ bool knn_rings(const MapDev& M, const float* w, Top5&
   return false;
 }
 
-// warp-cooperative exact scan of all n0 centroids; result valid in every lane
-__device__ __forceinline__ void knn_brute_warp(const MapDev& M, int n0, const float* w, Top5& top) {
-  const int lane = threadIdx.x & 31;
-  Top5 mine;
-  mine.init();
-  for (int pos = lane; pos < n0; pos += 32) {
-    float4 c = M.l0_cent[pos];
-    mine.push(knn_dist2(w, c.x, c.y, c.z), pos);
-  }
+// merge the per-lane sorted candidate lists into the warp-wide top 5 (ascending (d2, index)); result valid in every lane
+__device__ __forceinline__ void knn_warp_merge(const Top5& mine, Top5& top) {
   top.init();
   int head = 0;
   for (int k = 0; k < KNN_K; ++k) {
@@ -99,6 +92,65 @@ __device__ __forceinline__ void knn_brute_warp(const MapDev& M, int n0, const fl
     if (bi == id && head < mine.n) ++head;
     top.d[top.n] = bd; top.id[top.n] = bi; ++top.n;
   }
+}
+
+// warp-cooperative exact scan of all n0 centroids; result valid in every lane
+__device__ __forceinline__ void knn_brute_warp(const MapDev& M, int n0, const float* w, Top5& top) {
+  const int lane = threadIdx.x & 31;
+  Top5 mine;
+  mine.init();
+  for (int pos = lane; pos < n0; pos += 32) {
+    float4 c = M.l0_cent[pos];
+    mine.push(knn_dist2(w, c.x, c.y, c.z), pos);
+  }
+  knn_warp_merge(mine, top);
+}
+
+__device__ __forceinline__ bool knn_exact_within(const MapDev& M, const float* w, int kx, int ky, int kz, int r, const Top5& top, float slop) {
+  if (top.n < KNN_K) return false;
+  const float lo = (float)r * M.voxel, hi = (float)(r + 1) * M.voxel;
+  float m = 3.402823466e+38f;
+  const int k3[3] = {kx, ky, kz};
+  for (int a = 0; a < 3; ++a) {
+    float base = (float)k3[a] * M.voxel;
+    m = fminf(m, fminf((w[a] - base) + lo, (base - w[a]) + hi));
+  }
+  m -= slop;
+  return m > 0.0f && top.d[KNN_K - 1] < m * m;
+}
+// one WARP per query: lane c probes cell c of the 3x3x3 cube around the query's cell (27 independent probes in flight), the
+// candidates are merged with shuffles; if the 5th distance does not clear the cube's faces, the 98 cells of the next shell
+// follow (<= 4 per lane).  Same result as knn_rings; returns true when the top-5 is provably exact.  Result in every lane.
+__device__ __forceinline__ bool knn_rings_warp(const MapDev& M, const float* w, Top5& top) {
+  const int lane = threadIdx.x & 31;
+  top.init();
+  int kx = voxel_coord(w[0], M.voxel), ky = voxel_coord(w[1], M.voxel), kz = voxel_coord(w[2], M.voxel);
+  if (!key_in_range(kx, ky, kz)) return false;
+  const float slop = 1e-3f * M.voxel + 4e-6f * fmaxf(fabsf(w[0]), fmaxf(fabsf(w[1]), fabsf(w[2])));
+  Top5 mine;
+  mine.init();
+  if (lane < 27) {
+    int x = kx + lane % 3 - 1, y = ky + (lane / 3) % 3 - 1, z = kz + lane / 9 - 1;
+    if (key_in_range(x, y, z)) {
+      int s0 = l0_find(M, key_morton(x, y, z));
+      if (s0 >= 0) { int pos = (int)M.l0_tab[s0].pos; float4 c = M.l0_cent[pos]; mine.push(knn_dist2(w, c.x, c.y, c.z), pos); }
+    }
+  }
+  knn_warp_merge(mine, top);
+  if (knn_exact_within(M, w, kx, ky, kz, 1, top, slop)) return true;
+  for (int c = lane; c < 125; c += 32) {
+    int dx = c % 5 - 2, dy = (c / 5) % 5 - 2, dz = c / 25 - 2;
+    if (dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1 && dz >= -1 && dz <= 1) continue;   // inner cube already visited
+    int x = kx + dx, y = ky + dy, z = kz + dz;
+    if (!key_in_range(x, y, z)) continue;
+    int s0 = l0_find(M, key_morton(x, y, z));
+    if (s0 < 0) continue;
+    int pos = (int)M.l0_tab[s0].pos;
+    float4 cc = M.l0_cent[pos];
+    mine.push(knn_dist2(w, cc.x, cc.y, cc.z), pos);
+  }
+  knn_warp_merge(mine, top);
+  return knn_exact_within(M, w, kx, ky, kz, 2, top, slop);
 }
 
 // is_collinear (ICP.cpp:785-792), f64, Eigen normalized() / cross / norm
