@@ -10,16 +10,17 @@
 //
 // No separate index is built: every L0 centroid lies inside the cell of its own Z-order key, so the L0 hash
 // IS a uniform grid.  A query walks Chebyshev shells of cells around its own cell and stops as soon as the
-// 5th-best distance is smaller than the distance to the boundary of the visited cube.  Queries still
-// unresolved after KNN_MAX_RING shells (far from the map) are finished by a warp-per-query exact scan of the
-// dense L0 centroid stream (coalesced float4, 16 B / voxel).
+// 5th-best distance is smaller than the distance to the boundary of the visited cube (one warp per query, one
+// lane per cell).  Queries still unresolved after KNN_MAX_RING shells (farther than ~2 cells from five map points)
+// are finished by a warp-per-query exact scan of the dense L0 centroid stream (coalesced float4, 16 B / voxel).
 #pragma once
 #include "b2lo_dev.cuh"
 
 namespace b2 {
 
 constexpr int KNN_K = 5;
-constexpr int KNN_MAX_RING = 2;
+constexpr int KNN_MAX_RING = 2;   // shells of L0 cells probed before a query falls back to the exact full scan (measured: more shells
+                                  // do not pay - queries that miss two shells are usually far from the map altogether)
 
 struct Top5 {
   float d[KNN_K]; int id[KNN_K]; int n;
@@ -36,42 +37,6 @@ struct Top5 {
 __device__ __forceinline__ float knn_dist2(const float* w, float cx, float cy, float cz) {
   float dx = w[0] - cx, dy = w[1] - cy, dz = w[2] - cz;
   return (dx * dx + dy * dy) + dz * dz;
-}
-
-// shell walk; returns true when the top-5 is provably exact
-__device__ __forceinline__ bool knn_rings(const MapDev& M, const float* w, Top5& top) {
-  top.init();
-  int kx = voxel_coord(w[0], M.voxel), ky = voxel_coord(w[1], M.voxel), kz = voxel_coord(w[2], M.voxel);
-  if (!key_in_range(kx, ky, kz)) return false;
-  const float slop = 1e-3f * M.voxel + 4e-6f * fmaxf(fabsf(w[0]), fmaxf(fabsf(w[1]), fabsf(w[2])));
-  for (int r = 0; r <= KNN_MAX_RING; ++r) {
-    for (int dz = -r; dz <= r; ++dz)
-      for (int dy = -r; dy <= r; ++dy) {
-        const bool face = (dz == -r || dz == r || dy == -r || dy == r);
-        const int step = (face || r == 0) ? 1 : 2 * r;  // interior rows of the shell only touch dx = -r and dx = +r
-        for (int dx = -r; dx <= r; dx += step) {
-          int x = kx + dx, y = ky + dy, z = kz + dz;
-          if (!key_in_range(x, y, z)) continue;
-          int s0 = l0_find(M, key_morton(x, y, z));
-          if (s0 < 0) continue;
-          int pos = (int)M.l0_tab[s0].pos;
-          float4 c = M.l0_cent[pos];
-          top.push(knn_dist2(w, c.x, c.y, c.z), pos);
-        }
-      }
-    if (top.n == KNN_K) {
-      float lo = (float)r * M.voxel, hi = (float)(r + 1) * M.voxel;
-      float m = 3.402823466e+38f;
-      const int k3[3] = {kx, ky, kz};
-      for (int a = 0; a < 3; ++a) {
-        float base = (float)k3[a] * M.voxel;
-        m = fminf(m, fminf((w[a] - base) + lo, (base - w[a]) + hi));
-      }
-      m -= slop;
-      if (m > 0.0f && top.d[KNN_K - 1] < m * m) return true;
-    }
-  }
-  return false;
 }
 
 // merge the per-lane sorted candidate lists into the warp-wide top 5 (ascending (d2, index)); result valid in every lane
@@ -99,9 +64,18 @@ __device__ __forceinline__ void knn_brute_warp(const MapDev& M, int n0, const fl
   const int lane = threadIdx.x & 31;
   Top5 mine;
   mine.init();
-  for (int pos = lane; pos < n0; pos += 32) {
-    float4 c = M.l0_cent[pos];
-    mine.push(knn_dist2(w, c.x, c.y, c.z), pos);
+  // 8 independent 16 B loads in flight per lane (the loop is latency-bound otherwise), candidates rejected against the current
+  // 5th-best before the sorted insert
+  for (int pos0 = lane; pos0 < n0; pos0 += 32 * 8) {
+    float4 c[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int pos = pos0 + 32 * u; c[u] = (pos < n0) ? M.l0_cent[pos] : make_float4(3e18f, 3e18f, 3e18f, 0.0f); }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int pos = pos0 + 32 * u;
+      const float dd = knn_dist2(w, c[u].x, c[u].y, c[u].z);
+      if (pos < n0 && (mine.n < KNN_K || dd <= mine.d[KNN_K - 1])) mine.push(dd, pos);
+    }
   }
   knn_warp_merge(mine, top);
 }
@@ -119,8 +93,8 @@ __device__ __forceinline__ bool knn_exact_within(const MapDev& M, const float* w
   return m > 0.0f && top.d[KNN_K - 1] < m * m;
 }
 // one WARP per query: lane c probes cell c of the 3x3x3 cube around the query's cell (27 independent probes in flight), the
-// candidates are merged with shuffles; if the 5th distance does not clear the cube's faces, the 98 cells of the next shell
-// follow (<= 4 per lane).  Same result as knn_rings; returns true when the top-5 is provably exact.  Result in every lane.
+// candidates are merged with shuffles; while the 5th distance does not clear the visited cube's faces, the next shell of cells
+// follows (98, 218, 386 cells, one lane per cell).  Returns true when the top-5 is provably exact.  Result in every lane.
 __device__ __forceinline__ bool knn_rings_warp(const MapDev& M, const float* w, Top5& top) {
   const int lane = threadIdx.x & 31;
   top.init();
@@ -138,19 +112,23 @@ __device__ __forceinline__ bool knn_rings_warp(const MapDev& M, const float* w, 
   }
   knn_warp_merge(mine, top);
   if (knn_exact_within(M, w, kx, ky, kz, 1, top, slop)) return true;
-  for (int c = lane; c < 125; c += 32) {
-    int dx = c % 5 - 2, dy = (c / 5) % 5 - 2, dz = c / 25 - 2;
-    if (dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1 && dz >= -1 && dz <= 1) continue;   // inner cube already visited
-    int x = kx + dx, y = ky + dy, z = kz + dz;
-    if (!key_in_range(x, y, z)) continue;
-    int s0 = l0_find(M, key_morton(x, y, z));
-    if (s0 < 0) continue;
-    int pos = (int)M.l0_tab[s0].pos;
-    float4 cc = M.l0_cent[pos];
-    mine.push(knn_dist2(w, cc.x, cc.y, cc.z), pos);
+  for (int r = 2; r <= KNN_MAX_RING; ++r) {
+    const int side = 2 * r + 1, cells = side * side * side;
+    for (int c = lane; c < cells; c += 32) {
+      int dx = c % side - r, dy = (c / side) % side - r, dz = c / (side * side) - r;
+      if (dx > -r && dx < r && dy > -r && dy < r && dz > -r && dz < r) continue;   // inner cube already visited
+      int x = kx + dx, y = ky + dy, z = kz + dz;
+      if (!key_in_range(x, y, z)) continue;
+      int s0 = l0_find(M, key_morton(x, y, z));
+      if (s0 < 0) continue;
+      int pos = (int)M.l0_tab[s0].pos;
+      float4 cc = M.l0_cent[pos];
+      mine.push(knn_dist2(w, cc.x, cc.y, cc.z), pos);
+    }
+    knn_warp_merge(mine, top);
+    if (knn_exact_within(M, w, kx, ky, kz, r, top, slop)) return true;
   }
-  knn_warp_merge(mine, top);
-  return knn_exact_within(M, w, kx, ky, kz, 2, top, slop);
+  return false;
 }
 
 // is_collinear (ICP.cpp:785-792), f64, Eigen normalized() / cross / norm
