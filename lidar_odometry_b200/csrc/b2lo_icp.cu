@@ -324,31 +324,28 @@ __device__ int shuffled_head(const PkoTables* T, const int* hits, int n, int j) 
   return pos;
 }
 
-// exp(x) for the Gaussian terms of the EM (x <= 0).  Branch-free: the argument is clamped at -708 (exp = 3e-308, an
-// additive nothing next to the O(1) mixture sums), rounding to the nearest multiple of ln 2 uses the 1.5*2^52 trick
-// (no float->int conversion), Cody-Waite reduction, degree-13 Taylor polynomial in Estrin form.  The EM fixed point
-// is one long chain of dependent f64 operations, so DEPTH is what costs: ~11 dependent operations here against the
-// ~25-deep Horner chain of the library routine.  Relative error ~2e-16 (truncation 4e-18).
-__device__ __forceinline__ double em_exp(double x) {
+// exp(x) for the Gaussian terms of the EM (x <= 0).  Branch-free and short: the argument is clamped at -708 (exp = 3e-308, an
+// additive nothing next to the O(1) mixture sums); x = (32 q + j) ln2/32 + r with |r| <= ln2/64 by the 1.5*2^52 rounding trick (no
+// float->int conversion) and a two-step Cody-Waite reduction; exp(x) = 2^q * 2^(j/32) * P(r) with a 32-entry table in shared
+// memory and a degree-6 Taylor polynomial in Estrin form (truncation 3e-18).  13 f64 instructions with a dependent chain of ~9,
+// against ~30 / ~25 for the library routine - the EM fixed point is one long chain of dependent f64 operations and its f64
+// issue slots are the bottleneck.  Relative error ~2e-16.
+__device__ __forceinline__ double em_exp(double x, const double* __restrict__ s_exp2) {
   x = fmax(x, -708.0);
   const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
-  const double tm = x * 1.4426950408889634 + MAGIC;
+  const double tm = fma(x, 46.16624130844683, MAGIC);        // 32 / ln 2
   const double kd = tm - MAGIC;
-  const int k = __double2loint(tm);          // low word of the biased sum = round(x * log2 e) in two's complement
-  double r = fma(-kd, 6.93147180369123816490e-01, x);
-  r = fma(-kd, 1.90821492927058770002e-10, r);
-  const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+  const int k = __double2loint(tm);                           // round(32 x / ln 2) in two's complement
+  double r = fma(-kd, 2.16608493865351192653e-02, x);         // ln2/32 hi
+  r = fma(-kd, 5.96317165397058656257e-12, r);                // ln2/32 lo
+  const double r2 = r * r;
   const double p01 = 1.0 + r;
   const double p23 = fma(r, 1.0 / 6.0, 0.5);
   const double p45 = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-  const double p67 = fma(r, 1.0 / 5040.0, 1.0 / 720.0);
-  const double p89 = fma(r, 1.0 / 362880.0, 1.0 / 40320.0);
-  const double pab = fma(r, 1.0 / 39916800.0, 1.0 / 3628800.0);
-  const double pcd = fma(r, 1.0 / 6227020800.0, 1.0 / 479001600.0);
-  const double q0 = fma(p23, r2, p01), q1 = fma(p67, r2, p45), q2 = fma(pab, r2, p89);
-  const double s0 = fma(q1, r4, q0), s1 = fma(pcd, r4, q2);
-  const double pr = fma(s1, r8, s0);
-  return __hiloint2double(__double2hiint(pr) + k * 1048576, __double2loint(pr));
+  const double q0 = fma(p23, r2, p01);
+  const double q1 = fma(r2, 1.0 / 720.0, p45);
+  const double pr = fma(q1, r2 * r2, q0) * s_exp2[k & 31];
+  return __hiloint2double(__double2hiint(pr) + (k >> 5) * 1048576, __double2loint(pr));
 }
 
 // Reciprocal / reciprocal square root for the EM chain: hardware seed (rcp/rsqrt.approx.ftz.f64, ~2^-20) + two Newton steps
@@ -407,6 +404,7 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
   __shared__ double s_x[MAXS];
   __shared__ int s_head[MAXS];
   __shared__ double s_p[2][3][MAXS];
+  __shared__ double s_exp2[32];
   __shared__ double s_dm[2][4];
   __shared__ double s_par[3][4];
   const int tid = threadIdx.x;
@@ -418,6 +416,7 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
     if (!prm.use_pko) { if (tid == 0) { st->delta = prm.robust_delta; st->em_iters = 0; st->kmeans_iters = 0; st->scale = ext_scale; st->n_corr = ext_C; } return; }
     ns = T->sample_size < ext_C ? T->sample_size : ext_C;
     if (tid < ns) s_x[tid] = ext_sample[tid];
+    if (tid >= MAXS && tid < MAXS + 32) s_exp2[tid - MAXS] = T->exp2_32[tid - MAXS];
     if (tid == 0) { st->scale = ext_scale; st->n_corr = ext_C; }
     __syncthreads();
   } else {
@@ -461,6 +460,7 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
   ns = T->sample_size < C ? T->sample_size : C;
   const int mode = C >= 65536 ? 2 : ((C & 1) ? 1 : 0);
   if (tid < MAXS) s_head[tid] = T->head_r[mode][tid];
+  if (tid >= MAXS && tid < MAXS + 32) s_exp2[tid - MAXS] = T->exp2_32[tid - MAXS];
   __syncthreads();
   if (tid < ns) {
     // position tid of std::shuffle(iota(C), mt19937(42)): the LARGEST swap partner i in [128, C) that hit position tid
@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
 #pragma unroll
     for (int k = 0; k < EM_SPL; ++k) {
       const double d = x[k] - mean;
-      p[k] = coef * em_exp((d * d) * hiv);
+      p[k] = coef * em_exp((d * d) * hiv, s_exp2);
       s_p[ph][c][lane + 32 * k] = p[k];
     }
     if (lane == 0) s_dm[ph][c] = dm;

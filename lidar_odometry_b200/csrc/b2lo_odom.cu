@@ -210,7 +210,7 @@ static int steady_scan(b2lo_odom* od, const float* src_dev, size_t ns, size_t sa
   while ((1ull << l2) < 2 * ns) ++l2;
   const unsigned long long sig[4] = {ctx->alloc_epoch, map->alloc_epoch, (unsigned long long)l2, (unsigned long long)cap};
   const bool profiling = ctx->prof && ctx->prof->on;
-  bool use_graph = od->allow_graph && !profiling && od->n_keyframes >= 2;
+  bool use_graph = od->allow_graph && !profiling && od->n_keyframes >= 1;
   if (use_graph && (!od->gexec || std::memcmp(sig, od->gsig, sizeof sig) != 0)) {
     if (od->gexec) { cudaGraphExecDestroy(od->gexec); od->gexec = nullptr; }
     cudaGraph_t g = nullptr;
