@@ -491,3 +491,63 @@ def test_graph_replay_pinned_and_pageable_paths_agree(b2, small_kitti, monkeypat
     assert with_graph.graph_stats()["replays"] > 0 and plain.graph_stats()["replays"] == 0
     a, b = with_graph.map().export_l0(), plain.map().export_l0()
     assert np.array_equal(a[1], b[1]) and np.array_equal(bits(a[0]), bits(b[0]))
+
+
+# ---- BASELINE.json sizes ------------------------------------------------------------------------------------------------
+def test_full_size_kitti_scans(orc, b2):
+    """configs[1] at full size (64 x 1900 rays, ~120 k points per scan): K1 bit-exact on whole scans, and the free-running
+    pipeline stays within 0.1 % of the oracle's trajectory."""
+    import torch
+    from lidar_odometry_b200 import synth
+    scans, poses = synth.kitti_sequence(n_scans=10, seed=42, device="cuda" if torch.cuda.is_available() else None)
+    assert all(len(s) > 110_000 for s in scans)
+    f = b2.FastVoxelFilter(0.5)
+    for s in scans[:3]:
+        ref, rk = orc.voxel_filter(s[:, :3], 8, 0.5)
+        got = f.filter(s, 8, want_keys=True)
+        assert np.array_equal(rk, f.last_keys) and np.array_equal(bits(ref), bits(got))
+    pipe, odo = orc.Pipeline(), b2.Odometry()
+    path = 0.0
+    prev = None
+    for k, s in enumerate(scans):
+        a, b = pipe.process(s), odo.process(s)
+        assert (a["ok"], a["n_features"], a["keyframe"], a["icp_ok"]) == (b["ok"], b["n_features"], b["keyframe"], b["icp_ok"]), f"scan {k}"
+        if prev is not None:
+            path += float(np.linalg.norm(a["pose"][:3, 3] - prev))
+        prev = a["pose"][:3, 3].copy()
+        err = float(np.linalg.norm(a["pose"][:3, 3].astype(np.float64) - b["pose"][:3, 3]))
+        assert err <= max(1e-3 * path, 1e-5), f"scan {k}: drift {err} m after {path} m"
+        assert _rot_angle(a["pose"][:3, :3], b["pose"][:3, :3]) < 1e-3
+    assert path > 8.0   # the sequence really moved (~1.2 m / scan)
+
+
+def test_large_map_matches_oracle(orc, b2):
+    """configs[3] scaled to what the oracle builds in seconds (~1.2 M voxels): dense order, centroids, counts and every surfel
+    agree after bulk inserts, a keyframe-sized update and a radius cull on the big map."""
+    rng = np.random.default_rng(77)
+    side, layers = 440, 6
+    gx, gy = np.meshgrid(np.arange(side, dtype=np.float32), np.arange(side, dtype=np.float32), indexing="ij")
+    base = np.stack([gx.ravel(), gy.ravel()], axis=1) * np.float32(0.5) - np.float32(110.0)
+    omap = orc.VoxelMap(0.5, 3, 0.1, True)
+    gmap = b2.VoxelMap(0.5, capacity_hint=int(side * side * layers * 1.2))
+    for l in range(layers):
+        pts = np.empty((side * side, 3), np.float32)
+        pts[:, :2] = base + rng.uniform(0.05, 0.45, (side * side, 2)).astype(np.float32)
+        pts[:, 2] = np.float32(-3.0 + 1.5 * l + 0.7) + rng.normal(0.0, 0.01, side * side).astype(np.float32)
+        omap.update(pts, [0.0, 0.0, 0.0], 400.0)
+        gmap.UpdateVoxelMap(pts, [0.0, 0.0, 0.0], 400.0)
+    assert gmap.GetVoxelCount() == omap.counts()[0] > 1_100_000
+    ang = rng.uniform(0, 2 * np.pi, 10000); rad = rng.uniform(2, 80, 10000)
+    upd = np.stack([rad * np.cos(ang), rad * np.sin(ang), -3.0 + 1.5 * rng.integers(0, layers, 10000) + 0.7 + rng.normal(0, 0.01, 10000)], axis=1).astype(np.float32)
+    omap.update(upd, [1.0, 0.0, 0.0], 100.0)      # culls everything beyond 100 m of the sensor: ~1/3 of the map
+    gmap.UpdateVoxelMap(upd, [1.0, 0.0, 0.0], 100.0)
+    assert gmap.GetVoxelCount() == omap.counts()[0] < 1_000_000
+    assert gmap.GetL1VoxelCount() == omap.counts()[1] and gmap.GetSurfelCount() == omap.counts()[2]
+    ok_, oc, on = omap.export_l0()
+    gc, gk, gn = gmap.export_l0()
+    assert np.array_equal(ok_, gk) and np.array_equal(on, gn) and np.array_equal(bits(oc), bits(gc))
+    o1, g1 = omap.export_l1(), gmap.export_l1()
+    oi = np.lexsort(o1["keys"].T[::-1]); gi = np.lexsort(g1["keys"].T[::-1])
+    assert np.array_equal(o1["keys"][oi], g1["keys"][gi]) and np.array_equal(o1["has_surfel"][oi], g1["has_surfel"][gi])
+    hs = o1["has_surfel"][oi] > 0
+    assert np.array_equal(bits(o1["normal"][oi][hs]), bits(g1["normal"][gi][hs])) and np.array_equal(bits(o1["centroid"][oi][hs]), bits(g1["centroid"][gi][hs]))
