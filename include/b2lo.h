@@ -190,14 +190,22 @@ typedef struct {
 void b2lo_default_odom_cfg(b2lo_odom_cfg* cfg, int mid360);
 int b2lo_odom_create(b2lo_ctx* ctx, const b2lo_odom_cfg* cfg, b2lo_odom** out);
 int b2lo_odom_destroy(b2lo_odom* od);
-int b2lo_odom_reset(b2lo_odom* od);
+int b2lo_odom_reset(b2lo_odom* od);   /* clear the map and the pose state (new sequence) */
 /* steady-state scans replay one captured CUDA graph (K1 -> ICP -> pose/keyframe decision -> gated K6 -> read-backs); how often it was
  * replayed / rebuilt (buffers grew) and how many kernels one replay holds.  B2LO_NO_GRAPH=1 in the environment disables the capture. */
-int b2lo_odom_graph_stats(b2lo_odom* od, long long* replays, long long* builds, long long* kernels_per_replay);   /* clear the map and the pose state (new sequence) */
+int b2lo_odom_graph_stats(b2lo_odom* od, long long* replays, long long* builds, long long* kernels_per_replay);
 b2lo_map* b2lo_odom_map(b2lo_odom* od);
 /* process_frame on a host scan (H2D inside) or on a scan already resident in HBM */
 int b2lo_odom_process(b2lo_odom* od, const float* xyz, size_t n, size_t stride_floats, b2lo_odom_result* res);
 int b2lo_odom_process_dev(b2lo_odom* od, const float* xyz_dev, size_t n, size_t stride_floats, b2lo_odom_result* res);
+/* Look-ahead for recorded sequences (the reference's players read scan i+1 from disk while scan i registers, kitti_player.cpp /
+ * mid360_player.cpp): announce, BEFORE processing scan i, the buffer that the following b2lo_odom_process{,_dev} call will be given.
+ * Its voxel downsample (K1, preprocess_frame, Estimator.cpp:561-589) then runs on a side stream into a second feature buffer while
+ * scan i registers, and the next call finds its features ready.  Results are bit-identical with and without it; K1 does not depend on
+ * the pose or the map.  The buffer must stay valid and unchanged until that next call returns.  on_device = 0: host memory, which
+ * must be page-locked and mapped (cudaMallocHost / cudaHostRegister; K1 reads it in place) - for pageable memory the announcement is
+ * ignored and B2LO_S_EMPTY is returned.  A following call with another buffer / size simply runs its own K1. */
+int b2lo_odom_lookahead(b2lo_odom* od, const float* xyz_next, size_t n, size_t stride_floats, int on_device);
 
 #ifdef __cplusplus
 }

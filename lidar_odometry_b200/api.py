@@ -588,13 +588,31 @@ class Odometry:
         return dict(ok=rc == B2LO_OK, pose=np.array(r.pose, np.float32).reshape(4, 4), keyframe=bool(r.keyframe), icp_ok=r.icp_status == B2LO_OK,
                     n_features=r.n_features, n_corr=r.n_corr, n_iters=r.n_iters, device_ms=r.device_ms, l0=r.l0, l1=r.l1)
 
-    def process(self, scan):
+    def lookahead(self, next_scan) -> bool:
+        """Announce the scan the NEXT process() call will get (b2lo_odom_lookahead): its K1 runs beside this scan's registration.
+        next_scan: a page-locked host array, or (device_ptr, n, stride_floats).  Returns False when the announcement was ignored
+        (pageable host memory).  The caller keeps the buffer alive and unchanged until that next call returns."""
+        if isinstance(next_scan, tuple):
+            ptr, n, sf = next_scan
+            rc = check(capi.lib().b2lo_odom_lookahead(self.h, C.c_void_p(ptr), n, sf, 1))
+        else:
+            a, n, sf = _cloud(next_scan)
+            if a is not next_scan and not (isinstance(next_scan, np.ndarray) and np.shares_memory(a, next_scan)):
+                return False   # _cloud had to copy (dtype / layout): the copy would not outlive this call
+            rc = check(capi.lib().b2lo_odom_lookahead(self.h, _p(a), n, sf, 0))
+        return rc == B2LO_OK
+
+    def process(self, scan, lookahead=None):
         a, n, sf = _cloud(scan)
+        if lookahead is not None:
+            self.lookahead(lookahead)
         r = OdomResult()
         rc = check(capi.lib().b2lo_odom_process(self.h, _p(a), n, sf, C.byref(r)))
         return self._result(rc, r)
 
-    def process_dev(self, dev_ptr, n, stride_floats):
+    def process_dev(self, dev_ptr, n, stride_floats, lookahead=None):
+        if lookahead is not None:
+            self.lookahead(lookahead)
         r = OdomResult()
         rc = check(capi.lib().b2lo_odom_process_dev(self.h, C.c_void_p(dev_ptr), n, stride_floats, C.byref(r)))
         return self._result(rc, r)

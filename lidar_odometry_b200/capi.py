@@ -141,6 +141,7 @@ SIGNATURES = {
     "b2lo_odom_map": (_vp, [_vp]),
     "b2lo_odom_process": (_i, [_vp, _vp, _sz, _sz, C.POINTER(OdomResult)]),
     "b2lo_odom_process_dev": (_i, [_vp, _vp, _sz, _sz, C.POINTER(OdomResult)]),
+    "b2lo_odom_lookahead": (_i, [_vp, _vp, _sz, _sz, C.c_int]),
 }
 
 

@@ -105,14 +105,22 @@ int ctx_reserve_points(b2lo_ctx* ctx, size_t n) {
   if (cap > (size_t)1 << 27) { set_error("point cloud too large (%zu points)", n); return B2LO_E_CAPACITY; }
   B2_CUDA(cudaStreamSynchronize(ctx->stream));
   int rc;
-  // the feature / query clouds survive a grow (odometry keeps the feature buffer across calls)
-  float4* old_feat = ctx->d_feat; unsigned long long* old_key = ctx->d_feat_key; size_t old_cap = ctx->pts_cap;
-  ctx->d_feat = nullptr; ctx->d_feat_key = nullptr;
-  if ((rc = dev_alloc(&ctx->d_feat, cap)) || (rc = dev_alloc(&ctx->d_feat_key, cap))) return rc;
-  if (old_feat) {
-    B2_CUDA(cudaMemcpy(ctx->d_feat, old_feat, old_cap * sizeof(float4), cudaMemcpyDeviceToDevice));
-    B2_CUDA(cudaMemcpy(ctx->d_feat_key, old_key, old_cap * sizeof(unsigned long long), cudaMemcpyDeviceToDevice));
-    cudaFree(old_feat); cudaFree(old_key);
+  // the feature clouds survive a grow (odometry keeps them across calls; a prefetched scan may sit in the second set)
+  if (ctx->stream2) B2_CUDA(cudaStreamSynchronize(ctx->stream2));
+  const size_t old_cap = ctx->pts_cap;
+  {
+    float4** fv[2] = {&ctx->d_feat, &ctx->d_feat2};
+    unsigned long long** kv[2] = {&ctx->d_feat_key, &ctx->d_feat_key2};
+    for (int s = 0; s < 2; ++s) {
+      float4* old_feat = *fv[s]; unsigned long long* old_key = *kv[s];
+      *fv[s] = nullptr; *kv[s] = nullptr;
+      if ((rc = dev_alloc(fv[s], cap)) || (rc = dev_alloc(kv[s], cap))) return rc;
+      if (old_feat) {
+        B2_CUDA(cudaMemcpy(*fv[s], old_feat, old_cap * sizeof(float4), cudaMemcpyDeviceToDevice));
+        B2_CUDA(cudaMemcpy(*kv[s], old_key, old_cap * sizeof(unsigned long long), cudaMemcpyDeviceToDevice));
+        cudaFree(old_feat); cudaFree(old_key);
+      }
+    }
   }
   if ((rc = dev_alloc(&ctx->d_query, cap)) || (rc = dev_alloc(&ctx->d_world, cap))) return rc;
   int l2 = 4;
@@ -244,7 +252,9 @@ extern "C" int b2lo_ctx_create(int device, b2lo_ctx** out) {
   b2lo_ctx* ctx = new b2lo_ctx();
   ctx->device = device;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&ctx->ev0) != cudaSuccess ||
-      cudaEventCreate(&ctx->ev1) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_stage, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreate(&ctx->ev1) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_stage, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
     set_error("stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete ctx;
     return B2LO_E_CUDA;
@@ -254,7 +264,8 @@ extern "C" int b2lo_ctx_create(int device, b2lo_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   ctx->i_max_blocks = prop.multiProcessorCount * 4;
   int rc = B2LO_OK;
-  if (cudaMalloc((void**)&ctx->d_nfeat, sizeof(int)) != cudaSuccess || cudaMalloc((void**)&ctx->d_nquery, sizeof(int)) != cudaSuccess ||
+  if (cudaMalloc((void**)&ctx->d_nfeat, sizeof(int)) != cudaSuccess || cudaMalloc((void**)&ctx->d_nfeat2, sizeof(int)) != cudaSuccess ||
+      cudaMalloc((void**)&ctx->d_nquery, sizeof(int)) != cudaSuccess ||
       cudaMalloc((void**)&ctx->d_icp, sizeof(IcpState)) != cudaSuccess ||
       cudaMalloc((void**)&ctx->i_partial, ((size_t)ctx->i_max_blocks * 28 + 320) * sizeof(double)) != cudaSuccess ||
       cudaMallocHost((void**)&ctx->h_icp, sizeof(IcpState)) != cudaSuccess || cudaMalloc((void**)&ctx->d_sp, sizeof(ScanParams)) != cudaSuccess ||
@@ -262,6 +273,7 @@ extern "C" int b2lo_ctx_create(int device, b2lo_ctx** out) {
     rc = B2LO_E_NOMEM;
   if (!rc) {
     cudaMemsetAsync(ctx->d_nfeat, 0, sizeof(int), ctx->stream);
+    cudaMemsetAsync(ctx->d_nfeat2, 0, sizeof(int), ctx->stream);
     cudaMemsetAsync(ctx->d_nquery, 0, sizeof(int), ctx->stream);
     cudaMemsetAsync(ctx->d_icp, 0, sizeof(IcpState), ctx->stream);
     cudaMemsetAsync(ctx->i_partial, 0, ((size_t)ctx->i_max_blocks * 28 + 320) * sizeof(double), ctx->stream);
@@ -276,9 +288,10 @@ extern "C" int b2lo_ctx_create(int device, b2lo_ctx** out) {
 extern "C" int b2lo_ctx_destroy(b2lo_ctx* ctx) {
   if (!ctx) return B2LO_E_ARG;
   cudaSetDevice(ctx->device);
+  if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->icp_graph_exec) cudaGraphExecDestroy(ctx->icp_graph_exec);
-  void* dptrs[] = {ctx->d_raw, ctx->d_stage, ctx->d_feat, ctx->d_feat_key, ctx->d_nfeat, ctx->d_query, ctx->d_nquery, ctx->d_world, ctx->f_tab, ctx->f_samp,
+  void* dptrs[] = {ctx->d_raw, ctx->d_stage, ctx->d_feat, ctx->d_feat_key, ctx->d_nfeat, ctx->d_feat2, ctx->d_feat_key2, ctx->d_nfeat2, ctx->d_query, ctx->d_nquery, ctx->d_world, ctx->f_tab, ctx->f_samp,
                    ctx->f_slot, ctx->f_vid, ctx->f_segstart, ctx->f_segcnt, ctx->f_lead, ctx->f_bucket, ctx->f_ordered, ctx->f_packed, ctx->f_sorted, ctx->i_res, ctx->i_slot,
                    ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff, ctx->i_tilesum, ctx->i_partial, ctx->d_icp, ctx->d_pko, ctx->d_pko_hits, ctx->d_tap_state,
                    ctx->d_tap_key, ctx->d_tap_morton, ctx->d_tap_n, ctx->d_tap_c, ctx->d_mapdev, ctx->k_idx, ctx->k_n, ctx->k_unres, ctx->k_nunres,
@@ -293,6 +306,9 @@ extern "C" int b2lo_ctx_destroy(b2lo_ctx* ctx) {
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ev_stage) cudaEventDestroy(ctx->ev_stage);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->prof) { if (ctx->prof->created) for (int i = 0; i < Prof::POOL; ++i) { cudaEventDestroy(ctx->prof->a[i]); cudaEventDestroy(ctx->prof->b[i]); } delete ctx->prof; }
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -381,12 +397,12 @@ extern "C" int b2lo_ctx_features(b2lo_ctx* ctx, float* out_xyz, size_t cap, size
   size_t ncap = cap < ctx->pts_cap ? cap : ctx->pts_cap;
   if (!out_xyz) ncap = 0;
   // first the count, then at most `cap` points
-  B2_CUDA(cudaMemcpyAsync(ctx->h_counts + 17, ctx->d_nfeat, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  B2_CUDA(cudaMemcpyAsync(ctx->h_counts + 17, ctx->nfeat(ctx->feat_set), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   B2_CUDA(cudaStreamSynchronize(ctx->stream));
   size_t have = (size_t)ctx->h_counts[17];
   if (!out_xyz) { *m = have; return B2LO_OK; }
   if (have > cap) { *m = have; set_error("features: buffer too small (%zu < %zu)", cap, have); return B2LO_E_CAPACITY; }
-  return ctx_read_cloud(ctx, ctx->d_feat, ctx->d_nfeat, have, out_xyz, cap, m);
+  return ctx_read_cloud(ctx, ctx->feat(ctx->feat_set), ctx->nfeat(ctx->feat_set), have, out_xyz, cap, m);
 }
 
 // ---- ICP ----------------------------------------------------------------------------------------------------

@@ -183,8 +183,10 @@ __global__ void k_flt_reduce(const int* __restrict__ d_nvox, const int* __restri
   }
 }
 
-int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sample_stride_floats, float voxel) {
-  if (n_samples == 0) { ctx->feat_cap_hint = 0; B2_CUDA(cudaMemsetAsync(ctx->d_nfeat, 0, sizeof(int), ctx->stream)); return B2LO_OK; }
+int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sample_stride_floats, float voxel, int set, cudaStream_t on) {
+  cudaStream_t st = on ? on : ctx->stream;
+  if (set == 0) ctx->feat_set = 0;
+  if (n_samples == 0) { if (set == 0) ctx->feat_cap_hint = 0; B2_CUDA(cudaMemsetAsync(ctx->nfeat(set), 0, sizeof(int), st)); return B2LO_OK; }
   if (n_samples > (size_t)INT_MAX / 4) { set_error("filter: too many samples"); return B2LO_E_CAPACITY; }
   int rc = ctx_reserve_points(ctx, n_samples);
   if (rc) return rc;
@@ -194,8 +196,7 @@ int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sam
   while ((1ull << log2cap) < 2 * n_samples) ++log2cap;   // constant while the sample count stays in one power-of-two bucket
   if (log2cap > ctx->f_log2cap) { set_error("filter: scratch hash too small"); return B2LO_E_CAPACITY; }
   ctx->f_log2_last = log2cap;
-  ctx->feat_cap_hint = n_samples;
-  cudaStream_t st = ctx->stream;
+  if (set == 0) ctx->feat_cap_hint = n_samples;
   if (!ctx->sp_preloaded) {
     if ((rc = sp_begin_write(ctx))) return rc;
     ctx->h_sp->flt_src = src_dev; ctx->h_sp->flt_ns = (int)n_samples; ctx->h_sp->flt_stride = sample_stride_floats;
@@ -205,15 +206,16 @@ int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sam
   B2_CUDA(cudaMemsetAsync(ctx->f_tab, 0xFF, sizeof(FEntry) << log2cap, st));
   int blocks = (int)((ctx->pts_cap + 255) / 256); if (blocks > 1184) blocks = 1184;
   const ScanParams* sp = ctx->d_sp;
-  prof_begin(ctx, PS_FILTER);
+  const bool prof = st == ctx->stream;   // the per-stage events live on the context stream
+  if (prof) prof_begin(ctx, PS_FILTER);
   k_flt_insert<<<blocks, 256, 0, st>>>(sp, ctx->f_tab, log2cap, ctx->f_samp, ctx->f_slot);
   k_flt_flags<<<blocks, 256, 0, st>>>(ctx->f_tab, ctx->f_slot, sp, ctx->f_packed);
-  k_flt_scan<<<1, 1024, 0, st>>>(ctx->f_packed, sp, ctx->f_vid, ctx->f_segstart, ctx->f_segcnt, ctx->f_lead, ctx->d_nfeat);
+  k_flt_scan<<<1, 1024, 0, st>>>(ctx->f_packed, sp, ctx->f_vid, ctx->f_segstart, ctx->f_segcnt, ctx->f_lead, ctx->nfeat(set));
   k_flt_fill<<<blocks, 256, 0, st>>>(ctx->f_tab, ctx->f_slot, sp, ctx->f_vid, ctx->f_segstart, ctx->f_bucket);
   k_flt_rank<<<blocks, 256, 0, st>>>(ctx->f_tab, ctx->f_slot, sp, ctx->f_vid, ctx->f_segstart, ctx->f_segcnt, ctx->f_bucket, ctx->f_samp, ctx->f_sorted);
-  k_flt_reduce<<<blocks, 256, 0, st>>>(ctx->d_nfeat, ctx->f_segstart, ctx->f_segcnt, ctx->f_sorted, ctx->f_lead, ctx->f_slot, ctx->f_tab,
-                                       ctx->d_feat, ctx->d_feat_key);
-  prof_end(ctx);
+  k_flt_reduce<<<blocks, 256, 0, st>>>(ctx->nfeat(set), ctx->f_segstart, ctx->f_segcnt, ctx->f_sorted, ctx->f_lead, ctx->f_slot, ctx->f_tab,
+                                       ctx->feat(set), ctx->feat_key(set));
+  if (prof) prof_end(ctx);
   ctx->launches += 6;
   B2_CUDA(cudaGetLastError());
   return B2LO_OK;

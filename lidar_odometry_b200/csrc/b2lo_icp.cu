@@ -368,6 +368,7 @@ __device__ __forceinline__ double em_rsqrt(double x) {
   return y;
 }
 
+constexpr int PKO_TOFF = 1024;
 constexpr int EM_SPL = MAXS / 32;   // samples per lane in the EM (4): sample index = lane + 32 k
 static_assert(MAXS % 32 == 0, "EM layout needs a multiple of 32 samples");
 
@@ -407,6 +408,7 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
   __shared__ double s_exp2[32];
   __shared__ double s_dm[2][4];
   __shared__ double s_par[3][4];
+  __shared__ int s_toff[PKO_TOFF];   // tile offsets of the first PKO_TOFF tiles: the sample draw's binary search stays on chip
   const int tid = threadIdx.x;
   const long long c0 = clock64();
   long long c1 = c0, c2 = c0;
@@ -430,7 +432,7 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
     int c = t < ntiles ? tilecnt[t] : 0;
     int tot;
     int e = block_excl_scan(c, &tot, sm);
-    if (t < ntiles) tileoff[t] = base + e;
+    if (t < ntiles) { tileoff[t] = base + e; if (t < PKO_TOFF) s_toff[t] = base + e; }
     base += tot;
   }
   const int C = base;
@@ -477,13 +479,19 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
     }
     int ci = best;
     if (best < 0) {
-      int pos = tid;
-      const int top = C - 1 < MAXS - 1 ? C - 1 : MAXS - 1;
-      for (int i = top; i >= 1; --i) { int r = s_head[i]; pos = (pos == i) ? r : ((pos == r) ? i : pos); }
-      ci = pos;
+      if (C >= MAXS) ci = T->head_pos[mode][tid];   // all 127 head swaps apply: the trace is a constant of the mode
+      else {
+        int pos = tid;
+        for (int i = C - 1; i >= 1; --i) { int r = s_head[i]; pos = (pos == i) ? r : ((pos == r) ? i : pos); }
+        ci = pos;
+      }
     }
     int tl = 0, th = ntiles - 1;  // last tile with tileoff <= ci
-    while (tl < th) { int mid = (tl + th + 1) >> 1; if (tileoff[mid] <= ci) tl = mid; else th = mid - 1; }
+    if (ntiles <= PKO_TOFF) {
+      while (tl < th) { int mid = (tl + th + 1) >> 1; if (s_toff[mid] <= ci) tl = mid; else th = mid - 1; }
+    } else {
+      while (tl < th) { int mid = (tl + th + 1) >> 1; if (tileoff[mid] <= ci) tl = mid; else th = mid - 1; }
+    }
     int q = cidx[tl * ctile + (ci - tileoff[tl])];
     s_x[tid] = res[q] / sdiv;
   }
@@ -505,7 +513,8 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
   double cnt[3] = {0.0, 0.0, 0.0};
   for (;;) {
     ++km_iters;
-    double v[4] = {0.0, 0.0, 0.0, 0.0};   // sum1, sum2, count1, count2
+    double v[2] = {0.0, 0.0};   // sum1, sum2
+    int cn = 0;                 // count1 | count2 << 16 (exact in any order, so they travel as integers)
 #pragma unroll
     for (int k = 0; k < EM_SPL; ++k) {
       double md = fabs(x[k]);  // |x - mean0|, mean0 = 0
@@ -513,12 +522,16 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
       int cl = 0;
       if (d1 < md) { md = d1; cl = 1; }
       if (d2 < md) { md = d2; cl = 2; }
-      if (act[k]) { v[0] += (cl == 1) ? x[k] : 0.0; v[1] += (cl == 2) ? x[k] : 0.0; v[2] += (cl == 1) ? 1.0 : 0.0; v[3] += (cl == 2) ? 1.0 : 0.0; }
+      cl = act[k] ? cl : 0;
+      v[0] += (cl == 1) ? x[k] : 0.0; v[1] += (cl == 2) ? x[k] : 0.0;   // idle lanes hold x = 0 and add +0.0
+      cn += (cl == 1 ? 1 : 0) + (cl == 2 ? 65536 : 0);
     }
-    warp_sum_multi<4>(v);
-    const double n1 = v[2] > 0.0 ? v[0] / v[2] : v[0];
-    const double n2 = v[3] > 0.0 ? v[1] / v[3] : v[1];
-    cnt[1] = v[2]; cnt[2] = v[3]; cnt[0] = (double)ns - v[2] - v[3];
+    warp_sum_multi<2>(v);
+    cn = __reduce_add_sync(0xffffffffu, cn);
+    const double k1 = (double)(cn & 0xffff), k2 = (double)(cn >> 16);
+    const double n1 = k1 > 0.0 ? v[0] / k1 : v[0];
+    const double n2 = k2 > 0.0 ? v[1] / k2 : v[1];
+    cnt[1] = k1; cnt[2] = k2; cnt[0] = (double)ns - k1 - k2;
     const bool same = (n1 == m1 && n2 == m2);
     if (same || km_iters >= 100000) break;
     m1 = n1; m2 = n2;

@@ -30,6 +30,7 @@ struct PkoTables {                // built on the host once per context (b2lo_pk
   int n_alpha;                    // num_alpha_segments + 1
   int kmeans_seed[129][2];        // uniform_int_distribution(0, ns-1)(mt19937(42)) draws for sample size ns
   int head_r[3][128];             // first swaps r_i (i < 128) of std::shuffle per mode (even, odd, large n)
+  int head_pos[3][128];           // per mode: where position j ends up after the first 127 swaps alone (valid for n >= 128)
   int hit_off[3][129];            // per mode, per head position j: [hit_off[j], hit_off[j+1]) into hits
   int hit_n;
   // config scalars
@@ -100,6 +101,13 @@ struct b2lo_ctx {
   float* d_raw = nullptr; size_t raw_floats = 0;     // raw scan DMA target when the caller's buffer is page-locked
   // feature cloud (output of the filter, input of ICP / transform)
   float4* d_feat = nullptr; unsigned long long* d_feat_key = nullptr; int* d_nfeat = nullptr;
+  // second feature set: the odometry's look-ahead K1 fills it on stream2 while the current scan registers out of the other one
+  float4* d_feat2 = nullptr; unsigned long long* d_feat_key2 = nullptr; int* d_nfeat2 = nullptr;
+  cudaStream_t stream2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int feat_set = 0;                // which set holds the features of the scan processed last (b2lo_ctx_features reads it)
+  float4* feat(int set) const { return set ? d_feat2 : d_feat; }
+  unsigned long long* feat_key(int set) const { return set ? d_feat_key2 : d_feat_key; }
+  int* nfeat(int set) const { return set ? d_nfeat2 : d_nfeat; }
   // ICP query cloud uploaded from the host
   float4* d_query = nullptr; int* d_nquery = nullptr;
   float4* d_world = nullptr;       // transformed cloud (map update input)
@@ -163,7 +171,7 @@ int ctx_stage_h2d(b2lo_ctx* ctx, const float* xyz, size_t n, size_t stride_float
 int ctx_transform(b2lo_ctx* ctx, const float4* src, const int* d_n, size_t n_cap, const float T16[16], float4* dst);
 int ctx_transform_dev(b2lo_ctx* ctx, const float4* src, const int* d_n, size_t n_cap, const float* T16_dev, const int* gate, float4* dst);
 int ctx_read_cloud(b2lo_ctx* ctx, const float4* src, const int* d_n, size_t n_cap, float* out_xyz, size_t out_cap, size_t* n_out);
-int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sample_stride_floats, float voxel);
+int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sample_stride_floats, float voxel, int set = 0, cudaStream_t on = nullptr);
 int icp_build_pko(b2lo_ctx* ctx, const b2lo_icp_cfg* cfg);
 int icp_prepare(b2lo_ctx* ctx, const b2lo_icp_cfg* cfg);
 int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_cap, const float* T_init16, const b2lo_icp_cfg* cfg, bool init_pose_on_device);

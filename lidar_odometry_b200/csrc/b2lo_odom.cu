@@ -24,8 +24,14 @@ struct b2lo_odom {
   Pose pose, prev_pose, velocity, last_kf_pose;
   bool initialized = false;
   int n_keyframes = 0;
-  cudaGraphExec_t gexec = nullptr;  // replayable launch sequence of one steady-state scan
-  unsigned long long gsig[4] = {0, 0, 0, 0};
+  // replayable launch sequences of one steady-state scan, one per (where K1 runs, which feature set registers): index 2 * mode + set
+  cudaGraphExec_t gexec[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  unsigned long long gsig[6][4] = {};
+  // look-ahead (b2lo_odom_lookahead): the scan announced for the NEXT call, and the scan whose K1 already ran into set pre_set
+  bool la_valid = false, pre_valid = false;
+  const float* la_src = nullptr; size_t la_ns = 0, la_stride = 0;
+  const float* pre_src = nullptr; size_t pre_ns = 0, pre_stride = 0; int pre_set = 0;
+  long long lookahead_hits = 0;
   bool allow_graph = true;
   long long graph_launches = 0, graph_builds = 0, launches_per_graph = 0;
   OdomDev* d_out = nullptr;        // device result block of k_odom_decide
@@ -113,7 +119,7 @@ extern "C" int b2lo_odom_create(b2lo_ctx* ctx, const b2lo_odom_cfg* cfg, b2lo_od
 }
 extern "C" int b2lo_odom_destroy(b2lo_odom* od) {
   if (!od) return B2LO_E_ARG;
-  if (od->gexec) cudaGraphExecDestroy(od->gexec);
+  for (cudaGraphExec_t g : od->gexec) if (g) cudaGraphExecDestroy(g);
   if (od->d_out) cudaFree(od->d_out);
   if (od->h_out) cudaFreeHost(od->h_out);
   if (od->map) b2lo_map_destroy(od->map);
@@ -150,34 +156,60 @@ static int create_keyframe(b2lo_odom* od, size_t n_cap) {
   return B2LO_OK;
 }
 
+// where K1 runs relative to the captured sequence
+enum ScanMode { K1_SERIAL = 0 /* this scan's K1, in line */, K1_NEXT = 1 /* the announced next scan's K1, beside the registration */, K1_NONE = 2 };
+
 // the launch sequence of one steady-state scan on the context stream: K1 -> ICP -> pose/keyframe decision -> gated K6 -> read-backs.
 // Everything that changes from scan to scan sits in the parameter block, so the very same sequence is what the CUDA graph replays.
-static int enqueue_scan(b2lo_odom* od, size_t ns, size_t cap, bool in_graph) {
+// In K1_NEXT mode the filter fields of the block describe the NEXT scan: its K1 runs on the side stream into the other feature set
+// while this scan registers (mostly single-CTA, latency-bound kernels) out of set `set`; the two branches join before the read-backs end.
+static int enqueue_scan(b2lo_odom* od, size_t flt_ns, size_t cap, bool in_graph, int mode, int set, bool side_stream) {
   b2lo_ctx* ctx = od->ctx;
   b2lo_map* map = od->map;
   cudaStream_t st = ctx->stream;
-  int rc;
+  int rc = B2LO_OK;
   if (in_graph) B2_CUDA(cudaMemcpyAsync(ctx->d_sp, ctx->h_sp, sizeof(ScanParams), cudaMemcpyHostToDevice, st));
   ctx->sp_preloaded = true;
-  rc = filter_run(ctx, ctx->h_sp->flt_src, ns, (size_t)ctx->h_sp->flt_stride, od->cfg.voxel_size);
-  if (!rc) rc = icp_run(map, ctx->d_feat, ctx->d_nfeat, cap, ctx->h_sp->T_init, &od->cfg.icp, false);
+  bool forked = false;
+  if (mode == K1_SERIAL) rc = filter_run(ctx, ctx->h_sp->flt_src, flt_ns, (size_t)ctx->h_sp->flt_stride, od->cfg.voxel_size, set, st);
+  else if (mode == K1_NEXT) {
+    cudaStream_t fs = side_stream ? ctx->stream2 : st;
+    if (fs != st) {
+      cudaError_t e = cudaEventRecord(ctx->ev_fork, st);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(fs, ctx->ev_fork, 0);
+      if (e != cudaSuccess) { ctx->sp_preloaded = false; set_error("odometry: fork failed: %s", cudaGetErrorString(e)); return B2LO_E_CUDA; }
+      forked = true;
+    }
+    rc = filter_run(ctx, ctx->h_sp->flt_src, flt_ns, (size_t)ctx->h_sp->flt_stride, od->cfg.voxel_size, set ^ 1, fs);
+    if (forked && cudaEventRecord(ctx->ev_join, fs) != cudaSuccess) rc = rc ? rc : B2LO_E_CUDA;
+  }
+  float4* feat = ctx->feat(set);
+  int* nfeat = ctx->nfeat(set);
+  if (!rc) rc = icp_run(map, feat, nfeat, cap, ctx->h_sp->T_init, &od->cfg.icp, false);
   ctx->sp_preloaded = false;
-  if (rc) return rc;
-  k_odom_decide<<<1, 32, 0, st>>>(ctx->d_icp, ctx->d_sp, ctx->d_nfeat, od->d_out);
-  ctx->launches++;
-  rc = ctx_transform_dev(ctx, ctx->d_feat, ctx->d_nfeat, cap, od->d_out->pose, &od->d_out->keyframe, ctx->d_world);
-  if (rc) return rc;
-  const double md = od->cfg.max_range * 1.2;  // Estimator.cpp:455
-  const float zero3[3] = {0.0f, 0.0f, 0.0f};
-  map->graph_mode = true;   // cull kernels take the live voxel count from the device counter, grids from the capacity
-  rc = map_update_dev(map, ctx->d_world, ctx->d_nfeat, cap, zero3, (float)(md * md), 0, &od->d_out->keyframe, od->d_out->pose);
-  map->graph_mode = false;
-  if (rc < 0) return rc;
-  B2_CUDA(cudaMemcpyAsync(ctx->h_icp, ctx->d_icp, offsetof(IcpState, trace), cudaMemcpyDeviceToHost, st));
-  B2_CUDA(cudaMemcpyAsync(od->h_out, od->d_out, sizeof(OdomDev), cudaMemcpyDeviceToHost, st));
-  B2_CUDA(cudaMemcpyAsync(ctx->h_counts, map->d.ctr, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
-  B2_CUDA(cudaMemcpyAsync(ctx->h_counts + 32, ctx->d_nfeat, sizeof(int), cudaMemcpyDeviceToHost, st));
-  return B2LO_OK;
+  if (!rc) {
+    k_odom_decide<<<1, 32, 0, st>>>(ctx->d_icp, ctx->d_sp, nfeat, od->d_out);
+    ctx->launches++;
+    rc = ctx_transform_dev(ctx, feat, nfeat, cap, od->d_out->pose, &od->d_out->keyframe, ctx->d_world);
+  }
+  if (!rc) {
+    const double md = od->cfg.max_range * 1.2;  // Estimator.cpp:455
+    const float zero3[3] = {0.0f, 0.0f, 0.0f};
+    map->graph_mode = true;   // cull kernels take the live voxel count from the device counter, grids from the capacity
+    rc = map_update_dev(map, ctx->d_world, nfeat, cap, zero3, (float)(md * md), 0, &od->d_out->keyframe, od->d_out->pose);
+    map->graph_mode = false;
+    if (rc > 0) rc = B2LO_OK;
+  }
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(ctx->h_icp, ctx->d_icp, offsetof(IcpState, trace), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(od->h_out, od->d_out, sizeof(OdomDev), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_counts, map->d.ctr, 8 * sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_counts + 32, nfeat, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) { set_error("odometry: read-back failed: %s", cudaGetErrorString(e)); rc = B2LO_E_CUDA; }
+  }
+  // always re-join a forked branch, also on errors: a capture must not end with an unjoined stream
+  if (forked && cudaStreamWaitEvent(st, ctx->ev_join, 0) != cudaSuccess && !rc) rc = B2LO_E_CUDA;
+  return rc;
 }
 
 static int steady_scan(b2lo_odom* od, const float* src_dev, size_t ns, size_t sample_stride_floats, b2lo_odom_result* res, double t0) {
@@ -190,33 +222,48 @@ static int steady_scan(b2lo_odom* od, const float* src_dev, size_t ns, size_t sa
     set_error("odometry: the map is empty after initialisation");
     return B2LO_E_ARG;
   }
+  // look-ahead bookkeeping: was this scan's K1 already done by the previous call, and is a next scan announced?
+  const bool have_pre = od->pre_valid && od->pre_src == src_dev && od->pre_ns == ns && od->pre_stride == sample_stride_floats;
+  const int set = have_pre ? od->pre_set : 0;
+  const bool want_next = od->la_valid && od->la_ns > 0;
+  const float* nx_src = od->la_src; const size_t nx_ns = od->la_ns, nx_stride = od->la_stride;
+  od->pre_valid = false; od->la_valid = false;
+  if (have_pre) od->lookahead_hits++;
   // capacities first (may reallocate and synchronise): nothing below allocates
-  if ((rc = ctx_reserve_points(ctx, ns))) return rc;
+  if ((rc = ctx_reserve_points(ctx, want_next && nx_ns > ns ? nx_ns : ns))) return rc;
   const size_t cap = ctx->pts_cap;
   if ((rc = map_reserve(map, map->n0 + cap, cap))) return rc;
   if ((rc = icp_prepare(ctx, &od->cfg.icp))) return rc;
+  const int mode = want_next ? K1_NEXT : (have_pre ? K1_NONE : K1_SERIAL);
+  if (!have_pre && mode != K1_SERIAL) {   // first scan of a pipelined run: this scan's K1 in line, ahead of the replayed sequence
+    if ((rc = filter_run(ctx, src_dev, ns, sample_stride_floats, od->cfg.voxel_size, 0, st))) return rc;
+  }
   // the parameter block of this scan
   Pose guess = pose_mul(od->prev_pose, od->velocity);  // Estimator.cpp:154
   Pose init = pose_reproject(guess);
   if ((rc = sp_begin_write(ctx))) return rc;
   ScanParams* sp = ctx->h_sp;
-  sp->flt_src = src_dev; sp->flt_ns = (int)ns; sp->flt_stride = sample_stride_floats; sp->flt_inv = 1.0f / od->cfg.voxel_size;
+  const size_t flt_ns = mode == K1_NEXT ? nx_ns : ns;
+  sp->flt_src = mode == K1_NEXT ? nx_src : src_dev; sp->flt_ns = (int)flt_ns;
+  sp->flt_stride = mode == K1_NEXT ? nx_stride : sample_stride_floats; sp->flt_inv = 1.0f / od->cfg.voxel_size;
   pose_to_T16(init, sp->T_init);
   pose_to_T16(guess, sp->decide.guess);
   pose_to_T16(od->last_kf_pose, sp->decide.last_kf);
   sp->decide.ran_icp = 1; sp->decide.n_keyframes = od->n_keyframes;
   sp->decide.kf_dist = od->cfg.keyframe_distance_threshold; sp->decide.kf_rot = od->cfg.keyframe_rotation_threshold;
   int l2 = 12;
-  while ((1ull << l2) < 2 * ns) ++l2;
+  while ((1ull << l2) < 2 * flt_ns) ++l2;
+  if (mode == K1_NONE) l2 = 0;
   const unsigned long long sig[4] = {ctx->alloc_epoch, map->alloc_epoch, (unsigned long long)l2, (unsigned long long)cap};
   const bool profiling = ctx->prof && ctx->prof->on;
   bool use_graph = od->allow_graph && !profiling && od->n_keyframes >= 1;
-  if (use_graph && (!od->gexec || std::memcmp(sig, od->gsig, sizeof sig) != 0)) {
-    if (od->gexec) { cudaGraphExecDestroy(od->gexec); od->gexec = nullptr; }
+  const int gi = 2 * mode + set;
+  if (use_graph && (!od->gexec[gi] || std::memcmp(sig, od->gsig[gi], sizeof sig) != 0)) {
+    if (od->gexec[gi]) { cudaGraphExecDestroy(od->gexec[gi]); od->gexec[gi] = nullptr; }
     cudaGraph_t g = nullptr;
     long long launches0 = ctx->launches;
     B2_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    rc = enqueue_scan(od, ns, cap, true);
+    rc = enqueue_scan(od, flt_ns, cap, true, mode, set, true);
     cudaError_t ce = cudaStreamEndCapture(st, &g);
     const long long in_capture = ctx->launches - launches0;
     ctx->launches = launches0;
@@ -226,25 +273,27 @@ static int steady_scan(b2lo_odom* od, const float* src_dev, size_t ns, size_t sa
       od->allow_graph = false;  // fall back to plain stream launches for good
       use_graph = false;
     } else {
-      ce = cudaGraphInstantiate(&od->gexec, g, 0);
+      ce = cudaGraphInstantiate(&od->gexec[gi], g, 0);
       cudaGraphDestroy(g);
-      if (ce != cudaSuccess) { od->gexec = nullptr; od->allow_graph = false; use_graph = false; cudaGetLastError(); }
-      else { std::memcpy(od->gsig, sig, sizeof sig); od->graph_builds++; od->launches_per_graph = in_capture; }
+      if (ce != cudaSuccess) { od->gexec[gi] = nullptr; od->allow_graph = false; use_graph = false; cudaGetLastError(); }
+      else { std::memcpy(od->gsig[gi], sig, sizeof sig); od->graph_builds++; od->launches_per_graph = in_capture; }
     }
   }
   if (use_graph) {
-    B2_CUDA(cudaGraphLaunch(od->gexec, st));
+    B2_CUDA(cudaGraphLaunch(od->gexec[gi], st));
     ctx->launches += od->launches_per_graph;
     od->graph_launches++;
   } else {
     if ((rc = sp_upload(ctx, 0, sizeof(ScanParams)))) return rc;
-    if ((rc = enqueue_scan(od, ns, cap, false))) return rc;
+    if ((rc = enqueue_scan(od, flt_ns, cap, false, mode, set, !profiling))) return rc;
   }
+  ctx->feat_set = set;
   double t1 = now_us();
   B2_CUDA(cudaStreamSynchronize(st));
   double t2 = now_us();
   ctx->host_us[1] += t1 - t0; ctx->host_us[2] += t2 - t1;
   ctx->d2h_bytes += offsetof(IcpState, trace) + sizeof(int) + sizeof(OdomDev) + 8 * sizeof(int);
+  if (mode == K1_NEXT) { od->pre_valid = true; od->pre_src = nx_src; od->pre_ns = nx_ns; od->pre_stride = nx_stride; od->pre_set = set ^ 1; }
   res->n_features = hc[0];
   if (hc[0] == 0) return B2LO_S_EMPTY;   // nothing was changed: the gated update was switched off, the pose state is untouched
   res->icp_status = od->h_out->icp_status;
@@ -274,6 +323,7 @@ static int process_common(b2lo_odom* od, const float* src_dev, size_t ns, size_t
   int rc = B2LO_OK;
   int* hc = ctx->h_counts + 32;
   if (!od->initialized) {  // initialize_first_frame
+    od->la_valid = false;   // the first frame never runs beside anything: an announcement made before it is dropped
     rc = filter_run(ctx, src_dev, ns, sample_stride_floats, od->cfg.voxel_size);
     if (rc) return rc;
     B2_CUDA(cudaMemcpyAsync(hc, ctx->d_nfeat, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -368,6 +418,28 @@ extern "C" int b2lo_odom_process_dev(b2lo_odom* od, const float* xyz_dev, size_t
   return process_timed(od, xyz_dev, ns, stride_floats * S, res, false);
 }
 
+extern "C" int b2lo_odom_lookahead(b2lo_odom* od, const float* xyz_next, size_t n, size_t stride_floats, int on_device) {
+  if (!od) return B2LO_E_ARG;
+  if (stride_floats < 3) return B2LO_E_ARG;
+  b2lo_ctx* ctx = od->ctx;
+  std::lock_guard<std::recursive_mutex> lk(od->map->mu);
+  std::lock_guard<std::mutex> lk2(ctx->mu);
+  od->la_valid = false;
+  if (!xyz_next || n == 0) return B2LO_S_EMPTY;
+  cudaSetDevice(ctx->device);
+  const float* src = xyz_next;
+  if (!on_device) {
+    cudaPointerAttributes attr;
+    const bool pinned = (cudaPointerGetAttributes(&attr, xyz_next) == cudaSuccess) && attr.type == cudaMemoryTypeHost && attr.devicePointer;
+    if (!pinned || getenv("B2LO_NO_ZERO_COPY")) { cudaGetLastError(); return B2LO_S_EMPTY; }
+    src = static_cast<const float*>(attr.devicePointer);
+  }
+  const size_t S = (size_t)(od->cfg.point_stride < 1 ? 1 : od->cfg.point_stride);
+  od->la_src = src; od->la_ns = (n + S - 1) / S; od->la_stride = stride_floats * S;
+  od->la_valid = true;
+  return B2LO_OK;
+}
+
 extern "C" int b2lo_odom_graph_stats(b2lo_odom* od, long long* replays, long long* builds, long long* kernels_per_replay) {
   if (!od) return B2LO_E_ARG;
   if (replays) *replays = od->graph_launches;
@@ -382,5 +454,6 @@ extern "C" int b2lo_odom_reset(b2lo_odom* od) {
   od->pose = od->prev_pose = od->velocity = od->last_kf_pose = pose_identity();
   od->initialized = false;
   od->n_keyframes = 0;
+  od->la_valid = od->pre_valid = false;
   return rc;
 }

@@ -98,6 +98,11 @@ void pko_build_host(const b2lo_icp_cfg* cfg, PkoTables* t, std::vector<int>* hit
   for (int mode = 0; mode < 3; ++mode) {
     std::vector<int> r = shuffle_partners(sizes[mode]);
     for (int i = 0; i < HEAD; ++i) t->head_r[mode][i] = r[i];
+    for (int j = 0; j < HEAD; ++j) {   // backward trace of position j through swaps HEAD-1 .. 1
+      int pos = j;
+      for (int i = HEAD - 1; i >= 1; --i) { int ri = r[i]; pos = (pos == i) ? ri : ((pos == ri) ? i : pos); }
+      t->head_pos[mode][j] = pos;
+    }
     std::vector<std::vector<int>> per(HEAD);
     for (int i = HEAD; i < sizes[mode]; ++i) if (r[i] < HEAD) per[r[i]].push_back(i);
     for (int j = 0; j < HEAD; ++j) {

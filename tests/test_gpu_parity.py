@@ -493,6 +493,54 @@ def test_graph_replay_pinned_and_pageable_paths_agree(b2, small_kitti, monkeypat
     assert np.array_equal(a[1], b[1]) and np.array_equal(bits(a[0]), bits(b[0]))
 
 
+def test_lookahead_overlap_is_bit_identical(b2, small_kitti, monkeypatch):
+    """b2lo_odom_lookahead: K1 of scan i+1 runs beside the registration of scan i (second feature set, side stream, own graphs).
+    Poses, counters, the map and the feature buffer are bit-identical to the plain call sequence - with page-locked host scans,
+    with device-resident scans, with plain launches instead of graphs, and when an announcement is not honoured by the next call."""
+    import torch
+    scans, _ = small_kitti
+    scans = list(scans) + list(scans[::-1]) + list(scans[2:5])
+    plain = b2.Odometry()
+    want = [plain.process(s) for s in scans]
+    want_feat = plain.ctx.features() if hasattr(plain.ctx, "features") else None
+    pins = [torch.from_numpy(np.ascontiguousarray(s)).pin_memory() for s in scans]
+    devs = [torch.from_numpy(np.ascontiguousarray(s)).cuda() for s in scans]
+
+    def same(r, w, k):
+        assert np.array_equal(bits(r["pose"]), bits(w["pose"])), f"scan {k}"
+        assert (r["ok"], r["keyframe"], r["icp_ok"], r["n_features"], r["n_corr"], r["n_iters"], r["l0"], r["l1"]) == \
+               (w["ok"], w["keyframe"], w["icp_ok"], w["n_features"], w["n_corr"], w["n_iters"], w["l0"], w["l1"]), f"scan {k}"
+
+    def run(odo, mode):
+        for k in range(len(scans)):
+            nxt = k + 1 if k + 1 < len(scans) else None
+            if mode == "host":
+                r = odo.process(pins[k].numpy(), lookahead=pins[nxt].numpy() if nxt is not None else None)
+            elif mode == "dev":
+                la = (devs[nxt].data_ptr(), devs[nxt].shape[0], devs[nxt].shape[1]) if nxt is not None else None
+                r = odo.process_dev(devs[k].data_ptr(), devs[k].shape[0], devs[k].shape[1], lookahead=la)
+            else:   # every third announcement names the wrong scan: the next call must notice and run its own K1
+                wrong = nxt is not None and k % 3 == 1
+                la = pins[(nxt + 2) % len(scans)].numpy() if wrong else (pins[nxt].numpy() if nxt is not None else None)
+                r = odo.process(pins[k].numpy(), lookahead=la)
+            same(r, want[k], k)
+        a, b = odo.map().export_l0(), plain.map().export_l0()
+        assert np.array_equal(a[1], b[1]) and np.array_equal(bits(a[0]), bits(b[0]))
+        if want_feat is not None:
+            assert np.array_equal(bits(odo.ctx.features()), bits(want_feat))
+
+    for mode in ("host", "dev", "mismatch"):
+        odo = b2.Odometry(b2.Context(0))
+        run(odo, mode)
+        assert odo.graph_stats()["replays"] > 0
+    assert not b2.Odometry().lookahead(np.zeros((100, 4), np.float32))       # pageable host memory: ignored, not an error
+    monkeypatch.setenv("B2LO_NO_GRAPH", "1")
+    odo = b2.Odometry(b2.Context(0))
+    monkeypatch.delenv("B2LO_NO_GRAPH")
+    run(odo, "host")
+    assert odo.graph_stats()["replays"] == 0
+
+
 # ---- BASELINE.json sizes ------------------------------------------------------------------------------------------------
 def test_full_size_kitti_scans(orc, b2):
     """configs[1] at full size (64 x 1900 rays, ~120 k points per scan): K1 bit-exact on whole scans, and the free-running
