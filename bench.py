@@ -233,30 +233,44 @@ def stress_leg(ctx, api, capi, target_voxels, peak, peak_kind):
     L.b2lo_ctx_profile_read(ctx.h, 8, C.byref(ms_cull), C.byref(n_cull))
     L.b2lo_ctx_profile_read(ctx.h, 5, C.byref(ms_upd), C.byref(n_updl))
     cull_gbs = 16.0 * v0 * n_cull.value / max(ms_cull.value * 1e-3, 1e-12) / 1e9
-    # K2 probe: 2^20 queries spread over the map, one correspondence pass per optimize call
+    # K2 probe: 2^20 queries, one correspondence pass per optimize call.  "random": uniformly spread over the map (every query
+    # its own 32 B table sector -> the worst case for DRAM); "coherent": a raster sweep over the slabs like a real scan, where
+    # the ~9 queries of one 1.5 m L1 cell share a sector through L2.
     nq = 1 << 20
-    q = np.stack([rng.uniform(-109, 109, nq), rng.uniform(-109, 109, nq), -39.0 + 1.5 * rng.integers(0, layers, nq) + 0.7 + rng.normal(0, 0.02, nq)], axis=1).astype(np.float32)
+    probes = {}
     icp = api.IterativeClosestPointOptimizer(api.ICPConfig(max_iterations=1), api.AdaptiveMEstimator())
-    icp.optimize(vmap, q, np.eye(4, dtype=np.float32))   # warm-up (allocations, PKO tables)
-    L.b2lo_ctx_profile(ctx.h, 1)
-    reps = 10
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    for _ in range(reps):
-        flush.zero_(); torch.cuda.synchronize()
-        ok, _T = icp.optimize(vmap, q, np.eye(4, dtype=np.float32))
-    ncorr = icp.get_last_stats().num_correspondences
-    ms_k2, n_k2, ms_gn, n_gn = C.c_double(), C.c_longlong(), C.c_double(), C.c_longlong()
-    L.b2lo_ctx_profile_read(ctx.h, 1, C.byref(ms_k2), C.byref(n_k2))
-    L.b2lo_ctx_profile_read(ctx.h, 4, C.byref(ms_gn), C.byref(n_gn))
-    L.b2lo_ctx_profile(ctx.h, 0)
-    k2_gbs = ALGO_BYTES_PER_QUERY * nq * n_k2.value / max(ms_k2.value * 1e-3, 1e-12) / 1e9
+    ms_gn, n_gn = C.c_double(), C.c_longlong()
+    for kind in ("random", "coherent"):
+        if kind == "random":
+            q = np.stack([rng.uniform(-109, 109, nq), rng.uniform(-109, 109, nq), -39.0 + 1.5 * rng.integers(0, layers, nq) + 0.7 + rng.normal(0, 0.02, nq)], axis=1).astype(np.float32)
+        else:
+            ax = np.arange(-109.0, 109.0, 0.5)          # one query per 0.5 m L0 cell, raster order: 9 queries per 1.5 m L1 cell and layer
+            xx, yy = np.meshgrid(ax, ax, indexing="ij")
+            xy = np.stack([xx.ravel(), yy.ravel()], axis=1)
+            need = (nq + len(xy) - 1) // len(xy)
+            q = np.concatenate([np.concatenate([xy, np.full((len(xy), 1), -39.0 + 1.5 * l + 0.7)], axis=1) for l in range(need)])[:nq]
+            q = (q + rng.normal(0, 0.01, q.shape)).astype(np.float32)
+        icp.optimize(vmap, q, np.eye(4, dtype=np.float32))   # warm-up (allocations, PKO tables)
+        L.b2lo_ctx_profile(ctx.h, 1)
+        reps = 10
+        for _ in range(reps):
+            flush.zero_(); torch.cuda.synchronize()
+            ok, _T = icp.optimize(vmap, q, np.eye(4, dtype=np.float32))
+        ncorr = icp.get_last_stats().num_correspondences
+        ms_k2, n_k2 = C.c_double(), C.c_longlong()
+        L.b2lo_ctx_profile_read(ctx.h, 1, C.byref(ms_k2), C.byref(n_k2))
+        L.b2lo_ctx_profile_read(ctx.h, 4, C.byref(ms_gn), C.byref(n_gn))
+        L.b2lo_ctx_profile(ctx.h, 0)
+        k2_gbs = ALGO_BYTES_PER_QUERY * nq * n_k2.value / max(ms_k2.value * 1e-3, 1e-12) / 1e9
+        probes[kind] = {"queries": nq, "accepted": ncorr, "avg_launch_us": 1e3 * ms_k2.value / max(n_k2.value, 1), "achieved_gbs": k2_gbs,
+                        "frac_of_hbm_peak": k2_gbs / peak, "peak_kind": f"of {peak_kind}", "queries_per_s": nq * n_k2.value / max(ms_k2.value * 1e-3, 1e-12),
+                        "algorithmic_bytes_per_query": ALGO_BYTES_PER_QUERY, "l2": "flushed between launches; L1 hash table > L2"}
+    probes["random"].update({"traffic_bytes_per_launch": 113600000, "traffic_source": "ncu --set full, profiles/r01_ncu_full_k2_stress.csv: 2.26x the algorithmic bytes (64 B DRAM access per random 32 B sector + 12 B/query of results) = 2.4 TB/s, bound by random-sector DRAM access"})
     del vmap
     return {"workload": f"{layers} planar slabs of {side}x{side} voxels (0.5 m), one point per voxel", "l0_voxels": v0, "l1_voxels": v1, "surfels": nsurf,
             "build_s": t_build,
-            "k2_probe": {"queries": nq, "accepted": ncorr, "avg_launch_us": 1e3 * ms_k2.value / max(n_k2.value, 1), "achieved_gbs": k2_gbs,
-                         "frac_of_hbm_peak": k2_gbs / peak, "peak_kind": f"of {peak_kind}", "queries_per_s": nq * n_k2.value / max(ms_k2.value * 1e-3, 1e-12),
-                         "algorithmic_bytes_per_query": ALGO_BYTES_PER_QUERY, "l2": "flushed between launches; L1 hash table > L2",
-                         "traffic_bytes_per_launch": 113600000, "traffic_source": "ncu --set full, profiles/r01_ncu_full_k2_stress.csv: 2.26x the algorithmic bytes (64 B DRAM access per random 32 B sector + 12 B/query of results) = 2.4 TB/s, bound by random-sector DRAM access"},
+            "k2_probe": probes["random"], "k2_probe_coherent": probes["coherent"],
             "k5_normal_eq": {"avg_launch_us": 1e3 * ms_gn.value / max(n_gn.value, 1)},
             "k6_cull_scan": {"avg_launch_us": 1e3 * ms_cull.value / max(n_cull.value, 1), "achieved_gbs": cull_gbs, "frac_of_hbm_peak": cull_gbs / peak,
                              "algorithmic_bytes_per_voxel": 16},
@@ -302,7 +316,8 @@ def main():
     K, W = args.steps, args.warmup
     if args.stress_only:
         peak, peak_kind = peaks()
-        print(json.dumps(stress_leg(api.Context(local), api, capi, int(args.stress_voxels), peak, peak_kind)["k2_probe"]))
+        st = stress_leg(api.Context(local), api, capi, int(args.stress_voxels), peak, peak_kind)
+        print(json.dumps({"k2_probe": st["k2_probe"], "k2_probe_coherent": st["k2_probe_coherent"]}))
         return
     scans, _ = make_scans(K + W + 1, 42, f"cuda:{local}")   # weak scaling: every rank processes its own copy of the same sequence; +1: the look-ahead of the last timed scan
     ctx = api.Context(local)

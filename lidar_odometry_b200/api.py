@@ -31,7 +31,7 @@ def _f32(a):
 
 
 def _p(a):
-    return None if a is None else a.ctypes.data_as(C.c_void_p)
+    return None if a is None else C.c_void_p(a.ctypes.data)   # the caller holds `a` for the duration of the call
 
 
 def _cloud(a):
@@ -585,7 +585,7 @@ class Odometry:
 
     @staticmethod
     def _result(rc, r: OdomResult):
-        return dict(ok=rc == B2LO_OK, pose=np.array(r.pose, np.float32).reshape(4, 4), keyframe=bool(r.keyframe), icp_ok=r.icp_status == B2LO_OK,
+        return dict(ok=rc == B2LO_OK, pose=np.frombuffer(r.pose, dtype=np.float32).reshape(4, 4).copy(), keyframe=bool(r.keyframe), icp_ok=r.icp_status == B2LO_OK,
                     n_features=r.n_features, n_corr=r.n_corr, n_iters=r.n_iters, device_ms=r.device_ms, l0=r.l0, l1=r.l1)
 
     def lookahead(self, next_scan) -> bool:

@@ -40,8 +40,8 @@ __device__ __forceinline__ void transform_point(const float* R, const float* t, 
 __device__ __forceinline__ int surfel_probe(const MapDev& M, const float* w, float* n, float* c, int* key3, unsigned long long* morton) {
   int kx = voxel_coord(w[0], M.scale1), ky = voxel_coord(w[1], M.scale1), kz = voxel_coord(w[2], M.scale1);
   if (key3) { key3[0] = kx; key3[1] = ky; key3[2] = kz; }
-  unsigned long long key = key_morton(kx, ky, kz);
-  if (morton) *morton = key;
+  unsigned long long key = key_pack(kx, ky, kz);
+  if (morton) *morton = key_morton(kx, ky, kz);   // debug tap: the reference's VoxelKeyHash value
   if (!key_in_range(kx, ky, kz)) return -1;
   uint32_t mask = (1u << M.l1_log2cap) - 1u;
   uint32_t s = hash_slot(key, M.l1_log2cap);
@@ -83,77 +83,109 @@ __device__ __forceinline__ void block_sum2_t0(double& a, double& b, double* smd 
   __syncthreads();
 }
 
-// K2.  One thread takes QPT consecutive queries (64 B of the float4 query stream), issues their QPT first hash probes
-// back to back (independent 32 B sectors in flight), then gates and compacts.  Accepted queries are written in
-// ascending query order per CT-query tile (cidx) with the tile count (tilecnt); k_icp_pko1 scans the tile counts.
+// K2.  One query per thread, TILE queries per compaction tile, persistent CTAs striding over the tiles.  Each query is a
+// chain of two dependent memory round trips (16 B query point -> key -> 32 B surfel sector), so the loop is software-pipelined
+// three deep: while tile t is gated and compacted, the sector loads of tile t+G and the point loads of tile t+2G are in flight
+// (G = gridDim.x).  Both 16 B halves of a sector are requested together, all loop-invariant loads (done flag, pose, count,
+// first point) are issued before the first use, and compaction costs one barrier per tile (warp ballots + one shared exchange).
+// Accepted queries are written in ascending query order per tile (cidx) with the tile count (tilecnt) and the tile's raw
+// residual moments (tilesum); k_icp_pko1 scans the tile counts.
 // Algorithmic traffic per query: 16 B query + 32 B surfel sector (+ 12 B of per-query results: slot, f64 residual).
-// QPT = 1 for scan-sized clouds (more threads, shortest chain), 4 for dense clouds (more probes in flight per thread).
-template <int QPT>
-__global__ void __launch_bounds__(TILE) k_icp_corr(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, IcpState* st,
+struct CorrStage {   // a query between its key computation and its gate
+  float w[3];
+  unsigned long long key;
+  uint32_t hs;
+  float4 ea, eb;
+};
+__device__ __forceinline__ void corr_issue(const MapDev& M, const float* sR, const float* sT, float4 p, bool valid, CorrStage& q) {
+  transform_point(sR, sT, p.x, p.y, p.z, q.w);
+  int kx = voxel_coord(q.w[0], M.scale1), ky = voxel_coord(q.w[1], M.scale1), kz = voxel_coord(q.w[2], M.scale1);
+  q.key = (valid && key_in_range(kx, ky, kz)) ? key_pack(kx, ky, kz) : KEY_TOMB;   // TOMB never matches: no surfel
+  q.hs = hash_slot(q.key, M.l1_log2cap);
+  const float4* e = reinterpret_cast<const float4*>(&M.l1_tab[q.hs]);
+  q.ea = __ldg(e);        // key (8 B), n.x, n.y
+  q.eb = __ldg(e + 1);    // n.z, c.x, c.y, c.z  (same 32 B sector)
+}
+template <int DEPTH, int MINB>
+__global__ void __launch_bounds__(TILE, MINB) k_icp_corr(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, IcpState* st,
                                                    IcpParams prm, double* res, int* slot_out, int* cidx, int* tilecnt, double* tilesum) {
-  if (st->done) return;
-  __shared__ int sm[40];
-  __shared__ double smd2[16];
   __shared__ float sR[9], sT[3];
-  if (threadIdx.x < 9) sR[threadIdx.x] = st->R[threadIdx.x];
-  if (threadIdx.x < 3) sT[threadIdx.x] = st->t[threadIdx.x];
-  __syncthreads();
-  constexpr int CT = TILE * QPT;   // queries per compaction tile
+  __shared__ int s_cnt[2][TILE / 32];
+  __shared__ double s_sum[2][TILE / 32][2];
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const int G = gridDim.x;
+  // every loop-invariant load and the first point go out together (the buffers are sized in whole tiles, see ctx_reserve_points)
+  const int done = st->done;
   const int npts = *d_npts;
-  const int ntiles = (npts + CT - 1) / CT;
+  float pose_v = 0.0f;
+  if (tid < 12) pose_v = tid < 9 ? st->R[tid] : st->t[tid - 9];
+  int tile = blockIdx.x;
+  float4 p1 = pts[tile * TILE + tid];
+  if (done) return;
+  if (tid < 9) sR[tid] = pose_v; else if (tid < 12) sT[tid - 9] = pose_v;
+  __syncthreads();
+  const int ntiles = (npts + TILE - 1) / TILE;
+  if (tile >= ntiles) return;
   const uint32_t mask = (1u << M.l1_log2cap) - 1u;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int i0 = tile * CT + threadIdx.x * QPT;
-    float w[QPT][3];
-    unsigned long long key[QPT];
-    uint32_t hs[QPT];
-    float4 ea[QPT];
-#pragma unroll
-    for (int u = 0; u < QPT; ++u) {
-      const int i = i0 + u;
-      float4 p = (i < npts) ? pts[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-      transform_point(sR, sT, p.x, p.y, p.z, w[u]);
-      int kx = voxel_coord(w[u][0], M.scale1), ky = voxel_coord(w[u][1], M.scale1), kz = voxel_coord(w[u][2], M.scale1);
-      key[u] = (i < npts && key_in_range(kx, ky, kz)) ? key_morton(kx, ky, kz) : KEY_TOMB;   // TOMB never matches: no surfel
-      hs[u] = hash_slot(key[u], M.l1_log2cap);
-    }
-#pragma unroll
-    for (int u = 0; u < QPT; ++u) ea[u] = __ldg(reinterpret_cast<const float4*>(&M.l1_tab[hs[u]]));   // QPT sectors in flight
-    int okm = 0, nok = 0;
-    double a1 = 0.0, a2 = 0.0;   // sum r, sum r^2 over the accepted queries of this tile (residual scale, ICP.cpp:304-316)
-#pragma unroll
-    for (int u = 0; u < QPT; ++u) {
-      const int i = i0 + u;
-      int s = -1;
-      double r = 0.0;
-      if (key[u] != KEY_TOMB) {
-        uint32_t h = hs[u];
-        float4 a = ea[u];
-        for (uint32_t probe = 0; probe <= mask; ++probe) {
-          unsigned long long k = ((unsigned long long)__float_as_uint(a.y) << 32) | (unsigned long long)__float_as_uint(a.x);
-          if (k == KEY_EMPTY) break;
-          if (k != KEY_TOMB && (k & KEY_MASK) == key[u]) {
-            if (k & SURFEL_BIT) {
-              float4 b = __ldg(reinterpret_cast<const float4*>(&M.l1_tab[h]) + 1);   // same 32 B sector
-              float n[3] = {a.z, a.w, b.x}, c[3] = {b.y, b.z, b.w};
-              r = gate_residual(n, c, w[u]);
-              if (!(r > prm.max_dist)) s = (int)h;
-            }
-            break;
+  CorrStage cur;
+  corr_issue(M, sR, sT, p1, tile * TILE + tid < npts, cur);
+  if (DEPTH >= 3 && tile + G < ntiles) p1 = pts[(tile + G) * TILE + tid];
+  int ph = 0;
+  for (; tile < ntiles; tile += G) {
+    const int i = tile * TILE + tid;
+    // point of tile + 2G
+    float4 p2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (DEPTH >= 3) { if (tile + 2 * G < ntiles) p2 = pts[(tile + 2 * G) * TILE + tid]; }
+    else if (tile + G < ntiles) p1 = pts[(tile + G) * TILE + tid];
+    // gate of this tile
+    int s = -1;
+    double r = 0.0;
+    if (cur.key != KEY_TOMB) {
+      uint32_t h = cur.hs;
+      float4 a = cur.ea, b = cur.eb;
+      for (uint32_t probe = 0; probe <= mask; ++probe) {
+        unsigned long long k = ((unsigned long long)__float_as_uint(a.y) << 32) | (unsigned long long)__float_as_uint(a.x);
+        if (k == KEY_EMPTY) break;
+        if (k != KEY_TOMB && (k & KEY_MASK) == cur.key) {
+          if (k & SURFEL_BIT) {
+            float n[3] = {a.z, a.w, b.x}, c[3] = {b.y, b.z, b.w};
+            r = gate_residual(n, c, cur.w);
+            if (!(r > prm.max_dist)) s = (int)h;
           }
-          h = (h + 1) & mask;
-          a = __ldg(reinterpret_cast<const float4*>(&M.l1_tab[h]));
+          break;
         }
+        h = (h + 1) & mask;
+        const float4* e = reinterpret_cast<const float4*>(&M.l1_tab[h]);
+        a = __ldg(e); b = __ldg(e + 1);
       }
-      if (i < npts) { slot_out[i] = s; res[i] = r; }
-      if (s >= 0) { okm |= 1 << u; ++nok; a1 += r; a2 += r * r; }
     }
-    int total;
-    int off = tile * CT + block_excl_scan(nok, &total, sm);
+    const bool in = i < npts;
+    // sector loads of tile + G
+    CorrStage nxt;
+    const bool more = tile + G < ntiles;
+    if (more) corr_issue(M, sR, sT, p1, (tile + G) * TILE + tid < npts, nxt);
+    // results + compaction of this tile: ascending query order, one barrier
+    if (in) { slot_out[i] = s; res[i] = r; }
+    const bool ok = s >= 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    double a1 = ok ? r : 0.0, a2 = ok ? r * r : 0.0;   // sum r, sum r^2 over the accepted queries (residual scale, ICP.cpp:304-316)
 #pragma unroll
-    for (int u = 0; u < QPT; ++u) if (okm & (1 << u)) cidx[off++] = i0 + u;
-    block_sum2_t0(a1, a2, smd2);
-    if (threadIdx.x == 0) { tilecnt[tile] = total; tilesum[2 * tile] = a1; tilesum[2 * tile + 1] = a2; }
+    for (int o = 16; o > 0; o >>= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o); }
+    if (lane == 0) { s_cnt[ph][wrp] = __popc(bal); s_sum[ph][wrp][0] = a1; s_sum[ph][wrp][1] = a2; }
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < TILE / 32; ++w2) { const int c = s_cnt[ph][w2]; before += w2 < wrp ? c : 0; total += c; }
+    if (ok) cidx[tile * TILE + before + __popc(bal & ((1u << lane) - 1u))] = i;
+    if (tid == 0) {
+      double sa = 0.0, sb = 0.0;
+#pragma unroll
+      for (int w2 = 0; w2 < TILE / 32; ++w2) { sa += s_sum[ph][w2][0]; sb += s_sum[ph][w2][1]; }
+      tilecnt[tile] = total; tilesum[2 * tile] = sa; tilesum[2 * tile + 1] = sb;
+    }
+    ph ^= 1;   // the other buffer is rewritten only after the next barrier: nobody still reads it then
+    if (more) cur = nxt;
+    p1 = p2;
   }
 }
 
@@ -876,6 +908,26 @@ __global__ void k_icp_taps(MapDev M, const float4* __restrict__ pts, int npts, c
 }
 
 // ---------------------------------------------------------------------------------------------------
+typedef void (*corr_kernel_t)(MapDev, const float4*, const int*, IcpState*, IcpParams, double*, int*, int*, int*, double*);
+static corr_kernel_t corr_kernel() {
+  static corr_kernel_t k = nullptr;
+  if (!k) {
+    int v = 0;
+    if (const char* e = getenv("B2LO_CORR_V")) v = atoi(e);
+    k = v == 1 ? k_icp_corr<3, 6> : v == 2 ? k_icp_corr<2, 8> : v == 3 ? k_icp_corr<2, 6> : k_icp_corr<3, 1>;
+  }
+  return k;
+}
+static int corr_resident_ctas(b2lo_ctx* ctx) {
+  static int per_sm = 0;   // a property of the compiled kernel, identical on every device of this build
+  if (per_sm == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, corr_kernel(), TILE, 0) != cudaSuccess || n < 1) { cudaGetLastError(); n = 4; }
+    per_sm = n;
+  }
+  return ctx->sm_count * per_sm;
+}
+
 static int knn_reserve(b2lo_ctx* ctx) {
   if (ctx->k_cap >= ctx->pts_cap) return B2LO_OK;
   B2_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -939,8 +991,7 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
   prm.loss_type = cfg->loss_type; prm.use_pko = cfg->use_adaptive_m_estimator; prm.use_surfel = cfg->use_surfel_correspondence;
   prm.tol_t = cfg->translation_tolerance; prm.tol_r = cfg->rotation_tolerance; prm.max_dist = cfg->max_correspondence_distance;
   prm.robust_delta = cfg->robust_loss_delta;
-  int qpt = 1;   // measured on the 10^7-voxel map: 1 query/thread (32 regs, 8 CTAs/SM) 45.5 us, 2: 47.7 us, 4: 52.4 us per 2^20 probes
-  if (const char* e = getenv("B2LO_QPT")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) qpt = v; }
+  const int qpt = 1;   // measured on the 10^7-voxel map: 1 query/thread 45.5 us, 2: 47.7 us, 4: 52.4 us per 2^20 random probes
   prm.ctile = surfel ? TILE * qpt : TILE;
   (void)init_pose_on_device;
   if (!ctx->sp_preloaded) {
@@ -953,7 +1004,8 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
   if (grid_knn > ctx->sm_count * 8) grid_knn = ctx->sm_count * 8;
   if (grid_knn < 1) grid_knn = 1;
   int ctiles_cap = (int)((npts_cap + prm.ctile - 1) / prm.ctile);
-  int grid_corr = ctiles_cap < 1 ? 1 : (ctiles_cap > ctx->sm_count * 8 ? ctx->sm_count * 8 : ctiles_cap);
+  const int corr_res = corr_resident_ctas(ctx);   // persistent, software-pipelined: exactly one wave
+  int grid_corr = ctiles_cap < 1 ? 1 : (ctiles_cap > corr_res ? corr_res : ctiles_cap);
   int ntiles_cap = (int)((npts_cap + TILE - 1) / TILE);
   int grid = ntiles_cap < 1 ? 1 : (ntiles_cap > ctx->i_max_blocks ? ctx->i_max_blocks : ntiles_cap);
   double* gmm = ctx->i_partial + (size_t)ctx->i_max_blocks * 28;      // 9 GMM doubles, then P(r_k) at [16, 116)
@@ -962,9 +1014,7 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
   for (int it = 0; it < cfg->max_iterations; ++it) {
     if (surfel) {
       prof_begin(ctx, PS_CORR);
-      if (qpt == 4) k_icp_corr<4><<<grid_corr, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum);
-      else if (qpt == 2) k_icp_corr<2><<<grid_corr, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum);
-      else k_icp_corr<1><<<grid_corr, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum);
+      corr_kernel()<<<grid_corr, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum);
       prof_end(ctx);
     } else {
       prof_begin(ctx, PS_KNN);
@@ -1235,11 +1285,11 @@ extern "C" int b2lo_icp_shard_corr(b2lo_map* map, const b2lo_icp_cfg* cfg, doubl
   const size_t m = ctx->shard_m ? ctx->shard_m : 1;
   shard_params(cfg, m, prm, qpt);
   int ctiles = (int)((m + prm.ctile - 1) / prm.ctile);
-  int grid = ctiles > ctx->sm_count * 8 ? ctx->sm_count * 8 : ctiles;
+  const int corr_res = corr_resident_ctas(ctx);
+  int grid = ctiles > corr_res ? corr_res : ctiles;
   cudaStream_t s = ctx->stream;
   prof_begin(ctx, PS_CORR);
-  if (qpt == 4) k_icp_corr<4><<<grid, TILE, 0, s>>>(map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum);
-  else k_icp_corr<1><<<grid, TILE, 0, s>>>(map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum);
+  corr_kernel()<<<grid, TILE, 0, s>>>(map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum);
   prof_end(ctx);
   k_shard_stats<<<1, 256, 0, s>>>(ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_blkcnt, ctx->i_blkoff, stats3_dev, ctx->i_tilesum);
   ctx->launches += 2;

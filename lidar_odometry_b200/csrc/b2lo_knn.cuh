@@ -106,7 +106,7 @@ __device__ __forceinline__ bool knn_rings_warp(const MapDev& M, const float* w, 
   if (lane < 27) {
     int x = kx + lane % 3 - 1, y = ky + (lane / 3) % 3 - 1, z = kz + lane / 9 - 1;
     if (key_in_range(x, y, z)) {
-      int s0 = l0_find(M, key_morton(x, y, z));
+      int s0 = l0_find(M, key_pack(x, y, z));
       if (s0 >= 0) { int pos = (int)M.l0_tab[s0].pos; float4 c = M.l0_cent[pos]; mine.push(knn_dist2(w, c.x, c.y, c.z), pos); }
     }
   }
@@ -119,7 +119,7 @@ __device__ __forceinline__ bool knn_rings_warp(const MapDev& M, const float* w, 
       if (dx > -r && dx < r && dy > -r && dy < r && dz > -r && dz < r) continue;   // inner cube already visited
       int x = kx + dx, y = ky + dy, z = kz + dz;
       if (!key_in_range(x, y, z)) continue;
-      int s0 = l0_find(M, key_morton(x, y, z));
+      int s0 = l0_find(M, key_pack(x, y, z));
       if (s0 < 0) continue;
       int pos = (int)M.l0_tab[s0].pos;
       float4 cc = M.l0_cent[pos];

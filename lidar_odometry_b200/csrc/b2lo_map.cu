@@ -31,7 +31,7 @@ constexpr int SIM_SMEM_K = 12000;  // (4k+2) ints <= 192 KB of dynamic shared me
 constexpr int SIM_SMEM_BYTES = (4 * SIM_SMEM_K + 2) * (int)sizeof(int);
 
 __device__ __forceinline__ unsigned long long child_key(int px, int py, int pz, int f, int code) {
-  return key_morton(px * f + code % 3, py * f + (code / 3) % 3, pz * f + code / 9);
+  return key_pack(px * f + code % 3, py * f + (code / 3) % 3, pz * f + code / 9);
 }
 
 // Replay of k swap-with-last erases (in the given order) on a dense vector of size n, on indices only; whole CTA.
@@ -149,8 +149,8 @@ __global__ void __launch_bounds__(1024) k_cull_lists(MapDev M, int n0, const uin
     if (pos >= n0 || !mk) continue;
     removed[pre] = pos;
     int x, y, z;
-    morton_key(M.l0_key[pos], x, y, z);
-    unsigned long long pk = key_morton(parent_coord(x, M.factor), parent_coord(y, M.factor), parent_coord(z, M.factor));
+    key_unpack(M.l0_key[pos], x, y, z);
+    unsigned long long pk = key_pack(parent_coord(x, M.factor), parent_coord(y, M.factor), parent_coord(z, M.factor));
     int s1 = l1_find(M, pk);
     if (s1 >= 0 && atomicCAS(&M.l1_meta[s1].mark, 0, 1) == 0) l1work[atomicAdd(&us[US_NWORK], 1)] = s1;
   }
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(1024) k_cull_fix(MapDev M, const uint8_t* flag
     L1Meta* mt = &M.l1_meta[s1];
     unsigned long long k1 = M.l1_tab[s1].key;
     int px, py, pz;
-    morton_key(k1 & KEY_MASK, px, py, pz);
+    key_unpack(k1 & KEY_MASK, px, py, pz);
     int n = mt->nchild;
     int code = lane < n ? mt->child[lane] : -1;
     int rp = INT_MAX;  // dense position of this lane's child if it is being removed
@@ -226,7 +226,7 @@ __global__ void k_ins_probe(MapDev M, const float4* __restrict__ pts, const int*
     int ax = voxel_coord(p.x, M.scale1), ay = voxel_coord(p.y, M.scale1), az = voxel_coord(p.z, M.scale1);
     if (!key_in_range(x, y, z) || !(p.x == p.x) || !(p.y == p.y) || !(p.z == p.z)) { atomicOr(&us[US_ERR], ERR_RANGE); pslot[i] = -1; continue; }
     bool ins;
-    int s0 = l0_find_or_insert(M, key_morton(x, y, z), &ins);
+    int s0 = l0_find_or_insert(M, key_pack(x, y, z), &ins);
     if (s0 < 0) { atomicOr(&us[US_ERR], ERR_CAP); pslot[i] = -1; continue; }
     L0Entry* e = &M.l0_tab[s0];
     atomicMin(&e->first, (unsigned)i);
@@ -234,7 +234,7 @@ __global__ void k_ins_probe(MapDev M, const float4* __restrict__ pts, const int*
     nxt[i] = atomicExch(&e->head, i);      // idle value -1
     pslot[i] = s0;
     // affected_L1.insert(PointToVoxelKey(point, 1))  (VoxelMap.cpp:178-179) — float division by voxel*3
-    unsigned long long ak = key_morton(ax, ay, az);
+    unsigned long long ak = key_pack(ax, ay, az);
     uint32_t mask = (1u << alog2) - 1u, h = hash_slot(ak, alog2);
     for (;;) {
       unsigned long long kk = *((volatile unsigned long long*)&atab[h].key);
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(256) k_ins_place(MapDev M, const int* __restri
     const int pos = base + myrank;
     const unsigned long long key = M.l0_tab[s0].key;
     int x, y, z;
-    morton_key(key, x, y, z);
+    key_unpack(key, x, y, z);
     const int px = parent_coord(x, M.factor), py = parent_coord(y, M.factor), pz = parent_coord(z, M.factor);
     const int mycode = (x - px * M.factor) + 3 * (y - py * M.factor) + 9 * (z - pz * M.factor);
     int s1 = -1;
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(256) k_ins_place(MapDev M, const int* __restri
       M.l0_slot[pos] = (uint32_t)s0;
       M.l0_tab[s0].pos = (uint32_t)pos;
       bool ins;
-      s1 = l1_find_or_insert(M, key_morton(px, py, pz), &ins);  // a fresh slot has zeroed meta: no children, no surfel
+      s1 = l1_find_or_insert(M, key_pack(px, py, pz), &ins);  // a fresh slot has zeroed meta: no children, no surfel
       if (s1 < 0) atomicOr(&us[US_ERR], ERR_CAP);
       else if (ins) atomicAdd(&M.ctr[CT_N1], 1);
     }
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(256) k_surfel(MapDev M, FEntry* atab, const in
     if (N < 5) { if (lane == 0) M.l1_tab[s1].key = k1 & ~SURFEL_BIT; continue; }
     if ((k1 & SURFEL_BIT) && mt->last_child_count == N) continue;  // incremental skip (VoxelMap.cpp:202-205)
     int px, py, pz;
-    morton_key(k1 & KEY_MASK, px, py, pz);
+    key_unpack(k1 & KEY_MASK, px, py, pz);
     float cx = 0.0f, cy = 0.0f, cz = 0.0f;
     int have = 0;
     if (lane < N) {
@@ -450,7 +450,7 @@ __global__ void k_surfel_all(MapDev M) {
     int N = mt->nchild;
     if (N < 5) { M.l1_tab[s1].key = k1 & ~SURFEL_BIT; continue; }
     int px, py, pz;
-    morton_key(k1 & KEY_MASK, px, py, pz);
+    key_unpack(k1 & KEY_MASK, px, py, pz);
     float cents[27 * 3]; int nc = 0;
     for (int ci = 0; ci < N; ++ci) {
       int s0 = l0_find(M, child_key(px, py, pz, M.factor, mt->child[ci]));
@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(1024) k_upd_close(MapDev M, int* us, const int
     int s1 = pord[t];
     L1Meta* mt = &M.l1_meta[s1];
     int px, py, pz;
-    morton_key(M.l1_tab[s1].key & KEY_MASK, px, py, pz);
+    key_unpack(M.l1_tab[s1].key & KEY_MASK, px, py, pz);
     int N = mt->nchild, o = poff[t];
     if (lane < N) {
       int s0 = l0_find(M, child_key(px, py, pz, M.factor, mt->child[lane]));
@@ -582,7 +582,7 @@ __global__ void k_export_l0(MapDev M, int n0, float* xyz, int* keys, int* counts
   for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n0; pos += gridDim.x * blockDim.x) {
     float4 c = M.l0_cent[pos];
     xyz[pos * 3] = c.x; xyz[pos * 3 + 1] = c.y; xyz[pos * 3 + 2] = c.z;
-    if (keys) { int x, y, z; morton_key(M.l0_key[pos], x, y, z); keys[pos * 3] = x; keys[pos * 3 + 1] = y; keys[pos * 3 + 2] = z; }
+    if (keys) { int x, y, z; key_unpack(M.l0_key[pos], x, y, z); keys[pos * 3] = x; keys[pos * 3 + 1] = y; keys[pos * 3 + 2] = z; }
     if (counts) counts[pos] = __float_as_int(c.w);
   }
 }
@@ -597,7 +597,7 @@ __global__ void k_export_l1(MapDev M, int* counter, int cap, int surfels_only, i
     if (o >= cap) continue;
     const L1Meta* mt = &M.l1_meta[s];
     int px, py, pz;
-    morton_key(k & KEY_MASK, px, py, pz);
+    key_unpack(k & KEY_MASK, px, py, pz);
     if (keys) { keys[o * 3] = px; keys[o * 3 + 1] = py; keys[o * 3 + 2] = pz; }
     if (nchild) nchild[o] = mt->nchild;
     if (children) for (int ci = 0; ci < 27; ++ci) {
