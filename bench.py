@@ -266,7 +266,7 @@ def stress_leg(ctx, api, capi, target_voxels, peak, peak_kind):
         probes[kind] = {"queries": nq, "accepted": ncorr, "avg_launch_us": 1e3 * ms_k2.value / max(n_k2.value, 1), "achieved_gbs": k2_gbs,
                         "frac_of_hbm_peak": k2_gbs / peak, "peak_kind": f"of {peak_kind}", "queries_per_s": nq * n_k2.value / max(ms_k2.value * 1e-3, 1e-12),
                         "algorithmic_bytes_per_query": ALGO_BYTES_PER_QUERY, "l2": "flushed between launches; L1 hash table > L2"}
-    probes["random"].update({"traffic_bytes_per_launch": 113600000, "traffic_source": "ncu --set full, profiles/r01_ncu_full_k2_stress.csv: 2.26x the algorithmic bytes (64 B DRAM access per random 32 B sector + 12 B/query of results) = 2.4 TB/s, bound by random-sector DRAM access"})
+    probes["random"].update({"traffic_bytes_per_launch": 115305984, "traffic_source": "ncu, profiles/r01_ncu_k2_stress_final.csv: 2.3x the algorithmic bytes (64 B DRAM access per random 32 B sector + 12 B/query of results); 115.3 MB in 33.2 us = 3.5 TB/s = 53 % of the measured HBM peak in traffic terms: bound by random-sector DRAM access"})
     del vmap
     return {"workload": f"{layers} planar slabs of {side}x{side} voxels (0.5 m), one point per voxel", "l0_voxels": v0, "l1_voxels": v1, "surfels": nsurf,
             "build_s": t_build,

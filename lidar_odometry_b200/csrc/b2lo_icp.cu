@@ -173,9 +173,9 @@ __global__ void __launch_bounds__(TILE, MINB) k_icp_corr(MapDev M, const float4*
     for (int o = 16; o > 0; o >>= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o); }
     if (lane == 0) { s_cnt[ph][wrp] = __popc(bal); s_sum[ph][wrp][0] = a1; s_sum[ph][wrp][1] = a2; }
     __syncthreads();
-    int before = 0, total = 0;
-#pragma unroll
-    for (int w2 = 0; w2 < TILE / 32; ++w2) { const int c = s_cnt[ph][w2]; before += w2 < wrp ? c : 0; total += c; }
+    const int cw = lane < TILE / 32 ? s_cnt[ph][lane] : 0;            // lane l holds the count of warp l
+    const int total = __reduce_add_sync(0xffffffffu, cw);
+    const int before = __reduce_add_sync(0xffffffffu, lane < wrp ? cw : 0);
     if (ok) cidx[tile * TILE + before + __popc(bal & ((1u << lane) - 1u))] = i;
     if (tid == 0) {
       double sa = 0.0, sb = 0.0;
@@ -909,23 +909,24 @@ __global__ void k_icp_taps(MapDev M, const float4* __restrict__ pts, int npts, c
 
 // ---------------------------------------------------------------------------------------------------
 typedef void (*corr_kernel_t)(MapDev, const float4*, const int*, IcpState*, IcpParams, double*, int*, int*, int*, double*);
-static corr_kernel_t corr_kernel() {
-  static corr_kernel_t k = nullptr;
-  if (!k) {
-    int v = 0;
-    if (const char* e = getenv("B2LO_CORR_V")) v = atoi(e);
-    k = v == 1 ? k_icp_corr<3, 6> : v == 2 ? k_icp_corr<2, 8> : v == 3 ? k_icp_corr<2, 6> : k_icp_corr<3, 1>;
-  }
-  return k;
-}
-static int corr_resident_ctas(b2lo_ctx* ctx) {
+// K2 launch geometry for a sequence built for `ctiles_cap` tiles: the kernel is persistent and software-pipelined, so exactly one
+// resident wave.  (A cp.async-streamed variant with deeper thread-private shared-memory rings was tried for dense clouds and was
+// slower: the 16 B LDGSTS copies saturate the MIO queue - ncu: mio_throttle 9.4 stalls per issue, 44.8 us vs 33.2 us per 2^20 probes.)
+struct CorrLaunch { corr_kernel_t k; int grid; size_t smem; };
+static CorrLaunch corr_launch(b2lo_ctx* ctx, int ctiles_cap) {
   static int per_sm = 0;   // a property of the compiled kernel, identical on every device of this build
+  static corr_kernel_t kern = nullptr;
   if (per_sm == 0) {
+    kern = k_icp_corr<3, 1>;   // 80 registers, 3 CTAs/SM; capping at 64 registers for 4 CTAs/SM measured the same (37.1 vs 37.7 us)
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, corr_kernel(), TILE, 0) != cudaSuccess || n < 1) { cudaGetLastError(); n = 4; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, TILE, 0) != cudaSuccess || n < 1) { cudaGetLastError(); n = 2; }
     per_sm = n;
   }
-  return ctx->sm_count * per_sm;
+  if (ctiles_cap < 1) ctiles_cap = 1;
+  const int resident = ctx->sm_count * per_sm;
+  CorrLaunch L;
+  L.k = kern; L.grid = ctiles_cap < resident ? ctiles_cap : resident; L.smem = 0;
+  return L;
 }
 
 static int knn_reserve(b2lo_ctx* ctx) {
@@ -1004,8 +1005,7 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
   if (grid_knn > ctx->sm_count * 8) grid_knn = ctx->sm_count * 8;
   if (grid_knn < 1) grid_knn = 1;
   int ctiles_cap = (int)((npts_cap + prm.ctile - 1) / prm.ctile);
-  const int corr_res = corr_resident_ctas(ctx);   // persistent, software-pipelined: exactly one wave
-  int grid_corr = ctiles_cap < 1 ? 1 : (ctiles_cap > corr_res ? corr_res : ctiles_cap);
+  const CorrLaunch cl = corr_launch(ctx, ctiles_cap);
   int ntiles_cap = (int)((npts_cap + TILE - 1) / TILE);
   int grid = ntiles_cap < 1 ? 1 : (ntiles_cap > ctx->i_max_blocks ? ctx->i_max_blocks : ntiles_cap);
   double* gmm = ctx->i_partial + (size_t)ctx->i_max_blocks * 28;      // 9 GMM doubles, then P(r_k) at [16, 116)
@@ -1014,7 +1014,7 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
   for (int it = 0; it < cfg->max_iterations; ++it) {
     if (surfel) {
       prof_begin(ctx, PS_CORR);
-      corr_kernel()<<<grid_corr, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum);
+      cl.k<<<cl.grid, TILE, cl.smem, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum);
       prof_end(ctx);
     } else {
       prof_begin(ctx, PS_KNN);
@@ -1285,11 +1285,10 @@ extern "C" int b2lo_icp_shard_corr(b2lo_map* map, const b2lo_icp_cfg* cfg, doubl
   const size_t m = ctx->shard_m ? ctx->shard_m : 1;
   shard_params(cfg, m, prm, qpt);
   int ctiles = (int)((m + prm.ctile - 1) / prm.ctile);
-  const int corr_res = corr_resident_ctas(ctx);
-  int grid = ctiles > corr_res ? corr_res : ctiles;
+  const CorrLaunch cl = corr_launch(ctx, ctiles);
   cudaStream_t s = ctx->stream;
   prof_begin(ctx, PS_CORR);
-  corr_kernel()<<<grid, TILE, 0, s>>>(map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum);
+  cl.k<<<cl.grid, TILE, cl.smem, s>>>(map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum);
   prof_end(ctx);
   k_shard_stats<<<1, 256, 0, s>>>(ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_blkcnt, ctx->i_blkoff, stats3_dev, ctx->i_tilesum);
   ctx->launches += 2;

@@ -297,6 +297,32 @@ def test_icp_variants_and_failure(orc, b2, small_kitti):
     assert not ok_g
 
 
+def test_dense_cloud_streamed_correspondences(orc, b2, small_kitti):
+    """A dense cloud (400 k queries: more tiles than one resident wave) takes the cp.async-streamed K2 kernel; first GN iteration
+    against the oracle: same correspondence count, same residual scale, same alpha, H/g within 1e-5 relative."""
+    scans, poses = small_kitti
+    omap, gmap, kfs = _built_maps(orc, b2, scans, poses)
+    feat = kfs[3][0]
+    rng = np.random.default_rng(5)
+    reps = 400_000 // len(feat) + 1
+    dense = np.concatenate([feat + rng.normal(0.0, 0.05, feat.shape).astype(np.float32) for _ in range(reps)])[:400_000]
+    far = rng.random(len(dense)) < 0.01                        # a few queries far outside the map / outside the key range
+    dense[far] += np.float32(5.0e3)
+    dense[::50_000] = np.float32(3.0e6)
+    init = T32(poses[2])
+    cfg_o = orc.default_icp_cfg(); cfg_o.max_iterations = 1
+    ok_o, T_o, tr_o = orc.icp_optimize(omap, dense, init, cfg_o)
+    icp = b2.IterativeClosestPointOptimizer(b2.ICPConfig(max_iterations=1), b2.AdaptiveMEstimator())
+    ok_g, T_g = icp.optimize(gmap, dense, init)
+    tr_g = icp.get_last_stats().iterations
+    assert ok_o and ok_g
+    assert tr_o[0]["n_corr"] == tr_g[0]["n_corr"] > 100_000
+    assert abs(tr_o[0]["scale"] - tr_g[0]["scale"]) <= 1e-12 * abs(tr_o[0]["scale"]) and tr_o[0]["delta"] == tr_g[0]["delta"]
+    assert _rel(tr_g[0]["H"], tr_o[0]["H64"]) < 1e-5 and _rel(tr_g[0]["g"], tr_o[0]["g64"]) < 1e-5
+    # the oracle solves the reference's sequential-f32 sums, whose rounding error grows with the 3e5 correspondences of this cloud
+    assert np.abs(T_g - T_o).max() < 5e-4
+
+
 # ---- K3 ---------------------------------------------------------------------------------------------------------
 def test_knn_mode_parity(orc, b2, small_mid360):
     scans, poses = small_mid360
