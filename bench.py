@@ -267,8 +267,23 @@ def stress_leg(ctx, api, capi, target_voxels, peak, peak_kind):
                         "frac_of_hbm_peak": k2_gbs / peak, "peak_kind": f"of {peak_kind}", "queries_per_s": nq * n_k2.value / max(ms_k2.value * 1e-3, 1e-12),
                         "algorithmic_bytes_per_query": ALGO_BYTES_PER_QUERY, "l2": "flushed between launches; L1 hash table > L2"}
     probes["random"].update({"traffic_bytes_per_launch": 115305984, "traffic_source": "ncu, profiles/r01_ncu_k2_stress_final.csv: 2.3x the algorithmic bytes (64 B DRAM access per random 32 B sector + 12 B/query of results); 115.3 MB in 33.2 us = 3.5 TB/s = 53 % of the measured HBM peak in traffic terms: bound by random-sector DRAM access"})
+    # bulk rebuild (ApplyTransformAndRehash + RecomputeAllSurfels, VoxelMap.cpp:264-366; runs after pose-graph corrections): transform every
+    # L0 centroid, re-key, merge collisions, rebuild L1 and refit every surfel.  Algorithmic bytes per L0 voxel: 16 B read + 16 B written
+    # + one 32 B slot written + 16 B gathered by its parent's refit = 80 B.
+    import ctypes as C2
+    from lidar_odometry_b200 import synth
+    Tr = synth.pose_matrix(0.31, -0.22, 0.05, 0.02, 0.003, -0.004).astype(np.float32)
+    vmap.ApplyTransformAndRehash(Tr)          # warm-up: sizes the scratch tables
+    ctx.sync()
+    v0b = vmap.GetVoxelCount()
+    t_re = time.perf_counter()
+    vmap.ApplyTransformAndRehash(np.linalg.inv(Tr.astype(np.float64)).astype(np.float32))
+    ctx.sync()
+    t_re = time.perf_counter() - t_re
+    rehash = {"voxels_in": v0b, "voxels_out": vmap.GetVoxelCount(), "ms": 1e3 * t_re, "algorithmic_bytes_per_voxel": 80,
+              "achieved_gbs": 80.0 * v0b / t_re / 1e9, "frac_of_hbm_peak": 80.0 * v0b / t_re / 1e9 / peak, "timing": "host wall clock around the call, synchronised"}
     del vmap
-    return {"workload": f"{layers} planar slabs of {side}x{side} voxels (0.5 m), one point per voxel", "l0_voxels": v0, "l1_voxels": v1, "surfels": nsurf,
+    return {"rehash_rebuild": rehash, "workload": f"{layers} planar slabs of {side}x{side} voxels (0.5 m), one point per voxel", "l0_voxels": v0, "l1_voxels": v1, "surfels": nsurf,
             "build_s": t_build,
             "k2_probe": probes["random"], "k2_probe_coherent": probes["coherent"],
             "k5_normal_eq": {"avg_launch_us": 1e3 * ms_gn.value / max(n_gn.value, 1)},
@@ -317,7 +332,7 @@ def main():
     if args.stress_only:
         peak, peak_kind = peaks()
         st = stress_leg(api.Context(local), api, capi, int(args.stress_voxels), peak, peak_kind)
-        print(json.dumps({"k2_probe": st["k2_probe"], "k2_probe_coherent": st["k2_probe_coherent"]}))
+        print(json.dumps({"k2_probe": st["k2_probe"], "k2_probe_coherent": st["k2_probe_coherent"], "rehash_rebuild": st["rehash_rebuild"]}))
         return
     scans, _ = make_scans(K + W + 1, 42, f"cuda:{local}")   # weak scaling: every rank processes its own copy of the same sequence; +1: the look-ahead of the last timed scan
     ctx = api.Context(local)

@@ -142,6 +142,8 @@ struct b2lo_map {
   // update scratch sized by the number of new points
   size_t upd_cap = 0;
   float4* u_pts = nullptr; int* u_pslot = nullptr; int* u_next = nullptr; int* u_isnew = nullptr; int* u_newrank = nullptr;
+  int* u_part = nullptr;            // per-chunk totals of the new-voxel scan for bulk inserts (k_ins_scan_part/top/apply)
+  float4* r_tmp = nullptr; size_t r_tmp_cap = 0; int* r_n = nullptr;   // transformed centroids of ApplyTransformAndRehash (kept between calls)
   b2::FEntry* a_tab = nullptr; int a_log2cap = 0;   // affected-L1 set of the current update
   int* a_list = nullptr;                            // purge lists (4 x upd_cap)
   int* a_slots = nullptr;                           // compacted slots of the affected-L1 set

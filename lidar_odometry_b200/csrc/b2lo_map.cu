@@ -331,6 +331,68 @@ __global__ void __launch_bounds__(1024) k_ins_scan(MapDev M, const int* __restri
     if ((long long)us[US_N0] + base > (long long)M.l0_cap) atomicOr(&us[US_ERR], ERR_CAP);
   }
 }
+// Bulk inserts (more than BULK_UPD points, e.g. ApplyTransformAndRehash of a 10^7-voxel map): the same ranks from a three-step scan
+// over INS_CHUNK-point chunks instead of one CTA walking the whole update.
+constexpr int INS_CHUNK = 4096;
+constexpr size_t BULK_UPD = 1u << 16;
+__global__ void __launch_bounds__(1024) k_ins_scan_part(const int* __restrict__ d_m, const int* __restrict__ isnew, int* part) {
+  __shared__ int sm[40];
+  const int m = *d_m;
+  const int nchunks = (m + INS_CHUNK - 1) / INS_CHUNK;
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const int i0 = c * INS_CHUNK + 4 * threadIdx.x;
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sum += (i0 + k < m) ? isnew[i0 + k] : 0;
+    int tot;
+    block_excl_scan(sum, &tot, sm);
+    if (threadIdx.x == 0) part[c] = tot;
+  }
+}
+__global__ void __launch_bounds__(1024) k_ins_scan_top(MapDev M, const int* __restrict__ d_m, int* part, int* us) {
+  __shared__ int sm[40];
+  const int m = *d_m;
+  const int nchunks = (m + INS_CHUNK - 1) / INS_CHUNK;
+  int base = 0;
+  for (int t0 = 0; t0 < nchunks; t0 += blockDim.x) {
+    const int t = t0 + threadIdx.x;
+    const int v = t < nchunks ? part[t] : 0;
+    int tot;
+    const int e = block_excl_scan(v, &tot, sm);
+    if (t < nchunks) part[t] = base + e;
+    base += tot;
+  }
+  if (threadIdx.x == 0) {
+    us[US_NNEW] = base;
+    if ((long long)us[US_N0] + base > (long long)M.l0_cap) atomicOr(&us[US_ERR], ERR_CAP);
+  }
+}
+__global__ void __launch_bounds__(1024) k_ins_scan_apply(MapDev M, const int* __restrict__ d_m, const int* __restrict__ isnew, const int* __restrict__ pslot,
+                                                         int* newrank, const int* __restrict__ part) {
+  __shared__ int sm[40];
+  const int m = *d_m;
+  const int nchunks = (m + INS_CHUNK - 1) / INS_CHUNK;
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const int i0 = c * INS_CHUNK + 4 * threadIdx.x;
+    int f[4], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { f[k] = (i0 + k < m) ? isnew[i0 + k] : 0; sum += f[k]; }
+    int tot;
+    int e = part[c] + block_excl_scan(sum, &tot, sm);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i0 + k < m) {
+        newrank[i0 + k] = e;
+        if (f[k]) { M.l0_tab[pslot[i0 + k]].rank = e; ++e; }
+      }
+    }
+  }
+}
+// creation ranks back to idle after a bulk insert (k_upd_close does it itself for keyframe-sized updates)
+__global__ void __launch_bounds__(256) k_rank_clear(MapDev M, const int* __restrict__ d_m, const int* __restrict__ pslot, const int* __restrict__ isnew) {
+  const int m = *d_m;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) if (isnew[i]) M.l0_tab[pslot[i]].rank = -1;
+}
 // one warp per new voxel: append it to the dense vector, find-or-create its parent and place it in the parent's child
 // list in creation order (RegisterToParent, VoxelMap.cpp:77-80).  Lane c probes sibling cell c of the parent: the
 // position is (#siblings that already existed) + (#new siblings created earlier), so nobody has to read nchild while
@@ -486,12 +548,12 @@ __global__ void k_xform_l0(MapDev M, int n0, Rt12 T, float4* out, int* d_n) {
 // indices, apply the moves, publish the counters.
 __global__ void __launch_bounds__(1024) k_upd_close(MapDev M, int* us, const int* plist, const unsigned int* pfirst, int* pord, int* poff, int* seq_pos,
                                                     int* aux, int purge_ran, const int* __restrict__ d_m, const int* __restrict__ pslot,
-                                                    const int* __restrict__ isnew) {
+                                                    const int* __restrict__ isnew, int ranks_cleared) {
   if (M.gate && !*M.gate) return;
   extern __shared__ int smem[];
   __shared__ int sm[40];
   __shared__ int s_k;
-  {  // creation ranks are only meaningful inside one update: back to idle
+  if (!ranks_cleared) {  // creation ranks are only meaningful inside one update: back to idle
     const int m = *d_m;
     for (int i = threadIdx.x; i < m; i += blockDim.x) if (isnew[i]) M.l0_tab[pslot[i]].rank = -1;
   }
@@ -740,7 +802,7 @@ int map_reserve(b2lo_map* m, size_t need_l0, size_t need_upd) {
     while (ncap < need_upd) ncap *= 2;
     B2_CUDA(cudaStreamSynchronize(st));
     if ((rc = dmalloc(&m->u_pts, ncap)) || (rc = dmalloc(&m->u_pslot, ncap)) || (rc = dmalloc(&m->u_next, ncap)) || (rc = dmalloc(&m->u_isnew, ncap)) ||
-        (rc = dmalloc(&m->u_newrank, ncap)))
+        (rc = dmalloc(&m->u_newrank, ncap)) || (rc = dmalloc(&m->u_part, ncap / INS_CHUNK + 2)))
       return rc;
     m->a_log2cap = ceil_log2(ncap * 2);
     if ((rc = dmalloc(&m->a_tab, (size_t)1 << m->a_log2cap)) || (rc = dmalloc(&m->a_list, ncap * 4 + 16)) || (rc = dmalloc(&m->a_slots, ncap + 16))) return rc;
@@ -795,7 +857,16 @@ int map_update_dev(b2lo_map* m, const float4* d_world, const int* d_n, size_t n_
   int* pord = m->a_list + 2 * m->upd_cap; int* poff = m->a_list + 3 * m->upd_cap;
   k_ins_probe<<<gm, 256, 0, st>>>(d, d_world, d_n, us, m->u_pslot, m->u_next, m->a_tab, m->a_log2cap, m->a_slots);
   k_ins_apply<<<gm, 256, 0, st>>>(d, d_world, d_n, m->u_pslot, m->u_next, m->u_isnew, m->u_pts, rehash);
-  k_ins_scan<<<1, 1024, 0, st>>>(d, d_n, m->u_isnew, m->u_pslot, m->u_newrank, us);
+  const bool bulk = n_cap > BULK_UPD && !gate;
+  if (bulk) {
+    int gc = (int)((n_cap + INS_CHUNK - 1) / INS_CHUNK); if (gc > 4 * ctx->sm_count) gc = 4 * ctx->sm_count;
+    k_ins_scan_part<<<gc, 1024, 0, st>>>(d_n, m->u_isnew, m->u_part);
+    k_ins_scan_top<<<1, 1024, 0, st>>>(d, d_n, m->u_part, us);
+    k_ins_scan_apply<<<gc, 1024, 0, st>>>(d, d_n, m->u_isnew, m->u_pslot, m->u_newrank, m->u_part);
+    ctx->launches += 2;
+  } else {
+    k_ins_scan<<<1, 1024, 0, st>>>(d, d_n, m->u_isnew, m->u_pslot, m->u_newrank, us);
+  }
   k_ins_place<<<gw, 256, 0, st>>>(d, d_n, us, m->u_pslot, m->u_isnew, m->u_newrank, m->u_pts);
   ctx->launches += 4;
   int purge = 0;
@@ -811,7 +882,8 @@ int map_update_dev(b2lo_map* m, const float4* d_world, const int* d_n, size_t n_
     k_surfel<<<gw, 256, 0, st>>>(d, m->a_tab, m->a_slots, us, plist, pfirst);
     ctx->launches += 1;
   }
-  k_upd_close<<<1, 1024, SIM_SMEM_BYTES, st>>>(d, us, plist, pfirst, pord, poff, m->p_seq, m->p_aux, purge, d_n, m->u_pslot, m->u_isnew);
+  if (bulk) { k_rank_clear<<<gm, 256, 0, st>>>(d, d_n, m->u_pslot, m->u_isnew); ctx->launches++; }
+  k_upd_close<<<1, 1024, SIM_SMEM_BYTES, st>>>(d, us, plist, pfirst, pord, poff, m->p_seq, m->p_aux, purge, d_n, m->u_pslot, m->u_isnew, bulk ? 1 : 0);
   prof_end(ctx);
   ctx->launches += 1;
   B2_CUDA(cudaGetLastError());
@@ -860,7 +932,7 @@ extern "C" int b2lo_map_destroy(b2lo_map* m) {
   MapDev& d = m->d;
   void* ptrs[] = {d.l0_cent, d.l0_key, d.l0_slot, d.l0_tab, d.l1_tab, d.l1_meta, d.ctr,
                   m->u_pts, m->u_pslot, m->u_next, m->u_isnew, m->u_newrank, m->a_tab, m->a_list, m->a_slots, m->c_flag, m->c_blkcnt,
-                  m->c_blkoff, m->c_removed, m->c_aux, m->c_l1work, m->p_seq, m->p_aux, m->u_state};
+                  m->c_blkoff, m->c_removed, m->c_aux, m->c_l1work, m->p_seq, m->p_aux, m->u_state, m->u_part, m->r_tmp, m->r_n};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete m;
   return B2LO_OK;
@@ -1014,9 +1086,16 @@ extern "C" int b2lo_map_transform_rehash(b2lo_map* m, const float T16[16]) {
   cudaStream_t st = ctx->stream;
   const size_t n0 = m->n0;
   if (n0 == 0) return B2LO_S_EMPTY;
-  float4* tmp = nullptr; int* d_n = nullptr;
-  B2_CUDA(cudaMalloc(&tmp, n0 * sizeof(float4)));
-  B2_CUDA(cudaMalloc(&d_n, sizeof(int)));
+  if (n0 > m->r_tmp_cap) {   // kept between calls: pose-graph corrections come in bursts
+    B2_CUDA(cudaStreamSynchronize(st));
+    if (m->r_tmp) cudaFree(m->r_tmp);
+    m->r_tmp = nullptr; m->r_tmp_cap = 0;
+    const size_t cap = n0 + n0 / 8 + 1024;
+    if (cudaMalloc(&m->r_tmp, cap * sizeof(float4)) != cudaSuccess) { set_error("cudaMalloc(rehash scratch, %zu B) failed", cap * sizeof(float4)); return B2LO_E_NOMEM; }
+    m->r_tmp_cap = cap;
+  }
+  if (!m->r_n) B2_CUDA(cudaMalloc(&m->r_n, sizeof(int)));
+  float4* tmp = m->r_tmp; int* d_n = m->r_n;
   Rt12 T;
   for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) T.R[i * 3 + j] = T16[i * 4 + j]; T.t[i] = T16[i * 4 + 3]; }
   k_xform_l0<<<grid_for(n0, 256), 256, 0, st>>>(m->d, (int)n0, T, tmp, d_n);
@@ -1027,6 +1106,5 @@ extern "C" int b2lo_map_transform_rehash(b2lo_map* m, const float T16[16]) {
     rc = map_update_dev(m, tmp, d_n, n0, zero, 0.0f, 1);
   }
   cudaStreamSynchronize(st);
-  cudaFree(tmp); cudaFree(d_n);
   return rc;
 }

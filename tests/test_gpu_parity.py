@@ -625,3 +625,11 @@ def test_large_map_matches_oracle(orc, b2):
     assert np.array_equal(o1["keys"][oi], g1["keys"][gi]) and np.array_equal(o1["has_surfel"][oi], g1["has_surfel"][gi])
     hs = o1["has_surfel"][oi] > 0
     assert np.array_equal(bits(o1["normal"][oi][hs]), bits(g1["normal"][gi][hs])) and np.array_equal(bits(o1["centroid"][oi][hs]), bits(g1["centroid"][gi][hs]))
+    # bulk rebuild of the big map (ApplyTransformAndRehash + RecomputeAllSurfels, VoxelMap.cpp:264-366): merged collisions, order, surfels
+    from lidar_odometry_b200 import synth
+    T = T32(synth.pose_matrix(0.31, -0.22, 0.05, 0.02, 0.003, -0.004))
+    omap.transform_rehash(T); gmap.ApplyTransformAndRehash(T)
+    assert gmap.GetVoxelCount() == omap.counts()[0] and gmap.GetL1VoxelCount() == omap.counts()[1] and gmap.GetSurfelCount() == omap.counts()[2]
+    ok_, oc, on = omap.export_l0()
+    gc, gk, gn = gmap.export_l0()
+    assert np.array_equal(ok_, gk) and np.array_equal(on, gn) and np.array_equal(bits(oc), bits(gc))
