@@ -163,6 +163,18 @@ int b2lo_icp_shard_accumulate(b2lo_map* map, const b2lo_icp_cfg* cfg, long long 
 int b2lo_icp_shard_finish(b2lo_map* map, const b2lo_icp_cfg* cfg, const double* acc28_dev, float T_out[16], int* done /*0 go on, 1 finished, 2 failed*/,
                           b2lo_icp_stats* stats /*nullable*/);
 
+/* ---- loop-closure ICP ----------------------------------------------------------------------
+ * optimize_loop (IterativeClosestPointOptimizer.cpp:40-251; correspondences :465-585): registers the CURRENT keyframe's local
+ * feature cloud (world pose T_curr) against a MATCHED keyframe's local feature cloud (world pose T_matched): exact 5-NN in the
+ * matched cloud moved to world coordinates, plane through the 5 neighbours, no distance gate, residual anchored at the nearest
+ * neighbour, PKO-weighted Gauss-Newton for at most 100 iterations, then the 1-NN (< 1 m) inlier ratio.
+ * Returns B2LO_OK when the reference returns true (converged AND inlier ratio >= 0.5): T_rel = T_curr^-1 * optimised pose.
+ * B2LO_S_INSUFFICIENT otherwise (T_rel is still written once the loop converged, as the reference does; identity before that).
+ * The reference runs this on a background thread next to optimize(): give it its own b2lo_ctx (own stream and scratch). */
+int b2lo_icp_optimize_loop(b2lo_ctx* ctx, const float* curr_xyz, size_t m_curr, size_t curr_stride_floats, const float T_curr[16],
+                           const float* matched_xyz, size_t m_matched, size_t matched_stride_floats, const float T_matched[16],
+                           const b2lo_icp_cfg* cfg, float T_rel[16], float* inlier_ratio /*nullable*/, b2lo_icp_stats* stats /*nullable*/);
+
 /* ---- pose algebra used at the boundary (util::SE3 / SO3, MathUtils.h:57-168) --------------------- */
 void b2lo_se3_mul(const float A16[16], const float B16[16], float C16[16]);  /* SE3::operator*, re-projects the rotation */
 void b2lo_se3_inv(const float A16[16], float C16[16]);                       /* SE3::Inverse */

@@ -443,6 +443,35 @@ class IterativeClosestPointOptimizer:
             frame.set_pose(T)
         return ok, T
 
+    def optimize_loop(self, curr_keyframe, matched_keyframe, ctx=None):
+        """Loop-closure ICP between two keyframes (optimize_loop, ICP.cpp:40-251).  Each keyframe is ``(local_feature_cloud, pose)``
+        or an object with ``get_feature_cloud()`` / ``get_pose()`` like database::LidarFrame.  Returns
+        ``(success, optimized_relative_transform, inlier_ratio)`` with the reference's meaning: relative = curr_pose^-1 * optimised
+        curr pose, success only if the loop converged within 100 iterations and at least half of the points are inliers."""
+        def parts(kf):
+            if hasattr(kf, "get_feature_cloud"):
+                return kf.get_feature_cloud(), kf.get_pose()
+            return kf
+        cc, Tc = parts(curr_keyframe)
+        mc, Tm = parts(matched_keyframe)
+        ctx = ctx or default_context()
+        Tc, Tm = _f32(Tc).reshape(16), _f32(Tm).reshape(16)
+        Trel = np.zeros(16, np.float32)
+        ratio = C.c_float(0.0)
+        st = IcpStats()
+        ame = self.m_adaptive_estimator.get_config() if self.m_adaptive_estimator else None
+        cfg = _icp_cfg(self.m_config, ame)
+        self.m_last_stats = OptimizationStats()
+        if cc is None or mc is None or len(cc) == 0 or len(mc) == 0:
+            return False, np.eye(4, dtype=np.float32), 0.0
+        a, n, sf = _cloud(cc)
+        b, m, sg = _cloud(mc)
+        rc = check(capi.lib().b2lo_icp_optimize_loop(ctx.h, _p(a), n, sf, _p(Tc), _p(b), m, sg, _p(Tm), C.byref(cfg), _p(Trel), C.byref(ratio), C.byref(st)))
+        self.m_last_stats = OptimizationStats(num_iterations=st.num_iterations, num_correspondences=st.num_correspondences,
+                                              initial_cost=st.initial_cost, final_cost=st.final_cost, converged=bool(st.converged),
+                                              optimization_time_ms=st.device_ms, iterations=_trace(st))
+        return rc == B2LO_OK, Trel.reshape(4, 4).copy(), float(ratio.value)
+
     # parity taps -----------------------------------------------------------------------------------------------
     def find_correspondences(self, voxel_map: VoxelMap, cloud, pose):
         """Per-query view of find_correspondences (ICP.cpp:587-645) at a fixed pose."""

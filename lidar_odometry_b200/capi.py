@@ -118,6 +118,7 @@ SIGNATURES = {
     "b2lo_icp_correspondences": (_i, [_vp, _vp, _sz, _sz, _vp, _d, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_sz)]),
     "b2lo_icp_correspondences_knn": (_i, [_vp, _vp, _sz, _sz, _vp, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_sz), C.POINTER(_sz)]),
     "b2lo_icp_optimize": (_i, [_vp, _vp, _sz, _sz, _vp, C.POINTER(IcpCfg), _vp, C.POINTER(IcpStats)]),
+    "b2lo_icp_optimize_loop": (_i, [_vp, _vp, _sz, _sz, _vp, _vp, _sz, _sz, _vp, C.POINTER(IcpCfg), _vp, C.POINTER(C.c_float), C.POINTER(IcpStats)]),
     "b2lo_icp_optimize_features": (_i, [_vp, _vp, C.POINTER(IcpCfg), _vp, C.POINTER(IcpStats)]),
     "b2lo_icp_shard_begin": (_i, [_vp, _vp, _sz, _sz, _vp, C.POINTER(IcpCfg)]),
     "b2lo_icp_shard_corr": (_i, [_vp, C.POINTER(IcpCfg), _vp]),

@@ -295,7 +295,7 @@ extern "C" int b2lo_ctx_destroy(b2lo_ctx* ctx) {
                    ctx->f_slot, ctx->f_vid, ctx->f_segstart, ctx->f_segcnt, ctx->f_lead, ctx->f_bucket, ctx->f_ordered, ctx->f_packed, ctx->f_sorted, ctx->i_res, ctx->i_slot,
                    ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff, ctx->i_tilesum, ctx->i_partial, ctx->d_icp, ctx->d_pko, ctx->d_pko_hits, ctx->d_tap_state,
                    ctx->d_tap_key, ctx->d_tap_morton, ctx->d_tap_n, ctx->d_tap_c, ctx->d_mapdev, ctx->k_idx, ctx->k_n, ctx->k_unres, ctx->k_nunres,
-                   ctx->k_plane};
+                   ctx->k_plane, ctx->l_cnt};
   for (void* p : dptrs) if (p) cudaFree(p);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->h_icp) cudaFreeHost(ctx->h_icp);

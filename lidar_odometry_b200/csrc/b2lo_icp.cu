@@ -1365,3 +1365,212 @@ extern "C" int b2lo_icp_shard_finish(b2lo_map* map, const b2lo_icp_cfg* cfg, con
   }
   return B2LO_OK;
 }
+
+// ---- loop-closure ICP: optimize_loop / find_correspondences_loop, ICP.cpp:40-251, 465-585 -------------------------
+// The matched keyframe's cloud (a few thousand voxel-filtered points, moved to world coordinates once) is the kNN target; it is an
+// arbitrary cloud, not the map's one-centroid-per-cell grid, so the exact 5-NN is the warp-per-query scan of the dense target stream
+// (knn_brute_warp: ~5 k x 5 k distance evaluations per iteration, microseconds on this GPU; the reference walks a nanoflann tree).
+// Everything behind the correspondences - residual scale, PKO fit + arg-min, Gauss-Newton, pose update - is the scan-to-map machinery
+// unchanged: the gate kernel below writes the same per-query records (plane normal + anchor point, f64 residual, tile compaction).
+namespace b2 {
+struct LoopPose { float Rm[9], tm[3], Ri[9], ti[3]; };   // matched keyframe pose and its rigid inverse (both f32)
+
+__global__ void k_loop_iota(const int* __restrict__ d_npts, IcpState* st, int* unres, int* n_unres) {
+  if (st->done) return;
+  const int npts = *d_npts;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += gridDim.x * blockDim.x) unres[i] = i;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *n_unres = npts;
+}
+// plane through the 5 neighbours, NO distance gate (:571), anchor = the nearest neighbour taken through T_lw_last (f32 matrix, f64
+// product, :524) and back through the matched pose in f32 (:139-142)
+__global__ void __launch_bounds__(TILE) k_loop_gate(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, IcpState* st, IcpParams prm,
+                                                    LoopPose lp, const int* __restrict__ knn_idx, const int* __restrict__ knn_n, double* res,
+                                                    int* slot_out, int* cidx, int* tilecnt, float4* plane, double* tilesum) {
+  if (st->done) return;
+  __shared__ int sm[40];
+  __shared__ double smd2[16];
+  __shared__ float sR[9], sT[3];
+  if (threadIdx.x < 9) sR[threadIdx.x] = st->R[threadIdx.x];
+  if (threadIdx.x < 3) sT[threadIdx.x] = st->t[threadIdx.x];
+  __syncthreads();
+  const int npts = *d_npts;
+  const int ntiles = (npts + TILE - 1) / TILE;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int i = tile * TILE + threadIdx.x;
+    int ok = 0;
+    double a1 = 0.0, a2 = 0.0;
+    if (i < npts) {
+      float4 p = pts[i];
+      float w[3], n[3] = {0, 0, 0}, c[3] = {0, 0, 0};
+      transform_point(sR, sT, p.x, p.y, p.z, w);
+      Top5 top;
+      top.init();
+      top.n = knn_n[i] < 0 ? 0 : knn_n[i];
+      for (int k = 0; k < top.n; ++k) top.id[k] = knn_idx[i * KNN_K + k];
+      double r = 0.0;
+      const int state = knn_fit(M, top, w, 1.7976931348623157e308, n, c, &r);   // c = plane centroid, replaced by the anchor below
+      ok = (state == 2);
+      if (ok) {
+        const float4 nn0 = M.l0_cent[top.id[0]];
+        const double s0[3] = {(double)nn0.x, (double)nn0.y, (double)nn0.z};
+        double pl[3];
+        for (int a = 0; a < 3; ++a)
+          pl[a] = add3((double)lp.Ri[a * 3] * s0[0], (double)lp.Ri[a * 3 + 1] * s0[1], (double)lp.Ri[a * 3 + 2] * s0[2]) + (double)lp.ti[a];
+        const float pm[3] = {(float)pl[0], (float)pl[1], (float)pl[2]};
+        float Rq[3];
+        mat3_vec(lp.Rm, pm, Rq);
+        c[0] = Rq[0] + lp.tm[0]; c[1] = Rq[1] + lp.tm[1]; c[2] = Rq[2] + lp.tm[2];
+        a1 = r; a2 = r * r;
+      }
+      slot_out[i] = ok ? 0 : -1;
+      res[i] = r;
+      plane[2 * i] = make_float4(n[0], n[1], n[2], c[0]);
+      plane[2 * i + 1] = make_float4(c[1], c[2], 0.0f, 0.0f);
+    }
+    int total;
+    int off = block_excl_scan(ok, &total, sm);
+    if (ok) cidx[tile * TILE + off] = i;
+    block_sum2_t0(a1, a2, smd2);
+    if (threadIdx.x == 0) { tilecnt[tile] = total; tilesum[2 * tile] = a1; tilesum[2 * tile + 1] = a2; }
+  }
+}
+// validation (:214-247): share of the current keyframe's points whose nearest target point is closer than 1 m at the final pose
+__global__ void k_loop_inliers(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, const IcpState* st,
+                               const int* __restrict__ knn_idx, const int* __restrict__ knn_n, int* count) {
+  const int npts = *d_npts;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += gridDim.x * blockDim.x) {
+    if (knn_n[i] < 1) continue;
+    float4 p = pts[i];
+    float w[3];
+    transform_point(st->R, st->t, p.x, p.y, p.z, w);
+    const float4 c = M.l0_cent[knn_idx[i * KNN_K]];
+    if (sqrtf(knn_dist2(w, c.x, c.y, c.z)) < 1.0f) atomicAdd(count, 1);
+  }
+}
+// forces the brute-force search of every query regardless of the done flag (used for the validation pass)
+__global__ void k_loop_iota_all(const int* __restrict__ d_npts, int* unres, int* n_unres) {
+  const int npts = *d_npts;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += gridDim.x * blockDim.x) unres[i] = i;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *n_unres = npts;
+}
+__global__ void k_loop_set_done(IcpState* st, int v) { if (threadIdx.x == 0 && blockIdx.x == 0) st->done = v; }
+
+}  // namespace b2
+
+extern "C" int b2lo_icp_optimize_loop(b2lo_ctx* ctx, const float* curr_xyz, size_t m_curr, size_t curr_stride_floats, const float T_curr[16],
+                                      const float* matched_xyz, size_t m_matched, size_t matched_stride_floats, const float T_matched[16],
+                                      const b2lo_icp_cfg* cfg, float T_rel[16], float* inlier_ratio, b2lo_icp_stats* stats) {
+  if (!ctx || !T_curr || !T_matched || !cfg || !T_rel) return B2LO_E_ARG;
+  if (curr_stride_floats < 3 || matched_stride_floats < 3) return B2LO_E_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaSetDevice(ctx->device);
+  if (inlier_ratio) *inlier_ratio = 0.0f;
+  if (stats) std::memset(stats, 0, sizeof *stats);
+  { Pose id; id.R = mat3_identity(); id.t[0] = id.t[1] = id.t[2] = 0.0f; pose_to_T16(id, T_rel); }
+  if (!curr_xyz || !matched_xyz || m_curr == 0 || m_matched == 0) {   // empty clouds: no correspondences (:474-479) -> break -> false
+    if (stats) stats->status = B2LO_S_INSUFFICIENT;
+    return B2LO_S_INSUFFICIENT;
+  }
+  int rc = ctx_reserve_points(ctx, m_curr > m_matched ? m_curr : m_matched);
+  if (rc) return rc;
+  if ((rc = knn_reserve(ctx))) return rc;
+  if ((rc = icp_build_pko(ctx, cfg))) return rc;
+  if (!ctx->l_cnt) { B2_CUDA(cudaMalloc((void**)&ctx->l_cnt, 4 * sizeof(int))); }
+  cudaStream_t s = ctx->stream;
+  B2_CUDA(cudaEventRecord(ctx->ev0, s));
+  // target: the matched keyframe's cloud in world coordinates (transform_point_cloud, :56-58), kept in d_world
+  if ((rc = ctx_stage_h2d(ctx, matched_xyz, m_matched, matched_stride_floats, 1, ctx->d_world, ctx->l_cnt))) return rc;
+  if ((rc = ctx_transform(ctx, ctx->d_world, ctx->l_cnt, m_matched, T_matched, ctx->d_world))) return rc;
+  if ((rc = ctx_stage_h2d(ctx, curr_xyz, m_curr, curr_stride_floats, 1, ctx->d_query, ctx->d_nquery))) return rc;
+  B2_CUDA(cudaMemsetAsync(ctx->l_cnt + 1, 0, sizeof(int), s));
+  MapDev Ml;
+  std::memset(&Ml, 0, sizeof Ml);
+  Ml.l0_cent = ctx->d_world;
+  Ml.ctr = ctx->l_cnt;
+  LoopPose lp;
+  {
+    Pose pm = pose_from_T16(T_matched);
+    for (int i = 0; i < 9; ++i) lp.Rm[i] = pm.R.m[i];
+    for (int i = 0; i < 3; ++i) lp.tm[i] = pm.t[i];
+    Mat3 Rt = mat3_t(pm.R);
+    float rt[3];
+    mat3_vec(Rt.m, pm.t, rt);
+    for (int i = 0; i < 9; ++i) lp.Ri[i] = Rt.m[i];
+    for (int i = 0; i < 3; ++i) lp.ti[i] = -rt[i];
+  }
+  IcpParams prm;
+  prm.max_iterations = 100;   // :79
+  prm.min_corr = cfg->min_correspondence_points; prm.use_robust = cfg->use_robust_loss;
+  prm.loss_type = cfg->loss_type; prm.use_pko = cfg->use_adaptive_m_estimator; prm.use_surfel = 0;
+  prm.tol_t = cfg->translation_tolerance; prm.tol_r = cfg->rotation_tolerance; prm.max_dist = 1.7976931348623157e308;
+  prm.robust_delta = cfg->robust_loss_delta;
+  prm.ctile = TILE;
+  if ((rc = sp_begin_write(ctx))) return rc;
+  for (int i = 0; i < 16; ++i) ctx->h_sp->T_init[i] = T_curr[i];
+  if ((rc = sp_upload(ctx, offsetof(ScanParams, T_init), sizeof(float) * 16))) return rc;
+  k_icp_begin<<<1, 32, 0, s>>>(ctx->d_icp, ctx->d_sp);
+  ctx->launches++;
+  const int ntiles = (int)((m_curr + TILE - 1) / TILE);
+  const int grid = ntiles > ctx->i_max_blocks ? ctx->i_max_blocks : ntiles;
+  const int gb = ctx->sm_count * 2;
+  double* gmm = ctx->i_partial + (size_t)ctx->i_max_blocks * 28;
+  double* js = gmm + 120;
+  unsigned int* tk = reinterpret_cast<unsigned int*>(js + 132);
+  const int CHUNK = 8;   // iterations enqueued between two looks at the done flag (converged iterations turn into no-ops)
+  for (int it0 = 0; it0 < 100; it0 += CHUNK) {
+    for (int it = it0; it < it0 + CHUNK && it < 100; ++it) {
+      k_loop_iota<<<grid, TILE, 0, s>>>(ctx->d_nquery, ctx->d_icp, ctx->k_unres, ctx->k_nunres);
+      k_knn_brute<<<gb, 256, 0, s>>>(Ml, ctx->d_query, ctx->d_icp, ctx->k_idx, ctx->k_n, ctx->k_unres, ctx->k_nunres);
+      k_loop_gate<<<grid, TILE, 0, s>>>(Ml, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, lp, ctx->k_idx, ctx->k_n, ctx->i_res, ctx->i_slot, ctx->i_cidx,
+                                        ctx->i_blkcnt, ctx->k_plane, ctx->i_tilesum);
+      k_icp_pko1<<<1, PKO_THREADS, 0, s>>>(ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff, ctx->d_pko,
+                                           ctx->d_pko_hits, gmm, nullptr, 0, 0.0, ctx->i_tilesum);
+      if (cfg->use_adaptive_m_estimator) k_icp_pko2<<<cfg->num_alpha_segments, 128, 0, s>>>(ctx->d_icp, prm, ctx->d_pko, gmm, js, tk);
+      k_icp_gn<false><<<grid, TILE, 0, s>>>(Ml, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->k_plane, ctx->i_partial, nullptr);
+      ctx->launches += cfg->use_adaptive_m_estimator ? 6 : 5;
+    }
+    B2_CUDA(cudaMemcpyAsync(ctx->h_icp, ctx->d_icp, offsetof(IcpState, trace), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    ctx->d2h_bytes += offsetof(IcpState, trace);
+    if (ctx->h_icp->done) break;
+  }
+  // success = converged within 100 iterations (:196-201); insufficient correspondences just break out of the loop (:86-89)
+  const bool converged = ctx->h_icp->done == 1 && ctx->h_icp->converged;
+  int inl = 0;
+  if (converged) {
+    k_loop_iota_all<<<grid, TILE, 0, s>>>(ctx->d_nquery, ctx->k_unres, ctx->k_nunres);
+    k_loop_set_done<<<1, 32, 0, s>>>(ctx->d_icp, 0);   // the search kernel is gated by the flag
+    k_knn_brute<<<gb, 256, 0, s>>>(Ml, ctx->d_query, ctx->d_icp, ctx->k_idx, ctx->k_n, ctx->k_unres, ctx->k_nunres);
+    k_loop_set_done<<<1, 32, 0, s>>>(ctx->d_icp, 1);
+    k_loop_inliers<<<grid, TILE, 0, s>>>(Ml, ctx->d_query, ctx->d_nquery, ctx->d_icp, ctx->k_idx, ctx->k_n, ctx->l_cnt + 1);
+    ctx->launches += 5;
+    B2_CUDA(cudaMemcpyAsync(ctx->h_counts + 40, ctx->l_cnt + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+  }
+  B2_CUDA(cudaMemsetAsync(ctx->k_nunres, 0, sizeof(int), s));   // the scan-to-map KDTree path expects an empty queue
+  B2_CUDA(cudaEventRecord(ctx->ev1, s));
+  B2_CUDA(cudaMemcpyAsync(ctx->h_icp, ctx->d_icp, sizeof(IcpState), cudaMemcpyDeviceToHost, s));
+  B2_CUDA(cudaStreamSynchronize(s));
+  B2_CUDA(cudaGetLastError());
+  ctx->d2h_bytes += sizeof(IcpState) + sizeof(int);
+  if (converged) inl = ctx->h_counts[40];
+  const IcpState* h = ctx->h_icp;
+  float ms = 0.0f;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  const float ratio = converged ? (float)inl / (float)m_curr : 0.0f;
+  const bool success = converged && !(ratio < 0.5f);   // :249-251
+  if (stats) {
+    stats->status = success ? B2LO_OK : B2LO_S_INSUFFICIENT; stats->num_iterations = h->num_iterations; stats->num_correspondences = h->n_corr;
+    stats->converged = h->converged; stats->initial_cost = h->initial_cost; stats->final_cost = h->final_cost; stats->device_ms = ms;
+    std::memcpy(stats->it, h->trace, sizeof(stats->it));
+  }
+  if (inlier_ratio) *inlier_ratio = ratio;
+  if (converged) {   // optimized_relative_transform = curr_pose^-1 * optimized_curr_pose (:198), set as soon as the loop converges
+    Pose opt;
+    for (int i = 0; i < 9; ++i) opt.R.m[i] = h->R[i];
+    for (int i = 0; i < 3; ++i) opt.t[i] = h->t[i];
+    Pose cur = pose_from_T16(T_curr);
+    Pose inv = pose_inv(cur);
+    pose_to_T16(pose_mul(inv, opt), T_rel);
+  }
+  return success ? B2LO_OK : B2LO_S_INSUFFICIENT;
+}

@@ -125,6 +125,7 @@ struct b2lo_ctx {
   b2lo_icp_cfg pko_cfg_built{}; bool pko_built = false;
   // KDTree-mode scratch (b2lo_knn.cuh): 5 neighbour ids + found count per query, unresolved queue, fitted planes
   int* k_idx = nullptr; int* k_n = nullptr; int* k_unres = nullptr; int* k_nunres = nullptr; float4* k_plane = nullptr; size_t k_cap = 0;
+  int* l_cnt = nullptr;            // loop-closure ICP: [0] size of the matched keyframe's cloud, [1] inlier count
   // parity taps scratch
   int* d_tap_state = nullptr; int* d_tap_key = nullptr; unsigned long long* d_tap_morton = nullptr; float* d_tap_n = nullptr; float* d_tap_c = nullptr;
   int* h_counts = nullptr;         // pinned small readback area (64 ints)

@@ -79,6 +79,10 @@ size_t orc_kdtree_correspondences(const float* map_xyz, size_t nmap, const float
 void orc_knn(const float* map_xyz, size_t nmap, const float* q_xyz, size_t m, int k, int* idx, float* d2, int* found);
 
 /* PKO */
+/* optimize_loop (ICP.cpp:40-251): returns 1 on success (converged within 100 iterations and inlier ratio >= 0.5) */
+int orc_icp_optimize_loop(const float* curr_xyz, size_t m_curr, const float* T_curr16, const float* matched_xyz, size_t m_matched,
+                          const float* T_matched16, const orc_icp_cfg* cfg, float* T_rel16, float* inlier_ratio, int* iterations,
+                          orc_iter_trace* trace, int trace_cap, int* n_trace);
 double orc_pko_scale(const double* residuals, size_t n, const orc_icp_cfg* cfg, double* sample /*<=gmm_sample_size*/, int* n_sample,
                      double* means, double* vars, double* weights, int* em_iters, double* js /*num_alpha_segments+1*/);
 void orc_shuffle_head(int n, int head, int* out);  /* first `head` entries of std::shuffle(iota(n), mt19937(42)) */

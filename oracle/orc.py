@@ -229,6 +229,22 @@ def icp_optimize_kdtree(map_xyz, local_xyz, T_init, cfg=None, trace_cap=64):
     return bool(ok), Tout.reshape(4, 4), _trace_to_dicts(tr, nt.value)
 
 
+def icp_optimize_loop(curr_xyz, T_curr, matched_xyz, T_matched, cfg=None, trace_cap=128):
+    """optimize_loop (ICP.cpp:40-251) -> (success, T_relative, inlier_ratio, iterations, trace)."""
+    cfg = cfg or default_icp_cfg()
+    cur = f32(curr_xyz).reshape(-1, 3)
+    mat = f32(matched_xyz).reshape(-1, 3)
+    Tc, Tm = f32(T_curr).reshape(16), f32(T_matched).reshape(16)
+    Trel = np.zeros(16, np.float32)
+    ratio, iters, nt = C.c_float(0), C.c_int(0), C.c_int(0)
+    tr = (IterTrace * trace_cap)()
+    L = lib()
+    L.orc_icp_optimize_loop.restype = C.c_int
+    ok = L.orc_icp_optimize_loop(_p(cur), C.c_size_t(cur.shape[0]), _p(Tc), _p(mat), C.c_size_t(mat.shape[0]), _p(Tm), C.byref(cfg), _p(Trel),
+                                 C.byref(ratio), C.byref(iters), tr, trace_cap, C.byref(nt))
+    return bool(ok), Trel.reshape(4, 4), float(ratio.value), int(iters.value), _trace_to_dicts(tr, nt.value)
+
+
 def kdtree_correspondences(map_xyz, local_xyz, T, max_dist=1.0):
     mp = f32(map_xyz).reshape(-1, 3)
     local = f32(local_xyz).reshape(-1, 3)

@@ -180,6 +180,25 @@ int orc_icp_optimize_kdtree(const float* map_xyz, size_t nmap, const float* loca
   return ok ? 1 : 0;
 }
 
+// optimize_loop (ICP.cpp:40-251): loop-closure ICP of the current keyframe against a matched keyframe (local feature clouds + world poses)
+int orc_icp_optimize_loop(const float* curr_xyz, size_t m_curr, const float* T_curr16, const float* matched_xyz, size_t m_matched,
+                          const float* T_matched16, const orc_icp_cfg* cfg, float* T_rel16, float* inlier_ratio, int* iterations,
+                          orc_iter_trace* trace, int trace_cap, int* n_trace) {
+  auto ame = std::make_shared<AdaptiveMEstimator>(to_pko(cfg));
+  ICPOptimizer icp(to_icp(cfg), ame);
+  icp.keep_trace = trace != nullptr;
+  SE3f rel;
+  float ratio = 0.0f;
+  int iters = 0;
+  bool ok = icp.optimize_loop(reinterpret_cast<const P3*>(curr_xyz), m_curr, raw_se3(T_curr16), reinterpret_cast<const P3*>(matched_xyz), m_matched,
+                              raw_se3(T_matched16), rel, ratio, &iters);
+  if (T_rel16) rel.Matrix(T_rel16);
+  if (inlier_ratio) *inlier_ratio = ratio;
+  if (iterations) *iterations = iters;
+  if (trace) copy_trace(icp.trace, trace, trace_cap, n_trace);
+  return ok ? 1 : 0;
+}
+
 size_t orc_kdtree_correspondences(const float* map_xyz, size_t nmap, const float* local_xyz, size_t m, const float* T16, double max_dist,
                                   int* knn, int* state, float* normal, float* centroid, double* residual) {
   std::vector<P3> cloud(nmap);

@@ -567,6 +567,57 @@ def test_lookahead_overlap_is_bit_identical(b2, small_kitti, monkeypatch):
     assert odo.graph_stats()["replays"] == 0
 
 
+# ---- loop-closure ICP -----------------------------------------------------------------------------------------
+def test_loop_closure_icp_matches_oracle(orc, b2, small_kitti):
+    """optimize_loop (ICP.cpp:40-251): the current keyframe, displaced from its true pose, is registered against an earlier keyframe's
+    cloud.  Teacher-forced on the oracle's first iteration: same correspondence count, scale, alpha, H/g within 1e-5; free-running:
+    same success flag and iteration count, relative transform within 1e-5 m / 1e-5 rad, inlier ratio equal; plus the failure cases."""
+    scans, poses = small_kitti
+    feats = [orc.voxel_filter(s[:, :3], 8, 0.5)[0] for s in scans[:4]]
+    icp = b2.IterativeClosestPointOptimizer(b2.ICPConfig(), b2.AdaptiveMEstimator())
+    ctx = b2.Context(0)     # the reference runs loop closure on its own thread: own context
+    cases = [(2, 0, [0.15, -0.10, 0.02], 0.004), (3, 1, [-0.2, 0.12, -0.03], -0.006), (1, 0, [0.05, 0.05, 0.0], 0.0)]
+    for ci, mi, dt, yaw in cases:
+        Tc = T32(poses[ci]).copy()
+        c, s_ = np.float32(np.cos(yaw)), np.float32(np.sin(yaw))
+        Rz = np.array([[c, -s_, 0], [s_, c, 0], [0, 0, 1]], np.float32)
+        Tc[:3, :3] = Rz @ Tc[:3, :3]
+        Tc[:3, 3] += np.float32(dt)
+        Tm = T32(poses[mi])
+        ok_o, Trel_o, ratio_o, iters_o, tr_o = orc.icp_optimize_loop(feats[ci], Tc, feats[mi], Tm)
+        ok_g, Trel_g, ratio_g = icp.optimize_loop((feats[ci], Tc), (feats[mi], Tm), ctx=ctx)
+        st = icp.get_last_stats()
+        tr_g = st.iterations
+        assert ok_o and ok_g, (ci, mi)
+        a, b = tr_o[0], tr_g[0]
+        assert a["n_corr"] == b["n_corr"] and abs(a["scale"] - b["scale"]) <= 1e-12 * abs(a["scale"]) and a["delta"] == b["delta"]
+        assert _rel(b["H"], a["H64"]) < 1e-5 and _rel(b["g"], a["g64"]) < 1e-5
+        assert st.num_iterations == iters_o
+        assert np.abs(Trel_g[:3, 3] - Trel_o[:3, 3]).max() < 1e-5 and _rot_angle(Trel_g[:3, :3], Trel_o[:3, :3]) < 1e-5
+        assert ratio_g == ratio_o
+        # the registration undoes the displacement: curr_pose * relative ~ true pose
+        fixed = Tc.astype(np.float64) @ Trel_g.astype(np.float64)
+        assert np.abs(fixed[:3, 3] - poses[ci][:3, 3]).max() < 0.05
+    # too far apart: the loop never converges onto enough inliers -> false on both sides
+    Tc = T32(poses[2]).copy(); Tc[:3, 3] += np.float32([40.0, 25.0, 0.0])
+    ok_o, _, ratio_o, _, _ = orc.icp_optimize_loop(feats[2], Tc, feats[0], T32(poses[0]))
+    ok_g, _, ratio_g = icp.optimize_loop((feats[2], Tc), (feats[0], T32(poses[0])), ctx=ctx)
+    assert ok_o == ok_g and not ok_g
+    # fewer than 5 target points: no plane can be fitted -> insufficient correspondences -> false
+    ok_g, Trel_g, ratio_g = icp.optimize_loop((feats[2], T32(poses[2])), (feats[0][:4], T32(poses[0])), ctx=ctx)
+    ok_o, _, _, _, _ = orc.icp_optimize_loop(feats[2], T32(poses[2]), feats[0][:4], T32(poses[0]))
+    assert not ok_g and not ok_o and ratio_g == 0.0
+    ok_g, _, _ = icp.optimize_loop((np.zeros((0, 3), np.float32), np.eye(4)), (feats[0], T32(poses[0])), ctx=ctx)
+    assert not ok_g
+    # the scan-to-map KDTree path on the same context still works afterwards (shared kNN scratch)
+    gmap = b2.VoxelMap(0.5, ctx)
+    gmap.SetComputeSurfels(False)
+    gmap.UpdateVoxelMap(orc.transform(feats[0], T32(poses[0])) if hasattr(orc, "transform") else (feats[0] @ T32(poses[0])[:3, :3].T + T32(poses[0])[:3, 3]), [0, 0, 0], 120.0)
+    gmap.RebuildKdTree()
+    ok, _ = b2.IterativeClosestPointOptimizer(b2.ICPConfig(use_surfel_correspondence=False), b2.AdaptiveMEstimator()).optimize(gmap, feats[1], T32(poses[1]))
+    assert ok
+
+
 # ---- BASELINE.json sizes ------------------------------------------------------------------------------------------------
 def test_full_size_kitti_scans(orc, b2):
     """configs[1] at full size (64 x 1900 rays, ~120 k points per scan): K1 bit-exact on whole scans, and the free-running
