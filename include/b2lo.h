@@ -109,6 +109,30 @@ int b2lo_filter(b2lo_ctx* ctx, const float* xyz, size_t n, size_t stride_floats,
 int b2lo_filter_dev(b2lo_ctx* ctx, const float* xyz_dev, size_t n, size_t stride_floats, int stride, float voxel_size);
 int b2lo_ctx_features(b2lo_ctx* ctx, float* out_xyz, size_t cap, size_t* m); /* copy the feature buffer to the host */
 
+/* ---- scan ingest: K1 reads the dataset's own records in place ------------------------------
+ * A scan file image is a stream of fixed-size records holding three IEEE f32 coordinates at fixed byte offsets:
+ *   KITTI .bin (load_kitti_binary, src/util/PointCloudUtils.cpp:19-65): 16-byte records x,y,z,intensity -> {16, 0, 4, 8};
+ *   binary PLY (PLYPlayer::load_ply_point_cloud, app/player/ply_player.cpp:267-343): the vertex record described by the header,
+ *   x/y/z copied bytewise from their property offsets whatever their declared type, no byte swap (as the reference does).
+ * The device reads only every stride-th record (one or two 32 B sectors each); no host repack into util::PointCloud, no staging copy
+ * for page-locked or device-resident file images.  Offsets need no alignment (e.g. 15-byte xyz+rgb vertices). */
+typedef struct { uint32_t record_bytes, off_x, off_y, off_z; } b2lo_record_fmt;
+void b2lo_kitti_record_fmt(b2lo_record_fmt* fmt);
+/* PLYPlayer::parse_ply_header (ply_player.cpp:373-461) on a file image: element/property bookkeeping exactly as the reference does it
+ * (every `property` line of every element adds its size to the vertex record; `list` and unknown types count 4 bytes; exact-match
+ * `ply` / `end_header` lines).  Outputs: the record format, the header's vertex count, the byte offset of the first record and
+ * whether the body is binary.  *n_records = min(vertex_count, whole records present) for binary bodies (a truncated last record is
+ * dropped, :321-324), vertex_count for ASCII.  Returns B2LO_E_ARG for the files the reference rejects (no x/y/z, no vertices, no header). */
+int b2lo_ply_parse_header(const void* file, size_t len, b2lo_record_fmt* fmt, size_t* vertex_count, size_t* data_offset, int* is_binary,
+                          size_t* n_records);
+/* ASCII PLY body (ply_player.cpp:344-364) on the host: one vertex per line, every whitespace-separated float of the line is read; lines
+ * with fewer values than header properties are skipped.  out_xyz: capacity >= vertex_count points; *n receives the points kept. */
+int b2lo_ply_read_ascii(const void* file, size_t len, float* out_xyz, size_t cap, size_t* n);
+/* FastVoxelFilter::filter over a record stream (host image / device-resident image); results as b2lo_filter / b2lo_filter_dev */
+int b2lo_filter_records(b2lo_ctx* ctx, const void* records, size_t n_records, const b2lo_record_fmt* fmt, int stride, float voxel_size,
+                        float* out_xyz, uint64_t* out_keys /*nullable*/, size_t* m);
+int b2lo_filter_records_dev(b2lo_ctx* ctx, const void* records_dev, size_t n_records, const b2lo_record_fmt* fmt, int stride, float voxel_size);
+
 /* ---- VoxelMap ------------------------------------------------------------------------------------ */
 int b2lo_map_create(b2lo_ctx* ctx, float voxel_size, int hierarchy_factor, float planarity_threshold, int compute_surfels,
                     size_t l0_capacity_hint, b2lo_map** out);                         /* VoxelMap(), Set* (VoxelMap.h:195-209) */
@@ -218,6 +242,10 @@ int b2lo_odom_process_dev(b2lo_odom* od, const float* xyz_dev, size_t n, size_t 
  * must be page-locked and mapped (cudaMallocHost / cudaHostRegister; K1 reads it in place) - for pageable memory the announcement is
  * ignored and B2LO_S_EMPTY is returned.  A following call with another buffer / size simply runs its own K1. */
 int b2lo_odom_lookahead(b2lo_odom* od, const float* xyz_next, size_t n, size_t stride_floats, int on_device);
+/* Record-stream input for the per-scan driver: after this call b2lo_odom_process / _process_dev / _lookahead take `xyz` as the
+ * address of the first RECORD of a file image in the given format and `n` as the record count (stride_floats is ignored; pass 3).
+ * fmt = NULL returns to float-stride clouds.  Takes effect with the next scan. */
+int b2lo_odom_set_record_fmt(b2lo_odom* od, const b2lo_record_fmt* fmt);
 
 #ifdef __cplusplus
 }

@@ -20,10 +20,10 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import capi
-from .capi import B2LO_OK, B2LO_S_EMPTY, B2LO_S_INSUFFICIENT, IcpCfg, IcpStats, OdomCfg, OdomResult, check
+from .capi import B2LO_OK, B2LO_S_EMPTY, B2LO_S_INSUFFICIENT, IcpCfg, IcpStats, OdomCfg, OdomResult, RecordFmt, check
 
 __all__ = ["PointShardedICP", "Context", "default_context", "FastVoxelFilter", "FastVoxelGrid", "VoxelMap", "ICPConfig", "AdaptiveMEstimatorConfig",
-           "AdaptiveMEstimator", "OptimizationStats", "IterativeClosestPointOptimizer", "Odometry", "SE3"]
+           "AdaptiveMEstimator", "OptimizationStats", "IterativeClosestPointOptimizer", "Odometry", "SE3", "RecordFormat", "kitti_record_format", "parse_ply_header", "load_ply_point_cloud", "load_kitti_binary"]
 
 
 def _f32(a):
@@ -40,6 +40,70 @@ def _cloud(a):
     if a.ndim != 2 or a.shape[1] < 3:
         raise ValueError("point cloud must be (N, >=3) float32")
     return a, a.shape[0], a.shape[1]
+
+
+# ---- scan ingest: dataset records are the K1 input ---------------------------------------------------------------
+@dataclass
+class RecordFormat:
+    """Where the three f32 coordinates sit in a fixed-size record of a scan file image (b2lo_record_fmt)."""
+    record_bytes: int
+    off_x: int
+    off_y: int
+    off_z: int
+
+    def c(self) -> RecordFmt:
+        return RecordFmt(self.record_bytes, self.off_x, self.off_y, self.off_z)
+
+
+def kitti_record_format() -> RecordFormat:
+    """KITTI .bin: x, y, z, intensity float32 (util::load_kitti_binary, src/util/PointCloudUtils.cpp:40-58)."""
+    f = RecordFmt()
+    capi.lib().b2lo_kitti_record_fmt(C.byref(f))
+    return RecordFormat(f.record_bytes, f.off_x, f.off_y, f.off_z)
+
+
+def _bytes(image):
+    """file image (bytes / bytearray / uint8 array) -> contiguous uint8 array (no copy when it already is one)."""
+    if isinstance(image, np.ndarray):
+        a = image if image.dtype == np.uint8 else image.view(np.uint8)
+        return np.ascontiguousarray(a).reshape(-1)
+    return np.frombuffer(image, dtype=np.uint8)
+
+
+def parse_ply_header(image):
+    """PLYPlayer::parse_ply_header (app/player/ply_player.cpp:373-461) on a file image.  Returns a dict
+    (fmt, vertex_count, data_offset, is_binary, n_records) or None for the files the reference rejects."""
+    a = _bytes(image)
+    f, vc, off, isb, nr = RecordFmt(), C.c_size_t(), C.c_size_t(), C.c_int(), C.c_size_t()
+    rc = capi.lib().b2lo_ply_parse_header(_p(a), a.size, C.byref(f), C.byref(vc), C.byref(off), C.byref(isb), C.byref(nr))
+    if rc != B2LO_OK:
+        return None
+    return dict(fmt=RecordFormat(f.record_bytes, f.off_x, f.off_y, f.off_z), vertex_count=vc.value, data_offset=off.value,
+                is_binary=bool(isb.value), n_records=nr.value)
+
+
+def load_ply_point_cloud(image):
+    """PLYPlayer::load_ply_point_cloud (ply_player.cpp:267-371) as a HOST convenience: (N,3) float32, empty when the file is rejected.
+    The hot path does not need it for binary files: hand the body to FastVoxelFilter.filter_records / Odometry.set_record_format."""
+    a = _bytes(image)
+    h = parse_ply_header(a)
+    if h is None:
+        return np.zeros((0, 3), np.float32)
+    if h["is_binary"]:
+        f, n = h["fmt"], h["n_records"]
+        body = a[h["data_offset"]: h["data_offset"] + n * f.record_bytes].reshape(n, f.record_bytes)
+        cols = [np.ascontiguousarray(body[:, o:o + 4]).view(np.float32).reshape(-1) for o in (f.off_x, f.off_y, f.off_z)]
+        return np.stack(cols, axis=1) if n else np.zeros((0, 3), np.float32)
+    out = np.zeros((h["vertex_count"], 3), np.float32)
+    m = C.c_size_t()
+    check(capi.lib().b2lo_ply_read_ascii(_p(a), a.size, _p(out), out.shape[0], C.byref(m)))
+    return out[: m.value].copy()
+
+
+def load_kitti_binary(path):
+    """util::load_kitti_binary: the file image as (N,4) float32 records; every consumer here takes it as it is (stride 4)."""
+    raw = np.fromfile(path, dtype=np.float32)
+    return raw[: (raw.size // 4) * 4].reshape(-1, 4)
 
 
 class Context:
@@ -157,6 +221,27 @@ class FastVoxelFilter:
         keys = np.zeros(ns, np.uint64) if want_keys else None
         m = C.c_size_t()
         check(capi.lib().b2lo_filter(self.ctx.h, _p(a), n, sf, int(stride), C.c_float(self.m_voxel_size), _p(out), _p(keys), C.byref(m)))
+        self._count = m.value
+        self.last_keys = None if keys is None else keys[: m.value].copy()
+        return out[: m.value].copy()
+
+    def filter_records(self, image, fmt: RecordFormat, n_records=None, stride=1, want_keys=False, offset=0):
+        """filter() over a record stream (KITTI .bin image, binary PLY body) read in place by K1 (b2lo_filter_records)."""
+        a = _bytes(image)[offset:]
+        if n_records is None:
+            n_records = a.size // fmt.record_bytes
+        if n_records * fmt.record_bytes > a.size:
+            raise ValueError("record stream shorter than n_records")
+        if n_records == 0:
+            self._count = 0
+            self.last_keys = np.zeros(0, np.uint64)
+            return np.zeros((0, 3), np.float32)
+        ns = (n_records + stride - 1) // stride
+        out = np.zeros((ns, 3), np.float32)
+        keys = np.zeros(ns, np.uint64) if want_keys else None
+        m = C.c_size_t()
+        f = fmt.c()
+        check(capi.lib().b2lo_filter_records(self.ctx.h, _p(a), n_records, C.byref(f), int(stride), C.c_float(self.m_voxel_size), _p(out), _p(keys), C.byref(m)))
         self._count = m.value
         self.last_keys = None if keys is None else keys[: m.value].copy()
         return out[: m.value].copy()
@@ -630,6 +715,32 @@ class Odometry:
                 return False   # _cloud had to copy (dtype / layout): the copy would not outlive this call
             rc = check(capi.lib().b2lo_odom_lookahead(self.h, _p(a), n, sf, 0))
         return rc == B2LO_OK
+
+    def set_record_format(self, fmt: RecordFormat | None):
+        """Scans arrive as byte-record streams from now on (b2lo_odom_set_record_fmt); None returns to float clouds."""
+        self._fmt = fmt
+        if fmt is None:
+            check(capi.lib().b2lo_odom_set_record_fmt(self.h, None))
+        else:
+            f = fmt.c()
+            check(capi.lib().b2lo_odom_set_record_fmt(self.h, C.byref(f)))
+
+    def process_records(self, image, n_records=None, offset=0, lookahead=None):
+        """process() of one file image in the format given to set_record_format (uint8 array / bytes; offset = first record)."""
+        fmt = getattr(self, "_fmt", None)
+        if fmt is None:
+            raise ValueError("set_record_format first")
+        a = _bytes(image)[offset:]
+        if n_records is None:
+            n_records = a.size // fmt.record_bytes
+        if n_records * fmt.record_bytes > a.size:
+            raise ValueError("record stream shorter than n_records")
+        if lookahead is not None:   # (uint8 array, n_records) of the next image; must be page-locked to take effect
+            la, ln = lookahead
+            check(capi.lib().b2lo_odom_lookahead(self.h, _p(la), ln, 3, 0))
+        r = OdomResult()
+        rc = check(capi.lib().b2lo_odom_process(self.h, _p(a), n_records, 3, C.byref(r)))
+        return self._result(rc, r)
 
     def process(self, scan, lookahead=None):
         a, n, sf = _cloud(scan)

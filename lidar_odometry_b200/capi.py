@@ -69,6 +69,10 @@ class OdomResult(C.Structure):  # b2lo_odom_result
     ]
 
 
+class RecordFmt(C.Structure):  # b2lo_record_fmt
+    _fields_ = [("record_bytes", C.c_uint32), ("off_x", C.c_uint32), ("off_y", C.c_uint32), ("off_z", C.c_uint32)]
+
+
 def build(force=False, verbose=False):
     """Compile libb2lo.so for sm_100a with nvcc (cross-compiles without a GPU)."""
     if force:
@@ -101,6 +105,11 @@ SIGNATURES = {
     "b2lo_filter": (_i, [_vp, _vp, _sz, _sz, _i, _f, _vp, _vp, C.POINTER(_sz)]),
     "b2lo_filter_dev": (_i, [_vp, _vp, _sz, _sz, _i, _f]),
     "b2lo_ctx_features": (_i, [_vp, _vp, _sz, C.POINTER(_sz)]),
+    "b2lo_kitti_record_fmt": (None, [C.POINTER(RecordFmt)]),
+    "b2lo_ply_parse_header": (_i, [_vp, _sz, C.POINTER(RecordFmt), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_i), C.POINTER(_sz)]),
+    "b2lo_ply_read_ascii": (_i, [_vp, _sz, _vp, _sz, C.POINTER(_sz)]),
+    "b2lo_filter_records": (_i, [_vp, _vp, _sz, C.POINTER(RecordFmt), _i, _f, _vp, _vp, C.POINTER(_sz)]),
+    "b2lo_filter_records_dev": (_i, [_vp, _vp, _sz, C.POINTER(RecordFmt), _i, _f]),
     "b2lo_map_create": (_i, [_vp, _f, _i, _f, _i, _sz, C.POINTER(_vp)]),
     "b2lo_map_destroy": (_i, [_vp]),
     "b2lo_map_clear": (_i, [_vp]),
@@ -143,6 +152,7 @@ SIGNATURES = {
     "b2lo_odom_process": (_i, [_vp, _vp, _sz, _sz, C.POINTER(OdomResult)]),
     "b2lo_odom_process_dev": (_i, [_vp, _vp, _sz, _sz, C.POINTER(OdomResult)]),
     "b2lo_odom_lookahead": (_i, [_vp, _vp, _sz, _sz, C.c_int]),
+    "b2lo_odom_set_record_fmt": (_i, [_vp, C.POINTER(RecordFmt)]),
 }
 
 

@@ -36,15 +36,29 @@ __device__ __forceinline__ unsigned long long filter_key(float x, float y, float
   return expand21((uint64_t)ix) | (expand21((uint64_t)iy) << 1) | (expand21((uint64_t)iz) << 2);
 }
 
+// memcpy(&f, p, 4) of the reference's PLY reader for any alignment: one aligned 32-bit load when possible, else four byte loads
+__device__ __forceinline__ float load_f32_bytes(const unsigned char* p) {
+  if ((reinterpret_cast<uintptr_t>(p) & 3u) == 0) return *reinterpret_cast<const float*>(p);
+  const unsigned int u = (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16) | ((unsigned)p[3] << 24);
+  return __uint_as_float(u);
+}
+
 __global__ void k_flt_insert(const ScanParams* __restrict__ sp, FEntry* tab, int log2cap,
                              float4* samp, int* slot_of) {
   const float* __restrict__ src = sp->flt_src;
   const int n_samples = sp->flt_ns;
   const size_t sample_stride = (size_t)sp->flt_stride;
   const float inv = sp->flt_inv;
+  const unsigned int rec = sp->flt_rec, ox = sp->flt_off[0], oy = sp->flt_off[1], oz = sp->flt_off[2];
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_samples; j += gridDim.x * blockDim.x) {
-    const float* p = src + (size_t)j * sample_stride;
-    float x = p[0], y = p[1], z = p[2];
+    float x, y, z;
+    if (rec) {   // byte records (PLY vertices, ply_player.cpp:330-337): three 4-byte copies at arbitrary, possibly unaligned offsets
+      const unsigned char* b = reinterpret_cast<const unsigned char*>(src) + (size_t)j * sample_stride;
+      x = load_f32_bytes(b + ox); y = load_f32_bytes(b + oy); z = load_f32_bytes(b + oz);
+    } else {
+      const float* p = src + (size_t)j * sample_stride;
+      x = p[0]; y = p[1]; z = p[2];
+    }
     samp[j] = make_float4(x, y, z, 0.0f);
     int s = -1;
     if (isfinite(x) && isfinite(y) && isfinite(z)) {
@@ -183,7 +197,8 @@ __global__ void k_flt_reduce(const int* __restrict__ d_nvox, const int* __restri
   }
 }
 
-int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sample_stride_floats, float voxel, int set, cudaStream_t on) {
+int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sample_stride_floats, float voxel, int set, cudaStream_t on,
+               const b2lo_record_fmt* fmt) {
   cudaStream_t st = on ? on : ctx->stream;
   if (set == 0) ctx->feat_set = 0;
   if (n_samples == 0) { if (set == 0) ctx->feat_cap_hint = 0; B2_CUDA(cudaMemsetAsync(ctx->nfeat(set), 0, sizeof(int), st)); return B2LO_OK; }
@@ -201,6 +216,8 @@ int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sam
     if ((rc = sp_begin_write(ctx))) return rc;
     ctx->h_sp->flt_src = src_dev; ctx->h_sp->flt_ns = (int)n_samples; ctx->h_sp->flt_stride = sample_stride_floats;
     ctx->h_sp->flt_inv = 1.0f / voxel;  // m_inv_voxel_size (VoxelMap.h:57)
+    ctx->h_sp->flt_rec = fmt ? fmt->record_bytes : 0u;
+    for (int a = 0; a < 3; ++a) ctx->h_sp->flt_off[a] = fmt ? (&fmt->off_x)[a] : 0u;
     if ((rc = sp_upload(ctx, 0, offsetof(ScanParams, T_init)))) return rc;
   }
   B2_CUDA(cudaMemsetAsync(ctx->f_tab, 0xFF, sizeof(FEntry) << log2cap, st));

@@ -57,6 +57,9 @@ struct IcpState {                 // lives in device memory, one per context
 struct DecideArgs { float guess[16]; float last_kf[16]; int ran_icp; int n_keyframes; double kf_dist, kf_rot; };
 struct ScanParams {
   const float* flt_src; unsigned long long flt_stride; int flt_ns; float flt_inv;   // K1
+  // byte-record input (b2lo_record_fmt: PLY vertex records, any layout): flt_rec != 0 -> flt_src is a byte stream, flt_stride the
+  // distance between SAMPLED records in bytes, flt_off the byte offsets of the three IEEE f32 coordinates inside a record
+  unsigned int flt_rec; unsigned int flt_off[3];
   float T_init[16];                                                                   // ICP initial pose
   DecideArgs decide;                                                                  // odometry tail
 };
@@ -174,7 +177,10 @@ int ctx_stage_h2d(b2lo_ctx* ctx, const float* xyz, size_t n, size_t stride_float
 int ctx_transform(b2lo_ctx* ctx, const float4* src, const int* d_n, size_t n_cap, const float T16[16], float4* dst);
 int ctx_transform_dev(b2lo_ctx* ctx, const float4* src, const int* d_n, size_t n_cap, const float* T16_dev, const int* gate, float4* dst);
 int ctx_read_cloud(b2lo_ctx* ctx, const float4* src, const int* d_n, size_t n_cap, float* out_xyz, size_t out_cap, size_t* n_out);
-int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sample_stride_floats, float voxel, int set = 0, cudaStream_t on = nullptr);
+// sample_stride: floats between sampled points, or BYTES between sampled records when fmt != nullptr (byte-record input)
+int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sample_stride, float voxel, int set = 0, cudaStream_t on = nullptr,
+               const b2lo_record_fmt* fmt = nullptr);
+int ctx_stage_records_h2d(b2lo_ctx* ctx, const void* bytes, size_t n_records, const b2lo_record_fmt* fmt, size_t take_every);
 int icp_build_pko(b2lo_ctx* ctx, const b2lo_icp_cfg* cfg);
 int icp_prepare(b2lo_ctx* ctx, const b2lo_icp_cfg* cfg);
 int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_cap, const float* T_init16, const b2lo_icp_cfg* cfg, bool init_pose_on_device);

@@ -33,6 +33,7 @@ struct b2lo_odom {
   const float* pre_src = nullptr; size_t pre_ns = 0, pre_stride = 0; int pre_set = 0;
   long long lookahead_hits = 0;
   bool allow_graph = true;
+  bool has_fmt = false; b2lo_record_fmt fmt{};   // b2lo_odom_set_record_fmt: scans arrive as byte-record streams (KITTI .bin / PLY vertices)
   long long graph_launches = 0, graph_builds = 0, launches_per_graph = 0;
   OdomDev* d_out = nullptr;        // device result block of k_odom_decide
   OdomDev* h_out = nullptr;        // pinned mirror
@@ -212,7 +213,15 @@ static int enqueue_scan(b2lo_odom* od, size_t flt_ns, size_t cap, bool in_graph,
   return rc;
 }
 
-static int steady_scan(b2lo_odom* od, const float* src_dev, size_t ns, size_t sample_stride_floats, b2lo_odom_result* res, double t0) {
+static void sp_set_fmt(ScanParams* sp, const b2lo_record_fmt* f) {
+  sp->flt_rec = f ? f->record_bytes : 0u;
+  for (int a = 0; a < 3; ++a) sp->flt_off[a] = f ? (&f->off_x)[a] : 0u;
+}
+
+// eff: record format of THIS call's source (nullptr: float-stride cloud, e.g. the staged copy of a pageable image); an announced next
+// scan is always read in place and therefore in the odometry's own format
+static int steady_scan(b2lo_odom* od, const float* src_dev, size_t ns, size_t sample_stride_floats, b2lo_odom_result* res, double t0,
+                       const b2lo_record_fmt* eff) {
   b2lo_ctx* ctx = od->ctx;
   b2lo_map* map = od->map;
   cudaStream_t st = ctx->stream;
@@ -236,7 +245,7 @@ static int steady_scan(b2lo_odom* od, const float* src_dev, size_t ns, size_t sa
   if ((rc = icp_prepare(ctx, &od->cfg.icp))) return rc;
   const int mode = want_next ? K1_NEXT : (have_pre ? K1_NONE : K1_SERIAL);
   if (!have_pre && mode != K1_SERIAL) {   // first scan of a pipelined run: this scan's K1 in line, ahead of the replayed sequence
-    if ((rc = filter_run(ctx, src_dev, ns, sample_stride_floats, od->cfg.voxel_size, 0, st))) return rc;
+    if ((rc = filter_run(ctx, src_dev, ns, sample_stride_floats, od->cfg.voxel_size, 0, st, eff))) return rc;
   }
   // the parameter block of this scan
   Pose guess = pose_mul(od->prev_pose, od->velocity);  // Estimator.cpp:154
@@ -246,6 +255,7 @@ static int steady_scan(b2lo_odom* od, const float* src_dev, size_t ns, size_t sa
   const size_t flt_ns = mode == K1_NEXT ? nx_ns : ns;
   sp->flt_src = mode == K1_NEXT ? nx_src : src_dev; sp->flt_ns = (int)flt_ns;
   sp->flt_stride = mode == K1_NEXT ? nx_stride : sample_stride_floats; sp->flt_inv = 1.0f / od->cfg.voxel_size;
+  sp_set_fmt(sp, mode == K1_NEXT ? (od->has_fmt ? &od->fmt : nullptr) : eff);
   pose_to_T16(init, sp->T_init);
   pose_to_T16(guess, sp->decide.guess);
   pose_to_T16(od->last_kf_pose, sp->decide.last_kf);
@@ -314,7 +324,8 @@ static int steady_scan(b2lo_odom* od, const float* src_dev, size_t ns, size_t sa
   return B2LO_OK;
 }
 
-static int process_common(b2lo_odom* od, const float* src_dev, size_t ns, size_t sample_stride_floats, b2lo_odom_result* res) {
+static int process_common(b2lo_odom* od, const float* src_dev, size_t ns, size_t sample_stride_floats, b2lo_odom_result* res,
+                          const b2lo_record_fmt* eff) {
   b2lo_ctx* ctx = od->ctx;
   b2lo_map* map = od->map;
   cudaStream_t st = ctx->stream;
@@ -324,7 +335,7 @@ static int process_common(b2lo_odom* od, const float* src_dev, size_t ns, size_t
   int* hc = ctx->h_counts + 32;
   if (!od->initialized) {  // initialize_first_frame
     od->la_valid = false;   // the first frame never runs beside anything: an announcement made before it is dropped
-    rc = filter_run(ctx, src_dev, ns, sample_stride_floats, od->cfg.voxel_size);
+    rc = filter_run(ctx, src_dev, ns, sample_stride_floats, od->cfg.voxel_size, 0, nullptr, eff);
     if (rc) return rc;
     B2_CUDA(cudaMemcpyAsync(hc, ctx->d_nfeat, sizeof(int), cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
@@ -340,7 +351,7 @@ static int process_common(b2lo_odom* od, const float* src_dev, size_t ns, size_t
     res->keyframe = 1;
     res->icp_status = B2LO_S_EMPTY;
   } else {
-    rc = steady_scan(od, src_dev, ns, sample_stride_floats, res, t0);
+    rc = steady_scan(od, src_dev, ns, sample_stride_floats, res, t0, eff);
     if (rc) return rc;
   }
   pose_to_T16(od->pose, res->pose);
@@ -348,10 +359,11 @@ static int process_common(b2lo_odom* od, const float* src_dev, size_t ns, size_t
   return B2LO_OK;
 }
 
-static int process_timed(b2lo_odom* od, const float* src_dev, size_t ns, size_t sstride, b2lo_odom_result* res, bool ev0_recorded) {
+static int process_timed(b2lo_odom* od, const float* src_dev, size_t ns, size_t sstride, b2lo_odom_result* res, bool ev0_recorded,
+                         const b2lo_record_fmt* eff = nullptr) {
   b2lo_ctx* ctx = od->ctx;
   if (!ev0_recorded) B2_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-  int rc = process_common(od, src_dev, ns, sstride, res);
+  int rc = process_common(od, src_dev, ns, sstride, res, eff);
   if (rc < 0) return rc;
   B2_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
   B2_CUDA(cudaEventSynchronize(ctx->ev1));
@@ -369,6 +381,8 @@ extern "C" int b2lo_odom_process(b2lo_odom* od, const float* xyz, size_t n, size
   cudaSetDevice(ctx->device);
   const size_t S = (size_t)(od->cfg.point_stride < 1 ? 1 : od->cfg.point_stride);
   const size_t ns = (n + S - 1) / S;
+  const b2lo_record_fmt* F = od->has_fmt ? &od->fmt : nullptr;   // record streams: strides below are in bytes
+  const size_t unit = F ? (size_t)F->record_bytes : stride_floats;
   B2_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
   double tg = now_us();
   // Page-locked caller memory (cudaMallocHost / cudaHostRegister / torch pin_memory): DMA the raw scan as it is, asynchronously,
@@ -381,10 +395,10 @@ extern "C" int b2lo_odom_process(b2lo_odom* od, const float* xyz, size_t n, size
     // PCIe; nothing else of the ~1.9 MB scan ever crosses the bus and no staging copy exists
     ctx->h2d_bytes += ns * 32;
     ctx->host_us[0] += now_us() - tg;
-    return process_timed(od, static_cast<const float*>(attr.devicePointer), ns, stride_floats * S, res, true);
+    return process_timed(od, static_cast<const float*>(attr.devicePointer), ns, unit * S, res, true, F);
   }
   if (pinned) {
-    const size_t floats = n * stride_floats;
+    const size_t floats = F ? (n * unit + 3) / 4 : n * stride_floats;
     if (floats > ctx->raw_floats) {
       B2_CUDA(cudaStreamSynchronize(ctx->stream));
       if (ctx->d_raw) cudaFree(ctx->d_raw);
@@ -396,10 +410,10 @@ extern "C" int b2lo_odom_process(b2lo_odom* od, const float* xyz, size_t n, size
     B2_CUDA(cudaMemcpyAsync(ctx->d_raw, xyz, floats * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     ctx->h2d_bytes += floats * sizeof(float);
     ctx->host_us[0] += now_us() - tg;
-    return process_timed(od, ctx->d_raw, ns, stride_floats * S, res, true);
+    return process_timed(od, ctx->d_raw, ns, unit * S, res, true, F);
   }
   // pageable memory: only every S-th point is ever read by the filter (VoxelMap.h:81): gather those into pinned staging, one H2D
-  int rc = ctx_stage_h2d(ctx, xyz, n, stride_floats, S, nullptr, nullptr);
+  int rc = F ? ctx_stage_records_h2d(ctx, xyz, n, F, S) : ctx_stage_h2d(ctx, xyz, n, stride_floats, S, nullptr, nullptr);
   ctx->host_us[0] += now_us() - tg;
   if (rc) return rc;
   return process_timed(od, ctx->d_stage, ns, 3, res, true);
@@ -415,7 +429,8 @@ extern "C" int b2lo_odom_process_dev(b2lo_odom* od, const float* xyz_dev, size_t
   cudaSetDevice(ctx->device);
   const size_t S = (size_t)(od->cfg.point_stride < 1 ? 1 : od->cfg.point_stride);
   const size_t ns = (n + S - 1) / S;
-  return process_timed(od, xyz_dev, ns, stride_floats * S, res, false);
+  const b2lo_record_fmt* F = od->has_fmt ? &od->fmt : nullptr;
+  return process_timed(od, xyz_dev, ns, (F ? (size_t)F->record_bytes : stride_floats) * S, res, false, F);
 }
 
 extern "C" int b2lo_odom_lookahead(b2lo_odom* od, const float* xyz_next, size_t n, size_t stride_floats, int on_device) {
@@ -435,8 +450,23 @@ extern "C" int b2lo_odom_lookahead(b2lo_odom* od, const float* xyz_next, size_t 
     src = static_cast<const float*>(attr.devicePointer);
   }
   const size_t S = (size_t)(od->cfg.point_stride < 1 ? 1 : od->cfg.point_stride);
-  od->la_src = src; od->la_ns = (n + S - 1) / S; od->la_stride = stride_floats * S;
+  od->la_src = src; od->la_ns = (n + S - 1) / S; od->la_stride = (od->has_fmt ? (size_t)od->fmt.record_bytes : stride_floats) * S;
   od->la_valid = true;
+  return B2LO_OK;
+}
+
+extern "C" int b2lo_odom_set_record_fmt(b2lo_odom* od, const b2lo_record_fmt* fmt) {
+  if (!od) return B2LO_E_ARG;
+  std::lock_guard<std::recursive_mutex> lk(od->map->mu);
+  std::lock_guard<std::mutex> lk2(od->ctx->mu);
+  if (fmt) {
+    if (fmt->record_bytes == 0) { set_error("records: no format"); return B2LO_E_ARG; }
+    for (int a = 0; a < 3; ++a)
+      if ((size_t)(&fmt->off_x)[a] + 4 > fmt->record_bytes) { set_error("records: coordinate offset outside the record"); return B2LO_E_ARG; }
+    od->fmt = *fmt;
+  }
+  od->has_fmt = fmt != nullptr;
+  od->la_valid = od->pre_valid = false;   // announcements made under the previous format are dropped
   return B2LO_OK;
 }
 

@@ -53,6 +53,10 @@ void orc_parent_key(const int* key, int factor, int* parent);
 /* FastVoxelFilter */
 void orc_filter(const float* xyz, size_t n, int stride, float voxel, float* out_xyz, uint64_t* out_keys, size_t* m);
 
+/* scan loaders on file images (orc_ingest.hpp): out_xyz capacity in points; return 0 ok / -1 buffer too small */
+int orc_ply_load(const void* image, size_t len, float* out_xyz, size_t cap, size_t* n);
+int orc_kitti_load(const void* image, size_t len, float* out_xyz, size_t cap, size_t* n);
+
 /* VoxelMap */
 void* orc_map_create(float voxel, int factor, float planarity, int compute_surfels);
 void orc_map_destroy(void* h);

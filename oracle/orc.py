@@ -133,6 +133,26 @@ def voxel_filter(xyz, stride, voxel):
     return out[: m.value].copy(), keys[: m.value].copy()
 
 
+def _load_image(fn, image):
+    a = np.frombuffer(bytes(image), dtype=np.uint8) if not isinstance(image, np.ndarray) else np.ascontiguousarray(image.view(np.uint8)).reshape(-1)
+    cap = max(a.size // 4, 1)
+    out = np.zeros((cap, 3), np.float32)
+    n = C.c_size_t(0)
+    rc = fn(_p(a), C.c_size_t(a.size), _p(out), C.c_size_t(cap), C.byref(n))
+    assert rc == 0
+    return out[: n.value].copy()
+
+
+def ply_load(image):
+    """PLYPlayer::load_ply_point_cloud on a file image -> (N,3) f32 (empty when the reference rejects the file)."""
+    return _load_image(lib().orc_ply_load, image)
+
+
+def kitti_load(image):
+    """util::load_kitti_binary on a file image -> (N,3) f32."""
+    return _load_image(lib().orc_kitti_load, image)
+
+
 class VoxelMap:
     def __init__(self, voxel=0.5, factor=3, planarity=0.1, compute_surfels=True, handle=None):
         self._own = handle is None

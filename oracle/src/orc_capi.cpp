@@ -309,3 +309,18 @@ size_t orc_dense_order(const int64_t* ops, size_t n_ops, uint64_t* out_keys) {
 }
 
 }  // extern "C"
+
+// ---- scan loaders on file images (orc_ingest.hpp) ---------------------------------------------------------
+#include "orc_ingest.hpp"
+static int emit_cloud(const std::vector<float>& v, float* out_xyz, size_t cap, size_t* n) {
+  *n = v.size() / 3;
+  if (*n > cap) return -1;
+  if (!v.empty()) std::memcpy(out_xyz, v.data(), v.size() * sizeof(float));
+  return 0;
+}
+extern "C" int orc_ply_load(const void* image, size_t len, float* out_xyz, size_t cap, size_t* n) {
+  return emit_cloud(orc::ply_load(std::string(static_cast<const char*>(image), len)), out_xyz, cap, n);
+}
+extern "C" int orc_kitti_load(const void* image, size_t len, float* out_xyz, size_t cap, size_t* n) {
+  return emit_cloud(orc::kitti_load(std::string(static_cast<const char*>(image), len)), out_xyz, cap, n);
+}
