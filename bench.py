@@ -335,6 +335,32 @@ def concurrent_leg(api, local, dev_args, S, K, W):
             "note": "aggregate over independent sequences sharing one B200; not the per-sequence latency of `value`"}
 
 
+def export_leg(ctx, api, scans, poses, K):
+    """SURVEY 8f-4: the final-map downsample of Estimator::save_map_to_ply (util::VoxelGrid, leaf 0.4 m) over the accumulated world
+    cloud of the benchmark sequence, through the host-buffer call (H2D + D2H inside), next to the CPU oracle on the same cloud."""
+    from oracle import orc
+    world = []
+    for s, T in zip(scans[:K], poses[:K]):
+        T = np.asarray(T, np.float32)
+        world.append((s[::8, :3] @ T[:3, :3].T + T[:3, 3]).astype(np.float32))
+    acc = np.ascontiguousarray(np.concatenate(world))
+    g = api.VoxelGrid(ctx)
+    g.setLeafSize(0.4)
+    g.setInputCloud(acc)
+    out = g.filter()                 # warm-up: sizes the K1 scratch for this cloud
+    ctx.sync()
+    t0 = time.perf_counter()
+    out = g.filter()
+    t_gpu = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ref = orc.voxel_grid_filter(acc, 0.4)
+    t_cpu = time.perf_counter() - t0
+    return {"workload": f"util::VoxelGrid leaf 0.4 m over {len(acc)} accumulated world points ({K} scans, every 8th point)", "points_in": int(len(acc)),
+            "voxels_out": int(len(out)), "ms": 1e3 * t_gpu, "points_per_s": len(acc) / t_gpu, "cpu_oracle_ms": 1e3 * t_cpu,
+            "bit_identical_to_oracle": bool(out.shape == ref.shape and np.array_equal(out.view(np.uint32), ref.view(np.uint32))),
+            "algorithmic_bytes": 12 * int(len(acc)) + 12 * int(len(out)), "timing": "host wall clock around the host-buffer call (pageable input, H2D + D2H inside)"}
+
+
 def _cuda():
     try:
         import torch
@@ -355,7 +381,7 @@ def main():
     ap.add_argument("--no-stress", action="store_true", help="skip the 10^7-voxel map leg (BASELINE.json configs[3])")
     ap.add_argument("--stress-voxels", type=float, default=1.0e7)
     ap.add_argument("--stress-only", action="store_true")
-    ap.add_argument("--concurrent", type=int, nargs="*", default=[4, 16], help="sequences sharing one GPU in the throughput-mode leg (empty: skip)")
+    ap.add_argument("--concurrent", type=int, nargs="*", default=[8, 16], help="sequences sharing one GPU in the throughput-mode leg (empty: skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
@@ -378,7 +404,7 @@ def main():
         st = stress_leg(api.Context(local), api, capi, int(args.stress_voxels), peak, peak_kind)
         print(json.dumps({"k2_probe": st["k2_probe"], "k2_probe_coherent": st["k2_probe_coherent"], "rehash_rebuild": st["rehash_rebuild"]}))
         return
-    scans, _ = make_scans(K + W + 1, 42, f"cuda:{local}")   # weak scaling: every rank processes its own copy of the same sequence; +1: the look-ahead of the last timed scan
+    scans, true_poses = make_scans(K + W + 1, 42, f"cuda:{local}")   # weak scaling: every rank processes its own copy of the same sequence; +1: the look-ahead of the last timed scan
     ctx = api.Context(local)
     dev_scans = [torch.from_numpy(s).cuda() for s in scans]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
@@ -514,8 +540,9 @@ def main():
     if world == 1 and args.concurrent:
         conc = [concurrent_leg(api, local, dev_args, S, K, W) for S in args.concurrent]
 
-    stress = mid360 = None
+    stress = mid360 = export = None
     if world == 1 and not args.no_stress:
+        export = export_leg(ctx, api, scans, true_poses, K)
         mid360 = mid360_leg(ctx, api, capi, flush, torch)
         stress = stress_leg(ctx, api, capi, int(args.stress_voxels), peak, peak_kind)
 
@@ -532,7 +559,7 @@ def main():
                     "d2h_bytes_per_step": (d1 - d0) / K},
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "stage_ms_per_scan": {k: v["ms_total"] / K for k, v in stage.items()},
             "dominant_kernel_group": dominant, "cpu_baseline": cpu,
-            "concurrent_sequences_one_gpu": conc, "large_map_stress": stress, "kdtree_mid360": mid360}
+            "concurrent_sequences_one_gpu": conc, "final_map_export": export, "large_map_stress": stress, "kdtree_mid360": mid360}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

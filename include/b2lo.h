@@ -155,6 +155,13 @@ int b2lo_map_rebuild_knn(b2lo_map* map);                                        
 int b2lo_map_has_knn(b2lo_map* map);                                                  /* HasKdTree (VoxelMap.h:268) */
 int b2lo_map_transform_rehash(b2lo_map* map, const float T16[16]);                    /* ApplyTransformAndRehash (:264-302) */
 
+/* ---- final-map export ----------------------------------------------------------------------
+ * util::VoxelGrid::filter (src/util/PointCloudUtils.h:462-557) as Estimator::save_map_to_ply applies it to the accumulated keyframe clouds
+ * (src/processing/Estimator.cpp:1248-1305): one running-average centroid per leaf-sized voxel, emitted in std::map<VoxelKey> order
+ * (x, then y, then z).  out_xyz: capacity `cap` points; *m receives the voxel count (also on B2LO_E_CAPACITY).  Points with a non-finite
+ * coordinate or beyond +-2^20 leaves are dropped.  Overwrites the context's feature buffer. */
+int b2lo_voxel_grid_filter(b2lo_ctx* ctx, const float* xyz, size_t n, size_t stride_floats, float leaf_size, float* out_xyz, size_t cap, size_t* m);
+
 /* ---- IterativeClosestPointOptimizer ------------------------------------------------------------- */
 /* find_correspondences (ICP.cpp:587-645) at a fixed pose; per-query taps for bit-exact parity:
  * state 0 no surfel / 1 gated out / 2 accepted; l1key 3 ints; morton = VoxelKeyHash; residual f64. */

@@ -22,7 +22,7 @@ import numpy as np
 from . import capi
 from .capi import B2LO_OK, B2LO_S_EMPTY, B2LO_S_INSUFFICIENT, IcpCfg, IcpStats, OdomCfg, OdomResult, RecordFmt, check
 
-__all__ = ["PointShardedICP", "Context", "default_context", "FastVoxelFilter", "FastVoxelGrid", "VoxelMap", "ICPConfig", "AdaptiveMEstimatorConfig",
+__all__ = ["PointShardedICP", "Context", "default_context", "FastVoxelFilter", "FastVoxelGrid", "VoxelGrid", "VoxelMap", "ICPConfig", "AdaptiveMEstimatorConfig",
            "AdaptiveMEstimator", "OptimizationStats", "IterativeClosestPointOptimizer", "Odometry", "SE3", "RecordFormat", "kitti_record_format", "parse_ply_header", "load_ply_point_cloud", "load_kitti_binary"]
 
 
@@ -251,6 +251,31 @@ class FastVoxelFilter:
 
 
 FastVoxelGrid = FastVoxelFilter  # VoxelMap.h:143
+
+
+class VoxelGrid:
+    """util::VoxelGrid (src/util/PointCloudUtils.h:462-557): setLeafSize / setInputCloud / filter, as save_map_to_ply uses it."""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or default_context()
+        self.leaf_size_ = 0.01
+        self.input_cloud_ = None
+
+    def setLeafSize(self, size):
+        self.leaf_size_ = float(size)
+
+    def setInputCloud(self, cloud):
+        self.input_cloud_ = cloud
+
+    def filter(self):
+        """Returns the (M,3) centroids in the reference's std::map order."""
+        if self.input_cloud_ is None or len(self.input_cloud_) == 0 or self.leaf_size_ <= 0:
+            return np.zeros((0, 3), np.float32)
+        a, n, sf = _cloud(self.input_cloud_)
+        out = np.zeros((n, 3), np.float32)
+        m = C.c_size_t()
+        check(capi.lib().b2lo_voxel_grid_filter(self.ctx.h, _p(a), n, sf, C.c_float(self.leaf_size_), _p(out), n, C.byref(m)))
+        return out[: m.value].copy()
 
 
 # ---- VoxelMap ---------------------------------------------------------------------------------------------------

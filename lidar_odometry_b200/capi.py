@@ -110,6 +110,7 @@ SIGNATURES = {
     "b2lo_ply_read_ascii": (_i, [_vp, _sz, _vp, _sz, C.POINTER(_sz)]),
     "b2lo_filter_records": (_i, [_vp, _vp, _sz, C.POINTER(RecordFmt), _i, _f, _vp, _vp, C.POINTER(_sz)]),
     "b2lo_filter_records_dev": (_i, [_vp, _vp, _sz, C.POINTER(RecordFmt), _i, _f]),
+    "b2lo_voxel_grid_filter": (_i, [_vp, _vp, _sz, _sz, _f, _vp, _sz, C.POINTER(_sz)]),
     "b2lo_map_create": (_i, [_vp, _f, _i, _f, _i, _sz, C.POINTER(_vp)]),
     "b2lo_map_destroy": (_i, [_vp]),
     "b2lo_map_clear": (_i, [_vp]),

@@ -50,6 +50,7 @@ __global__ void k_flt_insert(const ScanParams* __restrict__ sp, FEntry* tab, int
   const size_t sample_stride = (size_t)sp->flt_stride;
   const float inv = sp->flt_inv;
   const unsigned int rec = sp->flt_rec, ox = sp->flt_off[0], oy = sp->flt_off[1], oz = sp->flt_off[2];
+  const unsigned int mode = sp->flt_mode;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_samples; j += gridDim.x * blockDim.x) {
     float x, y, z;
     if (rec) {   // byte records (PLY vertices, ply_player.cpp:330-337): three 4-byte copies at arbitrary, possibly unaligned offsets
@@ -61,8 +62,19 @@ __global__ void k_flt_insert(const ScanParams* __restrict__ sp, FEntry* tab, int
     }
     samp[j] = make_float4(x, y, z, 0.0f);
     int s = -1;
-    if (isfinite(x) && isfinite(y) && isfinite(z)) {
-      unsigned long long key = filter_key(x, y, z, inv);
+    bool take = isfinite(x) && isfinite(y) && isfinite(z);
+    unsigned long long key = 0ull;
+    if (take) {
+      if (mode == 0) key = filter_key(x, y, z, inv);
+      else {
+        // util::VoxelGrid::get_voxel_key (PointCloudUtils.h:547-552): floor(p / leaf) per axis (true division; `inv` carries the leaf);
+        // x is packed highest so that ascending keys are std::map<VoxelKey>'s (x, y, z) order
+        const int gx = voxel_coord(x, inv), gy = voxel_coord(y, inv), gz = voxel_coord(z, inv);
+        take = key_in_range(gx, gy, gz);
+        key = key_pack(gz, gy, gx);
+      }
+    }
+    if (take) {
       uint32_t mask = (1u << log2cap) - 1u;
       uint32_t h = hash_slot(key, log2cap);
       for (;;) {
@@ -177,10 +189,26 @@ __global__ void k_flt_rank(const FEntry* __restrict__ tab, const int* __restrict
 // one thread per voxel adds its points in input order (sequential f32, VoxelMap.h:88-91) and writes centroid and key
 __global__ void k_flt_reduce(const int* __restrict__ d_nvox, const int* __restrict__ seg_start, const int* __restrict__ seg_cnt,
                              const float4* __restrict__ sorted, const int* __restrict__ lead_of_vid, const int* __restrict__ slot_of,
-                             const FEntry* __restrict__ tab, float4* out, unsigned long long* out_key) {
+                             const FEntry* __restrict__ tab, float4* out, unsigned long long* out_key, const ScanParams* __restrict__ sp) {
   const int nv = *d_nvox;
+  const unsigned int mode = sp->flt_mode;
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
     const int b = seg_start[v], m = seg_cnt[v];
+    if (mode == 1) {
+      // util::VoxelGrid::WeightedCentroid::add_point (PointCloudUtils.h:502-520): first point copied, then
+      // c = (w / (w + 1)) * c + (1 / (w + 1)) * p in f32, points in input order
+      float4 c = sorted[b];
+      float wgt = 1.0f;
+      for (int q = 1; q < m; ++q) {
+        const float4 p = sorted[b + q];
+        const float tot = wgt + 1.0f, ro = wgt / tot, rn = 1.0f / tot;
+        c.x = ro * c.x + rn * p.x; c.y = ro * c.y + rn * p.y; c.z = ro * c.z + rn * p.z;
+        wgt = tot;
+      }
+      out[v] = make_float4(c.x, c.y, c.z, wgt);
+      out_key[v] = tab[slot_of[lead_of_vid[v]]].key;
+      continue;
+    }
     float sx = 0.0f, sy = 0.0f, sz = 0.0f;
     int q = 0;
     for (; q + 4 <= m; q += 4) {  // four independent loads in flight, adds stay in order
@@ -198,7 +226,7 @@ __global__ void k_flt_reduce(const int* __restrict__ d_nvox, const int* __restri
 }
 
 int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sample_stride_floats, float voxel, int set, cudaStream_t on,
-               const b2lo_record_fmt* fmt) {
+               const b2lo_record_fmt* fmt, int mode) {
   cudaStream_t st = on ? on : ctx->stream;
   if (set == 0) ctx->feat_set = 0;
   if (n_samples == 0) { if (set == 0) ctx->feat_cap_hint = 0; B2_CUDA(cudaMemsetAsync(ctx->nfeat(set), 0, sizeof(int), st)); return B2LO_OK; }
@@ -215,7 +243,8 @@ int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sam
   if (!ctx->sp_preloaded) {
     if ((rc = sp_begin_write(ctx))) return rc;
     ctx->h_sp->flt_src = src_dev; ctx->h_sp->flt_ns = (int)n_samples; ctx->h_sp->flt_stride = sample_stride_floats;
-    ctx->h_sp->flt_inv = 1.0f / voxel;  // m_inv_voxel_size (VoxelMap.h:57)
+    ctx->h_sp->flt_inv = mode == 1 ? voxel : 1.0f / voxel;  // m_inv_voxel_size (VoxelMap.h:57); VoxelGrid divides by the leaf size itself
+    ctx->h_sp->flt_mode = (unsigned)mode;
     ctx->h_sp->flt_rec = fmt ? fmt->record_bytes : 0u;
     for (int a = 0; a < 3; ++a) ctx->h_sp->flt_off[a] = fmt ? (&fmt->off_x)[a] : 0u;
     if ((rc = sp_upload(ctx, 0, offsetof(ScanParams, T_init)))) return rc;
@@ -231,7 +260,7 @@ int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sam
   k_flt_fill<<<blocks, 256, 0, st>>>(ctx->f_tab, ctx->f_slot, sp, ctx->f_vid, ctx->f_segstart, ctx->f_bucket);
   k_flt_rank<<<blocks, 256, 0, st>>>(ctx->f_tab, ctx->f_slot, sp, ctx->f_vid, ctx->f_segstart, ctx->f_segcnt, ctx->f_bucket, ctx->f_samp, ctx->f_sorted);
   k_flt_reduce<<<blocks, 256, 0, st>>>(ctx->nfeat(set), ctx->f_segstart, ctx->f_segcnt, ctx->f_sorted, ctx->f_lead, ctx->f_slot, ctx->f_tab,
-                                       ctx->feat(set), ctx->feat_key(set));
+                                       ctx->feat(set), ctx->feat_key(set), sp);
   if (prof) prof_end(ctx);
   ctx->launches += 6;
   B2_CUDA(cudaGetLastError());

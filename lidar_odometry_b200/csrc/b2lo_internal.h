@@ -60,6 +60,7 @@ struct ScanParams {
   // byte-record input (b2lo_record_fmt: PLY vertex records, any layout): flt_rec != 0 -> flt_src is a byte stream, flt_stride the
   // distance between SAMPLED records in bytes, flt_off the byte offsets of the three IEEE f32 coordinates inside a record
   unsigned int flt_rec; unsigned int flt_off[3];
+  unsigned int flt_mode;   // 0: FastVoxelFilter (Z-order key of floor(x * inv), centroid = sum / count); 1: util::VoxelGrid (b2lo_export.cu)
   float T_init[16];                                                                   // ICP initial pose
   DecideArgs decide;                                                                  // odometry tail
 };
@@ -179,7 +180,7 @@ int ctx_transform_dev(b2lo_ctx* ctx, const float4* src, const int* d_n, size_t n
 int ctx_read_cloud(b2lo_ctx* ctx, const float4* src, const int* d_n, size_t n_cap, float* out_xyz, size_t out_cap, size_t* n_out);
 // sample_stride: floats between sampled points, or BYTES between sampled records when fmt != nullptr (byte-record input)
 int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sample_stride, float voxel, int set = 0, cudaStream_t on = nullptr,
-               const b2lo_record_fmt* fmt = nullptr);
+               const b2lo_record_fmt* fmt = nullptr, int mode = 0);
 int ctx_stage_records_h2d(b2lo_ctx* ctx, const void* bytes, size_t n_records, const b2lo_record_fmt* fmt, size_t take_every);
 int icp_build_pko(b2lo_ctx* ctx, const b2lo_icp_cfg* cfg);
 int icp_prepare(b2lo_ctx* ctx, const b2lo_icp_cfg* cfg);

@@ -256,6 +256,7 @@ static int steady_scan(b2lo_odom* od, const float* src_dev, size_t ns, size_t sa
   sp->flt_src = mode == K1_NEXT ? nx_src : src_dev; sp->flt_ns = (int)flt_ns;
   sp->flt_stride = mode == K1_NEXT ? nx_stride : sample_stride_floats; sp->flt_inv = 1.0f / od->cfg.voxel_size;
   sp_set_fmt(sp, mode == K1_NEXT ? (od->has_fmt ? &od->fmt : nullptr) : eff);
+  sp->flt_mode = 0;
   pose_to_T16(init, sp->T_init);
   pose_to_T16(guess, sp->decide.guess);
   pose_to_T16(od->last_kf_pose, sp->decide.last_kf);

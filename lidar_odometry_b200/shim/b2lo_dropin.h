@@ -6,8 +6,9 @@
 //   lidar_slam::optimization::IterativeClosestPointOptimizer  src/optimization/IterativeClosestPointOptimizer.h:158-225
 // so that src/processing/Estimator.cpp (and PangolinViewer.cpp:966-973) compile against it unchanged.  Everything
 // the reference computes on the CPU inside these classes runs on the GPU behind libb2lo.so; the classes themselves
-// only marshal host buffers.  optimize_loop (loop-closure ICP, out of scope) is forwarded to the reference's own
-// implementation when B2LO_KEEP_REFERENCE_LOOP_ICP is defined, otherwise it reports failure.
+// only marshal host buffers.  optimize_loop (loop-closure ICP) runs on the GPU as well (b2lo_icp_optimize_loop, on its own context
+// because the reference calls it from the loop/PGO thread next to optimize()); define B2LO_KEEP_REFERENCE_LOOP_ICP to keep the
+// reference's CPU body instead.  util::VoxelGrid (final-map export) and the scan-ingest helpers are at the end.
 //
 // Build inside the reference tree: replace the two headers' class bodies with `#include "b2lo_dropin.h"` as
 // INTEGRATION.md shows; the reference's own util/ headers (PointCloud, SE3f, KdTree, LidarFrame, ICPConfig,
@@ -251,7 +252,7 @@ class IterativeClosestPointOptimizer {  // IterativeClosestPointOptimizer.h:158-
     return true;
   }
 
-  // Loop-closure ICP (ICP.cpp:40-251) is out of the hot path; see INTEGRATION.md for keeping the reference's CPU body.
+  // Loop-closure ICP (ICP.cpp:40-251): defined below on the GPU; INTEGRATION.md shows how to keep the reference's CPU body instead.
   bool optimize_loop(std::shared_ptr<database::LidarFrame> curr_keyframe, std::shared_ptr<database::LidarFrame> matched_keyframe,
                      SE3f& optimized_relative_transform, float& inlier_ratio);
 
@@ -288,11 +289,111 @@ class IterativeClosestPointOptimizer {  // IterativeClosestPointOptimizer.h:158-
 };
 
 #ifndef B2LO_KEEP_REFERENCE_LOOP_ICP
-inline bool IterativeClosestPointOptimizer::optimize_loop(std::shared_ptr<database::LidarFrame>, std::shared_ptr<database::LidarFrame>, SE3f&, float& inlier_ratio) {
-  inlier_ratio = 0.0f;  // loop closure disabled in a hot-path-only build; Estimator treats false as "no loop" (Estimator.cpp:1001-1010)
-  return false;
+namespace b2lo_detail_loop {
+// the loop/PGO thread's own context: optimize_loop runs concurrently with optimize() (Estimator.cpp:1001)
+inline b2lo_ctx* context() {
+  static b2lo_ctx* ctx = [] {
+    b2lo_ctx* c = nullptr;
+    int dev = 0;
+    if (const char* e = std::getenv("B2LO_DEVICE")) dev = std::atoi(e);
+    if (b2lo_ctx_create(dev, &c) != B2LO_OK) throw std::runtime_error(std::string("b2lo: ") + b2lo_last_error());
+    return c;
+  }();
+  return ctx;
+}
+}  // namespace b2lo_detail_loop
+// ICP.cpp:40-251: relative = curr_pose^-1 * optimised curr pose; true only if the loop converged and >= half of the points are inliers.
+// The keyframes are only read (the reference works on deep copies for the same effect).
+inline bool IterativeClosestPointOptimizer::optimize_loop(std::shared_ptr<database::LidarFrame> curr_keyframe,
+                                                          std::shared_ptr<database::LidarFrame> matched_keyframe,
+                                                          SE3f& optimized_relative_transform, float& inlier_ratio) {
+  inlier_ratio = 0.0f;
+  if (!curr_keyframe || !matched_keyframe) return false;
+  if (m_adaptive_estimator) m_adaptive_estimator->reset();   // :52-55
+  auto cloud_of = [](const std::shared_ptr<database::LidarFrame>& f) {
+    util::PointCloudConstPtr c = f->get_feature_cloud();     // get_frame_cloud (:769-783)
+    if (!c || c->empty()) c = f->get_processed_cloud();
+    return c;
+  };
+  util::PointCloudConstPtr cc = cloud_of(curr_keyframe), mc = cloud_of(matched_keyframe);
+  if (!cc || cc->empty() || !mc || mc->empty()) return false;
+  b2lo_icp_cfg cfg;
+  fill_cfg(cfg);
+  float Tc[16], Tm[16], Trel[16];
+  b2lo_detail::to_row_major(curr_keyframe->get_pose().Matrix(), Tc);
+  b2lo_detail::to_row_major(matched_keyframe->get_pose().Matrix(), Tm);
+  b2lo_icp_stats st;
+  const int rc = b2lo_icp_optimize_loop(b2lo_detail_loop::context(), b2lo_detail::data(*cc), cc->size(), b2lo_detail::stride_floats(), Tc,
+                                        b2lo_detail::data(*mc), mc->size(), b2lo_detail::stride_floats(), Tm, &cfg, Trel, &inlier_ratio, &st);
+  if (rc < 0) throw std::runtime_error(std::string("b2lo_icp_optimize_loop: ") + b2lo_last_error());
+  optimized_relative_transform = SE3f(b2lo_detail::from_row_major(Trel));
+  return rc == B2LO_OK;
 }
 #endif
 
 }  // namespace optimization
+
+// ---- final-map export and scan ingest -------------------------------------------------------------
+namespace b2lo {
+
+// util::VoxelGrid (src/util/PointCloudUtils.h:462-557) with the same three calls; Estimator::save_map_to_ply (Estimator.cpp:1290-1298)
+// uses it as `lidar_slam::b2lo::VoxelGrid voxel_filter;` in place of `util::VoxelGrid voxel_filter;`
+class VoxelGrid {
+ public:
+  VoxelGrid() : leaf_size_(0.01f) {}
+  void setLeafSize(float size) { leaf_size_ = size; }
+  void setInputCloud(const util::PointCloudConstPtr& cloud) { input_cloud_ = cloud; }
+  void filter(util::PointCloud& output) {
+    output.clear();
+    if (!input_cloud_ || input_cloud_->empty() || leaf_size_ <= 0) return;
+    std::vector<float> buf(input_cloud_->size() * 3);
+    size_t m = 0;
+    int rc = b2lo_voxel_grid_filter(b2lo_detail::context(), b2lo_detail::data(*input_cloud_), input_cloud_->size(), b2lo_detail::stride_floats(),
+                                    leaf_size_, buf.data(), input_cloud_->size(), &m);
+    if (rc < 0) throw std::runtime_error(std::string("b2lo_voxel_grid_filter: ") + b2lo_last_error());
+    output.reserve(m);
+    for (size_t i = 0; i < m; ++i) output.push_back(util::Point3D(buf[i * 3], buf[i * 3 + 1], buf[i * 3 + 2]));
+  }
+
+ private:
+  float leaf_size_;
+  util::PointCloudConstPtr input_cloud_;
+};
+
+// preprocess_frame (Estimator.cpp:561-589) straight from a scan FILE IMAGE: a KITTI .bin (util::load_kitti_binary) or a binary PLY
+// (PLYPlayer::load_ply_point_cloud) is downsampled by K1 reading the file's own records; no util::PointCloud of the raw scan is built.
+// Returns false for the files the reference's loaders reject; ASCII PLY bodies are parsed on the host first.
+inline bool filter_scan_file_image(const void* image, size_t bytes, bool is_ply, float voxel_size, int stride, util::PointCloud& output) {
+  output.clear();
+  b2lo_record_fmt fmt;
+  size_t n_records = 0, data_offset = 0;
+  std::vector<float> ascii;
+  const unsigned char* body = static_cast<const unsigned char*>(image);
+  if (is_ply) {
+    size_t vertices = 0;
+    int is_binary = 0;
+    if (b2lo_ply_parse_header(image, bytes, &fmt, &vertices, &data_offset, &is_binary, &n_records) != B2LO_OK) return false;
+    if (!is_binary) {
+      ascii.resize(vertices * 3);
+      if (b2lo_ply_read_ascii(image, bytes, ascii.data(), vertices, &n_records) != B2LO_OK) return false;
+      fmt.record_bytes = 12; fmt.off_x = 0; fmt.off_y = 4; fmt.off_z = 8;
+      body = reinterpret_cast<const unsigned char*>(ascii.data());
+      data_offset = 0;
+    }
+  } else {
+    b2lo_kitti_record_fmt(&fmt);
+    n_records = bytes / fmt.record_bytes;
+  }
+  if (n_records == 0 || stride < 1) return true;
+  const size_t ns = (n_records + (size_t)stride - 1) / (size_t)stride;
+  std::vector<float> buf(ns * 3);
+  size_t m = 0;
+  int rc = b2lo_filter_records(b2lo_detail::context(), body + data_offset, n_records, &fmt, stride, voxel_size, buf.data(), nullptr, &m);
+  if (rc < 0) throw std::runtime_error(std::string("b2lo_filter_records: ") + b2lo_last_error());
+  output.reserve(m);
+  for (size_t i = 0; i < m; ++i) output.push_back(util::Point3D(buf[i * 3], buf[i * 3 + 1], buf[i * 3 + 2]));
+  return true;
+}
+
+}  // namespace b2lo
 }  // namespace lidar_slam

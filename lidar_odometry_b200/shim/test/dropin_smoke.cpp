@@ -47,7 +47,33 @@ int main() {
   Eigen::Vector3f n, c;
   bool hit = vmap.GetSurfelAtPoint(Eigen::Vector3f(1.0f, 1.0f, -1.7f), n, c);
   std::printf("export: %zu centroids, %zu surfels, lookup hit=%d n=(%.2f %.2f %.2f)\n", l0->size(), surfels.size(), (int)hit, n.x(), n.y(), n.z());
-  bool pass = ok && std::fabs(M(0, 3) - 0.3f) < 0.02f && std::fabs(M(1, 3)) < 0.02f && l0->size() == vmap.GetVoxelCount() && hit && std::fabs(std::fabs(n.z()) - 1.0f) < 0.05f;
+  // loop-closure ICP between the two "keyframes": ds1 sits 0.3 m further along x; the matched keyframe is ds0 at the origin, the
+  // current one starts 0.1 m off its true pose, so the relative correction must bring back ~(+0.1, 0, 0)
+  auto kf_m = std::make_shared<database::LidarFrame>(ds0);
+  auto kf_c = std::make_shared<database::LidarFrame>(ds1);
+  Eigen::Matrix4f Pc; Pc(0, 3) = 0.2f;
+  kf_c->set_pose(SE3f(Pc));
+  SE3f rel; float ratio = 0.0f;
+  bool lok = icp.optimize_loop(kf_c, kf_m, rel, ratio);
+  Eigen::Matrix4f Mr = rel.Matrix();
+  std::printf("optimize_loop: ok=%d inliers=%.3f rel t=(%.4f %.4f %.4f)\n", (int)lok, ratio, Mr(0, 3), Mr(1, 3), Mr(2, 3));
+  // final-map export (util::VoxelGrid) and KITTI-image ingest
+  b2lo::VoxelGrid vg;
+  vg.setLeafSize(1.0f);
+  vg.setInputCloud(ds0);
+  util::PointCloud coarse;
+  vg.filter(coarse);
+  bool sorted = coarse.size() > 100 && coarse.size() < ds0->size();
+  for (size_t i = 1; i < coarse.size() && sorted; ++i) sorted = std::floor(coarse[i - 1].x) <= std::floor(coarse[i].x);
+  std::vector<float> bin;
+  for (size_t i = 0; i < raw0->size(); ++i) { bin.push_back((*raw0)[i].x); bin.push_back((*raw0)[i].y); bin.push_back((*raw0)[i].z); bin.push_back(0.5f); }
+  util::PointCloud from_image;
+  bool iok = b2lo::filter_scan_file_image(bin.data(), bin.size() * sizeof(float), false, 0.5f, 2, from_image);
+  bool same = iok && from_image.size() == ds0->size();
+  for (size_t i = 0; i < from_image.size() && same; ++i) same = from_image[i].x == (*ds0)[i].x && from_image[i].y == (*ds0)[i].y && from_image[i].z == (*ds0)[i].z;
+  std::printf("voxel grid: %zu -> %zu (x-sorted %d); .bin image ingest identical to filter(): %d\n", ds0->size(), coarse.size(), (int)sorted, (int)same);
+  bool pass = lok && ratio > 0.9f && std::fabs(Mr(0, 3) - 0.1f) < 0.03f && std::fabs(Mr(1, 3)) < 0.03f && sorted && same &&
+              ok && std::fabs(M(0, 3) - 0.3f) < 0.02f && std::fabs(M(1, 3)) < 0.02f && l0->size() == vmap.GetVoxelCount() && hit && std::fabs(std::fabs(n.z()) - 1.0f) < 0.05f;
   std::printf(pass ? "DROPIN PASS\n" : "DROPIN FAIL\n");
   return pass ? 0 : 1;
 }

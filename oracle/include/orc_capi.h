@@ -57,6 +57,9 @@ void orc_filter(const float* xyz, size_t n, int stride, float voxel, float* out_
 int orc_ply_load(const void* image, size_t len, float* out_xyz, size_t cap, size_t* n);
 int orc_kitti_load(const void* image, size_t len, float* out_xyz, size_t cap, size_t* n);
 
+/* util::VoxelGrid::filter (orc_voxelgrid.hpp) */
+int orc_voxel_grid_filter(const float* xyz, size_t n, float leaf, float* out_xyz, size_t cap, size_t* m);
+
 /* VoxelMap */
 void* orc_map_create(float voxel, int factor, float planarity, int compute_surfels);
 void orc_map_destroy(void* h);

@@ -143,6 +143,17 @@ def _load_image(fn, image):
     return out[: n.value].copy()
 
 
+def voxel_grid_filter(xyz, leaf):
+    """util::VoxelGrid::filter: (N,3) f32 -> centroids (M,3) f32 in std::map key order."""
+    xyz = f32(xyz).reshape(-1, 3)
+    n = xyz.shape[0]
+    out = np.zeros((max(n, 1), 3), np.float32)
+    m = C.c_size_t(0)
+    rc = lib().orc_voxel_grid_filter(_p(xyz), C.c_size_t(n), C.c_float(leaf), _p(out), C.c_size_t(max(n, 1)), C.byref(m))
+    assert rc == 0
+    return out[: m.value].copy()
+
+
 def ply_load(image):
     """PLYPlayer::load_ply_point_cloud on a file image -> (N,3) f32 (empty when the reference rejects the file)."""
     return _load_image(lib().orc_ply_load, image)

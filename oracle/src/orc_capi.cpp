@@ -324,3 +324,9 @@ extern "C" int orc_ply_load(const void* image, size_t len, float* out_xyz, size_
 extern "C" int orc_kitti_load(const void* image, size_t len, float* out_xyz, size_t cap, size_t* n) {
   return emit_cloud(orc::kitti_load(std::string(static_cast<const char*>(image), len)), out_xyz, cap, n);
 }
+
+// ---- util::VoxelGrid (orc_voxelgrid.hpp) ------------------------------------------------------------------
+#include "orc_voxelgrid.hpp"
+extern "C" int orc_voxel_grid_filter(const float* xyz, size_t n, float leaf, float* out_xyz, size_t cap, size_t* m) {
+  return emit_cloud(orc::voxel_grid_filter(xyz, n, leaf), out_xyz, cap, m);
+}

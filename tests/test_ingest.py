@@ -205,3 +205,47 @@ def test_odometry_on_kitti_file_images_equals_odometry_on_clouds(b2, orc, small_
     # back to float clouds
     odo.set_record_format(None)
     assert odo.process(scans[-1])["ok"]
+
+
+# ---- final-map export: util::VoxelGrid ------------------------------------------------------------------
+def test_oracle_voxel_grid_known_answers(orc):
+    x = np.array([[0.1, 0.1, 0.1], [0.2, 0.2, 0.2], [-0.1, 5, 5], [0.3, 0.3, 0.3], [0.9, -0.2, 0.0]], np.float32)
+    got = orc.voxel_grid_filter(x, 1.0)
+    # std::map order: (-1,5,5) < (0,-1,0) < (0,0,0); the (0,0,0) cell holds the running mean of 3 points
+    c = np.float32(0.5) * x[0] + np.float32(0.5) * x[1]
+    c = (np.float32(2.0) / np.float32(3.0)) * c + (np.float32(1.0) / np.float32(3.0)) * x[3]
+    assert got.shape == (3, 3)
+    assert np.array_equal(got[0], x[2]) and np.array_equal(got[1], x[4])
+    assert np.array_equal(got[2].view(np.uint32), c.astype(np.float32).view(np.uint32))
+    assert orc.voxel_grid_filter(x, 0.0).shape == (0, 3) and orc.voxel_grid_filter(x[:0], 1.0).shape == (0, 3)
+
+
+@pytest.mark.gpu
+def test_voxel_grid_export_matches_the_oracle(b2, orc, small_kitti):
+    scans, poses = small_kitti
+    # what save_map_to_ply accumulates: keyframe feature clouds moved to world coordinates (Estimator.cpp:1262-1276)
+    f = b2.FastVoxelFilter(0.5)
+    world = []
+    for s, T in zip(scans, poses):
+        feat = f.filter(s, 8)
+        T = np.asarray(T, np.float32)
+        world.append((feat @ T[:3, :3].T + T[:3, 3]).astype(np.float32))
+    acc = np.ascontiguousarray(np.concatenate(world))
+    rng = np.random.default_rng(8)
+    dense = rng.normal(0, 0.6, size=(30000, 3)).astype(np.float32)              # many points per voxel (> 32), negative coordinates
+    for cloud, leaf in ((acc, 0.4), (acc, 1.0), (dense, 0.25), (dense[:1], 0.1)):
+        g = b2.VoxelGrid()
+        g.setLeafSize(leaf)
+        g.setInputCloud(cloud)
+        got = g.filter()
+        ref = orc.voxel_grid_filter(cloud, leaf)
+        assert got.shape == ref.shape and got.shape[0] > 0
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    g = b2.VoxelGrid()
+    g.setLeafSize(0.0)
+    g.setInputCloud(acc)
+    assert g.filter().shape == (0, 3)
+    # the feature path still works after the export reused the K1 buffers
+    again = f.filter(scans[0], 8)
+    ref0, _ = orc.voxel_filter(scans[0][:, :3], 8, 0.5)
+    assert np.array_equal(again.view(np.uint32), ref0.view(np.uint32))
