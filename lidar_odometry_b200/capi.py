@@ -11,7 +11,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb2lo.so")
+LIB_PATH = os.environ.get("B2LO_LIB") or os.path.join(HERE, "libb2lo.so")   # B2LO_LIB: an alternative build of the same library (kernel A/B experiments)
 CSRC = os.path.join(HERE, "csrc")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "b2lo.h")
 

@@ -357,39 +357,39 @@ __device__ int shuffled_head(const PkoTables* T, const int* hits, int n, int j) 
 }
 
 // exp(x) for the Gaussian terms of the EM (x <= 0).  Branch-free and short: the argument is clamped at -708 (exp = 3e-308, an
-// additive nothing next to the O(1) mixture sums); x = (32 q + j) ln2/32 + r with |r| <= ln2/64 by the 1.5*2^52 rounding trick (no
-// float->int conversion) and a two-step Cody-Waite reduction; exp(x) = 2^q * 2^(j/32) * P(r) with a 32-entry table in shared
-// memory and a degree-6 Taylor polynomial in Estrin form (truncation 3e-18).  13 f64 instructions with a dependent chain of ~9,
-// against ~30 / ~25 for the library routine - the EM fixed point is one long chain of dependent f64 operations and its f64
-// issue slots are the bottleneck.  Relative error ~2e-16.
-__device__ __forceinline__ double em_exp(double x, const double* __restrict__ s_exp2) {
+// additive nothing next to the O(1) mixture sums); x = k ln2/2^10 + r with |r| <= ln2/2^11 = 3.4e-4 by the 1.5*2^52 rounding trick (no
+// float->int conversion) and a two-step Cody-Waite reduction; exp(x) = 2^q * T1[j1] * T2[j2] * (1 + r + r^2/2 + r^3/6 + r^4/24),
+// k = 2^10 q + 2^5 j1 + j2, with two 32-entry tables in shared memory (2^(j/32), 2^(j/1024): at most 2-way bank conflicts on the
+// per-lane random look-ups; 256-entry tables would allow a quadratic but conflict ~6-way); truncation 4e-20.
+// 11 f64 instructions with a dependent chain of 9, against ~30 / ~25 for the library routine - the EM fixed point is one long chain
+// of dependent f64 operations.  Relative error ~3e-16.  Same-box A/B against the previous one-table degree-6 form (14 instructions),
+// together with the third-order reciprocal and the fused accumulations below: 1250 -> 1202 SM cycles per EM iteration; the loop is
+// bound by the dependent chain (rsqrt -> exp -> exchange -> rcp -> 5 shuffle levels -> rcp), not by f64 issue slots.
+__device__ __forceinline__ double em_exp(double x, const double* __restrict__ s_t1, const double* __restrict__ s_t2) {
   x = fmax(x, -708.0);
   const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
-  const double tm = fma(x, 46.16624130844683, MAGIC);        // 32 / ln 2
+  const double tm = fma(x, 1477.3197218702985, MAGIC);        // 2^10 / ln 2
   const double kd = tm - MAGIC;
-  const int k = __double2loint(tm);                           // round(32 x / ln 2) in two's complement
-  double r = fma(-kd, 2.16608493865351192653e-02, x);         // ln2/32 hi
-  r = fma(-kd, 5.96317165397058656257e-12, r);                // ln2/32 lo
+  const int k = __double2loint(tm);                           // round(2^10 x / ln 2) in two's complement
+  double r = fma(-kd, 6.769015435155716e-04, x);             // ln2/2^10 hi
+  r = fma(-kd, 2.264694154146777e-20, r);                       // ln2/2^10 lo
+  const double t = s_t1[(k >> 5) & 31] * s_t2[k & 31];
   const double r2 = r * r;
-  const double p01 = 1.0 + r;
-  const double p23 = fma(r, 1.0 / 6.0, 0.5);
-  const double p45 = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-  const double q0 = fma(p23, r2, p01);
-  const double q1 = fma(r2, 1.0 / 720.0, p45);
-  const double pr = fma(q1, r2 * r2, q0) * s_exp2[k & 31];
-  return __hiloint2double(__double2hiint(pr) + (k >> 5) * 1048576, __double2loint(pr));
+  const double u = fma(r, 1.0 / 6.0, 0.5);
+  const double v = fma(r2, 1.0 / 24.0, u);
+  const double q = fma(r2, v, r);                             // e^r - 1 up to r^5/120 (4e-20)
+  const double pr = fma(t, q, t);
+  return __hiloint2double(__double2hiint(pr) + (k >> 10) * 1048576, __double2loint(pr));
 }
 
-// Reciprocal / reciprocal square root for the EM chain: hardware seed (rcp/rsqrt.approx.ftz.f64, ~2^-20) + two Newton steps
-// (error ~1e-16, not correctly rounded).  5 / 9 dependent f64 operations instead of the ~20-40 instructions of the IEEE
+// Reciprocal / reciprocal square root for the EM chain: hardware seed (rcp/rsqrt.approx.ftz.f64, ~2^-20) + one third-order step /
+// two Newton steps (error ~1e-16, not correctly rounded).  4 / 9 dependent f64 operations instead of the ~20-40 instructions of the IEEE
 // library routines; the EM only needs the ~1e-14 agreement discussed at k_icp_pko1.
 __device__ __forceinline__ double em_rcp(double x) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  double e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
-  return fma(r, e, r);
+  const double e = fma(-x, r, 1.0);       // one third-order step: r (1 + e + e^2), error e^3 ~ 2^-60
+  return fma(r, fma(e, e, e), r);
 }
 __device__ __forceinline__ double em_rsqrt(double x) {
   double y;
@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
   __shared__ double s_x[MAXS];
   __shared__ int s_head[MAXS];
   __shared__ double s_p[2][3][MAXS];
-  __shared__ double s_exp2[32];
+  __shared__ double s_t1[32], s_t2[32];   // exp tables: 2^(j/32), 2^(j/1024)
   __shared__ double s_dm[2][4];
   __shared__ double s_par[3][4];
   __shared__ int s_toff[PKO_TOFF];   // tile offsets of the first PKO_TOFF tiles: the sample draw's binary search stays on chip
@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
     if (!prm.use_pko) { if (tid == 0) { st->delta = prm.robust_delta; st->em_iters = 0; st->kmeans_iters = 0; st->scale = ext_scale; st->n_corr = ext_C; } return; }
     ns = T->sample_size < ext_C ? T->sample_size : ext_C;
     if (tid < ns) s_x[tid] = ext_sample[tid];
-    if (tid >= MAXS && tid < MAXS + 32) s_exp2[tid - MAXS] = T->exp2_32[tid - MAXS];
+    if (tid >= MAXS && tid < MAXS + 32) { s_t1[tid - MAXS] = T->exp2_t1[tid - MAXS]; s_t2[tid - MAXS] = T->exp2_t2[tid - MAXS]; }
     if (tid == 0) { st->scale = ext_scale; st->n_corr = ext_C; }
     __syncthreads();
   } else {
@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
   ns = T->sample_size < C ? T->sample_size : C;
   const int mode = C >= 65536 ? 2 : ((C & 1) ? 1 : 0);
   if (tid < MAXS) s_head[tid] = T->head_r[mode][tid];
-  if (tid >= MAXS && tid < MAXS + 32) s_exp2[tid - MAXS] = T->exp2_32[tid - MAXS];
+  if (tid >= MAXS && tid < MAXS + 32) { s_t1[tid - MAXS] = T->exp2_t1[tid - MAXS]; s_t2[tid - MAXS] = T->exp2_t2[tid - MAXS]; }
   __syncthreads();
   if (tid < ns) {
     // position tid of std::shuffle(iota(C), mt19937(42)): the LARGEST swap partner i in [128, C) that hit position tid
@@ -535,9 +535,7 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
   double x[EM_SPL], xx[EM_SPL];
   bool act[EM_SPL];
 #pragma unroll
-  double msk[EM_SPL];
-#pragma unroll
-  for (int k = 0; k < EM_SPL; ++k) { const int i = lane + 32 * k; act[k] = i < ns; x[k] = act[k] ? s_x[i] : 0.0; xx[k] = x[k] * x[k]; msk[k] = act[k] ? 1.0 : 0.0; }
+  for (int k = 0; k < EM_SPL; ++k) { const int i = lane + 32 * k; act[k] = i < ns; x[k] = act[k] ? s_x[i] : 0.0; xx[k] = x[k] * x[k]; }
   const double inv_ns = 1.0 / (double)ns;
   // 4. k-means (:336-389): mean0 = 0, mean1/2 = sample[dis(gen)]; every warp runs it redundantly (no exchange needed)
   double m1 = s_x[T->kmeans_seed[ns][0]], m2 = s_x[T->kmeans_seed[ns][1]];
@@ -592,7 +590,7 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
 #pragma unroll
     for (int k = 0; k < EM_SPL; ++k) {
       const double d = x[k] - mean;
-      p[k] = coef * em_exp((d * d) * hiv, s_exp2);
+      p[k] = (act[k] ? coef : 0.0) * em_exp((d * d) * hiv, s_t1, s_t2);   // idle samples: p = 0, so their responsibility is 0 below (no branch)
       s_p[ph][c][lane + 32 * k] = p[k];
     }
     if (lane == 0) s_dm[ph][c] = dm;
@@ -613,8 +611,8 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
     for (int k = 0; k < EM_SPL; ++k) sum[k] = em_rcp(sum[k]);   // sum 0 -> NaN propagates as in the reference
 #pragma unroll
     for (int k = 0; k < EM_SPL; ++k) {
-      const double r = (p[k] * sum[k]) * msk[k];
-      a3[0] += r; a3[1] += r * x[k]; a3[2] += r * xx[k];
+      const double r = p[k] * sum[k];
+      a3[0] += r; a3[1] = fma(r, x[k], a3[1]); a3[2] = fma(r, xx[k], a3[2]);
     }
     warp_sum_multi<3>(a3);
     // M-step, own component (:436-474); mean0 stays pinned at 0

@@ -26,7 +26,7 @@ struct FEntry { unsigned long long key; int cnt; unsigned int first; };  // filt
 
 struct PkoTables {                // built on the host once per context (b2lo_pko_host.cpp)
   double alpha[129], Z[129];      // alpha candidates and partition functions (AdaptiveMEstimator.cpp:218-241)
-  double exp2_32[32];             // 2^(j/32): table of the EM's exp (k_icp_pko1)
+  double exp2_t1[32], exp2_t2[32];     // 2^(j/32), 2^(j/1024): tables of the EM's exp (k_icp_pko1)
   int n_alpha;                    // num_alpha_segments + 1
   int kmeans_seed[129][2];        // uniform_int_distribution(0, ns-1)(mt19937(42)) draws for sample size ns
   int head_r[3][128];             // first swaps r_i (i < 128) of std::shuffle per mode (even, odd, large n)

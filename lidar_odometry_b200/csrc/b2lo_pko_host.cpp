@@ -77,7 +77,7 @@ void pko_build_host(const b2lo_icp_cfg* cfg, PkoTables* t, std::vector<int>* hit
     for (double x = 0.0; x <= cfg->truncated_threshold; x += 0.01) integral += kernel_w(cfg->pko_kernel_type, x, alpha) * 0.01;
     return std::max(integral, 1e-10);
   };
-  for (int j = 0; j < 32; ++j) t->exp2_32[j] = std::exp2((double)j / 32.0);
+  for (int j = 0; j < 32; ++j) { t->exp2_t1[j] = std::exp2((double)j / 32.0); t->exp2_t2[j] = std::exp2((double)j / 1024.0); }
   t->alpha[0] = cfg->min_scale_factor;
   t->Z[0] = Zf(t->alpha[0]);
   for (int i = 1; i <= S; ++i) {  // initialize_pko (:218-241)

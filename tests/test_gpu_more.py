@@ -1,0 +1,99 @@
+"""More GPU parity cases: voxel-boundary values through every key computation (K1 multiply-by-inverse, map keys and K2 L1 keys by true
+f32 division), and independent sequences sharing one GPU from several host threads (bench.py's throughput-mode leg) giving exactly the
+results of a lone sequence."""
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view(np.uint32) if a.dtype == np.float32 else a.view(np.uint64)
+
+
+def _boundary_points(voxel, seed, n=6000, span=400):
+    """Coordinates sitting exactly on multiples of `voxel` and of 3*voxel, one and two ulps either side, mixed signs, +-0."""
+    rng = np.random.default_rng(seed)
+    k = rng.integers(-span, span, size=(n, 3))
+    base = (k.astype(np.float64) * voxel).astype(np.float32)
+    step = rng.integers(-2, 3, size=(n, 3))
+    pts = base.copy()
+    for s in (1, 2):
+        up, dn = step == s, step == -s
+        for _ in range(s):
+            pts = np.where(up, np.nextafter(pts, np.float32(np.inf)), pts)
+            pts = np.where(dn, np.nextafter(pts, np.float32(-np.inf)), pts)
+    pts[::97] = np.float32(-0.0)
+    pts[5::101, 0] = np.float32(1e-42)      # subnormal
+    pts[7::103, 1] = np.float32(-1e-42)
+    return np.ascontiguousarray(pts.astype(np.float32))
+
+
+@pytest.mark.parametrize("voxel", [0.5, 0.4, 0.1, 0.3])
+def test_voxel_boundary_values_keys_bit_exact(orc, b2, voxel):
+    pts = _boundary_points(voxel, seed=int(voxel * 100))
+    # K1: floor(x * (1/voxel)) keys and sequential sums
+    f = b2.FastVoxelFilter(voxel)
+    ref, rk = orc.voxel_filter(pts, 1, voxel)
+    got = f.filter(pts, 1, want_keys=True)
+    assert np.array_equal(rk, f.last_keys) and np.array_equal(bits(ref), bits(got))
+    # map keys: floor(x / voxel) for L0, floor(x / (voxel * 3)) for the parents; container order, centroids, surfels
+    omap = orc.VoxelMap(voxel, 3, 0.1, True)
+    gmap = b2.VoxelMap(voxel)
+    gmap.SetPlanarityThreshold(0.1)
+    half = len(pts) // 2
+    for chunk in (pts[:half], pts[half:]):
+        omap.update(chunk, np.zeros(3), 1e6)
+        gmap.UpdateVoxelMap(chunk, [0.0, 0.0, 0.0], 1e6, True)
+    ok, oc, on = omap.export_l0()
+    gc, gk, gn = gmap.export_l0()
+    assert np.array_equal(ok, gk) and np.array_equal(on, gn) and np.array_equal(bits(oc), bits(gc))
+    # K2: L1 key of every query by true division, Z-order hash, probe result
+    icp = b2.IterativeClosestPointOptimizer(b2.ICPConfig())
+    T = np.eye(4, dtype=np.float32)
+    r = orc.icp_correspondences(omap, pts, T, 1.0)
+    g = icp.find_correspondences(gmap, pts, T)
+    assert np.array_equal(r["l1key"], g["l1key"]) and np.array_equal(r["morton"], g["morton"]) and np.array_equal(r["state"], g["state"])
+    # final-map grid keys: floor(x / leaf), std::map order
+    vg = b2.VoxelGrid()
+    vg.setLeafSize(voxel)
+    vg.setInputCloud(pts)
+    assert np.array_equal(bits(vg.filter()), bits(orc.voxel_grid_filter(pts, voxel)))
+
+
+def test_concurrent_sequences_on_one_gpu_match_a_lone_sequence(b2, small_kitti):
+    scans, _ = small_kitti
+    lone = b2.Odometry(b2.Context(0))
+    want = [lone.process(s) for s in scans]
+    S = 6
+    odos = [b2.Odometry(b2.Context(0)) for _ in range(S)]
+    got = [None] * S
+    errs = []
+    start = threading.Barrier(S)
+
+    def work(j):
+        try:
+            start.wait()
+            out = []
+            for rep in range(3):                 # three passes over the sequence per thread keeps the threads overlapping
+                if rep:
+                    odos[j].reset()
+                out = [odos[j].process(s) for s in scans]
+            got[j] = out
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+
+    th = [threading.Thread(target=work, args=(j,)) for j in range(S)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    for j in range(S):
+        for k, (a, b) in enumerate(zip(got[j], want)):
+            assert np.array_equal(bits(a["pose"]), bits(b["pose"])), (j, k)
+            assert (a["keyframe"], a["n_features"], a["n_corr"], a["n_iters"], a["l0"], a["l1"]) == \
+                   (b["keyframe"], b["n_features"], b["n_corr"], b["n_iters"], b["l0"], b["l1"]), (j, k)
