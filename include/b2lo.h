@@ -253,6 +253,15 @@ int b2lo_odom_lookahead(b2lo_odom* od, const float* xyz_next, size_t n, size_t s
  * address of the first RECORD of a file image in the given format and `n` as the record count (stride_floats is ignored; pass 3).
  * fmt = NULL returns to float-stride clouds.  Takes effect with the next scan. */
 int b2lo_odom_set_record_fmt(b2lo_odom* od, const b2lo_record_fmt* fmt);
+/* Throughput mode for batches of recorded sequences on one GPU: one scan on each of `count` INDEPENDENT sequences (own b2lo_odom, own
+ * b2lo_ctx / stream each; the caller created them), all scans resident in HBM.  Every sequence's launch sequence (one CUDA graph replay) is
+ * enqueued before the first result is waited for, so the sequences overlap on the device from a single host thread: one sequence keeps
+ * about one SM busy (the PKO fit and the Gauss-Newton finish are one-CTA latency chains), the other 147 are free.  next_xyz_dev / next_n
+ * (nullable, per sequence) announce the scans of the NEXT call like b2lo_odom_lookahead(..., on_device = 1).  Results are those of
+ * b2lo_odom_process_dev on each sequence alone, bit for bit.  Returns the first error, else the last soft outcome, else B2LO_OK; res[i]
+ * is filled per sequence (res[i].device_ms = that sequence's own CUDA-event time, overlapping with the others). */
+int b2lo_odom_process_batch_dev(b2lo_odom* const* ods, const float* const* xyz_dev, const size_t* n, const float* const* next_xyz_dev,
+                                const size_t* next_n, size_t stride_floats, int count, b2lo_odom_result* res);
 
 #ifdef __cplusplus
 }

@@ -23,7 +23,7 @@ from . import capi
 from .capi import B2LO_OK, B2LO_S_EMPTY, B2LO_S_INSUFFICIENT, IcpCfg, IcpStats, OdomCfg, OdomResult, RecordFmt, check
 
 __all__ = ["PointShardedICP", "Context", "default_context", "FastVoxelFilter", "FastVoxelGrid", "VoxelGrid", "VoxelMap", "ICPConfig", "AdaptiveMEstimatorConfig",
-           "AdaptiveMEstimator", "OptimizationStats", "IterativeClosestPointOptimizer", "Odometry", "SE3", "RecordFormat", "kitti_record_format", "parse_ply_header", "load_ply_point_cloud", "load_kitti_binary"]
+           "AdaptiveMEstimator", "OptimizationStats", "IterativeClosestPointOptimizer", "Odometry", "OdometryBatch", "SE3", "RecordFormat", "kitti_record_format", "parse_ply_header", "load_ply_point_cloud", "load_kitti_binary"]
 
 
 def _f32(a):
@@ -792,6 +792,35 @@ class Odometry:
         m.m_compute_surfels = bool(self.cfg.icp.use_surfel_correspondence)
         m.__class__ = _BorrowedVoxelMap
         return m
+
+
+class OdometryBatch:
+    """Independent sequences sharing one GPU, driven from one host thread (b2lo_odom_process_batch_dev): one scan per sequence per call,
+    every sequence on its own context / stream / map / CUDA graphs."""
+
+    def __init__(self, n_sequences, device=0, mid360=False):
+        self.ctxs = [Context(device) for _ in range(n_sequences)]
+        self.odos = [Odometry(c, mid360=mid360) for c in self.ctxs]
+        self._h = (C.c_void_p * n_sequences)(*[o.h for o in self.odos])
+        self._ptr = (C.c_void_p * n_sequences)()
+        self._n = (C.c_size_t * n_sequences)()
+        self._nptr = (C.c_void_p * n_sequences)()
+        self._nn = (C.c_size_t * n_sequences)()
+        self._res = (OdomResult * n_sequences)()
+
+    def process_dev(self, dev_ptrs, ns, stride_floats, next_ptrs=None, next_ns=None):
+        """dev_ptrs / ns: device address and point count of this call's scan of every sequence; next_*: the scans of the next call."""
+        k = len(self.odos)
+        for i in range(k):
+            self._ptr[i] = dev_ptrs[i]; self._n[i] = ns[i]
+            self._nptr[i] = next_ptrs[i] if next_ptrs is not None else None
+            self._nn[i] = next_ns[i] if next_ns is not None else 0
+        rc = check(capi.lib().b2lo_odom_process_batch_dev(self._h, self._ptr, self._n, self._nptr if next_ptrs is not None else None,
+                                                           self._nn if next_ptrs is not None else None, stride_floats, k, self._res))
+        return rc
+
+    def results(self):
+        return [Odometry._result(B2LO_OK if r.n_features else B2LO_S_EMPTY, r) for r in self._res]
 
 
 class _BorrowedVoxelMap(VoxelMap):

@@ -11,6 +11,7 @@
 #include <climits>
 #include <cstdarg>
 #include <cstring>
+#include <cstdlib>
 #include "b2lo_internal.h"
 
 namespace b2 {
@@ -222,6 +223,11 @@ int ctx_read_cloud(b2lo_ctx* ctx, const float4* src, const int* d_n, size_t n_ca
 }  // namespace b2
 
 using namespace b2;
+
+// Independent sequences overlap on the device only if their streams map to different hardware work queues; the driver's default is 8
+// connections, which aliases the streams of a batch (measured: 32 sequences 11.4 k -> 30.9 k scans/s with 32).  Takes effect when this
+// library is loaded before the process initialises CUDA; an explicit setting in the environment wins.
+namespace { struct ConnInit { ConnInit() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); } } g_conn_init; }
 
 extern "C" const char* b2lo_version(void) { return "b2lo 0.1 (sm_100a)"; }
 extern "C" const char* b2lo_last_error(void) { return g_err; }

@@ -33,6 +33,8 @@ struct b2lo_odom {
   const float* pre_src = nullptr; size_t pre_ns = 0, pre_stride = 0; int pre_set = 0;
   long long lookahead_hits = 0;
   bool allow_graph = true;
+  // a steady-state scan between its launch (steady_begin) and the read of its results (steady_finish)
+  struct Pending { bool active = false; int mode = 0, set = 0; const float* nx_src = nullptr; size_t nx_ns = 0, nx_stride = 0; double t1 = 0.0; } pend;
   bool has_fmt = false; b2lo_record_fmt fmt{};   // b2lo_odom_set_record_fmt: scans arrive as byte-record streams (KITTI .bin / PLY vertices)
   long long graph_launches = 0, graph_builds = 0, launches_per_graph = 0;
   OdomDev* d_out = nullptr;        // device result block of k_odom_decide
@@ -220,8 +222,10 @@ static void sp_set_fmt(ScanParams* sp, const b2lo_record_fmt* f) {
 
 // eff: record format of THIS call's source (nullptr: float-stride cloud, e.g. the staged copy of a pageable image); an announced next
 // scan is always read in place and therefore in the odometry's own format
-static int steady_scan(b2lo_odom* od, const float* src_dev, size_t ns, size_t sample_stride_floats, b2lo_odom_result* res, double t0,
-                       const b2lo_record_fmt* eff) {
+// steady_begin enqueues the whole scan (graph replay or plain launches) and returns without waiting; steady_finish waits for it and
+// absorbs the results.  b2lo_odom_process* call them back to back; b2lo_odom_process_batch_dev begins a scan on every sequence of a
+// batch before it finishes the first one, so that independent sequences overlap on the GPU without a host thread per sequence.
+static int steady_begin(b2lo_odom* od, const float* src_dev, size_t ns, size_t sample_stride_floats, double t0, const b2lo_record_fmt* eff) {
   b2lo_ctx* ctx = od->ctx;
   b2lo_map* map = od->map;
   cudaStream_t st = ctx->stream;
@@ -299,10 +303,26 @@ static int steady_scan(b2lo_odom* od, const float* src_dev, size_t ns, size_t sa
     if ((rc = enqueue_scan(od, flt_ns, cap, false, mode, set, !profiling))) return rc;
   }
   ctx->feat_set = set;
-  double t1 = now_us();
+  const double t1 = now_us();
+  ctx->host_us[1] += t1 - t0;
+  od->pend.active = true; od->pend.mode = mode; od->pend.set = set; od->pend.nx_src = nx_src; od->pend.nx_ns = nx_ns; od->pend.nx_stride = nx_stride;
+  od->pend.t1 = t1;
+  return B2LO_OK;
+}
+
+static int steady_finish(b2lo_odom* od, b2lo_odom_result* res) {
+  b2lo_ctx* ctx = od->ctx;
+  b2lo_map* map = od->map;
+  cudaStream_t st = ctx->stream;
+  int* hc = ctx->h_counts + 32;
+  int rc;
+  if (!od->pend.active) { set_error("odometry: no scan in flight"); return B2LO_E_ARG; }
+  od->pend.active = false;
+  const int mode = od->pend.mode, set = od->pend.set;
+  const float* nx_src = od->pend.nx_src; const size_t nx_ns = od->pend.nx_ns, nx_stride = od->pend.nx_stride;
   B2_CUDA(cudaStreamSynchronize(st));
   double t2 = now_us();
-  ctx->host_us[1] += t1 - t0; ctx->host_us[2] += t2 - t1;
+  ctx->host_us[2] += t2 - od->pend.t1;
   ctx->d2h_bytes += offsetof(IcpState, trace) + sizeof(int) + sizeof(OdomDev) + 8 * sizeof(int);
   if (mode == K1_NEXT) { od->pre_valid = true; od->pre_src = nx_src; od->pre_ns = nx_ns; od->pre_stride = nx_stride; od->pre_set = set ^ 1; }
   res->n_features = hc[0];
@@ -352,7 +372,8 @@ static int process_common(b2lo_odom* od, const float* src_dev, size_t ns, size_t
     res->keyframe = 1;
     res->icp_status = B2LO_S_EMPTY;
   } else {
-    rc = steady_scan(od, src_dev, ns, sample_stride_floats, res, t0, eff);
+    rc = steady_begin(od, src_dev, ns, sample_stride_floats, t0, eff);
+    if (!rc) rc = steady_finish(od, res);
     if (rc) return rc;
   }
   pose_to_T16(od->pose, res->pose);
@@ -432,6 +453,83 @@ extern "C" int b2lo_odom_process_dev(b2lo_odom* od, const float* xyz_dev, size_t
   const size_t ns = (n + S - 1) / S;
   const b2lo_record_fmt* F = od->has_fmt ? &od->fmt : nullptr;
   return process_timed(od, xyz_dev, ns, (F ? (size_t)F->record_bytes : stride_floats) * S, res, false, F);
+}
+
+// One scan on each of `count` independent sequences (own b2lo_odom, own context and stream each), all scans already in HBM: every
+// sequence's launch sequence is enqueued before the first one is waited for.
+extern "C" int b2lo_odom_process_batch_dev(b2lo_odom* const* ods, const float* const* xyz_dev, const size_t* n, const float* const* next_xyz_dev,
+                                           const size_t* next_n, size_t stride_floats, int count, b2lo_odom_result* res) {
+  if (!ods || !xyz_dev || !n || !res || count < 0) return B2LO_E_ARG;
+  if (stride_floats < 3) return B2LO_E_ARG;
+  for (int a = 0; a < count; ++a) {
+    if (!ods[a]) return B2LO_E_ARG;
+    for (int b = 0; b < a; ++b) if (ods[a] == ods[b] || ods[a]->ctx == ods[b]->ctx) { set_error("batch: sequences must not share a handle or a context"); return B2LO_E_ARG; }
+  }
+  std::vector<int> state((size_t)count, 0);   // 0 nothing in flight, 1 begun
+  int first_err = B2LO_OK, soft = B2LO_OK;
+  static const bool dbg = getenv("B2LO_BATCH_DEBUG") != nullptr;
+  static double acc_begin = 0.0, acc_finish = 0.0, acc_wait = 0.0; static long long acc_calls = 0;
+  const double tb0 = now_us();
+  // phase 1: enqueue
+  for (int a = 0; a < count; ++a) {
+    b2lo_odom* od = ods[a];
+    b2lo_ctx* ctx = od->ctx;
+    std::memset(&res[a], 0, sizeof res[a]);
+    if (!xyz_dev[a] || n[a] == 0) { soft = B2LO_S_EMPTY; continue; }
+    od->map->mu.lock(); ctx->mu.lock();
+    cudaSetDevice(ctx->device);
+    const size_t S = (size_t)(od->cfg.point_stride < 1 ? 1 : od->cfg.point_stride);
+    const size_t ns = (n[a] + S - 1) / S;
+    const b2lo_record_fmt* F = od->has_fmt ? &od->fmt : nullptr;
+    const size_t sstride = (F ? (size_t)F->record_bytes : stride_floats) * S;
+    int rc;
+    if (!od->initialized) {   // the first frame of a sequence is synchronous (map build, no ICP)
+      rc = process_timed(od, xyz_dev[a], ns, sstride, &res[a], false, F);
+      ctx->mu.unlock(); od->map->mu.unlock();
+      if (rc < 0 && !first_err) first_err = rc; else if (rc > 0) soft = rc;
+      continue;
+    }
+    if (next_xyz_dev && next_n && next_xyz_dev[a] && next_n[a]) {   // b2lo_odom_lookahead(od, next, n, stride, on_device = 1)
+      od->la_src = next_xyz_dev[a]; od->la_ns = (next_n[a] + S - 1) / S; od->la_stride = sstride; od->la_valid = true;
+    }
+    if (cudaEventRecord(ctx->ev0, ctx->stream) != cudaSuccess) rc = B2LO_E_CUDA;
+    else rc = steady_begin(od, xyz_dev[a], ns, sstride, now_us(), F);
+    if (!rc && cudaEventRecord(ctx->ev1, ctx->stream) != cudaSuccess) rc = B2LO_E_CUDA;
+    if (rc) {
+      od->pend.active = false;
+      ctx->mu.unlock(); od->map->mu.unlock();
+      if (rc < 0 && !first_err) first_err = rc;
+      continue;
+    }
+    state[(size_t)a] = 1;
+  }
+  const double tb1 = now_us();
+  double wait0 = 0.0;
+  for (int a = 0; a < count; ++a) wait0 -= ods[a]->ctx->host_us[2];
+  // phase 2: wait and absorb, in the same order
+  for (int a = 0; a < count; ++a) {
+    if (!state[(size_t)a]) continue;
+    b2lo_odom* od = ods[a];
+    b2lo_ctx* ctx = od->ctx;
+    cudaSetDevice(ctx->device);
+    int rc = steady_finish(od, &res[a]);
+    if (rc >= 0) {
+      if (cudaEventSynchronize(ctx->ev1) == cudaSuccess) cudaEventElapsedTime(&res[a].device_ms, ctx->ev0, ctx->ev1);
+      pose_to_T16(od->pose, res[a].pose);
+      res[a].l0 = od->map->n0; res[a].l1 = od->map->n1;
+    }
+    ctx->mu.unlock(); od->map->mu.unlock();
+    if (rc < 0 && !first_err) first_err = rc; else if (rc > 0) soft = rc;
+  }
+  if (dbg) {
+    for (int a = 0; a < count; ++a) wait0 += ods[a]->ctx->host_us[2];
+    const double tb2 = now_us();
+    acc_begin += tb1 - tb0; acc_finish += tb2 - tb1; acc_wait += wait0;
+    if (++acc_calls % 50 == 0)
+      std::fprintf(stderr, "[b2lo batch] %d sequences: enqueue %.1f us/call, finish %.1f us/call of which stream waits %.1f us\n", count, acc_begin / acc_calls,
+                   acc_finish / acc_calls, acc_wait / acc_calls), acc_begin = acc_finish = acc_wait = 0.0, acc_calls = 0;
+  }
+  return first_err ? first_err : soft;
 }
 
 extern "C" int b2lo_odom_lookahead(b2lo_odom* od, const float* xyz_next, size_t n, size_t stride_floats, int on_device) {

@@ -97,3 +97,29 @@ def test_concurrent_sequences_on_one_gpu_match_a_lone_sequence(b2, small_kitti):
             assert np.array_equal(bits(a["pose"]), bits(b["pose"])), (j, k)
             assert (a["keyframe"], a["n_features"], a["n_corr"], a["n_iters"], a["l0"], a["l1"]) == \
                    (b["keyframe"], b["n_features"], b["n_corr"], b["n_iters"], b["l0"], b["l1"]), (j, k)
+
+
+def test_batch_call_matches_lone_sequences(b2, small_kitti):
+    """b2lo_odom_process_batch_dev: several sequences advanced by one call per scan (with look-ahead), each bit-identical to the sequence
+    processed alone; the sequences run the scans in different rotations so that they are not in lock-step."""
+    import torch
+    scans, _ = small_kitti
+    dev = [torch.from_numpy(np.ascontiguousarray(s)).cuda() for s in scans]
+    S, n = 5, len(scans)
+    order = [[(k + j) % n for k in range(n)] for j in range(S)]
+    want = []
+    for j in range(S):
+        o = b2.Odometry(b2.Context(0))
+        want.append([o.process_dev(dev[i].data_ptr(), scans[i].shape[0], 4) for i in order[j]])
+    bat = b2.OdometryBatch(S, 0)
+    for k in range(n):
+        cur = [order[j][k] for j in range(S)]
+        nxt = [order[j][k + 1] for j in range(S)] if k + 1 < n else None
+        bat.process_dev([dev[i].data_ptr() for i in cur], [scans[i].shape[0] for i in cur], 4,
+                        None if nxt is None else [dev[i].data_ptr() for i in nxt], None if nxt is None else [scans[i].shape[0] for i in nxt])
+        for j, r in enumerate(bat.results()):
+            w = want[j][k]
+            assert np.array_equal(bits(r["pose"]), bits(w["pose"])), (j, k)
+            assert (r["keyframe"], r["n_features"], r["n_corr"], r["n_iters"], r["l0"], r["l1"]) == \
+                   (w["keyframe"], w["n_features"], w["n_corr"], w["n_iters"], w["l0"], w["l1"]), (j, k)
+    assert sum(o.graph_stats()["replays"] for o in bat.odos) > 0
