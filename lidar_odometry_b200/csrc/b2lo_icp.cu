@@ -977,7 +977,7 @@ int icp_prepare(b2lo_ctx* ctx, const b2lo_icp_cfg* cfg) {
 // enqueue a whole optimize() on the context stream.  T_init16 (host) is copied through the pinned state
 // block unless init_pose_on_device (then st->T_init was written by a previous kernel).
 int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_cap, const float* T_init16, const b2lo_icp_cfg* cfg,
-            bool init_pose_on_device) {
+            bool init_pose_on_device, bool restore_on_failure) {
   b2lo_ctx* ctx = map->ctx;
   if (cfg->max_iterations < 1 || cfg->max_iterations > B2LO_MAX_ITERS) { set_error("max_iterations must be in [1,%d]", B2LO_MAX_ITERS); return B2LO_E_ARG; }
   const bool surfel = cfg->use_surfel_correspondence != 0;
@@ -1038,8 +1038,9 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
     prof_end(ctx);
     ctx->launches += cfg->use_adaptive_m_estimator ? 4 : 3;
   }
-  k_icp_end<<<1, 32, 0, s>>>(ctx->d_icp);
-  ctx->launches += 2;
+  // the per-scan driver's decision kernel never reads the pose of a failed optimize (it falls back to the motion-model guess itself)
+  if (restore_on_failure) { k_icp_end<<<1, 32, 0, s>>>(ctx->d_icp); ctx->launches++; }
+  ctx->launches += 1;
   B2_CUDA(cudaGetLastError());
   return B2LO_OK;
 }

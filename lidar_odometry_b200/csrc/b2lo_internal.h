@@ -184,7 +184,8 @@ int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sam
 int ctx_stage_records_h2d(b2lo_ctx* ctx, const void* bytes, size_t n_records, const b2lo_record_fmt* fmt, size_t take_every);
 int icp_build_pko(b2lo_ctx* ctx, const b2lo_icp_cfg* cfg);
 int icp_prepare(b2lo_ctx* ctx, const b2lo_icp_cfg* cfg);
-int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_cap, const float* T_init16, const b2lo_icp_cfg* cfg, bool init_pose_on_device);
+int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_cap, const float* T_init16, const b2lo_icp_cfg* cfg, bool init_pose_on_device,
+            bool restore_on_failure = true);
 int map_update_dev(b2lo_map* map, const float4* d_world, const int* d_n, size_t n_cap, const float sensor_f[3], float radius_sq, int rehash = 0,
                    const int* gate = nullptr, const float* sensor_dev = nullptr);
 int map_absorb_counts(b2lo_map* map);

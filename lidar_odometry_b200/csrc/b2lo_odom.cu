@@ -89,6 +89,21 @@ __global__ void k_odom_decide(const IcpState* st, const ScanParams* __restrict__
   out->icp_status = status;
 }
 
+// The scan's read-back in ONE launch: the ICP state header, the pose/keyframe block, the map counters and the feature count are written
+// straight into the context's page-locked host mirrors (cudaMallocHost memory is device-addressable under UVA), instead of four D2H
+// copy nodes at the end of the replayed graph (a small copy costs more than a small kernel there).  ~0.3 KB over PCIe, posted writes.
+__global__ void k_odom_readback(const IcpState* __restrict__ st, int icp_words, const OdomDev* __restrict__ out, const int* __restrict__ ctr,
+                                const int* __restrict__ d_nfeat, int* h_icp, int* h_out, int* h_counts) {
+  const int t = threadIdx.x;
+  const int* a = reinterpret_cast<const int*>(st);
+  for (int i = t; i < icp_words; i += blockDim.x) h_icp[i] = a[i];
+  const int* b = reinterpret_cast<const int*>(out);
+  for (int i = t; i < (int)(sizeof(OdomDev) / sizeof(int)); i += blockDim.x) h_out[i] = b[i];
+  if (t < 8) h_counts[t] = ctr[t];
+  if (t == 8) h_counts[32] = *d_nfeat;
+  __threadfence_system();
+}
+
 extern "C" void b2lo_default_odom_cfg(b2lo_odom_cfg* c, int mid360) {  // config/kitti.yaml / config/mid360.yaml
   if (!c) return;
   c->voxel_size = mid360 ? 0.4f : 0.5f;
@@ -188,7 +203,7 @@ static int enqueue_scan(b2lo_odom* od, size_t flt_ns, size_t cap, bool in_graph,
   }
   float4* feat = ctx->feat(set);
   int* nfeat = ctx->nfeat(set);
-  if (!rc) rc = icp_run(map, feat, nfeat, cap, ctx->h_sp->T_init, &od->cfg.icp, false);
+  if (!rc) rc = icp_run(map, feat, nfeat, cap, ctx->h_sp->T_init, &od->cfg.icp, false, /*restore_on_failure=*/false);
   ctx->sp_preloaded = false;
   if (!rc) {
     k_odom_decide<<<1, 32, 0, st>>>(ctx->d_icp, ctx->d_sp, nfeat, od->d_out);
@@ -204,10 +219,11 @@ static int enqueue_scan(b2lo_odom* od, size_t flt_ns, size_t cap, bool in_graph,
     if (rc > 0) rc = B2LO_OK;
   }
   if (!rc) {
-    cudaError_t e = cudaMemcpyAsync(ctx->h_icp, ctx->d_icp, offsetof(IcpState, trace), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(od->h_out, od->d_out, sizeof(OdomDev), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_counts, map->d.ctr, 8 * sizeof(int), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_counts + 32, nfeat, sizeof(int), cudaMemcpyDeviceToHost, st);
+    static_assert(offsetof(IcpState, trace) % sizeof(int) == 0 && sizeof(OdomDev) % sizeof(int) == 0, "read-back copies whole words");
+    k_odom_readback<<<1, 128, 0, st>>>(ctx->d_icp, (int)(offsetof(IcpState, trace) / sizeof(int)), od->d_out, map->d.ctr, nfeat,
+                                       reinterpret_cast<int*>(ctx->h_icp), reinterpret_cast<int*>(od->h_out), ctx->h_counts);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("odometry: read-back failed: %s", cudaGetErrorString(e)); rc = B2LO_E_CUDA; }
   }
   // always re-join a forked branch, also on errors: a capture must not end with an unjoined stream
