@@ -268,6 +268,11 @@ def stress_leg(ctx, api, capi, target_voxels, peak, peak_kind):
         probes[kind] = {"queries": nq, "accepted": ncorr, "avg_launch_us": 1e3 * ms_k2.value / max(n_k2.value, 1), "achieved_gbs": k2_gbs,
                         "frac_of_hbm_peak": k2_gbs / peak, "peak_kind": f"of {peak_kind}", "queries_per_s": nq * n_k2.value / max(ms_k2.value * 1e-3, 1e-12),
                         "algorithmic_bytes_per_query": ALGO_BYTES_PER_QUERY, "l2": "flushed between launches; L1 hash table > L2"}
+    # bare ceiling of the access pattern on this GPU (tools/gather_probe.cu, profiles/r01_gather_probe.txt): 2^20 independent random 32 B-sector
+    # gathers from a 128 MiB table, nothing else read or written, take 26.6 us (39.4 G sectors/s)
+    probes["random"].update({"random_sector_gather_ceiling_us": 26.6, "frac_of_random_gather_ceiling": 26.6 / max(probes["random"]["avg_launch_us"], 1e-9),
+                             "ceiling_source": "tools/gather_probe.cu on the same GPU model, profiles/r01_gather_probe.txt"})
+    probes["coherent"].update({"coherent_gather_ceiling_us": 10.2, "ceiling_source": "tools/gather_probe.cu, profiles/r01_gather_probe.txt (bare gathers only; K2 also streams 28 B/query)"})
     probes["random"].update({"traffic_bytes_per_launch": 115305984, "traffic_source": "ncu, profiles/r01_ncu_k2_stress_final.csv: 2.3x the algorithmic bytes (64 B DRAM access per random 32 B sector + 12 B/query of results); 115.3 MB in 33.2 us = 3.5 TB/s = 53 % of the measured HBM peak in traffic terms: bound by random-sector DRAM access"})
     # bulk rebuild (ApplyTransformAndRehash + RecomputeAllSurfels, VoxelMap.cpp:264-366; runs after pose-graph corrections): transform every
     # L0 centroid, re-key, merge collisions, rebuild L1 and refit every surfel.  Algorithmic bytes per L0 voxel: 16 B read + 16 B written
@@ -540,7 +545,7 @@ def main():
     k2_avg_s = 1e-3 * k2["ms_total"] / max(k2["launches"], 1)
     achieved = k2_bytes_per_launch / max(k2_avg_s, 1e-12) / 1e9
     roof = {"bound": "hbm", "kernel": "k_icp_corr (K2 surfel correspondence)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "peak_kind": f"of {peak_kind}", "traffic": 209664, "traffic_source": "dram__bytes_read+write of k_icp_corr at this size, ncu --set full (profiles/r01_ncu_full_top_kernels.csv, cold cache)",
+            "peak_kind": f"of {peak_kind}", "traffic": 416256, "traffic_source": "dram__bytes_read+write of k_icp_corr at this size, ncu --set full (profiles/r01_ncu_full_final.csv, cold cache)",
             "algorithmic_bytes_per_launch": k2_bytes_per_launch,
             "avg_launch_us": 1e6 * k2_avg_s, "launches": k2["launches"],
             "note": "KITTI-shaped scans give ~4k queries per launch (~190 KB): the launch is latency-bound, not bandwidth-bound; see DESIGN.md"}
