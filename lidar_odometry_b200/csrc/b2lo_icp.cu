@@ -106,9 +106,17 @@ __device__ __forceinline__ void corr_issue(const MapDev& M, const float* sR, con
   q.ea = __ldg(e);        // key (8 B), n.x, n.y
   q.eb = __ldg(e + 1);    // n.z, c.x, c.y, c.z  (same 32 B sector)
 }
-template <int DEPTH, int MINB>
+struct PkoTables;
+// the PKO fit (definition below, at k_icp_pko1): with FUSE the CTA that finishes LAST continues straight into it, so one Gauss-Newton
+// iteration is three launches instead of four (one kernel boundary and one launch less on the critical path; a converged iteration's
+// no-op launch disappears with it).  The body reads what the other CTAs wrote through L2 (__ldcg) behind a fence and a ticket.
+__device__ __noinline__ void pko1_body(const int* d_npts, IcpState* st, IcpParams prm, const double* res, const int* cidx, const int* tilecnt,
+                                       int* tileoff, const PkoTables* T, const int* hits, double* gmm_out, const double* ext_sample, int ext_C,
+                                       double ext_scale, const double* tilesum);
+template <int DEPTH, int MINB, bool FUSE>
 __global__ void __launch_bounds__(TILE, MINB) k_icp_corr(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, IcpState* st,
-                                                   IcpParams prm, double* res, int* slot_out, int* cidx, int* tilecnt, double* tilesum) {
+                                                   IcpParams prm, double* res, int* slot_out, int* cidx, int* tilecnt, double* tilesum,
+                                                   int* tileoff, const PkoTables* T, const int* hits, double* gmm_out) {
   __shared__ float sR[9], sT[3];
   __shared__ int s_cnt[2][TILE / 32];
   __shared__ double s_sum[2][TILE / 32][2];
@@ -125,10 +133,10 @@ __global__ void __launch_bounds__(TILE, MINB) k_icp_corr(MapDev M, const float4*
   if (tid < 9) sR[tid] = pose_v; else if (tid < 12) sT[tid - 9] = pose_v;
   __syncthreads();
   const int ntiles = (npts + TILE - 1) / TILE;
-  if (tile >= ntiles) return;
+  if (!FUSE && tile >= ntiles) return;
   const uint32_t mask = (1u << M.l1_log2cap) - 1u;
   CorrStage cur;
-  corr_issue(M, sR, sT, p1, tile * TILE + tid < npts, cur);
+  if (tile < ntiles) corr_issue(M, sR, sT, p1, tile * TILE + tid < npts, cur);
   if (DEPTH >= 3 && tile + G < ntiles) p1 = pts[(tile + G) * TILE + tid];
   int ph = 0;
   for (; tile < ntiles; tile += G) {
@@ -186,6 +194,20 @@ __global__ void __launch_bounds__(TILE, MINB) k_icp_corr(MapDev M, const float4*
     ph ^= 1;   // the other buffer is rewritten only after the next barrier: nobody still reads it then
     if (more) cur = nxt;
     p1 = p2;
+  }
+  if (FUSE) {
+    __shared__ int s_last;
+    __threadfence();                 // this CTA's tiles are visible before its ticket is
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned int t = atomicAdd(&st->ticket_corr, 1u);
+      s_last = (t == gridDim.x - 1);
+      if (s_last) st->ticket_corr = 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    pko1_body(d_npts, st, prm, res, cidx, tilecnt, tileoff, T, hits, gmm_out, nullptr, 0, 0.0, tilesum);
   }
 }
 
@@ -426,11 +448,9 @@ template <int V> __device__ __forceinline__ void warp_sum_multi(double (&v)[V]) 
 //     terms takes the slow denormal path).
 // The reference sums left to right and divides; the two evaluation orders agree to ~1e-14 relative, which can move
 // the discrete outputs (iteration counts, arg-min alpha) only on near-exact ties - tests/ assert they match the oracle.
-__global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict__ d_npts, IcpState* st, IcpParams prm, const double* __restrict__ res,
-                                                           const int* __restrict__ slot, const int* __restrict__ cidx, const int* __restrict__ tilecnt,
-                                                           int* tileoff, const PkoTables* __restrict__ T, const int* __restrict__ hits, double* gmm_out,
-                                                           const double* __restrict__ ext_sample, int ext_C, double ext_scale,
-                                                           const double* __restrict__ tilesum) {
+__device__ __noinline__ void pko1_body(const int* d_npts, IcpState* st, IcpParams prm, const double* res, const int* cidx, const int* tilecnt,
+                                       int* tileoff, const PkoTables* T, const int* hits, double* gmm_out, const double* ext_sample, int ext_C,
+                                       double ext_scale, const double* tilesum) {
   if (st->done) return;
   __shared__ int sm[40];
   __shared__ double smd[40];
@@ -461,7 +481,7 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
   int base = 0;
   for (int t0 = 0; t0 < ntiles; t0 += blockDim.x) {
     int t = t0 + tid;
-    int c = t < ntiles ? tilecnt[t] : 0;
+    int c = t < ntiles ? __ldcg(&tilecnt[t]) : 0;
     int tot;
     int e = block_excl_scan(c, &tot, sm);
     if (t < ntiles) { tileoff[t] = base + e; if (t < PKO_TOFF) s_toff[t] = base + e; }
@@ -479,7 +499,7 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
   if (st->iter == 0) {
     // population sigma / 6 from the per-tile raw moments K2 left behind (var = E[r^2] - mean^2)
     double a1 = 0.0, a2 = 0.0;
-    for (int t = tid; t < ntiles; t += blockDim.x) { a1 += tilesum[2 * t]; a2 += tilesum[2 * t + 1]; }
+    for (int t = tid; t < ntiles; t += blockDim.x) { a1 += __ldcg(&tilesum[2 * t]); a2 += __ldcg(&tilesum[2 * t + 1]); }
     a1 = block_sum_d(a1, smd);
     a2 = block_sum_d(a2, smd);
     const double mean = a1 / (double)C;
@@ -524,8 +544,8 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
     } else {
       while (tl < th) { int mid = (tl + th + 1) >> 1; if (tileoff[mid] <= ci) tl = mid; else th = mid - 1; }
     }
-    int q = cidx[tl * ctile + (ci - tileoff[tl])];
-    s_x[tid] = res[q] / sdiv;
+    int q = __ldcg(&cidx[tl * ctile + (ci - tileoff[tl])]);
+    s_x[tid] = __ldcg(&res[q]) / sdiv;
   }
   __syncthreads();
   }
@@ -639,6 +659,15 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
     for (int m = 0; m < 3; ++m) Pr += s_par[m][2] * gauss_pdf(rr, s_par[m][0], s_par[m][1]);
     gmm_out[16 + k] = Pr + 1e-10;
   }
+}
+// the fit as a launch of its own (KDTree mode, loop-closure ICP, point-sharded mode, profiling runs)
+__global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict__ d_npts, IcpState* st, IcpParams prm, const double* __restrict__ res,
+                                                           const int* __restrict__ slot, const int* __restrict__ cidx, const int* __restrict__ tilecnt,
+                                                           int* tileoff, const PkoTables* __restrict__ T, const int* __restrict__ hits, double* gmm_out,
+                                                           const double* __restrict__ ext_sample, int ext_C, double ext_scale,
+                                                           const double* __restrict__ tilesum) {
+  (void)slot;
+  pko1_body(d_npts, st, prm, res, cidx, tilecnt, tileoff, T, hits, gmm_out, ext_sample, ext_C, ext_scale, tilesum);
 }
 
 // one CTA per alpha candidate i = 1..S (blockIdx.x + 1); thread k handles r_k = dr * (1 + k); the last CTA takes the arg-min
@@ -877,7 +906,7 @@ __global__ void k_icp_begin(IcpState* st, const ScanParams* __restrict__ sp) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     for (int i = 0; i < 16; ++i) st->T_init[i] = sp->T_init[i];
     for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) st->R[i * 3 + j] = st->T_init[i * 4 + j]; st->t[i] = st->T_init[i * 4 + 3]; }
-    st->iter = 0; st->done = 0; st->status = B2LO_OK; st->n_corr = 0; st->scale = 1.0; st->delta = 0.0; st->ticket = 0u;
+    st->iter = 0; st->done = 0; st->status = B2LO_OK; st->n_corr = 0; st->scale = 1.0; st->delta = 0.0; st->ticket = 0u; st->ticket_corr = 0u;
     st->num_iterations = 0; st->converged = 0; st->initial_cost = 0.0; st->final_cost = 0.0; st->em_iters = 0; st->kmeans_iters = 0;
   }
 }
@@ -906,24 +935,26 @@ __global__ void k_icp_taps(MapDev M, const float4* __restrict__ pts, int npts, c
 }
 
 // ---------------------------------------------------------------------------------------------------
-typedef void (*corr_kernel_t)(MapDev, const float4*, const int*, IcpState*, IcpParams, double*, int*, int*, int*, double*);
+typedef void (*corr_kernel_t)(MapDev, const float4*, const int*, IcpState*, IcpParams, double*, int*, int*, int*, double*, int*, const PkoTables*, const int*, double*);
 // K2 launch geometry for a sequence built for `ctiles_cap` tiles: the kernel is persistent and software-pipelined, so exactly one
 // resident wave.  (A cp.async-streamed variant with deeper thread-private shared-memory rings was tried for dense clouds and was
 // slower: the 16 B LDGSTS copies saturate the MIO queue - ncu: mio_throttle 9.4 stalls per issue, 44.8 us vs 33.2 us per 2^20 probes.)
 struct CorrLaunch { corr_kernel_t k; int grid; size_t smem; };
-static CorrLaunch corr_launch(b2lo_ctx* ctx, int ctiles_cap) {
-  static int per_sm = 0;   // a property of the compiled kernel, identical on every device of this build
-  static corr_kernel_t kern = nullptr;
-  if (per_sm == 0) {
-    kern = k_icp_corr<3, 1>;   // 80 registers, 3 CTAs/SM; capping at 64 registers for 4 CTAs/SM measured the same (37.1 vs 37.7 us)
+static CorrLaunch corr_launch(b2lo_ctx* ctx, int ctiles_cap, bool fuse_pko = false) {
+  static int per_sm[2] = {0, 0};   // a property of the compiled kernel, identical on every device of this build
+  static corr_kernel_t kern[2] = {nullptr, nullptr};
+  const int f = fuse_pko ? 1 : 0;
+  if (per_sm[f] == 0) {
+    // 80 registers, 3 CTAs/SM; capping at 64 registers for 4 CTAs/SM measured the same (37.1 vs 37.7 us)
+    kern[f] = fuse_pko ? (corr_kernel_t)k_icp_corr<3, 1, true> : (corr_kernel_t)k_icp_corr<3, 1, false>;
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, TILE, 0) != cudaSuccess || n < 1) { cudaGetLastError(); n = 2; }
-    per_sm = n;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern[f], TILE, 0) != cudaSuccess || n < 1) { cudaGetLastError(); n = 2; }
+    per_sm[f] = n;
   }
   if (ctiles_cap < 1) ctiles_cap = 1;
-  const int resident = ctx->sm_count * per_sm;
+  const int resident = ctx->sm_count * per_sm[f];
   CorrLaunch L;
-  L.k = kern; L.grid = ctiles_cap < resident ? ctiles_cap : resident; L.smem = 0;
+  L.k = kern[f]; L.grid = ctiles_cap < resident ? ctiles_cap : resident; L.smem = 0;
   return L;
 }
 
@@ -1003,7 +1034,10 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
   if (grid_knn > ctx->sm_count * 8) grid_knn = ctx->sm_count * 8;
   if (grid_knn < 1) grid_knn = 1;
   int ctiles_cap = (int)((npts_cap + prm.ctile - 1) / prm.ctile);
-  const CorrLaunch cl = corr_launch(ctx, ctiles_cap);
+  // the last CTA of the correspondence kernel runs the PKO fit itself; per-kernel profiling keeps the two launches apart
+  // (scan-sized clouds only: the fused kernel needs 88 registers, which would cost a dense cloud one resident CTA per SM)
+  const bool fuse = surfel && !(ctx->prof && ctx->prof->on) && npts_cap <= 65536;
+  const CorrLaunch cl = corr_launch(ctx, ctiles_cap, fuse);
   int ntiles_cap = (int)((npts_cap + TILE - 1) / TILE);
   int grid = ntiles_cap < 1 ? 1 : (ntiles_cap > ctx->i_max_blocks ? ctx->i_max_blocks : ntiles_cap);
   double* gmm = ctx->i_partial + (size_t)ctx->i_max_blocks * 28;      // 9 GMM doubles, then P(r_k) at [16, 116)
@@ -1012,7 +1046,8 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
   for (int it = 0; it < cfg->max_iterations; ++it) {
     if (surfel) {
       prof_begin(ctx, PS_CORR);
-      cl.k<<<cl.grid, TILE, cl.smem, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum);
+      cl.k<<<cl.grid, TILE, cl.smem, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum,
+                                          ctx->i_blkoff, ctx->d_pko, ctx->d_pko_hits, gmm);
       prof_end(ctx);
     } else {
       prof_begin(ctx, PS_KNN);
@@ -1023,10 +1058,12 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
       prof_end(ctx);
       ctx->launches += 2;
     }
-    prof_begin(ctx, PS_PKO1);
-    k_icp_pko1<<<1, PKO_THREADS, 0, s>>>(d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff, ctx->d_pko,
-                                         ctx->d_pko_hits, gmm, nullptr, 0, 0.0, ctx->i_tilesum);
-    prof_end(ctx);
+    if (!fuse) {
+      prof_begin(ctx, PS_PKO1);
+      k_icp_pko1<<<1, PKO_THREADS, 0, s>>>(d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff, ctx->d_pko,
+                                           ctx->d_pko_hits, gmm, nullptr, 0, 0.0, ctx->i_tilesum);
+      prof_end(ctx);
+    }
     if (cfg->use_adaptive_m_estimator) {
       prof_begin(ctx, PS_PKO2);
       k_icp_pko2<<<cfg->num_alpha_segments, 128, 0, s>>>(ctx->d_icp, prm, ctx->d_pko, gmm, js, tk);
@@ -1036,7 +1073,7 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
     if (surfel) k_icp_gn<true><<<grid, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, nullptr, ctx->i_partial, nullptr);
     else k_icp_gn<false><<<grid, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->k_plane, ctx->i_partial, nullptr);
     prof_end(ctx);
-    ctx->launches += cfg->use_adaptive_m_estimator ? 4 : 3;
+    ctx->launches += (cfg->use_adaptive_m_estimator ? 4 : 3) - (fuse ? 1 : 0);
   }
   // the per-scan driver's decision kernel never reads the pose of a failed optimize (it falls back to the motion-model guess itself)
   if (restore_on_failure) { k_icp_end<<<1, 32, 0, s>>>(ctx->d_icp); ctx->launches++; }
@@ -1287,7 +1324,8 @@ extern "C" int b2lo_icp_shard_corr(b2lo_map* map, const b2lo_icp_cfg* cfg, doubl
   const CorrLaunch cl = corr_launch(ctx, ctiles);
   cudaStream_t s = ctx->stream;
   prof_begin(ctx, PS_CORR);
-  cl.k<<<cl.grid, TILE, cl.smem, s>>>(map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum);
+  cl.k<<<cl.grid, TILE, cl.smem, s>>>(map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum,
+                                      nullptr, nullptr, nullptr, nullptr);
   prof_end(ctx);
   k_shard_stats<<<1, 256, 0, s>>>(ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_blkcnt, ctx->i_blkoff, stats3_dev, ctx->i_tilesum);
   ctx->launches += 2;

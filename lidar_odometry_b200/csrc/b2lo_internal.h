@@ -46,6 +46,7 @@ struct IcpState {                 // lives in device memory, one per context
   double scale, delta;
   int em_iters, kmeans_iters;
   unsigned int ticket;            // last-block election of the GN reduction
+  unsigned int ticket_corr;       // last-block election of the correspondence kernel (fused PKO fit)
   int num_iterations; int converged; double initial_cost, final_cost;
   b2lo_iter_trace trace[B2LO_MAX_ITERS];
   long long dbg[32];                // clock64 stamps of the single-CTA phases (tools/gpu_phase_clocks.py)
