@@ -36,6 +36,14 @@ __device__ __forceinline__ void transform_point(const float* R, const float* t, 
   w[2] = ((R[6] * x + R[7] * y) + R[8] * z) + t[2] * 1.0f;
 }
 
+// state of a fresh optimize (one thread): pose = initial transform, counters cleared
+__device__ __forceinline__ void icp_state_begin(IcpState* st, const ScanParams* sp) {
+  for (int i = 0; i < 16; ++i) st->T_init[i] = sp->T_init[i];
+  for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) st->R[i * 3 + j] = st->T_init[i * 4 + j]; st->t[i] = st->T_init[i * 4 + 3]; }
+  st->iter = 0; st->done = 0; st->status = B2LO_OK; st->n_corr = 0; st->scale = 1.0; st->delta = 0.0; st->ticket = 0u; st->ticket_corr = 0u;
+  st->num_iterations = 0; st->converged = 0; st->initial_cost = 0.0; st->final_cost = 0.0; st->em_iters = 0; st->kmeans_iters = 0;
+}
+
 // returns slot (>=0) if the L1 voxel of w holds a surfel; fills n, c and the key taps
 __device__ __forceinline__ int surfel_probe(const MapDev& M, const float* w, float* n, float* c, int* key3, unsigned long long* morton) {
   int kx = voxel_coord(w[0], M.scale1), ky = voxel_coord(w[1], M.scale1), kz = voxel_coord(w[2], M.scale1);
@@ -116,17 +124,23 @@ __device__ __noinline__ void pko1_body(const int* d_npts, IcpState* st, IcpParam
 template <int DEPTH, int MINB, bool FUSE>
 __global__ void __launch_bounds__(TILE, MINB) k_icp_corr(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, IcpState* st,
                                                    IcpParams prm, double* res, int* slot_out, int* cidx, int* tilecnt, double* tilesum,
-                                                   int* tileoff, const PkoTables* T, const int* hits, double* gmm_out) {
+                                                   int* tileoff, const PkoTables* T, const int* hits, double* gmm_out, const ScanParams* sp_first) {
+  // sp_first != nullptr (FUSE only): this is the first correspondence pass of an optimize and no k_icp_begin ran - the pose comes from the
+  // scan parameter block, a stale `done` flag is ignored, and the elected last CTA initialises the state before it enters the fit
   __shared__ float sR[9], sT[3];
   __shared__ int s_cnt[2][TILE / 32];
   __shared__ double s_sum[2][TILE / 32][2];
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const int G = gridDim.x;
   // every loop-invariant load and the first point go out together (the buffers are sized in whole tiles, see ctx_reserve_points)
-  const int done = st->done;
+  const bool first = FUSE && sp_first != nullptr;
+  const int done = first ? 0 : st->done;
   const int npts = *d_npts;
   float pose_v = 0.0f;
-  if (tid < 12) pose_v = tid < 9 ? st->R[tid] : st->t[tid - 9];
+  if (tid < 12) {
+    if (first) pose_v = tid < 9 ? sp_first->T_init[(tid / 3) * 4 + tid % 3] : sp_first->T_init[(tid - 9) * 4 + 3];
+    else pose_v = tid < 9 ? st->R[tid] : st->t[tid - 9];
+  }
   int tile = blockIdx.x;
   float4 p1 = pts[tile * TILE + tid];
   if (done) return;
@@ -207,6 +221,10 @@ __global__ void __launch_bounds__(TILE, MINB) k_icp_corr(MapDev M, const float4*
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    if (first) {   // k_icp_begin, by the one CTA that is still running
+      if (tid == 0) icp_state_begin(st, sp_first);
+      __syncthreads();
+    }
     pko1_body(d_npts, st, prm, res, cidx, tilecnt, tileoff, T, hits, gmm_out, nullptr, 0, 0.0, tilesum);
   }
 }
@@ -903,12 +921,7 @@ __global__ void __launch_bounds__(TILE) k_icp_gn(MapDev M, const float4* __restr
 }
 
 __global__ void k_icp_begin(IcpState* st, const ScanParams* __restrict__ sp) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    for (int i = 0; i < 16; ++i) st->T_init[i] = sp->T_init[i];
-    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) st->R[i * 3 + j] = st->T_init[i * 4 + j]; st->t[i] = st->T_init[i * 4 + 3]; }
-    st->iter = 0; st->done = 0; st->status = B2LO_OK; st->n_corr = 0; st->scale = 1.0; st->delta = 0.0; st->ticket = 0u; st->ticket_corr = 0u;
-    st->num_iterations = 0; st->converged = 0; st->initial_cost = 0.0; st->final_cost = 0.0; st->em_iters = 0; st->kmeans_iters = 0;
-  }
+  if (threadIdx.x == 0 && blockIdx.x == 0) icp_state_begin(st, sp);
 }
 // on failure the reference leaves optimized_transform = initial (ICP.cpp:266,301)
 __global__ void k_icp_end(IcpState* st) {
@@ -935,7 +948,8 @@ __global__ void k_icp_taps(MapDev M, const float4* __restrict__ pts, int npts, c
 }
 
 // ---------------------------------------------------------------------------------------------------
-typedef void (*corr_kernel_t)(MapDev, const float4*, const int*, IcpState*, IcpParams, double*, int*, int*, int*, double*, int*, const PkoTables*, const int*, double*);
+typedef void (*corr_kernel_t)(MapDev, const float4*, const int*, IcpState*, IcpParams, double*, int*, int*, int*, double*, int*, const PkoTables*, const int*, double*,
+                              const ScanParams*);
 // K2 launch geometry for a sequence built for `ctiles_cap` tiles: the kernel is persistent and software-pipelined, so exactly one
 // resident wave.  (A cp.async-streamed variant with deeper thread-private shared-memory rings was tried for dense clouds and was
 // slower: the 16 B LDGSTS copies saturate the MIO queue - ncu: mio_throttle 9.4 stalls per issue, 44.8 us vs 33.2 us per 2^20 probes.)
@@ -1029,7 +1043,6 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
     for (int i = 0; i < 16; ++i) ctx->h_sp->T_init[i] = T_init16[i];
     if ((rc = sp_upload(ctx, offsetof(ScanParams, T_init), sizeof(float) * 16))) return rc;
   }
-  k_icp_begin<<<1, 32, 0, s>>>(ctx->d_icp, ctx->d_sp);
   int grid_knn = (int)((npts_cap + 7) / 8);   // one warp per query, 8 per CTA
   if (grid_knn > ctx->sm_count * 8) grid_knn = ctx->sm_count * 8;
   if (grid_knn < 1) grid_knn = 1;
@@ -1038,6 +1051,7 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
   // (scan-sized clouds only: the fused kernel needs 88 registers, which would cost a dense cloud one resident CTA per SM)
   const bool fuse = surfel && !(ctx->prof && ctx->prof->on) && npts_cap <= 65536;
   const CorrLaunch cl = corr_launch(ctx, ctiles_cap, fuse);
+  if (!fuse) { k_icp_begin<<<1, 32, 0, s>>>(ctx->d_icp, ctx->d_sp); ctx->launches++; }   // fused: the first correspondence pass initialises the state
   int ntiles_cap = (int)((npts_cap + TILE - 1) / TILE);
   int grid = ntiles_cap < 1 ? 1 : (ntiles_cap > ctx->i_max_blocks ? ctx->i_max_blocks : ntiles_cap);
   double* gmm = ctx->i_partial + (size_t)ctx->i_max_blocks * 28;      // 9 GMM doubles, then P(r_k) at [16, 116)
@@ -1047,7 +1061,7 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
     if (surfel) {
       prof_begin(ctx, PS_CORR);
       cl.k<<<cl.grid, TILE, cl.smem, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum,
-                                          ctx->i_blkoff, ctx->d_pko, ctx->d_pko_hits, gmm);
+                                          ctx->i_blkoff, ctx->d_pko, ctx->d_pko_hits, gmm, (fuse && it == 0) ? ctx->d_sp : nullptr);
       prof_end(ctx);
     } else {
       prof_begin(ctx, PS_KNN);
@@ -1077,7 +1091,6 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
   }
   // the per-scan driver's decision kernel never reads the pose of a failed optimize (it falls back to the motion-model guess itself)
   if (restore_on_failure) { k_icp_end<<<1, 32, 0, s>>>(ctx->d_icp); ctx->launches++; }
-  ctx->launches += 1;
   B2_CUDA(cudaGetLastError());
   return B2LO_OK;
 }
@@ -1325,7 +1338,7 @@ extern "C" int b2lo_icp_shard_corr(b2lo_map* map, const b2lo_icp_cfg* cfg, doubl
   cudaStream_t s = ctx->stream;
   prof_begin(ctx, PS_CORR);
   cl.k<<<cl.grid, TILE, cl.smem, s>>>(map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum,
-                                      nullptr, nullptr, nullptr, nullptr);
+                                      nullptr, nullptr, nullptr, nullptr, nullptr);
   prof_end(ctx);
   k_shard_stats<<<1, 256, 0, s>>>(ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_blkcnt, ctx->i_blkoff, stats3_dev, ctx->i_tilesum);
   ctx->launches += 2;
