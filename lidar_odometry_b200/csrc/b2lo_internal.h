@@ -187,8 +187,9 @@ int icp_build_pko(b2lo_ctx* ctx, const b2lo_icp_cfg* cfg);
 int icp_prepare(b2lo_ctx* ctx, const b2lo_icp_cfg* cfg);
 int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_cap, const float* T_init16, const b2lo_icp_cfg* cfg, bool init_pose_on_device,
             bool restore_on_failure = true);
-int map_update_dev(b2lo_map* map, const float4* d_world, const int* d_n, size_t n_cap, const float sensor_f[3], float radius_sq, int rehash = 0,
-                   const int* gate = nullptr, const float* sensor_dev = nullptr);
+// local / T16_dev (optional): d_world is an OUTPUT, filled inside the update with `local` moved by the device-resident pose T16_dev
+int map_update_dev(b2lo_map* map, float4* d_world, const int* d_n, size_t n_cap, const float sensor_f[3], float radius_sq, int rehash = 0,
+                   const int* gate = nullptr, const float* sensor_dev = nullptr, const float4* local = nullptr, const float* T16_dev = nullptr);
 int map_absorb_counts(b2lo_map* map);
 int map_reserve(b2lo_map* map, size_t need_l0, size_t need_upd);
 int map_refresh_counts(b2lo_map* map);

@@ -216,12 +216,22 @@ __global__ void __launch_bounds__(1024) k_cull_fix(MapDev M, const uint8_t* flag
 }
 
 // ---- insert ---------------------------------------------------------------------------------------------
-__global__ void k_ins_probe(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_m, int* us, int* pslot, int* nxt, FEntry* atab, int alog2,
-                            int* alist) {
+// local != nullptr: the update's points are the feature cloud `local` moved by the row-major pose T16 (transform_point_cloud,
+// PointCloudUtils.cpp:120-121, the arithmetic of k_transform_dev); they are computed here and left in `pts` for the kernels behind
+__global__ void k_ins_probe(MapDev M, float4* pts, const int* __restrict__ d_m, int* us, int* pslot, int* nxt, FEntry* atab, int alog2,
+                            int* alist, const float4* __restrict__ local, const float* __restrict__ T16) {
   if (M.gate && !*M.gate) return;
   const int m = *d_m;
+  float tm[12];
+  if (local) for (int i = 0; i < 12; ++i) tm[i] = T16[i];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
-    float4 p = pts[i];
+    float4 p;
+    if (local) {
+      const float4 q = local[i];
+      p = make_float4(((tm[0] * q.x + tm[1] * q.y) + tm[2] * q.z) + tm[3] * 1.0f, ((tm[4] * q.x + tm[5] * q.y) + tm[6] * q.z) + tm[7] * 1.0f,
+                      ((tm[8] * q.x + tm[9] * q.y) + tm[10] * q.z) + tm[11] * 1.0f, 0.0f);
+      pts[i] = p;
+    } else p = pts[i];
     int x = voxel_coord(p.x, M.voxel), y = voxel_coord(p.y, M.voxel), z = voxel_coord(p.z, M.voxel);
     int ax = voxel_coord(p.x, M.scale1), ay = voxel_coord(p.y, M.scale1), az = voxel_coord(p.z, M.scale1);
     if (!key_in_range(x, y, z) || !(p.x == p.x) || !(p.y == p.y) || !(p.z == p.z)) { atomicOr(&us[US_ERR], ERR_RANGE); pslot[i] = -1; continue; }
@@ -560,7 +570,10 @@ __global__ void __launch_bounds__(1024) k_upd_close(MapDev M, int* us, const int
   const int P = purge_ran ? us[US_NPURGE] : 0;
   const int n_all = us[US_N0] + ((us[US_ERR] & ERR_CAP) ? 0 : us[US_NNEW]);
   if (P == 0) {
-    if (threadIdx.x == 0) { M.ctr[CT_N0] = n_all; M.ctr[CT_ERR] = us[US_ERR]; M.ctr[6] = 0; M.ctr[7] = 0; }
+    const int err = us[US_ERR];
+    __syncthreads();   // everybody has read the update's scalars: the block goes back to all-zero for the next update (no memset node)
+    if (threadIdx.x == 0) { M.ctr[CT_N0] = n_all; M.ctr[CT_ERR] = err; M.ctr[6] = 0; M.ctr[7] = 0; }
+    if (threadIdx.x < US_COUNT) us[threadIdx.x] = 0;
     return;
   }
   for (int t = threadIdx.x; t < P; t += blockDim.x) {
@@ -609,8 +622,9 @@ __global__ void __launch_bounds__(1024) k_upd_close(MapDev M, int* us, const int
     atomicAdd(&M.ctr[CT_TOMB0], k);
     M.ctr[CT_ERR] = us[US_ERR];
     M.ctr[6] = k; M.ctr[7] = P;   // purge size of this update (debug / statistics)
-    us[US_KPURGE] = k;
   }
+  __syncthreads();
+  if (threadIdx.x < US_COUNT) us[threadIdx.x] = 0;   // self-cleaning state block (see the P == 0 exit)
 }
 
 // ---- table maintenance --------------------------------------------------------------------------------------
@@ -819,8 +833,8 @@ static int grid_for(size_t n, int threads) { size_t b = (n + threads - 1) / thre
 
 // UpdateVoxelMap on a world-frame cloud already on the device (float4 stream).  n_cap = host-known upper
 // bound of *d_n.  Ends with a counter read-back (one synchronisation).
-int map_update_dev(b2lo_map* m, const float4* d_world, const int* d_n, size_t n_cap, const float sensor[3], float radius_sq, int rehash,
-                   const int* gate, const float* sensor_dev) {
+int map_update_dev(b2lo_map* m, float4* d_world, const int* d_n, size_t n_cap, const float sensor[3], float radius_sq, int rehash,
+                   const int* gate, const float* sensor_dev, const float4* local, const float* T16_dev) {
   b2lo_ctx* ctx = m->ctx;
   if (n_cap == 0) return B2LO_S_EMPTY;
   int rc = map_reserve(m, m->n0 + n_cap, n_cap);
@@ -836,7 +850,7 @@ int map_update_dev(b2lo_map* m, const float4* d_world, const int* d_n, size_t n_
     ctx->sim_attr_set = true;
   }
   prof_begin(ctx, PS_MAP);
-  B2_CUDA(cudaMemsetAsync(us, 0, US_COUNT * sizeof(int), st));
+  // the per-update scalar block `us` is all-zero here: zeroed at creation / Clear and again by the closing kernel of every update
   const int n0 = m->graph_mode ? -1 : (int)m->n0;
   if ((n0 > 0 || m->graph_mode) && !rehash) {
     int tiles = (int)(((m->graph_mode ? (size_t)d.l0_cap : m->n0) + 1023) / 1024);
@@ -855,7 +869,7 @@ int map_update_dev(b2lo_map* m, const float4* d_world, const int* d_n, size_t n_
   int gw = grid_for(n_cap * 32, 256);   // one warp per point
   int* plist = m->a_list; unsigned int* pfirst = reinterpret_cast<unsigned int*>(m->a_list + m->upd_cap);
   int* pord = m->a_list + 2 * m->upd_cap; int* poff = m->a_list + 3 * m->upd_cap;
-  k_ins_probe<<<gm, 256, 0, st>>>(d, d_world, d_n, us, m->u_pslot, m->u_next, m->a_tab, m->a_log2cap, m->a_slots);
+  k_ins_probe<<<gm, 256, 0, st>>>(d, d_world, d_n, us, m->u_pslot, m->u_next, m->a_tab, m->a_log2cap, m->a_slots, local, T16_dev);
   k_ins_apply<<<gm, 256, 0, st>>>(d, d_world, d_n, m->u_pslot, m->u_next, m->u_isnew, m->u_pts, rehash);
   const bool bulk = n_cap > BULK_UPD && !gate;
   if (bulk) {
@@ -915,6 +929,7 @@ extern "C" int b2lo_map_create(b2lo_ctx* ctx, float voxel_size, int hierarchy_fa
   d.planarity_thr = planarity_threshold; d.compute_surfels = compute_surfels ? 1 : 0;
   if (cudaMalloc(&d.ctr, 16 * sizeof(int)) != cudaSuccess || cudaMalloc(&m->u_state, US_COUNT * sizeof(int)) != cudaSuccess) { delete m; return B2LO_E_NOMEM; }
   cudaMemsetAsync(d.ctr, 0, 16 * sizeof(int), ctx->stream);
+  cudaMemsetAsync(m->u_state, 0, US_COUNT * sizeof(int), ctx->stream);
   size_t hint = l0_capacity_hint ? l0_capacity_hint : (1u << 16);
   int rc = alloc_l0_table(m, ceil_log2(hint * 4));
   if (!rc) rc = alloc_l1_table(m, ceil_log2(hint));
@@ -947,6 +962,7 @@ extern "C" int b2lo_map_clear(b2lo_map* m) {
   B2_CUDA(cudaMemsetAsync(m->d.l1_tab, 0xFF, m->tcap1 * sizeof(L1Entry), st));
   B2_CUDA(cudaMemsetAsync(m->d.l1_meta, 0, m->tcap1 * sizeof(L1Meta), st));
   B2_CUDA(cudaMemsetAsync(m->d.ctr, 0, 16 * sizeof(int), st));
+  B2_CUDA(cudaMemsetAsync(m->u_state, 0, US_COUNT * sizeof(int), st));
   B2_CUDA(cudaStreamSynchronize(st));
   m->n0 = m->n1 = m->tomb0 = m->tomb1 = 0;
   return B2LO_OK;

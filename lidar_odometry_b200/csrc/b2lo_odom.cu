@@ -208,13 +208,13 @@ static int enqueue_scan(b2lo_odom* od, size_t flt_ns, size_t cap, bool in_graph,
   if (!rc) {
     k_odom_decide<<<1, 32, 0, st>>>(ctx->d_icp, ctx->d_sp, nfeat, od->d_out);
     ctx->launches++;
-    rc = ctx_transform_dev(ctx, feat, nfeat, cap, od->d_out->pose, &od->d_out->keyframe, ctx->d_world);
   }
   if (!rc) {
     const double md = od->cfg.max_range * 1.2;  // Estimator.cpp:455
     const float zero3[3] = {0.0f, 0.0f, 0.0f};
     map->graph_mode = true;   // cull kernels take the live voxel count from the device counter, grids from the capacity
-    rc = map_update_dev(map, ctx->d_world, nfeat, cap, zero3, (float)(md * md), 0, &od->d_out->keyframe, od->d_out->pose);
+    // the feature cloud is moved to the final pose inside the update's first insert kernel (transform_point_cloud, Estimator.cpp:165-169)
+    rc = map_update_dev(map, ctx->d_world, nfeat, cap, zero3, (float)(md * md), 0, &od->d_out->keyframe, od->d_out->pose, feat, od->d_out->pose);
     map->graph_mode = false;
     if (rc > 0) rc = B2LO_OK;
   }
