@@ -132,6 +132,8 @@ int ctx_reserve_points(b2lo_ctx* ctx, size_t n) {
       (rc = dev_alloc(&ctx->f_lead, cap)) || (rc = dev_alloc(&ctx->f_bucket, cap)) || (rc = dev_alloc(&ctx->f_ordered, cap)) ||
       (rc = dev_alloc(&ctx->f_packed, cap)) || (rc = dev_alloc(&ctx->f_sorted, cap)))
     return rc;
+  // the filter's scratch hash cleans itself after every run (k_flt_reduce); it only needs the idle pattern once
+  B2_CUDA(cudaMemsetAsync(ctx->f_tab, 0xFF, sizeof(FEntry) << l2, ctx->stream));
   if ((rc = dev_alloc(&ctx->i_res, cap)) || (rc = dev_alloc(&ctx->i_slot, cap)) || (rc = dev_alloc(&ctx->i_cidx, cap + 1024)) ||
       (rc = dev_alloc(&ctx->i_blkcnt, cap / 256 + 8)) || (rc = dev_alloc(&ctx->i_blkoff, cap / 256 + 8)) ||
       (rc = dev_alloc(&ctx->i_tilesum, 2 * (cap / 256 + 8))))

@@ -189,7 +189,9 @@ __global__ void k_flt_rank(const FEntry* __restrict__ tab, const int* __restrict
 // one thread per voxel adds its points in input order (sequential f32, VoxelMap.h:88-91) and writes centroid and key
 __global__ void k_flt_reduce(const int* __restrict__ d_nvox, const int* __restrict__ seg_start, const int* __restrict__ seg_cnt,
                              const float4* __restrict__ sorted, const int* __restrict__ lead_of_vid, const int* __restrict__ slot_of,
-                             const FEntry* __restrict__ tab, float4* out, unsigned long long* out_key, const ScanParams* __restrict__ sp) {
+                             FEntry* tab, float4* out, unsigned long long* out_key, const ScanParams* __restrict__ sp) {
+  // the scratch hash is self-cleaning: every entry in use belongs to exactly one voxel, whose thread puts it back to idle (all 0xFF)
+  // after taking the key - no 0.5 MB memset node per scan
   const int nv = *d_nvox;
   const unsigned int mode = sp->flt_mode;
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
@@ -206,7 +208,9 @@ __global__ void k_flt_reduce(const int* __restrict__ d_nvox, const int* __restri
         wgt = tot;
       }
       out[v] = make_float4(c.x, c.y, c.z, wgt);
-      out_key[v] = tab[slot_of[lead_of_vid[v]]].key;
+      FEntry* e = &tab[slot_of[lead_of_vid[v]]];
+      out_key[v] = e->key;
+      e->key = KEY_EMPTY; e->cnt = -1; e->first = 0xFFFFFFFFu;
       continue;
     }
     float sx = 0.0f, sy = 0.0f, sz = 0.0f;
@@ -221,7 +225,9 @@ __global__ void k_flt_reduce(const int* __restrict__ d_nvox, const int* __restri
     for (; q < m; ++q) { float4 p = sorted[b + q]; sx += p.x; sy += p.y; sz += p.z; }
     const float ic = 1.0f / (float)(unsigned)m;
     out[v] = make_float4(sx * ic, sy * ic, sz * ic, 0.0f);
-    out_key[v] = tab[slot_of[lead_of_vid[v]]].key;
+    FEntry* e = &tab[slot_of[lead_of_vid[v]]];
+    out_key[v] = e->key;
+    e->key = KEY_EMPTY; e->cnt = -1; e->first = 0xFFFFFFFFu;
   }
 }
 
@@ -249,7 +255,7 @@ int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sam
     for (int a = 0; a < 3; ++a) ctx->h_sp->flt_off[a] = fmt ? (&fmt->off_x)[a] : 0u;
     if ((rc = sp_upload(ctx, 0, offsetof(ScanParams, T_init)))) return rc;
   }
-  B2_CUDA(cudaMemsetAsync(ctx->f_tab, 0xFF, sizeof(FEntry) << log2cap, st));
+  // ctx->f_tab is all-idle (0xFF) here: memset when allocated, put back by k_flt_reduce after every run
   int blocks = (int)((ctx->pts_cap + 255) / 256); if (blocks > 1184) blocks = 1184;
   const ScanParams* sp = ctx->d_sp;
   const bool prof = st == ctx->stream;   // the per-stage events live on the context stream
