@@ -123,3 +123,22 @@ def test_batch_call_matches_lone_sequences(b2, small_kitti):
             assert (r["keyframe"], r["n_features"], r["n_corr"], r["n_iters"], r["l0"], r["l1"]) == \
                    (w["keyframe"], w["n_features"], w["n_corr"], w["n_iters"], w["l0"], w["l1"]), (j, k)
     assert sum(o.graph_stats()["replays"] for o in bat.odos) > 0
+
+
+def test_degenerate_scans_inside_a_sequence(b2, orc, small_kitti):
+    """Scans that yield no features (all points non-finite) or too few correspondences (a tiny far-away cloud) in the middle of a
+    sequence: the driver (fused first correspondence pass, gated map update, graph replay) follows the oracle pipeline and recovers."""
+    scans, _ = small_kitti
+    nan_scan = np.full((5000, 4), np.nan, np.float32)
+    far = np.zeros((4000, 4), np.float32)
+    far[:, :3] = np.random.default_rng(5).normal(0, 0.3, (4000, 3)).astype(np.float32) + np.array([900.0, 900.0, 50.0], np.float32)
+    seq = [scans[0], scans[1], nan_scan, scans[2], far, scans[3], scans[4]]
+    odo, pipe = b2.Odometry(b2.Context(0)), orc.Pipeline()
+    for k, s in enumerate(seq):
+        g, o = odo.process(s), pipe.process(s)
+        assert g["ok"] == o["ok"] and g["n_features"] == o["n_features"], (k, g, o)
+        assert g["keyframe"] == o["keyframe"] and g["icp_ok"] == o["icp_ok"], (k, g, o)
+        if o["ok"]:
+            assert np.linalg.norm(g["pose"][:3, 3].astype(np.float64) - o["pose"][:3, 3]) < 1e-3, k
+    l0o, l1o, _ = pipe.map().counts()
+    assert abs(int(g["l0"]) - l0o) <= max(3, l0o // 500)
