@@ -342,7 +342,12 @@ static int steady_finish(b2lo_odom* od, b2lo_odom_result* res) {
   ctx->d2h_bytes += offsetof(IcpState, trace) + sizeof(int) + sizeof(OdomDev) + 8 * sizeof(int);
   if (mode == K1_NEXT) { od->pre_valid = true; od->pre_src = nx_src; od->pre_ns = nx_ns; od->pre_stride = nx_stride; od->pre_set = set ^ 1; }
   res->n_features = hc[0];
-  if (hc[0] == 0) return B2LO_S_EMPTY;   // nothing was changed: the gated update was switched off, the pose state is untouched
+  if (hc[0] == 0) {   // nothing was changed: the gated update was switched off, the pose state is untouched
+    res->icp_status = B2LO_S_EMPTY;
+    pose_to_T16(od->pose, res->pose);
+    res->l0 = map->n0; res->l1 = map->n1;
+    return B2LO_S_EMPTY;
+  }
   res->icp_status = od->h_out->icp_status;
   res->n_corr = ctx->h_icp->n_corr; res->n_iters = ctx->h_icp->num_iterations;
   od->pose = pose_from_T16(od->h_out->pose);
@@ -378,7 +383,7 @@ static int process_common(b2lo_odom* od, const float* src_dev, size_t ns, size_t
     B2_CUDA(cudaStreamSynchronize(st));
     ctx->d2h_bytes += sizeof(int);
     res->n_features = hc[0];
-    if (hc[0] == 0) return B2LO_S_EMPTY;  // Estimator.cpp:131-134
+    if (hc[0] == 0) { res->icp_status = B2LO_S_EMPTY; pose_to_T16(od->pose, res->pose); return B2LO_S_EMPTY; }  // Estimator.cpp:131-134
     od->pose = pose_identity();
     od->velocity = pose_identity();
     rc = create_keyframe(od, ns);
