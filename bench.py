@@ -515,6 +515,18 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * K / float(te.item())
 
+    # ---- throughput mode on every rank (N > 1): 32 independent sequences per GPU through b2lo_odom_process_batch_dev, no collective;
+    # aggregate = all sequences of all ranks / the slowest rank's wall time between barriers (informational, `value` stays one sequence per GPU)
+    batched_all = None
+    if world > 1 and args.concurrent:
+        S_b = 32
+        barrier()
+        bl = batch_leg(api, local, dev_args, S_b, K, W)
+        tb = torch.tensor([S_b * K / bl["scans_per_s"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        batched_all = {"sequences_per_gpu": S_b, "gpus": world, "scans_per_s": world * S_b * K / float(tb.item()), "driver": bl["driver"],
+                       "timing": "slowest rank's wall clock around its K batch calls"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -592,7 +604,7 @@ def main():
                     "d2h_bytes_per_step": (d1 - d0) / K},
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "stage_ms_per_scan": {k: v["ms_total"] / K for k, v in stage.items()},
             "dominant_kernel_group": dominant, "cpu_baseline": cpu,
-            "concurrent_sequences_one_gpu": conc, "final_map_export": export, "large_map_stress": stress, "kdtree_mid360": mid360}
+            "concurrent_sequences_one_gpu": conc, "batched_sequences_all_gpus": batched_all, "final_map_export": export, "large_map_stress": stress, "kdtree_mid360": mid360}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
