@@ -129,9 +129,10 @@ __global__ void __launch_bounds__(TILE, MINB) k_icp_corr(MapDev M, const float4*
   // scan parameter block, a stale `done` flag is ignored, and the elected last CTA initialises the state before it enters the fit
   __shared__ float sR[9], sT[3];
   __shared__ int s_cnt[2][TILE / 32];
-  __shared__ double s_sum[2][TILE / 32][2];
+  __shared__ double s_sum[TILE / 32][2];
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const int G = gridDim.x;
+  double m1 = 0.0, m2 = 0.0;
   // every loop-invariant load and the first point go out together (the buffers are sized in whole tiles, see ctx_reserve_points)
   const bool first = FUSE && sp_first != nullptr;
   const int done = first ? 0 : st->done;
@@ -190,24 +191,35 @@ __global__ void __launch_bounds__(TILE, MINB) k_icp_corr(MapDev M, const float4*
     if (in) { slot_out[i] = s; res[i] = r; }
     const bool ok = s >= 0;
     const unsigned bal = __ballot_sync(0xffffffffu, ok);
-    double a1 = ok ? r : 0.0, a2 = ok ? r * r : 0.0;   // sum r, sum r^2 over the accepted queries (residual scale, ICP.cpp:304-316)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o); }
-    if (lane == 0) { s_cnt[ph][wrp] = __popc(bal); s_sum[ph][wrp][0] = a1; s_sum[ph][wrp][1] = a2; }
+    // sum r, sum r^2 over the accepted queries (residual scale, ICP.cpp:304-316): carried per thread across this CTA's tiles and reduced
+    // ONCE behind the loop (20 shuffles + 10 f64 adds per tile and warp less); the CTA's total is filed under its first tile
+    if (ok) { m1 += r; m2 += r * r; }
+    if (lane == 0) s_cnt[ph][wrp] = __popc(bal);
     __syncthreads();
     const int cw = lane < TILE / 32 ? s_cnt[ph][lane] : 0;            // lane l holds the count of warp l
     const int total = __reduce_add_sync(0xffffffffu, cw);
     const int before = __reduce_add_sync(0xffffffffu, lane < wrp ? cw : 0);
     if (ok) cidx[tile * TILE + before + __popc(bal & ((1u << lane) - 1u))] = i;
     if (tid == 0) {
-      double sa = 0.0, sb = 0.0;
-#pragma unroll
-      for (int w2 = 0; w2 < TILE / 32; ++w2) { sa += s_sum[ph][w2][0]; sb += s_sum[ph][w2][1]; }
-      tilecnt[tile] = total; tilesum[2 * tile] = sa; tilesum[2 * tile + 1] = sb;
+      tilecnt[tile] = total;
+      if (tile != (int)blockIdx.x) { tilesum[2 * tile] = 0.0; tilesum[2 * tile + 1] = 0.0; }
     }
     ph ^= 1;   // the other buffer is rewritten only after the next barrier: nobody still reads it then
     if (more) cur = nxt;
     p1 = p2;
+  }
+  if ((int)blockIdx.x < ntiles) {   // this CTA's residual moments -> the slot of its first tile
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { m1 += __shfl_xor_sync(0xffffffffu, m1, o); m2 += __shfl_xor_sync(0xffffffffu, m2, o); }
+    __syncthreads();   // the last tile's readers of s_sum's neighbours are done
+    if (lane == 0) { s_sum[wrp][0] = m1; s_sum[wrp][1] = m2; }
+    __syncthreads();
+    if (tid == 0) {
+      double sa = 0.0, sb = 0.0;
+#pragma unroll
+      for (int w2 = 0; w2 < TILE / 32; ++w2) { sa += s_sum[w2][0]; sb += s_sum[w2][1]; }
+      tilesum[2 * blockIdx.x] = sa; tilesum[2 * blockIdx.x + 1] = sb;
+    }
   }
   if (FUSE) {
     __shared__ int s_last;
