@@ -249,6 +249,9 @@ int b2lo_odom_process_dev(b2lo_odom* od, const float* xyz_dev, size_t n, size_t 
  * must be page-locked and mapped (cudaMallocHost / cudaHostRegister; K1 reads it in place) - for pageable memory the announcement is
  * ignored and B2LO_S_EMPTY is returned.  A following call with another buffer / size simply runs its own K1. */
 int b2lo_odom_lookahead(b2lo_odom* od, const float* xyz_next, size_t n, size_t stride_floats, int on_device);
+/* b2lo_odom_lookahead(next host scan) + b2lo_odom_process(this host scan) in one call; next_xyz = NULL: no announcement */
+int b2lo_odom_process_la(b2lo_odom* od, const float* xyz, size_t n, size_t stride_floats, const float* next_xyz, size_t next_n,
+                         size_t next_stride_floats, b2lo_odom_result* res);
 /* Record-stream input for the per-scan driver: after this call b2lo_odom_process / _process_dev / _lookahead take `xyz` as the
  * address of the first RECORD of a file image in the given format and `n` as the record count (stride_floats is ignored; pass 3).
  * fmt = NULL returns to float-stride clouds.  Takes effect with the next scan. */

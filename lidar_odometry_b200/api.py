@@ -27,6 +27,8 @@ __all__ = ["PointShardedICP", "Context", "default_context", "FastVoxelFilter", "
 
 
 def _f32(a):
+    if type(a) is np.ndarray and a.dtype == np.float32 and a.flags.c_contiguous:
+        return a
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
@@ -769,9 +771,14 @@ class Odometry:
 
     def process(self, scan, lookahead=None):
         a, n, sf = _cloud(scan)
-        if lookahead is not None:
-            self.lookahead(lookahead)
         r = OdomResult()
+        if lookahead is not None and not isinstance(lookahead, tuple):
+            b, bn, bsf = _cloud(lookahead)
+            if b is lookahead or (isinstance(lookahead, np.ndarray) and np.shares_memory(b, lookahead)):   # else the copy would not outlive the call
+                rc = check(capi.lib().b2lo_odom_process_la(self.h, a.ctypes.data, n, sf, b.ctypes.data, bn, bsf, C.byref(r)))   # one boundary crossing
+                return self._result(rc, r)
+        elif lookahead is not None:
+            self.lookahead(lookahead)
         rc = check(capi.lib().b2lo_odom_process(self.h, _p(a), n, sf, C.byref(r)))
         return self._result(rc, r)
 

@@ -153,6 +153,7 @@ SIGNATURES = {
     "b2lo_odom_process": (_i, [_vp, _vp, _sz, _sz, C.POINTER(OdomResult)]),
     "b2lo_odom_process_dev": (_i, [_vp, _vp, _sz, _sz, C.POINTER(OdomResult)]),
     "b2lo_odom_lookahead": (_i, [_vp, _vp, _sz, _sz, C.c_int]),
+    "b2lo_odom_process_la": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, C.POINTER(OdomResult)]),
     "b2lo_odom_set_record_fmt": (_i, [_vp, C.POINTER(RecordFmt)]),
     "b2lo_odom_process_batch_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
 }

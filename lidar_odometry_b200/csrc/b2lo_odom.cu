@@ -367,7 +367,7 @@ static int steady_finish(b2lo_odom* od, b2lo_odom_result* res) {
 }
 
 static int process_common(b2lo_odom* od, const float* src_dev, size_t ns, size_t sample_stride_floats, b2lo_odom_result* res,
-                          const b2lo_record_fmt* eff) {
+                          const b2lo_record_fmt* eff, bool* ev1_recorded = nullptr) {
   b2lo_ctx* ctx = od->ctx;
   b2lo_map* map = od->map;
   cudaStream_t st = ctx->stream;
@@ -394,6 +394,8 @@ static int process_common(b2lo_odom* od, const float* src_dev, size_t ns, size_t
     res->icp_status = B2LO_S_EMPTY;
   } else {
     rc = steady_begin(od, src_dev, ns, sample_stride_floats, t0, eff);
+    // the end-of-scan timing event goes in behind the launch, so that steady_finish's one stream synchronisation covers it too
+    if (!rc && ev1_recorded && cudaEventRecord(ctx->ev1, st) == cudaSuccess) *ev1_recorded = true;
     if (!rc) rc = steady_finish(od, res);
     if (rc) return rc;
   }
@@ -406,10 +408,13 @@ static int process_timed(b2lo_odom* od, const float* src_dev, size_t ns, size_t 
                          const b2lo_record_fmt* eff = nullptr) {
   b2lo_ctx* ctx = od->ctx;
   if (!ev0_recorded) B2_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-  int rc = process_common(od, src_dev, ns, sstride, res, eff);
+  bool ev1_done = false;
+  int rc = process_common(od, src_dev, ns, sstride, res, eff, &ev1_done);
   if (rc < 0) return rc;
-  B2_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-  B2_CUDA(cudaEventSynchronize(ctx->ev1));
+  if (!ev1_done) {   // first frame / paths that synchronise on their own
+    B2_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    B2_CUDA(cudaEventSynchronize(ctx->ev1));
+  }
   cudaEventElapsedTime(&res->device_ms, ctx->ev0, ctx->ev1);
   return rc;
 }
@@ -573,6 +578,18 @@ extern "C" int b2lo_odom_lookahead(b2lo_odom* od, const float* xyz_next, size_t 
   od->la_src = src; od->la_ns = (n + S - 1) / S; od->la_stride = (od->has_fmt ? (size_t)od->fmt.record_bytes : stride_floats) * S;
   od->la_valid = true;
   return B2LO_OK;
+}
+
+// b2lo_odom_lookahead(next) followed by b2lo_odom_process(xyz) in one call (one boundary crossing per scan for bindings whose calls are
+// expensive, e.g. ctypes): next_xyz = nullptr skips the announcement
+extern "C" int b2lo_odom_process_la(b2lo_odom* od, const float* xyz, size_t n, size_t stride_floats, const float* next_xyz, size_t next_n,
+                                    size_t next_stride_floats, b2lo_odom_result* res) {
+  if (!od || !res) return B2LO_E_ARG;
+  if (next_xyz && next_n) {
+    int rc = b2lo_odom_lookahead(od, next_xyz, next_n, next_stride_floats, 0);
+    if (rc < 0) return rc;
+  }
+  return b2lo_odom_process(od, xyz, n, stride_floats, res);
 }
 
 extern "C" int b2lo_odom_set_record_fmt(b2lo_odom* od, const b2lo_record_fmt* fmt) {
