@@ -94,11 +94,13 @@ __device__ void swap_erase_apply(const MapDev& M, int k, int s, const int* seq_p
 // mark: ||c - sensor||^2 > r^2 (VoxelMap.cpp:146-158), per-tile counts; the last CTA scans the tile counts
 __global__ void __launch_bounds__(1024) k_cull_mark(MapDev M, int n0, float sx, float sy, float sz, float r2, uint8_t* flag, int* blkcnt, int* blkoff,
                                                     int* us) {
-  if (M.gate && !*M.gate) return;
-  __shared__ int sm[40];
-  __shared__ int s_last;
+  // the gate and the first device-side scalars are loaded together: one memory round trip instead of two ahead of the work
+  const int gate_v = M.gate ? *M.gate : 1;
   if (M.sensor_dev) { sx = M.sensor_dev[3]; sy = M.sensor_dev[7]; sz = M.sensor_dev[11]; }   // translation of a row-major 4x4 pose
   if (n0 < 0) n0 = M.ctr[CT_N0];   // replayed launch sequence: the live voxel count is on the device
+  if (!gate_v) return;
+  __shared__ int sm[40];
+  __shared__ int s_last;
   int ntiles = (n0 + 1023) / 1024;
   // 4 tiles per trip: four independent 16 B loads in flight per thread (the scan streams 16 B / voxel from HBM)
   for (int tile0 = blockIdx.x * 4; tile0 < ntiles; tile0 += gridDim.x * 4) {
@@ -136,11 +138,11 @@ __global__ void __launch_bounds__(1024) k_cull_mark(MapDev M, int n0, float sx, 
 }
 // removed[] (ascending dense position) and the list of parents that lose children
 __global__ void __launch_bounds__(1024) k_cull_lists(MapDev M, int n0, const uint8_t* flag, const int* blkoff, int* us, int* removed, int* l1work) {
-  if (M.gate && !*M.gate) return;
+  const int gate_v = M.gate ? *M.gate : 1;
   __shared__ int sm[40];
-  const int k = us[US_K];
-  if (k == 0) return;
-  if (n0 < 0) n0 = us[US_K] + us[US_S];   // voxel count before the cull (k_cull_mark)
+  const int k = us[US_K], s_keep = us[US_S];
+  if (!gate_v || k == 0) return;
+  if (n0 < 0) n0 = k + s_keep;   // voxel count before the cull (k_cull_mark)
   int ntiles = (n0 + 1023) / 1024;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     int pos = tile * 1024 + threadIdx.x;
@@ -158,13 +160,13 @@ __global__ void __launch_bounds__(1024) k_cull_lists(MapDev M, int n0, const uin
 // one CTA: (1) per affected parent replay occupied_children.erase() in removal (= L0 dense) order, one warp per parent,
 // one lane per child; (2) replay the k dense-vector erases on indices; (3) apply the moves, drop the hash entries
 __global__ void __launch_bounds__(1024) k_cull_fix(MapDev M, const uint8_t* flag, int* us, const int* l1work, const int* removed, int* aux, int n0) {
-  if (M.gate && !*M.gate) return;
+  const int gate_v = M.gate ? *M.gate : 1;
   extern __shared__ int smem[];
   const int k = us[US_K];
-  if (k == 0) return;
   const int s = us[US_S];
-  if (n0 < 0) n0 = k + s;
   const int nwork = us[US_NWORK];
+  if (!gate_v || k == 0) return;
+  if (n0 < 0) n0 = k + s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int wi = warp; wi < nwork; wi += nwarps) {
     int s1 = l1work[wi];
@@ -220,10 +222,11 @@ __global__ void __launch_bounds__(1024) k_cull_fix(MapDev M, const uint8_t* flag
 // PointCloudUtils.cpp:120-121, the arithmetic of k_transform_dev); they are computed here and left in `pts` for the kernels behind
 __global__ void k_ins_probe(MapDev M, float4* pts, const int* __restrict__ d_m, int* us, int* pslot, int* nxt, FEntry* atab, int alog2,
                             int* alist, const float4* __restrict__ local, const float* __restrict__ T16) {
-  if (M.gate && !*M.gate) return;
+  const int gate_v = M.gate ? *M.gate : 1;
   const int m = *d_m;
   float tm[12];
   if (local) for (int i = 0; i < 12; ++i) tm[i] = T16[i];
+  if (!gate_v) return;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
     float4 p;
     if (local) {
@@ -235,19 +238,22 @@ __global__ void k_ins_probe(MapDev M, float4* pts, const int* __restrict__ d_m, 
     int x = voxel_coord(p.x, M.voxel), y = voxel_coord(p.y, M.voxel), z = voxel_coord(p.z, M.voxel);
     int ax = voxel_coord(p.x, M.scale1), ay = voxel_coord(p.y, M.scale1), az = voxel_coord(p.z, M.scale1);
     if (!key_in_range(x, y, z) || !(p.x == p.x) || !(p.y == p.y) || !(p.z == p.z)) { atomicOr(&us[US_ERR], ERR_RANGE); pslot[i] = -1; continue; }
+    // the affected-set probe below does not depend on the voxel probe: its first key load goes out ahead of it, so that the two
+    // dependent chains of memory round trips overlap
+    const unsigned long long ak = key_pack(ax, ay, az);
+    const uint32_t mask = (1u << alog2) - 1u;
+    uint32_t h = hash_slot(ak, alog2);
+    unsigned long long kk = *((volatile unsigned long long*)&atab[h].key);
     bool ins;
     int s0 = l0_find_or_insert(M, key_pack(x, y, z), &ins);
     if (s0 < 0) { atomicOr(&us[US_ERR], ERR_CAP); pslot[i] = -1; continue; }
     L0Entry* e = &M.l0_tab[s0];
     atomicMin(&e->first, (unsigned)i);
     atomicAdd(&e->cnt, 1);                 // idle value -1: holds count - 1
-    nxt[i] = atomicExch(&e->head, i);      // idle value -1
+    const int prev = atomicExch(&e->head, i);      // idle value -1; stored below, once the affected-set probe is on its way
     pslot[i] = s0;
     // affected_L1.insert(PointToVoxelKey(point, 1))  (VoxelMap.cpp:178-179) — float division by voxel*3
-    unsigned long long ak = key_pack(ax, ay, az);
-    uint32_t mask = (1u << alog2) - 1u, h = hash_slot(ak, alog2);
     for (;;) {
-      unsigned long long kk = *((volatile unsigned long long*)&atab[h].key);
       if (kk == ak) break;
       if (kk == KEY_EMPTY) {
         unsigned long long old = atomicCAS(&atab[h].key, KEY_EMPTY, ak);
@@ -255,16 +261,19 @@ __global__ void k_ins_probe(MapDev M, float4* pts, const int* __restrict__ d_m, 
         if (old == ak) break;
       }
       h = (h + 1) & mask;
+      kk = *((volatile unsigned long long*)&atab[h].key);
     }
     atomicMin(&atab[h].first, (unsigned)i);
+    nxt[i] = prev;
   }
 }
 // leader (first point of each touched voxel) replays AddPoint over the voxel's points in input order
 // weighted = 1: the "points" are voxels of a re-hash (w = point_count), merged as in ApplyTransformAndRehash (VoxelMap.cpp:283-297)
 __global__ void k_ins_apply(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_m, const int* pslot, const int* nxt, int* isnew,
                             float4* newc, int weighted) {
-  if (M.gate && !*M.gate) return;
+  const int gate_v = M.gate ? *M.gate : 1;
   const int m = *d_m;
+  if (!gate_v) return;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
     int s0 = pslot[i];
     if (s0 < 0) { isnew[i] = 0; continue; }
@@ -316,9 +325,10 @@ __global__ void k_ins_apply(MapDev M, const float4* __restrict__ pts, const int*
 // one CTA: rank of every new voxel in first-seen order (4 points per thread); the rank is also left in the voxel's
 // hash entry so that siblings can order themselves (k_ins_place)
 __global__ void __launch_bounds__(1024) k_ins_scan(MapDev M, const int* __restrict__ d_m, const int* isnew, const int* pslot, int* newrank, int* us) {
-  if (M.gate && !*M.gate) return;
+  const int gate_v = M.gate ? *M.gate : 1;
   __shared__ int sm[40];
   const int m = *d_m;
+  if (!gate_v) return;
   int base = 0;
   for (int t0 = 0; t0 < m; t0 += 4 * blockDim.x) {
     const int i0 = t0 + 4 * threadIdx.x;
@@ -409,10 +419,11 @@ __global__ void __launch_bounds__(256) k_rank_clear(MapDev M, const int* __restr
 // it is being updated; the first new sibling writes the new count.
 __global__ void __launch_bounds__(256) k_ins_place(MapDev M, const int* __restrict__ d_m, int* us, const int* pslot, const int* isnew,
                                                    const int* newrank, const float4* newc) {
-  if (M.gate && !*M.gate) return;
+  const int gate_v = M.gate ? *M.gate : 1;
   const int m = *d_m;
-  if (us[US_ERR] & ERR_CAP) return;
+  const int err_v = us[US_ERR];
   const int base = us[US_N0];
+  if (!gate_v || (err_v & ERR_CAP)) return;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int i = warp; i < m; i += nwarps) {
@@ -461,9 +472,10 @@ __global__ void __launch_bounds__(256) k_ins_place(MapDev M, const int* __restri
 // order (f32, as the reference), runs the Jacobi SVD and applies the planarity gate.  Non-planar parents are queued
 // for the purge.  The affected-set entry is cleared on the way out (the set is self-cleaning).
 __global__ void __launch_bounds__(256) k_surfel(MapDev M, FEntry* atab, const int* __restrict__ alist, int* us, int* plist, unsigned int* pfirst) {
-  if (M.gate && !*M.gate) return;
+  const int gate_v = M.gate ? *M.gate : 1;
   const int naff = us[US_NAFF];
   const bool skip = (us[US_ERR] & ERR_CAP) || !M.compute_surfels;
+  if (!gate_v) return;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int a = warp; a < naff; a += nwarps) {
