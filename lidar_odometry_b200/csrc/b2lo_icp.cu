@@ -703,19 +703,22 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
 // one CTA per alpha candidate i = 1..S (blockIdx.x + 1); thread k handles r_k = dr * (1 + k); the last CTA takes the arg-min
 __global__ void __launch_bounds__(128) k_icp_pko2(IcpState* st, IcpParams prm, const PkoTables* __restrict__ T, const double* __restrict__ gmm,
                                                    double* js, unsigned int* ticket) {
-  if (st->done || !prm.use_pko) return;
   __shared__ double s_c[4], s_n[4];
   __shared__ int s_i[4];
   __shared__ int s_last;
   const int k = threadIdx.x, lane = k & 31, w = k >> 5;
   const int ai = blockIdx.x + 1;
+  // the done flag and this thread's operands go out together
+  const int done_v = st->done;
   const double alpha = T->alpha[ai];
   const double pf = T->Z[ai];
   const double dr = T->trunc / 100.0;
+  const double Pr_v = k < 100 ? __ldcg(&gmm[16 + k]) : 0.0;
+  if (done_v || !prm.use_pko) return;
   double v = 0.0, c = 0.0;
   if (k < 100) {
     double r = dr * (1.0 + (double)k);
-    double Pr = gmm[16 + k];
+    double Pr = Pr_v;
     double Q = pko_kernel(T->kernel_type, r, alpha) / (pf + 1e-10) + 1e-10;
     double Mx = 0.5 * (Pr + Q);
     double jsd = 0.5 * (Pr * log(Pr / Mx) + Q * log(Q / Mx));
@@ -826,16 +829,20 @@ template <bool SURFEL>
 __global__ void __launch_bounds__(TILE) k_icp_gn(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, IcpState* st, IcpParams prm,
                                                  const double* __restrict__ res, const int* __restrict__ slot, const float4* __restrict__ plane,
                                                  double* partial, double* ext_out) {
-  if (st->done) return;
   __shared__ double red[8][28];
   __shared__ float sR[9], sT[3];
   __shared__ int s_last;
-  if (threadIdx.x < 9) sR[threadIdx.x] = st->R[threadIdx.x];
-  if (threadIdx.x < 3) sT[threadIdx.x] = st->t[threadIdx.x];
-  __syncthreads();
+  // the done flag, the pose and the loop-invariant scalars go out together (one memory round trip ahead of the work, not three)
+  const int done_v = st->done;
   const int npts = *d_npts;
-  const double sdiv = fmax(st->scale, 1e-6);
-  const float delta = (float)st->delta;
+  const double scale_v = st->scale, delta_v = st->delta;
+  float pose_v = 0.0f;
+  if (threadIdx.x < 12) pose_v = threadIdx.x < 9 ? st->R[threadIdx.x] : st->t[threadIdx.x - 9];
+  if (done_v) return;
+  if (threadIdx.x < 9) sR[threadIdx.x] = pose_v; else if (threadIdx.x < 12) sT[threadIdx.x - 9] = pose_v;
+  __syncthreads();
+  const double sdiv = fmax(scale_v, 1e-6);
+  const float delta = (float)delta_v;
   double acc[28];
 #pragma unroll
   for (int k = 0; k < 28; ++k) acc[k] = 0.0;
