@@ -112,19 +112,11 @@ template <class T> static inline void real_2x2_jacobi_svd(const T* W /*3x3 row-m
 
 // JacobiSVD of a square 3x3 matrix (Eigen/src/SVD/JacobiSVD.h, 3.4.0 compute()).
 // A, U, V row-major; S descending.  U and V are always accumulated (ComputeFullU|ComputeFullV).
-template <class T> static inline void jacobi_svd3(const T* A, T* U, T* S, T* V) {
+// jacobi_svd3_work: the sweeps + sign fix + scale + sort on an already prepared work matrix W (U, V hold the starting bases:
+// identity for a square input, the preconditioner's factors for a tall one).
+template <class T> static inline void jacobi_svd3_work(T* W, T* U, T* S, T* V, T scale) {
   const T precision = T(2) * std::numeric_limits<T>::epsilon();
   const T considerAsZero = std::numeric_limits<T>::min();
-  T scale = T(0);
-  for (int i = 0; i < 9; ++i) { T a = std::abs(A[i]); if (a > scale || a != a) scale = a; }
-  if (!std::isfinite(scale)) {  // InvalidInput: Eigen leaves U,V,S unspecified; we return identity/zero
-    for (int i = 0; i < 9; ++i) { U[i] = (i % 4 == 0) ? T(1) : T(0); V[i] = U[i]; }
-    S[0] = S[1] = S[2] = T(0);
-    return;
-  }
-  if (scale == T(0)) scale = T(1);
-  T W[9];
-  for (int i = 0; i < 9; ++i) { W[i] = A[i] / scale; U[i] = (i % 4 == 0) ? T(1) : T(0); V[i] = U[i]; }
   T maxDiag = std::max(std::abs(W[0]), std::max(std::abs(W[4]), std::abs(W[8])));
   bool finished = false;
   while (!finished) {
@@ -161,6 +153,19 @@ template <class T> static inline void jacobi_svd3(const T* A, T* U, T* S, T* V) 
       for (int r = 0; r < 3; ++r) { std::swap(U[r * 3 + pos], U[r * 3 + i]); std::swap(V[r * 3 + pos], V[r * 3 + i]); }
     }
   }
+}
+template <class T> static inline void jacobi_svd3(const T* A, T* U, T* S, T* V) {
+  T scale = T(0);
+  for (int i = 0; i < 9; ++i) { T a = std::abs(A[i]); if (a > scale || a != a) scale = a; }
+  if (!std::isfinite(scale)) {  // InvalidInput: Eigen leaves U,V,S unspecified; we return identity/zero
+    for (int i = 0; i < 9; ++i) { U[i] = (i % 4 == 0) ? T(1) : T(0); V[i] = U[i]; }
+    S[0] = S[1] = S[2] = T(0);
+    return;
+  }
+  if (scale == T(0)) scale = T(1);
+  T W[9];
+  for (int i = 0; i < 9; ++i) { W[i] = A[i] / scale; U[i] = (i % 4 == 0) ? T(1) : T(0); V[i] = U[i]; }
+  jacobi_svd3_work<T>(W, U, S, V, scale);
 }
 
 // Pivoted LDLT (lower) of a 6x6 float matrix and solve; Eigen/src/Cholesky/LDLT.h unblocked + _solve_impl.

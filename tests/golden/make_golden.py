@@ -6,6 +6,10 @@
                    /root/reference/src/optimization/AdaptiveMEstimator.cpp): residual vectors -> alpha.
 * ref_dense.npz  — iteration order of the REAL ankerl::unordered_dense::map under insert/erase sequences.
 * ref_knn.npz    — kNN indices/distances of the REAL nanoflann kd-tree (leaf 10).
+* ref_core.npz   — outputs of the REAL reference VoxelMap / FastVoxelFilter / IterativeClosestPointOptimizer::optimize
+                   (oracle/_ref/libref_core.so: the unmodified reference sources compiled against oracle/eigen_compat) on a seeded
+                   5-scan sequence: per-keyframe digests of the whole map state, the final map, H / g / dx of every Gauss-Newton
+                   iteration, the poses.  tests/test_reference_core.py::golden_run is the single definition of that run.
 * oracle_kat.npz — known-answer vectors of the oracle itself on seeded inputs (regression pin that travels to the GPU box).
 Nothing here is read from /root/reference at test time; the fixtures are committed.
 """
@@ -74,6 +78,12 @@ def main():
     tiny = cloud[:3]
     idx_t, d2_t, found_t = orc.ref_knn(tiny, q[:10], 5)
     np.savez_compressed(os.path.join(OUT, "ref_knn.npz"), cloud=cloud, q=q, idx=idx, d2=d2, found=found, idx_t=idx_t, found_t=found_t)
+    # --- real reference map + ICP (libref_core.so)
+    from oracle import ref
+    assert ref.available(), "oracle/_ref/libref_core.so missing"
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_reference_core import golden_run
+    np.savez_compressed(os.path.join(OUT, "ref_core.npz"), **golden_run(orc, ref))
     # --- oracle known answers
     scans, poses = synth.kitti_sequence(n_scans=3, seed=3, n_rings=32, n_az=400)
     feat, keys = orc.voxel_filter(scans[0][:, :3], 8, 0.5)

@@ -86,7 +86,11 @@ def test_keys_and_hashes(orc):
     assert orc.filter_morton_key(1e9, 0.0, 0.0, 0.5) == orc.voxel_key_hash((1 << 20) - 1, 0, 0)      # clamp high
     assert orc.filter_morton_key(-1e9, 0.0, 0.0, 0.5) == orc.voxel_key_hash(-(1 << 20), 0, 0)        # clamp low
     assert orc.voxel_key_hash(1 << 20, 0, 0) == orc.voxel_key_hash(-(1 << 20), 0, 0)                  # wrap
-    assert orc.voxel_key_hash(1, 0, 0) == 1 and orc.voxel_key_hash(0, 1, 0) == 2 and orc.voxel_key_hash(0, 0, 1) == 4 or True
+    # the 2^20 offset of every axis lands in bits 60/61/62 of the interleave; x is the lowest bit of each triple
+    base = orc.voxel_key_hash(0, 0, 0)
+    assert base == (1 << 60) | (1 << 61) | (1 << 62)
+    assert orc.voxel_key_hash(1, 0, 0) == base + 1 and orc.voxel_key_hash(0, 1, 0) == base + 2 and orc.voxel_key_hash(0, 0, 1) == base + 4
+    assert orc.voxel_key_hash(-1, 0, 0) == (base & ~(1 << 60)) | sum(1 << (3 * b) for b in range(20))
     # parents: floor division for negatives (VoxelMap.cpp:60-67)
     assert list(orc.parent_key([-1, -3, -4])) == [-1, -1, -2] and list(orc.parent_key([0, 2, 3])) == [0, 0, 1]
     # level-1 key uses a float division by voxel*3 (:50-58)

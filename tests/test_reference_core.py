@@ -1,0 +1,403 @@
+"""Pins the CPU oracle (oracle/include/orc_*.hpp) to the REFERENCE'S OWN CODE for the map, ICP and SE(3) parts of the path.
+
+oracle/_ref/libref_core.so is the unmodified /root/reference/src/database/{VoxelMap,LidarFrame}.cpp,
+src/util/{MathUtils,PointCloudUtils}.cpp and src/optimization/{IterativeClosestPointOptimizer,AdaptiveMEstimator}.cpp compiled
+against oracle/eigen_compat (Eigen3 is absent from the image).  Every branch, container interaction and evaluation order is the
+reference's; only the arithmetic inside the Eigen calls is restated (see the header of oracle/eigen_compat/Eigen/Dense).
+
+* live tests (skipped where the library was not built) run restatement and reference side by side;
+* fixture tests compare the restatement with tests/golden/ref_core.npz, written by tests/golden/make_golden.py from the same
+  library, so the pin also holds on a box without /root/reference.
+Bit-exact everywhere except where a tolerance is written next to the comparison (KDTree-mode plane normals: two different SVD
+algorithms; loop-closure ICP: Matrix4f::inverse() is unpinned).
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def u32(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def bits_equal(a, b):
+    return a.shape == b.shape and np.array_equal(u32(a), u32(b))
+
+
+@pytest.fixture(scope="module")
+def ref(orc):
+    from oracle import ref as _ref
+    if not _ref.available():
+        pytest.skip("oracle/_ref/libref_core.so not built (no /root/reference on this box)")
+    return _ref
+
+
+def world(T, pts):
+    """transform_point_cloud arithmetic (PointCloudUtils.cpp:120-123) in numpy f32: ((c0 x + c1 y) + c2 z) + c3"""
+    T = T.astype(np.float32); p = pts.astype(np.float32)
+    return np.stack([((T[r, 0] * p[:, 0] + T[r, 1] * p[:, 1]) + T[r, 2] * p[:, 2]) + T[r, 3] for r in range(3)], axis=1).astype(np.float32)
+
+
+def assert_maps_equal(om, rm, tag=""):
+    assert om.counts() == rm.counts(), (tag, om.counts(), rm.counts())
+    ko, co, no = om.export_l0(); kr, cr, nr = rm.export_l0()
+    assert np.array_equal(ko, kr), f"{tag}: L0 dense order"
+    assert bits_equal(co, cr), f"{tag}: L0 centroid bits"
+    assert np.array_equal(no, nr), f"{tag}: L0 point counts"
+    lo, lr = om.export_l1(), rm.export_l1()
+    for f in ("keys", "nchild", "children", "has_surfel", "last_child_count"):
+        assert np.array_equal(lo[f], lr[f]), f"{tag}: L1 {f}"
+    for f in ("normal", "centroid", "planarity"):
+        assert bits_equal(lo[f], lr[f]), f"{tag}: L1 {f} bits"
+
+
+# ---------------------------------------------------------------------------------------------------------------- keys / SE(3)
+def test_keys_match_reference(orc, ref):
+    rng = np.random.default_rng(0)
+    vals = []
+    for v in (0.5, 0.4, 0.1, 1.0):
+        for m in (-7, -3, -1, 0, 1, 2, 3, 9, 300):
+            for s in (v, np.float32(v) * np.float32(3.0)):
+                x = np.float32(m) * np.float32(s)
+                vals += [x, np.nextafter(x, np.float32(np.inf)), np.nextafter(x, np.float32(-np.inf))]
+    vals += [np.float32(0.0), np.float32(-0.0), np.float32(1e-40), np.float32(-1e-40)]
+    vals = np.array(vals, np.float32)
+    for v in (0.5, 0.4, 0.1, 1.0):
+        for lvl in (0, 1):
+            for x in vals:
+                p = np.array([x, -x, x * np.float32(0.5)], np.float32)
+                assert np.array_equal(orc.point_to_key(p, v, 3, lvl), ref.point_to_key(p, v, 3, lvl)), (v, lvl, x)
+    for _ in range(300):
+        k = rng.integers(-(1 << 20) - 5, (1 << 20) + 5, 3)
+        assert orc.voxel_key_hash(*k) == ref.voxel_key_hash(*k)
+        k = rng.integers(-50, 50, 3)
+        for f in (3, 5):
+            assert np.array_equal(orc.parent_key(k, f), ref.parent_key(k, f))
+    assert ref.voxel_key_hash(0, 0, 0) == (1 << 60) | (1 << 61) | (1 << 62)   # the 2^20 offset of each axis (VoxelMap.h:168-170)
+    assert ref.voxel_key_hash(1, 0, 0) == 1 + ref.voxel_key_hash(0, 0, 0)
+
+
+def test_se3_matches_reference(orc, ref):
+    rng = np.random.default_rng(1)
+    for i in range(200):
+        A = rng.standard_normal((3, 3)).astype(np.float32)
+        if i % 2:
+            A = orc.so3_exp((rng.standard_normal(3) * 0.5).astype(np.float32)) + (rng.standard_normal((3, 3)) * 1e-6).astype(np.float32)
+        assert bits_equal(orc.so3_normalize(A), ref.so3_normalize(A))
+        Uo, So, Vo = orc.svd3f(A); Ur, Sr, Vr = ref.svd3f(A)
+        assert bits_equal(Uo, Ur) and bits_equal(So, Sr) and bits_equal(Vo, Vr)
+        scale = [1.0, 1e-3, 1e-7, 1e-11, 3.0][i % 5]
+        w = (rng.standard_normal(3) * scale).astype(np.float32)
+        assert bits_equal(orc.so3_exp(w), ref.so3_exp(w)), w
+        Ta = np.eye(4, dtype=np.float32); Tb = np.eye(4, dtype=np.float32)
+        Ta[:3, :3] = orc.so3_exp((rng.standard_normal(3)).astype(np.float32)); Ta[:3, 3] = rng.standard_normal(3) * 50
+        Tb[:3, :3] = orc.so3_exp((rng.standard_normal(3) * 0.01).astype(np.float32)); Tb[:3, 3] = rng.standard_normal(3)
+        assert bits_equal(orc.se3_mul(Ta, Tb), ref.se3_mul(Ta, Tb))
+        assert bits_equal(orc.se3_inv(Ta), ref.se3_inv(Ta))
+    assert bits_equal(orc.so3_exp(np.zeros(3, np.float32)), ref.so3_exp(np.zeros(3, np.float32)))
+
+
+def test_plane_fit_two_algorithms_agree(orc, ref):
+    """ICP.cpp:745: JacobiSVD<MatrixXd>(5x3).  eigen_compat restates Eigen's QR-preconditioned two-sided Jacobi, the oracle (and the
+    CUDA kernel) use a one-sided Jacobi: normals must agree to rounding (sign aside), and with numpy."""
+    rng = np.random.default_rng(2)
+    for i in range(300):
+        A = rng.standard_normal((5, 3)) * [1.0, 1.0, [0.05, 0.5, 1e-4][i % 3]]
+        A = A @ np.linalg.qr(rng.standard_normal((3, 3)))[0]
+        A -= A.mean(0)
+        n_ref = ref.plane_normal_nx3(A)
+        n_np = np.linalg.svd(A)[2][2]
+        assert abs(abs(n_ref @ n_np) - 1.0) < 1e-12
+        assert abs(np.linalg.norm(n_ref) - 1.0) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------------------- filter / loaders
+def test_filter_matches_reference(orc, ref, small_kitti):
+    scans, _ = small_kitti
+    for s, stride, voxel in ((scans[0], 8, 0.5), (scans[1], 1, 0.5), (scans[2], 4, 0.4), (scans[3], 3, 1.0)):
+        fo, _ = orc.voxel_filter(s[:, :3], stride, voxel)
+        assert bits_equal(fo, ref.voxel_filter(s[:, :3], stride, voxel))
+    pts = scans[0][:2000, :3].copy()
+    pts[::7, 0] = np.nan; pts[3::11, 1] = np.inf; pts[5::13, 2] = -np.inf
+    pts[100:110] = 3e6; pts[110:120] = -3e6          # beyond the 21-bit clamp
+    fo, _ = orc.voxel_filter(pts, 1, 0.5)
+    assert bits_equal(fo, ref.voxel_filter(pts, 1, 0.5))
+    assert ref.voxel_filter(np.zeros((0, 3), np.float32), 1, 0.5).shape[0] == 0
+    one = np.array([[1.0, 2.0, 3.0]], np.float32)
+    assert bits_equal(orc.voxel_filter(one, 8, 0.5)[0], ref.voxel_filter(one, 8, 0.5))
+
+
+def test_loaders_and_voxel_grid_match_reference(orc, ref, small_kitti, tmp_path):
+    scans, poses = small_kitti
+    img = np.ascontiguousarray(scans[0][:5000], np.float32)
+    for cut in (0, 1, 7, 15):     # truncated last record (PointCloudUtils.cpp:40-47)
+        raw = img.tobytes()[: img.nbytes - cut]
+        path = tmp_path / f"s{cut}.bin"
+        path.write_bytes(raw)
+        assert bits_equal(orc.kitti_load(raw), ref.kitti_load_file(path, 5000))
+    cloud = world(poses[0], scans[0][::5, :3])
+    for leaf in (0.4, 1.0):
+        assert bits_equal(orc.voxel_grid_filter(cloud, leaf), ref.voxel_grid_filter(cloud, leaf))
+    T = poses[2].astype(np.float32)
+    assert bits_equal(world(T, scans[2][:3000, :3]), ref.transform_point_cloud(scans[2][:3000, :3], T))
+
+
+# ---------------------------------------------------------------------------------------------------------------- the map
+def run_map_sequence(orc, backends, scans, poses, voxel=0.5, stride=4, radii=None, check=None):
+    maps = [b.VoxelMap(voxel, 3, 0.1, True) for b in backends]
+    for k, s in enumerate(scans):
+        f, _ = orc.voxel_filter(s[:, :3], stride, voxel)
+        T = poses[k].astype(np.float32)
+        w = world(T, f)
+        rad = radii[k] if radii else 120.0
+        for m in maps:
+            m.update(w, T[:3, 3].astype(np.float64), rad)
+        if check:
+            check(k, maps, f, T)
+    return maps
+
+
+def test_map_update_matches_reference(orc, ref, small_kitti):
+    scans, poses = small_kitti
+    radii = [120.0, 120.0, 25.0, 120.0, 12.0, 120.0]   # culls (VoxelMap.cpp:146-158), incl. culled tail voxels and emptied parents
+    purged = []
+
+    def check(k, maps, f, T):
+        om, rm = maps
+        assert_maps_equal(om, rm, f"keyframe {k}")
+        assert bits_equal(rm.point_cloud(), rm.export_l0()[1])                       # GetPointCloud == dense order (VoxelMap.cpp:388-403)
+        c, n, p = rm.surfels(); l1 = om.export_l1(); hs = l1["has_surfel"] == 1      # GetL1Surfels (VoxelMap.cpp:405-418)
+        assert bits_equal(c, l1["centroid"][hs]) and bits_equal(n, l1["normal"][hs]) and bits_equal(p, l1["planarity"][hs])
+        q = world(T, f[::9]) + np.float32(0.01)
+        for p3 in q[:150]:
+            a, b = om.lookup(p3), rm.lookup(p3)
+            assert a[0] == b[0] and bits_equal(a[1], b[1]) and bits_equal(a[2], b[2])
+        purged.append(om.counts())
+
+    run_map_sequence(orc, (orc, ref), scans, poses, radii=radii, check=check)
+    assert len(purged) == 6
+
+
+def test_map_edge_cases_match_reference(orc, ref):
+    rng = np.random.default_rng(5)
+    om, rm = orc.VoxelMap(0.5, 3, 0.1, True), ref.VoxelMap(0.5, 3, 0.1, True)
+    # planar patch across the origin (negative coordinates: float-division keys vs floor-division parents), then a noisy blob that
+    # must be purged as non-planar together with its children (VoxelMap.cpp:244-253)
+    xy = rng.uniform(-6, 6, (4000, 2))
+    plane = np.c_[xy, 0.02 * rng.standard_normal(4000)].astype(np.float32)
+    blob = (rng.uniform(-0.7, 0.7, (600, 3)) + [3.0, 3.0, 4.0]).astype(np.float32)
+    s = np.zeros(3)
+    for m in (om, rm):
+        m.update(plane, s, 100.0)
+    assert_maps_equal(om, rm, "plane")
+    for m in (om, rm):
+        m.update(blob, s, 100.0)
+    assert_maps_equal(om, rm, "blob (purge)")
+    for m in (om, rm):
+        m.update(plane[:50] + np.float32([0, 0, 0.01]), s, 100.0)      # unchanged child counts: stale surfels kept (VoxelMap.cpp:202-205)
+    assert_maps_equal(om, rm, "stale")
+    far = np.array([500.0, 0.0, 0.0])
+    for m in (om, rm):
+        m.update((plane + np.float32([500, 0, 0])), far, 8.0)           # cull everything old, refill
+    assert_maps_equal(om, rm, "cull-all-refill")
+    for m in (om, rm):
+        m.update(np.zeros((0, 3), np.float32), far, 1.0)                # empty cloud: early return, nothing culled (VoxelMap.cpp:135-137)
+    assert_maps_equal(om, rm, "empty")
+    for m in (om, rm):
+        m.clear()
+        m.update(plane[:3], s, 10.0)
+    assert_maps_equal(om, rm, "tiny")
+    # no surfels at all (KDTree configuration, Estimator.cpp:81)
+    om2, rm2 = orc.VoxelMap(0.4, 3, 0.1, False), ref.VoxelMap(0.4, 3, 0.1, False)
+    for m in (om2, rm2):
+        m.update(plane, s, 100.0)
+        m.update(blob, s, 100.0)
+    assert_maps_equal(om2, rm2, "no surfels")
+
+
+def test_transform_rehash_matches_reference(orc, ref, small_kitti):
+    scans, poses = small_kitti
+    om, rm = run_map_sequence(orc, (orc, ref), scans[:3], poses[:3])
+    T = np.eye(4, dtype=np.float32)
+    T[:3, :3] = orc.so3_exp(np.float32([0.01, -0.02, 0.3])); T[:3, 3] = [1.3, -0.4, 0.05]
+    om.transform_rehash(T); rm.transform_rehash(T)                      # VoxelMap.cpp:264-366 (merges colliding voxels, refits all surfels)
+    assert_maps_equal(om, rm, "rehash")
+    f, _ = orc.voxel_filter(scans[3][:, :3], 4, 0.5)
+    w = world(poses[3], f)
+    for m in (om, rm):
+        m.update(w, poses[3][:3, 3].astype(np.float64), 120.0)
+    assert_maps_equal(om, rm, "update after rehash")
+
+
+# ---------------------------------------------------------------------------------------------------------------- ICP
+def compare_optimize(orc, ref, om, rm, f, T0, cfg, tag):
+    oko, To, tro = orc.icp_optimize(om, f, T0, cfg)
+    okr, Tr, trr, st, Tframe = ref.icp_optimize(rm, f, T0, cfg)
+    assert oko == okr, tag
+    assert bits_equal(To, Tr), f"{tag}: final pose bits"
+    if not okr:
+        assert bits_equal(Tr, T0), "failure contract: output = initial (ICP.cpp:266,301)"
+        return 0
+    assert len(tro) == len(trr) == st["num_iterations"], tag
+    for i, (a, b) in enumerate(zip(tro, trr)):
+        assert bits_equal(a["H"], b["H"]) and bits_equal(a["g"], b["g"]) and bits_equal(a["dx"], b["dx"]), f"{tag}: iteration {i}"
+    assert st["num_correspondences"] == tro[-1]["n_corr"]
+    assert np.float32(st["initial_cost"]) == np.float32(tro[0]["cost"]) and np.float32(st["final_cost"]) == np.float32(tro[-1]["cost"])
+    assert bits_equal(Tframe, tro[-1]["T_in"]), "frame pose = pose at the start of the last iteration (ICP.cpp:284)"
+    return len(trr)
+
+
+def test_surfel_icp_matches_reference(orc, ref, small_kitti):
+    scans, poses = small_kitti
+    cfg = orc.default_icp_cfg()
+    iters = []
+
+    def check(k, maps, f, T):
+        pass
+
+    om, rm = orc.VoxelMap(0.5, 3, 0.1, True), ref.VoxelMap(0.5, 3, 0.1, True)
+    rng = np.random.default_rng(3)
+    for k, s in enumerate(scans):
+        f, _ = orc.voxel_filter(s[:, :3], 8, 0.5)
+        T = poses[k].astype(np.float32)
+        if k > 0:
+            T0 = T.copy(); T0[:3, 3] += (rng.standard_normal(3) * 0.12).astype(np.float32)
+            T0[:3, :3] = T0[:3, :3] @ orc.so3_exp((rng.standard_normal(3) * 0.01).astype(np.float32))
+            co = orc.icp_correspondences(om, f, T0)
+            cr = ref.correspondence_list(rm, f, T0)
+            acc = co["state"] == 2
+            assert acc.sum() == len(cr["residuals"]) and np.array_equal(co["residual"][acc], cr["residuals"])
+            assert np.array_equal(co["normal"][acc].astype(np.float64), cr["normals_last"])
+            assert np.array_equal(co["centroid"][acc].astype(np.float64), cr["points_last"])
+            assert np.array_equal(f[acc].astype(np.float64), cr["points_curr"])
+            iters.append(compare_optimize(orc, ref, om, rm, f, T0, cfg, f"scan {k}"))
+            for variant in range(4):
+                c2 = orc.default_icp_cfg()
+                if variant == 0: c2.loss_type = 1                       # Cauchy weights (ICP.cpp:393-396)
+                if variant == 1: c2.use_adaptive_m_estimator = 0         # fixed delta = robust_loss_delta (ICP.cpp:319)
+                if variant == 2: c2.use_robust_loss = 0
+                if variant == 3: c2.max_iterations = 9; c2.translation_tolerance = 1e-6; c2.rotation_tolerance = 1e-6
+                compare_optimize(orc, ref, om, rm, f, T0, c2, f"scan {k} variant {variant}")
+        w = world(T, f)
+        for m in (om, rm):
+            m.update(w, T[:3, 3].astype(np.float64), 120.0)
+    assert max(iters) >= 3
+    # failure contract: fewer than 10 correspondences (ICP.cpp:298-302)
+    far = np.eye(4, dtype=np.float32); far[:3, 3] = [0, 0, 500]
+    assert compare_optimize(orc, ref, om, rm, f, far, cfg, "far") == 0
+    assert compare_optimize(orc, ref, om, rm, f[:5], poses[-1].astype(np.float32), cfg, "5 points") == 0
+    empty_o, empty_r = orc.VoxelMap(0.5), ref.VoxelMap(0.5)
+    assert compare_optimize(orc, ref, empty_o, empty_r, f, poses[-1].astype(np.float32), cfg, "empty map") == 0
+
+
+def test_kdtree_icp_matches_reference(orc, ref, small_mid360):
+    scans, poses = small_mid360
+    cfg = orc.default_icp_cfg(); cfg.use_surfel_correspondence = 0
+    om, rm = orc.VoxelMap(0.4, 3, 0.1, False), ref.VoxelMap(0.4, 3, 0.1, False)
+    rng = np.random.default_rng(4)
+    for k, s in enumerate(scans):
+        f, _ = orc.voxel_filter(s[:, :3], 4, 0.4)
+        T = poses[k].astype(np.float32)
+        if k > 0:
+            T0 = T.copy(); T0[:3, 3] += (rng.standard_normal(3) * 0.04).astype(np.float32)
+            mc = om.export_l0()[1]
+            rm.rebuild_kdtree()                                                   # Estimator.cpp:460-462
+            co = orc.kdtree_correspondences(mc, f, T0)
+            cr = ref.correspondence_list(rm, f, T0, kdtree=True)
+            acc = co["state"] == 2
+            assert acc.sum() == len(cr["residuals"])
+            assert np.array_equal(f[acc].astype(np.float64), cr["points_curr"])  # same accepted queries, same order
+            assert bits_equal(co["centroid"][acc], cr["points_last"].astype(np.float32))
+            assert np.abs(co["residual"][acc] - cr["residuals"]).max() < 1e-12    # two SVD algorithms (see the module docstring)
+            dots = np.abs((co["normal"][acc].astype(np.float64) * cr["normals_last"]).sum(1))
+            assert dots.min() > 1.0 - 1e-6                                         # f32-cast normals, sign aside
+            oko, To, tro = orc.icp_optimize_kdtree(mc, f, T0, cfg)
+            okr, Tr, trr, st, _ = ref.icp_optimize(rm, f, T0, cfg)
+            assert oko == okr and len(tro) == len(trr)
+            assert np.abs(To - Tr).max() < 1e-6                                    # tolerance: the normals differ in the last bits
+            for a, b in zip(tro, trr):
+                assert np.abs(a["H"] - b["H"]).max() <= 1e-5 * np.abs(a["H"]).max()
+        w = world(T, f)
+        for m in (om, rm):
+            m.update(w, T[:3, 3].astype(np.float64), 48.0)
+        assert_maps_equal(om, rm, f"mid360 keyframe {k}")
+
+
+def test_loop_icp_matches_reference(orc, ref, small_kitti):
+    """optimize_loop (ICP.cpp:40-251).  Matrix4f::inverse() (ICP.cpp:495) is unpinned (Eigen uses an SSE cofactor schedule, eigen_compat
+    an adjugate, the oracle the rigid inverse): the first iteration agrees to rounding, later ones may pick a neighbouring PKO alpha."""
+    scans, poses = small_kitti
+    f0, _ = orc.voxel_filter(scans[0][:, :3], 4, 0.5)
+    f1, _ = orc.voxel_filter(scans[1][:, :3], 4, 0.5)
+    T0 = poses[0].astype(np.float32); T1 = poses[1].astype(np.float32).copy(); T1[:3, 3] += np.float32([0.2, 0.1, 0.0])
+    a = orc.icp_optimize_loop(f1, T1, f0, T0)
+    b = ref.icp_optimize_loop(f1, T1, f0, T0)
+    assert a[0] == b[0] and abs(a[2] - b[2]) < 0.01 and abs(a[3] - b[3]) <= 1
+    assert np.abs(a[1] - b[1]).max() < 2e-3
+    assert np.abs(a[4][0]["H"] - b[4][0]["H"]).max() <= 1e-5 * np.abs(a[4][0]["H"]).max()
+    assert np.abs(a[4][0]["dx"] - b[4][0]["dx"]).max() < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------- fixtures
+def digest(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return np.frombuffer(h.digest(), np.uint8).copy()
+
+
+def map_digest(m):
+    k, c, n = m.export_l0(); l1 = m.export_l1()
+    return digest(k, c, n, l1["keys"], l1["nchild"], l1["children"], l1["has_surfel"], l1["normal"], l1["centroid"], l1["planarity"],
+                  l1["last_child_count"])
+
+
+def golden_sequence():
+    from lidar_odometry_b200 import synth
+    return synth.kitti_sequence(n_scans=5, seed=21, n_rings=32, n_az=500)
+
+
+def golden_run(orc, be):
+    """The sequence both make_golden.py (be = the reference) and the fixture test (be = the oracle) run."""
+    scans, poses = golden_sequence()
+    cfg = orc.default_icp_cfg()
+    m = be.VoxelMap(0.5, 3, 0.1, True)
+    rng = np.random.default_rng(8)
+    out = dict(map_digest=[], T_out=[], H=[], g=[], dx=[], n_iter=[], feat_digest=[])
+    for k, s in enumerate(scans):
+        f = be.voxel_filter(s[:, :3], 8, 0.5)
+        f = f[0] if isinstance(f, tuple) else f
+        out["feat_digest"].append(digest(f))
+        T = poses[k].astype(np.float32)
+        if k > 0:
+            T0 = T.copy(); T0[:3, 3] += (rng.standard_normal(3) * 0.1).astype(np.float32)
+            r = be.icp_optimize(m, f, T0, cfg)
+            out["T_out"].append(r[1]); out["n_iter"].append(len(r[2]))
+            for t in r[2]:
+                out["H"].append(t["H"]); out["g"].append(t["g"]); out["dx"].append(t["dx"])
+        m.update(world(T, f), T[:3, 3].astype(np.float64), 30.0 if k == 3 else 120.0)
+        out["map_digest"].append(map_digest(m))
+    k0, c0, n0 = m.export_l0(); l1 = m.export_l1()
+    out.update(l0_keys=k0, l0_cent=c0, l0_cnt=n0, l1_keys=l1["keys"], l1_has=l1["has_surfel"], l1_normal=l1["normal"], l1_centroid=l1["centroid"])
+    return {k: np.array(v) for k, v in out.items()}
+
+
+def test_oracle_matches_reference_fixture(orc):
+    z = np.load(os.path.join(G, "ref_core.npz"))
+    got = golden_run(orc, orc)
+    for k in z.files:
+        a, b = got[k], z[k]
+        assert a.shape == b.shape and a.dtype == b.dtype, k
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), f"oracle differs from the reference fixture in {k}"
+
+
+def test_fixture_is_current(orc, ref):
+    """The committed fixture is what the reference library produces today (guards against a stale ref_core.npz)."""
+    z = np.load(os.path.join(G, "ref_core.npz"))
+    got = golden_run(orc, ref)
+    for k in z.files:
+        assert np.array_equal(got[k].view(np.uint8), z[k].view(np.uint8)), k
