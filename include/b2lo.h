@@ -43,7 +43,7 @@ typedef struct b2lo_odom b2lo_odom;
 /* optimization::ICPConfig (ICP.h:55-76) + optimization::AdaptiveMEstimatorConfig (AdaptiveMEstimator.h:28-45),
  * with the values Estimator.cpp:49-70 wires in as defaults (b2lo_default_icp_cfg). */
 typedef struct {
-  int max_iterations;
+  int max_iterations;            /* >= 1, no upper bound (ICPConfig's default is 50); b2lo_icp_stats::it traces the first B2LO_MAX_ITERS */
   double translation_tolerance, rotation_tolerance;
   double max_correspondence_distance;
   int min_correspondence_points;
@@ -83,6 +83,11 @@ typedef struct {
 void b2lo_default_icp_cfg(b2lo_icp_cfg* cfg);
 const char* b2lo_version(void);
 const char* b2lo_last_error(void);
+/* Opt-in for the throughput mode (many independent sequences on one GPU, b2lo_odom_process_batch_dev): their streams overlap only if
+ * they map to different hardware work queues, and the driver's default is 8.  Sets CUDA_DEVICE_MAX_CONNECTIONS=<connections> (1..32)
+ * for THIS process unless the variable is already set; it takes effect only when called before the process's first CUDA call.  The
+ * library never touches the environment on its own. */
+int b2lo_process_env_for_batches(int connections);
 void b2lo_struct_sizes(size_t out[5]); /* sizeof icp_cfg, iter_trace, icp_stats, odom_cfg, odom_result: lets a binding verify its mirrors */
 
 /* ---- context ------------------------------------------------------------------------------------ */
@@ -178,6 +183,12 @@ int b2lo_icp_correspondences_knn(b2lo_map* map, const float* local_xyz, size_t m
  * T_out = T_init, as the reference leaves optimized_transform. */
 int b2lo_icp_optimize(b2lo_map* map, const float* local_xyz, size_t m, size_t stride_floats, const float T_init[16],
                       const b2lo_icp_cfg* cfg, float T_out[16], b2lo_icp_stats* stats /*nullable*/);
+/* parity tap: ONE Gauss-Newton iteration (the loop body ICP.cpp:280-448: correspondences, PKO delta, normal equations, solve, SE(3)
+ * update) entered at pose T_in.  scale > 0: the residual normalisation scale an earlier iteration fixed (ICP.cpp:304-316 computes it at
+ * iteration 0 only and reuses it); scale <= 0: computed from this pose's residuals.  Lets a test feed the reference's pose of iteration k
+ * (teacher forcing) and compare C, alpha, H, g and the updated pose of every iteration, not only of iteration 0. */
+int b2lo_icp_iterate(b2lo_map* map, const float* local_xyz, size_t m, size_t stride_floats, const float T_in[16], double scale,
+                     const b2lo_icp_cfg* cfg, float T_out[16], b2lo_icp_stats* stats /*nullable*/);
 /* same, query cloud = the context's feature buffer left by b2lo_filter / b2lo_filter_dev */
 int b2lo_icp_optimize_features(b2lo_map* map, const float T_init[16], const b2lo_icp_cfg* cfg, float T_out[16], b2lo_icp_stats* stats);
 

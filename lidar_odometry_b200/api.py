@@ -585,6 +585,19 @@ class IterativeClosestPointOptimizer:
         return rc == B2LO_OK, Trel.reshape(4, 4).copy(), float(ratio.value)
 
     # parity taps -----------------------------------------------------------------------------------------------
+    def iterate(self, voxel_map: VoxelMap, cloud, pose, scale=0.0):
+        """ONE Gauss-Newton iteration (the loop body ICP.cpp:280-448) entered at ``pose`` with the residual normalisation ``scale`` an
+        earlier iteration fixed (``scale <= 0``: computed here, as iteration 0 does).  Returns ``(status_ok, T_out, trace_dict)``."""
+        a, n, sf = _cloud(cloud)
+        T0 = _f32(pose).reshape(16)
+        Tout = np.zeros(16, np.float32)
+        ame = self.m_adaptive_estimator.get_config() if self.m_adaptive_estimator else None
+        cfg = _icp_cfg(self.m_config, ame)
+        st = IcpStats()
+        rc = check(capi.lib().b2lo_icp_iterate(voxel_map.h, _p(a), n, sf, _p(T0), C.c_double(scale), C.byref(cfg), _p(Tout), C.byref(st)))
+        tr = _trace(st)
+        return rc == B2LO_OK, Tout.reshape(4, 4).copy(), (tr[0] if tr else None)
+
     def find_correspondences(self, voxel_map: VoxelMap, cloud, pose):
         """Per-query view of find_correspondences (ICP.cpp:587-645) at a fixed pose."""
         a, m, sf = _cloud(cloud)

@@ -92,6 +92,7 @@ SIGNATURES = {
     "b2lo_version": (C.c_char_p, []),
     "b2lo_last_error": (C.c_char_p, []),
     "b2lo_struct_sizes": (None, [_vp]),
+    "b2lo_process_env_for_batches": (_i, [_i]),
     "b2lo_ctx_create": (_i, [_i, C.POINTER(_vp)]),
     "b2lo_ctx_destroy": (_i, [_vp]),
     "b2lo_ctx_sync": (_i, [_vp]),
@@ -128,6 +129,7 @@ SIGNATURES = {
     "b2lo_icp_correspondences": (_i, [_vp, _vp, _sz, _sz, _vp, _d, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_sz)]),
     "b2lo_icp_correspondences_knn": (_i, [_vp, _vp, _sz, _sz, _vp, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_sz), C.POINTER(_sz)]),
     "b2lo_icp_optimize": (_i, [_vp, _vp, _sz, _sz, _vp, C.POINTER(IcpCfg), _vp, C.POINTER(IcpStats)]),
+    "b2lo_icp_iterate": (_i, [_vp, _vp, _sz, _sz, _vp, _d, C.POINTER(IcpCfg), _vp, C.POINTER(IcpStats)]),
     "b2lo_icp_optimize_loop": (_i, [_vp, _vp, _sz, _sz, _vp, _vp, _sz, _sz, _vp, C.POINTER(IcpCfg), _vp, C.POINTER(C.c_float), C.POINTER(IcpStats)]),
     "b2lo_icp_optimize_features": (_i, [_vp, _vp, C.POINTER(IcpCfg), _vp, C.POINTER(IcpStats)]),
     "b2lo_icp_shard_begin": (_i, [_vp, _vp, _sz, _sz, _vp, C.POINTER(IcpCfg)]),

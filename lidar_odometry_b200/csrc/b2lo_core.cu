@@ -229,7 +229,14 @@ using namespace b2;
 // Independent sequences overlap on the device only if their streams map to different hardware work queues; the driver's default is 8
 // connections, which aliases the streams of a batch (measured: 32 sequences 11.4 k -> 30.9 k scans/s with 32).  Takes effect when this
 // library is loaded before the process initialises CUDA; an explicit setting in the environment wins.
-namespace { struct ConnInit { ConnInit() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); } } g_conn_init; }
+// Opt-in (bench.py and the batch tools call it before the first CUDA call): a library must not edit its host's environment behind
+// its back.
+extern "C" int b2lo_process_env_for_batches(int connections) {
+  if (connections < 1 || connections > 32) return B2LO_E_ARG;
+  char buf[16];
+  snprintf(buf, sizeof buf, "%d", connections);
+  return setenv("CUDA_DEVICE_MAX_CONNECTIONS", buf, 0) == 0 ? B2LO_OK : B2LO_E_ARG;
+}
 
 extern "C" const char* b2lo_version(void) { return "b2lo 0.1 (sm_100a)"; }
 extern "C" const char* b2lo_last_error(void) { return g_err; }
@@ -280,6 +287,8 @@ extern "C" int b2lo_ctx_create(int device, b2lo_ctx** out) {
       cudaMallocHost((void**)&ctx->h_sp, sizeof(ScanParams)) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_sp, cudaEventDisableTiming) != cudaSuccess || cudaMallocHost((void**)&ctx->h_counts, 64 * sizeof(int)) != cudaSuccess)
     rc = B2LO_E_NOMEM;
   if (!rc) {
+    std::memset(ctx->h_sp, 0, sizeof(ScanParams));
+    cudaMemsetAsync(ctx->d_sp, 0, sizeof(ScanParams), ctx->stream);
     cudaMemsetAsync(ctx->d_nfeat, 0, sizeof(int), ctx->stream);
     cudaMemsetAsync(ctx->d_nfeat2, 0, sizeof(int), ctx->stream);
     cudaMemsetAsync(ctx->d_nquery, 0, sizeof(int), ctx->stream);
@@ -372,7 +381,7 @@ extern "C" int b2lo_filter(b2lo_ctx* ctx, const float* xyz, size_t n, size_t str
   *m = 0;
   if (stride < 1 || stride_floats < 3 || !(voxel_size > 0.0f)) { set_error("filter: bad stride / voxel size"); return B2LO_E_ARG; }
   if (!xyz || n == 0) return B2LO_S_EMPTY;  // input.empty() (VoxelMap.h:75)
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   cudaSetDevice(ctx->device);
   size_t ns = (n + (size_t)stride - 1) / (size_t)stride;
   int rc = ctx_stage_h2d(ctx, xyz, n, stride_floats, (size_t)stride, nullptr, nullptr);
@@ -392,7 +401,7 @@ extern "C" int b2lo_filter(b2lo_ctx* ctx, const float* xyz, size_t n, size_t str
 extern "C" int b2lo_filter_dev(b2lo_ctx* ctx, const float* xyz_dev, size_t n, size_t stride_floats, int stride, float voxel_size) {
   if (!ctx) return B2LO_E_ARG;
   if (stride < 1 || stride_floats < 3 || !(voxel_size > 0.0f)) { set_error("filter: bad stride / voxel size"); return B2LO_E_ARG; }
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   cudaSetDevice(ctx->device);
   if (!xyz_dev || n == 0) { B2_CUDA(cudaMemsetAsync(ctx->d_nfeat, 0, sizeof(int), ctx->stream)); return B2LO_S_EMPTY; }
   size_t ns = (n + (size_t)stride - 1) / (size_t)stride;
@@ -400,7 +409,7 @@ extern "C" int b2lo_filter_dev(b2lo_ctx* ctx, const float* xyz_dev, size_t n, si
 }
 extern "C" int b2lo_ctx_features(b2lo_ctx* ctx, float* out_xyz, size_t cap, size_t* m) {
   if (!ctx || !m) return B2LO_E_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   cudaSetDevice(ctx->device);
   size_t ncap = cap < ctx->pts_cap ? cap : ctx->pts_cap;
   if (!out_xyz) ncap = 0;
@@ -449,7 +458,7 @@ extern "C" int b2lo_icp_optimize(b2lo_map* map, const float* local_xyz, size_t m
   if (stride_floats < 3) return B2LO_E_ARG;
   std::lock_guard<std::recursive_mutex> lk(map->mu);
   b2lo_ctx* ctx = map->ctx;
-  std::lock_guard<std::mutex> lk2(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk2(ctx->mu);
   cudaSetDevice(ctx->device);
   // empty map / empty cloud: find_correspondences returns 0 (ICP.cpp:593-603) -> below the minimum -> false, output = initial
   if (!local_xyz || m == 0 || map->n0 == 0) {
@@ -463,18 +472,37 @@ extern "C" int b2lo_icp_optimize(b2lo_map* map, const float* local_xyz, size_t m
   return icp_optimize_common(map, ctx->d_query, ctx->d_nquery, m, T_init, cfg, T_out, stats);
 }
 
+// parity tap: ONE Gauss-Newton iteration (the loop body ICP.cpp:280-448) entered at T_in with the residual normalisation scale an earlier
+// iteration fixed (scale <= 0: computed from this pose's residuals, as iteration 0 does)
+extern "C" int b2lo_icp_iterate(b2lo_map* map, const float* local_xyz, size_t m, size_t stride_floats, const float T_in[16], double scale,
+                                const b2lo_icp_cfg* cfg, float T_out[16], b2lo_icp_stats* stats) {
+  if (!map || !cfg) return B2LO_E_ARG;
+  b2lo_icp_cfg one = *cfg;
+  one.max_iterations = 1;
+  {
+    std::lock_guard<std::recursive_mutex> lk(map->ctx->mu);
+    map->ctx->force_scale = scale > 0.0 ? scale : 0.0;
+  }
+  int rc = b2lo_icp_optimize(map, local_xyz, m, stride_floats, T_in, &one, T_out, stats);
+  map->ctx->force_scale = 0.0;
+  return rc;
+}
+
 extern "C" int b2lo_icp_optimize_features(b2lo_map* map, const float T_init[16], const b2lo_icp_cfg* cfg, float T_out[16], b2lo_icp_stats* stats) {
   if (!map || !T_init || !cfg || !T_out) return B2LO_E_ARG;
   std::lock_guard<std::recursive_mutex> lk(map->mu);
   b2lo_ctx* ctx = map->ctx;
-  std::lock_guard<std::mutex> lk2(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk2(ctx->mu);
   cudaSetDevice(ctx->device);
-  if (map->n0 == 0 || ctx->feat_cap_hint == 0) {
+  // the features of the scan filtered LAST: after a look-ahead run they may sit in the second set (what b2lo_ctx_features reads)
+  const int set = ctx->feat_set;
+  const size_t cap = ctx->feat_cap_hint_set[set];
+  if (map->n0 == 0 || cap == 0) {
     std::memcpy(T_out, T_init, 16 * sizeof(float));
     if (stats) { std::memset(stats, 0, sizeof *stats); stats->status = B2LO_S_INSUFFICIENT; }
     return B2LO_S_INSUFFICIENT;
   }
-  return icp_optimize_common(map, ctx->d_feat, ctx->d_nfeat, ctx->feat_cap_hint, T_init, cfg, T_out, stats);
+  return icp_optimize_common(map, ctx->feat(set), ctx->nfeat(set), cap, T_init, cfg, T_out, stats);
 }
 
 // ---- pose algebra (host; the same inline functions the device uses) ----------------------------------------------

@@ -37,7 +37,7 @@ extern "C" int b2lo_voxel_grid_filter(b2lo_ctx* ctx, const float* xyz, size_t n,
   *m = 0;
   if (stride_floats < 3) { set_error("voxel grid: bad stride"); return B2LO_E_ARG; }
   if (!xyz || n == 0 || !(leaf_size > 0.0f)) return B2LO_S_EMPTY;   // output.clear() (PointCloudUtils.h:471-474)
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
   int rc = ctx_stage_h2d(ctx, xyz, n, stride_floats, 1, nullptr, nullptr);
@@ -48,7 +48,7 @@ extern "C" int b2lo_voxel_grid_filter(b2lo_ctx* ctx, const float* xyz, size_t n,
   B2_CUDA(cudaStreamSynchronize(st));
   const size_t M = (size_t)ctx->h_counts[18];
   ctx->d2h_bytes += sizeof(int);
-  ctx->feat_cap_hint = 0;   // the feature buffer now holds map voxels, not scan features
+  ctx->feat_cap_hint = 0; ctx->feat_cap_hint_set[0] = 0; ctx->feat_set = 0;   // the feature buffer now holds map voxels, not scan features
   if (M == 0) return B2LO_OK;
   if (M > cap || !out_xyz) { *m = M; set_error("voxel grid: output buffer too small (%zu < %zu)", cap, M); return B2LO_E_CAPACITY; }
   Scratch s;

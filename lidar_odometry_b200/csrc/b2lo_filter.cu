@@ -235,6 +235,7 @@ int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sam
                const b2lo_record_fmt* fmt, int mode) {
   cudaStream_t st = on ? on : ctx->stream;
   if (set == 0) ctx->feat_set = 0;
+  ctx->feat_cap_hint_set[set] = n_samples;
   if (n_samples == 0) { if (set == 0) ctx->feat_cap_hint = 0; B2_CUDA(cudaMemsetAsync(ctx->nfeat(set), 0, sizeof(int), st)); return B2LO_OK; }
   if (n_samples > (size_t)INT_MAX / 4) { set_error("filter: too many samples"); return B2LO_E_CAPACITY; }
   int rc = ctx_reserve_points(ctx, n_samples);

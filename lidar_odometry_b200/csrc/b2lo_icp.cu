@@ -25,6 +25,8 @@
 namespace b2 {
 
 constexpr int TILE = 256;
+// the slice of the scan parameter block an optimize outside the per-scan driver refreshes: initial pose + forced scale
+constexpr size_t SP_POSE_BYTES = offsetof(ScanParams, force_scale) + sizeof(double) - offsetof(ScanParams, T_init);
 constexpr int PKO_THREADS = 256;
 constexpr int MAXS = 128;  // max GMM sample size / alpha candidates handled
 
@@ -40,7 +42,9 @@ __device__ __forceinline__ void transform_point(const float* R, const float* t, 
 __device__ __forceinline__ void icp_state_begin(IcpState* st, const ScanParams* sp) {
   for (int i = 0; i < 16; ++i) st->T_init[i] = sp->T_init[i];
   for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) st->R[i * 3 + j] = st->T_init[i * 4 + j]; st->t[i] = st->T_init[i * 4 + 3]; }
-  st->iter = 0; st->done = 0; st->status = B2LO_OK; st->n_corr = 0; st->scale = 1.0; st->delta = 0.0; st->ticket = 0u; st->ticket_corr = 0u;
+  const double fs = sp->force_scale;
+  st->iter = 0; st->done = 0; st->status = B2LO_OK; st->n_corr = 0; st->scale = fs > 0.0 ? fs : 1.0; st->scale_forced = fs > 0.0 ? 1 : 0;
+  st->delta = 0.0; st->ticket = 0u; st->ticket_corr = 0u;
   st->num_iterations = 0; st->converged = 0; st->initial_cost = 0.0; st->final_cost = 0.0; st->em_iters = 0; st->kmeans_iters = 0;
 }
 
@@ -526,7 +530,7 @@ __device__ __noinline__ void pko1_body(const int* d_npts, IcpState* st, IcpParam
   // 2. residual normalisation scale, first iteration only (ICP.cpp:304-316)
   c1 = clock64();
   double scale = st->scale;
-  if (st->iter == 0) {
+  if (st->iter == 0 && !st->scale_forced) {
     // population sigma / 6 from the per-tile raw moments K2 left behind (var = E[r^2] - mean^2)
     double a1 = 0.0, a2 = 0.0;
     for (int t = tid; t < ntiles; t += blockDim.x) { a1 += __ldcg(&tilesum[2 * t]); a2 += __ldcg(&tilesum[2 * t + 1]); }
@@ -1043,7 +1047,8 @@ int icp_prepare(b2lo_ctx* ctx, const b2lo_icp_cfg* cfg) {
 int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_cap, const float* T_init16, const b2lo_icp_cfg* cfg,
             bool init_pose_on_device, bool restore_on_failure) {
   b2lo_ctx* ctx = map->ctx;
-  if (cfg->max_iterations < 1 || cfg->max_iterations > B2LO_MAX_ITERS) { set_error("max_iterations must be in [1,%d]", B2LO_MAX_ITERS); return B2LO_E_ARG; }
+  // any iteration count >= 1 (ICPConfig's default is 50, ICP.h:57); only the per-iteration trace is limited to the first B2LO_MAX_ITERS
+  if (cfg->max_iterations < 1) { set_error("max_iterations must be >= 1"); return B2LO_E_ARG; }
   const bool surfel = cfg->use_surfel_correspondence != 0;
   int rc = icp_build_pko(ctx, cfg);
   if (rc) return rc;
@@ -1060,8 +1065,10 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
   if (!ctx->sp_preloaded) {
     if ((rc = sp_begin_write(ctx))) return rc;
     for (int i = 0; i < 16; ++i) ctx->h_sp->T_init[i] = T_init16[i];
-    if ((rc = sp_upload(ctx, offsetof(ScanParams, T_init), sizeof(float) * 16))) return rc;
+    ctx->h_sp->force_scale = ctx->force_scale;
+    if ((rc = sp_upload(ctx, offsetof(ScanParams, T_init), SP_POSE_BYTES))) return rc;
   }
+  ctx->force_scale = 0.0;
   int grid_knn = (int)((npts_cap + 7) / 8);   // one warp per query, 8 per CTA
   if (grid_knn > ctx->sm_count * 8) grid_knn = ctx->sm_count * 8;
   if (grid_knn < 1) grid_knn = 1;
@@ -1071,6 +1078,9 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
   const bool fuse = surfel && !(ctx->prof && ctx->prof->on) && npts_cap <= 65536;
   const CorrLaunch cl = corr_launch(ctx, ctiles_cap, fuse);
   if (!fuse) { k_icp_begin<<<1, 32, 0, s>>>(ctx->d_icp, ctx->d_sp); ctx->launches++; }   // fused: the first correspondence pass initialises the state
+  cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s, &cap_status);
+  const bool capturing = cap_status != cudaStreamCaptureStatusNone;
   int ntiles_cap = (int)((npts_cap + TILE - 1) / TILE);
   int grid = ntiles_cap < 1 ? 1 : (ntiles_cap > ctx->i_max_blocks ? ctx->i_max_blocks : ntiles_cap);
   double* gmm = ctx->i_partial + (size_t)ctx->i_max_blocks * 28;      // 9 GMM doubles, then P(r_k) at [16, 116)
@@ -1107,6 +1117,12 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
     else k_icp_gn<false><<<grid, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->k_plane, ctx->i_partial, nullptr);
     prof_end(ctx);
     ctx->launches += (cfg->use_adaptive_m_estimator ? 4 : 3) - (fuse ? 1 : 0);
+    // long runs (max_iterations beyond the usual 4): look at the done flag every 8 iterations instead of enqueueing dozens of no-op launches
+    if (!capturing && (it & 7) == 7 && it + 1 < cfg->max_iterations) {
+      B2_CUDA(cudaMemcpyAsync(ctx->h_counts + 48, &ctx->d_icp->done, sizeof(int), cudaMemcpyDeviceToHost, s));
+      B2_CUDA(cudaStreamSynchronize(s));
+      if (ctx->h_counts[48]) break;
+    }
   }
   // the per-scan driver's decision kernel never reads the pose of a failed optimize (it falls back to the motion-model guess itself)
   if (restore_on_failure) { k_icp_end<<<1, 32, 0, s>>>(ctx->d_icp); ctx->launches++; }
@@ -1204,7 +1220,7 @@ extern "C" int b2lo_icp_correspondences(b2lo_map* map, const float* local_xyz, s
   if (!local_xyz || m == 0) return B2LO_S_EMPTY;
   std::lock_guard<std::recursive_mutex> lk(map->mu);
   b2lo_ctx* ctx = map->ctx;
-  std::lock_guard<std::mutex> lk2(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk2(ctx->mu);
   cudaSetDevice(ctx->device);
   { int rr = ctx_reserve_points(ctx, m); if (rr) return rr; }  // may reallocate d_query: reserve before taking the pointer
   int rc = ctx_stage_h2d(ctx, local_xyz, m, stride_floats, 1, ctx->d_query, ctx->d_nquery);
@@ -1263,7 +1279,7 @@ extern "C" int b2lo_icp_correspondences_knn(b2lo_map* map, const float* local_xy
   if (!local_xyz || m == 0) return B2LO_S_EMPTY;
   std::lock_guard<std::recursive_mutex> lk(map->mu);
   b2lo_ctx* ctx = map->ctx;
-  std::lock_guard<std::mutex> lk2(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk2(ctx->mu);
   cudaSetDevice(ctx->device);
   { int rr = ctx_reserve_points(ctx, m); if (rr) return rr; }  // may reallocate d_query: reserve before taking the pointer
   int rc = ctx_stage_h2d(ctx, local_xyz, m, stride_floats, 1, ctx->d_query, ctx->d_nquery);
@@ -1272,7 +1288,8 @@ extern "C" int b2lo_icp_correspondences_knn(b2lo_map* map, const float* local_xy
   cudaStream_t s = ctx->stream;
   if ((rc = sp_begin_write(ctx))) return rc;
   for (int i = 0; i < 16; ++i) ctx->h_sp->T_init[i] = T16[i];
-  if ((rc = sp_upload(ctx, offsetof(ScanParams, T_init), sizeof(float) * 16))) return rc;
+  ctx->h_sp->force_scale = 0.0;
+  if ((rc = sp_upload(ctx, offsetof(ScanParams, T_init), SP_POSE_BYTES))) return rc;
   k_icp_begin<<<1, 32, 0, s>>>(ctx->d_icp, ctx->d_sp);
   int grid = (int)((m + 7) / 8);
   if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
@@ -1319,7 +1336,8 @@ static void shard_params(const b2lo_icp_cfg* cfg, size_t npts_cap, IcpParams& pr
 static int shard_check(b2lo_map* map, const b2lo_icp_cfg* cfg) {
   if (!map || !cfg) return B2LO_E_ARG;
   if (!cfg->use_surfel_correspondence) { set_error("the point-sharded mode supports surfel correspondence only"); return B2LO_E_ARG; }
-  if (cfg->max_iterations < 1 || cfg->max_iterations > B2LO_MAX_ITERS) { set_error("max_iterations must be in [1,%d]", B2LO_MAX_ITERS); return B2LO_E_ARG; }
+  // any iteration count >= 1 (ICPConfig's default is 50, ICP.h:57); only the per-iteration trace is limited to the first B2LO_MAX_ITERS
+  if (cfg->max_iterations < 1) { set_error("max_iterations must be >= 1"); return B2LO_E_ARG; }
   return B2LO_OK;
 }
 extern "C" int b2lo_icp_shard_begin(b2lo_map* map, const float* local_xyz, size_t m, size_t stride_floats, const float T_init[16], const b2lo_icp_cfg* cfg) {
@@ -1328,7 +1346,7 @@ extern "C" int b2lo_icp_shard_begin(b2lo_map* map, const float* local_xyz, size_
   if (!T_init || stride_floats < 3) return B2LO_E_ARG;
   std::lock_guard<std::recursive_mutex> lk(map->mu);
   b2lo_ctx* ctx = map->ctx;
-  std::lock_guard<std::mutex> lk2(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk2(ctx->mu);
   cudaSetDevice(ctx->device);
   if ((rc = icp_build_pko(ctx, cfg))) return rc;
   { int rr = ctx_reserve_points(ctx, m); if (rr) return rr; }  // may reallocate d_query: reserve before taking the pointer
@@ -1336,7 +1354,8 @@ extern "C" int b2lo_icp_shard_begin(b2lo_map* map, const float* local_xyz, size_
   ctx->shard_m = m;
   if ((rc = sp_begin_write(ctx))) return rc;
   for (int i = 0; i < 16; ++i) ctx->h_sp->T_init[i] = T_init[i];
-  if ((rc = sp_upload(ctx, offsetof(ScanParams, T_init), sizeof(float) * 16))) return rc;
+  ctx->h_sp->force_scale = 0.0;
+  if ((rc = sp_upload(ctx, offsetof(ScanParams, T_init), SP_POSE_BYTES))) return rc;
   k_icp_begin<<<1, 32, 0, ctx->stream>>>(ctx->d_icp, ctx->d_sp);
   ctx->launches++;
   B2_CUDA(cudaGetLastError());
@@ -1531,7 +1550,7 @@ extern "C" int b2lo_icp_optimize_loop(b2lo_ctx* ctx, const float* curr_xyz, size
                                       const b2lo_icp_cfg* cfg, float T_rel[16], float* inlier_ratio, b2lo_icp_stats* stats) {
   if (!ctx || !T_curr || !T_matched || !cfg || !T_rel) return B2LO_E_ARG;
   if (curr_stride_floats < 3 || matched_stride_floats < 3) return B2LO_E_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   cudaSetDevice(ctx->device);
   if (inlier_ratio) *inlier_ratio = 0.0f;
   if (stats) std::memset(stats, 0, sizeof *stats);
@@ -1576,7 +1595,8 @@ extern "C" int b2lo_icp_optimize_loop(b2lo_ctx* ctx, const float* curr_xyz, size
   prm.ctile = TILE;
   if ((rc = sp_begin_write(ctx))) return rc;
   for (int i = 0; i < 16; ++i) ctx->h_sp->T_init[i] = T_curr[i];
-  if ((rc = sp_upload(ctx, offsetof(ScanParams, T_init), sizeof(float) * 16))) return rc;
+  ctx->h_sp->force_scale = 0.0;
+  if ((rc = sp_upload(ctx, offsetof(ScanParams, T_init), SP_POSE_BYTES))) return rc;
   k_icp_begin<<<1, 32, 0, s>>>(ctx->d_icp, ctx->d_sp);
   ctx->launches++;
   const int ntiles = (int)((m_curr + TILE - 1) / TILE);

@@ -217,7 +217,7 @@ extern "C" int b2lo_filter_records_dev(b2lo_ctx* ctx, const void* records_dev, s
   if (stride < 1 || !(voxel_size > 0.0f)) { set_error("filter: bad stride / voxel size"); return B2LO_E_ARG; }
   int rc = check_fmt(fmt);
   if (rc) return rc;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   cudaSetDevice(ctx->device);
   if (!records_dev || n_records == 0) { B2_CUDA(cudaMemsetAsync(ctx->d_nfeat, 0, sizeof(int), ctx->stream)); return B2LO_S_EMPTY; }
   const size_t ns = (n_records + (size_t)stride - 1) / (size_t)stride;
@@ -234,7 +234,7 @@ extern "C" int b2lo_filter_records(b2lo_ctx* ctx, const void* records, size_t n_
   if (!records || n_records == 0) return B2LO_S_EMPTY;
   const size_t ns = (n_records + (size_t)stride - 1) / (size_t)stride;
   {
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     cudaSetDevice(ctx->device);
     // page-locked image: K1 reads the sampled records in place over PCIe; pageable: gather the sampled coordinates, one H2D
     cudaPointerAttributes attr;

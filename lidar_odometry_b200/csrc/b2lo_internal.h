@@ -45,6 +45,7 @@ struct IcpState {                 // lives in device memory, one per context
   int n_corr, n_blocks;
   double scale, delta;
   int em_iters, kmeans_iters;
+  int scale_forced;               // the scale came from ScanParams::force_scale: iteration 0 must not recompute it
   unsigned int ticket;            // last-block election of the GN reduction
   unsigned int ticket_corr;       // last-block election of the correspondence kernel (fused PKO fit)
   int num_iterations; int converged; double initial_cost, final_cost;
@@ -63,6 +64,7 @@ struct ScanParams {
   unsigned int flt_rec; unsigned int flt_off[3];
   unsigned int flt_mode;   // 0: FastVoxelFilter (Z-order key of floor(x * inv), centroid = sum / count); 1: util::VoxelGrid (b2lo_export.cu)
   float T_init[16];                                                                   // ICP initial pose
+  double force_scale;      // parity tap (b2lo_icp_iterate): > 0 -> residual normalisation scale given by the caller instead of iteration 0's
   DecideArgs decide;                                                                  // odometry tail
 };
 
@@ -95,7 +97,8 @@ struct b2lo_ctx {
   unsigned long long alloc_epoch = 1;   // bumped whenever a device buffer of the context is reallocated (invalidates captured graphs)
   int sm_count = 148;
   size_t shard_m = 0;              // query count of the current point-sharded optimize (b2lo_icp_shard_begin)
-  size_t feat_cap_hint = 0;        // host-known upper bound of *d_nfeat (samples of the last filter run)
+  size_t feat_cap_hint = 0;        // host-known upper bound of *d_nfeat (samples of the last filter run into set 0)
+  size_t feat_cap_hint_set[2] = {0, 0};   // the same bound per feature set (b2lo_icp_optimize_features follows feat_set)
   cudaGraphExec_t icp_graph_exec = nullptr; unsigned long long icp_graph_sig = 0;
   b2::MapDev* d_mapdev = nullptr;
   // capacities (points)
@@ -137,8 +140,9 @@ struct b2lo_ctx {
   b2::ScanParams* d_sp = nullptr; b2::ScanParams* h_sp = nullptr /*pinned*/; cudaEvent_t ev_sp = nullptr; bool sp_busy = false;
   bool sp_preloaded = false;       // the caller has already uploaded the whole parameter block for this launch sequence
   b2::Prof* prof = nullptr;
+  double force_scale = 0.0;        // next icp_run: ScanParams::force_scale (b2lo_icp_iterate), reset by icp_run
   double host_us[8] = {0};         // wall-clock split of the host side of b2lo_odom_process (debug aid): gather, enqueue, wait, ...
-  std::mutex mu;
+  std::recursive_mutex mu;   // taken AFTER a map's mutex by every entry point that touches the context's staging buffers, counters or stream
 };
 
 struct b2lo_map {

@@ -968,6 +968,7 @@ extern "C" int b2lo_map_destroy(b2lo_map* m) {
 extern "C" int b2lo_map_clear(b2lo_map* m) {
   if (!m) return B2LO_E_ARG;
   std::lock_guard<std::recursive_mutex> lk(m->mu);
+  std::lock_guard<std::recursive_mutex> lkc(m->ctx->mu);   // the context's staging buffers / counters / stream (same order as b2lo_icp_optimize)
   cudaSetDevice(m->ctx->device);
   cudaStream_t st = m->ctx->stream;
   B2_CUDA(cudaMemsetAsync(m->d.l0_tab, 0xFF, m->tcap0 * sizeof(L0Entry), st));
@@ -987,6 +988,7 @@ extern "C" int b2lo_map_update(b2lo_map* m, const float* world_xyz, size_t n, si
   if (!world_xyz || n == 0) return B2LO_S_EMPTY;  // VoxelMap.cpp:134-136
   if (stride_floats < 3) return B2LO_E_ARG;
   std::lock_guard<std::recursive_mutex> lk(m->mu);
+  std::lock_guard<std::recursive_mutex> lkc(m->ctx->mu);   // the context's staging buffers / counters / stream (same order as b2lo_icp_optimize)
   b2lo_ctx* ctx = m->ctx;
   cudaSetDevice(ctx->device);
   int rc = ctx_reserve_points(ctx, n);
@@ -1001,6 +1003,7 @@ extern "C" int b2lo_map_update(b2lo_map* m, const float* world_xyz, size_t n, si
 extern "C" int b2lo_map_counts(b2lo_map* m, size_t* l0, size_t* l1, size_t* surfels) {
   if (!m) return B2LO_E_ARG;
   std::lock_guard<std::recursive_mutex> lk(m->mu);
+  std::lock_guard<std::recursive_mutex> lkc(m->ctx->mu);   // the context's staging buffers / counters / stream (same order as b2lo_icp_optimize)
   b2lo_ctx* ctx = m->ctx;
   if (l0) *l0 = m->n0;
   if (l1) *l1 = m->n1;
@@ -1019,6 +1022,7 @@ extern "C" int b2lo_map_counts(b2lo_map* m, size_t* l0, size_t* l1, size_t* surf
 extern "C" int b2lo_map_export_l0(b2lo_map* m, float* xyz, int* keys, int* counts, size_t cap, size_t* n) {
   if (!m || !n) return B2LO_E_ARG;
   std::lock_guard<std::recursive_mutex> lk(m->mu);
+  std::lock_guard<std::recursive_mutex> lkc(m->ctx->mu);   // the context's staging buffers / counters / stream (same order as b2lo_icp_optimize)
   b2lo_ctx* ctx = m->ctx;
   *n = m->n0;
   if (m->n0 == 0) return B2LO_OK;
@@ -1083,11 +1087,13 @@ extern "C" int b2lo_map_export_l1(b2lo_map* m, int* keys, int* nchild, int* chil
                                   float* planarity, int* last_child_count, size_t cap, size_t* n) {
   if (!m || !n) return B2LO_E_ARG;
   std::lock_guard<std::recursive_mutex> lk(m->mu);
+  std::lock_guard<std::recursive_mutex> lkc(m->ctx->mu);   // the context's staging buffers / counters / stream (same order as b2lo_icp_optimize)
   return export_l1_common(m, 0, keys, nchild, children, has_surfel, normal, centroid, planarity, last_child_count, cap, n);
 }
 extern "C" int b2lo_map_export_surfels(b2lo_map* m, float* centroid, float* normal, float* planarity, int* l1keys, size_t cap, size_t* n) {
   if (!m || !n) return B2LO_E_ARG;
   std::lock_guard<std::recursive_mutex> lk(m->mu);
+  std::lock_guard<std::recursive_mutex> lkc(m->ctx->mu);   // the context's staging buffers / counters / stream (same order as b2lo_icp_optimize)
   return export_l1_common(m, 1, l1keys, nullptr, nullptr, nullptr, normal, centroid, planarity, nullptr, cap, n);
 }
 
@@ -1100,6 +1106,7 @@ int b2::map_rebuild_knn_locked(b2lo_map* m) {
 extern "C" int b2lo_map_rebuild_knn(b2lo_map* m) {
   if (!m) return B2LO_E_ARG;
   std::lock_guard<std::recursive_mutex> lk(m->mu);
+  std::lock_guard<std::recursive_mutex> lkc(m->ctx->mu);   // the context's staging buffers / counters / stream (same order as b2lo_icp_optimize)
   return map_rebuild_knn_locked(m);
 }
 extern "C" int b2lo_map_has_knn(b2lo_map* m) { return (m && m->knn_ready) ? 1 : 0; }
@@ -1109,6 +1116,7 @@ extern "C" int b2lo_map_has_knn(b2lo_map* m) { return (m && m->knn_ready) ? 1 : 
 extern "C" int b2lo_map_transform_rehash(b2lo_map* m, const float T16[16]) {
   if (!m || !T16) return B2LO_E_ARG;
   std::lock_guard<std::recursive_mutex> lk(m->mu);
+  std::lock_guard<std::recursive_mutex> lkc(m->ctx->mu);   // the context's staging buffers / counters / stream (same order as b2lo_icp_optimize)
   b2lo_ctx* ctx = m->ctx;
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;

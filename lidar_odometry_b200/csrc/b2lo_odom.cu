@@ -278,6 +278,7 @@ static int steady_begin(b2lo_odom* od, const float* src_dev, size_t ns, size_t s
   sp_set_fmt(sp, mode == K1_NEXT ? (od->has_fmt ? &od->fmt : nullptr) : eff);
   sp->flt_mode = 0;
   pose_to_T16(init, sp->T_init);
+  sp->force_scale = 0.0;
   pose_to_T16(guess, sp->decide.guess);
   pose_to_T16(od->last_kf_pose, sp->decide.last_kf);
   sp->decide.ran_icp = 1; sp->decide.n_keyframes = od->n_keyframes;
@@ -425,7 +426,7 @@ extern "C" int b2lo_odom_process(b2lo_odom* od, const float* xyz, size_t n, size
   if (!xyz || n == 0) { std::memset(res, 0, sizeof *res); return B2LO_S_EMPTY; }
   b2lo_ctx* ctx = od->ctx;
   std::lock_guard<std::recursive_mutex> lk(od->map->mu);
-  std::lock_guard<std::mutex> lk2(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk2(ctx->mu);
   cudaSetDevice(ctx->device);
   const size_t S = (size_t)(od->cfg.point_stride < 1 ? 1 : od->cfg.point_stride);
   const size_t ns = (n + S - 1) / S;
@@ -473,7 +474,7 @@ extern "C" int b2lo_odom_process_dev(b2lo_odom* od, const float* xyz_dev, size_t
   if (!xyz_dev || n == 0) { std::memset(res, 0, sizeof *res); return B2LO_S_EMPTY; }
   b2lo_ctx* ctx = od->ctx;
   std::lock_guard<std::recursive_mutex> lk(od->map->mu);
-  std::lock_guard<std::mutex> lk2(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk2(ctx->mu);
   cudaSetDevice(ctx->device);
   const size_t S = (size_t)(od->cfg.point_stride < 1 ? 1 : od->cfg.point_stride);
   const size_t ns = (n + S - 1) / S;
@@ -563,7 +564,7 @@ extern "C" int b2lo_odom_lookahead(b2lo_odom* od, const float* xyz_next, size_t 
   if (stride_floats < 3) return B2LO_E_ARG;
   b2lo_ctx* ctx = od->ctx;
   std::lock_guard<std::recursive_mutex> lk(od->map->mu);
-  std::lock_guard<std::mutex> lk2(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk2(ctx->mu);
   od->la_valid = false;
   if (!xyz_next || n == 0) return B2LO_S_EMPTY;
   cudaSetDevice(ctx->device);
@@ -595,7 +596,7 @@ extern "C" int b2lo_odom_process_la(b2lo_odom* od, const float* xyz, size_t n, s
 extern "C" int b2lo_odom_set_record_fmt(b2lo_odom* od, const b2lo_record_fmt* fmt) {
   if (!od) return B2LO_E_ARG;
   std::lock_guard<std::recursive_mutex> lk(od->map->mu);
-  std::lock_guard<std::mutex> lk2(od->ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk2(od->ctx->mu);
   if (fmt) {
     if (fmt->record_bytes == 0) { set_error("records: no format"); return B2LO_E_ARG; }
     for (int a = 0; a < 3; ++a)
