@@ -527,3 +527,19 @@ extern "C" void b2lo_svd3(const float A9[9], float U9[9], float S3[3], float V9[
 extern "C" void b2lo_ldlt6_solve(const float H36[36], const float b6[6], float x6[6]) { ldlt6_solve(H36, b6, x6); }
 extern "C" void b2lo_fit_plane(const float* pts, int n, float mu[3], float normal[3], float* planarity) { fit_plane(pts, n, mu, normal, planarity); }
 extern "C" uint64_t b2lo_voxel_key_hash(int x, int y, int z) { return key_morton(x, y, z); }
+
+// ---- in-graph timeline (debug builds only, see b2lo_dev.cuh) ---------------------------------------------------------------------
+#ifdef B2LO_TIMELINE
+namespace b2 { int tl_fetch_filter(unsigned long long*, int); int tl_fetch_icp(unsigned long long*, int); int tl_fetch_odom(unsigned long long*, int);
+               int tl_fetch_map(unsigned long long*, int); }
+// out: pairs (file id << 32 | source line, %globaltimer ns), unsorted; returns the number of marks and clears the buffers
+extern "C" int b2lo_debug_timeline(unsigned long long* out, int cap) {
+  cudaDeviceSynchronize();
+  int n = 0;
+  n += b2::tl_fetch_filter(out + 2 * n, cap - n);
+  n += b2::tl_fetch_icp(out + 2 * n, cap - n);
+  n += b2::tl_fetch_odom(out + 2 * n, cap - n);
+  n += b2::tl_fetch_map(out + 2 * n, cap - n);
+  return n;
+}
+#endif

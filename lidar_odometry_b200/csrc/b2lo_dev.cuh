@@ -18,6 +18,44 @@
 #include <cstdint>
 #include "b2lo_math.cuh"
 
+// ---- in-graph timeline (debug builds only: make TIMELINE=1 -> libb2lo_tl.so) ----------------------------------------------------
+// A replayed CUDA graph is one opaque item to ncu, and its serialised, cold-cache launch list says nothing about the gaps between
+// kernels.  With -DB2LO_TIMELINE the first thread of every kernel of the per-scan path files (file id, source line, %globaltimer) into a
+// per-translation-unit buffer; b2lo_debug_timeline() merges them by time, which gives the start-to-start intervals of the scan's
+// kernels as they really run inside the graph (tools/gpu_timeline.py).  The macro is empty in the product build.
+#ifdef B2LO_TIMELINE
+#ifndef B2LO_TL_FILE
+#define B2LO_TL_FILE 0
+#endif
+namespace b2 {
+constexpr int TL_CAP = 4096;
+static __device__ unsigned long long g_tl[2 * TL_CAP];
+static __device__ unsigned int g_tl_n;
+__device__ __forceinline__ void tl_mark(int line) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  const unsigned int i = atomicAdd(&g_tl_n, 1u);
+  if (i < TL_CAP) { g_tl[2 * i] = ((unsigned long long)B2LO_TL_FILE << 32) | (unsigned)line; g_tl[2 * i + 1] = t; }
+}
+// host side of this translation unit's buffer: copies the marks out and clears the counter
+static inline int tl_fetch(unsigned long long* out, int cap) {
+  unsigned int n = 0;
+  cudaMemcpyFromSymbol(&n, g_tl_n, sizeof n);
+  if ((int)n > TL_CAP) n = TL_CAP;
+  if ((int)n > cap) n = cap;
+  if (n) cudaMemcpyFromSymbol(out, g_tl, sizeof(unsigned long long) * 2 * n);
+  unsigned int zero = 0;
+  cudaMemcpyToSymbol(g_tl_n, &zero, sizeof zero);
+  return (int)n;
+}
+}  // namespace b2
+#define TL_START() do { if (threadIdx.x == 0 && blockIdx.x == 0) b2::tl_mark(__LINE__); } while (0)
+#define TL_HERE() b2::tl_mark(__LINE__)
+#else
+#define TL_START() do {} while (0)
+#define TL_HERE() do {} while (0)
+#endif
+
 namespace b2 {
 
 constexpr uint64_t KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;

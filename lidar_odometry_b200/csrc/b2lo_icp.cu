@@ -19,6 +19,7 @@
 #include <climits>
 #include <cstdlib>
 #include <cstring>
+#define B2LO_TL_FILE 2
 #include "b2lo_internal.h"
 #include "b2lo_knn.cuh"
 
@@ -128,7 +129,7 @@ __device__ __noinline__ void pko1_body(const int* d_npts, IcpState* st, IcpParam
 template <int DEPTH, int MINB, bool FUSE>
 __global__ void __launch_bounds__(TILE, MINB) k_icp_corr(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, IcpState* st,
                                                    IcpParams prm, double* res, int* slot_out, int* cidx, int* tilecnt, double* tilesum,
-                                                   int* tileoff, const PkoTables* T, const int* hits, double* gmm_out, const ScanParams* sp_first) {
+                                                   int* tileoff, const PkoTables* T, const int* hits, double* gmm_out, const ScanParams* sp_first) { TL_START();
   // sp_first != nullptr (FUSE only): this is the first correspondence pass of an optimize and no k_icp_begin ran - the pose comes from the
   // scan parameter block, a stale `done` flag is ignored, and the elected last CTA initialises the state before it enters the fit
   __shared__ float sR[9], sT[3];
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(TILE, MINB) k_icp_corr(MapDev M, const float4*
 // ---- KDTree-mode correspondence (K3) ----------------------------------------------------------------
 // search: one warp per query probes the cell shells of the L0 hash (27, then 98 cells, one lane per cell); unresolved queries are queued
 __global__ void __launch_bounds__(TILE) k_knn_search(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, IcpState* st,
-                                                     int* knn_idx, int* knn_n, int* unres, int* n_unres) {
+                                                     int* knn_idx, int* knn_n, int* unres, int* n_unres) { TL_START();
   if (st->done) return;
   __shared__ float sR[9], sT[3];
   if (threadIdx.x < 9) sR[threadIdx.x] = st->R[threadIdx.x];
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(TILE) k_knn_search(MapDev M, const float4* __r
 }
 // exact scan for the queued queries: one warp per query over the dense L0 centroid stream
 __global__ void __launch_bounds__(256) k_knn_brute(MapDev M, const float4* __restrict__ pts, IcpState* st, int* knn_idx, int* knn_n,
-                                                   const int* __restrict__ unres, const int* __restrict__ n_unres) {
+                                                   const int* __restrict__ unres, const int* __restrict__ n_unres) { TL_START();
   if (st->done) return;
   const int nu = *n_unres;
   const int n0 = M.ctr[0];
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(256) k_knn_brute(MapDev M, const float4* __res
 // plane fit + gate + per-tile compaction (same outputs as k_icp_corr, plus the per-query plane)
 __global__ void __launch_bounds__(TILE) k_knn_gate(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, IcpState* st, IcpParams prm,
                                                    const int* __restrict__ knn_idx, const int* __restrict__ knn_n, int* n_unres, double* res,
-                                                   int* slot_out, int* cidx, int* tilecnt, float4* plane, double* tilesum) {
+                                                   int* slot_out, int* cidx, int* tilecnt, float4* plane, double* tilesum) { TL_START();
   if (st->done) return;
   __shared__ int sm[40];
   __shared__ double smd2[16];
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(TILE) k_knn_gate(MapDev M, const float4* __res
 }
 // parity tap of the KDTree-mode correspondence at the pose held in st
 __global__ void k_knn_taps(MapDev M, const float4* __restrict__ pts, int npts, IcpState* st, double max_dist, const int* __restrict__ knn_idx,
-                           const int* __restrict__ knn_n, int* idx_out, float* d2_out, int* found, int* state, float* nout, float* cout, double* res) {
+                           const int* __restrict__ knn_n, int* idx_out, float* d2_out, int* found, int* state, float* nout, float* cout, double* res) { TL_START();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npts) return;
   float4 p = pts[i];
@@ -486,6 +487,7 @@ __device__ __noinline__ void pko1_body(const int* d_npts, IcpState* st, IcpParam
                                        int* tileoff, const PkoTables* T, const int* hits, double* gmm_out, const double* ext_sample, int ext_C,
                                        double ext_scale, const double* tilesum) {
   if (st->done) return;
+  if (threadIdx.x == 0) TL_HERE();   // fit begins
   __shared__ int sm[40];
   __shared__ double smd[40];
   __shared__ double s_x[MAXS];
@@ -685,6 +687,7 @@ __device__ __noinline__ void pko1_body(const int* d_npts, IcpState* st, IcpParam
     const long long c5 = clock64();
     long long* dg = st->dbg + 8 * (st->iter & 1);
     dg[0] = c1 - c0; dg[1] = c2 - c1; dg[2] = c3 - c2; dg[3] = c4 - c3; dg[4] = c5 - c4; dg[5] = em_iters; dg[6] = km_iters;
+    TL_HERE();   // EM done
   }
   // 7. P(r_k) of the fitted mixture on the JS grid r_k = dr * (1 + k) (:741-752), shared by all alpha candidates
   for (int k = tid; k < 100; k += 96) {
@@ -699,14 +702,14 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
                                                            const int* __restrict__ slot, const int* __restrict__ cidx, const int* __restrict__ tilecnt,
                                                            int* tileoff, const PkoTables* __restrict__ T, const int* __restrict__ hits, double* gmm_out,
                                                            const double* __restrict__ ext_sample, int ext_C, double ext_scale,
-                                                           const double* __restrict__ tilesum) {
+                                                           const double* __restrict__ tilesum) { TL_START();
   (void)slot;
   pko1_body(d_npts, st, prm, res, cidx, tilecnt, tileoff, T, hits, gmm_out, ext_sample, ext_C, ext_scale, tilesum);
 }
 
 // one CTA per alpha candidate i = 1..S (blockIdx.x + 1); thread k handles r_k = dr * (1 + k); the last CTA takes the arg-min
 __global__ void __launch_bounds__(128) k_icp_pko2(IcpState* st, IcpParams prm, const PkoTables* __restrict__ T, const double* __restrict__ gmm,
-                                                   double* js, unsigned int* ticket) {
+                                                   double* js, unsigned int* ticket) { TL_START();
   __shared__ double s_c[4], s_n[4];
   __shared__ int s_i[4];
   __shared__ int s_last;
@@ -832,7 +835,7 @@ __device__ void gn_finish(IcpState* st, const IcpParams& prm, const double* acc 
 template <bool SURFEL>
 __global__ void __launch_bounds__(TILE) k_icp_gn(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, IcpState* st, IcpParams prm,
                                                  const double* __restrict__ res, const int* __restrict__ slot, const float4* __restrict__ plane,
-                                                 double* partial, double* ext_out) {
+                                                 double* partial, double* ext_out) { TL_START();
   __shared__ double red[8][28];
   __shared__ float sR[9], sT[3];
   __shared__ int s_last;
@@ -938,16 +941,18 @@ __global__ void __launch_bounds__(TILE) k_icp_gn(MapDev M, const float4* __restr
   if (threadIdx.x == 0) {
     const long long g1 = clock64();
     st->ticket = 0u;
+    TL_HERE();   // partials summed, finish begins
     gn_finish(st, prm, red[0]);
+    TL_HERE();   // finish done
     st->dbg[16] = g1 - g0; st->dbg[17] = clock64() - g1;
   }
 }
 
-__global__ void k_icp_begin(IcpState* st, const ScanParams* __restrict__ sp) {
+__global__ void k_icp_begin(IcpState* st, const ScanParams* __restrict__ sp) { TL_START();
   if (threadIdx.x == 0 && blockIdx.x == 0) icp_state_begin(st, sp);
 }
 // on failure the reference leaves optimized_transform = initial (ICP.cpp:266,301)
-__global__ void k_icp_end(IcpState* st) {
+__global__ void k_icp_end(IcpState* st) { TL_START();
   if (threadIdx.x == 0 && blockIdx.x == 0 && st->done == 2) {
     for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) st->R[i * 3 + j] = st->T_init[i * 4 + j]; st->t[i] = st->T_init[i * 4 + 3]; }
   }
@@ -955,7 +960,7 @@ __global__ void k_icp_end(IcpState* st) {
 
 // parity tap: per-query correspondence state at a fixed pose
 __global__ void k_icp_taps(MapDev M, const float4* __restrict__ pts, int npts, const float* __restrict__ T16, double max_dist, int* state,
-                           int* key3, unsigned long long* morton, float* nout, float* cout, double* res) {
+                           int* key3, unsigned long long* morton, float* nout, float* cout, double* res) { TL_START();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npts) return;
   float R[9], t[3];
@@ -1134,7 +1139,7 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
 // local statistics of this rank's shard after K2: tile offsets, accepted count, sum r, sum r^2
 __global__ void __launch_bounds__(256) k_shard_stats(const int* __restrict__ d_npts, IcpState* st, IcpParams prm, const double* __restrict__ res,
                                                       const int* __restrict__ slot, const int* __restrict__ tilecnt, int* tileoff, double* stats3,
-                                                      const double* __restrict__ tilesum) {
+                                                      const double* __restrict__ tilesum) { TL_START();
   __shared__ int sm[40];
   __shared__ double smd[40];
   const int tid = threadIdx.x;
@@ -1158,7 +1163,7 @@ __global__ void __launch_bounds__(256) k_shard_stats(const int* __restrict__ d_n
 // the rank owning it ([offset, offset + C_local)) writes the normalised residual, everybody else writes 0
 __global__ void __launch_bounds__(MAXS) k_shard_sample(const int* __restrict__ d_npts, IcpState* st, IcpParams prm, const double* __restrict__ res,
                                                         const int* __restrict__ cidx, const int* __restrict__ tileoff, const PkoTables* __restrict__ T,
-                                                        const int* __restrict__ hits, long long offset, long long c_total, double scale, double* sample) {
+                                                        const int* __restrict__ hits, long long offset, long long c_total, double scale, double* sample) { TL_START();
   __shared__ int s_head[MAXS];
   const int tid = threadIdx.x;
   const int C = (int)c_total;
@@ -1191,7 +1196,7 @@ __global__ void __launch_bounds__(MAXS) k_shard_sample(const int* __restrict__ d
   }
   if (tid < MAXS) sample[tid] = out;
 }
-__global__ void k_shard_finish(IcpState* st, IcpParams prm, const double* __restrict__ acc28) {
+__global__ void k_shard_finish(IcpState* st, IcpParams prm, const double* __restrict__ acc28) { TL_START();
   if (threadIdx.x == 0 && blockIdx.x == 0 && !st->done) {
     double acc[28];
     for (int i = 0; i < 28; ++i) acc[i] = acc28[i];
@@ -1199,7 +1204,7 @@ __global__ void k_shard_finish(IcpState* st, IcpParams prm, const double* __rest
   }
 }
 
-__global__ void k_lookup(MapDev M, float px, float py, float pz, float* out7) {
+__global__ void k_lookup(MapDev M, float px, float py, float pz, float* out7) { TL_START();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float w[3] = {px, py, pz}, n[3] = {0, 0, 0}, c[3] = {0, 0, 0};
   int s = surfel_probe(M, w, n, c, nullptr, nullptr);
@@ -1463,7 +1468,7 @@ extern "C" int b2lo_icp_shard_finish(b2lo_map* map, const b2lo_icp_cfg* cfg, con
 namespace b2 {
 struct LoopPose { float Rm[9], tm[3], Ri[9], ti[3]; };   // matched keyframe pose and its rigid inverse (both f32)
 
-__global__ void k_loop_iota(const int* __restrict__ d_npts, IcpState* st, int* unres, int* n_unres) {
+__global__ void k_loop_iota(const int* __restrict__ d_npts, IcpState* st, int* unres, int* n_unres) { TL_START();
   if (st->done) return;
   const int npts = *d_npts;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += gridDim.x * blockDim.x) unres[i] = i;
@@ -1473,7 +1478,7 @@ __global__ void k_loop_iota(const int* __restrict__ d_npts, IcpState* st, int* u
 // product, :524) and back through the matched pose in f32 (:139-142)
 __global__ void __launch_bounds__(TILE) k_loop_gate(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, IcpState* st, IcpParams prm,
                                                     LoopPose lp, const int* __restrict__ knn_idx, const int* __restrict__ knn_n, double* res,
-                                                    int* slot_out, int* cidx, int* tilecnt, float4* plane, double* tilesum) {
+                                                    int* slot_out, int* cidx, int* tilecnt, float4* plane, double* tilesum) { TL_START();
   if (st->done) return;
   __shared__ int sm[40];
   __shared__ double smd2[16];
@@ -1524,7 +1529,7 @@ __global__ void __launch_bounds__(TILE) k_loop_gate(MapDev M, const float4* __re
 }
 // validation (:214-247): share of the current keyframe's points whose nearest target point is closer than 1 m at the final pose
 __global__ void k_loop_inliers(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, const IcpState* st,
-                               const int* __restrict__ knn_idx, const int* __restrict__ knn_n, int* count) {
+                               const int* __restrict__ knn_idx, const int* __restrict__ knn_n, int* count) { TL_START();
   const int npts = *d_npts;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += gridDim.x * blockDim.x) {
     if (knn_n[i] < 1) continue;
@@ -1536,12 +1541,12 @@ __global__ void k_loop_inliers(MapDev M, const float4* __restrict__ pts, const i
   }
 }
 // forces the brute-force search of every query regardless of the done flag (used for the validation pass)
-__global__ void k_loop_iota_all(const int* __restrict__ d_npts, int* unres, int* n_unres) {
+__global__ void k_loop_iota_all(const int* __restrict__ d_npts, int* unres, int* n_unres) { TL_START();
   const int npts = *d_npts;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += gridDim.x * blockDim.x) unres[i] = i;
   if (blockIdx.x == 0 && threadIdx.x == 0) *n_unres = npts;
 }
-__global__ void k_loop_set_done(IcpState* st, int v) { if (threadIdx.x == 0 && blockIdx.x == 0) st->done = v; }
+__global__ void k_loop_set_done(IcpState* st, int v) { TL_START(); if (threadIdx.x == 0 && blockIdx.x == 0) st->done = v; }
 
 }  // namespace b2
 
@@ -1663,3 +1668,7 @@ extern "C" int b2lo_icp_optimize_loop(b2lo_ctx* ctx, const float* curr_xyz, size
   }
   return success ? B2LO_OK : B2LO_S_INSUFFICIENT;
 }
+
+#ifdef B2LO_TIMELINE
+namespace b2 { int tl_fetch_icp(unsigned long long* out, int cap) { return tl_fetch(out, cap); } }
+#endif

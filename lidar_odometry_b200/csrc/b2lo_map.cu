@@ -20,6 +20,7 @@
 //             arbitrary-order swap-erase on the dense L0 vector; one thread replays it on indices only
 //             (shared memory), then the moves are applied in parallel.
 #include <climits>
+#define B2LO_TL_FILE 4
 #include "b2lo_internal.h"
 
 namespace b2 {
@@ -93,7 +94,7 @@ __device__ void swap_erase_apply(const MapDev& M, int k, int s, const int* seq_p
 // ---- cull ---------------------------------------------------------------------------------------------
 // mark: ||c - sensor||^2 > r^2 (VoxelMap.cpp:146-158), per-tile counts; the last CTA scans the tile counts
 __global__ void __launch_bounds__(1024) k_cull_mark(MapDev M, int n0, float sx, float sy, float sz, float r2, uint8_t* flag, int* blkcnt, int* blkoff,
-                                                    int* us) {
+                                                    int* us) { TL_START();
   // the gate and the first device-side scalars are loaded together: one memory round trip instead of two ahead of the work
   const int gate_v = M.gate ? *M.gate : 1;
   if (M.sensor_dev) { sx = M.sensor_dev[3]; sy = M.sensor_dev[7]; sz = M.sensor_dev[11]; }   // translation of a row-major 4x4 pose
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(1024) k_cull_mark(MapDev M, int n0, float sx, 
   if (threadIdx.x == 0) { us[US_K] = base; us[US_S] = n0 - base; us[US_N0] = n0 - base; us[US_NWORK] = 0; us[US_TICKET] = 0; }
 }
 // removed[] (ascending dense position) and the list of parents that lose children
-__global__ void __launch_bounds__(1024) k_cull_lists(MapDev M, int n0, const uint8_t* flag, const int* blkoff, int* us, int* removed, int* l1work) {
+__global__ void __launch_bounds__(1024) k_cull_lists(MapDev M, int n0, const uint8_t* flag, const int* blkoff, int* us, int* removed, int* l1work) { TL_START();
   const int gate_v = M.gate ? *M.gate : 1;
   __shared__ int sm[40];
   const int k = us[US_K], s_keep = us[US_S];
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(1024) k_cull_lists(MapDev M, int n0, const uin
 }
 // one CTA: (1) per affected parent replay occupied_children.erase() in removal (= L0 dense) order, one warp per parent,
 // one lane per child; (2) replay the k dense-vector erases on indices; (3) apply the moves, drop the hash entries
-__global__ void __launch_bounds__(1024) k_cull_fix(MapDev M, const uint8_t* flag, int* us, const int* l1work, const int* removed, int* aux, int n0) {
+__global__ void __launch_bounds__(1024) k_cull_fix(MapDev M, const uint8_t* flag, int* us, const int* l1work, const int* removed, int* aux, int n0) { TL_START();
   const int gate_v = M.gate ? *M.gate : 1;
   extern __shared__ int smem[];
   const int k = us[US_K];
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(1024) k_cull_fix(MapDev M, const uint8_t* flag
 // local != nullptr: the update's points are the feature cloud `local` moved by the row-major pose T16 (transform_point_cloud,
 // PointCloudUtils.cpp:120-121, the arithmetic of k_transform_dev); they are computed here and left in `pts` for the kernels behind
 __global__ void k_ins_probe(MapDev M, float4* pts, const int* __restrict__ d_m, int* us, int* pslot, int* nxt, FEntry* atab, int alog2,
-                            int* alist, const float4* __restrict__ local, const float* __restrict__ T16) {
+                            int* alist, const float4* __restrict__ local, const float* __restrict__ T16) { TL_START();
   const int gate_v = M.gate ? *M.gate : 1;
   const int m = *d_m;
   float tm[12];
@@ -270,7 +271,7 @@ __global__ void k_ins_probe(MapDev M, float4* pts, const int* __restrict__ d_m, 
 // leader (first point of each touched voxel) replays AddPoint over the voxel's points in input order
 // weighted = 1: the "points" are voxels of a re-hash (w = point_count), merged as in ApplyTransformAndRehash (VoxelMap.cpp:283-297)
 __global__ void k_ins_apply(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_m, const int* pslot, const int* nxt, int* isnew,
-                            float4* newc, int weighted) {
+                            float4* newc, int weighted) { TL_START();
   const int gate_v = M.gate ? *M.gate : 1;
   const int m = *d_m;
   if (!gate_v) return;
@@ -324,7 +325,7 @@ __global__ void k_ins_apply(MapDev M, const float4* __restrict__ pts, const int*
 }
 // one CTA: rank of every new voxel in first-seen order (4 points per thread); the rank is also left in the voxel's
 // hash entry so that siblings can order themselves (k_ins_place)
-__global__ void __launch_bounds__(1024) k_ins_scan(MapDev M, const int* __restrict__ d_m, const int* isnew, const int* pslot, int* newrank, int* us) {
+__global__ void __launch_bounds__(1024) k_ins_scan(MapDev M, const int* __restrict__ d_m, const int* isnew, const int* pslot, int* newrank, int* us) { TL_START();
   const int gate_v = M.gate ? *M.gate : 1;
   __shared__ int sm[40];
   const int m = *d_m;
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(1024) k_ins_scan(MapDev M, const int* __restri
 // over INS_CHUNK-point chunks instead of one CTA walking the whole update.
 constexpr int INS_CHUNK = 4096;
 constexpr size_t BULK_UPD = 1u << 16;
-__global__ void __launch_bounds__(1024) k_ins_scan_part(const int* __restrict__ d_m, const int* __restrict__ isnew, int* part) {
+__global__ void __launch_bounds__(1024) k_ins_scan_part(const int* __restrict__ d_m, const int* __restrict__ isnew, int* part) { TL_START();
   __shared__ int sm[40];
   const int m = *d_m;
   const int nchunks = (m + INS_CHUNK - 1) / INS_CHUNK;
@@ -369,7 +370,7 @@ __global__ void __launch_bounds__(1024) k_ins_scan_part(const int* __restrict__ 
     if (threadIdx.x == 0) part[c] = tot;
   }
 }
-__global__ void __launch_bounds__(1024) k_ins_scan_top(MapDev M, const int* __restrict__ d_m, int* part, int* us) {
+__global__ void __launch_bounds__(1024) k_ins_scan_top(MapDev M, const int* __restrict__ d_m, int* part, int* us) { TL_START();
   __shared__ int sm[40];
   const int m = *d_m;
   const int nchunks = (m + INS_CHUNK - 1) / INS_CHUNK;
@@ -388,7 +389,7 @@ __global__ void __launch_bounds__(1024) k_ins_scan_top(MapDev M, const int* __re
   }
 }
 __global__ void __launch_bounds__(1024) k_ins_scan_apply(MapDev M, const int* __restrict__ d_m, const int* __restrict__ isnew, const int* __restrict__ pslot,
-                                                         int* newrank, const int* __restrict__ part) {
+                                                         int* newrank, const int* __restrict__ part) { TL_START();
   __shared__ int sm[40];
   const int m = *d_m;
   const int nchunks = (m + INS_CHUNK - 1) / INS_CHUNK;
@@ -409,7 +410,7 @@ __global__ void __launch_bounds__(1024) k_ins_scan_apply(MapDev M, const int* __
   }
 }
 // creation ranks back to idle after a bulk insert (k_upd_close does it itself for keyframe-sized updates)
-__global__ void __launch_bounds__(256) k_rank_clear(MapDev M, const int* __restrict__ d_m, const int* __restrict__ pslot, const int* __restrict__ isnew) {
+__global__ void __launch_bounds__(256) k_rank_clear(MapDev M, const int* __restrict__ d_m, const int* __restrict__ pslot, const int* __restrict__ isnew) { TL_START();
   const int m = *d_m;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) if (isnew[i]) M.l0_tab[pslot[i]].rank = -1;
 }
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(256) k_rank_clear(MapDev M, const int* __restr
 // position is (#siblings that already existed) + (#new siblings created earlier), so nobody has to read nchild while
 // it is being updated; the first new sibling writes the new count.
 __global__ void __launch_bounds__(256) k_ins_place(MapDev M, const int* __restrict__ d_m, int* us, const int* pslot, const int* isnew,
-                                                   const int* newrank, const float4* newc) {
+                                                   const int* newrank, const float4* newc) { TL_START();
   const int gate_v = M.gate ? *M.gate : 1;
   const int m = *d_m;
   const int err_v = us[US_ERR];
@@ -471,7 +472,7 @@ __global__ void __launch_bounds__(256) k_ins_place(MapDev M, const int* __restri
 // one warp per affected L1 (VoxelMap.cpp:187-261): lane c fetches child c of the child set; lane 0 sums in child-set
 // order (f32, as the reference), runs the Jacobi SVD and applies the planarity gate.  Non-planar parents are queued
 // for the purge.  The affected-set entry is cleared on the way out (the set is self-cleaning).
-__global__ void __launch_bounds__(256) k_surfel(MapDev M, FEntry* atab, const int* __restrict__ alist, int* us, int* plist, unsigned int* pfirst) {
+__global__ void __launch_bounds__(256) k_surfel(MapDev M, FEntry* atab, const int* __restrict__ alist, int* us, int* plist, unsigned int* pfirst) { TL_START();
   const int gate_v = M.gate ? *M.gate : 1;
   const int naff = us[US_NAFF];
   const bool skip = (us[US_ERR] & ERR_CAP) || !M.compute_surfels;
@@ -525,7 +526,7 @@ __global__ void __launch_bounds__(256) k_surfel(MapDev M, FEntry* atab, const in
 }
 
 // RecomputeAllSurfels (VoxelMap.cpp:304-366): every L1; non-planar parents only lose the surfel (no purge)
-__global__ void k_surfel_all(MapDev M) {
+__global__ void k_surfel_all(MapDev M) { TL_START();
   const int tcap = 1 << M.l1_log2cap;
   for (int s1 = blockIdx.x * blockDim.x + threadIdx.x; s1 < tcap; s1 += gridDim.x * blockDim.x) {
     unsigned long long k1 = M.l1_tab[s1].key;
@@ -555,7 +556,7 @@ __global__ void k_surfel_all(MapDev M) {
 }
 // new_centroid = R * centroid + t (VoxelMap.cpp:273-276), point_count carried in w
 struct Rt12 { float R[9]; float t[3]; };
-__global__ void k_xform_l0(MapDev M, int n0, Rt12 T, float4* out, int* d_n) {
+__global__ void k_xform_l0(MapDev M, int n0, Rt12 T, float4* out, int* d_n) { TL_START();
   for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n0; pos += gridDim.x * blockDim.x) {
     float4 c = M.l0_cent[pos];
     float v[3] = {c.x, c.y, c.z}, r[3];
@@ -570,7 +571,7 @@ __global__ void k_xform_l0(MapDev M, int n0, Rt12 T, float4* out, int* d_n) {
 // indices, apply the moves, publish the counters.
 __global__ void __launch_bounds__(1024) k_upd_close(MapDev M, int* us, const int* plist, const unsigned int* pfirst, int* pord, int* poff, int* seq_pos,
                                                     int* aux, int purge_ran, const int* __restrict__ d_m, const int* __restrict__ pslot,
-                                                    const int* __restrict__ isnew, int ranks_cleared) {
+                                                    const int* __restrict__ isnew, int ranks_cleared) { TL_START();
   if (M.gate && !*M.gate) return;
   extern __shared__ int smem[];
   __shared__ int sm[40];
@@ -640,14 +641,14 @@ __global__ void __launch_bounds__(1024) k_upd_close(MapDev M, int* us, const int
 }
 
 // ---- table maintenance --------------------------------------------------------------------------------------
-__global__ void k_l0_reinsert(MapDev M, int n0) {
+__global__ void k_l0_reinsert(MapDev M, int n0) { TL_START();
   for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n0; pos += gridDim.x * blockDim.x) {
     bool ins;
     int s0 = l0_find_or_insert(M, M.l0_key[pos], &ins);
     if (s0 >= 0) { M.l0_tab[s0].pos = (uint32_t)pos; M.l0_slot[pos] = (uint32_t)s0; }
   }
 }
-__global__ void k_l1_reinsert(MapDev Mnew, const L1Entry* oldtab, const L1Meta* oldmeta, int oldcap) {
+__global__ void k_l1_reinsert(MapDev Mnew, const L1Entry* oldtab, const L1Meta* oldmeta, int oldcap) { TL_START();
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < oldcap; s += gridDim.x * blockDim.x) {
     unsigned long long k = oldtab[s].key;
     if (k == KEY_EMPTY || k == KEY_TOMB) continue;
@@ -661,12 +662,12 @@ __global__ void k_l1_reinsert(MapDev Mnew, const L1Entry* oldtab, const L1Meta* 
     Mnew.l1_tab[ns].key = k;
   }
 }
-__global__ void k_fill_int(int* p, size_t n, int v) {
+__global__ void k_fill_int(int* p, size_t n, int v) { TL_START();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
 // ---- exports ----------------------------------------------------------------------------------------------------
-__global__ void k_export_l0(MapDev M, int n0, float* xyz, int* keys, int* counts) {
+__global__ void k_export_l0(MapDev M, int n0, float* xyz, int* keys, int* counts) { TL_START();
   for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n0; pos += gridDim.x * blockDim.x) {
     float4 c = M.l0_cent[pos];
     xyz[pos * 3] = c.x; xyz[pos * 3 + 1] = c.y; xyz[pos * 3 + 2] = c.z;
@@ -675,7 +676,7 @@ __global__ void k_export_l0(MapDev M, int n0, float* xyz, int* keys, int* counts
   }
 }
 __global__ void k_export_l1(MapDev M, int* counter, int cap, int surfels_only, int* keys, int* nchild, int* children, int* has, float* normal,
-                            float* centroid, float* planarity, int* last) {
+                            float* centroid, float* planarity, int* last) { TL_START();
   const int tcap = 1 << M.l1_log2cap;
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < tcap; s += gridDim.x * blockDim.x) {
     unsigned long long k = M.l1_tab[s].key;
@@ -701,7 +702,7 @@ __global__ void k_export_l1(MapDev M, int* counter, int cap, int surfels_only, i
     if (last) last[o] = mt->last_child_count;
   }
 }
-__global__ void k_count_surfels(MapDev M, int* out) {
+__global__ void k_count_surfels(MapDev M, int* out) { TL_START();
   const int tcap = 1 << M.l1_log2cap;
   int c = 0;
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < tcap; s += gridDim.x * blockDim.x) {
@@ -1144,3 +1145,7 @@ extern "C" int b2lo_map_transform_rehash(b2lo_map* m, const float T16[16]) {
   cudaStreamSynchronize(st);
   return rc;
 }
+
+#ifdef B2LO_TIMELINE
+namespace b2 { int tl_fetch_map(unsigned long long* out, int cap) { return tl_fetch(out, cap); } }
+#endif

@@ -10,6 +10,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#define B2LO_TL_FILE 3
 #include "b2lo_internal.h"
 
 static inline double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -57,7 +58,7 @@ static Pose pose_reproject(const Pose& a) {  // SE3f(R.matrix, t): the SO3(Matri
 // update can be enqueued behind the ICP without a host round trip: one thread turns the ICP state into the scan's pose
 // and decides whether the (already enqueued, gated) map update runs.
 struct OdomDev { float pose[16]; int keyframe; int icp_status; int pad[2]; };
-__global__ void k_odom_decide(const IcpState* st, const ScanParams* __restrict__ sp, const int* __restrict__ d_nfeat, OdomDev* out) {
+__global__ void k_odom_decide(const IcpState* st, const ScanParams* __restrict__ sp, const int* __restrict__ d_nfeat, OdomDev* out) { TL_START();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const DecideArgs a = sp->decide;
   Pose result = pose_from_T16(a.guess);
@@ -93,7 +94,7 @@ __global__ void k_odom_decide(const IcpState* st, const ScanParams* __restrict__
 // straight into the context's page-locked host mirrors (cudaMallocHost memory is device-addressable under UVA), instead of four D2H
 // copy nodes at the end of the replayed graph (a small copy costs more than a small kernel there).  ~0.3 KB over PCIe, posted writes.
 __global__ void k_odom_readback(const IcpState* __restrict__ st, int icp_words, const OdomDev* __restrict__ out, const int* __restrict__ ctr,
-                                const int* __restrict__ d_nfeat, int* h_icp, int* h_out, int* h_counts) {
+                                const int* __restrict__ d_nfeat, int* h_icp, int* h_out, int* h_counts) { TL_START();
   const int t = threadIdx.x;
   const int* a = reinterpret_cast<const int*>(st);
   for (int i = t; i < icp_words; i += blockDim.x) h_icp[i] = a[i];
@@ -625,3 +626,7 @@ extern "C" int b2lo_odom_reset(b2lo_odom* od) {
   od->la_valid = od->pre_valid = false;
   return rc;
 }
+
+#ifdef B2LO_TIMELINE
+namespace b2 { int tl_fetch_odom(unsigned long long* out, int cap) { return tl_fetch(out, cap); } }
+#endif
