@@ -205,6 +205,19 @@ int b2lo_icp_shard_accumulate(b2lo_map* map, const b2lo_icp_cfg* cfg, long long 
 int b2lo_icp_shard_finish(b2lo_map* map, const b2lo_icp_cfg* cfg, const double* acc28_dev, float T_out[16], int* done /*0 go on, 1 finished, 2 failed*/,
                           b2lo_icp_stats* stats /*nullable*/);
 
+/* The same loop in ONE call with device-ordered exchanges: the all-gather of the counts / moments, the all-reduce of the global GMM
+ * sample and the all-reduce of the 28 normal-equation sums are NCCL calls enqueued on the context stream between the kernels (no host
+ * synchronisation inside the Gauss-Newton loop; the counts, the C < min test and the residual scale are evaluated on the device from the
+ * gathered values).  NCCL is the one already loaded in the process (dlopen "libnccl.so.2"); the communicator is created from a unique id
+ * that rank 0 makes with b2lo_shard_unique_id and the host distributes (128 bytes).  world = 1 needs no NCCL (local copies).  Every rank
+ * gets the same pose.  collective_ms (nullable): CUDA-event time of the exchanges of the last iteration issued. */
+typedef struct b2lo_shard_comm b2lo_shard_comm;
+int b2lo_shard_unique_id(void* out, size_t bytes /* >= 128 */);
+int b2lo_shard_comm_create(b2lo_ctx* ctx, int world, int rank, const void* unique_id, size_t bytes, b2lo_shard_comm** out);
+int b2lo_shard_comm_destroy(b2lo_shard_comm* comm);
+int b2lo_icp_shard_optimize(b2lo_map* map, b2lo_shard_comm* comm, const float* local_xyz, size_t m, size_t stride_floats, const float T_init[16],
+                            const b2lo_icp_cfg* cfg, float T_out[16], b2lo_icp_stats* stats /*nullable*/, float* collective_ms /*nullable*/);
+
 /* ---- loop-closure ICP ----------------------------------------------------------------------
  * optimize_loop (IterativeClosestPointOptimizer.cpp:40-251; correspondences :465-585): registers the CURRENT keyframe's local
  * feature cloud (world pose T_curr) against a MATCHED keyframe's local feature cloud (world pose T_matched): exact 5-NN in the
@@ -252,8 +265,10 @@ b2lo_map* b2lo_odom_map(b2lo_odom* od);
 /* process_frame on a host scan (H2D inside) or on a scan already resident in HBM */
 int b2lo_odom_process(b2lo_odom* od, const float* xyz, size_t n, size_t stride_floats, b2lo_odom_result* res);
 int b2lo_odom_process_dev(b2lo_odom* od, const float* xyz_dev, size_t n, size_t stride_floats, b2lo_odom_result* res);
-/* Look-ahead for recorded sequences (the reference's players read scan i+1 from disk while scan i registers, kitti_player.cpp /
- * mid360_player.cpp): announce, BEFORE processing scan i, the buffer that the following b2lo_odom_process{,_dev} call will be given.
+/* Look-ahead for recorded sequences - an EXTENSION of this engine, not a call pattern of the reference: its players load a scan and then
+ * process it, strictly one after the other (app/player/kitti_player.cpp:109-123; there is no prefetch thread).  A player that has the
+ * next scan in memory anyway (a recorded dataset) may announce, BEFORE processing scan i, the buffer that the following
+ * b2lo_odom_process{,_dev} call will be given.
  * Its voxel downsample (K1, preprocess_frame, Estimator.cpp:561-589) then runs on a side stream into a second feature buffer while
  * scan i registers, and the next call finds its features ready.  Results are bit-identical with and without it; K1 does not depend on
  * the pose or the map.  The buffer must stay valid and unchanged until that next call returns.  on_device = 0: host memory, which

@@ -631,17 +631,78 @@ class PointShardedICP:
     Collectives (3 tiny ones per Gauss-Newton iteration) go through torch.distributed on the caller's process group;
     with ``group=None`` and an uninitialised torch.distributed the exchange is the identity (single rank)."""
 
-    def __init__(self, config: ICPConfig | None = None, adaptive_estimator: AdaptiveMEstimator | None = None, group=None):
+    def __init__(self, config: ICPConfig | None = None, adaptive_estimator: AdaptiveMEstimator | None = None, group=None, device_ordered=True):
+        """device_ordered=True: the whole loop is ONE C call (b2lo_icp_shard_optimize) whose three exchanges per iteration are NCCL calls
+        enqueued on the context stream between the kernels - no host round trip inside the loop; torch.distributed only carries the 128-byte
+        NCCL unique id once.  device_ordered=False: the host-driven phase API (b2lo_icp_shard_corr / _sample / _accumulate / _finish with
+        torch.distributed collectives between them), kept as the readable specification of the exchange and for A/B runs."""
         self.m_config = config or ICPConfig()
         self.m_adaptive_estimator = adaptive_estimator
         self.group = group
+        self.device_ordered = device_ordered
         self.m_last_stats = OptimizationStats()
         self.collective_seconds = 0.0
+        self._comm = None
+        self._comm_ctx = None
+
+    def __del__(self):
+        if getattr(self, "_comm", None):
+            try:
+                capi.lib().b2lo_shard_comm_destroy(self._comm)
+            except Exception:
+                pass
+            self._comm = None
+
+    def _communicator(self, ctx):
+        """b2lo_shard_comm of this rank on ``ctx`` (created once): rank 0's NCCL unique id travels through torch.distributed."""
+        if self._comm is not None and self._comm_ctx is ctx:
+            return self._comm
+        import torch
+        import torch.distributed as dist
+        L = capi.lib()
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+        rank = dist.get_rank(self.group) if multi else 0
+        world = dist.get_world_size(self.group) if multi else 1
+        uid = np.zeros(128, np.uint8)
+        if multi:
+            if rank == 0:
+                check(L.b2lo_shard_unique_id(_p(uid), 128))
+            on_gpu = dist.get_backend(self.group) == "nccl"
+            t = torch.from_numpy(uid).cuda(ctx.device) if on_gpu else torch.from_numpy(uid)
+            dist.broadcast(t, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+            uid = t.cpu().numpy().copy()
+        h = C.c_void_p()
+        check(L.b2lo_shard_comm_create(ctx.h, world, rank, _p(uid), 128, C.byref(h)))
+        self._comm, self._comm_ctx = h, ctx
+        return h
+
+    def _optimize_device_ordered(self, voxel_map, cloud_shard, initial_transform):
+        a, n, sf = _cloud(cloud_shard)
+        T0 = _f32(initial_transform).reshape(16)
+        ame = self.m_adaptive_estimator.get_config() if self.m_adaptive_estimator else None
+        cfg = _icp_cfg(self.m_config, ame)
+        comm = self._communicator(voxel_map.ctx)
+        Tout = np.zeros(16, np.float32)
+        st = IcpStats()
+        cms = C.c_float(0.0)
+        rc = check(capi.lib().b2lo_icp_shard_optimize(voxel_map.h, comm, _p(a), n, sf, _p(T0), C.byref(cfg), _p(Tout), C.byref(st), C.byref(cms)))
+        self.collective_ms_last_iteration = float(cms.value)
+        self.device_ms = float(st.device_ms)
+        self.collective_seconds = 0.0
+        if rc != B2LO_OK:
+            self.m_last_stats = OptimizationStats()
+            return False, T0.reshape(4, 4).copy()
+        self.m_last_stats = OptimizationStats(num_iterations=st.num_iterations, num_correspondences=st.num_correspondences,
+                                              initial_cost=st.initial_cost, final_cost=st.final_cost, converged=True,
+                                              optimization_time_ms=st.device_ms, iterations=_trace(st))
+        return True, Tout.reshape(4, 4).copy()
 
     def get_last_stats(self):
         return self.m_last_stats
 
     def optimize(self, voxel_map: VoxelMap, cloud_shard, initial_transform):
+        if self.device_ordered:
+            return self._optimize_device_ordered(voxel_map, cloud_shard, initial_transform)
         import time
         import torch
         import torch.distributed as dist

@@ -137,6 +137,10 @@ SIGNATURES = {
     "b2lo_icp_shard_sample": (_i, [_vp, C.POINTER(IcpCfg), C.c_longlong, C.c_longlong, _d, _vp]),
     "b2lo_icp_shard_accumulate": (_i, [_vp, C.POINTER(IcpCfg), C.c_longlong, _d, _vp, _vp]),
     "b2lo_icp_shard_finish": (_i, [_vp, C.POINTER(IcpCfg), _vp, _vp, C.POINTER(_i), C.POINTER(IcpStats)]),
+    "b2lo_shard_unique_id": (_i, [_vp, _sz]),
+    "b2lo_shard_comm_create": (_i, [_vp, _i, _i, _vp, _sz, C.POINTER(_vp)]),
+    "b2lo_shard_comm_destroy": (_i, [_vp]),
+    "b2lo_icp_shard_optimize": (_i, [_vp, _vp, _vp, _sz, _sz, _vp, C.POINTER(IcpCfg), _vp, C.POINTER(IcpStats), C.POINTER(C.c_float)]),
     "b2lo_se3_mul": (None, [_vp, _vp, _vp]),
     "b2lo_se3_inv": (None, [_vp, _vp]),
     "b2lo_se3_from_rt": (None, [_vp, _vp]),

@@ -125,7 +125,7 @@ struct PkoTables;
 // no-op launch disappears with it).  The body reads what the other CTAs wrote through L2 (__ldcg) behind a fence and a ticket.
 __device__ __noinline__ void pko1_body(const int* d_npts, IcpState* st, IcpParams prm, const double* res, const int* cidx, const int* tilecnt,
                                        int* tileoff, const PkoTables* T, const int* hits, double* gmm_out, const double* ext_sample, int ext_C,
-                                       double ext_scale, const double* tilesum);
+                                       double ext_scale, const double* tilesum, const double* ext_plan = nullptr);
 template <int DEPTH, int MINB, bool FUSE>
 __global__ void __launch_bounds__(TILE, MINB) k_icp_corr(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, IcpState* st,
                                                    IcpParams prm, double* res, int* slot_out, int* cidx, int* tilecnt, double* tilesum,
@@ -485,8 +485,9 @@ template <int V> __device__ __forceinline__ void warp_sum_multi(double (&v)[V]) 
 // the discrete outputs (iteration counts, arg-min alpha) only on near-exact ties - tests/ assert they match the oracle.
 __device__ __noinline__ void pko1_body(const int* d_npts, IcpState* st, IcpParams prm, const double* res, const int* cidx, const int* tilecnt,
                                        int* tileoff, const PkoTables* T, const int* hits, double* gmm_out, const double* ext_sample, int ext_C,
-                                       double ext_scale, const double* tilesum) {
+                                       double ext_scale, const double* tilesum, const double* ext_plan) {
   if (st->done) return;
+  if (ext_plan) { ext_C = (int)ext_plan[1]; ext_scale = ext_plan[2]; }   // device-ordered point-sharded mode: the plan of k_shard_plan
   if (threadIdx.x == 0) TL_HERE();   // fit begins
   __shared__ int sm[40];
   __shared__ double smd[40];
@@ -702,9 +703,9 @@ __global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict_
                                                            const int* __restrict__ slot, const int* __restrict__ cidx, const int* __restrict__ tilecnt,
                                                            int* tileoff, const PkoTables* __restrict__ T, const int* __restrict__ hits, double* gmm_out,
                                                            const double* __restrict__ ext_sample, int ext_C, double ext_scale,
-                                                           const double* __restrict__ tilesum) { TL_START();
+                                                           const double* __restrict__ tilesum, const double* __restrict__ ext_plan) { TL_START();
   (void)slot;
-  pko1_body(d_npts, st, prm, res, cidx, tilecnt, tileoff, T, hits, gmm_out, ext_sample, ext_C, ext_scale, tilesum);
+  pko1_body(d_npts, st, prm, res, cidx, tilecnt, tileoff, T, hits, gmm_out, ext_sample, ext_C, ext_scale, tilesum, ext_plan);
 }
 
 // one CTA per alpha candidate i = 1..S (blockIdx.x + 1); thread k handles r_k = dr * (1 + k); the last CTA takes the arg-min
@@ -1109,7 +1110,7 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
     if (!fuse) {
       prof_begin(ctx, PS_PKO1);
       k_icp_pko1<<<1, PKO_THREADS, 0, s>>>(d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff, ctx->d_pko,
-                                           ctx->d_pko_hits, gmm, nullptr, 0, 0.0, ctx->i_tilesum);
+                                           ctx->d_pko_hits, gmm, nullptr, 0, 0.0, ctx->i_tilesum, nullptr);
       prof_end(ctx);
     }
     if (cfg->use_adaptive_m_estimator) {
@@ -1163,9 +1164,14 @@ __global__ void __launch_bounds__(256) k_shard_stats(const int* __restrict__ d_n
 // the rank owning it ([offset, offset + C_local)) writes the normalised residual, everybody else writes 0
 __global__ void __launch_bounds__(MAXS) k_shard_sample(const int* __restrict__ d_npts, IcpState* st, IcpParams prm, const double* __restrict__ res,
                                                         const int* __restrict__ cidx, const int* __restrict__ tileoff, const PkoTables* __restrict__ T,
-                                                        const int* __restrict__ hits, long long offset, long long c_total, double scale, double* sample) { TL_START();
+                                                        const int* __restrict__ hits, long long offset, long long c_total, double scale, double* sample,
+                                                        const double* __restrict__ plan) { TL_START();
   __shared__ int s_head[MAXS];
   const int tid = threadIdx.x;
+  if (plan) {   // device-ordered mode: offset / total / scale come from k_shard_plan; a finished or failed optimize contributes nothing
+    offset = (long long)plan[0]; c_total = (long long)plan[1]; scale = plan[2];
+    if (st->done || c_total < 1) { if (tid < MAXS) sample[tid] = 0.0; return; }
+  }
   const int C = (int)c_total;
   const int c_local = st->n_blocks;  // accepted count of this shard (k_shard_stats)
   const int npts = *d_npts;
@@ -1202,6 +1208,30 @@ __global__ void k_shard_finish(IcpState* st, IcpParams prm, const double* __rest
     for (int i = 0; i < 28; ++i) acc[i] = acc28[i];
     gn_finish(st, prm, acc);
   }
+}
+
+// device-ordered point-sharded mode: every rank turns the all-gathered (C_r, sum r, sum r^2) triples into the same plan -
+// plan[0] = global offset of this rank's accepted correspondences, plan[1] = global count C, plan[2] = residual scale - and applies
+// the reference's C < min_correspondence_points test (ICP.cpp:298-302) and iteration-0 scale (ICP.cpp:304-316) to the GLOBAL values
+__global__ void k_shard_plan(IcpState* st, IcpParams prm, const double* __restrict__ gathered, int world, int rank, double* plan) { TL_START();
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (st->done) { plan[0] = 0.0; plan[1] = 0.0; plan[2] = st->scale; return; }
+  long long off = 0, total = 0;
+  double a1 = 0.0, a2 = 0.0;
+  for (int r = 0; r < world; ++r) {
+    const long long c = (long long)gathered[3 * r];
+    if (r < rank) off += c;
+    total += c; a1 += gathered[3 * r + 1]; a2 += gathered[3 * r + 2];
+  }
+  double scale = st->scale;
+  st->n_corr = (int)total;
+  if (total < prm.min_corr) { st->done = 2; st->status = B2LO_S_INSUFFICIENT; }
+  else if (st->iter == 0 && !st->scale_forced) {
+    const double mean = a1 / (double)total;
+    scale = sqrt(fmax(a2 / (double)total - mean * mean, 0.0)) / 6.0;
+    st->scale = scale;
+  }
+  plan[0] = (double)off; plan[1] = (double)total; plan[2] = scale;
 }
 
 __global__ void k_lookup(MapDev M, float px, float py, float pz, float* out7) { TL_START();
@@ -1398,7 +1428,7 @@ extern "C" int b2lo_icp_shard_sample(b2lo_map* map, const b2lo_icp_cfg* cfg, lon
   IcpParams prm; int qpt;
   shard_params(cfg, ctx->shard_m ? ctx->shard_m : 1, prm, qpt);
   k_shard_sample<<<1, MAXS, 0, ctx->stream>>>(ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_cidx, ctx->i_blkoff, ctx->d_pko, ctx->d_pko_hits, offset, c_total,
-                                              scale, sample_dev);
+                                              scale, sample_dev, nullptr);
   ctx->launches++;
   B2_CUDA(cudaGetLastError());
   return B2LO_OK;
@@ -1421,7 +1451,7 @@ extern "C" int b2lo_icp_shard_accumulate(b2lo_map* map, const b2lo_icp_cfg* cfg,
   int grid = ntiles < 1 ? 1 : (ntiles > ctx->i_max_blocks ? ctx->i_max_blocks : ntiles);
   prof_begin(ctx, PS_PKO1);
   k_icp_pko1<<<1, PKO_THREADS, 0, s>>>(ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff, ctx->d_pko,
-                                       ctx->d_pko_hits, gmm, sample_dev, (int)c_total, scale, ctx->i_tilesum);
+                                       ctx->d_pko_hits, gmm, sample_dev, (int)c_total, scale, ctx->i_tilesum, nullptr);
   prof_end(ctx);
   if (cfg->use_adaptive_m_estimator) { k_icp_pko2<<<cfg->num_alpha_segments, 128, 0, s>>>(ctx->d_icp, prm, ctx->d_pko, gmm, js, tk); ctx->launches++; }
   prof_begin(ctx, PS_GN);
@@ -1457,6 +1487,173 @@ extern "C" int b2lo_icp_shard_finish(b2lo_map* map, const b2lo_icp_cfg* cfg, con
     std::memcpy(stats->it, h->trace, sizeof(stats->it));
   }
   return B2LO_OK;
+}
+
+// ---- device-ordered point-sharded optimize: the three exchanges of a Gauss-Newton iteration are NCCL calls
+// enqueued on the context stream between the kernels - no host synchronisation inside the loop, one at the end.
+//   K2 -> k_shard_stats -> ncclAllGather(3 doubles / rank) -> k_shard_plan -> k_shard_sample -> ncclAllReduce(128 doubles)
+//      -> PKO fit + arg-min (replicated: every rank fits the identical global sample) -> K5 partial sums -> ncclAllReduce(28 doubles)
+//      -> k_shard_finish (every rank solves the identical 6x6 system and keeps the identical pose)
+// NCCL is taken from the process (torch has it loaded) with dlopen: the library itself carries no link-time dependency on it.
+#include <dlfcn.h>
+#include <nccl.h>
+namespace b2 {
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+static NcclApi& nccl_api() {
+  static NcclApi a;
+  static bool tried = false;
+  if (tried) return a;
+  tried = true;
+  for (const char* name : {"libnccl.so.2", "libnccl.so"}) { a.h = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (a.h) break; }
+  if (!a.h) return a;
+  a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.h, "ncclGetUniqueId");
+  a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.h, "ncclCommInitRank");
+  a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.h, "ncclCommDestroy");
+  a.AllReduce = (decltype(a.AllReduce))dlsym(a.h, "ncclAllReduce");
+  a.AllGather = (decltype(a.AllGather))dlsym(a.h, "ncclAllGather");
+  a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.h, "ncclGetErrorString");
+  a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce && a.AllGather && a.GetErrorString;
+  return a;
+}
+}  // namespace b2
+struct b2lo_shard_comm {
+  b2lo_ctx* ctx = nullptr;
+  ncclComm_t comm = nullptr;
+  int world = 1, rank = 0;
+  double* d_buf = nullptr;   // [0,3) this rank's stats | [8, 8 + 3 world) gathered | plan (3) | sample (128) | acc (28)
+  double *d_stats = nullptr, *d_gathered = nullptr, *d_plan = nullptr, *d_sample = nullptr, *d_acc = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+#define B2_NCCL(expr)                                                                                          \
+  do {                                                                                                         \
+    ncclResult_t _r = (expr);                                                                                  \
+    if (_r != ncclSuccess) { b2::set_error("%s failed: %s", #expr, b2::nccl_api().GetErrorString(_r)); return B2LO_E_CUDA; } \
+  } while (0)
+
+extern "C" int b2lo_shard_unique_id(void* out, size_t bytes) {
+  NcclApi& N = nccl_api();
+  if (!N.ok) { set_error("NCCL is not available in this process (dlopen libnccl.so.2 failed)"); return B2LO_E_CUDA; }
+  if (!out || bytes < sizeof(ncclUniqueId)) return B2LO_E_ARG;
+  ncclUniqueId id;
+  B2_NCCL(N.GetUniqueId(&id));
+  std::memcpy(out, &id, sizeof id);
+  return B2LO_OK;
+}
+extern "C" int b2lo_shard_comm_create(b2lo_ctx* ctx, int world, int rank, const void* unique_id, size_t bytes, b2lo_shard_comm** out) {
+  if (!ctx || !out || world < 1 || rank < 0 || rank >= world) return B2LO_E_ARG;
+  *out = nullptr;
+  cudaSetDevice(ctx->device);
+  b2lo_shard_comm* c = new b2lo_shard_comm();
+  c->ctx = ctx; c->world = world; c->rank = rank;
+  if (world > 1) {
+    NcclApi& N = nccl_api();
+    if (!N.ok) { delete c; set_error("NCCL is not available in this process (dlopen libnccl.so.2 failed)"); return B2LO_E_CUDA; }
+    if (!unique_id || bytes < sizeof(ncclUniqueId)) { delete c; return B2LO_E_ARG; }
+    ncclUniqueId id;
+    std::memcpy(&id, unique_id, sizeof id);
+    ncclResult_t r = N.CommInitRank(&c->comm, world, id, rank);
+    if (r != ncclSuccess) { set_error("ncclCommInitRank failed: %s", N.GetErrorString(r)); delete c; return B2LO_E_CUDA; }
+  }
+  const size_t n = 8 + 3 * (size_t)world + 8 + 128 + 32;
+  if (cudaMalloc(&c->d_buf, n * sizeof(double)) != cudaSuccess) { set_error("cudaMalloc(shard exchange buffer) failed"); delete c; return B2LO_E_NOMEM; }
+  cudaMemset(c->d_buf, 0, n * sizeof(double));
+  c->d_stats = c->d_buf; c->d_gathered = c->d_buf + 8; c->d_plan = c->d_gathered + 3 * world; c->d_sample = c->d_plan + 8; c->d_acc = c->d_sample + 128;
+  for (auto& e : c->ev) cudaEventCreate(&e);
+  *out = c;
+  return B2LO_OK;
+}
+extern "C" int b2lo_shard_comm_destroy(b2lo_shard_comm* c) {
+  if (!c) return B2LO_E_ARG;
+  cudaSetDevice(c->ctx->device);
+  cudaStreamSynchronize(c->ctx->stream);
+  if (c->comm) nccl_api().CommDestroy(c->comm);
+  if (c->d_buf) cudaFree(c->d_buf);
+  for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+  delete c;
+  return B2LO_OK;
+}
+// optimize() on this rank's slice of a dense scan; every rank receives the same pose.  collective_ms (nullable): CUDA-event time of the
+// exchanges of the LAST iteration issued (the three collectives plus the plan / sample kernels between them), for the latency report.
+extern "C" int b2lo_icp_shard_optimize(b2lo_map* map, b2lo_shard_comm* c, const float* local_xyz, size_t m, size_t stride_floats, const float T_init[16],
+                                       const b2lo_icp_cfg* cfg, float T_out[16], b2lo_icp_stats* stats, float* collective_ms) {
+  int rc = shard_check(map, cfg);
+  if (rc) return rc;
+  if (!c || c->ctx != map->ctx || !T_init || !T_out || stride_floats < 3) return B2LO_E_ARG;
+  if ((rc = b2lo_icp_shard_begin(map, local_xyz, m, stride_floats, T_init, cfg))) return rc;
+  std::lock_guard<std::recursive_mutex> lk(map->mu);
+  b2lo_ctx* ctx = map->ctx;
+  std::lock_guard<std::recursive_mutex> lk2(ctx->mu);
+  NcclApi& N = nccl_api();
+  IcpParams prm; int qpt;
+  const size_t mm = m ? m : 1;
+  shard_params(cfg, mm, prm, qpt);
+  const int ctiles = (int)((mm + prm.ctile - 1) / prm.ctile);
+  const CorrLaunch cl = corr_launch(ctx, ctiles);
+  cudaStream_t s = ctx->stream;
+  double* gmm = ctx->i_partial + (size_t)ctx->i_max_blocks * 28;
+  double* js = gmm + 120;
+  unsigned int* tk = reinterpret_cast<unsigned int*>(js + 132);
+  const int ntiles = (int)((mm + TILE - 1) / TILE);
+  const int grid = ntiles < 1 ? 1 : (ntiles > ctx->i_max_blocks ? ctx->i_max_blocks : ntiles);
+  B2_CUDA(cudaEventRecord(ctx->ev0, s));
+  for (int it = 0; it < cfg->max_iterations; ++it) {
+    const bool last = it + 1 == cfg->max_iterations;
+    cl.k<<<cl.grid, TILE, cl.smem, s>>>(map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum,
+                                        nullptr, nullptr, nullptr, nullptr, nullptr);
+    k_shard_stats<<<1, 256, 0, s>>>(ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_blkcnt, ctx->i_blkoff, c->d_stats, ctx->i_tilesum);
+    if (last) cudaEventRecord(c->ev[0], s);
+    if (c->world > 1) B2_NCCL(N.AllGather(c->d_stats, c->d_gathered, 3, ncclDouble, c->comm, s));
+    else B2_CUDA(cudaMemcpyAsync(c->d_gathered, c->d_stats, 3 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    k_shard_plan<<<1, 32, 0, s>>>(ctx->d_icp, prm, c->d_gathered, c->world, c->rank, c->d_plan);
+    k_shard_sample<<<1, MAXS, 0, s>>>(ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_cidx, ctx->i_blkoff, ctx->d_pko, ctx->d_pko_hits, 0, 0, 0.0, c->d_sample,
+                                      c->d_plan);
+    if (c->world > 1) B2_NCCL(N.AllReduce(c->d_sample, c->d_sample, 128, ncclDouble, ncclSum, c->comm, s));
+    if (last) cudaEventRecord(c->ev[1], s);
+    k_icp_pko1<<<1, PKO_THREADS, 0, s>>>(ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff, ctx->d_pko,
+                                         ctx->d_pko_hits, gmm, c->d_sample, 0, 0.0, ctx->i_tilesum, c->d_plan);
+    if (cfg->use_adaptive_m_estimator) { k_icp_pko2<<<cfg->num_alpha_segments, 128, 0, s>>>(ctx->d_icp, prm, ctx->d_pko, gmm, js, tk); ctx->launches++; }
+    k_icp_gn<true><<<grid, TILE, 0, s>>>(map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, nullptr, ctx->i_partial, c->d_acc);
+    if (last) cudaEventRecord(c->ev[2], s);
+    if (c->world > 1) B2_NCCL(N.AllReduce(c->d_acc, c->d_acc, 28, ncclDouble, ncclSum, c->comm, s));
+    if (last) cudaEventRecord(c->ev[3], s);
+    k_shard_finish<<<1, 32, 0, s>>>(ctx->d_icp, prm, c->d_acc);
+    ctx->launches += 7;
+  }
+  k_icp_end<<<1, 32, 0, s>>>(ctx->d_icp);
+  ctx->launches++;
+  B2_CUDA(cudaGetLastError());
+  B2_CUDA(cudaEventRecord(ctx->ev1, s));
+  B2_CUDA(cudaMemcpyAsync(ctx->h_icp, ctx->d_icp, sizeof(IcpState), cudaMemcpyDeviceToHost, s));
+  B2_CUDA(cudaStreamSynchronize(s));
+  ctx->d2h_bytes += sizeof(IcpState);
+  const IcpState* h = ctx->h_icp;
+  Pose p;
+  for (int i = 0; i < 9; ++i) p.R.m[i] = h->R[i];
+  for (int i = 0; i < 3; ++i) p.t[i] = h->t[i];
+  pose_to_T16(p, T_out);
+  float ms = 0.0f;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  if (stats) {
+    stats->status = h->status; stats->num_iterations = h->num_iterations; stats->num_correspondences = h->n_corr; stats->converged = h->converged;
+    stats->initial_cost = h->initial_cost; stats->final_cost = h->final_cost; stats->device_ms = ms;
+    std::memcpy(stats->it, h->trace, sizeof(stats->it));
+  }
+  if (collective_ms) {
+    float a = 0.0f, b = 0.0f;
+    cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&b, c->ev[2], c->ev[3]);
+    *collective_ms = a + b;
+  }
+  return h->status == B2LO_S_INSUFFICIENT ? B2LO_S_INSUFFICIENT : B2LO_OK;
 }
 
 // ---- loop-closure ICP: optimize_loop / find_correspondences_loop, ICP.cpp:40-251, 465-585 -------------------------
@@ -1618,7 +1815,7 @@ extern "C" int b2lo_icp_optimize_loop(b2lo_ctx* ctx, const float* curr_xyz, size
       k_loop_gate<<<grid, TILE, 0, s>>>(Ml, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, lp, ctx->k_idx, ctx->k_n, ctx->i_res, ctx->i_slot, ctx->i_cidx,
                                         ctx->i_blkcnt, ctx->k_plane, ctx->i_tilesum);
       k_icp_pko1<<<1, PKO_THREADS, 0, s>>>(ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff, ctx->d_pko,
-                                           ctx->d_pko_hits, gmm, nullptr, 0, 0.0, ctx->i_tilesum);
+                                           ctx->d_pko_hits, gmm, nullptr, 0, 0.0, ctx->i_tilesum, nullptr);
       if (cfg->use_adaptive_m_estimator) k_icp_pko2<<<cfg->num_alpha_segments, 128, 0, s>>>(ctx->d_icp, prm, ctx->d_pko, gmm, js, tk);
       k_icp_gn<false><<<grid, TILE, 0, s>>>(Ml, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->k_plane, ctx->i_partial, nullptr);
       ctx->launches += cfg->use_adaptive_m_estimator ? 6 : 5;

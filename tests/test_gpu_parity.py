@@ -472,22 +472,24 @@ def test_point_sharded_single_rank_matches_fused(orc, b2, small_kitti):
     omap, gmap, kfs = _built_maps(orc, b2, scans, poses)
     ame = b2.AdaptiveMEstimator()
     fused = b2.IterativeClosestPointOptimizer(b2.ICPConfig(), ame)
-    shard = b2.PointShardedICP(b2.ICPConfig(), ame)
-    for k in (3, 4):
-        feat, init = kfs[k][0], T32(poses[k - 1])
-        ok_f, T_f = fused.optimize(gmap, feat, init)
-        tr_f = fused.get_last_stats().iterations
-        ok_s, T_s = shard.optimize(gmap, feat, init)
-        tr_s = shard.get_last_stats().iterations
-        assert ok_f and ok_s and len(tr_f) == len(tr_s)
-        assert tr_f[0]["n_corr"] == tr_s[0]["n_corr"] and tr_f[0]["delta"] == tr_s[0]["delta"]
-        assert abs(tr_f[0]["scale"] - tr_s[0]["scale"]) <= 1e-9 * tr_f[0]["scale"]
-        assert _rel(tr_s[0]["H"], tr_f[0]["H"]) < 1e-9 and _rel(tr_s[0]["g"], tr_f[0]["g"]) < 1e-9
-        assert np.linalg.norm(T_f[:3, 3].astype(np.float64) - T_s[:3, 3]) < 1e-5
-    # too few correspondences -> false, output = initial
-    far = T32(poses[3]).copy(); far[:3, 3] += np.float32(900.0)
-    ok_s, T_s = shard.optimize(gmap, kfs[3][0], far)
-    assert not ok_s and np.array_equal(bits(T_s), bits(far))
+    for device_ordered in (False, True):     # host-driven phase API / one C call with device-ordered exchanges (local copies at world 1)
+        shard = b2.PointShardedICP(b2.ICPConfig(), ame, device_ordered=device_ordered)
+        for k in (3, 4):
+            feat, init = kfs[k][0], T32(poses[k - 1])
+            ok_f, T_f = fused.optimize(gmap, feat, init)
+            tr_f = fused.get_last_stats().iterations
+            ok_s, T_s = shard.optimize(gmap, feat, init)
+            tr_s = shard.get_last_stats().iterations
+            assert ok_f and ok_s and len(tr_f) == len(tr_s), device_ordered
+            for a, b in zip(tr_f, tr_s):
+                assert a["n_corr"] == b["n_corr"] and a["delta"] == b["delta"]
+                assert abs(a["scale"] - b["scale"]) <= 1e-9 * a["scale"]
+                assert _rel(b["H"], a["H"]) < 1e-9 and _rel(b["g"], a["g"]) < 1e-9
+            assert np.linalg.norm(T_f[:3, 3].astype(np.float64) - T_s[:3, 3]) < 1e-5
+        # too few correspondences -> false, output = initial
+        far = T32(poses[3]).copy(); far[:3, 3] += np.float32(900.0)
+        ok_s, T_s = shard.optimize(gmap, kfs[3][0], far)
+        assert not ok_s and np.array_equal(bits(T_s), bits(far))
 
 
 def _sharded_worker(rank, world, port, out):
@@ -510,12 +512,16 @@ def _sharded_worker(rank, world, port, out):
     init = np.asarray(poses[2], np.float64).astype(np.float32)
     ame = api.AdaptiveMEstimator()
     lo, hi = sharding.shard_bounds(len(feats[3]), world, rank)
-    shard = api.PointShardedICP(api.ICPConfig(), ame)
+    shard = api.PointShardedICP(api.ICPConfig(), ame, device_ordered=False)
     ok_s, T_s = shard.optimize(gmap, feats[3][lo:hi], init)
+    shard_d = api.PointShardedICP(api.ICPConfig(), ame, device_ordered=True)     # NCCL enqueued from C on the context stream
+    ok_d, T_d = shard_d.optimize(gmap, feats[3][lo:hi], init)
     ok_f, T_f = api.IterativeClosestPointOptimizer(api.ICPConfig(), ame).optimize(gmap, feats[3], init)
     if rank == 0:
         np.savez(out, ok_s=ok_s, ok_f=ok_f, T_s=T_s, T_f=T_f, n_s=shard.get_last_stats().iterations[0]["n_corr"],
-                 d_s=shard.get_last_stats().iterations[0]["delta"], coll=shard.collective_seconds)
+                 d_s=shard.get_last_stats().iterations[0]["delta"], coll=shard.collective_seconds, ok_d=ok_d, T_d=T_d,
+                 n_d=shard_d.get_last_stats().iterations[0]["n_corr"], d_d=shard_d.get_last_stats().iterations[0]["delta"],
+                 it_d=shard_d.get_last_stats().num_iterations, it_s=shard.get_last_stats().num_iterations)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -530,8 +536,11 @@ def test_point_sharded_two_gpus(tmp_path):
     out = str(tmp_path / "r0.npz")
     mp.spawn(_sharded_worker, args=(2, port, out), nprocs=2, join=True)
     z = np.load(out)
-    assert bool(z["ok_s"]) and bool(z["ok_f"])
+    assert bool(z["ok_s"]) and bool(z["ok_f"]) and bool(z["ok_d"])
     assert np.linalg.norm(z["T_s"][:3, 3].astype(np.float64) - z["T_f"][:3, 3]) < 1e-5
+    # the device-ordered exchange (NCCL from C, no host round trip in the loop): same global count, same alpha, same iteration count, same pose
+    assert int(z["n_d"]) == int(z["n_s"]) and float(z["d_d"]) == float(z["d_s"]) and int(z["it_d"]) == int(z["it_s"])
+    assert np.linalg.norm(z["T_d"][:3, 3].astype(np.float64) - z["T_f"][:3, 3]) < 1e-5
 
 
 # ---- launch plumbing must not change results -------------------------------------------------------------------------
