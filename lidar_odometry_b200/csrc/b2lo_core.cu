@@ -13,6 +13,7 @@
 #include <cstring>
 #include <cstdlib>
 #include "b2lo_internal.h"
+#include "b2lo_launch.cuh"
 
 namespace b2 {
 
@@ -237,6 +238,8 @@ extern "C" int b2lo_process_env_for_batches(int connections) {
   snprintf(buf, sizeof buf, "%d", connections);
   return setenv("CUDA_DEVICE_MAX_CONNECTIONS", buf, 0) == 0 ? B2LO_OK : B2LO_E_ARG;
 }
+
+namespace b2 { Recorder* ctx_recorder(b2lo_ctx* ctx) { return ctx->rec; } }
 
 extern "C" const char* b2lo_version(void) { return "b2lo 0.1 (sm_100a)"; }
 extern "C" const char* b2lo_last_error(void) { return g_err; }

@@ -19,6 +19,7 @@
 #include <cstdlib>
 #define B2LO_TL_FILE 1
 #include "b2lo_internal.h"
+#include "b2lo_launch.cuh"
 
 namespace b2 {
 
@@ -45,7 +46,7 @@ __device__ __forceinline__ float load_f32_bytes(const unsigned char* p) {
   return __uint_as_float(u);
 }
 
-__global__ void k_flt_insert(const ScanParams* __restrict__ sp, FEntry* tab, int log2cap,
+struct k_flt_insert { static __device__ __forceinline__ void run(const ScanParams* __restrict__ sp, FEntry* tab, int log2cap,
                              float4* samp, int* slot_of) { TL_START();
   const float* __restrict__ src = sp->flt_src;
   const int n_samples = sp->flt_ns;
@@ -94,7 +95,7 @@ __global__ void k_flt_insert(const ScanParams* __restrict__ sp, FEntry* tab, int
     }
     slot_of[j] = s;
   }
-}
+} };
 
 // exclusive scan of one u64 per thread across the block; *total = block sum (smem: >= 33 u64)
 __device__ __forceinline__ unsigned long long block_excl_scan64(unsigned long long v, unsigned long long* total, unsigned long long* smem) {
@@ -119,7 +120,7 @@ __device__ __forceinline__ unsigned long long block_excl_scan64(unsigned long lo
   return res;
 }
 
-__global__ void k_flt_flags(const FEntry* __restrict__ tab, const int* __restrict__ slot_of, const ScanParams* __restrict__ sp,
+struct k_flt_flags { static __device__ __forceinline__ void run(const FEntry* __restrict__ tab, const int* __restrict__ slot_of, const ScanParams* __restrict__ sp,
                             unsigned long long* __restrict__ packed) { TL_START();
   const int n_samples = sp->flt_ns;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_samples; j += gridDim.x * blockDim.x) {
@@ -128,11 +129,11 @@ __global__ void k_flt_flags(const FEntry* __restrict__ tab, const int* __restric
     if (s >= 0) { const FEntry e = tab[s]; if (e.first == (unsigned)j) p = (1ull << 32) | (unsigned long long)(unsigned)(e.cnt + 1); }
     packed[j] = p;
   }
-}
+} };
 // one CTA of 1024 threads walks the packed flags in input order, IPT per thread; the voxel rank (count of earlier leaders) and
 // the segment offset (sum of earlier leaders' point counts) ride one packed 64-bit scan: leaders << 32 | points
 template <int IPT>
-__global__ void __launch_bounds__(1024) k_flt_scan(const unsigned long long* __restrict__ packed, const ScanParams* __restrict__ sp,
+struct k_flt_scan { static __device__ __forceinline__ void run(const unsigned long long* __restrict__ packed, const ScanParams* __restrict__ sp,
                                                     int* vid_of_point, int* seg_start, int* seg_cnt, int* lead_of_vid, int* d_nvox) { TL_START();
   __shared__ unsigned long long sm[40];
   const int n_samples = sp->flt_ns;
@@ -166,10 +167,10 @@ __global__ void __launch_bounds__(1024) k_flt_scan(const unsigned long long* __r
     base += tot;
   }
   if (threadIdx.x == 0) { *d_nvox = (int)(base >> 32); seg_start[(int)(base >> 32)] = (int)(base & 0xffffffffull); }
-}
+} };
 
 // vid_pt[j] = voxel id of sample j (-1: dropped), left for k_flt_rank so that it does not repeat the slot -> leader -> voxel chain
-__global__ void k_flt_fill(FEntry* tab, const int* __restrict__ slot_of, const ScanParams* __restrict__ sp, const int* __restrict__ vid_of_point,
+struct k_flt_fill { static __device__ __forceinline__ void run(FEntry* tab, const int* __restrict__ slot_of, const ScanParams* __restrict__ sp, const int* __restrict__ vid_of_point,
                            const int* __restrict__ seg_start, int* bucket, int* vid_pt) { TL_START();
   const int n_samples = sp->flt_ns;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_samples; j += gridDim.x * blockDim.x) {
@@ -180,12 +181,12 @@ __global__ void k_flt_fill(FEntry* tab, const int* __restrict__ slot_of, const S
     vid_pt[j] = v;
     bucket[seg_start[v] + t] = j;
   }
-}
+} };
 
 // every point counts the smaller indices of its voxel's segment -> its position in input order; it drops its COORDINATES
 // there, so that the reduction below streams contiguous float4s (the O(m^2) ordering work of a crowded voxel is spread
 // over its m points' threads instead of serialising on one)
-__global__ void k_flt_rank(const int* __restrict__ vid_pt, const ScanParams* __restrict__ sp, const int* __restrict__ seg_start,
+struct k_flt_rank { static __device__ __forceinline__ void run(const int* __restrict__ vid_pt, const ScanParams* __restrict__ sp, const int* __restrict__ seg_start,
                            const int* __restrict__ seg_cnt, const int* __restrict__ bucket, const float4* __restrict__ samp,
                            float4* __restrict__ sorted) { TL_START();
   const int n_samples = sp->flt_ns;
@@ -205,7 +206,7 @@ __global__ void k_flt_rank(const int* __restrict__ vid_pt, const ScanParams* __r
     for (; q < m; ++q) r += (bucket[b + q] < j);
     sorted[b + r] = p;
   }
-}
+} };
 
 // one thread per voxel adds its points in input order (sequential f32, VoxelMap.h:88-91) and writes centroid and key.  A crowded voxel
 // (a wall or the ground next to the sensor: 100-350 sampled points) would make its one thread the critical path of the whole kernel
@@ -214,7 +215,7 @@ __global__ void k_flt_rank(const int* __restrict__ vid_pt, const ScanParams* __r
 // same box, 60 KITTI-shaped scans: 19.5 us per scan with a thread per voxel and neighbours in one warp, 13.5 with the spread mapping
 // below, 10.2 with the warp hand-over on top.
 constexpr int FLT_HEAVY = 48;
-__global__ void k_flt_reduce(const int* __restrict__ d_nvox, const int* __restrict__ seg_start, const int* __restrict__ seg_cnt,
+struct k_flt_reduce { static __device__ __forceinline__ void run(const int* __restrict__ d_nvox, const int* __restrict__ seg_start, const int* __restrict__ seg_cnt,
                              const float4* __restrict__ sorted, const int* __restrict__ lead_of_vid, const int* __restrict__ slot_of,
                              FEntry* tab, float4* out, unsigned long long* out_key, const ScanParams* __restrict__ sp, int heavy_min) { TL_START();
   // the scratch hash is self-cleaning: every entry in use belongs to exactly one voxel, whose thread puts it back to idle (all 0xFF)
@@ -284,7 +285,7 @@ __global__ void k_flt_reduce(const int* __restrict__ d_nvox, const int* __restri
       e->key = KEY_EMPTY; e->cnt = -1; e->first = 0xFFFFFFFFu;
     }
   }
-}
+} };
 
 int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sample_stride_floats, float voxel, int set, cudaStream_t on,
                const b2lo_record_fmt* fmt, int mode) {
@@ -316,15 +317,15 @@ int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sam
   const ScanParams* sp = ctx->d_sp;
   const bool prof = st == ctx->stream;   // the per-stage events live on the context stream
   if (prof) prof_begin(ctx, PS_FILTER);
-  k_flt_insert<<<blocks, 256, 0, st>>>(sp, ctx->f_tab, log2cap, ctx->f_samp, ctx->f_slot);
+  launch<k_flt_insert, 256, 1>(ctx, dim3((unsigned)(blocks)), dim3((unsigned)(256)), 0, st, sp, ctx->f_tab, log2cap, ctx->f_samp, ctx->f_slot);
   // the launch geometry follows the capacity, not the count (graph-replayable): scan-sized buffers take the one-trip scan
-  k_flt_flags<<<blocks, 256, 0, st>>>(ctx->f_tab, ctx->f_slot, sp, ctx->f_packed);
+  launch<k_flt_flags, 256, 1>(ctx, dim3((unsigned)(blocks)), dim3((unsigned)(256)), 0, st, ctx->f_tab, ctx->f_slot, sp, ctx->f_packed);
   // 4 flags per thread and trip: a one-trip variant with 16 per thread measured slower (13.3 vs 9.9 us per scan, same box)
-  k_flt_scan<4><<<1, 1024, 0, st>>>(ctx->f_packed, sp, ctx->f_vid, ctx->f_segstart, ctx->f_segcnt, ctx->f_lead, ctx->nfeat(set));
+  launch<k_flt_scan<4>, 1024, 1>(ctx, dim3((unsigned)(1)), dim3((unsigned)(1024)), 0, st, ctx->f_packed, sp, ctx->f_vid, ctx->f_segstart, ctx->f_segcnt, ctx->f_lead, ctx->nfeat(set));
   // (the packed flags are dead after the scan: their buffer carries the per-sample voxel ids from here on)
-  k_flt_fill<<<blocks, 256, 0, st>>>(ctx->f_tab, ctx->f_slot, sp, ctx->f_vid, ctx->f_segstart, ctx->f_bucket, reinterpret_cast<int*>(ctx->f_packed));
-  k_flt_rank<<<blocks, 256, 0, st>>>(reinterpret_cast<const int*>(ctx->f_packed), sp, ctx->f_segstart, ctx->f_segcnt, ctx->f_bucket, ctx->f_samp, ctx->f_sorted);
-  k_flt_reduce<<<blocks, 256, 0, st>>>(ctx->nfeat(set), ctx->f_segstart, ctx->f_segcnt, ctx->f_sorted, ctx->f_lead, ctx->f_slot, ctx->f_tab,
+  launch<k_flt_fill, 256, 1>(ctx, dim3((unsigned)(blocks)), dim3((unsigned)(256)), 0, st, ctx->f_tab, ctx->f_slot, sp, ctx->f_vid, ctx->f_segstart, ctx->f_bucket, reinterpret_cast<int*>(ctx->f_packed));
+  launch<k_flt_rank, 256, 1>(ctx, dim3((unsigned)(blocks)), dim3((unsigned)(256)), 0, st, reinterpret_cast<const int*>(ctx->f_packed), sp, ctx->f_segstart, ctx->f_segcnt, ctx->f_bucket, ctx->f_samp, ctx->f_sorted);
+  launch<k_flt_reduce, 256, 1>(ctx, dim3((unsigned)(blocks)), dim3((unsigned)(256)), 0, st, ctx->nfeat(set), ctx->f_segstart, ctx->f_segcnt, ctx->f_sorted, ctx->f_lead, ctx->f_slot, ctx->f_tab,
                                        ctx->feat(set), ctx->feat_key(set), sp, FLT_HEAVY);
   if (prof) prof_end(ctx);
   ctx->launches += 6;

@@ -21,6 +21,7 @@
 #include <cstring>
 #define B2LO_TL_FILE 2
 #include "b2lo_internal.h"
+#include "b2lo_launch.cuh"
 #include "b2lo_knn.cuh"
 
 namespace b2 {
@@ -127,7 +128,7 @@ __device__ __noinline__ void pko1_body(const int* d_npts, IcpState* st, IcpParam
                                        int* tileoff, const PkoTables* T, const int* hits, double* gmm_out, const double* ext_sample, int ext_C,
                                        double ext_scale, const double* tilesum, const double* ext_plan = nullptr);
 template <int DEPTH, int MINB, bool FUSE>
-__global__ void __launch_bounds__(TILE, MINB) k_icp_corr(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, IcpState* st,
+struct k_icp_corr { static __device__ __forceinline__ void run(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, IcpState* st,
                                                    IcpParams prm, double* res, int* slot_out, int* cidx, int* tilecnt, double* tilesum,
                                                    int* tileoff, const PkoTables* T, const int* hits, double* gmm_out, const ScanParams* sp_first) { TL_START();
   // sp_first != nullptr (FUSE only): this is the first correspondence pass of an optimize and no k_icp_begin ran - the pose comes from the
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(TILE, MINB) k_icp_corr(MapDev M, const float4*
     }
     pko1_body(d_npts, st, prm, res, cidx, tilecnt, tileoff, T, hits, gmm_out, nullptr, 0, 0.0, tilesum);
   }
-}
+} };
 
 // ---- KDTree-mode correspondence (K3) ----------------------------------------------------------------
 // search: one warp per query probes the cell shells of the L0 hash (27, then 98 cells, one lane per cell); unresolved queries are queued
@@ -699,17 +700,17 @@ __device__ __noinline__ void pko1_body(const int* d_npts, IcpState* st, IcpParam
   }
 }
 // the fit as a launch of its own (KDTree mode, loop-closure ICP, point-sharded mode, profiling runs)
-__global__ void __launch_bounds__(PKO_THREADS) k_icp_pko1(const int* __restrict__ d_npts, IcpState* st, IcpParams prm, const double* __restrict__ res,
+struct k_icp_pko1 { static __device__ __forceinline__ void run(const int* __restrict__ d_npts, IcpState* st, IcpParams prm, const double* __restrict__ res,
                                                            const int* __restrict__ slot, const int* __restrict__ cidx, const int* __restrict__ tilecnt,
                                                            int* tileoff, const PkoTables* __restrict__ T, const int* __restrict__ hits, double* gmm_out,
                                                            const double* __restrict__ ext_sample, int ext_C, double ext_scale,
                                                            const double* __restrict__ tilesum, const double* __restrict__ ext_plan) { TL_START();
   (void)slot;
   pko1_body(d_npts, st, prm, res, cidx, tilecnt, tileoff, T, hits, gmm_out, ext_sample, ext_C, ext_scale, tilesum, ext_plan);
-}
+} };
 
 // one CTA per alpha candidate i = 1..S (blockIdx.x + 1); thread k handles r_k = dr * (1 + k); the last CTA takes the arg-min
-__global__ void __launch_bounds__(128) k_icp_pko2(IcpState* st, IcpParams prm, const PkoTables* __restrict__ T, const double* __restrict__ gmm,
+struct k_icp_pko2 { static __device__ __forceinline__ void run(IcpState* st, IcpParams prm, const PkoTables* __restrict__ T, const double* __restrict__ gmm,
                                                    double* js, unsigned int* ticket) { TL_START();
   __shared__ double s_c[4], s_n[4];
   __shared__ int s_i[4];
@@ -763,7 +764,7 @@ __global__ void __launch_bounds__(128) k_icp_pko2(IcpState* st, IcpParams prm, c
     st->delta = (bi != 0x7fffffff && best < 1.7976931348623157e308) ? T->alpha[bi] : T->min_sf;
     *ticket = 0u;
   }
-}
+} };
 
 // ---------------------------------------------------------------------------------------------------
 __device__ void gn_finish(IcpState* st, const IcpParams& prm, const double* acc /*28*/) {
@@ -834,7 +835,7 @@ __device__ void gn_finish(IcpState* st, const IcpParams& prm, const double* acc 
 }
 
 template <bool SURFEL>
-__global__ void __launch_bounds__(TILE) k_icp_gn(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, IcpState* st, IcpParams prm,
+struct k_icp_gn { static __device__ __forceinline__ void run(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_npts, IcpState* st, IcpParams prm,
                                                  const double* __restrict__ res, const int* __restrict__ slot, const float4* __restrict__ plane,
                                                  double* partial, double* ext_out) { TL_START();
   __shared__ double red[8][28];
@@ -947,17 +948,17 @@ __global__ void __launch_bounds__(TILE) k_icp_gn(MapDev M, const float4* __restr
     TL_HERE();   // finish done
     st->dbg[16] = g1 - g0; st->dbg[17] = clock64() - g1;
   }
-}
+} };
 
-__global__ void k_icp_begin(IcpState* st, const ScanParams* __restrict__ sp) { TL_START();
+struct k_icp_begin { static __device__ __forceinline__ void run(IcpState* st, const ScanParams* __restrict__ sp) { TL_START();
   if (threadIdx.x == 0 && blockIdx.x == 0) icp_state_begin(st, sp);
-}
+} };
 // on failure the reference leaves optimized_transform = initial (ICP.cpp:266,301)
-__global__ void k_icp_end(IcpState* st) { TL_START();
+struct k_icp_end { static __device__ __forceinline__ void run(IcpState* st) { TL_START();
   if (threadIdx.x == 0 && blockIdx.x == 0 && st->done == 2) {
     for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) st->R[i * 3 + j] = st->T_init[i * 4 + j]; st->t[i] = st->T_init[i * 4 + 3]; }
   }
-}
+} };
 
 // parity tap: per-query correspondence state at a fixed pose
 __global__ void k_icp_taps(MapDev M, const float4* __restrict__ pts, int npts, const float* __restrict__ T16, double max_dist, int* state,
@@ -977,28 +978,35 @@ __global__ void k_icp_taps(MapDev M, const float4* __restrict__ pts, int npts, c
 }
 
 // ---------------------------------------------------------------------------------------------------
-typedef void (*corr_kernel_t)(MapDev, const float4*, const int*, IcpState*, IcpParams, double*, int*, int*, int*, double*, int*, const PkoTables*, const int*, double*,
-                              const ScanParams*);
 // K2 launch geometry for a sequence built for `ctiles_cap` tiles: the kernel is persistent and software-pipelined, so exactly one
 // resident wave.  (A cp.async-streamed variant with deeper thread-private shared-memory rings was tried for dense clouds and was
 // slower: the 16 B LDGSTS copies saturate the MIO queue - ncu: mio_throttle 9.4 stalls per issue, 44.8 us vs 33.2 us per 2^20 probes.)
-struct CorrLaunch { corr_kernel_t k; int grid; size_t smem; };
+#define B2_CORR_ARGS MapDev, const float4*, const int*, IcpState*, IcpParams, double*, int*, int*, int*, double*, int*, const PkoTables*, const int*, double*, const ScanParams*
+struct CorrLaunch { bool fuse; int grid; size_t smem; };
 static CorrLaunch corr_launch(b2lo_ctx* ctx, int ctiles_cap, bool fuse_pko = false) {
   static int per_sm[2] = {0, 0};   // a property of the compiled kernel, identical on every device of this build
-  static corr_kernel_t kern[2] = {nullptr, nullptr};
   const int f = fuse_pko ? 1 : 0;
   if (per_sm[f] == 0) {
     // 80 registers, 3 CTAs/SM; capping at 64 registers for 4 CTAs/SM measured the same (37.1 vs 37.7 us)
-    kern[f] = fuse_pko ? (corr_kernel_t)k_icp_corr<3, 1, true> : (corr_kernel_t)k_icp_corr<3, 1, false>;
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern[f], TILE, 0) != cudaSuccess || n < 1) { cudaGetLastError(); n = 2; }
+    cudaError_t e = fuse_pko ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_one<k_icp_corr<3, 1, true>, TILE, 1, B2_CORR_ARGS>, TILE, 0)
+                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_one<k_icp_corr<3, 1, false>, TILE, 1, B2_CORR_ARGS>, TILE, 0);
+    if (e != cudaSuccess || n < 1) { cudaGetLastError(); n = 2; }
     per_sm[f] = n;
   }
   if (ctiles_cap < 1) ctiles_cap = 1;
   const int resident = ctx->sm_count * per_sm[f];
   CorrLaunch L;
-  L.k = kern[f]; L.grid = ctiles_cap < resident ? ctiles_cap : resident; L.smem = 0;
+  L.fuse = fuse_pko; L.grid = ctiles_cap < resident ? ctiles_cap : resident; L.smem = 0;
   return L;
+}
+// start K2 (the argument types are spelled out so that the instantiation is the one the occupancy query above looked at)
+static void corr_start(b2lo_ctx* ctx, const CorrLaunch& cl, cudaStream_t s, MapDev M, const float4* pts, const int* d_npts, IcpState* st, IcpParams prm, double* res,
+                       int* slot, int* cidx, int* tilecnt, double* tilesum, int* tileoff, const PkoTables* T, const int* hits, double* gmm, const ScanParams* sp_first) {
+  if (cl.fuse) launch<k_icp_corr<3, 1, true>, TILE, 1, B2_CORR_ARGS>(ctx, dim3((unsigned)cl.grid), dim3(TILE), cl.smem, s, M, pts, d_npts, st, prm, res, slot, cidx, tilecnt, tilesum,
+                                                                     tileoff, T, hits, gmm, sp_first);
+  else launch<k_icp_corr<3, 1, false>, TILE, 1, B2_CORR_ARGS>(ctx, dim3((unsigned)cl.grid), dim3(TILE), cl.smem, s, M, pts, d_npts, st, prm, res, slot, cidx, tilecnt, tilesum,
+                                                              tileoff, T, hits, gmm, sp_first);
 }
 
 static int knn_reserve(b2lo_ctx* ctx) {
@@ -1083,7 +1091,7 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
   // (scan-sized clouds only: the fused kernel needs 88 registers, which would cost a dense cloud one resident CTA per SM)
   const bool fuse = surfel && !(ctx->prof && ctx->prof->on) && npts_cap <= 65536;
   const CorrLaunch cl = corr_launch(ctx, ctiles_cap, fuse);
-  if (!fuse) { k_icp_begin<<<1, 32, 0, s>>>(ctx->d_icp, ctx->d_sp); ctx->launches++; }   // fused: the first correspondence pass initialises the state
+  if (!fuse) { launch<k_icp_begin, 32, 1>(ctx, dim3((unsigned)(1)), dim3((unsigned)(32)), 0, s, ctx->d_icp, ctx->d_sp); ctx->launches++; }   // fused: the first correspondence pass initialises the state
   cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(s, &cap_status);
   const bool capturing = cap_status != cudaStreamCaptureStatusNone;
@@ -1095,7 +1103,7 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
   for (int it = 0; it < cfg->max_iterations; ++it) {
     if (surfel) {
       prof_begin(ctx, PS_CORR);
-      cl.k<<<cl.grid, TILE, cl.smem, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum,
+      corr_start(ctx, cl, s, map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum,
                                           ctx->i_blkoff, ctx->d_pko, ctx->d_pko_hits, gmm, (fuse && it == 0) ? ctx->d_sp : nullptr);
       prof_end(ctx);
     } else {
@@ -1109,18 +1117,18 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
     }
     if (!fuse) {
       prof_begin(ctx, PS_PKO1);
-      k_icp_pko1<<<1, PKO_THREADS, 0, s>>>(d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff, ctx->d_pko,
+      launch<k_icp_pko1, PKO_THREADS, 1>(ctx, dim3((unsigned)(1)), dim3((unsigned)(PKO_THREADS)), 0, s, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff, ctx->d_pko,
                                            ctx->d_pko_hits, gmm, nullptr, 0, 0.0, ctx->i_tilesum, nullptr);
       prof_end(ctx);
     }
     if (cfg->use_adaptive_m_estimator) {
       prof_begin(ctx, PS_PKO2);
-      k_icp_pko2<<<cfg->num_alpha_segments, 128, 0, s>>>(ctx->d_icp, prm, ctx->d_pko, gmm, js, tk);
+      launch<k_icp_pko2, 128, 1>(ctx, dim3((unsigned)(cfg->num_alpha_segments)), dim3((unsigned)(128)), 0, s, ctx->d_icp, prm, ctx->d_pko, gmm, js, tk);
       prof_end(ctx);
     }
     prof_begin(ctx, PS_GN);
-    if (surfel) k_icp_gn<true><<<grid, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, nullptr, ctx->i_partial, nullptr);
-    else k_icp_gn<false><<<grid, TILE, 0, s>>>(map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->k_plane, ctx->i_partial, nullptr);
+    if (surfel) launch<k_icp_gn<true>, TILE, 1>(ctx, dim3((unsigned)(grid)), dim3((unsigned)(TILE)), 0, s, map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, nullptr, ctx->i_partial, nullptr);
+    else launch<k_icp_gn<false>, TILE, 1>(ctx, dim3((unsigned)(grid)), dim3((unsigned)(TILE)), 0, s, map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->k_plane, ctx->i_partial, nullptr);
     prof_end(ctx);
     ctx->launches += (cfg->use_adaptive_m_estimator ? 4 : 3) - (fuse ? 1 : 0);
     // long runs (max_iterations beyond the usual 4): look at the done flag every 8 iterations instead of enqueueing dozens of no-op launches
@@ -1131,7 +1139,7 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
     }
   }
   // the per-scan driver's decision kernel never reads the pose of a failed optimize (it falls back to the motion-model guess itself)
-  if (restore_on_failure) { k_icp_end<<<1, 32, 0, s>>>(ctx->d_icp); ctx->launches++; }
+  if (restore_on_failure) { launch<k_icp_end, 32, 1>(ctx, dim3((unsigned)(1)), dim3((unsigned)(32)), 0, s, ctx->d_icp); ctx->launches++; }
   B2_CUDA(cudaGetLastError());
   return B2LO_OK;
 }
@@ -1325,7 +1333,7 @@ extern "C" int b2lo_icp_correspondences_knn(b2lo_map* map, const float* local_xy
   for (int i = 0; i < 16; ++i) ctx->h_sp->T_init[i] = T16[i];
   ctx->h_sp->force_scale = 0.0;
   if ((rc = sp_upload(ctx, offsetof(ScanParams, T_init), SP_POSE_BYTES))) return rc;
-  k_icp_begin<<<1, 32, 0, s>>>(ctx->d_icp, ctx->d_sp);
+  launch<k_icp_begin, 32, 1>(ctx, dim3((unsigned)(1)), dim3((unsigned)(32)), 0, s, ctx->d_icp, ctx->d_sp);
   int grid = (int)((m + 7) / 8);
   if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
   k_knn_search<<<grid, TILE, 0, s>>>(map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, ctx->k_idx, ctx->k_n, ctx->k_unres, ctx->k_nunres);
@@ -1391,7 +1399,7 @@ extern "C" int b2lo_icp_shard_begin(b2lo_map* map, const float* local_xyz, size_
   for (int i = 0; i < 16; ++i) ctx->h_sp->T_init[i] = T_init[i];
   ctx->h_sp->force_scale = 0.0;
   if ((rc = sp_upload(ctx, offsetof(ScanParams, T_init), SP_POSE_BYTES))) return rc;
-  k_icp_begin<<<1, 32, 0, ctx->stream>>>(ctx->d_icp, ctx->d_sp);
+  launch<k_icp_begin, 32, 1>(ctx, dim3((unsigned)(1)), dim3((unsigned)(32)), 0, ctx->stream, ctx->d_icp, ctx->d_sp);
   ctx->launches++;
   B2_CUDA(cudaGetLastError());
   return B2LO_OK;
@@ -1410,7 +1418,7 @@ extern "C" int b2lo_icp_shard_corr(b2lo_map* map, const b2lo_icp_cfg* cfg, doubl
   const CorrLaunch cl = corr_launch(ctx, ctiles);
   cudaStream_t s = ctx->stream;
   prof_begin(ctx, PS_CORR);
-  cl.k<<<cl.grid, TILE, cl.smem, s>>>(map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum,
+  corr_start(ctx, cl, s, map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum,
                                       nullptr, nullptr, nullptr, nullptr, nullptr);
   prof_end(ctx);
   k_shard_stats<<<1, 256, 0, s>>>(ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_blkcnt, ctx->i_blkoff, stats3_dev, ctx->i_tilesum);
@@ -1450,12 +1458,12 @@ extern "C" int b2lo_icp_shard_accumulate(b2lo_map* map, const b2lo_icp_cfg* cfg,
   int ntiles = (int)((m + TILE - 1) / TILE);
   int grid = ntiles < 1 ? 1 : (ntiles > ctx->i_max_blocks ? ctx->i_max_blocks : ntiles);
   prof_begin(ctx, PS_PKO1);
-  k_icp_pko1<<<1, PKO_THREADS, 0, s>>>(ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff, ctx->d_pko,
+  launch<k_icp_pko1, PKO_THREADS, 1>(ctx, dim3((unsigned)(1)), dim3((unsigned)(PKO_THREADS)), 0, s, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff, ctx->d_pko,
                                        ctx->d_pko_hits, gmm, sample_dev, (int)c_total, scale, ctx->i_tilesum, nullptr);
   prof_end(ctx);
-  if (cfg->use_adaptive_m_estimator) { k_icp_pko2<<<cfg->num_alpha_segments, 128, 0, s>>>(ctx->d_icp, prm, ctx->d_pko, gmm, js, tk); ctx->launches++; }
+  if (cfg->use_adaptive_m_estimator) { launch<k_icp_pko2, 128, 1>(ctx, dim3((unsigned)(cfg->num_alpha_segments)), dim3((unsigned)(128)), 0, s, ctx->d_icp, prm, ctx->d_pko, gmm, js, tk); ctx->launches++; }
   prof_begin(ctx, PS_GN);
-  k_icp_gn<true><<<grid, TILE, 0, s>>>(map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, nullptr, ctx->i_partial, acc28_dev);
+  launch<k_icp_gn<true>, TILE, 1>(ctx, dim3((unsigned)(grid)), dim3((unsigned)(TILE)), 0, s, map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, nullptr, ctx->i_partial, acc28_dev);
   prof_end(ctx);
   ctx->launches += 2;
   B2_CUDA(cudaGetLastError());
@@ -1607,7 +1615,7 @@ extern "C" int b2lo_icp_shard_optimize(b2lo_map* map, b2lo_shard_comm* c, const 
   B2_CUDA(cudaEventRecord(ctx->ev0, s));
   for (int it = 0; it < cfg->max_iterations; ++it) {
     const bool last = it + 1 == cfg->max_iterations;
-    cl.k<<<cl.grid, TILE, cl.smem, s>>>(map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum,
+    corr_start(ctx, cl, s, map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum,
                                         nullptr, nullptr, nullptr, nullptr, nullptr);
     k_shard_stats<<<1, 256, 0, s>>>(ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_blkcnt, ctx->i_blkoff, c->d_stats, ctx->i_tilesum);
     if (last) cudaEventRecord(c->ev[0], s);
@@ -1618,17 +1626,17 @@ extern "C" int b2lo_icp_shard_optimize(b2lo_map* map, b2lo_shard_comm* c, const 
                                       c->d_plan);
     if (c->world > 1) B2_NCCL(N.AllReduce(c->d_sample, c->d_sample, 128, ncclDouble, ncclSum, c->comm, s));
     if (last) cudaEventRecord(c->ev[1], s);
-    k_icp_pko1<<<1, PKO_THREADS, 0, s>>>(ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff, ctx->d_pko,
+    launch<k_icp_pko1, PKO_THREADS, 1>(ctx, dim3((unsigned)(1)), dim3((unsigned)(PKO_THREADS)), 0, s, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff, ctx->d_pko,
                                          ctx->d_pko_hits, gmm, c->d_sample, 0, 0.0, ctx->i_tilesum, c->d_plan);
-    if (cfg->use_adaptive_m_estimator) { k_icp_pko2<<<cfg->num_alpha_segments, 128, 0, s>>>(ctx->d_icp, prm, ctx->d_pko, gmm, js, tk); ctx->launches++; }
-    k_icp_gn<true><<<grid, TILE, 0, s>>>(map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, nullptr, ctx->i_partial, c->d_acc);
+    if (cfg->use_adaptive_m_estimator) { launch<k_icp_pko2, 128, 1>(ctx, dim3((unsigned)(cfg->num_alpha_segments)), dim3((unsigned)(128)), 0, s, ctx->d_icp, prm, ctx->d_pko, gmm, js, tk); ctx->launches++; }
+    launch<k_icp_gn<true>, TILE, 1>(ctx, dim3((unsigned)(grid)), dim3((unsigned)(TILE)), 0, s, map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, nullptr, ctx->i_partial, c->d_acc);
     if (last) cudaEventRecord(c->ev[2], s);
     if (c->world > 1) B2_NCCL(N.AllReduce(c->d_acc, c->d_acc, 28, ncclDouble, ncclSum, c->comm, s));
     if (last) cudaEventRecord(c->ev[3], s);
     k_shard_finish<<<1, 32, 0, s>>>(ctx->d_icp, prm, c->d_acc);
     ctx->launches += 7;
   }
-  k_icp_end<<<1, 32, 0, s>>>(ctx->d_icp);
+  launch<k_icp_end, 32, 1>(ctx, dim3((unsigned)(1)), dim3((unsigned)(32)), 0, s, ctx->d_icp);
   ctx->launches++;
   B2_CUDA(cudaGetLastError());
   B2_CUDA(cudaEventRecord(ctx->ev1, s));
@@ -1799,7 +1807,7 @@ extern "C" int b2lo_icp_optimize_loop(b2lo_ctx* ctx, const float* curr_xyz, size
   for (int i = 0; i < 16; ++i) ctx->h_sp->T_init[i] = T_curr[i];
   ctx->h_sp->force_scale = 0.0;
   if ((rc = sp_upload(ctx, offsetof(ScanParams, T_init), SP_POSE_BYTES))) return rc;
-  k_icp_begin<<<1, 32, 0, s>>>(ctx->d_icp, ctx->d_sp);
+  launch<k_icp_begin, 32, 1>(ctx, dim3((unsigned)(1)), dim3((unsigned)(32)), 0, s, ctx->d_icp, ctx->d_sp);
   ctx->launches++;
   const int ntiles = (int)((m_curr + TILE - 1) / TILE);
   const int grid = ntiles > ctx->i_max_blocks ? ctx->i_max_blocks : ntiles;
@@ -1814,10 +1822,10 @@ extern "C" int b2lo_icp_optimize_loop(b2lo_ctx* ctx, const float* curr_xyz, size
       k_knn_brute<<<gb, 256, 0, s>>>(Ml, ctx->d_query, ctx->d_icp, ctx->k_idx, ctx->k_n, ctx->k_unres, ctx->k_nunres);
       k_loop_gate<<<grid, TILE, 0, s>>>(Ml, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, lp, ctx->k_idx, ctx->k_n, ctx->i_res, ctx->i_slot, ctx->i_cidx,
                                         ctx->i_blkcnt, ctx->k_plane, ctx->i_tilesum);
-      k_icp_pko1<<<1, PKO_THREADS, 0, s>>>(ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff, ctx->d_pko,
+      launch<k_icp_pko1, PKO_THREADS, 1>(ctx, dim3((unsigned)(1)), dim3((unsigned)(PKO_THREADS)), 0, s, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff, ctx->d_pko,
                                            ctx->d_pko_hits, gmm, nullptr, 0, 0.0, ctx->i_tilesum, nullptr);
-      if (cfg->use_adaptive_m_estimator) k_icp_pko2<<<cfg->num_alpha_segments, 128, 0, s>>>(ctx->d_icp, prm, ctx->d_pko, gmm, js, tk);
-      k_icp_gn<false><<<grid, TILE, 0, s>>>(Ml, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->k_plane, ctx->i_partial, nullptr);
+      if (cfg->use_adaptive_m_estimator) launch<k_icp_pko2, 128, 1>(ctx, dim3((unsigned)(cfg->num_alpha_segments)), dim3((unsigned)(128)), 0, s, ctx->d_icp, prm, ctx->d_pko, gmm, js, tk);
+      launch<k_icp_gn<false>, TILE, 1>(ctx, dim3((unsigned)(grid)), dim3((unsigned)(TILE)), 0, s, Ml, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->k_plane, ctx->i_partial, nullptr);
       ctx->launches += cfg->use_adaptive_m_estimator ? 6 : 5;
     }
     B2_CUDA(cudaMemcpyAsync(ctx->h_icp, ctx->d_icp, offsetof(IcpState, trace), cudaMemcpyDeviceToHost, s));

@@ -9,6 +9,7 @@
 #include "../../include/b2lo.h"
 #include "b2lo_dev.cuh"
 
+namespace b2 { struct Recorder; }
 namespace b2 {
 
 void set_error(const char* fmt, ...);
@@ -140,6 +141,7 @@ struct b2lo_ctx {
   b2::ScanParams* d_sp = nullptr; b2::ScanParams* h_sp = nullptr /*pinned*/; cudaEvent_t ev_sp = nullptr; bool sp_busy = false;
   bool sp_preloaded = false;       // the caller has already uploaded the whole parameter block for this launch sequence
   b2::Prof* prof = nullptr;
+  b2::Recorder* rec = nullptr;     // non-null while a lock-step batch records this context's launch sequence (b2lo_launch.cuh)
   double force_scale = 0.0;        // next icp_run: ScanParams::force_scale (b2lo_icp_iterate), reset by icp_run
   double host_us[8] = {0};         // wall-clock split of the host side of b2lo_odom_process (debug aid): gather, enqueue, wait, ...
   std::recursive_mutex mu;   // taken AFTER a map's mutex by every entry point that touches the context's staging buffers, counters or stream

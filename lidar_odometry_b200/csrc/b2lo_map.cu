@@ -22,6 +22,7 @@
 #include <climits>
 #define B2LO_TL_FILE 4
 #include "b2lo_internal.h"
+#include "b2lo_launch.cuh"
 
 namespace b2 {
 
@@ -93,7 +94,7 @@ __device__ void swap_erase_apply(const MapDev& M, int k, int s, const int* seq_p
 
 // ---- cull ---------------------------------------------------------------------------------------------
 // mark: ||c - sensor||^2 > r^2 (VoxelMap.cpp:146-158), per-tile counts; the last CTA scans the tile counts
-__global__ void __launch_bounds__(1024) k_cull_mark(MapDev M, int n0, float sx, float sy, float sz, float r2, uint8_t* flag, int* blkcnt, int* blkoff,
+struct k_cull_mark { static __device__ __forceinline__ void run(MapDev M, int n0, float sx, float sy, float sz, float r2, uint8_t* flag, int* blkcnt, int* blkoff,
                                                     int* us) { TL_START();
   // the gate and the first device-side scalars are loaded together: one memory round trip instead of two ahead of the work
   const int gate_v = M.gate ? *M.gate : 1;
@@ -136,9 +137,9 @@ __global__ void __launch_bounds__(1024) k_cull_mark(MapDev M, int n0, float sx, 
     base += tot;
   }
   if (threadIdx.x == 0) { us[US_K] = base; us[US_S] = n0 - base; us[US_N0] = n0 - base; us[US_NWORK] = 0; us[US_TICKET] = 0; }
-}
+} };
 // removed[] (ascending dense position) and the list of parents that lose children
-__global__ void __launch_bounds__(1024) k_cull_lists(MapDev M, int n0, const uint8_t* flag, const int* blkoff, int* us, int* removed, int* l1work) { TL_START();
+struct k_cull_lists { static __device__ __forceinline__ void run(MapDev M, int n0, const uint8_t* flag, const int* blkoff, int* us, int* removed, int* l1work) { TL_START();
   const int gate_v = M.gate ? *M.gate : 1;
   __shared__ int sm[40];
   const int k = us[US_K], s_keep = us[US_S];
@@ -157,10 +158,10 @@ __global__ void __launch_bounds__(1024) k_cull_lists(MapDev M, int n0, const uin
     int s1 = l1_find(M, pk);
     if (s1 >= 0 && atomicCAS(&M.l1_meta[s1].mark, 0, 1) == 0) l1work[atomicAdd(&us[US_NWORK], 1)] = s1;
   }
-}
+} };
 // one CTA: (1) per affected parent replay occupied_children.erase() in removal (= L0 dense) order, one warp per parent,
 // one lane per child; (2) replay the k dense-vector erases on indices; (3) apply the moves, drop the hash entries
-__global__ void __launch_bounds__(1024) k_cull_fix(MapDev M, const uint8_t* flag, int* us, const int* l1work, const int* removed, int* aux, int n0) { TL_START();
+struct k_cull_fix { static __device__ __forceinline__ void run(MapDev M, const uint8_t* flag, int* us, const int* l1work, const int* removed, int* aux, int n0) { TL_START();
   const int gate_v = M.gate ? *M.gate : 1;
   extern __shared__ int smem[];
   const int k = us[US_K];
@@ -216,12 +217,12 @@ __global__ void __launch_bounds__(1024) k_cull_fix(MapDev M, const uint8_t* flag
   __syncthreads();
   swap_erase_apply(M, k, s, removed, aux);
   if (threadIdx.x == 0) atomicAdd(&M.ctr[CT_TOMB0], k);
-}
+} };
 
 // ---- insert ---------------------------------------------------------------------------------------------
 // local != nullptr: the update's points are the feature cloud `local` moved by the row-major pose T16 (transform_point_cloud,
 // PointCloudUtils.cpp:120-121, the arithmetic of k_transform_dev); they are computed here and left in `pts` for the kernels behind
-__global__ void k_ins_probe(MapDev M, float4* pts, const int* __restrict__ d_m, int* us, int* pslot, int* nxt, FEntry* atab, int alog2,
+struct k_ins_probe { static __device__ __forceinline__ void run(MapDev M, float4* pts, const int* __restrict__ d_m, int* us, int* pslot, int* nxt, FEntry* atab, int alog2,
                             int* alist, const float4* __restrict__ local, const float* __restrict__ T16) { TL_START();
   const int gate_v = M.gate ? *M.gate : 1;
   const int m = *d_m;
@@ -267,10 +268,10 @@ __global__ void k_ins_probe(MapDev M, float4* pts, const int* __restrict__ d_m, 
     atomicMin(&atab[h].first, (unsigned)i);
     nxt[i] = prev;
   }
-}
+} };
 // leader (first point of each touched voxel) replays AddPoint over the voxel's points in input order
 // weighted = 1: the "points" are voxels of a re-hash (w = point_count), merged as in ApplyTransformAndRehash (VoxelMap.cpp:283-297)
-__global__ void k_ins_apply(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_m, const int* pslot, const int* nxt, int* isnew,
+struct k_ins_apply { static __device__ __forceinline__ void run(MapDev M, const float4* __restrict__ pts, const int* __restrict__ d_m, const int* pslot, const int* nxt, int* isnew,
                             float4* newc, int weighted) { TL_START();
   const int gate_v = M.gate ? *M.gate : 1;
   const int m = *d_m;
@@ -322,10 +323,10 @@ __global__ void k_ins_apply(MapDev M, const float4* __restrict__ pts, const int*
     else { M.l0_cent[pos] = out; isnew[i] = 0; }
     e->first = 0xFFFFFFFFu; e->cnt = -1; e->head = -1;  // scratch back to idle
   }
-}
+} };
 // one CTA: rank of every new voxel in first-seen order (4 points per thread); the rank is also left in the voxel's
 // hash entry so that siblings can order themselves (k_ins_place)
-__global__ void __launch_bounds__(1024) k_ins_scan(MapDev M, const int* __restrict__ d_m, const int* isnew, const int* pslot, int* newrank, int* us) { TL_START();
+struct k_ins_scan { static __device__ __forceinline__ void run(MapDev M, const int* __restrict__ d_m, const int* isnew, const int* pslot, int* newrank, int* us) { TL_START();
   const int gate_v = M.gate ? *M.gate : 1;
   __shared__ int sm[40];
   const int m = *d_m;
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(1024) k_ins_scan(MapDev M, const int* __restri
     us[US_NNEW] = base;
     if ((long long)us[US_N0] + base > (long long)M.l0_cap) atomicOr(&us[US_ERR], ERR_CAP);
   }
-}
+} };
 // Bulk inserts (more than BULK_UPD points, e.g. ApplyTransformAndRehash of a 10^7-voxel map): the same ranks from a three-step scan
 // over INS_CHUNK-point chunks instead of one CTA walking the whole update.
 constexpr int INS_CHUNK = 4096;
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(256) k_rank_clear(MapDev M, const int* __restr
 // list in creation order (RegisterToParent, VoxelMap.cpp:77-80).  Lane c probes sibling cell c of the parent: the
 // position is (#siblings that already existed) + (#new siblings created earlier), so nobody has to read nchild while
 // it is being updated; the first new sibling writes the new count.
-__global__ void __launch_bounds__(256) k_ins_place(MapDev M, const int* __restrict__ d_m, int* us, const int* pslot, const int* isnew,
+struct k_ins_place { static __device__ __forceinline__ void run(MapDev M, const int* __restrict__ d_m, int* us, const int* pslot, const int* isnew,
                                                    const int* newrank, const float4* newc) { TL_START();
   const int gate_v = M.gate ? *M.gate : 1;
   const int m = *d_m;
@@ -467,12 +468,12 @@ __global__ void __launch_bounds__(256) k_ins_place(MapDev M, const int* __restri
       if (n_before == 0) mt->nchild = (uint8_t)(n_old + n_new);
     }
   }
-}
+} };
 // ---- surfels ----------------------------------------------------------------------------------------------
 // one warp per affected L1 (VoxelMap.cpp:187-261): lane c fetches child c of the child set; lane 0 sums in child-set
 // order (f32, as the reference), runs the Jacobi SVD and applies the planarity gate.  Non-planar parents are queued
 // for the purge.  The affected-set entry is cleared on the way out (the set is self-cleaning).
-__global__ void __launch_bounds__(256) k_surfel(MapDev M, FEntry* atab, const int* __restrict__ alist, int* us, int* plist, unsigned int* pfirst) { TL_START();
+struct k_surfel { static __device__ __forceinline__ void run(MapDev M, FEntry* atab, const int* __restrict__ alist, int* us, int* plist, unsigned int* pfirst) { TL_START();
   const int gate_v = M.gate ? *M.gate : 1;
   const int naff = us[US_NAFF];
   const bool skip = (us[US_ERR] & ERR_CAP) || !M.compute_surfels;
@@ -523,7 +524,7 @@ __global__ void __launch_bounds__(256) k_surfel(MapDev M, FEntry* atab, const in
     __threadfence();
     e->key = k1 | SURFEL_BIT;
   }
-}
+} };
 
 // RecomputeAllSurfels (VoxelMap.cpp:304-366): every L1; non-planar parents only lose the surfel (no purge)
 __global__ void k_surfel_all(MapDev M) { TL_START();
@@ -569,7 +570,7 @@ __global__ void k_xform_l0(MapDev M, int n0, Rt12 T, float4* out, int* d_n) { TL
 // one CTA closes the update: order the purged parents by the position of their key in affected_L1 (= first touching
 // point), lay out the erase sequence (children in child-set order, one warp per parent), replay the swap-erases on
 // indices, apply the moves, publish the counters.
-__global__ void __launch_bounds__(1024) k_upd_close(MapDev M, int* us, const int* plist, const unsigned int* pfirst, int* pord, int* poff, int* seq_pos,
+struct k_upd_close { static __device__ __forceinline__ void run(MapDev M, int* us, const int* plist, const unsigned int* pfirst, int* pord, int* poff, int* seq_pos,
                                                     int* aux, int purge_ran, const int* __restrict__ d_m, const int* __restrict__ pslot,
                                                     const int* __restrict__ isnew, int ranks_cleared) { TL_START();
   if (M.gate && !*M.gate) return;
@@ -638,7 +639,7 @@ __global__ void __launch_bounds__(1024) k_upd_close(MapDev M, int* us, const int
   }
   __syncthreads();
   if (threadIdx.x < US_COUNT) us[threadIdx.x] = 0;   // self-cleaning state block (see the P == 0 exit)
-}
+} };
 
 // ---- table maintenance --------------------------------------------------------------------------------------
 __global__ void k_l0_reinsert(MapDev M, int n0) { TL_START();
@@ -857,11 +858,7 @@ int map_update_dev(b2lo_map* m, float4* d_world, const int* d_n, size_t n_cap, c
   m->d.gate = nullptr; m->d.sensor_dev = nullptr;
   cudaStream_t st = ctx->stream;
   int* us = m->u_state;
-  if (!ctx->sim_attr_set) {
-    B2_CUDA(cudaFuncSetAttribute(k_cull_fix, cudaFuncAttributeMaxDynamicSharedMemorySize, SIM_SMEM_BYTES));
-    B2_CUDA(cudaFuncSetAttribute(k_upd_close, cudaFuncAttributeMaxDynamicSharedMemorySize, SIM_SMEM_BYTES));
-    ctx->sim_attr_set = true;
-  }
+  // (k_cull_fix / k_upd_close take SIM_SMEM_BYTES of dynamic shared memory: launch<>() raises their limit on first use)
   prof_begin(ctx, PS_MAP);
   // the per-update scalar block `us` is all-zero here: zeroed at creation / Clear and again by the closing kernel of every update
   const int n0 = m->graph_mode ? -1 : (int)m->n0;
@@ -871,19 +868,19 @@ int map_update_dev(b2lo_map* m, float4* d_world, const int* d_n, size_t n_cap, c
     int g4 = (tiles + 3) / 4; if (g4 > 2 * ctx->sm_count) g4 = 2 * ctx->sm_count;
     prof_end(ctx);
     prof_begin(ctx, PS_CULL);
-    k_cull_mark<<<g4, 1024, 0, st>>>(d, n0, sensor[0], sensor[1], sensor[2], radius_sq, m->c_flag, m->c_blkcnt, m->c_blkoff, us);
+    launch<k_cull_mark, 1024, 1>(ctx, dim3((unsigned)(g4)), dim3((unsigned)(1024)), 0, st, d, n0, sensor[0], sensor[1], sensor[2], radius_sq, m->c_flag, m->c_blkcnt, m->c_blkoff, us);
     prof_end(ctx);
     prof_begin(ctx, PS_MAP);
-    k_cull_lists<<<g, 1024, 0, st>>>(d, n0, m->c_flag, m->c_blkoff, us, m->c_removed, m->c_l1work);
-    k_cull_fix<<<1, 1024, SIM_SMEM_BYTES, st>>>(d, m->c_flag, us, m->c_l1work, m->c_removed, m->c_aux, n0);
+    launch<k_cull_lists, 1024, 1>(ctx, dim3((unsigned)(g)), dim3((unsigned)(1024)), 0, st, d, n0, m->c_flag, m->c_blkoff, us, m->c_removed, m->c_l1work);
+    launch<k_cull_fix, 1024, 1>(ctx, dim3((unsigned)(1)), dim3((unsigned)(1024)), SIM_SMEM_BYTES, st, d, m->c_flag, us, m->c_l1work, m->c_removed, m->c_aux, n0);
     ctx->launches += 3;
   }
   int gm = grid_for(n_cap, 256);
   int gw = grid_for(n_cap * 32, 256);   // one warp per point
   int* plist = m->a_list; unsigned int* pfirst = reinterpret_cast<unsigned int*>(m->a_list + m->upd_cap);
   int* pord = m->a_list + 2 * m->upd_cap; int* poff = m->a_list + 3 * m->upd_cap;
-  k_ins_probe<<<gm, 256, 0, st>>>(d, d_world, d_n, us, m->u_pslot, m->u_next, m->a_tab, m->a_log2cap, m->a_slots, local, T16_dev);
-  k_ins_apply<<<gm, 256, 0, st>>>(d, d_world, d_n, m->u_pslot, m->u_next, m->u_isnew, m->u_pts, rehash);
+  launch<k_ins_probe, 256, 1>(ctx, dim3((unsigned)(gm)), dim3((unsigned)(256)), 0, st, d, d_world, d_n, us, m->u_pslot, m->u_next, m->a_tab, m->a_log2cap, m->a_slots, local, T16_dev);
+  launch<k_ins_apply, 256, 1>(ctx, dim3((unsigned)(gm)), dim3((unsigned)(256)), 0, st, d, d_world, d_n, m->u_pslot, m->u_next, m->u_isnew, m->u_pts, rehash);
   const bool bulk = n_cap > BULK_UPD && !gate;
   if (bulk) {
     int gc = (int)((n_cap + INS_CHUNK - 1) / INS_CHUNK); if (gc > 4 * ctx->sm_count) gc = 4 * ctx->sm_count;
@@ -892,25 +889,25 @@ int map_update_dev(b2lo_map* m, float4* d_world, const int* d_n, size_t n_cap, c
     k_ins_scan_apply<<<gc, 1024, 0, st>>>(d, d_n, m->u_isnew, m->u_pslot, m->u_newrank, m->u_part);
     ctx->launches += 2;
   } else {
-    k_ins_scan<<<1, 1024, 0, st>>>(d, d_n, m->u_isnew, m->u_pslot, m->u_newrank, us);
+    launch<k_ins_scan, 1024, 1>(ctx, dim3((unsigned)(1)), dim3((unsigned)(1024)), 0, st, d, d_n, m->u_isnew, m->u_pslot, m->u_newrank, us);
   }
-  k_ins_place<<<gw, 256, 0, st>>>(d, d_n, us, m->u_pslot, m->u_isnew, m->u_newrank, m->u_pts);
+  launch<k_ins_place, 256, 1>(ctx, dim3((unsigned)(gw)), dim3((unsigned)(256)), 0, st, d, d_n, us, m->u_pslot, m->u_isnew, m->u_newrank, m->u_pts);
   ctx->launches += 4;
   int purge = 0;
   if (rehash) {
     // ApplyTransformAndRehash always ends in RecomputeAllSurfels (VoxelMap.cpp:301), whatever compute_surfels says;
     // the affected set is still drained (skip = !compute_surfels is overridden by passing through k_surfel with surfels off)
     MapDev dd = d; dd.compute_surfels = 0;
-    k_surfel<<<gw, 256, 0, st>>>(dd, m->a_tab, m->a_slots, us, plist, pfirst);
+    launch<k_surfel, 256, 1>(ctx, dim3((unsigned)(gw)), dim3((unsigned)(256)), 0, st, dd, m->a_tab, m->a_slots, us, plist, pfirst);
     k_surfel_all<<<grid_for(m->tcap1, 128), 128, 0, st>>>(d);
     ctx->launches += 2;
   } else {
     purge = d.compute_surfels;
-    k_surfel<<<gw, 256, 0, st>>>(d, m->a_tab, m->a_slots, us, plist, pfirst);
+    launch<k_surfel, 256, 1>(ctx, dim3((unsigned)(gw)), dim3((unsigned)(256)), 0, st, d, m->a_tab, m->a_slots, us, plist, pfirst);
     ctx->launches += 1;
   }
   if (bulk) { k_rank_clear<<<gm, 256, 0, st>>>(d, d_n, m->u_pslot, m->u_isnew); ctx->launches++; }
-  k_upd_close<<<1, 1024, SIM_SMEM_BYTES, st>>>(d, us, plist, pfirst, pord, poff, m->p_seq, m->p_aux, purge, d_n, m->u_pslot, m->u_isnew, bulk ? 1 : 0);
+  launch<k_upd_close, 1024, 1>(ctx, dim3((unsigned)(1)), dim3((unsigned)(1024)), SIM_SMEM_BYTES, st, d, us, plist, pfirst, pord, poff, m->p_seq, m->p_aux, purge, d_n, m->u_pslot, m->u_isnew, bulk ? 1 : 0);
   prof_end(ctx);
   ctx->launches += 1;
   B2_CUDA(cudaGetLastError());

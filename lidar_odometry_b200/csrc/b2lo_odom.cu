@@ -12,6 +12,7 @@
 #include <cstring>
 #define B2LO_TL_FILE 3
 #include "b2lo_internal.h"
+#include "b2lo_launch.cuh"
 
 static inline double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -58,7 +59,7 @@ static Pose pose_reproject(const Pose& a) {  // SE3f(R.matrix, t): the SO3(Matri
 // update can be enqueued behind the ICP without a host round trip: one thread turns the ICP state into the scan's pose
 // and decides whether the (already enqueued, gated) map update runs.
 struct OdomDev { float pose[16]; int keyframe; int icp_status; int pad[2]; };
-__global__ void k_odom_decide(const IcpState* st, const ScanParams* __restrict__ sp, const int* __restrict__ d_nfeat, OdomDev* out) { TL_START();
+struct k_odom_decide { static __device__ __forceinline__ void run(const IcpState* st, const ScanParams* __restrict__ sp, const int* __restrict__ d_nfeat, OdomDev* out) { TL_START();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const DecideArgs a = sp->decide;
   Pose result = pose_from_T16(a.guess);
@@ -88,12 +89,12 @@ __global__ void k_odom_decide(const IcpState* st, const ScanParams* __restrict__
   pose_to_T16(result, out->pose);
   out->keyframe = kf;
   out->icp_status = status;
-}
+} };
 
 // The scan's read-back in ONE launch: the ICP state header, the pose/keyframe block, the map counters and the feature count are written
 // straight into the context's page-locked host mirrors (cudaMallocHost memory is device-addressable under UVA), instead of four D2H
 // copy nodes at the end of the replayed graph (a small copy costs more than a small kernel there).  ~0.3 KB over PCIe, posted writes.
-__global__ void k_odom_readback(const IcpState* __restrict__ st, int icp_words, const OdomDev* __restrict__ out, const int* __restrict__ ctr,
+struct k_odom_readback { static __device__ __forceinline__ void run(const IcpState* __restrict__ st, int icp_words, const OdomDev* __restrict__ out, const int* __restrict__ ctr,
                                 const int* __restrict__ d_nfeat, int* h_icp, int* h_out, int* h_counts) { TL_START();
   const int t = threadIdx.x;
   const int* a = reinterpret_cast<const int*>(st);
@@ -103,7 +104,7 @@ __global__ void k_odom_readback(const IcpState* __restrict__ st, int icp_words, 
   if (t < 8) h_counts[t] = ctr[t];
   if (t == 8) h_counts[32] = *d_nfeat;
   __threadfence_system();
-}
+} };
 
 extern "C" void b2lo_default_odom_cfg(b2lo_odom_cfg* c, int mid360) {  // config/kitti.yaml / config/mid360.yaml
   if (!c) return;
@@ -207,7 +208,7 @@ static int enqueue_scan(b2lo_odom* od, size_t flt_ns, size_t cap, bool in_graph,
   if (!rc) rc = icp_run(map, feat, nfeat, cap, ctx->h_sp->T_init, &od->cfg.icp, false, /*restore_on_failure=*/false);
   ctx->sp_preloaded = false;
   if (!rc) {
-    k_odom_decide<<<1, 32, 0, st>>>(ctx->d_icp, ctx->d_sp, nfeat, od->d_out);
+    launch<k_odom_decide, 32, 1>(ctx, dim3((unsigned)(1)), dim3((unsigned)(32)), 0, st, ctx->d_icp, ctx->d_sp, nfeat, od->d_out);
     ctx->launches++;
   }
   if (!rc) {
@@ -221,7 +222,7 @@ static int enqueue_scan(b2lo_odom* od, size_t flt_ns, size_t cap, bool in_graph,
   }
   if (!rc) {
     static_assert(offsetof(IcpState, trace) % sizeof(int) == 0 && sizeof(OdomDev) % sizeof(int) == 0, "read-back copies whole words");
-    k_odom_readback<<<1, 128, 0, st>>>(ctx->d_icp, (int)(offsetof(IcpState, trace) / sizeof(int)), od->d_out, map->d.ctr, nfeat,
+    launch<k_odom_readback, 128, 1>(ctx, dim3((unsigned)(1)), dim3((unsigned)(128)), 0, st, ctx->d_icp, (int)(offsetof(IcpState, trace) / sizeof(int)), od->d_out, map->d.ctr, nfeat,
                                        reinterpret_cast<int*>(ctx->h_icp), reinterpret_cast<int*>(od->h_out), ctx->h_counts);
     ctx->launches++;
     cudaError_t e = cudaGetLastError();

@@ -29,7 +29,7 @@ def label(fid, line):
     if "TL_HERE" in text:
         return "  . " + text.split("//")[-1].strip()
     for k in range(line - 1, max(line - 12, -1), -1):
-        m = re.search(r"\b(k_[a-z0-9_]+)\s*\(", src[fid][k])
+        m = re.search(r"\bstruct\s+(k_[a-z0-9_]+)", src[fid][k]) or re.search(r"\b(k_[a-z0-9_]+)\s*\(", src[fid][k])
         if m:
             return m.group(1)
     return f"{FILES[fid]}:{line}"
