@@ -422,6 +422,77 @@ def batch_leg(api, local, dev_args, S, K, W):
             "note": "aggregate over independent sequences sharing one B200; not the per-sequence latency of `value`"}
 
 
+def lockstep_leg(api, local, dev_args, S, K, W, peak, peak_kind):
+    """Lock-step batch (b2lo_lockstep_*): S independent sequences, ONE graph replay per step, every kernel started once per step with
+    blockIdx.y = sequence.  Sequence j runs the scans rotated by j, so the S maps and poses differ inside a step.  Time = CUDA events around
+    each step's graph on the batch stream (device-resident scans, no L2 flush between steps: S maps + S scans are far larger than L2)."""
+    import torch
+    n_have = K + W + 1
+    odos = [api.Odometry(api.Context(local)) for _ in range(S)]
+    ls = api.LockstepBatch(odos)
+
+    plans = [[dev_args((k + j) % n_have)[:2] for j in range(S)] for k in range(n_have)]   # argument lists built outside the timed loop
+
+    def step(k):
+        return ls.process_dev(plans[k % n_have], dev_args(0)[2], raw=True)
+
+    for k in range(W):
+        step(k)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter(); dev_ms = 0.0; nq = 0; iters = 0
+    for k in range(W, W + K):
+        res, ms = step(k)
+        dev_ms += ms
+        for r in res:
+            nq += r.n_features * r.n_iters; iters += r.n_iters
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    st = ls.stats()
+    out = {"sequences": S, "scans": S * K, "scans_per_s": S * K / (dev_ms * 1e-3), "ms_per_step": dev_ms / K, "scans_per_s_wall": S * K / wall,
+           "wall_ms_per_step": 1e3 * wall / K, "gn_iterations_per_scan": iters / (S * K), "queries_per_step_iteration": nq / max(iters, 1) * S,
+           "kernels_per_step": st["kernels_per_step"], "graph_builds": st["builds"], "fallback_steps": st["fallbacks"],
+           "driver": "b2lo_lockstep_process_dev: one CUDA graph replay per step for all sequences, grid.y = sequence",
+           "timing": "CUDA events around every step on the batch stream; wall = host clock around the K calls"}
+    del ls, odos
+    return out
+
+
+def lockstep_groups_leg(api, local, dev_args, G, S, K, W):
+    """G lock-step batches of S sequences each, one host thread and one stream per batch, running side by side on one GPU: while one
+    batch sits in a latency-bound step (the S PKO fits: one CTA per sequence), the kernels of the other batches fill the remaining SMs.
+    Whole-leg wall clock between barriers (the batches overlap, so per-step event times would double count)."""
+    import threading
+    import torch
+    n_have = K + W + 1
+    groups = []
+    for g in range(G):
+        odos = [api.Odometry(api.Context(local)) for _ in range(S)]
+        groups.append((odos, api.LockstepBatch(odos)))
+
+    plans = [[[dev_args((k + j + 7 * g) % n_have)[:2] for j in range(S)] for k in range(n_have)] for g in range(G)]
+
+    def run(g, k0, k1):
+        odos, ls = groups[g]
+        for k in range(k0, k1):
+            ls.process_dev(plans[g][k % n_have], dev_args(0)[2], raw=True)
+
+    for g in range(G):
+        run(g, 0, W)
+    torch.cuda.synchronize()
+    th = [threading.Thread(target=run, args=(g, W, W + K)) for g in range(G)]
+    t0 = time.perf_counter()
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    out = {"batches": G, "sequences_per_batch": S, "sequences": G * S, "scans": G * S * K, "scans_per_s": G * S * K / wall, "wall_ms_per_step": 1e3 * wall / K,
+           "driver": "G x b2lo_lockstep_process_dev from G host threads (one stream each)", "timing": "host wall clock around the whole leg, device synchronised on both sides"}
+    del groups
+    return out
+
+
 def export_leg(ctx, api, scans, poses, K):
     """SURVEY 8f-4: the final-map downsample of Estimator::save_map_to_ply (util::VoxelGrid, leaf 0.4 m) over the accumulated world
     cloud of the benchmark sequence, through the host-buffer call (H2D + D2H inside), next to the CPU oracle on the same cloud."""
@@ -469,6 +540,7 @@ def main():
     ap.add_argument("--stress-voxels", type=float, default=1.0e7)
     ap.add_argument("--stress-only", action="store_true")
     ap.add_argument("--concurrent", type=int, nargs="*", default=[16, 32, 96], help="sequences sharing one GPU in the throughput-mode leg (empty: skip); the first size is also run with one host thread per sequence")
+    ap.add_argument("--lockstep", type=int, nargs="*", default=[32, 128, 256], help="batch sizes of the lock-step throughput leg (empty: skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
@@ -664,6 +736,10 @@ def main():
     if world == 1 and args.concurrent:
         conc = [concurrent_leg(api, local, dev_args, S, K, W) for S in args.concurrent[:1]]
         conc += [batch_leg(api, local, dev_args, S, K, W) for S in args.concurrent]
+    lockstep = None
+    if world == 1 and args.lockstep:
+        lockstep = [lockstep_leg(api, local, dev_args, S, K, W, peak, peak_kind) for S in args.lockstep]
+        lockstep += [lockstep_groups_leg(api, local, dev_args, G, S, K, W) for G, S in ((3, 96), (4, 64))]
 
     stress = mid360 = export = None
     if world == 1 and not args.no_stress:
@@ -688,7 +764,7 @@ def main():
                     "d2h_bytes_per_step": (d1 - d0) / K},
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "stage_ms_per_scan": {k: v["ms_total"] / K for k, v in stage.items()},
             "dominant_kernel_group": dominant, "cpu_baseline": cpu,
-            "concurrent_sequences_one_gpu": conc, "batched_sequences_all_gpus": batched_all, "point_sharded": sharded, "final_map_export": export, "large_map_stress": stress, "kdtree_mid360": mid360}
+            "concurrent_sequences_one_gpu": conc, "lockstep_sequences_one_gpu": lockstep, "batched_sequences_all_gpus": batched_all, "point_sharded": sharded, "final_map_export": export, "large_map_stress": stress, "kdtree_mid360": mid360}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

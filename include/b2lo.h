@@ -292,6 +292,20 @@ int b2lo_odom_set_record_fmt(b2lo_odom* od, const b2lo_record_fmt* fmt);
 int b2lo_odom_process_batch_dev(b2lo_odom* const* ods, const float* const* xyz_dev, const size_t* n, const float* const* next_xyz_dev,
                                 const size_t* next_n, size_t stride_floats, int count, b2lo_odom_result* res);
 
+/* Lock-step batches: S independent sequences on one GPU advance by ONE scan per call, and every kernel of the scan is started once per
+ * call for all of them (grid.y = sequence; per-sequence arguments in a device array) inside one replayed CUDA graph.  The single-CTA
+ * latency chains of a scan (PKO fit, Gauss-Newton finish, update close) run for S sequences at once on S SMs, and the GPU's front end
+ * dispatches ~30 kernels per STEP instead of ~30 per scan (what caps b2lo_odom_process_batch_dev).  Results per sequence are those of the
+ * sequence processed alone, bit for bit.  The sequences (own b2lo_odom and own b2lo_ctx each, surfel mode, same device) stay usable on
+ * their own between calls; first frames, empty scans and record-stream input fall back to the per-sequence path inside the call.
+ * res[i].device_ms = CUDA-event time of the whole step (all sequences share it). */
+typedef struct b2lo_lockstep b2lo_lockstep;
+int b2lo_lockstep_create(b2lo_odom* const* ods, int count, b2lo_lockstep** out);
+int b2lo_lockstep_destroy(b2lo_lockstep* ls);
+int b2lo_lockstep_process_dev(b2lo_lockstep* ls, const float* const* xyz_dev, const size_t* n, size_t stride_floats, b2lo_odom_result* res,
+                              float* device_ms /*nullable*/);
+int b2lo_lockstep_stats(b2lo_lockstep* ls, long long* kernels_per_step, long long* replays, long long* builds, long long* fallbacks);
+
 #ifdef __cplusplus
 }
 #endif

@@ -907,3 +907,45 @@ class OdometryBatch:
 class _BorrowedVoxelMap(VoxelMap):
     def __del__(self):  # owned by the Odometry handle
         pass
+
+
+class LockstepBatch:
+    """S independent sequences on one GPU advancing one scan per call, every kernel of the scan started once per call for all of them
+    (b2lo_lockstep_*): the throughput mode for batches of recorded sequences.  ``odometries``: Odometry objects, one context each."""
+
+    def __init__(self, odometries):
+        self.ods = list(odometries)
+        arr = (C.c_void_p * len(self.ods))(*[o.h for o in self.ods])
+        self.h = C.c_void_p()
+        check(capi.lib().b2lo_lockstep_create(arr, len(self.ods), C.byref(self.h)))
+        self._res = (OdomResult * len(self.ods))()
+        self._ptrs = (C.c_void_p * len(self.ods))()
+        self._ns = (C.c_size_t * len(self.ods))()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            try:
+                capi.lib().b2lo_lockstep_destroy(self.h)
+            except Exception:
+                pass
+            self.h = None
+
+    def process_dev(self, scans, stride_floats, raw=False):
+        """scans: one (device pointer, point count) per sequence.  Returns (list of result dicts, CUDA-event ms of the whole step)."""
+        for i, (ptr, n) in enumerate(scans):
+            self._ptrs[i] = ptr
+            self._ns[i] = n
+        ms = C.c_float(0.0)
+        check(capi.lib().b2lo_lockstep_process_dev(self.h, self._ptrs, self._ns, stride_floats, self._res, C.byref(ms)))
+        if raw:          # the b2lo_odom_result array itself (valid until the next call): no per-sequence Python objects on the hot loop
+            return self._res, float(ms.value)
+        out = []
+        for r in self._res:
+            out.append(dict(pose=np.array(r.pose, np.float32).reshape(4, 4), keyframe=bool(r.keyframe), icp_status=r.icp_status, n_features=r.n_features,
+                            n_corr=r.n_corr, n_iters=r.n_iters, l0=r.l0, l1=r.l1))
+        return out, float(ms.value)
+
+    def stats(self):
+        a, b, c, d = C.c_longlong(), C.c_longlong(), C.c_longlong(), C.c_longlong()
+        check(capi.lib().b2lo_lockstep_stats(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return dict(kernels_per_step=a.value, replays=b.value, builds=c.value, fallbacks=d.value)

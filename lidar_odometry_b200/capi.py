@@ -162,6 +162,10 @@ SIGNATURES = {
     "b2lo_odom_process_la": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, C.POINTER(OdomResult)]),
     "b2lo_odom_set_record_fmt": (_i, [_vp, C.POINTER(RecordFmt)]),
     "b2lo_odom_process_batch_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "b2lo_lockstep_create": (_i, [_vp, _i, C.POINTER(_vp)]),
+    "b2lo_lockstep_destroy": (_i, [_vp]),
+    "b2lo_lockstep_process_dev": (_i, [_vp, _vp, _vp, _sz, _vp, C.POINTER(C.c_float)]),
+    "b2lo_lockstep_stats": (_i, [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
 }
 
 

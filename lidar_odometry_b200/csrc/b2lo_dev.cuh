@@ -28,7 +28,7 @@
 #define B2LO_TL_FILE 0
 #endif
 namespace b2 {
-constexpr int TL_CAP = 4096;
+constexpr int TL_CAP = 1 << 16;
 static __device__ unsigned long long g_tl[2 * TL_CAP];
 static __device__ unsigned int g_tl_n;
 __device__ __forceinline__ void tl_mark(int line) {

@@ -314,6 +314,7 @@ int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sam
   }
   // ctx->f_tab is all-idle (0xFF) here: memset when allocated, put back by k_flt_reduce after every run
   int blocks = (int)((ctx->pts_cap + 255) / 256); if (blocks > 1184) blocks = 1184;
+  blocks = batch_grid(ctx, blocks);
   const ScanParams* sp = ctx->d_sp;
   const bool prof = st == ctx->stream;   // the per-stage events live on the context stream
   if (prof) prof_begin(ctx, PS_FILTER);

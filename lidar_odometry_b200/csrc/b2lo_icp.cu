@@ -154,7 +154,9 @@ struct k_icp_corr { static __device__ __forceinline__ void run(MapDev M, const f
   if (tid < 9) sR[tid] = pose_v; else if (tid < 12) sT[tid - 9] = pose_v;
   __syncthreads();
   const int ntiles = (npts + TILE - 1) / TILE;
-  if (!FUSE && tile >= ntiles) return;
+  // CTAs without a tile leave at once (also from the fused kernel's election, which counts the active CTAs only; see k_icp_gn)
+  const unsigned nact = (unsigned)(ntiles < 1 ? 1 : (ntiles < G ? ntiles : G));
+  if (blockIdx.x >= nact) return;
   const uint32_t mask = (1u << M.l1_log2cap) - 1u;
   CorrStage cur;
   if (tile < ntiles) corr_issue(M, sR, sT, p1, tile * TILE + tid < npts, cur);
@@ -233,7 +235,7 @@ struct k_icp_corr { static __device__ __forceinline__ void run(MapDev M, const f
     __syncthreads();
     if (tid == 0) {
       const unsigned int t = atomicAdd(&st->ticket_corr, 1u);
-      s_last = (t == gridDim.x - 1);
+      s_last = (t == nact - 1);
       if (s_last) st->ticket_corr = 0u;
     }
     __syncthreads();
@@ -716,30 +718,37 @@ struct k_icp_pko2 { static __device__ __forceinline__ void run(IcpState* st, Icp
   __shared__ int s_i[4];
   __shared__ int s_last;
   const int k = threadIdx.x, lane = k & 31, w = k >> 5;
-  const int ai = blockIdx.x + 1;
   // the done flag and this thread's operands go out together
   const int done_v = st->done;
-  const double alpha = T->alpha[ai];
-  const double pf = T->Z[ai];
+  const int na_all = T->n_alpha;
   const double dr = T->trunc / 100.0;
   const double Pr_v = k < 100 ? __ldcg(&gmm[16 + k]) : 0.0;
   if (done_v || !prm.use_pko) return;
-  double v = 0.0, c = 0.0;
-  if (k < 100) {
-    double r = dr * (1.0 + (double)k);
-    double Pr = Pr_v;
-    double Q = pko_kernel(T->kernel_type, r, alpha) / (pf + 1e-10) + 1e-10;
-    double Mx = 0.5 * (Pr + Q);
-    double jsd = 0.5 * (Pr * log(Pr / Mx) + Q * log(Q / Mx));
-    if (jsd == jsd) { v = jsd; c = 1.0; }   // NaN terms are skipped (:777-779)
-  }
+  // one candidate per CTA for a lone sequence (gridDim.x = segments); a lock-step batch starts fewer CTAs per sequence and each walks
+  // several candidates - the per-candidate sums are the same either way
+  for (int ai = blockIdx.x + 1; ai < na_all; ai += gridDim.x) {
+    const double alpha = T->alpha[ai];
+    const double pf = T->Z[ai];
+    double v = 0.0, c = 0.0;
+    if (k < 100) {
+      double r = dr * (1.0 + (double)k);
+      double Pr = Pr_v;
+      double Q = pko_kernel(T->kernel_type, r, alpha) / (pf + 1e-10) + 1e-10;
+      double Mx = 0.5 * (Pr + Q);
+      double jsd = 0.5 * (Pr * log(Pr / Mx) + Q * log(Q / Mx));
+      if (jsd == jsd) { v = jsd; c = 1.0; }   // NaN terms are skipped (:777-779)
+    }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
-  if (lane == 0) { s_c[w] = v; s_n[w] = c; }
-  __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+    if (lane == 0) { s_c[w] = v; s_n[w] = c; }
+    __syncthreads();
+    if (k == 0) {
+      double cost = (s_c[0] + s_c[1]) + (s_c[2] + s_c[3]), cnt = (s_n[0] + s_n[1]) + (s_n[2] + s_n[3]);
+      js[ai] = (pf < 1e-10 || cnt == 0.0) ? 1.7976931348623157e308 : cost / cnt;
+    }
+    __syncthreads();
+  }
   if (k == 0) {
-    double cost = (s_c[0] + s_c[1]) + (s_c[2] + s_c[3]), cnt = (s_n[0] + s_n[1]) + (s_n[2] + s_n[3]);
-    js[ai] = (pf < 1e-10 || cnt == 0.0) ? 1.7976931348623157e308 : cost / cnt;
     __threadfence();
     unsigned int old = atomicAdd(ticket, 1u);
     s_last = (old == gridDim.x - 1);
@@ -848,6 +857,13 @@ struct k_icp_gn { static __device__ __forceinline__ void run(MapDev M, const flo
   float pose_v = 0.0f;
   if (threadIdx.x < 12) pose_v = threadIdx.x < 9 ? st->R[threadIdx.x] : st->t[threadIdx.x - 9];
   if (done_v) return;
+  // CTAs beyond the last tile of this scan have nothing to add: they leave before the reduction, and the election and the final sum
+  // run over the active CTAs only (their partial sums would be exact zeros: the result is bit-identical).  The grid is sized by the
+  // buffer capacity (graph-replayable), so for a 4 k-point scan 48 of 64 CTAs are of this kind - harmless for a lone sequence, but a
+  // lock-step batch of 128 sequences would push 6000 of them through the SMs per launch.
+  const int ntile_v = (npts + (int)blockDim.x - 1) / (int)blockDim.x;
+  const unsigned nact = (unsigned)(ntile_v < 1 ? 1 : (ntile_v < (int)gridDim.x ? ntile_v : (int)gridDim.x));
+  if (blockIdx.x >= nact) return;
   if (threadIdx.x < 9) sR[threadIdx.x] = pose_v; else if (threadIdx.x < 12) sT[threadIdx.x - 9] = pose_v;
   __syncthreads();
   const double sdiv = fmax(scale_v, 1e-6);
@@ -915,7 +931,7 @@ struct k_icp_gn { static __device__ __forceinline__ void run(MapDev M, const flo
   }
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) { unsigned int old = atomicAdd(&st->ticket, 1u); s_last = (old == gridDim.x - 1); }
+  if (threadIdx.x == 0) { unsigned int old = atomicAdd(&st->ticket, 1u); s_last = (old == nact - 1); }
   __syncthreads();
   if (!s_last) return;
   const long long g0 = clock64();
@@ -924,7 +940,7 @@ struct k_icp_gn { static __device__ __forceinline__ void run(MapDev M, const flo
   // then the 8 warp totals are added in order -> bit-reproducible from run to run
   {
     double v = 0.0;
-    if (lane < 28) for (unsigned b = wid; b < gridDim.x; b += 8) v += __ldcg(&partial[b * 28 + lane]);
+    if (lane < 28) for (unsigned b = wid; b < nact; b += 8) v += __ldcg(&partial[b * 28 + lane]);
     __syncthreads();
     if (lane < 28) red[wid][lane] = v;
     __syncthreads();
@@ -1123,11 +1139,11 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
     }
     if (cfg->use_adaptive_m_estimator) {
       prof_begin(ctx, PS_PKO2);
-      launch<k_icp_pko2, 128, 1>(ctx, dim3((unsigned)(cfg->num_alpha_segments)), dim3((unsigned)(128)), 0, s, ctx->d_icp, prm, ctx->d_pko, gmm, js, tk);
+      launch<k_icp_pko2, 128, 1>(ctx, dim3((unsigned)(batch_grid(ctx, cfg->num_alpha_segments))), dim3((unsigned)(128)), 0, s, ctx->d_icp, prm, ctx->d_pko, gmm, js, tk);
       prof_end(ctx);
     }
     prof_begin(ctx, PS_GN);
-    if (surfel) launch<k_icp_gn<true>, TILE, 1>(ctx, dim3((unsigned)(grid)), dim3((unsigned)(TILE)), 0, s, map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, nullptr, ctx->i_partial, nullptr);
+    if (surfel) launch<k_icp_gn<true>, TILE, 2>(ctx, dim3((unsigned)(grid)), dim3((unsigned)(TILE)), 0, s, map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, nullptr, ctx->i_partial, nullptr);
     else launch<k_icp_gn<false>, TILE, 1>(ctx, dim3((unsigned)(grid)), dim3((unsigned)(TILE)), 0, s, map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->k_plane, ctx->i_partial, nullptr);
     prof_end(ctx);
     ctx->launches += (cfg->use_adaptive_m_estimator ? 4 : 3) - (fuse ? 1 : 0);
@@ -1463,7 +1479,7 @@ extern "C" int b2lo_icp_shard_accumulate(b2lo_map* map, const b2lo_icp_cfg* cfg,
   prof_end(ctx);
   if (cfg->use_adaptive_m_estimator) { launch<k_icp_pko2, 128, 1>(ctx, dim3((unsigned)(cfg->num_alpha_segments)), dim3((unsigned)(128)), 0, s, ctx->d_icp, prm, ctx->d_pko, gmm, js, tk); ctx->launches++; }
   prof_begin(ctx, PS_GN);
-  launch<k_icp_gn<true>, TILE, 1>(ctx, dim3((unsigned)(grid)), dim3((unsigned)(TILE)), 0, s, map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, nullptr, ctx->i_partial, acc28_dev);
+  launch<k_icp_gn<true>, TILE, 2>(ctx, dim3((unsigned)(grid)), dim3((unsigned)(TILE)), 0, s, map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, nullptr, ctx->i_partial, acc28_dev);
   prof_end(ctx);
   ctx->launches += 2;
   B2_CUDA(cudaGetLastError());
@@ -1629,7 +1645,7 @@ extern "C" int b2lo_icp_shard_optimize(b2lo_map* map, b2lo_shard_comm* c, const 
     launch<k_icp_pko1, PKO_THREADS, 1>(ctx, dim3((unsigned)(1)), dim3((unsigned)(PKO_THREADS)), 0, s, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff, ctx->d_pko,
                                          ctx->d_pko_hits, gmm, c->d_sample, 0, 0.0, ctx->i_tilesum, c->d_plan);
     if (cfg->use_adaptive_m_estimator) { launch<k_icp_pko2, 128, 1>(ctx, dim3((unsigned)(cfg->num_alpha_segments)), dim3((unsigned)(128)), 0, s, ctx->d_icp, prm, ctx->d_pko, gmm, js, tk); ctx->launches++; }
-    launch<k_icp_gn<true>, TILE, 1>(ctx, dim3((unsigned)(grid)), dim3((unsigned)(TILE)), 0, s, map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, nullptr, ctx->i_partial, c->d_acc);
+    launch<k_icp_gn<true>, TILE, 2>(ctx, dim3((unsigned)(grid)), dim3((unsigned)(TILE)), 0, s, map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, nullptr, ctx->i_partial, c->d_acc);
     if (last) cudaEventRecord(c->ev[2], s);
     if (c->world > 1) B2_NCCL(N.AllReduce(c->d_acc, c->d_acc, 28, ncclDouble, ncclSum, c->comm, s));
     if (last) cudaEventRecord(c->ev[3], s);

@@ -141,6 +141,7 @@ struct b2lo_ctx {
   b2::ScanParams* d_sp = nullptr; b2::ScanParams* h_sp = nullptr /*pinned*/; cudaEvent_t ev_sp = nullptr; bool sp_busy = false;
   bool sp_preloaded = false;       // the caller has already uploaded the whole parameter block for this launch sequence
   b2::Prof* prof = nullptr;
+  int batch_S = 0;                 // > 0 while a lock-step batch of that many sequences records: grids of order-independent kernels shrink (batch_grid)
   b2::Recorder* rec = nullptr;     // non-null while a lock-step batch records this context's launch sequence (b2lo_launch.cuh)
   double force_scale = 0.0;        // next icp_run: ScanParams::force_scale (b2lo_icp_iterate), reset by icp_run
   double host_us[8] = {0};         // wall-clock split of the host side of b2lo_odom_process (debug aid): gather, enqueue, wait, ...
@@ -154,6 +155,7 @@ struct b2lo_map {
   // update scratch sized by the number of new points
   size_t upd_cap = 0;
   float4* u_pts = nullptr; int* u_pslot = nullptr; int* u_next = nullptr; int* u_isnew = nullptr; int* u_newrank = nullptr;
+  float* s_rec = nullptr;           // per affected L1: gathered child centroids (lock-step surfel refit)
   int* u_part = nullptr;            // per-chunk totals of the new-voxel scan for bulk inserts (k_ins_scan_part/top/apply)
   float4* r_tmp = nullptr; size_t r_tmp_cap = 0; int* r_n = nullptr;   // transformed centroids of ApplyTransformAndRehash (kept between calls)
   b2::FEntry* a_tab = nullptr; int a_log2cap = 0;   // affected-L1 set of the current update
@@ -174,6 +176,16 @@ struct b2lo_map {
 };
 
 namespace b2 {
+// Launch geometry inside a lock-step batch.  A lone sequence sizes its grids by capacity (up to 1184 CTAs for the warp-per-point kernels),
+// which costs nothing when the other SMs idle; S sequences side by side would start S x 3900 mostly empty CTAs per step (measured: +19 us
+// per sequence and step).  Kernels whose results do not depend on the grid (grid-stride loops over hash / per-voxel work) therefore get
+// about two resident waves divided by S.  K2 and K5 keep their grids: their per-CTA partial sums are part of the bit-exact result.
+inline int batch_grid(const b2lo_ctx* ctx, int g) {
+  if (ctx->batch_S <= 0) return g;
+  int lim = 2368 / ctx->batch_S;
+  if (lim < 4) lim = 4;
+  return g < lim ? g : lim;
+}
 void prof_begin(b2lo_ctx* ctx, int slot);
 void prof_end(b2lo_ctx* ctx);
 void prof_drain(b2lo_ctx* ctx);

@@ -35,6 +35,7 @@ template <class K, int MAXT, int MINB, class... A> __global__ void __launch_boun
 
 struct LaunchRec {
   void (*many)(const void* packs, int S, dim3 grid, dim3 block, size_t smem, cudaStream_t st) = nullptr;   // also the identity of the kernel
+  void (*prep)(size_t smem) = nullptr;   // function attributes of the batched instantiation, to be set OUTSIDE a stream capture
   dim3 grid, block;
   size_t smem = 0;
   std::vector<unsigned char> args;   // the Pack<A...> of this sequence
@@ -43,9 +44,12 @@ struct Recorder { std::vector<LaunchRec> recs; };
 Recorder* ctx_recorder(b2lo_ctx* ctx);   // b2lo_core.cu: the context's recorder while it is recording, else nullptr
 
 template <class K, int MAXT, int MINB, class... A>
+void launch_many_prep(size_t smem) {
+  static size_t have = 48 * 1024;
+  if (smem > have) { cudaFuncSetAttribute(k_many<K, MAXT, MINB, A...>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); have = smem; }
+}
+template <class K, int MAXT, int MINB, class... A>
 void launch_many(const void* packs, int S, dim3 g, dim3 b, size_t smem, cudaStream_t st) {
-  static bool attr = false;
-  if (smem > 48 * 1024 && !attr) { cudaFuncSetAttribute(k_many<K, MAXT, MINB, A...>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
   k_many<K, MAXT, MINB, A...><<<dim3(g.x, (unsigned)S), b, smem, st>>>(static_cast<const Pack<A...>*>(packs));
 }
 
@@ -54,6 +58,7 @@ inline void launch(b2lo_ctx* ctx, dim3 g, dim3 b, size_t smem, cudaStream_t st, 
   if (Recorder* r = ctx_recorder(ctx)) {
     LaunchRec rec;
     rec.many = &launch_many<K, MAXT, MINB, A...>;
+    rec.prep = &launch_many_prep<K, MAXT, MINB, A...>;
     rec.grid = g; rec.block = b; rec.smem = smem;
     Pack<A...> p;
     std::memset(&p, 0, sizeof p);      // padding bytes compare equal between recordings

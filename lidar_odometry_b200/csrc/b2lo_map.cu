@@ -20,6 +20,7 @@
 //             arbitrary-order swap-erase on the dense L0 vector; one thread replays it on indices only
 //             (shared memory), then the moves are applied in parallel.
 #include <climits>
+#include <cstdlib>
 #define B2LO_TL_FILE 4
 #include "b2lo_internal.h"
 #include "b2lo_launch.cuh"
@@ -326,7 +327,7 @@ struct k_ins_apply { static __device__ __forceinline__ void run(MapDev M, const 
 } };
 // one CTA: rank of every new voxel in first-seen order (4 points per thread); the rank is also left in the voxel's
 // hash entry so that siblings can order themselves (k_ins_place)
-struct k_ins_scan { static __device__ __forceinline__ void run(MapDev M, const int* __restrict__ d_m, const int* isnew, const int* pslot, int* newrank, int* us) { TL_START();
+struct k_ins_scan { static __device__ __forceinline__ void run(MapDev M, const int* __restrict__ d_m, const int* isnew, const int* pslot, int* newrank, int* us, int* newlist) { TL_START();
   const int gate_v = M.gate ? *M.gate : 1;
   __shared__ int sm[40];
   const int m = *d_m;
@@ -343,7 +344,7 @@ struct k_ins_scan { static __device__ __forceinline__ void run(MapDev M, const i
     for (int k = 0; k < 4; ++k) {
       if (i0 + k < m) {
         newrank[i0 + k] = e;
-        if (f[k]) { M.l0_tab[pslot[i0 + k]].rank = e; ++e; }
+        if (f[k]) { M.l0_tab[pslot[i0 + k]].rank = e; newlist[e] = i0 + k; ++e; }   // newlist: the points that created a voxel, compact, in creation order
       }
     }
     base += tot;
@@ -390,7 +391,7 @@ __global__ void __launch_bounds__(1024) k_ins_scan_top(MapDev M, const int* __re
   }
 }
 __global__ void __launch_bounds__(1024) k_ins_scan_apply(MapDev M, const int* __restrict__ d_m, const int* __restrict__ isnew, const int* __restrict__ pslot,
-                                                         int* newrank, const int* __restrict__ part) { TL_START();
+                                                         int* newrank, const int* __restrict__ part, int* newlist) { TL_START();
   __shared__ int sm[40];
   const int m = *d_m;
   const int nchunks = (m + INS_CHUNK - 1) / INS_CHUNK;
@@ -405,7 +406,7 @@ __global__ void __launch_bounds__(1024) k_ins_scan_apply(MapDev M, const int* __
     for (int k = 0; k < 4; ++k) {
       if (i0 + k < m) {
         newrank[i0 + k] = e;
-        if (f[k]) { M.l0_tab[pslot[i0 + k]].rank = e; ++e; }
+        if (f[k]) { M.l0_tab[pslot[i0 + k]].rank = e; newlist[e] = i0 + k; ++e; }   // newlist: the points that created a voxel, compact, in creation order
       }
     }
   }
@@ -420,7 +421,7 @@ __global__ void __launch_bounds__(256) k_rank_clear(MapDev M, const int* __restr
 // position is (#siblings that already existed) + (#new siblings created earlier), so nobody has to read nchild while
 // it is being updated; the first new sibling writes the new count.
 struct k_ins_place { static __device__ __forceinline__ void run(MapDev M, const int* __restrict__ d_m, int* us, const int* pslot, const int* isnew,
-                                                   const int* newrank, const float4* newc) { TL_START();
+                                                   const int* newrank, const float4* newc, const int* __restrict__ newlist) { TL_START();
   const int gate_v = M.gate ? *M.gate : 1;
   const int m = *d_m;
   const int err_v = us[US_ERR];
@@ -428,8 +429,11 @@ struct k_ins_place { static __device__ __forceinline__ void run(MapDev M, const 
   if (!gate_v || (err_v & ERR_CAP)) return;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int i = warp; i < m; i += nwarps) {
-    if (!isnew[i]) continue;
+  // the compact list of the points that created a voxel (k_ins_scan): a warp never looks at the ~85 % of the points that did not
+  const int nnew = us[US_NNEW];
+  (void)m; (void)isnew;
+  for (int r = warp; r < nnew; r += nwarps) {
+    const int i = newlist[r];
     const int s0 = pslot[i];
     const int myrank = newrank[i];
     const int pos = base + myrank;
@@ -510,6 +514,77 @@ struct k_surfel { static __device__ __forceinline__ void run(MapDev M, FEntry* a
     }
     if (lane != 0) continue;
     if (nc < 3) { M.l1_tab[s1].key = k1 & ~SURFEL_BIT; continue; }
+    float mu[3], nrm[3], plan;
+    fit_plane(cents, nc, mu, nrm, &plan);
+    if (plan > M.planarity_thr) {  // not planar: the parent and all its children go (VoxelMap.cpp:244-253)
+      int idx = atomicAdd(&us[US_NPURGE], 1);
+      plist[idx] = s1; pfirst[idx] = first;
+      continue;
+    }
+    L1Entry* e = &M.l1_tab[s1];
+    e->n[0] = nrm[0]; e->n[1] = nrm[1]; e->n[2] = nrm[2];
+    e->c[0] = mu[0]; e->c[1] = mu[1]; e->c[2] = mu[2];
+    mt->planarity = plan; mt->last_child_count = N;
+    __threadfence();
+    e->key = k1 | SURFEL_BIT;
+  }
+} };
+
+// The same refit in TWO kernels for lock-step batches: a warp gathers the child centroids of an affected L1 (lane c fetches child c,
+// as above) into a scratch record, then ONE THREAD per affected L1 runs the sums, the Jacobi SVD and the planarity gate.  With S x ~900
+// refits per step a warp per refit would leave 31 lanes waiting for lane 0's SVD (in-graph timeline at S = 128: 312 us per step in one
+// kernel; a thread-per-L1 kernel that also walks the children serially: 231 us).  Same arithmetic in the same order: identical bits.
+constexpr int SURFEL_REC = 88;   // floats per scratch record: s1, nc, first, N, then <= 27 centroids
+struct k_surfel_gather { static __device__ __forceinline__ void run(MapDev M, FEntry* atab, const int* __restrict__ alist, int* us, float* rec) { TL_START();
+  const int gate_v = M.gate ? *M.gate : 1;
+  const int naff = us[US_NAFF];
+  const bool skip = (us[US_ERR] & ERR_CAP) || !M.compute_surfels;
+  if (!gate_v) return;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int a = warp; a < naff; a += nwarps) {
+    float* r = rec + (size_t)a * SURFEL_REC;
+    const int h = alist[a];
+    const unsigned long long ak = atab[h].key;
+    const unsigned int first = atab[h].first;
+    __syncwarp();
+    if (lane == 0) { atab[h].key = KEY_EMPTY; atab[h].first = 0xFFFFFFFFu; atab[h].cnt = -1; r[0] = __int_as_float(-1); }
+    if (skip) continue;
+    int s1 = l1_find(M, ak);
+    if (s1 < 0) continue;
+    L1Meta* mt = &M.l1_meta[s1];
+    const unsigned long long k1 = M.l1_tab[s1].key;
+    const int N = mt->nchild;
+    if (N < 5) { if (lane == 0) M.l1_tab[s1].key = k1 & ~SURFEL_BIT; continue; }
+    if ((k1 & SURFEL_BIT) && mt->last_child_count == N) continue;  // incremental skip (VoxelMap.cpp:202-205)
+    int px, py, pz;
+    key_unpack(k1 & KEY_MASK, px, py, pz);
+    float cx = 0.0f, cy = 0.0f, cz = 0.0f;
+    int have = 0;
+    if (lane < N) {
+      int s0 = l0_find(M, child_key(px, py, pz, M.factor, mt->child[lane]));
+      if (s0 >= 0) { float4 c = M.l0_cent[M.l0_tab[s0].pos]; cx = c.x; cy = c.y; cz = c.z; have = 1; }
+    }
+    const unsigned hm = __ballot_sync(0xffffffffu, have);
+    if (have) { const int q = __popc(hm & ((1u << lane) - 1u)); r[4 + 3 * q] = cx; r[5 + 3 * q] = cy; r[6 + 3 * q] = cz; }   // child-set order, present children only
+    if (lane == 0) { r[1] = __int_as_float(__popc(hm)); r[2] = __uint_as_float(first); r[3] = __int_as_float(N); r[0] = __int_as_float(s1); }
+  }
+} };
+struct k_surfel_fit { static __device__ __forceinline__ void run(MapDev M, int* us, const float* __restrict__ rec, int* plist, unsigned int* pfirst) { TL_START();
+  const int gate_v = M.gate ? *M.gate : 1;
+  const int naff = us[US_NAFF];
+  if (!gate_v) return;
+  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < naff; a += gridDim.x * blockDim.x) {
+    const float* r = rec + (size_t)a * SURFEL_REC;
+    const int s1 = __float_as_int(r[0]);
+    if (s1 < 0) continue;
+    const int nc = __float_as_int(r[1]), N = __float_as_int(r[3]);
+    const unsigned int first = __float_as_uint(r[2]);
+    L1Meta* mt = &M.l1_meta[s1];
+    const unsigned long long k1 = M.l1_tab[s1].key;
+    if (nc < 3) { M.l1_tab[s1].key = k1 & ~SURFEL_BIT; continue; }
+    float cents[27 * 3];
+    for (int c = 0; c < nc * 3; ++c) cents[c] = r[4 + c];
     float mu[3], nrm[3], plan;
     fit_plane(cents, nc, mu, nrm, &plan);
     if (plan > M.planarity_thr) {  // not planar: the parent and all its children go (VoxelMap.cpp:244-253)
@@ -830,12 +905,13 @@ int map_reserve(b2lo_map* m, size_t need_l0, size_t need_upd) {
     while (ncap < need_upd) ncap *= 2;
     B2_CUDA(cudaStreamSynchronize(st));
     if ((rc = dmalloc(&m->u_pts, ncap)) || (rc = dmalloc(&m->u_pslot, ncap)) || (rc = dmalloc(&m->u_next, ncap)) || (rc = dmalloc(&m->u_isnew, ncap)) ||
-        (rc = dmalloc(&m->u_newrank, ncap)) || (rc = dmalloc(&m->u_part, ncap / INS_CHUNK + 2)))
+        (rc = dmalloc(&m->u_newrank, 2 * ncap)) || (rc = dmalloc(&m->u_part, ncap / INS_CHUNK + 2)))
       return rc;
     m->a_log2cap = ceil_log2(ncap * 2);
     if ((rc = dmalloc(&m->a_tab, (size_t)1 << m->a_log2cap)) || (rc = dmalloc(&m->a_list, ncap * 4 + 16)) || (rc = dmalloc(&m->a_slots, ncap + 16))) return rc;
     B2_CUDA(cudaMemsetAsync(m->a_tab, 0xFF, sizeof(FEntry) << m->a_log2cap, st));  // the affected set cleans itself afterwards (k_surfel)
     // purge scratch: up to 27 children per affected parent
+    if ((rc = dmalloc(&m->s_rec, ncap * (size_t)SURFEL_REC))) return rc;   // surfel refit records of the lock-step path (k_surfel_gather / k_surfel_fit)
     m->p_cap = ncap * 27;
     if ((rc = dmalloc(&m->p_seq, m->p_cap + 16)) || (rc = dmalloc(&m->p_aux, m->p_cap * 4 + 16))) return rc;
     m->upd_cap = ncap;
@@ -866,6 +942,7 @@ int map_update_dev(b2lo_map* m, float4* d_world, const int* d_n, size_t n_cap, c
     int tiles = (int)(((m->graph_mode ? (size_t)d.l0_cap : m->n0) + 1023) / 1024);
     int g = tiles > ctx->sm_count ? ctx->sm_count : tiles;
     int g4 = (tiles + 3) / 4; if (g4 > 2 * ctx->sm_count) g4 = 2 * ctx->sm_count;
+    g = batch_grid(ctx, g); g4 = batch_grid(ctx, g4);
     prof_end(ctx);
     prof_begin(ctx, PS_CULL);
     launch<k_cull_mark, 1024, 1>(ctx, dim3((unsigned)(g4)), dim3((unsigned)(1024)), 0, st, d, n0, sensor[0], sensor[1], sensor[2], radius_sq, m->c_flag, m->c_blkcnt, m->c_blkoff, us);
@@ -875,8 +952,8 @@ int map_update_dev(b2lo_map* m, float4* d_world, const int* d_n, size_t n_cap, c
     launch<k_cull_fix, 1024, 1>(ctx, dim3((unsigned)(1)), dim3((unsigned)(1024)), SIM_SMEM_BYTES, st, d, m->c_flag, us, m->c_l1work, m->c_removed, m->c_aux, n0);
     ctx->launches += 3;
   }
-  int gm = grid_for(n_cap, 256);
-  int gw = grid_for(n_cap * 32, 256);   // one warp per point
+  int gm = batch_grid(ctx, grid_for(n_cap, 256));
+  int gw = batch_grid(ctx, grid_for(n_cap * 32, 256));   // one warp per point
   int* plist = m->a_list; unsigned int* pfirst = reinterpret_cast<unsigned int*>(m->a_list + m->upd_cap);
   int* pord = m->a_list + 2 * m->upd_cap; int* poff = m->a_list + 3 * m->upd_cap;
   launch<k_ins_probe, 256, 1>(ctx, dim3((unsigned)(gm)), dim3((unsigned)(256)), 0, st, d, d_world, d_n, us, m->u_pslot, m->u_next, m->a_tab, m->a_log2cap, m->a_slots, local, T16_dev);
@@ -886,12 +963,12 @@ int map_update_dev(b2lo_map* m, float4* d_world, const int* d_n, size_t n_cap, c
     int gc = (int)((n_cap + INS_CHUNK - 1) / INS_CHUNK); if (gc > 4 * ctx->sm_count) gc = 4 * ctx->sm_count;
     k_ins_scan_part<<<gc, 1024, 0, st>>>(d_n, m->u_isnew, m->u_part);
     k_ins_scan_top<<<1, 1024, 0, st>>>(d, d_n, m->u_part, us);
-    k_ins_scan_apply<<<gc, 1024, 0, st>>>(d, d_n, m->u_isnew, m->u_pslot, m->u_newrank, m->u_part);
+    k_ins_scan_apply<<<gc, 1024, 0, st>>>(d, d_n, m->u_isnew, m->u_pslot, m->u_newrank, m->u_part, m->u_newrank + m->upd_cap);
     ctx->launches += 2;
   } else {
-    launch<k_ins_scan, 1024, 1>(ctx, dim3((unsigned)(1)), dim3((unsigned)(1024)), 0, st, d, d_n, m->u_isnew, m->u_pslot, m->u_newrank, us);
+    launch<k_ins_scan, 1024, 1>(ctx, dim3((unsigned)(1)), dim3((unsigned)(1024)), 0, st, d, d_n, m->u_isnew, m->u_pslot, m->u_newrank, us, m->u_newrank + m->upd_cap);
   }
-  launch<k_ins_place, 256, 1>(ctx, dim3((unsigned)(gw)), dim3((unsigned)(256)), 0, st, d, d_n, us, m->u_pslot, m->u_isnew, m->u_newrank, m->u_pts);
+  launch<k_ins_place, 256, 1>(ctx, dim3((unsigned)(gw)), dim3((unsigned)(256)), 0, st, d, d_n, us, m->u_pslot, m->u_isnew, m->u_newrank, m->u_pts, m->u_newrank + m->upd_cap);
   ctx->launches += 4;
   int purge = 0;
   if (rehash) {
@@ -903,7 +980,12 @@ int map_update_dev(b2lo_map* m, float4* d_world, const int* d_n, size_t n_cap, c
     ctx->launches += 2;
   } else {
     purge = d.compute_surfels;
-    launch<k_surfel, 256, 1>(ctx, dim3((unsigned)(gw)), dim3((unsigned)(256)), 0, st, d, m->a_tab, m->a_slots, us, plist, pfirst);
+    if (ctx->batch_S > 0 && m->s_rec) {   // lock-step batches: gather by warps, fit by threads (see k_surfel_gather)
+      launch<k_surfel_gather, 256, 1>(ctx, dim3((unsigned)(gw)), dim3(256u), 0, st, d, m->a_tab, m->a_slots, us, m->s_rec);
+      launch<k_surfel_fit, 128, 1>(ctx, dim3((unsigned)(batch_grid(ctx, grid_for(n_cap, 128)))), dim3(128u), 0, st, d, us, (const float*)m->s_rec, plist, pfirst);
+      ctx->launches += 1;
+    }
+    else launch<k_surfel, 256, 1>(ctx, dim3((unsigned)(gw)), dim3((unsigned)(256)), 0, st, d, m->a_tab, m->a_slots, us, plist, pfirst);
     ctx->launches += 1;
   }
   if (bulk) { k_rank_clear<<<gm, 256, 0, st>>>(d, d_n, m->u_pslot, m->u_isnew); ctx->launches++; }
@@ -957,7 +1039,7 @@ extern "C" int b2lo_map_destroy(b2lo_map* m) {
   MapDev& d = m->d;
   void* ptrs[] = {d.l0_cent, d.l0_key, d.l0_slot, d.l0_tab, d.l1_tab, d.l1_meta, d.ctr,
                   m->u_pts, m->u_pslot, m->u_next, m->u_isnew, m->u_newrank, m->a_tab, m->a_list, m->a_slots, m->c_flag, m->c_blkcnt,
-                  m->c_blkoff, m->c_removed, m->c_aux, m->c_l1work, m->p_seq, m->p_aux, m->u_state, m->u_part, m->r_tmp, m->r_n};
+                  m->c_blkoff, m->c_removed, m->c_aux, m->c_l1work, m->p_seq, m->p_aux, m->u_state, m->u_part, m->r_tmp, m->r_n, m->s_rec};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete m;
   return B2LO_OK;

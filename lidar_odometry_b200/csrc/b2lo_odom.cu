@@ -10,6 +10,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 #define B2LO_TL_FILE 3
 #include "b2lo_internal.h"
 #include "b2lo_launch.cuh"
@@ -238,6 +239,24 @@ static void sp_set_fmt(ScanParams* sp, const b2lo_record_fmt* f) {
   for (int a = 0; a < 3; ++a) sp->flt_off[a] = f ? (&f->off_x)[a] : 0u;
 }
 
+// the scan parameter block of one steady-state scan in the context's page-locked mirror: K1 source, motion-model guess (Estimator.cpp:154),
+// keyframe thresholds
+static void fill_scan_params(b2lo_odom* od, const float* flt_src, size_t flt_ns, size_t flt_stride, const b2lo_record_fmt* fmt) {
+  ScanParams* sp = od->ctx->h_sp;
+  Pose guess = pose_mul(od->prev_pose, od->velocity);  // Estimator.cpp:154
+  Pose init = pose_reproject(guess);
+  sp->flt_src = flt_src; sp->flt_ns = (int)flt_ns;
+  sp->flt_stride = flt_stride; sp->flt_inv = 1.0f / od->cfg.voxel_size;
+  sp_set_fmt(sp, fmt);
+  sp->flt_mode = 0;
+  pose_to_T16(init, sp->T_init);
+  sp->force_scale = 0.0;
+  pose_to_T16(guess, sp->decide.guess);
+  pose_to_T16(od->last_kf_pose, sp->decide.last_kf);
+  sp->decide.ran_icp = 1; sp->decide.n_keyframes = od->n_keyframes;
+  sp->decide.kf_dist = od->cfg.keyframe_distance_threshold; sp->decide.kf_rot = od->cfg.keyframe_rotation_threshold;
+}
+
 // eff: record format of THIS call's source (nullptr: float-stride cloud, e.g. the staged copy of a pageable image); an announced next
 // scan is always read in place and therefore in the odometry's own format
 // steady_begin enqueues the whole scan (graph replay or plain launches) and returns without waiting; steady_finish waits for it and
@@ -270,21 +289,10 @@ static int steady_begin(b2lo_odom* od, const float* src_dev, size_t ns, size_t s
     if ((rc = filter_run(ctx, src_dev, ns, sample_stride_floats, od->cfg.voxel_size, 0, st, eff))) return rc;
   }
   // the parameter block of this scan
-  Pose guess = pose_mul(od->prev_pose, od->velocity);  // Estimator.cpp:154
-  Pose init = pose_reproject(guess);
   if ((rc = sp_begin_write(ctx))) return rc;
-  ScanParams* sp = ctx->h_sp;
   const size_t flt_ns = mode == K1_NEXT ? nx_ns : ns;
-  sp->flt_src = mode == K1_NEXT ? nx_src : src_dev; sp->flt_ns = (int)flt_ns;
-  sp->flt_stride = mode == K1_NEXT ? nx_stride : sample_stride_floats; sp->flt_inv = 1.0f / od->cfg.voxel_size;
-  sp_set_fmt(sp, mode == K1_NEXT ? (od->has_fmt ? &od->fmt : nullptr) : eff);
-  sp->flt_mode = 0;
-  pose_to_T16(init, sp->T_init);
-  sp->force_scale = 0.0;
-  pose_to_T16(guess, sp->decide.guess);
-  pose_to_T16(od->last_kf_pose, sp->decide.last_kf);
-  sp->decide.ran_icp = 1; sp->decide.n_keyframes = od->n_keyframes;
-  sp->decide.kf_dist = od->cfg.keyframe_distance_threshold; sp->decide.kf_rot = od->cfg.keyframe_rotation_threshold;
+  fill_scan_params(od, mode == K1_NEXT ? nx_src : src_dev, flt_ns, mode == K1_NEXT ? nx_stride : sample_stride_floats,
+                   mode == K1_NEXT ? (od->has_fmt ? &od->fmt : nullptr) : eff);
   int l2 = 12;
   while ((1ull << l2) < 2 * flt_ns) ++l2;
   if (mode == K1_NONE) l2 = 0;
@@ -557,6 +565,207 @@ extern "C" int b2lo_odom_process_batch_dev(b2lo_odom* const* ods, const float* c
     if (++acc_calls % 50 == 0)
       std::fprintf(stderr, "[b2lo batch] %d sequences: enqueue %.1f us/call, finish %.1f us/call of which stream waits %.1f us\n", count, acc_begin / acc_calls,
                    acc_finish / acc_calls, acc_wait / acc_calls), acc_begin = acc_finish = acc_wait = 0.0, acc_calls = 0;
+  }
+  return first_err ? first_err : soft;
+}
+
+// ---- lock-step batches (b2lo_launch.cuh): S independent sequences advance by one scan per replay of ONE graph ------------------------
+// Every kernel of the scan is started once per STEP with blockIdx.y = sequence; its per-sequence arguments (map descriptor, buffers, state
+// blocks) sit in a device array recorded from the unchanged per-sequence host code.  Results per sequence are those of the sequence
+// processed alone, bit for bit (same kernels, same grids in x, same arguments).
+namespace b2 {
+struct k_ls_params {   // the S scan parameter blocks, from the contexts' page-locked mirrors to their device blocks (zero-copy reads)
+  static __device__ __forceinline__ void run(const int* const* h_sp, int* const* d_sp, int words) {
+    const int* src = h_sp[blockIdx.x];
+    int* dst = d_sp[blockIdx.x];
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+  }
+};
+}  // namespace b2
+struct b2lo_lockstep {
+  std::vector<b2lo_odom*> ods;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  std::vector<unsigned long long> sig;
+  std::vector<void*> d_packs;            // one device array of S argument packs per step of the recorded sequence
+  const int** d_hsp = nullptr; int** d_dsp = nullptr;
+  long long kernels_per_step = 0, replays = 0, builds = 0, fallbacks = 0;
+};
+extern "C" int b2lo_lockstep_create(b2lo_odom* const* ods, int count, b2lo_lockstep** out) {
+  if (!ods || !out || count < 1) return B2LO_E_ARG;
+  *out = nullptr;
+  for (int a = 0; a < count; ++a) {
+    if (!ods[a]) return B2LO_E_ARG;
+    if (ods[a]->ctx->device != ods[0]->ctx->device) { set_error("lock-step: all sequences must live on one device"); return B2LO_E_ARG; }
+    if (!ods[a]->cfg.icp.use_surfel_correspondence) { set_error("lock-step: surfel correspondence mode only"); return B2LO_E_ARG; }
+    for (int b = 0; b < a; ++b) if (ods[a] == ods[b] || ods[a]->ctx == ods[b]->ctx) { set_error("lock-step: sequences must not share a handle or a context"); return B2LO_E_ARG; }
+  }
+  cudaSetDevice(ods[0]->ctx->device);
+  b2lo_lockstep* ls = new b2lo_lockstep();
+  ls->ods.assign(ods, ods + count);
+  if (cudaStreamCreateWithFlags(&ls->st, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&ls->ev0) != cudaSuccess || cudaEventCreate(&ls->ev1) != cudaSuccess ||
+      cudaMalloc((void**)&ls->d_hsp, sizeof(void*) * count) != cudaSuccess || cudaMalloc((void**)&ls->d_dsp, sizeof(void*) * count) != cudaSuccess) {
+    set_error("lock-step: allocation failed");
+    delete ls;
+    return B2LO_E_NOMEM;
+  }
+  std::vector<const int*> h((size_t)count); std::vector<int*> d((size_t)count);
+  for (int a = 0; a < count; ++a) { h[(size_t)a] = reinterpret_cast<const int*>(ods[a]->ctx->h_sp); d[(size_t)a] = reinterpret_cast<int*>(ods[a]->ctx->d_sp); }
+  cudaMemcpy(ls->d_hsp, h.data(), sizeof(void*) * count, cudaMemcpyHostToDevice);
+  cudaMemcpy(ls->d_dsp, d.data(), sizeof(void*) * count, cudaMemcpyHostToDevice);
+  *out = ls;
+  return B2LO_OK;
+}
+static void lockstep_drop_graph(b2lo_lockstep* ls) {
+  if (ls->exec) { cudaGraphExecDestroy(ls->exec); ls->exec = nullptr; }
+  for (void* p : ls->d_packs) if (p) cudaFree(p);
+  ls->d_packs.clear();
+}
+extern "C" int b2lo_lockstep_destroy(b2lo_lockstep* ls) {
+  if (!ls) return B2LO_E_ARG;
+  cudaSetDevice(ls->ods[0]->ctx->device);
+  if (ls->st) cudaStreamSynchronize(ls->st);
+  lockstep_drop_graph(ls);
+  if (ls->d_hsp) cudaFree(ls->d_hsp);
+  if (ls->d_dsp) cudaFree(ls->d_dsp);
+  if (ls->ev0) cudaEventDestroy(ls->ev0);
+  if (ls->ev1) cudaEventDestroy(ls->ev1);
+  if (ls->st) cudaStreamDestroy(ls->st);
+  delete ls;
+  return B2LO_OK;
+}
+extern "C" int b2lo_lockstep_stats(b2lo_lockstep* ls, long long* kernels_per_step, long long* replays, long long* builds, long long* fallbacks) {
+  if (!ls) return B2LO_E_ARG;
+  if (kernels_per_step) *kernels_per_step = ls->kernels_per_step;
+  if (replays) *replays = ls->replays;
+  if (builds) *builds = ls->builds;
+  if (fallbacks) *fallbacks = ls->fallbacks;
+  return B2LO_OK;
+}
+// record the launch sequence of one scan for every sequence, zip the lists and capture one batched launch per step
+static int lockstep_build(b2lo_lockstep* ls, const std::vector<size_t>& flt_ns, const std::vector<size_t>& caps) {
+  const int S = (int)ls->ods.size();
+  lockstep_drop_graph(ls);
+  std::vector<Recorder> recs((size_t)S);
+  int rc = B2LO_OK;
+  for (int a = 0; a < S && !rc; ++a) {
+    b2lo_odom* od = ls->ods[a];
+    od->ctx->rec = &recs[(size_t)a];
+    od->ctx->batch_S = S;
+    rc = enqueue_scan(od, flt_ns[(size_t)a], caps[(size_t)a], /*in_graph=*/false, K1_SERIAL, 0, false);
+    od->ctx->rec = nullptr;
+    od->ctx->batch_S = 0;
+  }
+  if (rc) return rc;
+  const size_t steps = recs[0].recs.size();
+  for (int a = 1; a < S; ++a) {
+    if (recs[(size_t)a].recs.size() != steps) { set_error("lock-step: sequences record different launch sequences (%zu vs %zu kernels)", recs[(size_t)a].recs.size(), steps); return B2LO_E_ARG; }
+    for (size_t k = 0; k < steps; ++k) {
+      const LaunchRec& x = recs[0].recs[k]; const LaunchRec& y = recs[(size_t)a].recs[k];
+      if (x.many != y.many || x.block.x != y.block.x || x.smem != y.smem || x.args.size() != y.args.size()) {
+        set_error("lock-step: step %zu differs between sequences (kernel / block / shared memory)", k);
+        return B2LO_E_ARG;
+      }
+    }
+  }
+  ls->d_packs.assign(steps, nullptr);
+  std::vector<unsigned char> host;
+  for (size_t k = 0; k < steps; ++k) {
+    const size_t bytes = recs[0].recs[k].args.size();
+    host.resize(bytes * (size_t)S);
+    for (int a = 0; a < S; ++a) std::memcpy(host.data() + bytes * (size_t)a, recs[(size_t)a].recs[k].args.data(), bytes);
+    B2_CUDA(cudaMalloc(&ls->d_packs[k], host.size()));
+    B2_CUDA(cudaMemcpy(ls->d_packs[k], host.data(), host.size(), cudaMemcpyHostToDevice));
+  }
+  for (size_t k = 0; k < steps; ++k) recs[0].recs[k].prep(recs[0].recs[k].smem);
+  cudaGraph_t g = nullptr;
+  B2_CUDA(cudaStreamBeginCapture(ls->st, cudaStreamCaptureModeThreadLocal));
+  launch<k_ls_params, 64, 1>(ls->ods[0]->ctx, dim3((unsigned)S), dim3(64), 0, ls->st, (const int* const*)ls->d_hsp, (int* const*)ls->d_dsp, (int)(sizeof(ScanParams) / sizeof(int)));
+  for (size_t k = 0; k < steps; ++k) {
+    dim3 grid = recs[0].recs[k].grid;
+    for (int a = 1; a < S; ++a) if (recs[(size_t)a].recs[k].grid.x > grid.x) grid.x = recs[(size_t)a].recs[k].grid.x;   // grid-stride kernels: the widest sequence sets x
+    recs[0].recs[k].many(ls->d_packs[k], S, grid, recs[0].recs[k].block, recs[0].recs[k].smem, ls->st);
+  }
+  cudaError_t ce = cudaStreamEndCapture(ls->st, &g);
+  if (ce != cudaSuccess || !g) { if (g) cudaGraphDestroy(g); set_error("lock-step: capture failed: %s", cudaGetErrorString(ce)); cudaGetLastError(); return B2LO_E_CUDA; }
+  ce = cudaGraphInstantiate(&ls->exec, g, 0);
+  cudaGraphDestroy(g);
+  if (ce != cudaSuccess) { ls->exec = nullptr; set_error("lock-step: graph instantiation failed: %s", cudaGetErrorString(ce)); return B2LO_E_CUDA; }
+  ls->kernels_per_step = (long long)steps + 1;
+  ls->builds++;
+  return B2LO_OK;
+}
+// One scan on every sequence of the batch, all scans resident in HBM.  device_ms (nullable): CUDA-event time of the whole step.
+extern "C" int b2lo_lockstep_process_dev(b2lo_lockstep* ls, const float* const* xyz_dev, const size_t* n, size_t stride_floats, b2lo_odom_result* res,
+                                         float* device_ms) {
+  if (!ls || !xyz_dev || !n || !res) return B2LO_E_ARG;
+  if (stride_floats < 3) return B2LO_E_ARG;
+  const int S = (int)ls->ods.size();
+  if (device_ms) *device_ms = 0.0f;
+  cudaSetDevice(ls->ods[0]->ctx->device);
+  bool steady = true;
+  for (int a = 0; a < S; ++a) {
+    b2lo_odom* od = ls->ods[a];
+    if (!xyz_dev[a] || n[a] == 0 || !od->initialized || od->n_keyframes < 1 || od->map->n0 == 0 || od->has_fmt || (od->ctx->prof && od->ctx->prof->on)) steady = false;
+  }
+  if (!steady) {   // first frames (map build), empty scans, record streams, profiling: sequence by sequence through the ordinary path
+    ls->fallbacks++;
+    int first_err = B2LO_OK, soft = B2LO_OK;
+    for (int a = 0; a < S; ++a) {
+      std::memset(&res[a], 0, sizeof res[a]);
+      if (!xyz_dev[a] || n[a] == 0) { soft = B2LO_S_EMPTY; continue; }
+      int rc = b2lo_odom_process_dev(ls->ods[a], xyz_dev[a], n[a], stride_floats, &res[a]);
+      if (rc < 0 && !first_err) first_err = rc; else if (rc > 0) soft = rc;
+    }
+    return first_err ? first_err : soft;
+  }
+  struct Unlock { b2lo_lockstep* l; int k = 0; ~Unlock() { for (int a = k - 1; a >= 0; --a) { l->ods[a]->ctx->mu.unlock(); l->ods[a]->map->mu.unlock(); } } } guard{ls};
+  std::vector<size_t> flt_ns((size_t)S), caps((size_t)S);
+  std::vector<unsigned long long> sig;
+  int rc = B2LO_OK;
+  for (int a = 0; a < S; ++a) {
+    b2lo_odom* od = ls->ods[a];
+    b2lo_ctx* ctx = od->ctx;
+    od->map->mu.lock(); ctx->mu.lock(); guard.k = a + 1;
+    std::memset(&res[a], 0, sizeof res[a]);
+    od->la_valid = od->pre_valid = false;   // no look-ahead inside a lock-step batch: the S sequences fill the GPU already
+    const size_t St = (size_t)(od->cfg.point_stride < 1 ? 1 : od->cfg.point_stride);
+    const size_t ns = (n[a] + St - 1) / St;
+    if ((rc = ctx_reserve_points(ctx, ns))) return rc;
+    const size_t cap = ctx->pts_cap;
+    if ((rc = map_reserve(od->map, od->map->n0 + cap, cap))) return rc;
+    if ((rc = icp_prepare(ctx, &od->cfg.icp))) return rc;
+    if ((rc = sp_begin_write(ctx))) return rc;
+    fill_scan_params(od, xyz_dev[a], ns, stride_floats * St, nullptr);
+    flt_ns[(size_t)a] = ns; caps[(size_t)a] = cap;
+    int l2 = 12;
+    while ((1ull << l2) < 2 * ns) ++l2;
+    sig.push_back(ctx->alloc_epoch); sig.push_back(od->map->alloc_epoch); sig.push_back((unsigned long long)l2); sig.push_back((unsigned long long)cap);
+  }
+  if (!ls->exec || sig != ls->sig) {
+    for (int a = 0; a < S; ++a) B2_CUDA(cudaStreamSynchronize(ls->ods[a]->ctx->stream));   // whatever the sequences did on their own streams is done
+    B2_CUDA(cudaStreamSynchronize(ls->st));
+    if ((rc = lockstep_build(ls, flt_ns, caps))) return rc;
+    ls->sig = sig;
+  }
+  B2_CUDA(cudaEventRecord(ls->ev0, ls->st));
+  B2_CUDA(cudaGraphLaunch(ls->exec, ls->st));
+  B2_CUDA(cudaEventRecord(ls->ev1, ls->st));
+  B2_CUDA(cudaStreamSynchronize(ls->st));
+  ls->replays++;
+  float ms = 0.0f;
+  cudaEventElapsedTime(&ms, ls->ev0, ls->ev1);
+  if (device_ms) *device_ms = ms;
+  int first_err = B2LO_OK, soft = B2LO_OK;
+  for (int a = 0; a < S; ++a) {
+    b2lo_odom* od = ls->ods[a];
+    od->ctx->launches += ls->kernels_per_step;
+    od->ctx->feat_set = 0;
+    od->pend.active = true; od->pend.mode = K1_SERIAL; od->pend.set = 0; od->pend.nx_src = nullptr; od->pend.nx_ns = 0; od->pend.nx_stride = 0; od->pend.t1 = now_us();
+    int r = steady_finish(od, &res[a]);
+    if (r >= 0) { pose_to_T16(od->pose, res[a].pose); res[a].l0 = od->map->n0; res[a].l1 = od->map->n1; res[a].device_ms = ms; }
+    if (r < 0 && !first_err) first_err = r; else if (r > 0) soft = r;
   }
   return first_err ? first_err : soft;
 }

@@ -125,6 +125,49 @@ def test_batch_call_matches_lone_sequences(b2, small_kitti):
     assert sum(o.graph_stats()["replays"] for o in bat.odos) > 0
 
 
+def test_lockstep_batch_matches_lone_sequences(b2, small_kitti):
+    """b2lo_lockstep_*: S sequences advanced by ONE graph replay per scan, every kernel started once per step with blockIdx.y = sequence.
+    Each sequence must be bit-identical to the same sequence processed alone; the sequences run the scans in different rotations (their
+    maps, correspondence counts and Gauss-Newton iteration counts differ inside one step), one of them holds a degenerate scan (falls back
+    to the per-sequence path for that step), and the sequences remain usable on their own afterwards."""
+    import torch
+    scans, _ = small_kitti
+    scans = list(scans) + list(scans[::-1])
+    dev = [torch.from_numpy(np.ascontiguousarray(s)).cuda() for s in scans]
+    bad = torch.full((2000, 4), float("nan"), dtype=torch.float32, device="cuda")
+    S, n = 6, len(scans)
+    order = [[(k + j) % n for k in range(n)] for j in range(S)]
+
+    def scan_of(j, k):   # sequence 2 sees an all-NaN scan at step 4
+        if j == 2 and k == 4:
+            return bad.data_ptr(), bad.shape[0]
+        i = order[j][k]
+        return dev[i].data_ptr(), scans[i].shape[0]
+
+    want = []
+    for j in range(S):
+        o = b2.Odometry(b2.Context(0))
+        want.append([o.process_dev(*scan_of(j, k), 4) for k in range(n)])
+    odos = [b2.Odometry(b2.Context(0)) for _ in range(S)]
+    ls = b2.LockstepBatch(odos)
+    for k in range(n):
+        res, ms = ls.process_dev([scan_of(j, k) for j in range(S)], 4)
+        for j, r in enumerate(res):
+            w = want[j][k]
+            assert np.array_equal(bits(r["pose"]), bits(w["pose"])), (j, k)
+            assert (r["keyframe"], r["n_features"], r["n_corr"], r["n_iters"], r["l0"], r["l1"]) == \
+                   (w["keyframe"], w["n_features"], w["n_corr"], w["n_iters"], w["l0"], w["l1"]), (j, k)
+    st = ls.stats()
+    assert st["replays"] >= n - 2 and st["fallbacks"] >= 1 and st["kernels_per_step"] >= 20, st   # the first frames build the maps sequence by sequence
+    # the sequences stay ordinary odometry handles: one more scan each, alone, still equal to a lone sequence
+    lone = b2.Odometry(b2.Context(0))
+    for k in range(n):
+        lone.process_dev(*scan_of(0, k), 4)
+    a = lone.process_dev(dev[0].data_ptr(), scans[0].shape[0], 4)
+    b = odos[0].process_dev(dev[0].data_ptr(), scans[0].shape[0], 4)
+    assert np.array_equal(bits(a["pose"]), bits(b["pose"])) and a["n_corr"] == b["n_corr"]
+
+
 def test_degenerate_scans_inside_a_sequence(b2, orc, small_kitti):
     """Scans that yield no features (all points non-finite) or too few correspondences (a tiny far-away cloud) in the middle of a
     sequence: the driver (fused first correspondence pass, gated map update, graph replay) follows the oracle pipeline and recovers."""
