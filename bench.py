@@ -493,6 +493,38 @@ def lockstep_groups_leg(api, local, dev_args, G, S, K, W):
     return out
 
 
+def dropin_leg(scans, K, W):
+    """The class-by-class drop-in through the C++ shim (lidar_odometry_b200/shim/b2lo_dropin.h) in Estimator::process_frame order
+    (Estimator.cpp:116-233, 449-470): FastVoxelFilter::filter -> optimize -> host transform -> UpdateVoxelMap -> GetPointCloud, pageable
+    std::vector clouds, every hand-over through the host.  A C++ program (shim/test/dropin_bench.cpp) compiled here with g++; wall clock
+    per scan, stage split like the reference's TimingStats.  This is what an UNMODIFIED Estimator.cpp pays; `e2e` is the widened call."""
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.abspath(__file__))
+    shim = os.path.join(root, "lidar_odometry_b200", "shim")
+    exe = os.path.join(shim, "test", "dropin_bench")
+    cmd = ["g++", "-std=c++17", "-O2", "-I" + os.path.join(root, "include"), "-I" + shim, os.path.join(shim, "test", "dropin_bench.cpp"), "-o", exe,
+           "-L" + os.path.join(root, "lidar_odometry_b200"), "-lb2lo", "-Wl,-rpath," + os.path.join(root, "lidar_odometry_b200")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        return {"unavailable": "g++ failed: " + r.stderr[-300:]}
+    with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
+        for s in scans[:W + K]:
+            a = np.ascontiguousarray(s[:, :4], np.float32)
+            f.write(np.uint32(a.shape[0]).tobytes()); f.write(a.tobytes())
+        path = f.name
+    try:
+        r = subprocess.run([exe, path, str(W)], capture_output=True, text=True, timeout=600)
+    finally:
+        os.unlink(path)
+    if r.returncode != 0:
+        return {"unavailable": "dropin_bench failed: " + (r.stderr or r.stdout)[-300:]}
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    out.update({"unit": UNIT, "value": out["scans_per_s"], "driver": "shim/test/dropin_bench.cpp over b2lo_dropin.h (the reference's three classes), pageable host clouds",
+                "timing": "host wall clock per scan inside the C++ program; no L2 flush between scans (a separate process)"})
+    return out
+
+
 def export_leg(ctx, api, scans, poses, K):
     """SURVEY 8f-4: the final-map downsample of Estimator::save_map_to_ply (util::VoxelGrid, leaf 0.4 m) over the accumulated world
     cloud of the benchmark sequence, through the host-buffer call (H2D + D2H inside), next to the CPU oracle on the same cloud."""
@@ -732,6 +764,8 @@ def main():
                "sample": f"the same {K} scans after {W} warm-up scans, single thread (the reference hot path is single-threaded)",
                "ms_per_scan": 1e3 * dt / K, "stage_ms_per_scan": {"preprocess": st[0] / K, "icp": st[1] / K, "map_update": st[2] / K}}
 
+    dropin = dropin_leg(scans, K, W) if world == 1 else None
+
     conc = None
     if world == 1 and args.concurrent:
         conc = [concurrent_leg(api, local, dev_args, S, K, W) for S in args.concurrent[:1]]
@@ -762,7 +796,7 @@ def main():
                                   "timing": "wall clock around b2lo_odom_process on page-locked host scans, copies inside"}},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_scan": 1e3 * float(te.item()) / K, "h2d_bytes_per_step": (h1 - h0) / K,
                     "d2h_bytes_per_step": (d1 - d0) / K},
-            "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "stage_ms_per_scan": {k: v["ms_total"] / K for k, v in stage.items()},
+            "dropin_e2e": dropin, "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "stage_ms_per_scan": {k: v["ms_total"] / K for k, v in stage.items()},
             "dominant_kernel_group": dominant, "cpu_baseline": cpu,
             "concurrent_sequences_one_gpu": conc, "lockstep_sequences_one_gpu": lockstep, "batched_sequences_all_gpus": batched_all, "point_sharded": sharded, "final_map_export": export, "large_map_stress": stress, "kdtree_mid360": mid360}
     print(json.dumps(line))

@@ -263,7 +263,7 @@ class IterativeClosestPointOptimizer {  // IterativeClosestPointOptimizer.h:158-
  private:
   void fill_cfg(b2lo_icp_cfg& c) const {
     b2lo_default_icp_cfg(&c);
-    c.max_iterations = m_config.max_iterations > B2LO_MAX_ITERS ? B2LO_MAX_ITERS : m_config.max_iterations;
+    c.max_iterations = m_config.max_iterations;   // any count >= 1 (ICPConfig's default is 50, ICP.h:57); the engine stops issuing work once converged
     c.translation_tolerance = m_config.translation_tolerance;
     c.rotation_tolerance = m_config.rotation_tolerance;
     c.max_correspondence_distance = m_config.max_correspondence_distance;

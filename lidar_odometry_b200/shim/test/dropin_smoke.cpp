@@ -42,6 +42,13 @@ int main() {
   Eigen::Matrix4f M = out.Matrix();
   std::printf("optimize: ok=%d iters=%zu corr=%zu t=(%.4f %.4f %.4f)\n", (int)ok, icp.get_last_stats().num_iterations,
               icp.get_last_stats().num_correspondences, M(0, 3), M(1, 3), M(2, 3));
+  // a default-constructed ICPConfig (max_iterations = 50, tolerances 1e-6: ICP.h:55-76) must register as well, not throw
+  optimization::IterativeClosestPointOptimizer icp_default(optimization::ICPConfig(), std::make_shared<optimization::AdaptiveMEstimator>());
+  SE3f out_d;
+  bool ok_d = icp_default.optimize(&vmap, std::make_shared<database::LidarFrame>(ds1), init, out_d);
+  Eigen::Matrix4f Md = out_d.Matrix();
+  std::printf("optimize (default ICPConfig): ok=%d iters=%zu t=(%.4f %.4f %.4f)\n", (int)ok_d, icp_default.get_last_stats().num_iterations, Md(0, 3), Md(1, 3), Md(2, 3));
+  ok = ok && ok_d && std::fabs(Md(0, 3) - 0.3f) < 0.02f && icp_default.get_last_stats().num_iterations >= 1;
   auto l0 = vmap.GetPointCloud();
   auto surfels = vmap.GetL1Surfels();
   Eigen::Vector3f n, c;
