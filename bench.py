@@ -76,6 +76,17 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(self.rows)}
 
 
+def k2_traffic():
+    """DRAM traffic of K2 per launch as ncu measured it for the committed kernel (profiles/k2_traffic.json, written from the ncu summaries
+    of the round); bench.py cannot count DRAM bytes itself, so a missing entry reads as null instead of a stale constant."""
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "k2_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
+
+
 def make_scans(n, seed, device):
     from lidar_odometry_b200 import synth
     scans, poses = synth.kitti_sequence(n_scans=n, seed=seed, device=device)
@@ -328,7 +339,11 @@ def stress_leg(ctx, api, capi, target_voxels, peak, peak_kind):
     probes["random"].update({"random_sector_gather_ceiling_us": 26.6, "frac_of_random_gather_ceiling": 26.6 / max(probes["random"]["avg_launch_us"], 1e-9),
                              "ceiling_source": "tools/gather_probe.cu on the same GPU model, profiles/r01_gather_probe.txt"})
     probes["coherent"].update({"coherent_gather_ceiling_us": 10.2, "ceiling_source": "tools/gather_probe.cu, profiles/r01_gather_probe.txt (bare gathers only; K2 also streams 28 B/query)"})
-    probes["random"].update({"traffic_bytes_per_launch": 115305984, "traffic_source": "ncu, profiles/r01_ncu_k2_stress_final.csv: 2.3x the algorithmic bytes (64 B DRAM access per random 32 B sector + 12 B/query of results); 115.3 MB in 33.2 us = 3.5 TB/s = 53 % of the measured HBM peak in traffic terms: bound by random-sector DRAM access"})
+    tr = k2_traffic()
+    for kind, key in (("random", "k2_stress_random"), ("coherent", "k2_stress_coherent")):
+        t = tr.get(key)
+        probes[kind].update({"traffic_bytes_per_launch": t["bytes_per_launch"] if t else None, "traffic_source": (t["source"] + " (ncu, cold caches)") if t else None,
+                             "traffic_over_algorithmic": (t["bytes_per_launch"] / (ALGO_BYTES_PER_QUERY * nq)) if t else None})
     # bulk rebuild (ApplyTransformAndRehash + RecomputeAllSurfels, VoxelMap.cpp:264-366; runs after pose-graph corrections): transform every
     # L0 centroid, re-key, merge collisions, rebuild L1 and refit every surfel.  Algorithmic bytes per L0 voxel: 16 B read + 16 B written
     # + one 32 B slot written + 16 B gathered by its parent's refit = 80 B.
@@ -493,7 +508,7 @@ def lockstep_groups_leg(api, local, dev_args, G, S, K, W):
     return out
 
 
-def dropin_leg(scans, K, W):
+def dropin_leg(scans, K, W, show_stderr=False):
     """The class-by-class drop-in through the C++ shim (lidar_odometry_b200/shim/b2lo_dropin.h) in Estimator::process_frame order
     (Estimator.cpp:116-233, 449-470): FastVoxelFilter::filter -> optimize -> host transform -> UpdateVoxelMap -> GetPointCloud, pageable
     std::vector clouds, every hand-over through the host.  A C++ program (shim/test/dropin_bench.cpp) compiled here with g++; wall clock
@@ -514,7 +529,7 @@ def dropin_leg(scans, K, W):
             f.write(np.uint32(a.shape[0]).tobytes()); f.write(a.tobytes())
         path = f.name
     try:
-        r = subprocess.run([exe, path, str(W)], capture_output=True, text=True, timeout=600)
+        r = subprocess.run([exe, path, str(W)], stdout=subprocess.PIPE, stderr=None if show_stderr else subprocess.PIPE, text=True, timeout=600)
     finally:
         os.unlink(path)
     if r.returncode != 0:
@@ -741,7 +756,8 @@ def main():
     k2_avg_s = 1e-3 * k2["ms_total"] / max(k2["launches"], 1)
     achieved = k2_bytes_per_launch / max(k2_avg_s, 1e-12) / 1e9
     roof = {"bound": "hbm", "kernel": "k_icp_corr (K2 surfel correspondence)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "peak_kind": f"of {peak_kind}", "traffic": 416256, "traffic_source": "dram__bytes_read+write of k_icp_corr at this size, ncu --set full (profiles/r01_ncu_full_final.csv, cold cache)",
+            "peak_kind": f"of {peak_kind}", "traffic": (k2_traffic().get("k2_kitti_scan") or {}).get("bytes_per_launch"),
+            "traffic_source": (k2_traffic().get("k2_kitti_scan") or {}).get("source"),
             "algorithmic_bytes_per_launch": k2_bytes_per_launch,
             "avg_launch_us": 1e6 * k2_avg_s, "launches": k2["launches"],
             "note": "KITTI-shaped scans give ~4k queries per launch (~190 KB): the launch is latency-bound, not bandwidth-bound; see DESIGN.md"}
@@ -773,7 +789,7 @@ def main():
     lockstep = None
     if world == 1 and args.lockstep:
         lockstep = [lockstep_leg(api, local, dev_args, S, K, W, peak, peak_kind) for S in args.lockstep]
-        lockstep += [lockstep_groups_leg(api, local, dev_args, G, S, K, W) for G, S in ((3, 96), (4, 64))]
+        lockstep += [lockstep_groups_leg(api, local, dev_args, G, S, K, W) for G, S in ((3, 96), (4, 96))]
 
     stress = mid360 = export = None
     if world == 1 and not args.no_stress:

@@ -19,7 +19,9 @@
 //             planarity gate; non-planar parents are purged with all their L0 children.  The purge is an
 //             arbitrary-order swap-erase on the dense L0 vector; one thread replays it on indices only
 //             (shared memory), then the moves are applied in parallel.
+#include <chrono>
 #include <climits>
+#include <cstdio>
 #include <cstdlib>
 #define B2LO_TL_FILE 4
 #include "b2lo_internal.h"
@@ -1071,13 +1073,27 @@ extern "C" int b2lo_map_update(b2lo_map* m, const float* world_xyz, size_t n, si
   std::lock_guard<std::recursive_mutex> lkc(m->ctx->mu);   // the context's staging buffers / counters / stream (same order as b2lo_icp_optimize)
   b2lo_ctx* ctx = m->ctx;
   cudaSetDevice(ctx->device);
+  static const bool trace = getenv("B2LO_TRACE_UPDATE") != nullptr;   // debug aid: where the stand-alone call spends its wall time
+  auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = trace ? now() : 0.0;
   int rc = ctx_reserve_points(ctx, n);
   if (rc) return rc;
   rc = ctx_stage_h2d(ctx, world_xyz, n, stride_floats, 1, ctx->d_world, ctx->d_nquery);
   if (rc) return rc;
+  const double t1 = trace ? now() : 0.0;
+  const unsigned long long ep0 = m->alloc_epoch;
+  rc = map_reserve(m, m->n0 + n, n);
+  if (rc) return rc;
+  const double t2 = trace ? now() : 0.0;
   float sf[3] = {(float)sensor[0], (float)sensor[1], (float)sensor[2]};  // sensor_position.cast<float>()  (VoxelMap.cpp:143)
   float r2 = (float)(max_distance * max_distance);                        // (:144)
-  return map_update_dev(m, ctx->d_world, ctx->d_nquery, n, sf, r2);
+  rc = map_update_dev(m, ctx->d_world, ctx->d_nquery, n, sf, r2);
+  if (trace) {
+    const double t3 = now();
+    std::fprintf(stderr, "[b2lo map_update] n %zu n0 %zu tomb0 %zu: stage %.1f us, reserve %.1f us (%s), update %.1f us\n", n, m->n0, m->tomb0, t1 - t0, t2 - t1,
+                 m->alloc_epoch != ep0 ? "REBUILT" : "-", t3 - t2);
+  }
+  return rc;
 }
 
 extern "C" int b2lo_map_counts(b2lo_map* m, size_t* l0, size_t* l1, size_t* surfels) {

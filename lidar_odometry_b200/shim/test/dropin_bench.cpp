@@ -54,7 +54,7 @@ int main(int argc, char** argv) {
   std::memcpy(pose, I, sizeof I); std::memcpy(prev, I, sizeof I); std::memcpy(vel, I, sizeof I); std::memcpy(last_kf, I, sizeof I);
   bool initialized = false;
   int keyframes = 0;
-  double t_total = 0, t_pre = 0, t_icp = 0, t_map = 0, t_export = 0;
+  double t_total = 0, t_pre = 0, t_icp = 0, t_map = 0, t_export = 0, t_xf = 0;
   size_t exported = 0, feats = 0;
   int timed = 0;
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -93,6 +93,8 @@ int main(int argc, char** argv) {
         world->push_back(((pose[0] * p.x + pose[1] * p.y) + pose[2] * p.z) + pose[3], ((pose[4] * p.x + pose[5] * p.y) + pose[6] * p.z) + pose[7],
                          ((pose[8] * p.x + pose[9] * p.y) + pose[10] * p.z) + pose[11]);
       }
+      const double t2a = now();
+      if (count) t_xf += t2a - t2;
       vmap.UpdateVoxelMap(world, Eigen::Vector3d(pose[3], pose[7], pose[11]), 1.2 * max_range, true);   // :455-457
       t3 = now();
       local_map = vmap.GetPointCloud();                                      // :469-470: every L0 centroid to the host
@@ -104,9 +106,9 @@ int main(int argc, char** argv) {
     std::memcpy(prev, pose, sizeof pose);
     if (count) { t_total += t4 - t0; t_pre += t1 - t0; t_icp += t2 - t1; t_map += t3 - t2; t_export += t4 - t3; feats += ds->size(); ++timed; }
   }
-  std::printf("{\"scans\": %d, \"ms_per_scan\": %.5f, \"scans_per_s\": %.2f, \"stage_ms_per_scan\": {\"filter\": %.5f, \"optimize\": %.5f, \"update_voxel_map\": %.5f, "
+  std::printf("{\"scans\": %d, \"ms_per_scan\": %.5f, \"scans_per_s\": %.2f, \"stage_ms_per_scan\": {\"filter\": %.5f, \"optimize\": %.5f, \"host_transform\": %.5f, \"update_voxel_map\": %.5f, "
               "\"get_point_cloud\": %.5f}, \"keyframes\": %d, \"features_per_scan\": %.1f, \"l0_exported_per_keyframe\": %.1f, \"final_pose_t\": [%.4f, %.4f, %.4f]}\n",
-              timed, t_total / timed, 1e3 * timed / t_total, t_pre / timed, t_icp / timed, t_map / timed, t_export / timed, keyframes, (double)feats / timed,
+              timed, t_total / timed, 1e3 * timed / t_total, t_pre / timed, t_icp / timed, t_xf / timed, (t_map - t_xf) / timed, t_export / timed, keyframes, (double)feats / timed,
               keyframes ? (double)exported / keyframes : 0.0, pose[3], pose[7], pose[11]);
   return 0;
 }

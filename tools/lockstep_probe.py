@@ -9,8 +9,8 @@ scans, _ = bench.make_scans(K + W + 1, 42, "cuda:0")
 dev = [torch.from_numpy(s).cuda() for s in scans]
 def dev_args(i):
     return dev[i].data_ptr(), scans[i].shape[0], scans[i].shape[1]
-for S in [int(x) for x in sys.argv[1:]] or [16, 64]:
+for S in [int(x) for x in sys.argv[1:]]:
     print(json.dumps(bench.lockstep_leg(api, 0, dev_args, S, K, W, 0, "")), flush=True)
 
-for G, S in [(2, 64), (4, 32), (2, 128), (4, 64), (3, 96)]:
+for G, S in [(3, 96), (4, 96), (6, 64), (8, 48), (6, 48), (8, 32)]:
     print(json.dumps(bench.lockstep_groups_leg(api, 0, dev_args, G, S, K, W)), flush=True)

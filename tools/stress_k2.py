@@ -18,7 +18,16 @@ for l in range(layers):
     vmap.UpdateVoxelMap(pts, [0.0, 0.0, 0.0], 400.0)
 nq = 1 << 20
 q = np.stack([rng.uniform(-109, 109, nq), rng.uniform(-109, 109, nq), -39.0 + 1.5 * rng.integers(0, layers, nq) + 0.7 + rng.normal(0, 0.02, nq)], axis=1).astype(np.float32)
+# coherent: a raster sweep over the slabs like a real scan (one query per 0.5 m L0 cell: 9 queries per 1.5 m L1 cell and layer)
+ax = np.arange(-109.0, 109.0, 0.5)
+xx, yy = np.meshgrid(ax, ax, indexing="ij")
+xy = np.stack([xx.ravel(), yy.ravel()], axis=1)
+need = (nq + len(xy) - 1) // len(xy)
+qc = np.concatenate([np.concatenate([xy, np.full((len(xy), 1), -39.0 + 1.5 * l + 0.7)], axis=1) for l in range(need)])[:nq]
+qc = (qc + rng.normal(0, 0.01, qc.shape)).astype(np.float32)
 icp = api.IterativeClosestPointOptimizer(api.ICPConfig(max_iterations=1), api.AdaptiveMEstimator())
-for _ in range(3):
-    ok, T = icp.optimize(vmap, q, np.eye(4, dtype=np.float32))
-print("ok", ok, vmap.GetVoxelCount(), icp.get_last_stats().num_correspondences)
+# launch order of k_icp_corr (what `ncu -k regex:k_icp_corr -s 2 -c 4` picks): random x3, then coherent x3
+for name, cloud in (("random", q), ("coherent", qc)):
+    for _ in range(3):
+        ok, T = icp.optimize(vmap, cloud, np.eye(4, dtype=np.float32))
+    print(name, "ok", ok, vmap.GetVoxelCount(), icp.get_last_stats().num_correspondences)
