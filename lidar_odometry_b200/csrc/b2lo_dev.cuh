@@ -128,11 +128,10 @@ __device__ __forceinline__ int voxel_coord(float p, float scale) {
   return (int)q;
 }
 
-// The same value without the division on the common path: q = p * (1/scale) is within 1.5 * 2^-23 |q| of the correctly rounded quotient,
+// EXPERIMENT, not used by K2 (see corr_issue): the same value without the division on the common path: q = p * (1/scale) is within 1.5 * 2^-23 |q| of the correctly rounded quotient,
 // so floor(q) can differ from floor(p / scale) only when q sits within a few ulp of an integer - then (and for |q| >= 2^23, where every
 // float is an integer) the true division decides.  Bit-identical to voxel_coord for every input (tests: voxel-boundary values through
-// the correspondence taps); ~6 instructions instead of the ~20 of an IEEE f32 division, three times per query in K2 (same-box A/B on the
-// 10^7-voxel map: coherent sweep 25.6 -> 24.8 us per 2^20 queries, random probes unchanged).
+// the correspondence taps); ~6 instructions instead of the ~20 of an IEEE f32 division, three times per query in K2.
 __device__ __forceinline__ int voxel_coord_fast(float p, float scale, float inv) {
   const float qm = p * inv;
   float q = floorf(qm);

@@ -52,8 +52,7 @@ __device__ __forceinline__ void icp_state_begin(IcpState* st, const ScanParams* 
 
 // returns slot (>=0) if the L1 voxel of w holds a surfel; fills n, c and the key taps
 __device__ __forceinline__ int surfel_probe(const MapDev& M, const float* w, float* n, float* c, int* key3, unsigned long long* morton) {
-  const float inv1 = 1.0f / M.scale1;
-  int kx = voxel_coord_fast(w[0], M.scale1, inv1), ky = voxel_coord_fast(w[1], M.scale1, inv1), kz = voxel_coord_fast(w[2], M.scale1, inv1);
+  int kx = voxel_coord(w[0], M.scale1), ky = voxel_coord(w[1], M.scale1), kz = voxel_coord(w[2], M.scale1);
   if (key3) { key3[0] = kx; key3[1] = ky; key3[2] = kz; }
   unsigned long long key = key_pack(kx, ky, kz);
   if (morton) *morton = key_morton(kx, ky, kz);   // debug tap: the reference's VoxelKeyHash value
@@ -112,9 +111,12 @@ struct CorrStage {   // a query between its key computation and its gate
   uint32_t hs;
   float4 ea, eb;
 };
-__device__ __forceinline__ void corr_issue(const MapDev& M, const float* sR, const float* sT, float4 p, bool valid, CorrStage& q, float inv1) {
+__device__ __forceinline__ void corr_issue(const MapDev& M, const float* sR, const float* sT, float4 p, bool valid, CorrStage& q) {
   transform_point(sR, sT, p.x, p.y, p.z, q.w);
-  int kx = voxel_coord_fast(q.w[0], M.scale1, inv1), ky = voxel_coord_fast(q.w[1], M.scale1, inv1), kz = voxel_coord_fast(q.w[2], M.scale1, inv1);
+  // (true f32 divisions: a division-free floor with an exact fallback near cell faces - voxel_coord_fast in b2lo_dev.cuh - saves ~40
+  // instructions per query but measured SLOWER here, 41.2 vs 37.6 us per 2^20 random probes on the 10^7-voxel map: the three fallback
+  // branches disturb the schedule of this software-pipelined loop more than the shorter common path gains)
+  int kx = voxel_coord(q.w[0], M.scale1), ky = voxel_coord(q.w[1], M.scale1), kz = voxel_coord(q.w[2], M.scale1);
   q.key = (valid && key_in_range(kx, ky, kz)) ? key_pack(kx, ky, kz) : KEY_TOMB;   // TOMB never matches: no surfel
   q.hs = hash_slot(q.key, M.l1_log2cap);
   const float4* e = reinterpret_cast<const float4*>(&M.l1_tab[q.hs]);
@@ -160,8 +162,7 @@ struct k_icp_corr { static __device__ __forceinline__ void run(MapDev M, const f
   if (blockIdx.x >= nact) return;
   const uint32_t mask = (1u << M.l1_log2cap) - 1u;
   CorrStage cur;
-  const float inv1 = 1.0f / M.scale1;
-  if (tile < ntiles) corr_issue(M, sR, sT, p1, tile * TILE + tid < npts, cur, inv1);
+  if (tile < ntiles) corr_issue(M, sR, sT, p1, tile * TILE + tid < npts, cur);
   if (DEPTH >= 3 && tile + G < ntiles) p1 = pts[(tile + G) * TILE + tid];
   int ph = 0;
   for (; tile < ntiles; tile += G) {
@@ -196,7 +197,7 @@ struct k_icp_corr { static __device__ __forceinline__ void run(MapDev M, const f
     // sector loads of tile + G
     CorrStage nxt;
     const bool more = tile + G < ntiles;
-    if (more) corr_issue(M, sR, sT, p1, (tile + G) * TILE + tid < npts, nxt, inv1);
+    if (more) corr_issue(M, sR, sT, p1, (tile + G) * TILE + tid < npts, nxt);
     // results + compaction of this tile: ascending query order, one barrier
     if (in) { slot_out[i] = s; res[i] = r; }
     const bool ok = s >= 0;
