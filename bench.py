@@ -708,17 +708,17 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * K / float(te.item())
 
-    # ---- throughput mode on every rank (N > 1): 32 independent sequences per GPU through b2lo_odom_process_batch_dev, no collective;
+    # ---- throughput mode on every rank (N > 1): 3 lock-step batches of 96 independent sequences per GPU (b2lo_lockstep_process_dev), no collective;
     # aggregate = all sequences of all ranks / the slowest rank's wall time between barriers (informational, `value` stays one sequence per GPU)
     batched_all = None
     if world > 1 and args.concurrent:
-        S_b = 32
+        G_b, S_b = 3, 96
         barrier()
-        bl = batch_leg(api, local, dev_args, S_b, K, W)
-        tb = torch.tensor([S_b * K / bl["scans_per_s"]], dtype=torch.float64, device="cuda")
+        bl = lockstep_groups_leg(api, local, dev_args, G_b, S_b, K, W)
+        tb = torch.tensor([G_b * S_b * K / bl["scans_per_s"]], dtype=torch.float64, device="cuda")
         dist.all_reduce(tb, op=dist.ReduceOp.MAX)
-        batched_all = {"sequences_per_gpu": S_b, "gpus": world, "scans_per_s": world * S_b * K / float(tb.item()), "driver": bl["driver"],
-                       "timing": "slowest rank's wall clock around its K batch calls"}
+        batched_all = {"sequences_per_gpu": G_b * S_b, "lockstep_batches_per_gpu": G_b, "gpus": world, "scans_per_s": world * G_b * S_b * K / float(tb.item()),
+                       "driver": bl["driver"], "timing": "slowest rank's wall clock around its leg"}
 
     # ---- point-sharded dense scan (configs[4], second half) at N > 1: every rank takes part, rank 0 reports -----------------------------
     sharded = None
