@@ -215,6 +215,14 @@ typedef struct b2lo_shard_comm b2lo_shard_comm;
 int b2lo_shard_unique_id(void* out, size_t bytes /* >= 128 */);
 int b2lo_shard_comm_create(b2lo_ctx* ctx, int world, int rank, const void* unique_id, size_t bytes, b2lo_shard_comm** out);
 int b2lo_shard_comm_destroy(b2lo_shard_comm* comm);
+/* Peer-memory exchange instead of NCCL (one process per GPU on one NVLink / NVSwitch node, <= 8 ranks): every rank owns a mailbox in
+ * its HBM; b2lo_shard_comm_ipc_handle returns its cudaIpc handle (64 bytes), the host hands all handles to every rank (rank order) and
+ * b2lo_shard_comm_open_peers maps them.  From then on each exchange of b2lo_icp_shard_optimize is ONE small kernel per rank that stores
+ * its payload straight into every peer's mailbox over NVLink, publishes an epoch and adds the peers' payloads in rank order (identical
+ * bits on every rank) - no NCCL launch.  b2lo_shard_comm_create may then be given unique_id = NULL (no NCCL at all).  A rank that never
+ * arrives makes the others give up after ~3 s with B2LO_E_CUDA instead of hanging the GPU. */
+int b2lo_shard_comm_ipc_handle(b2lo_shard_comm* comm, void* out, size_t bytes /* >= 64 */);
+int b2lo_shard_comm_open_peers(b2lo_shard_comm* comm, const void* handles /* world x bytes_each, rank order */, size_t bytes_each);
 int b2lo_icp_shard_optimize(b2lo_map* map, b2lo_shard_comm* comm, const float* local_xyz, size_t m, size_t stride_floats, const float T_init[16],
                             const b2lo_icp_cfg* cfg, float T_out[16], b2lo_icp_stats* stats /*nullable*/, float* collective_ms /*nullable*/);
 

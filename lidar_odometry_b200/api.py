@@ -631,8 +631,10 @@ class PointShardedICP:
     Collectives (3 tiny ones per Gauss-Newton iteration) go through torch.distributed on the caller's process group;
     with ``group=None`` and an uninitialised torch.distributed the exchange is the identity (single rank)."""
 
-    def __init__(self, config: ICPConfig | None = None, adaptive_estimator: AdaptiveMEstimator | None = None, group=None, device_ordered=True):
-        """device_ordered=True: the whole loop is ONE C call (b2lo_icp_shard_optimize) whose three exchanges per iteration are NCCL calls
+    def __init__(self, config: ICPConfig | None = None, adaptive_estimator: AdaptiveMEstimator | None = None, group=None, device_ordered=True, exchange="nccl"):
+        """exchange="peer" (with device_ordered=True): the three exchanges per iteration are one small kernel each that stores straight into
+        the peers' mailboxes over NVLink (cudaIpc peer memory, b2lo_shard_comm_open_peers) - no NCCL at all; "nccl": NCCL calls on the stream.
+        device_ordered=True: the whole loop is ONE C call (b2lo_icp_shard_optimize) whose three exchanges per iteration are NCCL calls
         enqueued on the context stream between the kernels - no host round trip inside the loop; torch.distributed only carries the 128-byte
         NCCL unique id once.  device_ordered=False: the host-driven phase API (b2lo_icp_shard_corr / _sample / _accumulate / _finish with
         torch.distributed collectives between them), kept as the readable specification of the exchange and for A/B runs."""
@@ -640,6 +642,9 @@ class PointShardedICP:
         self.m_adaptive_estimator = adaptive_estimator
         self.group = group
         self.device_ordered = device_ordered
+        if exchange not in ("nccl", "peer"):
+            raise ValueError("exchange must be 'nccl' or 'peer'")
+        self.exchange = exchange
         self.m_last_stats = OptimizationStats()
         self.collective_seconds = 0.0
         self._comm = None
@@ -664,15 +669,33 @@ class PointShardedICP:
         rank = dist.get_rank(self.group) if multi else 0
         world = dist.get_world_size(self.group) if multi else 1
         uid = np.zeros(128, np.uint8)
-        if multi:
+        peer = multi and self.exchange == "peer"
+        on_gpu = multi and dist.get_backend(self.group) == "nccl"
+        if multi and not peer:
             if rank == 0:
                 check(L.b2lo_shard_unique_id(_p(uid), 128))
-            on_gpu = dist.get_backend(self.group) == "nccl"
             t = torch.from_numpy(uid).cuda(ctx.device) if on_gpu else torch.from_numpy(uid)
             dist.broadcast(t, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
             uid = t.cpu().numpy().copy()
         h = C.c_void_p()
-        check(L.b2lo_shard_comm_create(ctx.h, world, rank, _p(uid), 128, C.byref(h)))
+        check(L.b2lo_shard_comm_create(ctx.h, world, rank, None if peer else _p(uid), 128, C.byref(h)))
+        if peer:    # every rank's mailbox handle (64 bytes) to every rank, in rank order
+            mine = np.zeros(64, np.uint8)
+            check(L.b2lo_shard_comm_ipc_handle(h, _p(mine), 64))
+            t = torch.from_numpy(mine).cuda(ctx.device) if on_gpu else torch.from_numpy(mine)
+            got = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(got, t, group=self.group)
+            handles = np.ascontiguousarray(np.stack([g.cpu().numpy() for g in got]))
+            rc = L.b2lo_shard_comm_open_peers(h, _p(handles), 64)
+            why = capi.last_error() if rc < 0 else ""
+            # every rank learns whether ALL ranks mapped all mailboxes (this is also the barrier before the first store into one):
+            # a rank that could not must not leave the others spinning on its payload
+            flag = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32)
+            flag = flag.cuda(ctx.device) if on_gpu else flag
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            if int(flag.item()) == 0:
+                L.b2lo_shard_comm_destroy(h)
+                raise capi.B2loError(rc if rc < 0 else -1, "peer-memory exchange unavailable: " + (why or "another rank could not map the mailboxes (no P2P access between the GPUs?)"))
         self._comm, self._comm_ctx = h, ctx
         return h
 

@@ -140,6 +140,8 @@ SIGNATURES = {
     "b2lo_shard_unique_id": (_i, [_vp, _sz]),
     "b2lo_shard_comm_create": (_i, [_vp, _i, _i, _vp, _sz, C.POINTER(_vp)]),
     "b2lo_shard_comm_destroy": (_i, [_vp]),
+    "b2lo_shard_comm_ipc_handle": (_i, [_vp, _vp, _sz]),
+    "b2lo_shard_comm_open_peers": (_i, [_vp, _vp, _sz]),
     "b2lo_icp_shard_optimize": (_i, [_vp, _vp, _vp, _sz, _sz, _vp, C.POINTER(IcpCfg), _vp, C.POINTER(IcpStats), C.POINTER(C.c_float)]),
     "b2lo_se3_mul": (None, [_vp, _vp, _vp]),
     "b2lo_se3_inv": (None, [_vp, _vp]),

@@ -452,6 +452,7 @@ static int icp_optimize_common(b2lo_map* map, const float4* d_pts, const int* d_
   float ms = 0.0f;
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   fill_stats(ctx, T_out, stats, ms);
+  if (ctx->h_icp->status == B2LO_E_CAPACITY) { set_error("more than 2^22 correspondences in one optimize: outside the PKO sample tables"); return B2LO_E_CAPACITY; }
   return ctx->h_icp->status == B2LO_S_INSUFFICIENT ? B2LO_S_INSUFFICIENT : B2LO_OK;
 }
 

@@ -464,6 +464,41 @@ __device__ __forceinline__ double em_rsqrt(double x) {
 }
 
 constexpr int PKO_TOFF = 1024;
+// Exclusive scan of the per-tile accepted counts by ONE block when there are many tiles (dense scans: thousands).  Warp w owns a
+// contiguous run of tiles; pass 1 sums it with independent loads, one barrier orders the warp totals, pass 2 re-reads the run (L2 hits)
+// and writes the offsets with a warp-shuffle scan per 128 tiles - two barriers in all instead of two per blockDim tiles, and no load
+// sits on the critical path of a barrier.  Integer sums: the result is the same in any order.  Returns the total.
+__device__ __forceinline__ int tile_scan_warps(const int* tilecnt, int* tileoff, int ntiles, int* sm /* >= 32 ints */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int per = ((ntiles + nw * 128 - 1) / (nw * 128)) * 128;
+  const int b = wid * per, e = (b + per < ntiles) ? b + per : ntiles;
+  int s = 0;
+  for (int t = b + lane * 4; t < e; t += 128) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) if (t + u < e) s += __ldcg(&tilecnt[t + u]);
+  }
+  s = __reduce_add_sync(0xffffffffu, s);
+  __syncthreads();
+  if (lane == 0) sm[wid] = s;
+  __syncthreads();
+  int base = 0, tot = 0;
+  for (int w = 0; w < nw; ++w) { const int v = sm[w]; if (w < wid) base += v; tot += v; }
+  for (int t0 = b; t0 < e; t0 += 128) {
+    const int t = t0 + lane * 4;
+    int c[4], ls = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { c[u] = (t + u < e) ? __ldcg(&tilecnt[t + u]) : 0; ls += c[u]; }
+    int incl = ls;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    int ex = base + incl - ls;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) if (t + u < e) { tileoff[t + u] = ex; ex += c[u]; }
+    base += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  __syncthreads();
+  return tot;
+}
 constexpr int EM_SPL = MAXS / 32;   // samples per lane in the EM (4): sample index = lane + 32 k
 static_assert(MAXS % 32 == 0, "EM layout needs a multiple of 32 samples");
 
@@ -522,6 +557,8 @@ __device__ __noinline__ void pko1_body(const int* d_npts, IcpState* st, IcpParam
   const int ntiles = (npts + ctile - 1) / ctile;
   // 1. exclusive scan of the per-tile accepted counts
   int base = 0;
+  if (ntiles > PKO_TOFF) base = tile_scan_warps(tilecnt, tileoff, ntiles, sm);   // dense scans; s_toff is not used beyond PKO_TOFF tiles
+  else
   for (int t0 = 0; t0 < ntiles; t0 += blockDim.x) {
     int t = t0 + tid;
     int c = t < ntiles ? __ldcg(&tilecnt[t]) : 0;
@@ -536,6 +573,8 @@ __device__ __noinline__ void pko1_body(const int* d_npts, IcpState* st, IcpParam
     if (tid == 0) { st->done = 2; st->status = B2LO_S_INSUFFICIENT; }
     return;
   }
+  // the precomputed image of std::shuffle's swap partners (the sample draw below) covers index vectors of up to 2^22 correspondences
+  if (prm.use_pko && C > (1 << 22)) { if (tid == 0) { st->done = 2; st->status = B2LO_E_CAPACITY; } return; }
   // 2. residual normalisation scale, first iteration only (ICP.cpp:304-316)
   c1 = clock64();
   double scale = st->scale;
@@ -802,7 +841,9 @@ __device__ void gn_finish(IcpState* st, const IcpParams& prm, const double* acc 
   }
   float mg[6], dx[6];
   for (int a = 0; a < 6; ++a) mg[a] = -g[a];
+  TL_HERE();   // finish: unpacked, trace head written
   ldlt6_solve(H, mg, dx);
+  TL_HERE();   // finish: LDLT solved
   float dt[3] = {dx[0], dx[1], dx[2]}, dw[3] = {dx[3], dx[4], dx[5]};
   Pose d;
   float wn = sqrtf(sqn3(dw));
@@ -833,6 +874,7 @@ __device__ void gn_finish(IcpState* st, const IcpParams& prm, const double* acc 
     nxt.t[0] = cur.t[0] + rt[0]; nxt.t[1] = cur.t[1] + rt[1]; nxt.t[2] = cur.t[2] + rt[2];
     nxt.R = so3_project_near(mat3_mul(cur.R, d.R));
   }
+  TL_HERE();   // finish: pose updated
   for (int i = 0; i < 9; ++i) st->R[i] = nxt.R.m[i];
   for (int i = 0; i < 3; ++i) st->t[i] = nxt.t[i];
   if (tr) { for (int i = 0; i < 6; ++i) tr->dx[i] = dx[i]; pose_to_T16(nxt, tr->T_out); }
@@ -1165,34 +1207,34 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
 
 // ---- point-sharded mode: queries split across ranks, map replicated ---------------------------------------
 // local statistics of this rank's shard after K2: tile offsets, accepted count, sum r, sum r^2
-__global__ void __launch_bounds__(256) k_shard_stats(const int* __restrict__ d_npts, IcpState* st, IcpParams prm, const double* __restrict__ res,
-                                                      const int* __restrict__ slot, const int* __restrict__ tilecnt, int* tileoff, double* stats3,
-                                                      const double* __restrict__ tilesum) { TL_START();
+__device__ __forceinline__ void shard_stats_body(const int* __restrict__ d_npts, IcpState* st, const IcpParams& prm, const int* __restrict__ tilecnt, int* tileoff,
+                                                 double* stats3, const double* __restrict__ tilesum) {
   __shared__ int sm[40];
   __shared__ double smd[40];
   const int tid = threadIdx.x;
   const int npts = *d_npts;
   const int ntiles = (npts + prm.ctile - 1) / prm.ctile;
-  int base = 0;
-  for (int t0 = 0; t0 < ntiles; t0 += blockDim.x) {
-    int t = t0 + tid;
-    int c = t < ntiles ? tilecnt[t] : 0, tot;
-    int e = block_excl_scan(c, &tot, sm);
-    if (t < ntiles) tileoff[t] = base + e;
-    base += tot;
-  }
+  const int base = tile_scan_warps(tilecnt, tileoff, ntiles, sm);
   double a1 = 0.0, a2 = 0.0;
-  for (int t = tid; t < ntiles; t += blockDim.x) { a1 += tilesum[2 * t]; a2 += tilesum[2 * t + 1]; }
-  a1 = block_sum_d(a1, smd);
-  a2 = block_sum_d(a2, smd);
+  if (st->iter == 0) {   // the moments only feed the iteration-0 residual scale (shard_plan_body)
+    for (int t = tid; t < ntiles; t += blockDim.x) { a1 += tilesum[2 * t]; a2 += tilesum[2 * t + 1]; }
+    a1 = block_sum_d(a1, smd);
+    a2 = block_sum_d(a2, smd);
+  }
   if (tid == 0) { st->n_blocks = base; stats3[0] = (double)base; stats3[1] = a1; stats3[2] = a2; }
+}
+__global__ void __launch_bounds__(256) k_shard_stats(const int* __restrict__ d_npts, IcpState* st, IcpParams prm, const double* __restrict__ res,
+                                                      const int* __restrict__ slot, const int* __restrict__ tilecnt, int* tileoff, double* stats3,
+                                                      const double* __restrict__ tilesum) { TL_START();
+  shard_stats_body(d_npts, st, prm, tilecnt, tileoff, stats3, tilesum);
 }
 // this rank's contribution to the global GMM sample: position j of shuffle(iota(C_total)) is a global compacted index;
 // the rank owning it ([offset, offset + C_local)) writes the normalised residual, everybody else writes 0
-__global__ void __launch_bounds__(MAXS) k_shard_sample(const int* __restrict__ d_npts, IcpState* st, IcpParams prm, const double* __restrict__ res,
-                                                        const int* __restrict__ cidx, const int* __restrict__ tileoff, const PkoTables* __restrict__ T,
-                                                        const int* __restrict__ hits, long long offset, long long c_total, double scale, double* sample,
-                                                        const double* __restrict__ plan) { TL_START();
+// (called by every thread of the block; threads >= MAXS only take part in the barrier)
+__device__ __forceinline__ void shard_sample_body(const int* __restrict__ d_npts, IcpState* st, const IcpParams& prm, const double* __restrict__ res,
+                                                  const int* __restrict__ cidx, const int* __restrict__ tileoff, const PkoTables* __restrict__ T,
+                                                  const int* __restrict__ hits, long long offset, long long c_total, double scale, double* sample,
+                                                  const double* plan) {
   __shared__ int s_head[MAXS];
   const int tid = threadIdx.x;
   if (plan) {   // device-ordered mode: offset / total / scale come from k_shard_plan; a finished or failed optimize contributes nothing
@@ -1204,20 +1246,29 @@ __global__ void __launch_bounds__(MAXS) k_shard_sample(const int* __restrict__ d
   const int npts = *d_npts;
   const int ntiles = (npts + prm.ctile - 1) / prm.ctile;
   const int mode = C >= 65536 ? 2 : ((C & 1) ? 1 : 0);
-  s_head[tid] = T->head_r[mode][tid];
+  if (tid < MAXS) s_head[tid] = T->head_r[mode][tid];
   __syncthreads();
   const int ns = T->sample_size < C ? T->sample_size : C;
   double out = 0.0;
   if (tid < ns) {
     const int lo = T->hit_off[mode][tid], hi = T->hit_off[mode][tid + 1];
     int best = -1;
-    for (int q = lo; q < hi; ++q) { int v = hits[q]; if (v < C) best = v; else break; }
+    for (int q0 = lo; q0 < hi; q0 += 8) {   // ascending hit list, eight independent loads per round (as in pko1_body)
+      int v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = (q0 + u < hi) ? hits[q0 + u] : 0x7fffffff;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) if (v[u] < C) best = v[u];
+      if (v[7] >= C) break;
+    }
     long long ci = best;
     if (best < 0) {
-      int pos = tid;
-      const int top = C - 1 < MAXS - 1 ? C - 1 : MAXS - 1;
-      for (int i = top; i >= 1; --i) { int r = s_head[i]; pos = (pos == i) ? r : ((pos == r) ? i : pos); }
-      ci = pos;
+      if (C >= MAXS) ci = T->head_pos[mode][tid];   // all 127 head swaps apply: the trace is a constant of the mode
+      else {
+        int pos = tid;
+        for (int i = C - 1; i >= 1; --i) { int r = s_head[i]; pos = (pos == i) ? r : ((pos == r) ? i : pos); }
+        ci = pos;
+      }
     }
     ci -= offset;
     if (ci >= 0 && ci < c_local) {
@@ -1228,6 +1279,12 @@ __global__ void __launch_bounds__(MAXS) k_shard_sample(const int* __restrict__ d
     }
   }
   if (tid < MAXS) sample[tid] = out;
+}
+__global__ void __launch_bounds__(MAXS) k_shard_sample(const int* __restrict__ d_npts, IcpState* st, IcpParams prm, const double* __restrict__ res,
+                                                        const int* __restrict__ cidx, const int* __restrict__ tileoff, const PkoTables* __restrict__ T,
+                                                        const int* __restrict__ hits, long long offset, long long c_total, double scale, double* sample,
+                                                        const double* __restrict__ plan) { TL_START();
+  shard_sample_body(d_npts, st, prm, res, cidx, tileoff, T, hits, offset, c_total, scale, sample, plan);
 }
 __global__ void k_shard_finish(IcpState* st, IcpParams prm, const double* __restrict__ acc28) { TL_START();
   if (threadIdx.x == 0 && blockIdx.x == 0 && !st->done) {
@@ -1240,7 +1297,7 @@ __global__ void k_shard_finish(IcpState* st, IcpParams prm, const double* __rest
 // device-ordered point-sharded mode: every rank turns the all-gathered (C_r, sum r, sum r^2) triples into the same plan -
 // plan[0] = global offset of this rank's accepted correspondences, plan[1] = global count C, plan[2] = residual scale - and applies
 // the reference's C < min_correspondence_points test (ICP.cpp:298-302) and iteration-0 scale (ICP.cpp:304-316) to the GLOBAL values
-__global__ void k_shard_plan(IcpState* st, IcpParams prm, const double* __restrict__ gathered, int world, int rank, double* plan) { TL_START();
+__device__ __forceinline__ void shard_plan_body(IcpState* st, const IcpParams& prm, const double* gathered, int world, int rank, double* plan) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (st->done) { plan[0] = 0.0; plan[1] = 0.0; plan[2] = st->scale; return; }
   long long off = 0, total = 0;
@@ -1253,12 +1310,98 @@ __global__ void k_shard_plan(IcpState* st, IcpParams prm, const double* __restri
   double scale = st->scale;
   st->n_corr = (int)total;
   if (total < prm.min_corr) { st->done = 2; st->status = B2LO_S_INSUFFICIENT; }
+  else if (prm.use_pko && total > (1ll << 22)) { st->done = 2; st->status = B2LO_E_CAPACITY; }   // the GLOBAL count left the PKO sample tables
   else if (st->iter == 0 && !st->scale_forced) {
     const double mean = a1 / (double)total;
     scale = sqrt(fmax(a2 / (double)total - mean * mean, 0.0)) / 6.0;
     st->scale = scale;
   }
   plan[0] = (double)off; plan[1] = (double)total; plan[2] = scale;
+}
+__global__ void k_shard_plan(IcpState* st, IcpParams prm, const double* __restrict__ gathered, int world, int rank, double* plan) { TL_START();
+  shard_plan_body(st, prm, gathered, world, rank, plan);
+}
+
+// ---- peer-memory exchange over NVLink (the B200-native alternative to the three NCCL launches per iteration) -------------------------
+// Every rank owns a MAILBOX in its HBM that the peers write into directly (cudaIpc-mapped pointers, one process per GPU): slot
+// [exchange][source rank] holds the source's payload tagged with the epoch of the exchange.  One exchange: store the own payload
+// into every peer's mailbox, then wait for the current epoch from all sources in the OWN mailbox and add / gather the payloads in
+// rank order (the same order on every rank: bit-identical results everywhere).  No NCCL launch, no proxy thread, no ring.  A slot is
+// reused every third exchange at the earliest, and every exchange in between is a barrier of all ranks, so no payload is overwritten
+// before it is read.
+// Because an exchange is a few lines inside a CTA, the single-CTA steps around it fuse: per iteration the peer path launches
+//   K2 -> k_shard_pre_peer (shard statistics, all-gather, plan, sample, all-reduce, GMM fit) -> arg-min -> K5 -> k_shard_post_peer
+// (all-reduce of the 28 sums + the 6x6 solve) = 5 kernels instead of the 11 of the NCCL path.
+constexpr int P2P_MAXW = 8, P2P_MAXN = 128;
+// A payload double travels as two 8-byte words {32 data bits, 32-bit epoch}: an aligned 8-byte store arrives whole, so the reader
+// needs no separate flag and the writer no fence between payload and flag (the "low-latency" wire format NCCL also uses for small
+// messages) - one NVLink store latency per exchange.
+struct ShardMailbox { unsigned long long w[4][P2P_MAXW][2 * P2P_MAXN]; };   // exchange kinds 0..2 of an iteration + 3 = the start line of an optimize
+struct PeerTable { ShardMailbox* p[P2P_MAXW]; };
+struct PeerArgs { PeerTable peers; int rank, world; unsigned long long epoch; int* err; };
+// mode 0: dst[r * n + t] = payload of rank r (all-gather); mode 1: dst[t] = sum over ranks in rank order (all-reduce).
+// Called by every thread of a block of >= P2P_MAXN threads; src/dst are read/written by this block only.
+__device__ __forceinline__ void p2p_exchange_body(const PeerArgs& pa, const double* src, double* dst, int n, int e, unsigned long long epoch, int mode) {
+  const int t = threadIdx.x;
+  __syncthreads();                   // src was written by other threads of this block
+  unsigned long long g0 = 0;
+  if (t == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
+  const unsigned long long tag = (epoch & 0xffffffffull) << 32;
+  if (t < n) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(src[t]);
+    const unsigned long long w0 = tag | (bits & 0xffffffffull), w1 = tag | (bits >> 32);
+    for (int p = 0; p < pa.world; ++p) {
+      volatile unsigned long long* q = pa.peers.p[p]->w[e][pa.rank];
+      q[2 * t] = w0; q[2 * t + 1] = w1;
+    }
+    const volatile unsigned long long* mine = pa.peers.p[pa.rank]->w[e][0];
+    const long long t0 = clock64();
+    double a = 0.0;
+    for (int r = 0; r < pa.world; ++r) {   // rank order: the same sum on every rank
+      unsigned long long v0, v1;
+      for (;;) {                           // bounded: a lost peer must not hang the GPU
+        v0 = mine[(size_t)r * 2 * P2P_MAXN + 2 * t]; v1 = mine[(size_t)r * 2 * P2P_MAXN + 2 * t + 1];
+        if ((v0 >> 32) == (tag >> 32) && (v1 >> 32) == (tag >> 32)) break;
+        if (clock64() - t0 > 6000000000ll) { atomicExch(pa.err, 1); break; }
+      }
+      const double x = __longlong_as_double((long long)((v0 & 0xffffffffull) | (v1 << 32)));
+      if (mode == 0) dst[r * n + t] = x; else a += x;
+    }
+    if (mode != 0) dst[t] = a;
+  }
+  __syncthreads();
+  if (t == 0) {                      // latency report: ns this exchange took on this rank, waiting for the slowest peer included
+    unsigned long long g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    if (e < 3) reinterpret_cast<unsigned long long*>(pa.err + 2)[e] = g1 - g0;
+  }
+}
+__global__ void __launch_bounds__(P2P_MAXN) k_p2p_exchange(PeerArgs pa, const double* src, double* dst, int n, int e, int mode) {
+  p2p_exchange_body(pa, src, dst, n, e, pa.epoch, mode);
+}
+// everything between K2 and the arg-min of one point-sharded iteration in ONE single-CTA kernel (epochs pa.epoch and pa.epoch + 1)
+__global__ void __launch_bounds__(PKO_THREADS) k_shard_pre_peer(PeerArgs pa, const int* d_npts, IcpState* st, IcpParams prm, const double* res, const int* cidx,
+                                                                const int* tilecnt, int* tileoff, const double* tilesum, const PkoTables* T, const int* hits,
+                                                                double* stats3, double* gathered, double* plan, double* sample, double* gmm_out) { TL_START();
+  shard_stats_body(d_npts, st, prm, tilecnt, tileoff, stats3, tilesum);
+  if (threadIdx.x == 0) TL_HERE();   // shard statistics done
+  p2p_exchange_body(pa, stats3, gathered, 3, 0, pa.epoch, 0);
+  if (threadIdx.x == 0) TL_HERE();   // statistics gathered
+  shard_plan_body(st, prm, gathered, pa.world, pa.rank, plan);
+  __syncthreads();
+  shard_sample_body(d_npts, st, prm, res, cidx, tileoff, T, hits, 0, 0, 0.0, sample, plan);
+  if (threadIdx.x == 0) TL_HERE();   // sample share drawn
+  p2p_exchange_body(pa, sample, sample, MAXS, 1, pa.epoch + 1, 1);
+  pko1_body(d_npts, st, prm, res, cidx, tilecnt, tileoff, T, hits, gmm_out, sample, 0, 0.0, tilesum, plan);
+}
+// all-reduce of this rank's 28 Gauss-Newton sums + the 6x6 solve and pose update (every rank: identical bits)
+__global__ void __launch_bounds__(P2P_MAXN) k_shard_post_peer(PeerArgs pa, IcpState* st, IcpParams prm, double* acc28) { TL_START();
+  p2p_exchange_body(pa, acc28, acc28, 28, 2, pa.epoch, 1);
+  if (threadIdx.x == 0 && !st->done) {
+    double acc[28];
+    for (int i = 0; i < 28; ++i) acc[i] = acc28[i];
+    gn_finish(st, prm, acc);
+  }
 }
 
 __global__ void k_lookup(MapDev M, float px, float py, float pz, float* out7) { TL_START();
@@ -1556,6 +1699,10 @@ struct b2lo_shard_comm {
   b2lo_ctx* ctx = nullptr;
   ncclComm_t comm = nullptr;
   int world = 1, rank = 0;
+  // peer-memory exchange (b2lo_shard_comm_ipc_handle / _open_peers)
+  b2::ShardMailbox* d_mail = nullptr; b2::PeerTable peers{}; bool p2p = false; unsigned long long epoch = 0; int* d_err = nullptr;
+  b2::PeerArgs peer_args(unsigned long long first_epoch) const { b2::PeerArgs a; a.peers = peers; a.rank = rank; a.world = world; a.epoch = first_epoch; a.err = d_err; return a; }
+  void* opened[b2::P2P_MAXW] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double* d_buf = nullptr;   // [0,3) this rank's stats | [8, 8 + 3 world) gathered | plan (3) | sample (128) | acc (28)
   double *d_stats = nullptr, *d_gathered = nullptr, *d_plan = nullptr, *d_sample = nullptr, *d_acc = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -1581,10 +1728,11 @@ extern "C" int b2lo_shard_comm_create(b2lo_ctx* ctx, int world, int rank, const 
   cudaSetDevice(ctx->device);
   b2lo_shard_comm* c = new b2lo_shard_comm();
   c->ctx = ctx; c->world = world; c->rank = rank;
-  if (world > 1) {
+  if (world > P2P_MAXW) { delete c; set_error("shard communicator: at most %d ranks", P2P_MAXW); return B2LO_E_ARG; }
+  if (world > 1 && unique_id) {   // NCCL is optional: a communicator that only uses the peer-memory exchange passes unique_id = NULL
     NcclApi& N = nccl_api();
     if (!N.ok) { delete c; set_error("NCCL is not available in this process (dlopen libnccl.so.2 failed)"); return B2LO_E_CUDA; }
-    if (!unique_id || bytes < sizeof(ncclUniqueId)) { delete c; return B2LO_E_ARG; }
+    if (bytes < sizeof(ncclUniqueId)) { delete c; return B2LO_E_ARG; }
     ncclUniqueId id;
     std::memcpy(&id, unique_id, sizeof id);
     ncclResult_t r = N.CommInitRank(&c->comm, world, id, rank);
@@ -1595,7 +1743,39 @@ extern "C" int b2lo_shard_comm_create(b2lo_ctx* ctx, int world, int rank, const 
   cudaMemset(c->d_buf, 0, n * sizeof(double));
   c->d_stats = c->d_buf; c->d_gathered = c->d_buf + 8; c->d_plan = c->d_gathered + 3 * world; c->d_sample = c->d_plan + 8; c->d_acc = c->d_sample + 128;
   for (auto& e : c->ev) cudaEventCreate(&e);
+  if (cudaMalloc((void**)&c->d_mail, sizeof(ShardMailbox)) != cudaSuccess || cudaMalloc((void**)&c->d_err, 8 * sizeof(int)) != cudaSuccess) {
+    set_error("cudaMalloc(shard mailbox) failed"); delete c; return B2LO_E_NOMEM;
+  }
+  cudaMemset(c->d_mail, 0, sizeof(ShardMailbox));
+  cudaMemset(c->d_err, 0, 8 * sizeof(int));
   *out = c;
+  return B2LO_OK;
+}
+// the cudaIpc handle of this rank's mailbox (64 bytes), to be handed to every peer by the host
+extern "C" int b2lo_shard_comm_ipc_handle(b2lo_shard_comm* c, void* out, size_t bytes) {
+  if (!c || !out || bytes < sizeof(cudaIpcMemHandle_t)) return B2LO_E_ARG;
+  cudaSetDevice(c->ctx->device);
+  cudaIpcMemHandle_t h;
+  B2_CUDA(cudaIpcGetMemHandle(&h, c->d_mail));
+  std::memcpy(out, &h, sizeof h);
+  return B2LO_OK;
+}
+// handles: world x bytes_each, in rank order (this rank's own entry is ignored).  After this call the exchanges of
+// b2lo_icp_shard_optimize go through the peers' mailboxes over NVLink instead of NCCL.
+extern "C" int b2lo_shard_comm_open_peers(b2lo_shard_comm* c, const void* handles, size_t bytes_each) {
+  if (!c || !handles || bytes_each < sizeof(cudaIpcMemHandle_t)) return B2LO_E_ARG;
+  cudaSetDevice(c->ctx->device);
+  for (int r = 0; r < c->world; ++r) {
+    if (r == c->rank) { c->peers.p[r] = c->d_mail; continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, static_cast<const char*>(handles) + (size_t)r * bytes_each, sizeof h);
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { set_error("cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e)); cudaGetLastError(); return B2LO_E_CUDA; }
+    c->opened[r] = ptr;
+    c->peers.p[r] = static_cast<ShardMailbox*>(ptr);
+  }
+  c->p2p = true;
   return B2LO_OK;
 }
 extern "C" int b2lo_shard_comm_destroy(b2lo_shard_comm* c) {
@@ -1603,6 +1783,9 @@ extern "C" int b2lo_shard_comm_destroy(b2lo_shard_comm* c) {
   cudaSetDevice(c->ctx->device);
   cudaStreamSynchronize(c->ctx->stream);
   if (c->comm) nccl_api().CommDestroy(c->comm);
+  for (void* p : c->opened) if (p) cudaIpcCloseMemHandle(p);
+  if (c->d_mail) cudaFree(c->d_mail);
+  if (c->d_err) cudaFree(c->d_err);
   if (c->d_buf) cudaFree(c->d_buf);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   delete c;
@@ -1620,6 +1803,7 @@ extern "C" int b2lo_icp_shard_optimize(b2lo_map* map, b2lo_shard_comm* c, const 
   b2lo_ctx* ctx = map->ctx;
   std::lock_guard<std::recursive_mutex> lk2(ctx->mu);
   NcclApi& N = nccl_api();
+  if (c->world > 1 && !c->p2p && !c->comm) { set_error("shard communicator has neither NCCL nor opened peers"); return B2LO_E_ARG; }
   IcpParams prm; int qpt;
   const size_t mm = m ? m : 1;
   shard_params(cfg, mm, prm, qpt);
@@ -1631,11 +1815,30 @@ extern "C" int b2lo_icp_shard_optimize(b2lo_map* map, b2lo_shard_comm* c, const 
   unsigned int* tk = reinterpret_cast<unsigned int*>(js + 132);
   const int ntiles = (int)((mm + TILE - 1) / TILE);
   const int grid = ntiles < 1 ? 1 : (ntiles > ctx->i_max_blocks ? ctx->i_max_blocks : ntiles);
+  const bool peer = c->world > 1 && c->p2p;
+  // start line: the ranks finish uploading their shards at different times; one tiny exchange lines them up so that the timed loop
+  // (and the first real exchange) does not absorb the upload skew
+  if (peer) k_p2p_exchange<<<1, P2P_MAXN, 0, s>>>(c->peer_args(++c->epoch), c->d_plan + 4, c->d_plan + 5, 1, 3, 1);
+  else if (c->world > 1) B2_NCCL(N.AllReduce(c->d_plan + 4, c->d_plan + 5, 1, ncclDouble, ncclSum, c->comm, s));
   B2_CUDA(cudaEventRecord(ctx->ev0, s));
   for (int it = 0; it < cfg->max_iterations; ++it) {
     const bool last = it + 1 == cfg->max_iterations;
     corr_start(ctx, cl, s, map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_cidx, ctx->i_blkcnt, ctx->i_tilesum,
                                         nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (peer) {   // 5 launches per iteration; the exchanges are stores into the peers' mailboxes inside the single-CTA kernels
+      if (last) cudaEventRecord(c->ev[0], s);
+      k_shard_pre_peer<<<1, PKO_THREADS, 0, s>>>(c->peer_args(c->epoch + 1), ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_cidx, ctx->i_blkcnt, ctx->i_blkoff,
+                                                 ctx->i_tilesum, ctx->d_pko, ctx->d_pko_hits, c->d_stats, c->d_gathered, c->d_plan, c->d_sample, gmm);
+      c->epoch += 2;
+      if (last) cudaEventRecord(c->ev[1], s);
+      if (cfg->use_adaptive_m_estimator) { launch<k_icp_pko2, 128, 1>(ctx, dim3((unsigned)(cfg->num_alpha_segments)), dim3((unsigned)(128)), 0, s, ctx->d_icp, prm, ctx->d_pko, gmm, js, tk); ctx->launches++; }
+      launch<k_icp_gn<true>, TILE, 2>(ctx, dim3((unsigned)(grid)), dim3((unsigned)(TILE)), 0, s, map->d, ctx->d_query, ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, nullptr, ctx->i_partial, c->d_acc);
+      if (last) cudaEventRecord(c->ev[2], s);
+      k_shard_post_peer<<<1, P2P_MAXN, 0, s>>>(c->peer_args(++c->epoch), ctx->d_icp, prm, c->d_acc);
+      if (last) cudaEventRecord(c->ev[3], s);
+      ctx->launches += 4;
+      continue;
+    }
     k_shard_stats<<<1, 256, 0, s>>>(ctx->d_nquery, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->i_blkcnt, ctx->i_blkoff, c->d_stats, ctx->i_tilesum);
     if (last) cudaEventRecord(c->ev[0], s);
     if (c->world > 1) B2_NCCL(N.AllGather(c->d_stats, c->d_gathered, 3, ncclDouble, c->comm, s));
@@ -1660,8 +1863,10 @@ extern "C" int b2lo_icp_shard_optimize(b2lo_map* map, b2lo_shard_comm* c, const 
   B2_CUDA(cudaGetLastError());
   B2_CUDA(cudaEventRecord(ctx->ev1, s));
   B2_CUDA(cudaMemcpyAsync(ctx->h_icp, ctx->d_icp, sizeof(IcpState), cudaMemcpyDeviceToHost, s));
+  if (c->p2p) B2_CUDA(cudaMemcpyAsync(ctx->h_counts + 50, c->d_err, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));   // [0] timeout flag, [2..8) ns of the last exchange of each kind
   B2_CUDA(cudaStreamSynchronize(s));
   ctx->d2h_bytes += sizeof(IcpState);
+  if (c->p2p && ctx->h_counts[50]) { set_error("peer-memory exchange timed out (a rank did not reach the exchange)"); cudaMemset(c->d_err, 0, sizeof(int)); return B2LO_E_CUDA; }
   const IcpState* h = ctx->h_icp;
   Pose p;
   for (int i = 0; i < 9; ++i) p.R.m[i] = h->R[i];
@@ -1679,7 +1884,12 @@ extern "C" int b2lo_icp_shard_optimize(b2lo_map* map, b2lo_shard_comm* c, const 
     cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
     cudaEventElapsedTime(&b, c->ev[2], c->ev[3]);
     *collective_ms = a + b;
+    if (peer) {   // peer mode: the exchanges sit inside fused kernels; the kernels report the ns of their last exchange themselves
+      const unsigned long long* ns = reinterpret_cast<const unsigned long long*>(ctx->h_counts + 52);
+      *collective_ms = (float)((double)(ns[0] + ns[1] + ns[2]) * 1e-6);
+    }
   }
+  if (h->status == B2LO_E_CAPACITY) { set_error("more than 2^22 correspondences over all ranks: outside the PKO sample tables"); return B2LO_E_CAPACITY; }
   return h->status == B2LO_S_INSUFFICIENT ? B2LO_S_INSUFFICIENT : B2LO_OK;
 }
 

@@ -492,6 +492,28 @@ def test_point_sharded_single_rank_matches_fused(orc, b2, small_kitti):
         assert not ok_s and np.array_equal(bits(T_s), bits(far))
 
 
+def test_optimize_beyond_the_pko_sample_tables_is_refused(orc, b2, small_kitti):
+    """The sample draw is a precomputed image of std::shuffle(iota(C), mt19937(42)) for C <= 2^22; a denser optimize must fail loudly
+    (B2LO_E_CAPACITY) instead of drawing another sample than the reference would.  Without PKO there is no draw and no limit."""
+    from lidar_odometry_b200.capi import B2loError
+    scans, poses = small_kitti
+    omap, gmap, kfs = _built_maps(orc, b2, scans, poses)
+    feat, init = kfs[3][0], T32(poses[2])
+    ame = b2.AdaptiveMEstimator()
+    probe = b2.IterativeClosestPointOptimizer(b2.ICPConfig(), ame)
+    assert probe.optimize(gmap, feat, init)[0]
+    accepted = min(it["n_corr"] for it in probe.get_last_stats().iterations)
+    reps = (1 << 22) // accepted + 2             # enough copies that the ACCEPTED count exceeds 2^22 in the first iteration
+    dense = np.ascontiguousarray(np.tile(feat[:, :3], (reps, 1)))
+    for icp in (b2.IterativeClosestPointOptimizer(b2.ICPConfig(), ame), b2.PointShardedICP(b2.ICPConfig(), ame)):
+        with pytest.raises(B2loError) as e:
+            icp.optimize(gmap, dense, init)
+        assert e.value.code == -4 and "2^22" in str(e.value)
+    ok, T = b2.IterativeClosestPointOptimizer(b2.ICPConfig(), None).optimize(gmap, dense, init)
+    ok1, T1 = b2.IterativeClosestPointOptimizer(b2.ICPConfig(), None).optimize(gmap, feat, init)
+    assert ok and ok1 and np.linalg.norm(T[:3, 3].astype(np.float64) - T1[:3, 3]) < 1e-4   # the same cloud repeated: the same minimiser
+
+
 def _sharded_worker(rank, world, port, out):
     import os
     import torch
@@ -516,8 +538,16 @@ def _sharded_worker(rank, world, port, out):
     ok_s, T_s = shard.optimize(gmap, feats[3][lo:hi], init)
     shard_d = api.PointShardedICP(api.ICPConfig(), ame, device_ordered=True)     # NCCL enqueued from C on the context stream
     ok_d, T_d = shard_d.optimize(gmap, feats[3][lo:hi], init)
+    shard_p = api.PointShardedICP(api.ICPConfig(), ame, device_ordered=True, exchange="peer")   # stores into the peers' mailboxes over NVLink
+    ok_p, T_p = shard_p.optimize(gmap, feats[3][lo:hi], init)
+    ok_p2, T_p2 = shard_p.optimize(gmap, feats[3][lo:hi], init)      # the epochs keep counting across calls
     ok_f, T_f = api.IterativeClosestPointOptimizer(api.ICPConfig(), ame).optimize(gmap, feats[3], init)
+    Tp_all = [torch.zeros(16, device="cuda") for _ in range(world)]
+    dist.all_gather(Tp_all, torch.from_numpy(np.ascontiguousarray(T_p).reshape(16)).cuda())
     if rank == 0:
+        np.savez(out + ".peer.npz", ok_p=ok_p and ok_p2, T_p=T_p, T_p2=T_p2, T_ranks=np.stack([t.cpu().numpy() for t in Tp_all]),
+                 it_p=shard_p.get_last_stats().num_iterations, n_p=shard_p.get_last_stats().iterations[0]["n_corr"],
+                 d_p=shard_p.get_last_stats().iterations[0]["delta"])
         np.savez(out, ok_s=ok_s, ok_f=ok_f, T_s=T_s, T_f=T_f, n_s=shard.get_last_stats().iterations[0]["n_corr"],
                  d_s=shard.get_last_stats().iterations[0]["delta"], coll=shard.collective_seconds, ok_d=ok_d, T_d=T_d,
                  n_d=shard_d.get_last_stats().iterations[0]["n_corr"], d_d=shard_d.get_last_stats().iterations[0]["delta"],
@@ -541,6 +571,11 @@ def test_point_sharded_two_gpus(tmp_path):
     # the device-ordered exchange (NCCL from C, no host round trip in the loop): same global count, same alpha, same iteration count, same pose
     assert int(z["n_d"]) == int(z["n_s"]) and float(z["d_d"]) == float(z["d_s"]) and int(z["it_d"]) == int(z["it_s"])
     assert np.linalg.norm(z["T_d"][:3, 3].astype(np.float64) - z["T_f"][:3, 3]) < 1e-5
+    # the peer-memory exchange: the sum of two payloads has one order, so the bits equal NCCL's; every rank ends with the same pose bits
+    p = np.load(out + ".peer.npz")
+    assert bool(p["ok_p"]) and int(p["n_p"]) == int(z["n_d"]) and float(p["d_p"]) == float(z["d_d"]) and int(p["it_p"]) == int(z["it_d"])
+    assert np.array_equal(p["T_p"].view(np.uint32), z["T_d"].view(np.uint32)) and np.array_equal(p["T_p"].view(np.uint32), p["T_p2"].view(np.uint32))
+    assert np.array_equal(p["T_ranks"][0].view(np.uint32), p["T_ranks"][1].view(np.uint32))
 
 
 # ---- launch plumbing must not change results -------------------------------------------------------------------------
