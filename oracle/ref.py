@@ -37,6 +37,12 @@ def lib():
         L.ref_map_create.argtypes = [C.c_float, C.c_int, C.c_float, C.c_int]
         for name in ("ref_map_point_cloud", "ref_map_surfels", "ref_icp_correspondence_list"):
             getattr(L, name).restype = C.c_size_t
+        L.ref_pipe_create.restype = C.c_void_p
+        L.ref_pipe_create.argtypes = [C.c_void_p]
+        L.ref_pipe_destroy.argtypes = [C.c_void_p]
+        L.ref_pipe_process.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_pipe_map.restype = C.c_void_p
+        L.ref_pipe_map.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -101,9 +107,9 @@ class VoxelMap:
         self.h = C.c_void_p(lib().ref_map_create(voxel, factor, planarity, int(compute_surfels)))
 
     def __del__(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and getattr(self, "owned", True):
             lib().ref_map_destroy(self.h)
-            self.h = None
+        self.h = None
 
     def clear(self):
         lib().ref_map_clear(self.h)
@@ -243,3 +249,29 @@ def plane_normal_nx3(A):
     n = np.zeros(3)
     lib().ref_plane_normal_nx3(_p(A), int(A.shape[0]), _p(n))
     return n
+
+
+class Pipeline:
+    """The per-scan driver (Estimator.cpp:116-233 control flow) over the reference's OWN classes; same interface as orc.Pipeline."""
+
+    def __init__(self, cfg=None):
+        self.cfg = cfg or orc.default_pipe_cfg()
+        self.h = C.c_void_p(lib().ref_pipe_create(C.byref(self.cfg)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_pipe_destroy(self.h)
+            self.h = None
+
+    def process(self, scan):
+        s = f32(scan)
+        pose = np.zeros(16, np.float32); flags = C.c_int(0); times = np.zeros(4)
+        nf, nc, ni = C.c_int(0), C.c_int(0), C.c_int(0)
+        ok = lib().ref_pipe_process(self.h, _p(s), s.shape[0], s.shape[1], _p(pose), C.byref(flags), _p(times), C.byref(nf), C.byref(nc), C.byref(ni))
+        return dict(ok=bool(ok), pose=pose.reshape(4, 4).copy(), keyframe=bool(flags.value & 1), icp_ok=bool(flags.value & 2),
+                    times_ms=times, n_features=nf.value, n_corr=nc.value, n_iters=ni.value)
+
+    def map(self):
+        m = VoxelMap.__new__(VoxelMap)
+        m.h = C.c_void_p(lib().ref_pipe_map(self.h)); m.owned = False; m._pipe = self   # borrowed: the pipeline owns it
+        return m

@@ -7,6 +7,7 @@
 // the restatement and the reference on the same inputs and compare bits.  This file is built with -fno-access-control: it
 // reads the private containers of map::VoxelMap and calls the private find_correspondences* members; the reference sources
 // themselves are compiled as they are.
+#include <chrono>
 #include <cstring>
 #include <fstream>
 #include <memory>
@@ -316,3 +317,134 @@ void ref_plane_normal_nx3(const double* A, int n, double* normal) {
 }
 
 }  // extern "C"
+
+// ---- the per-scan driver over the REAL reference classes --------------------------------------------------------------------------------
+// processing::Estimator itself does not compile here (it pulls in the loop detector, the pose graph and their third-party
+// dependencies), so the driver below restates ONLY its control flow - which reference function is called with which argument, in
+// Estimator.cpp's order (process_frame :116-233, initialize_first_frame :235-269, estimate_motion_dual_frame :271-320,
+// should_create_keyframe :349-368, create_keyframe :449-470, preprocess_frame :561-589) - while every function on the hot path
+// (FastVoxelFilter::filter, IterativeClosestPointOptimizer::optimize, transform_point_cloud, VoxelMap::UpdateVoxelMap /
+// RebuildKdTree / GetPointCloud, SE3f algebra) is the reference's own compiled code.  Used (a) to pin oracle/include/orc_pipeline.hpp
+// pose for pose and (b) as bench.py's CPU baseline of kind "reference".
+namespace {
+struct RefPipe {
+  orc_pipe_cfg cfg;
+  std::unique_ptr<map::FastVoxelFilter> filter;
+  std::unique_ptr<map::VoxelMap> vmap;
+  std::shared_ptr<optimization::AdaptiveMEstimator> pko;
+  std::unique_ptr<rp::IterativeClosestPointOptimizer> icp;
+  std::shared_ptr<database::LidarFrame> previous, last_keyframe;
+  SE3f T_wl, velocity, last_keyframe_pose;
+  bool initialized = false, last_kf = false, last_ok = false;
+  int n_keyframes = 0, next_id = 0;
+  double times[4] = {0, 0, 0, 0};
+  size_t n_features = 0;
+
+  explicit RefPipe(const orc_pipe_cfg& c) : cfg(c) {   // Estimator.cpp:48-81
+    filter.reset(new map::FastVoxelFilter(c.voxel_size));
+    vmap.reset(new map::VoxelMap(c.map_voxel_size));
+    vmap->SetHierarchyFactor(3);
+    vmap->SetPlanarityThreshold(c.surfel_planarity_threshold);
+    vmap->SetComputeSurfels(c.icp.use_surfel_correspondence != 0);
+    pko = to_pko(&c.icp);
+    icp.reset(new rp::IterativeClosestPointOptimizer(to_icp(&c.icp), pko));
+  }
+  void create_keyframe(const std::shared_ptr<database::LidarFrame>& f) {   // :449-470
+    Eigen::Vector3f pos = f->get_pose().Translation();
+    Eigen::Vector3d sensor = pos.cast<double>();
+    vmap->UpdateVoxelMap(f->get_feature_cloud_global(), sensor, cfg.max_range * 1.2, true);
+    if (!cfg.icp.use_surfel_correspondence) vmap->RebuildKdTree();
+    f->set_local_map(vmap->GetPointCloud());
+    last_keyframe = f;
+    last_keyframe_pose = f->get_pose();
+    ++n_keyframes;
+    last_kf = true;
+  }
+  bool process(const float* xyz, size_t n, size_t stride) {
+    using clk = std::chrono::high_resolution_clock;
+    auto t0 = clk::now();
+    last_kf = last_ok = false;
+    times[0] = times[1] = times[2] = times[3] = 0.0;
+    auto raw = std::make_shared<PointCloud>();
+    raw->reserve(n);
+    for (size_t i = 0; i < n; ++i) { Point3D p; p.x = xyz[i * stride]; p.y = xyz[i * stride + 1]; p.z = xyz[i * stride + 2]; raw->push_back(p); }
+    auto frame = std::make_shared<database::LidarFrame>(next_id++, 0.0, raw);
+    auto ta = clk::now();                        // the cloud conversion above is the player's job, not the estimator's: outside the stage times
+    auto down = std::make_shared<PointCloud>();  // preprocess_frame :561-589
+    filter->filter(*raw, *down, cfg.point_stride);
+    n_features = down->size();
+    auto t1 = clk::now();
+    times[0] = std::chrono::duration<double, std::milli>(t1 - ta).count();
+    if (down->empty()) return false;
+    frame->set_processed_cloud(down);
+    frame->set_feature_cloud(down);
+    if (!initialized) {                          // initialize_first_frame :235-269
+      T_wl = frame->get_initial_pose();
+      velocity = SE3f();
+      frame->set_pose(T_wl);
+      auto world = std::make_shared<PointCloud>();
+      Eigen::Matrix4f M = T_wl.Matrix();
+      util::transform_point_cloud(down, world, M);
+      frame->set_feature_cloud_global(world);
+      create_keyframe(frame);
+      previous = frame;
+      initialized = true;
+      auto t2 = clk::now();
+      times[2] = std::chrono::duration<double, std::milli>(t2 - t1).count();
+      times[3] = std::chrono::duration<double, std::milli>(t2 - ta).count();
+      (void)t0;
+      return true;
+    }
+    SE3f guess = previous->get_pose() * velocity;                      // :154
+    SE3f result = guess;
+    auto local_map = last_keyframe ? last_keyframe->get_local_map() : nullptr;
+    if (local_map && !local_map->empty()) {                            // estimate_motion_dual_frame :271-320
+      SE3f init(guess.RotationMatrix(), guess.Translation()), opt;
+      last_ok = icp->optimize(vmap.get(), frame, init, opt);
+      if (last_ok) result = SE3f(opt.RotationMatrix(), opt.Translation());
+    }
+    auto t2 = clk::now();
+    times[1] = std::chrono::duration<double, std::milli>(t2 - t1).count();
+    auto world = std::make_shared<PointCloud>();
+    Eigen::Matrix4f M = result.Matrix();
+    util::transform_point_cloud(down, world, M);                       // :163-166
+    frame->set_feature_cloud_global(world);
+    T_wl = result;
+    velocity = previous->get_pose().Inverse() * T_wl;                  // :177
+    frame->set_pose(T_wl);
+    bool kf = n_keyframes == 0;                                        // should_create_keyframe :349-368
+    if (!kf) {
+      Eigen::Vector3f d = T_wl.Translation() - last_keyframe_pose.Translation();
+      double distance = d.norm();
+      SO3f rd = last_keyframe_pose.Rotation().Inverse() * T_wl.Rotation();
+      double angle = rd.Log().norm();
+      kf = distance > cfg.keyframe_distance_threshold || angle > cfg.keyframe_rotation_threshold;
+    }
+    if (kf) create_keyframe(frame);
+    if (previous && previous != last_keyframe) previous->clear_non_keyframe_data();   // :214-219
+    previous = frame;
+    auto t3 = clk::now();
+    times[2] = std::chrono::duration<double, std::milli>(t3 - t2).count();
+    times[3] = std::chrono::duration<double, std::milli>(t3 - ta).count();
+    return true;
+  }
+};
+}  // namespace
+
+extern "C" {
+void* ref_pipe_create(const orc_pipe_cfg* cfg) { return new RefPipe(*cfg); }
+void ref_pipe_destroy(void* h) { delete static_cast<RefPipe*>(h); }
+int ref_pipe_process(void* h, const float* xyz, size_t n, size_t stride_floats, float* pose16, int* flags, double* times_ms, int* n_features,
+                     int* n_corr, int* n_iters) {
+  RefPipe* p = static_cast<RefPipe*>(h);
+  bool ok = p->process(xyz, n, stride_floats);
+  if (pose16) put_se3(p->T_wl, pose16);
+  if (flags) *flags = (p->last_kf ? 1 : 0) | (p->last_ok ? 2 : 0);
+  if (times_ms) for (int i = 0; i < 4; ++i) times_ms[i] = p->times[i];
+  if (n_features) *n_features = (int)p->n_features;
+  if (n_corr) *n_corr = (int)p->icp->get_last_stats().num_correspondences;
+  if (n_iters) *n_iters = (int)p->icp->get_last_stats().num_iterations;
+  return ok ? 1 : 0;
+}
+void* ref_pipe_map(void* h) { return static_cast<RefPipe*>(h)->vmap.get(); }
+}

@@ -383,6 +383,11 @@ def golden_run(orc, be):
         out["map_digest"].append(map_digest(m))
     k0, c0, n0 = m.export_l0(); l1 = m.export_l1()
     out.update(l0_keys=k0, l0_cent=c0, l0_cnt=n0, l1_keys=l1["keys"], l1_has=l1["has_surfel"], l1_normal=l1["normal"], l1_centroid=l1["centroid"])
+    # the per-scan driver (Estimator::process_frame order) end to end: poses, keyframe flags and counts of every scan
+    pipe = be.Pipeline()
+    rs = [pipe.process(s) for s in scans]
+    out.update(pipe_pose=[r["pose"] for r in rs], pipe_flags=[[int(r["keyframe"]), int(r["icp_ok"]), r["n_features"], r["n_corr"], r["n_iters"]] for r in rs],
+               pipe_map_counts=list(pipe.map().counts()))
     return {k: np.array(v) for k, v in out.items()}
 
 
@@ -401,3 +406,24 @@ def test_fixture_is_current(orc, ref):
     got = golden_run(orc, ref)
     for k in z.files:
         assert np.array_equal(got[k].view(np.uint8), z[k].view(np.uint8)), k
+
+
+def test_per_scan_driver_matches_reference_classes_pose_for_pose(orc, ref):
+    """oracle/include/orc_pipeline.hpp (the restated Estimator::process_frame control flow over the restated classes) against the same
+    control flow over the reference's OWN classes (ref_pipe_* in oracle/src/ref_core_wrap.cpp): filter -> motion-model guess -> optimize ->
+    keyframe decision -> UpdateVoxelMap -> GetPointCloud, scan after scan.  Poses, keyframe decisions, feature / correspondence / iteration
+    counts and the final map must agree bit for bit: an error anywhere on the path compounds through the map and the velocity model."""
+    from lidar_odometry_b200 import synth
+    scans, _ = synth.kitti_sequence(n_scans=7, seed=11, n_rings=64, n_az=500)
+    a, b = orc.Pipeline(), ref.Pipeline()
+    for k, s in enumerate(scans):
+        ra, rb = a.process(s), b.process(s)
+        assert ra["ok"] and rb["ok"]
+        assert np.array_equal(ra["pose"].view(np.uint32), rb["pose"].view(np.uint32)), k
+        for key in ("keyframe", "icp_ok", "n_features", "n_corr", "n_iters"):
+            assert ra[key] == rb[key], (k, key)
+    assert ra["icp_ok"] and ra["n_iters"] >= 1
+    assert a.map().counts() == b.map().counts()
+    ea, eb = a.map().export_l0(), b.map().export_l0()
+    for x, y in zip(ea, eb):
+        assert np.array_equal(np.asarray(x), np.asarray(y))
