@@ -139,6 +139,7 @@ struct k_icp_corr { static __device__ __forceinline__ void run(MapDev M, const f
   __shared__ float sR[9], sT[3];
   __shared__ int s_cnt[2][TILE / 32];
   __shared__ double s_sum[TILE / 32][2];
+  __shared__ double s_tsum[FUSE ? 2 : 1][TILE / 32][2];
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const int G = gridDim.x;
   double m1 = 0.0, m2 = 0.0;
@@ -205,6 +206,14 @@ struct k_icp_corr { static __device__ __forceinline__ void run(MapDev M, const f
     // sum r, sum r^2 over the accepted queries (residual scale, ICP.cpp:304-316): carried per thread across this CTA's tiles and reduced
     // ONCE behind the loop (20 shuffles + 10 f64 adds per tile and warp less); the CTA's total is filed under its first tile
     if (ok) { m1 += r; m2 += r * r; }
+    if (FUSE) {
+      // scan-sized inputs (the per-scan graph): the moments are filed per TILE, so that the result does not depend on how many tiles a
+      // CTA walks - a lock-step batch starts fewer CTAs per sequence than a lone sequence and must produce the same bits
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { m1 += __shfl_xor_sync(0xffffffffu, m1, o); m2 += __shfl_xor_sync(0xffffffffu, m2, o); }
+      if (lane == 0) { s_tsum[ph][wrp][0] = m1; s_tsum[ph][wrp][1] = m2; }
+      m1 = 0.0; m2 = 0.0;
+    }
     if (lane == 0) s_cnt[ph][wrp] = __popc(bal);
     __syncthreads();
     const int cw = lane < TILE / 32 ? s_cnt[ph][lane] : 0;            // lane l holds the count of warp l
@@ -213,13 +222,18 @@ struct k_icp_corr { static __device__ __forceinline__ void run(MapDev M, const f
     if (ok) cidx[tile * TILE + before + __popc(bal & ((1u << lane) - 1u))] = i;
     if (tid == 0) {
       tilecnt[tile] = total;
-      if (tile != (int)blockIdx.x) { tilesum[2 * tile] = 0.0; tilesum[2 * tile + 1] = 0.0; }
+      if (FUSE) {
+        double sa = 0.0, sb = 0.0;
+#pragma unroll
+        for (int w2 = 0; w2 < TILE / 32; ++w2) { sa += s_tsum[ph][w2][0]; sb += s_tsum[ph][w2][1]; }
+        tilesum[2 * tile] = sa; tilesum[2 * tile + 1] = sb;
+      } else if (tile != (int)blockIdx.x) { tilesum[2 * tile] = 0.0; tilesum[2 * tile + 1] = 0.0; }
     }
     ph ^= 1;   // the other buffer is rewritten only after the next barrier: nobody still reads it then
     if (more) cur = nxt;
     p1 = p2;
   }
-  if ((int)blockIdx.x < ntiles) {   // this CTA's residual moments -> the slot of its first tile
+  if (!FUSE && (int)blockIdx.x < ntiles) {   // this CTA's residual moments -> the slot of its first tile
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { m1 += __shfl_xor_sync(0xffffffffu, m1, o); m2 += __shfl_xor_sync(0xffffffffu, m2, o); }
     __syncthreads();   // the last tile's readers of s_sum's neighbours are done
@@ -906,17 +920,24 @@ struct k_icp_gn { static __device__ __forceinline__ void run(MapDev M, const flo
   // run over the active CTAs only (their partial sums would be exact zeros: the result is bit-identical).  The grid is sized by the
   // buffer capacity (graph-replayable), so for a 4 k-point scan 48 of 64 CTAs are of this kind - harmless for a lone sequence, but a
   // lock-step batch of 128 sequences would push 6000 of them through the SMs per launch.
+  // The partial sums are partitioned over VIRTUAL blocks: VG = the grid a lone sequence starts (then virtual = real and the loop below
+  // runs once).  A lock-step batch starts fewer CTAs per sequence (its share of the GPU) and each walks several virtual blocks, one
+  // reduction each - the same additions in the same order, without pushing 48 idle CTAs per sequence through the SMs.
   const int ntile_v = (npts + (int)blockDim.x - 1) / (int)blockDim.x;
-  const unsigned nact = (unsigned)(ntile_v < 1 ? 1 : (ntile_v < (int)gridDim.x ? ntile_v : (int)gridDim.x));
-  if (blockIdx.x >= nact) return;
+  const int VG = prm.gn_vgrid > 0 ? prm.gn_vgrid : (int)gridDim.x;
+  const unsigned nact = (unsigned)(ntile_v < 1 ? 1 : (ntile_v < VG ? ntile_v : VG));                  // virtual blocks with work
+  const unsigned nreal = nact < gridDim.x ? nact : gridDim.x;                                          // CTAs taking part
+  if (blockIdx.x >= nreal) return;
   if (threadIdx.x < 9) sR[threadIdx.x] = pose_v; else if (threadIdx.x < 12) sT[threadIdx.x - 9] = pose_v;
   __syncthreads();
   const double sdiv = fmax(scale_v, 1e-6);
   const float delta = (float)delta_v;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (unsigned vb = blockIdx.x; vb < nact; vb += gridDim.x) {
   double acc[28];
 #pragma unroll
   for (int k = 0; k < 28; ++k) acc[k] = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += gridDim.x * blockDim.x) {
+  for (int i = (int)vb * blockDim.x + threadIdx.x; i < npts; i += VG * blockDim.x) {
     int s = slot[i];
     if (s < 0) continue;
     float4 P = pts[i];
@@ -959,24 +980,38 @@ struct k_icp_gn { static __device__ __forceinline__ void run(MapDev M, const flo
     for (int a = 0; a < 6; ++a) acc[21 + a] += (double)(wr * J[a]);
     acc[27] += (double)(wr * r);
   }
-  // block reduction: warp shuffle, then shared memory across the 8 warps
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // block reduction: warp shuffle, then shared memory across the 8 warps.  The 28 sums are reduced by RECURSIVE HALVING: in the stage
+  // with partner lane ^ s a lane keeps the half of its values whose index has bit s equal to its own and hands the other half over,
+  // so 16 + 8 + 4 + 2 + 1 = 31 shuffle-adds leave the total of value L on lane L - instead of 28 five-stage butterflies (140).
+  // Every total is built by the same tree of pairwise additions as in the butterfly (lane L's view of it; fp addition commutes), so
+  // the bits are unchanged.
+  {
+    double v[32];
 #pragma unroll
-  for (int k = 0; k < 28; ++k) {
-    double v = acc[k];
+    for (int k = 0; k < 32; ++k) v[k] = k < 28 ? acc[k] : 0.0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) red[wid][k] = v;
+    for (int s = 16; s >= 1; s >>= 1) {
+      const bool upper = (lane & s) != 0;
+#pragma unroll
+      for (int i = 0; i < s; ++i) {
+        const double send = upper ? v[i] : v[i + s];
+        const double keep = upper ? v[i + s] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+      }
+    }
+    if (lane < 28) red[wid][lane] = v[0];
   }
   __syncthreads();
   if (threadIdx.x < 28) {
     double v = 0.0;
     for (int w8 = 0; w8 < 8; ++w8) v += red[w8][threadIdx.x];
-    partial[blockIdx.x * 28 + threadIdx.x] = v;
+    partial[vb * 28 + threadIdx.x] = v;
+  }
+  if (vb + gridDim.x < nact) __syncthreads();   // red is rewritten by the next virtual block
   }
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) { unsigned int old = atomicAdd(&st->ticket, 1u); s_last = (old == nact - 1); }
+  if (threadIdx.x == 0) { unsigned int old = atomicAdd(&st->ticket, 1u); s_last = (old == nreal - 1); }
   __syncthreads();
   if (!s_last) return;
   const long long g0 = clock64();
@@ -1059,14 +1094,18 @@ static CorrLaunch corr_launch(b2lo_ctx* ctx, int ctiles_cap, bool fuse_pko = fal
   const int resident = ctx->sm_count * per_sm[f];
   CorrLaunch L;
   L.fuse = fuse_pko; L.grid = ctiles_cap < resident ? ctiles_cap : resident; L.smem = 0;
+  // lock-step batch: the fused kernel's outputs are per tile (independent of the grid), so a sequence starts only as many CTAs as its
+  // share of the GPU; the CTAs walk the tiles.  (A lone sequence keeps one CTA per tile of the buffer capacity: 48 of 64 leave at once,
+  // but 128 sequences x 48 idle CTAs took a third of the SM slot time of the batched launch.)
+  if (fuse_pko) L.grid = batch_grid(ctx, L.grid);
   return L;
 }
 // start K2 (the argument types are spelled out so that the instantiation is the one the occupancy query above looked at)
 static void corr_start(b2lo_ctx* ctx, const CorrLaunch& cl, cudaStream_t s, MapDev M, const float4* pts, const int* d_npts, IcpState* st, IcpParams prm, double* res,
                        int* slot, int* cidx, int* tilecnt, double* tilesum, int* tileoff, const PkoTables* T, const int* hits, double* gmm, const ScanParams* sp_first) {
-  if (cl.fuse) launch<k_icp_corr<3, 1, true>, TILE, 1, B2_CORR_ARGS>(ctx, dim3((unsigned)cl.grid), dim3(TILE), cl.smem, s, M, pts, d_npts, st, prm, res, slot, cidx, tilecnt, tilesum,
+  if (cl.fuse) launch<k_icp_corr<3, 1, true>, TILE, 1, 1, B2_CORR_ARGS>(ctx, dim3((unsigned)cl.grid), dim3(TILE), cl.smem, s, M, pts, d_npts, st, prm, res, slot, cidx, tilecnt, tilesum,
                                                                      tileoff, T, hits, gmm, sp_first);
-  else launch<k_icp_corr<3, 1, false>, TILE, 1, B2_CORR_ARGS>(ctx, dim3((unsigned)cl.grid), dim3(TILE), cl.smem, s, M, pts, d_npts, st, prm, res, slot, cidx, tilecnt, tilesum,
+  else launch<k_icp_corr<3, 1, false>, TILE, 1, 1, B2_CORR_ARGS>(ctx, dim3((unsigned)cl.grid), dim3(TILE), cl.smem, s, M, pts, d_npts, st, prm, res, slot, cidx, tilecnt, tilesum,
                                                               tileoff, T, hits, gmm, sp_first);
 }
 
@@ -1188,8 +1227,11 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
       prof_end(ctx);
     }
     prof_begin(ctx, PS_GN);
-    if (surfel) launch<k_icp_gn<true>, TILE, 2>(ctx, dim3((unsigned)(grid)), dim3((unsigned)(TILE)), 0, s, map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, nullptr, ctx->i_partial, nullptr);
-    else launch<k_icp_gn<false>, TILE, 1>(ctx, dim3((unsigned)(grid)), dim3((unsigned)(TILE)), 0, s, map->d, d_pts, d_npts, ctx->d_icp, prm, ctx->i_res, ctx->i_slot, ctx->k_plane, ctx->i_partial, nullptr);
+    IcpParams pg = prm;
+    pg.gn_vgrid = grid;                       // the partition of the partial sums is the lone sequence's, whatever grid is started
+    const int gstart = batch_grid(ctx, grid);
+    if (surfel) launch<k_icp_gn<true>, TILE, 2>(ctx, dim3((unsigned)(gstart)), dim3((unsigned)(TILE)), 0, s, map->d, d_pts, d_npts, ctx->d_icp, pg, ctx->i_res, ctx->i_slot, nullptr, ctx->i_partial, nullptr);
+    else launch<k_icp_gn<false>, TILE, 1>(ctx, dim3((unsigned)(gstart)), dim3((unsigned)(TILE)), 0, s, map->d, d_pts, d_npts, ctx->d_icp, pg, ctx->i_res, ctx->i_slot, ctx->k_plane, ctx->i_partial, nullptr);
     prof_end(ctx);
     ctx->launches += (cfg->use_adaptive_m_estimator ? 4 : 3) - (fuse ? 1 : 0);
     // long runs (max_iterations beyond the usual 4): look at the done flag every 8 iterations instead of enqueueing dozens of no-op launches

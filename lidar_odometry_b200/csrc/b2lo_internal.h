@@ -71,6 +71,7 @@ struct ScanParams {
 
 struct IcpParams {                // kernel-argument POD
   int max_iterations, min_corr, use_robust, loss_type, use_pko, use_surfel, ctile;
+  int gn_vgrid = 0;               // K5 in a lock-step batch: the grid a LONE sequence would start (the partition of its partial sums); 0 = gridDim.x
   double tol_t, tol_r, max_dist, robust_delta;
 };
 

@@ -53,12 +53,15 @@ void launch_many(const void* packs, int S, dim3 g, dim3 b, size_t smem, cudaStre
   k_many<K, MAXT, MINB, A...><<<dim3(g.x, (unsigned)S), b, smem, st>>>(static_cast<const Pack<A...>*>(packs));
 }
 
-template <class K, int MAXT = 1024, int MINB = 1, class... A>
+// MINBM: min CTAs per SM of the BATCHED instantiation.  A lone sequence's gather kernels are latency chains of a few CTAs and take
+// the registers they like; the same body running for 128 sequences is bound by the number of warps in flight, so its register budget
+// is capped separately (a few spilled pointers cost less than half the occupancy).
+template <class K, int MAXT = 1024, int MINB = 1, int MINBM = MINB, class... A>
 inline void launch(b2lo_ctx* ctx, dim3 g, dim3 b, size_t smem, cudaStream_t st, A... a) {
   if (Recorder* r = ctx_recorder(ctx)) {
     LaunchRec rec;
-    rec.many = &launch_many<K, MAXT, MINB, A...>;
-    rec.prep = &launch_many_prep<K, MAXT, MINB, A...>;
+    rec.many = &launch_many<K, MAXT, MINBM, A...>;
+    rec.prep = &launch_many_prep<K, MAXT, MINBM, A...>;
     rec.grid = g; rec.block = b; rec.smem = smem;
     Pack<A...> p;
     std::memset(&p, 0, sizeof p);      // padding bytes compare equal between recordings

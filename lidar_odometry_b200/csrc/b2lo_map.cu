@@ -537,39 +537,53 @@ struct k_surfel { static __device__ __forceinline__ void run(MapDev M, FEntry* a
 // refits per step a warp per refit would leave 31 lanes waiting for lane 0's SVD (in-graph timeline at S = 128: 312 us per step in one
 // kernel; a thread-per-L1 kernel that also walks the children serially: 231 us).  Same arithmetic in the same order: identical bits.
 constexpr int SURFEL_REC = 88;   // floats per scratch record: s1, nc, first, N, then <= 27 centroids
+// Four affected L1s per warp (eight lanes each: lane c of a group fetches children c, c + 8, ... - most voxels have <= 8 children, so a
+// warp per voxel left three quarters of the lanes idle and, the chain being seven dependent memory round trips, a quarter of the
+// possible requests in flight; in-graph timeline at S = 128: 245 -> see DESIGN.md).
 struct k_surfel_gather { static __device__ __forceinline__ void run(MapDev M, FEntry* atab, const int* __restrict__ alist, int* us, float* rec) { TL_START();
   const int gate_v = M.gate ? *M.gate : 1;
   const int naff = us[US_NAFF];
   const bool skip = (us[US_ERR] & ERR_CAP) || !M.compute_surfels;
   if (!gate_v) return;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, g = lane >> 3, gl = lane & 7;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int a = warp; a < naff; a += nwarps) {
-    float* r = rec + (size_t)a * SURFEL_REC;
-    const int h = alist[a];
-    const unsigned long long ak = atab[h].key;
-    const unsigned int first = atab[h].first;
+  for (int a0 = warp * 4; a0 < naff; a0 += nwarps * 4) {   // warp-uniform trip count
+    const int a = a0 + g;
+    bool go = a < naff;
+    float* r = rec + (size_t)(go ? a : 0) * SURFEL_REC;
+    unsigned long long ak = 0; unsigned int first = 0; int h = 0;
+    if (go) { h = alist[a]; ak = atab[h].key; first = atab[h].first; }
     __syncwarp();
-    if (lane == 0) { atab[h].key = KEY_EMPTY; atab[h].first = 0xFFFFFFFFu; atab[h].cnt = -1; r[0] = __int_as_float(-1); }
-    if (skip) continue;
-    int s1 = l1_find(M, ak);
-    if (s1 < 0) continue;
-    L1Meta* mt = &M.l1_meta[s1];
-    const unsigned long long k1 = M.l1_tab[s1].key;
-    const int N = mt->nchild;
-    if (N < 5) { if (lane == 0) M.l1_tab[s1].key = k1 & ~SURFEL_BIT; continue; }
-    if ((k1 & SURFEL_BIT) && mt->last_child_count == N) continue;  // incremental skip (VoxelMap.cpp:202-205)
-    int px, py, pz;
-    key_unpack(k1 & KEY_MASK, px, py, pz);
-    float cx = 0.0f, cy = 0.0f, cz = 0.0f;
-    int have = 0;
-    if (lane < N) {
-      int s0 = l0_find(M, child_key(px, py, pz, M.factor, mt->child[lane]));
-      if (s0 >= 0) { float4 c = M.l0_cent[M.l0_tab[s0].pos]; cx = c.x; cy = c.y; cz = c.z; have = 1; }
+    if (go && gl == 0) { atab[h].key = KEY_EMPTY; atab[h].first = 0xFFFFFFFFu; atab[h].cnt = -1; r[0] = __int_as_float(-1); }
+    go = go && !skip;
+    int s1 = go ? l1_find(M, ak) : -1;
+    go = go && s1 >= 0;
+    unsigned long long k1 = 0; int N = 0; L1Meta* mt = nullptr;
+    if (go) {
+      mt = &M.l1_meta[s1];
+      k1 = M.l1_tab[s1].key;
+      N = mt->nchild;
+      if (N < 5) { if (gl == 0) M.l1_tab[s1].key = k1 & ~SURFEL_BIT; go = false; }
+      else if ((k1 & SURFEL_BIT) && mt->last_child_count == N) go = false;  // incremental skip (VoxelMap.cpp:202-205)
     }
-    const unsigned hm = __ballot_sync(0xffffffffu, have);
-    if (have) { const int q = __popc(hm & ((1u << lane) - 1u)); r[4 + 3 * q] = cx; r[5 + 3 * q] = cy; r[6 + 3 * q] = cz; }   // child-set order, present children only
-    if (lane == 0) { r[1] = __int_as_float(__popc(hm)); r[2] = __uint_as_float(first); r[3] = __int_as_float(N); r[0] = __int_as_float(s1); }
+    int px = 0, py = 0, pz = 0;
+    if (go) key_unpack(k1 & KEY_MASK, px, py, pz);
+    int q0 = 0;   // present children of this group's voxel so far
+    for (int c0 = 0; c0 < 27; c0 += 8) {
+      const int c = c0 + gl;
+      const bool mine = go && c < N;
+      if (!__any_sync(0xffffffffu, mine)) break;
+      float cx = 0.0f, cy = 0.0f, cz = 0.0f;
+      int have = 0;
+      if (mine) {
+        int s0 = l0_find(M, child_key(px, py, pz, M.factor, mt->child[c]));
+        if (s0 >= 0) { float4 cc = M.l0_cent[M.l0_tab[s0].pos]; cx = cc.x; cy = cc.y; cz = cc.z; have = 1; }
+      }
+      const unsigned hm = (__ballot_sync(0xffffffffu, have) >> (g * 8)) & 0xffu;
+      if (have) { const int q = q0 + __popc(hm & ((1u << gl) - 1u)); r[4 + 3 * q] = cx; r[5 + 3 * q] = cy; r[6 + 3 * q] = cz; }   // child-set order, present children only
+      q0 += __popc(hm);
+    }
+    if (go && gl == 0) { r[1] = __int_as_float(q0); r[2] = __uint_as_float(first); r[3] = __int_as_float(N); r[0] = __int_as_float(s1); }
   }
 } };
 struct k_surfel_fit { static __device__ __forceinline__ void run(MapDev M, int* us, const float* __restrict__ rec, int* plist, unsigned int* pfirst) { TL_START();
@@ -958,7 +972,7 @@ int map_update_dev(b2lo_map* m, float4* d_world, const int* d_n, size_t n_cap, c
   int gw = batch_grid(ctx, grid_for(n_cap * 32, 256));   // one warp per point
   int* plist = m->a_list; unsigned int* pfirst = reinterpret_cast<unsigned int*>(m->a_list + m->upd_cap);
   int* pord = m->a_list + 2 * m->upd_cap; int* poff = m->a_list + 3 * m->upd_cap;
-  launch<k_ins_probe, 256, 1>(ctx, dim3((unsigned)(gm)), dim3((unsigned)(256)), 0, st, d, d_world, d_n, us, m->u_pslot, m->u_next, m->a_tab, m->a_log2cap, m->a_slots, local, T16_dev);
+  launch<k_ins_probe, 256, 1, 5>(ctx, dim3((unsigned)(gm)), dim3((unsigned)(256)), 0, st, d, d_world, d_n, us, m->u_pslot, m->u_next, m->a_tab, m->a_log2cap, m->a_slots, local, T16_dev);
   launch<k_ins_apply, 256, 1>(ctx, dim3((unsigned)(gm)), dim3((unsigned)(256)), 0, st, d, d_world, d_n, m->u_pslot, m->u_next, m->u_isnew, m->u_pts, rehash);
   const bool bulk = n_cap > BULK_UPD && !gate;
   if (bulk) {
@@ -970,7 +984,7 @@ int map_update_dev(b2lo_map* m, float4* d_world, const int* d_n, size_t n_cap, c
   } else {
     launch<k_ins_scan, 1024, 1>(ctx, dim3((unsigned)(1)), dim3((unsigned)(1024)), 0, st, d, d_n, m->u_isnew, m->u_pslot, m->u_newrank, us, m->u_newrank + m->upd_cap);
   }
-  launch<k_ins_place, 256, 1>(ctx, dim3((unsigned)(gw)), dim3((unsigned)(256)), 0, st, d, d_n, us, m->u_pslot, m->u_isnew, m->u_newrank, m->u_pts, m->u_newrank + m->upd_cap);
+  launch<k_ins_place, 256, 1, 5>(ctx, dim3((unsigned)(gw)), dim3((unsigned)(256)), 0, st, d, d_n, us, m->u_pslot, m->u_isnew, m->u_newrank, m->u_pts, m->u_newrank + m->upd_cap);
   ctx->launches += 4;
   int purge = 0;
   if (rehash) {
@@ -983,7 +997,7 @@ int map_update_dev(b2lo_map* m, float4* d_world, const int* d_n, size_t n_cap, c
   } else {
     purge = d.compute_surfels;
     if (ctx->batch_S > 0 && m->s_rec) {   // lock-step batches: gather by warps, fit by threads (see k_surfel_gather)
-      launch<k_surfel_gather, 256, 1>(ctx, dim3((unsigned)(gw)), dim3(256u), 0, st, d, m->a_tab, m->a_slots, us, m->s_rec);
+      launch<k_surfel_gather, 256, 1, 6>(ctx, dim3((unsigned)(gw)), dim3(256u), 0, st, d, m->a_tab, m->a_slots, us, m->s_rec);
       launch<k_surfel_fit, 128, 1>(ctx, dim3((unsigned)(batch_grid(ctx, grid_for(n_cap, 128)))), dim3(128u), 0, st, d, us, (const float*)m->s_rec, plist, pfirst);
       ctx->launches += 1;
     }
