@@ -54,8 +54,13 @@ struct k_flt_insert { static __device__ __forceinline__ void run(const ScanParam
   const float inv = sp->flt_inv;
   const unsigned int rec = sp->flt_rec, ox = sp->flt_off[0], oy = sp->flt_off[1], oz = sp->flt_off[2];
   const unsigned int mode = sp->flt_mode;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_samples; j += gridDim.x * blockDim.x) {
-    float x, y, z;
+  const int lane = threadIdx.x & 31;
+  // warp-uniform trip count: the lanes of a warp pool their table updates below
+  for (int j0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); j0 < n_samples; j0 += gridDim.x * blockDim.x) {
+    const int j = j0 + lane;
+    const bool valid = j < n_samples;
+    float x = 0.0f, y = 0.0f, z = 0.0f;
+    if (valid) {
     if (rec) {   // byte records (PLY vertices, ply_player.cpp:330-337): three 4-byte copies at arbitrary, possibly unaligned offsets
       const unsigned char* b = reinterpret_cast<const unsigned char*>(src) + (size_t)j * sample_stride;
       x = load_f32_bytes(b + ox); y = load_f32_bytes(b + oy); z = load_f32_bytes(b + oz);
@@ -64,8 +69,9 @@ struct k_flt_insert { static __device__ __forceinline__ void run(const ScanParam
       x = p[0]; y = p[1]; z = p[2];
     }
     samp[j] = make_float4(x, y, z, 0.0f);
+    }
     int s = -1;
-    bool take = isfinite(x) && isfinite(y) && isfinite(z);
+    bool take = valid && isfinite(x) && isfinite(y) && isfinite(z);
     unsigned long long key = 0ull;
     if (take) {
       if (mode == 0) key = filter_key(x, y, z, inv);
@@ -77,7 +83,11 @@ struct k_flt_insert { static __device__ __forceinline__ void run(const ScanParam
         key = key_pack(gz, gy, gx);
       }
     }
-    if (take) {
+    // consecutive returns of a ring fall into the same voxel: the lanes of a warp that hold the same key elect their lowest lane
+    // (= lowest point index) to find / insert the cell and to file the whole group's count - a quarter of the atomics on hot cells
+    const unsigned grp = __match_any_sync(0xffffffffu, take ? key : 0xFFFFFFFFFFFFFFFFull);
+    const int leader = __ffs(grp) - 1;
+    if (take && lane == leader) {
       uint32_t mask = (1u << log2cap) - 1u;
       uint32_t h = hash_slot(key, log2cap);
       for (;;) {
@@ -90,10 +100,11 @@ struct k_flt_insert { static __device__ __forceinline__ void run(const ScanParam
         h = (h + 1) & mask;
       }
       s = (int)h;
-      atomicAdd(&tab[h].cnt, 1);                 // starts at -1 (memset 0xFF): holds count-1
+      atomicAdd(&tab[h].cnt, __popc(grp));       // starts at -1 (memset 0xFF): holds count-1
       atomicMin(&tab[h].first, (unsigned)j);     // starts at 0xFFFFFFFF
     }
-    slot_of[j] = s;
+    s = __shfl_sync(0xffffffffu, s, leader);
+    if (valid) slot_of[j] = take ? s : -1;
   }
 } };
 

@@ -513,6 +513,24 @@ __device__ __forceinline__ int tile_scan_warps(const int* tilecnt, int* tileoff,
   __syncthreads();
   return tot;
 }
+// last tile whose offset is <= ci (offsets are non-decreasing, tileoff[0] = 0 <= ci).  Eight-way search: the seven probes of a step are
+// independent loads, so a table of thousands of tiles in L2 costs 4 memory round trips instead of the 12-13 of a binary search.
+__device__ __forceinline__ int tile_of(const int* tileoff, int ntiles, int ci) {
+  int lo = 0, hi = ntiles - 1;
+  while (lo < hi) {
+    const int step = (hi - lo + 8) >> 3;
+    int v[7];
+#pragma unroll
+    for (int u = 0; u < 7; ++u) { const int idx = lo + (u + 1) * step; v[u] = tileoff[idx < hi ? idx : hi]; }
+    int nl = lo, nh = hi;
+#pragma unroll
+    for (int u = 6; u >= 0; --u) { const int idx = lo + (u + 1) * step < hi ? lo + (u + 1) * step : hi; if (v[u] > ci) nh = idx - 1; }
+#pragma unroll
+    for (int u = 0; u < 7; ++u) { const int idx = lo + (u + 1) * step < hi ? lo + (u + 1) * step : hi; if (v[u] <= ci && idx <= nh) nl = idx; }
+    lo = nl; hi = nh;
+  }
+  return lo;
+}
 constexpr int EM_SPL = MAXS / 32;   // samples per lane in the EM (4): sample index = lane + 32 k
 static_assert(MAXS % 32 == 0, "EM layout needs a multiple of 32 samples");
 
@@ -637,9 +655,7 @@ __device__ __noinline__ void pko1_body(const int* d_npts, IcpState* st, IcpParam
     int tl = 0, th = ntiles - 1;  // last tile with tileoff <= ci
     if (ntiles <= PKO_TOFF) {
       while (tl < th) { int mid = (tl + th + 1) >> 1; if (s_toff[mid] <= ci) tl = mid; else th = mid - 1; }
-    } else {
-      while (tl < th) { int mid = (tl + th + 1) >> 1; if (tileoff[mid] <= ci) tl = mid; else th = mid - 1; }
-    }
+    } else tl = tile_of(tileoff, ntiles, ci);
     int q = __ldcg(&cidx[tl * ctile + (ci - tileoff[tl])]);
     s_x[tid] = __ldcg(&res[q]) / sdiv;
   }
@@ -1223,6 +1239,8 @@ int icp_run(b2lo_map* map, const float4* d_pts, const int* d_npts, size_t npts_c
     }
     if (cfg->use_adaptive_m_estimator) {
       prof_begin(ctx, PS_PKO2);
+      // (a warp-per-candidate variant for batches - four candidates in flight per CTA, no block barrier - measured the same: at 128
+      // sequences the 2.6 M f64 logarithms of a step's arg-min are FP64-throughput-bound, 21 us per launch either way)
       launch<k_icp_pko2, 128, 1>(ctx, dim3((unsigned)(batch_grid(ctx, cfg->num_alpha_segments))), dim3((unsigned)(128)), 0, s, ctx->d_icp, prm, ctx->d_pko, gmm, js, tk);
       prof_end(ctx);
     }
@@ -1314,8 +1332,7 @@ __device__ __forceinline__ void shard_sample_body(const int* __restrict__ d_npts
     }
     ci -= offset;
     if (ci >= 0 && ci < c_local) {
-      int tl = 0, th = ntiles - 1;
-      while (tl < th) { int mid = (tl + th + 1) >> 1; if (tileoff[mid] <= (int)ci) tl = mid; else th = mid - 1; }
+      const int tl = tile_of(tileoff, ntiles, (int)ci);
       int q = cidx[tl * prm.ctile + ((int)ci - tileoff[tl])];
       out = res[q] / fmax(scale, 1e-6);
     }
