@@ -337,7 +337,7 @@ int filter_run(b2lo_ctx* ctx, const float* src_dev, size_t n_samples, size_t sam
   // (the packed flags are dead after the scan: their buffer carries the per-sample voxel ids from here on)
   launch<k_flt_fill, 256, 1>(ctx, dim3((unsigned)(blocks)), dim3((unsigned)(256)), 0, st, ctx->f_tab, ctx->f_slot, sp, ctx->f_vid, ctx->f_segstart, ctx->f_bucket, reinterpret_cast<int*>(ctx->f_packed));
   launch<k_flt_rank, 256, 1>(ctx, dim3((unsigned)(blocks)), dim3((unsigned)(256)), 0, st, reinterpret_cast<const int*>(ctx->f_packed), sp, ctx->f_segstart, ctx->f_segcnt, ctx->f_bucket, ctx->f_samp, ctx->f_sorted);
-  launch<k_flt_reduce, 256, 1>(ctx, dim3((unsigned)(blocks)), dim3((unsigned)(256)), 0, st, ctx->nfeat(set), ctx->f_segstart, ctx->f_segcnt, ctx->f_sorted, ctx->f_lead, ctx->f_slot, ctx->f_tab,
+  launch<k_flt_reduce, 256, 1, 4>(ctx, dim3((unsigned)(blocks)), dim3((unsigned)(256)), 0, st, ctx->nfeat(set), ctx->f_segstart, ctx->f_segcnt, ctx->f_sorted, ctx->f_lead, ctx->f_slot, ctx->f_tab,
                                        ctx->feat(set), ctx->feat_key(set), sp, FLT_HEAVY);
   if (prof) prof_end(ctx);
   ctx->launches += 6;

@@ -125,8 +125,12 @@ def test_batch_call_matches_lone_sequences(b2, small_kitti):
     assert sum(o.graph_stats()["replays"] for o in bat.odos) > 0
 
 
-def test_lockstep_batch_matches_lone_sequences(b2, small_kitti):
-    """b2lo_lockstep_*: S sequences advanced by ONE graph replay per scan, every kernel started once per step with blockIdx.y = sequence.
+@pytest.mark.parametrize("grid_limit", [0, 2])
+def test_lockstep_batch_matches_lone_sequences(b2, small_kitti, monkeypatch, grid_limit):
+    """grid_limit = 2: the per-sequence grids of the batched kernels are forced down to two CTAs (B2LO_BATCH_GRID_LIMIT), as in a batch
+    of hundreds of sequences - K2 CTAs walk several tiles (per-tile residual moments), K5 CTAs several virtual blocks, the map kernels
+    stride over their work - and the bits must still be those of a lone sequence.
+    b2lo_lockstep_*: S sequences advanced by ONE graph replay per scan, every kernel started once per step with blockIdx.y = sequence.
     Each sequence must be bit-identical to the same sequence processed alone; the sequences run the scans in different rotations (their
     maps, correspondence counts and Gauss-Newton iteration counts differ inside one step), one of them holds a degenerate scan (falls back
     to the per-sequence path for that step), and the sequences remain usable on their own afterwards."""
@@ -148,6 +152,8 @@ def test_lockstep_batch_matches_lone_sequences(b2, small_kitti):
     for j in range(S):
         o = b2.Odometry(b2.Context(0))
         want.append([o.process_dev(*scan_of(j, k), 4) for k in range(n)])
+    if grid_limit:
+        monkeypatch.setenv("B2LO_BATCH_GRID_LIMIT", str(grid_limit))
     odos = [b2.Odometry(b2.Context(0)) for _ in range(S)]
     ls = b2.LockstepBatch(odos)
     for k in range(n):

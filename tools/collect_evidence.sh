@@ -13,7 +13,7 @@ if [ -f $TL ]; then
 fi
 SHORT="bench.py --steps 20 --warmup 3 --no-stress --no-cpu-baseline --concurrent --lockstep"
 timeout 600 python $SHORT > $OUT/${TAG}_short.json 2> $OUT/${TAG}_short.err && \
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/${TAG}_launches.csv python $SHORT > $OUT/${TAG}_launches_run.log 2>&1
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 1500 --csv --log-file $OUT/${TAG}_launches.csv python $SHORT > $OUT/${TAG}_launches_run.log 2>&1
 python tools/launch_summary.py $OUT/${TAG}_launches.csv $OUT/${TAG}_launches_summary.csv
 if [ "$2" != "quick" ]; then
   timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:k_icp_corr -s 40 -c 8 -o $OUT/${TAG}_k2_kitti -f python $SHORT > $OUT/${TAG}_k2_kitti_run.log 2>&1
