@@ -154,6 +154,7 @@ struct b2lo_map {
   b2lo_ctx* ctx = nullptr;
   b2::MapDev d{};                  // device pointers + params (passed by value to kernels)
   size_t tcap0 = 0, tcap1 = 0;
+  b2::L1Entry* l1_spare_tab = nullptr; b2::L1Meta* l1_spare_meta = nullptr; size_t l1_spare_cap = 0;   // the L1 table of the previous same-size rebuild
   // update scratch sized by the number of new points
   size_t upd_cap = 0;
   float4* u_pts = nullptr; int* u_pslot = nullptr; int* u_next = nullptr; int* u_isnew = nullptr; int* u_newrank = nullptr;

@@ -824,7 +824,9 @@ static int alloc_l0_table(b2lo_map* m, int log2cap) {
   MapDev& d = m->d;
   int rc;
   size_t cap = 1ull << log2cap;
-  if ((rc = dmalloc(&d.l0_tab, cap))) return rc;
+  // same size (a rebuild that only sheds tombstones): the table is refilled from the dense key vector, so it is cleared in place -
+  // no cudaFree (a device-wide synchronisation that would stall every other sequence on the GPU) and no cudaMalloc
+  if (!(d.l0_tab && log2cap == d.l0_log2cap && m->tcap0 == cap) && (rc = dmalloc(&d.l0_tab, cap))) return rc;
   d.l0_log2cap = log2cap; m->tcap0 = cap;
   cudaStream_t st = m->ctx->stream;
   B2_CUDA(cudaMemsetAsync(d.l0_tab, 0xFF, cap * sizeof(L0Entry), st));  // key EMPTY, pos PENDING, scratch idle
@@ -891,10 +893,12 @@ int map_reserve(b2lo_map* m, size_t need_l0, size_t need_upd) {
   }
   // L0 hash: keep (live + tombstones + incoming) under half the table
   if ((m->n0 + m->tomb0 + need_upd) * 2 > m->tcap0) {
-    m->alloc_epoch++;
     int l2 = ceil_log2((m->n0 + need_upd) * 4);
     if (l2 < d.l0_log2cap) l2 = d.l0_log2cap;
-    B2_CUDA(cudaStreamSynchronize(st));
+    if (!(d.l0_tab && l2 == d.l0_log2cap)) {   // the table moves: the old one must be idle before it is freed
+      m->alloc_epoch++;
+      B2_CUDA(cudaStreamSynchronize(st));
+    }
     if ((rc = alloc_l0_table(m, l2))) return rc;
     if (m->n0) { int blocks = (int)((m->n0 + 255) / 256); if (blocks > 2368) blocks = 2368; k_l0_reinsert<<<blocks, 256, 0, st>>>(d, (int)m->n0); ctx->launches++; }
     B2_CUDA(cudaMemsetAsync(d.ctr + CT_TOMB0, 0, sizeof(int), st));
@@ -904,15 +908,26 @@ int map_reserve(b2lo_map* m, size_t need_l0, size_t need_upd) {
     m->alloc_epoch++;
     int l2 = ceil_log2((m->n1 + need_upd) * 4);
     if (l2 < d.l1_log2cap) l2 = d.l1_log2cap;
-    B2_CUDA(cudaStreamSynchronize(st));
     L1Entry* oldtab = d.l1_tab; L1Meta* oldmeta = d.l1_meta; size_t oldcap = m->tcap1;
-    d.l1_tab = nullptr; d.l1_meta = nullptr;
-    if ((rc = alloc_l1_table(m, l2))) return rc;
+    // a rebuild that only sheds tombstones ping-pongs between two buffers of the same size: the table left behind by the previous
+    // rebuild is the target of this one (no cudaMalloc / cudaFree - the latter synchronises the whole device - in steady state)
+    const bool reuse = m->l1_spare_tab && m->l1_spare_cap == ((size_t)1 << l2);
+    d.l1_tab = reuse ? m->l1_spare_tab : nullptr; d.l1_meta = reuse ? m->l1_spare_meta : nullptr;
+    if (!reuse && m->l1_spare_tab) { cudaFree(m->l1_spare_tab); cudaFree(m->l1_spare_meta); }
+    m->l1_spare_tab = nullptr; m->l1_spare_meta = nullptr; m->l1_spare_cap = 0;
+    if (reuse) {
+      d.l1_log2cap = l2; m->tcap1 = (size_t)1 << l2;
+      B2_CUDA(cudaMemsetAsync(d.l1_tab, 0xFF, m->tcap1 * sizeof(L1Entry), st));
+      B2_CUDA(cudaMemsetAsync(d.l1_meta, 0, m->tcap1 * sizeof(L1Meta), st));
+    } else if ((rc = alloc_l1_table(m, l2))) return rc;
     if (oldtab && m->n1) { int blocks = (int)((oldcap + 255) / 256); if (blocks > 2368) blocks = 2368; k_l1_reinsert<<<blocks, 256, 0, st>>>(d, oldtab, oldmeta, (int)oldcap); ctx->launches++; }
     B2_CUDA(cudaMemsetAsync(d.ctr + CT_TOMB1, 0, sizeof(int), st));
-    B2_CUDA(cudaStreamSynchronize(st));
-    if (oldtab) cudaFree(oldtab);
-    if (oldmeta) cudaFree(oldmeta);
+    if (oldtab && oldcap == m->tcap1) { m->l1_spare_tab = oldtab; m->l1_spare_meta = oldmeta; m->l1_spare_cap = oldcap; }   // stream-ordered: reused only by a later rebuild
+    else {
+      B2_CUDA(cudaStreamSynchronize(st));
+      if (oldtab) cudaFree(oldtab);
+      if (oldmeta) cudaFree(oldmeta);
+    }
     m->tomb1 = 0;
   }
   if (need_upd > m->upd_cap) {
@@ -1038,6 +1053,17 @@ extern "C" int b2lo_map_create(b2lo_ctx* ctx, float voxel_size, int hierarchy_fa
   if (cudaMalloc(&d.ctr, 16 * sizeof(int)) != cudaSuccess || cudaMalloc(&m->u_state, US_COUNT * sizeof(int)) != cudaSuccess) { delete m; return B2LO_E_NOMEM; }
   cudaMemsetAsync(d.ctr, 0, 16 * sizeof(int), ctx->stream);
   cudaMemsetAsync(m->u_state, 0, US_COUNT * sizeof(int), ctx->stream);
+  {
+    // CUDA loads a kernel when it is first used; the table-maintenance kernels first run dozens of scans into a sequence (when
+    // tombstones have piled up), where a cold load showed up as a 15-190 ms stall of one UpdateVoxelMap call.  Load them now.
+    static bool loaded = false;
+    if (!loaded) {
+      cudaFuncAttributes fa;
+      cudaFuncGetAttributes(&fa, k_l0_reinsert); cudaFuncGetAttributes(&fa, k_l1_reinsert); cudaFuncGetAttributes(&fa, k_fill_int);
+      cudaGetLastError();
+      loaded = true;
+    }
+  }
   size_t hint = l0_capacity_hint ? l0_capacity_hint : (1u << 16);
   int rc = alloc_l0_table(m, ceil_log2(hint * 4));
   if (!rc) rc = alloc_l1_table(m, ceil_log2(hint));
@@ -1056,6 +1082,8 @@ extern "C" int b2lo_map_destroy(b2lo_map* m) {
   void* ptrs[] = {d.l0_cent, d.l0_key, d.l0_slot, d.l0_tab, d.l1_tab, d.l1_meta, d.ctr,
                   m->u_pts, m->u_pslot, m->u_next, m->u_isnew, m->u_newrank, m->a_tab, m->a_list, m->a_slots, m->c_flag, m->c_blkcnt,
                   m->c_blkoff, m->c_removed, m->c_aux, m->c_l1work, m->p_seq, m->p_aux, m->u_state, m->u_part, m->r_tmp, m->r_n, m->s_rec};
+  if (m->l1_spare_tab) cudaFree(m->l1_spare_tab);
+  if (m->l1_spare_meta) cudaFree(m->l1_spare_meta);
   for (void* p : ptrs) if (p) cudaFree(p);
   delete m;
   return B2LO_OK;
