@@ -585,12 +585,17 @@ struct k_ls_params {   // the S scan parameter blocks, from the contexts' page-l
 struct b2lo_lockstep {
   std::vector<b2lo_odom*> ods;
   cudaStream_t st = nullptr;
+  static constexpr int MAXB = 4;          // branches of one step's graph (see lockstep_build)
+  cudaStream_t side[MAXB] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[MAXB] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaGraphExec_t exec = nullptr;
   std::vector<unsigned long long> sig;
   std::vector<void*> d_packs;            // one device array of S argument packs per step of the recorded sequence
   const int** d_hsp = nullptr; int** d_dsp = nullptr;
   long long kernels_per_step = 0, replays = 0, builds = 0, fallbacks = 0;
+  long long kernels_per_seq = 0;
+  int branches = 1;
 };
 extern "C" int b2lo_lockstep_create(b2lo_odom* const* ods, int count, b2lo_lockstep** out) {
   if (!ods || !out || count < 1) return B2LO_E_ARG;
@@ -610,6 +615,10 @@ extern "C" int b2lo_lockstep_create(b2lo_odom* const* ods, int count, b2lo_locks
     delete ls;
     return B2LO_E_NOMEM;
   }
+  bool ok = cudaEventCreateWithFlags(&ls->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int g = 1; g < b2lo_lockstep::MAXB && ok; ++g)
+    ok = cudaStreamCreateWithFlags(&ls->side[g], cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&ls->ev_join[g], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) { set_error("lock-step: stream / event creation failed"); b2lo_lockstep_destroy(ls); return B2LO_E_NOMEM; }
   std::vector<const int*> h((size_t)count); std::vector<int*> d((size_t)count);
   for (int a = 0; a < count; ++a) { h[(size_t)a] = reinterpret_cast<const int*>(ods[a]->ctx->h_sp); d[(size_t)a] = reinterpret_cast<int*>(ods[a]->ctx->d_sp); }
   cudaMemcpy(ls->d_hsp, h.data(), sizeof(void*) * count, cudaMemcpyHostToDevice);
@@ -631,6 +640,8 @@ extern "C" int b2lo_lockstep_destroy(b2lo_lockstep* ls) {
   if (ls->d_dsp) cudaFree(ls->d_dsp);
   if (ls->ev0) cudaEventDestroy(ls->ev0);
   if (ls->ev1) cudaEventDestroy(ls->ev1);
+  if (ls->ev_fork) cudaEventDestroy(ls->ev_fork);
+  for (int g = 1; g < b2lo_lockstep::MAXB; ++g) { if (ls->ev_join[g]) cudaEventDestroy(ls->ev_join[g]); if (ls->side[g]) cudaStreamDestroy(ls->side[g]); }
   if (ls->st) cudaStreamDestroy(ls->st);
   delete ls;
   return B2LO_OK;
@@ -682,17 +693,36 @@ static int lockstep_build(b2lo_lockstep* ls, const std::vector<size_t>& flt_ns, 
   cudaGraph_t g = nullptr;
   B2_CUDA(cudaStreamBeginCapture(ls->st, cudaStreamCaptureModeThreadLocal));
   launch<k_ls_params, 64, 1>(ls->ods[0]->ctx, dim3((unsigned)S), dim3(64), 0, ls->st, (const int* const*)ls->d_hsp, (int* const*)ls->d_dsp, (int)(sizeof(ScanParams) / sizeof(int)));
-  for (size_t k = 0; k < steps; ++k) {
-    dim3 grid = recs[0].recs[k].grid;
-    for (int a = 1; a < S; ++a) if (recs[(size_t)a].recs[k].grid.x > grid.x) grid.x = recs[(size_t)a].recs[k].grid.x;   // grid-stride kernels: the widest sequence sets x
-    recs[0].recs[k].many(ls->d_packs[k], S, grid, recs[0].recs[k].block, recs[0].recs[k].smem, ls->st);
+  // Large batches run as B independent BRANCHES of the one graph (sequences [a0, a1) each, on forked streams): every Gauss-Newton
+  // iteration of a branch ends in the slowest of its single-SM PKO fits, and while one branch sits in that tail the kernels of the
+  // others fill the GPU - what several batches driven from several host threads achieve, inside one call.  B = 1 below 64 sequences.
+  int B = S / 64;
+  if (B < 1) B = 1;
+  if (B > b2lo_lockstep::MAXB) B = b2lo_lockstep::MAXB;
+  if (const char* e = std::getenv("B2LO_LOCKSTEP_BRANCHES")) { const int v = std::atoi(e); if (v >= 1 && v <= b2lo_lockstep::MAXB && v <= S) B = v; }   // test hook
+  if (B > 1) {
+    cudaEventRecord(ls->ev_fork, ls->st);
+    for (int b = 1; b < B; ++b) cudaStreamWaitEvent(ls->side[b], ls->ev_fork, 0);
   }
+  for (int b = 0; b < B; ++b) {
+    const int a0 = (int)((long long)S * b / B), a1 = (int)((long long)S * (b + 1) / B);
+    cudaStream_t sb = b == 0 ? ls->st : ls->side[b];
+    for (size_t k = 0; k < steps; ++k) {
+      dim3 grid = recs[0].recs[k].grid;
+      for (int a = 1; a < S; ++a) if (recs[(size_t)a].recs[k].grid.x > grid.x) grid.x = recs[(size_t)a].recs[k].grid.x;   // grid-stride kernels: the widest sequence sets x
+      const size_t bytes = recs[0].recs[k].args.size();
+      recs[0].recs[k].many(static_cast<const unsigned char*>(ls->d_packs[k]) + bytes * (size_t)a0, a1 - a0, grid, recs[0].recs[k].block, recs[0].recs[k].smem, sb);
+    }
+  }
+  for (int b = 1; b < B; ++b) { cudaEventRecord(ls->ev_join[b], ls->side[b]); cudaStreamWaitEvent(ls->st, ls->ev_join[b], 0); }
+  ls->branches = B;
   cudaError_t ce = cudaStreamEndCapture(ls->st, &g);
   if (ce != cudaSuccess || !g) { if (g) cudaGraphDestroy(g); set_error("lock-step: capture failed: %s", cudaGetErrorString(ce)); cudaGetLastError(); return B2LO_E_CUDA; }
   ce = cudaGraphInstantiate(&ls->exec, g, 0);
   cudaGraphDestroy(g);
   if (ce != cudaSuccess) { ls->exec = nullptr; set_error("lock-step: graph instantiation failed: %s", cudaGetErrorString(ce)); return B2LO_E_CUDA; }
-  ls->kernels_per_step = (long long)steps + 1;
+  ls->kernels_per_step = (long long)steps * ls->branches + 1;
+  ls->kernels_per_seq = (long long)steps + 1;
   ls->builds++;
   return B2LO_OK;
 }
@@ -760,7 +790,7 @@ extern "C" int b2lo_lockstep_process_dev(b2lo_lockstep* ls, const float* const* 
   int first_err = B2LO_OK, soft = B2LO_OK;
   for (int a = 0; a < S; ++a) {
     b2lo_odom* od = ls->ods[a];
-    od->ctx->launches += ls->kernels_per_step;
+    od->ctx->launches += ls->kernels_per_seq;
     od->ctx->feat_set = 0;
     od->pend.active = true; od->pend.mode = K1_SERIAL; od->pend.set = 0; od->pend.nx_src = nullptr; od->pend.nx_ns = 0; od->pend.nx_stride = 0; od->pend.t1 = now_us();
     int r = steady_finish(od, &res[a]);

@@ -125,9 +125,10 @@ def test_batch_call_matches_lone_sequences(b2, small_kitti):
     assert sum(o.graph_stats()["replays"] for o in bat.odos) > 0
 
 
-@pytest.mark.parametrize("grid_limit", [0, 2])
-def test_lockstep_batch_matches_lone_sequences(b2, small_kitti, monkeypatch, grid_limit):
-    """grid_limit = 2: the per-sequence grids of the batched kernels are forced down to two CTAs (B2LO_BATCH_GRID_LIMIT), as in a batch
+@pytest.mark.parametrize("grid_limit,branches", [(0, 0), (2, 0), (0, 3)])
+def test_lockstep_batch_matches_lone_sequences(b2, small_kitti, monkeypatch, grid_limit, branches):
+    """branches = 3: the step's graph runs the batch as three forked branches of two sequences each (B2LO_LOCKSTEP_BRANCHES; what a batch
+    of >= 128 sequences does on its own).  grid_limit = 2: the per-sequence grids of the batched kernels are forced down to two CTAs (B2LO_BATCH_GRID_LIMIT), as in a batch
     of hundreds of sequences - K2 CTAs walk several tiles (per-tile residual moments), K5 CTAs several virtual blocks, the map kernels
     stride over their work - and the bits must still be those of a lone sequence.
     b2lo_lockstep_*: S sequences advanced by ONE graph replay per scan, every kernel started once per step with blockIdx.y = sequence.
@@ -154,6 +155,8 @@ def test_lockstep_batch_matches_lone_sequences(b2, small_kitti, monkeypatch, gri
         want.append([o.process_dev(*scan_of(j, k), 4) for k in range(n)])
     if grid_limit:
         monkeypatch.setenv("B2LO_BATCH_GRID_LIMIT", str(grid_limit))
+    if branches:
+        monkeypatch.setenv("B2LO_LOCKSTEP_BRANCHES", str(branches))
     odos = [b2.Odometry(b2.Context(0)) for _ in range(S)]
     ls = b2.LockstepBatch(odos)
     for k in range(n):
