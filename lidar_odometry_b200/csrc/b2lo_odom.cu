@@ -585,9 +585,9 @@ struct k_ls_params {   // the S scan parameter blocks, from the contexts' page-l
 struct b2lo_lockstep {
   std::vector<b2lo_odom*> ods;
   cudaStream_t st = nullptr;
-  static constexpr int MAXB = 4;          // branches of one step's graph (see lockstep_build)
-  cudaStream_t side[MAXB] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join[MAXB] = {nullptr, nullptr, nullptr, nullptr};
+  static constexpr int MAXB = 8;          // branches of one step's graph (see lockstep_build)
+  cudaStream_t side[MAXB] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[MAXB] = {};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaGraphExec_t exec = nullptr;
   std::vector<unsigned long long> sig;
@@ -695,8 +695,10 @@ static int lockstep_build(b2lo_lockstep* ls, const std::vector<size_t>& flt_ns, 
   launch<k_ls_params, 64, 1>(ls->ods[0]->ctx, dim3((unsigned)S), dim3(64), 0, ls->st, (const int* const*)ls->d_hsp, (int* const*)ls->d_dsp, (int)(sizeof(ScanParams) / sizeof(int)));
   // Large batches run as B independent BRANCHES of the one graph (sequences [a0, a1) each, on forked streams): every Gauss-Newton
   // iteration of a branch ends in the slowest of its single-SM PKO fits, and while one branch sits in that tail the kernels of the
-  // others fill the GPU - what several batches driven from several host threads achieve, inside one call.  B = 1 below 64 sequences.
-  int B = S / 64;
+  // others fill the GPU - what several batches driven from several host threads achieve, inside one call.  Measured on one B200
+  // (tools/lockstep_branches.py): 128 sequences 90 k scans/s unbranched, 101 k / 110 k / 115 k with 2 / 4 / 8 branches; 256 sequences
+  // 110 k -> 134 k / 138 k with 4 / 8; 384 sequences 144 k.  One branch per 16 sequences, at most eight.
+  int B = S / 16;
   if (B < 1) B = 1;
   if (B > b2lo_lockstep::MAXB) B = b2lo_lockstep::MAXB;
   if (const char* e = std::getenv("B2LO_LOCKSTEP_BRANCHES")) { const int v = std::atoi(e); if (v >= 1 && v <= b2lo_lockstep::MAXB && v <= S) B = v; }   // test hook
