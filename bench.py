@@ -650,7 +650,7 @@ def main():
     ap.add_argument("--stress-voxels", type=float, default=1.0e7)
     ap.add_argument("--stress-only", action="store_true")
     ap.add_argument("--concurrent", type=int, nargs="*", default=[16, 32, 96], help="sequences sharing one GPU in the throughput-mode leg (empty: skip); the first size is also run with one host thread per sequence")
-    ap.add_argument("--lockstep", type=int, nargs="*", default=[32, 128, 256], help="batch sizes of the lock-step throughput leg (empty: skip)")
+    ap.add_argument("--lockstep", type=int, nargs="*", default=[32, 128, 256, 384], help="batch sizes of the lock-step throughput leg (empty: skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
@@ -771,11 +771,12 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * K / float(te.item())
 
-    # ---- throughput mode on every rank (N > 1): 3 lock-step batches of 96 independent sequences per GPU (b2lo_lockstep_process_dev), no collective;
+    # ---- throughput mode on every rank (N > 1): one lock-step batch of 384 independent sequences per GPU (b2lo_lockstep_process_dev: one call per step,
+    # the batch runs as eight branches of its graph), no collective;
     # aggregate = all sequences of all ranks / the slowest rank's wall time between barriers (informational, `value` stays one sequence per GPU)
     batched_all = None
     if world > 1 and args.concurrent:
-        G_b, S_b = 3, 96
+        G_b, S_b = 1, 384
         barrier()
         bl = lockstep_groups_leg(api, local, dev_args, G_b, S_b, K, W)
         tb = torch.tensor([G_b * S_b * K / bl["scans_per_s"]], dtype=torch.float64, device="cuda")
@@ -845,7 +846,7 @@ def main():
     lockstep = None
     if world == 1 and args.lockstep:
         lockstep = [lockstep_leg(api, local, dev_args, S, K, W, peak, peak_kind) for S in args.lockstep]
-        lockstep += [lockstep_groups_leg(api, local, dev_args, G, S, K, W) for G, S in ((3, 96), (4, 96))]
+        lockstep += [lockstep_groups_leg(api, local, dev_args, G, S, K, W) for G, S in ((3, 96),)]   # for comparison: batches driven from several host threads
 
     stress = mid360 = export = None
     if world == 1 and not args.no_stress:

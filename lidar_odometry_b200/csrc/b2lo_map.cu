@@ -1066,7 +1066,15 @@ extern "C" int b2lo_map_create(b2lo_ctx* ctx, float voxel_size, int hierarchy_fa
   }
   size_t hint = l0_capacity_hint ? l0_capacity_hint : (1u << 16);
   int rc = alloc_l0_table(m, ceil_log2(hint * 4));
-  if (!rc) rc = alloc_l1_table(m, ceil_log2(hint));
+  // the L1 table starts at the size its first tombstone-shedding rebuild would pick for a map of `hint` voxels, and the second buffer
+  // of that rebuild's ping-pong exists from the start: a sequence never waits for cudaMalloc in the middle of a run
+  const int l1_l2 = ceil_log2(hint * 2);
+  if (!rc) rc = alloc_l1_table(m, l1_l2);
+  if (!rc) {
+    if (cudaMalloc((void**)&m->l1_spare_tab, sizeof(L1Entry) << l1_l2) == cudaSuccess && cudaMalloc((void**)&m->l1_spare_meta, sizeof(L1Meta) << l1_l2) == cudaSuccess)
+      m->l1_spare_cap = (size_t)1 << l1_l2;
+    else { cudaGetLastError(); if (m->l1_spare_tab) cudaFree(m->l1_spare_tab); m->l1_spare_tab = nullptr; m->l1_spare_meta = nullptr; }   // optional: the rebuild allocates on demand
+  }
   if (!rc) rc = map_reserve(m, hint, 4096);
   if (rc) { b2lo_map_destroy(m); return rc; }
   cudaStreamSynchronize(ctx->stream);
