@@ -771,12 +771,13 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * K / float(te.item())
 
-    # ---- throughput mode on every rank (N > 1): one lock-step batch of 384 independent sequences per GPU (b2lo_lockstep_process_dev: one call per step,
-    # the batch runs as eight branches of its graph), no collective;
+    # ---- throughput mode on every rank (N > 1): three lock-step batches of 128 independent sequences per GPU (b2lo_lockstep_process_dev from three host
+    # threads: by the wall clock the per-sequence host work of ONE 384-sequence call - 3.4 us per sequence and step through Python - would bound the
+    # rate at ~87 k scans/s per GPU; three threads overlap it: 134 k), no collective;
     # aggregate = all sequences of all ranks / the slowest rank's wall time between barriers (informational, `value` stays one sequence per GPU)
     batched_all = None
     if world > 1 and args.concurrent:
-        G_b, S_b = 1, 384
+        G_b, S_b = 3, 128
         barrier()
         bl = lockstep_groups_leg(api, local, dev_args, G_b, S_b, K, W)
         tb = torch.tensor([G_b * S_b * K / bl["scans_per_s"]], dtype=torch.float64, device="cuda")
@@ -846,7 +847,7 @@ def main():
     lockstep = None
     if world == 1 and args.lockstep:
         lockstep = [lockstep_leg(api, local, dev_args, S, K, W, peak, peak_kind) for S in args.lockstep]
-        lockstep += [lockstep_groups_leg(api, local, dev_args, G, S, K, W) for G, S in ((3, 96),)]   # for comparison: batches driven from several host threads
+        lockstep += [lockstep_groups_leg(api, local, dev_args, G, S, K, W) for G, S in ((3, 128),)]   # wall clock, host work included: three batches from three host threads
 
     stress = mid360 = export = None
     if world == 1 and not args.no_stress:
