@@ -772,8 +772,8 @@ def main():
     e2e_value = world * K / float(te.item())
 
     # ---- throughput mode on every rank (N > 1): three lock-step batches of 128 independent sequences per GPU (b2lo_lockstep_process_dev from three host
-    # threads: by the wall clock the per-sequence host work of ONE 384-sequence call - 3.4 us per sequence and step through Python - would bound the
-    # rate at ~87 k scans/s per GPU; three threads overlap it: 134 k), no collective;
+    # threads: by the wall clock the per-sequence host work of ONE 384-sequence call bounds the rate at ~117 k scans/s per GPU; three threads overlap
+    # it: 136 k), no collective;
     # aggregate = all sequences of all ranks / the slowest rank's wall time between barriers (informational, `value` stays one sequence per GPU)
     batched_all = None
     if world > 1 and args.concurrent:

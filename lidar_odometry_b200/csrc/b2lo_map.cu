@@ -895,13 +895,17 @@ int map_reserve(b2lo_map* m, size_t need_l0, size_t need_upd) {
   if ((m->n0 + m->tomb0 + need_upd) * 2 > m->tcap0) {
     int l2 = ceil_log2((m->n0 + need_upd) * 4);
     if (l2 < d.l0_log2cap) l2 = d.l0_log2cap;
-    if (!(d.l0_tab && l2 == d.l0_log2cap)) {   // the table moves: the old one must be idle before it is freed
+    if (!(d.l0_tab && l2 == d.l0_log2cap)) {   // the table moves: the old one must be idle before it is freed (and graphs must be rebuilt)
       m->alloc_epoch++;
       B2_CUDA(cudaStreamSynchronize(st));
     }
+    const bool moved = !(d.l0_tab && l2 == d.l0_log2cap);
     if ((rc = alloc_l0_table(m, l2))) return rc;
     if (m->n0) { int blocks = (int)((m->n0 + 255) / 256); if (blocks > 2368) blocks = 2368; k_l0_reinsert<<<blocks, 256, 0, st>>>(d, (int)m->n0); ctx->launches++; }
     B2_CUDA(cudaMemsetAsync(d.ctr + CT_TOMB0, 0, sizeof(int), st));
+    // an in-place rebuild leaves the pointers (and alloc_epoch) alone, so nobody downstream knows that this stream carries work: a
+    // lock-step batch runs the sequence's kernels on the BATCH's stream.  Wait here (tens of microseconds, once in dozens of scans).
+    if (!moved) B2_CUDA(cudaStreamSynchronize(st));
     m->tomb0 = 0;
   }
   if ((m->n1 + m->tomb1 + need_upd) * 2 > m->tcap1) {
