@@ -306,6 +306,8 @@ int b2lo_odom_process_batch_dev(b2lo_odom* const* ods, const float* const* xyz_d
  * dispatches ~30 kernels per STEP instead of ~30 per scan (what caps b2lo_odom_process_batch_dev).  Results per sequence are those of the
  * sequence processed alone, bit for bit.  The sequences (own b2lo_odom and own b2lo_ctx each, surfel mode, same device) stay usable on
  * their own between calls; first frames, empty scans and record-stream input fall back to the per-sequence path inside the call.
+ * A batch of 32 or more sequences runs as forked branches of the step's graph (one per 16 sequences, at most eight), so that the
+ * single-SM tails of one branch overlap the kernels of the others: ~100 k scans/s for 128 sequences, ~125 k for 384 on one B200.
  * res[i].device_ms = CUDA-event time of the whole step (all sequences share it). */
 typedef struct b2lo_lockstep b2lo_lockstep;
 int b2lo_lockstep_create(b2lo_odom* const* ods, int count, b2lo_lockstep** out);
