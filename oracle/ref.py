@@ -275,3 +275,40 @@ class Pipeline:
         m = VoxelMap.__new__(VoxelMap)
         m.h = C.c_void_p(lib().ref_pipe_map(self.h)); m.owned = False; m._pipe = self   # borrowed: the pipeline owns it
         return m
+
+
+# ---- the reference's own PLY reader (oracle/_ref/libref_ply.so: the unmodified app/player/ply_player.cpp) ---------------------------
+REF_PLY = os.path.join(HERE, "_ref", "libref_ply.so")
+_ply_lib = None
+
+
+def ply_available():
+    return os.path.exists(REF_PLY)
+
+
+def _ply():
+    global _ply_lib
+    if _ply_lib is None:
+        L = C.CDLL(REF_PLY)
+        L.ref_ply_load_file.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.ref_ply_parse_header.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _ply_lib = L
+    return _ply_lib
+
+
+def ply_load_file(path, cap=1 << 20):
+    """PLYPlayer::load_ply_point_cloud(path) -> (N,3) f32 (empty when the reference returns nullptr / an empty cloud)."""
+    out = np.zeros((cap, 3), np.float32)
+    n = C.c_size_t(0)
+    rc = _ply().ref_ply_load_file(os.fsencode(path), _p(out), cap, C.byref(n))
+    if rc < 0:
+        raise RuntimeError("ref_ply_load_file: buffer too small")
+    return out[: n.value].copy() if rc == 1 else np.zeros((0, 3), np.float32)
+
+
+def ply_parse_header(path):
+    """PLYPlayer::parse_ply_header(path) -> dict(ok, vertex_count, is_binary, n_props, stride)."""
+    vc, st = C.c_size_t(0), C.c_size_t(0)
+    b, npr = C.c_int(0), C.c_int(0)
+    ok = _ply().ref_ply_parse_header(os.fsencode(path), C.byref(vc), C.byref(b), C.byref(npr), C.byref(st))
+    return dict(ok=bool(ok), vertex_count=vc.value, is_binary=bool(b.value), n_props=npr.value, stride=st.value)

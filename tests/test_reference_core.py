@@ -446,3 +446,62 @@ def test_per_scan_driver_kdtree_mode_matches_reference_classes(orc, ref):
             assert ra[key] == rb[key], (k, key)
     assert ra["icp_ok"] and ra["n_corr"] > 1000
     assert a.map().counts() == b.map().counts()
+
+
+# ---- the PLY reader: oracle/include/orc_ingest.hpp against the reference's own app/player/ply_player.cpp ---------------
+def _ply_images():
+    """Every PLY image tests/test_ingest.py feeds to the product's parser, as (name, bytes): the five binary layouts, the header quirks,
+    the rejected files, the ASCII body."""
+    from test_ingest import CASES, _cloud, _ply, _records
+    out = []
+    xyz = _cloud(257)
+    for name, (props, layout) in sorted(CASES.items()):
+        out.append((name, _ply(props, 257, _records(xyz, layout).tobytes())))
+    x10 = _cloud(10)
+    rec = _records(x10, ["x", "y", "z"])
+    P = CASES["xyz"][0]
+    out += [
+        ("later_element_properties", _ply(P, 10, rec.tobytes(), extra="element face 2\nproperty list uchar int vertex_indices")),
+        ("truncated_last_record", _ply(P, 10, rec.tobytes()[:-5])),
+        ("more_vertices_announced", _ply(P, 50, rec.tobytes())),
+        ("no_z", _ply([("float", "x"), ("float", "y")], 10, rec.tobytes())),
+        ("zero_vertices", _ply(P, 0)),
+        ("crlf_header", _ply(P, 10).replace(b"\n", b"\r\n")),
+        ("missing_magic", _ply(P, 10, rec.tobytes())[4:]),
+        ("bad_count", _ply(P, "many", rec.tobytes())),
+        ("empty_file", b""),
+        ("no_end_header", _ply(P, 10).replace(b"end_header\n", b"") + rec.tobytes()),
+        ("big_endian", _ply(P, 10, rec.tobytes(), fmt="binary_big_endian")),
+        ("duplicate_x", _ply([("float", "x"), ("float", "x"), ("float", "y"), ("float", "z")], 10, _records(x10, [("pad", 4), "x", "y", "z"]).tobytes())),
+    ]
+    body = "\n".join(["1 2 3 255", "4.5 -6.25 7e-2 0", "  8\t9   10  1  ", "11 12", "", "13 14 15 16 17 18", "1e5 .5 -.25 3", "19 2x 21 22", "+1 -2 +3.5e+1 0",
+                      "nan 1 2 3", "23 24 25 26", "0x10 1 2 3", "1e 2 3 4", "27 28 29 30"]) + "\n"
+    out.append(("ascii", _ply([("float", "x"), ("float", "y"), ("float", "z"), ("uchar", "i")], 14, body.encode(), fmt="ascii")))
+    out.append(("ascii_short", _ply(P, 100, b"1 2 3\n4 5 6\n", fmt="ascii")))
+    return out
+
+
+def test_ply_reader_matches_the_reference_player(orc, ref, tmp_path):
+    """The restated loader (orc.ply_load on a file image) against PLYPlayer::load_ply_point_cloud of the UNMODIFIED ply_player.cpp on the
+    same bytes written to a file: the same points bit for bit, the same files rejected."""
+    if not ref.ply_available():
+        pytest.skip("oracle/_ref/libref_ply.so not built")
+    n_loaded = 0
+    for name, img in _ply_images():
+        path = tmp_path / (name + ".ply")
+        path.write_bytes(img)
+        want = ref.ply_load_file(str(path))
+        got = orc.ply_load(img)
+        assert got.shape == want.shape, (name, got.shape, want.shape)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), name
+        n_loaded += int(want.shape[0] > 0)
+        # the product's own host-side header parser (b2lo_ply_parse_header, no GPU involved) against parse_ply_header of the reference
+        from lidar_odometry_b200 import api
+        h, r = api.parse_ply_header(img), ref.ply_parse_header(str(path))
+        if h is not None:
+            assert r["ok"] and h["vertex_count"] == r["vertex_count"] and h["is_binary"] == r["is_binary"] and h["fmt"].record_bytes == r["stride"], name
+            got_b2 = api.load_ply_point_cloud(img)
+            assert got_b2.shape == want.shape and np.array_equal(got_b2.view(np.uint32), want.view(np.uint32)), name
+        else:
+            assert want.shape[0] == 0, name     # whatever the product refuses, the reference loads nothing from
+    assert n_loaded >= 10   # the comparison is not vacuous: most images load
