@@ -365,7 +365,12 @@ static int steady_finish(b2lo_odom* od, b2lo_odom_result* res) {
   res->icp_status = od->h_out->icp_status;
   res->n_corr = ctx->h_icp->n_corr; res->n_iters = ctx->h_icp->num_iterations;
   od->pose = pose_from_T16(od->h_out->pose);
-  od->velocity = pose_mul(pose_inv(od->prev_pose), od->pose);  // :177
+  od->velocity = pose_mul(pose_inv(od->prev_pose), od->pose);  // :177 (prev_pose = what m_previous_frame->get_pose() returns, see below)
+  // Estimator.cpp:186-190 + LidarFrame.cpp:113-128: the next scan reads m_previous_frame->get_pose() - this frame's stored pose if it
+  // becomes a keyframe, else last_keyframe.pose * (last_keyframe.pose^-1 * pose): the same pose up to the f32 rounding of two products,
+  // which reaches the next motion-model guess and velocity (pinned against the real Estimator through the oracle pipeline)
+  const Pose rel_to_kf = pose_mul(pose_inv(od->last_kf_pose), od->pose);
+  const Pose kf_before = od->last_kf_pose;
   if (od->h_out->keyframe) {
     ctx->host_us[5] += ctx->h_counts[6]; ctx->host_us[6] += ctx->h_counts[7]; ctx->host_us[7] += 1.0;   // purge statistics
     rc = map_absorb_counts(map);
@@ -376,7 +381,7 @@ static int steady_finish(b2lo_odom* od, b2lo_odom_result* res) {
     res->keyframe = 1;
   }
   ctx->host_us[3] += now_us() - t2;
-  od->prev_pose = od->pose;
+  od->prev_pose = od->h_out->keyframe ? od->pose : pose_mul(kf_before, rel_to_kf);
   return B2LO_OK;
 }
 

@@ -46,6 +46,12 @@ class Pipeline {
   std::vector<P3> feature_cloud;   // downsampled scan (sensor frame)
   std::vector<P3> feature_world;   // same, at the optimised pose
   SE3f pose, prev_pose, velocity, last_keyframe_pose;
+  // m_previous_frame->get_pose() (LidarFrame.cpp:113-128): a keyframe returns its stored pose; any other frame returns
+  // previous_keyframe.pose * relative_pose, the relative pose being last_keyframe.pose^-1 * pose as stored at Estimator.cpp:186-190 -
+  // the same pose up to f32 rounding of the two products, and that rounding reaches the motion-model guess and the velocity
+  SE3f prev_relative;
+  bool prev_is_keyframe = true;
+  SE3f prev_frame_pose() const { return prev_is_keyframe ? prev_pose : last_keyframe_pose * prev_relative; }
   bool initialized = false;
   int n_keyframes = 0;
   bool last_was_keyframe = false, last_icp_ok = false;
@@ -101,14 +107,14 @@ class Pipeline {
       pose = SE3f(); velocity = SE3f();
       transform_cloud(feature_cloud, pose, feature_world);
       create_keyframe();
-      prev_pose = pose;
+      prev_pose = pose; prev_is_keyframe = true;
       initialized = true;
       auto t2 = clk::now();
       last_times.map_update_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
       last_times.total_ms = std::chrono::duration<double, std::milli>(t2 - t0).count();
       return true;
     }
-    SE3f guess = prev_pose * velocity;  // :154
+    SE3f guess = prev_frame_pose() * velocity;  // :154
     SE3f result = guess;
     if (!local_map.empty()) {  // estimate_motion_dual_frame :271-320
       SE3f init = SE3f::FromRt(guess.R.m, guess.t);  // SE3f(initial_guess.RotationMatrix(), ...) re-projects
@@ -121,9 +127,11 @@ class Pipeline {
     last_times.icp_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
     transform_cloud(feature_cloud, result, feature_world);
     pose = result;
-    velocity = prev_pose.Inverse() * pose;  // :177
-    if (should_create_keyframe(pose)) create_keyframe();
-    prev_pose = pose;
+    velocity = prev_frame_pose().Inverse() * pose;  // :177
+    const SE3f rel = last_keyframe_pose.Inverse() * pose;   // :189 (relative to the keyframe that precedes this frame)
+    const bool kf = should_create_keyframe(pose);
+    if (kf) create_keyframe();
+    prev_pose = pose; prev_is_keyframe = kf; prev_relative = rel;
     auto t3 = clk::now();
     last_times.map_update_ms = std::chrono::duration<double, std::milli>(t3 - t2).count();
     last_times.total_ms = std::chrono::duration<double, std::milli>(t3 - t0).count();

@@ -312,3 +312,51 @@ def ply_parse_header(path):
     b, npr = C.c_int(0), C.c_int(0)
     ok = _ply().ref_ply_parse_header(os.fsencode(path), C.byref(vc), C.byref(b), C.byref(npr), C.byref(st))
     return dict(ok=bool(ok), vertex_count=vc.value, is_binary=bool(b.value), n_props=npr.value, stride=st.value)
+
+
+# ---- the reference's own Estimator (oracle/_ref/libref_estimator.so: the unmodified src/processing/Estimator.cpp) --------------------
+REF_EST = os.path.join(HERE, "_ref", "libref_estimator.so")
+_est_lib = None
+
+
+def estimator_available():
+    return os.path.exists(REF_EST) and available()
+
+
+def _est():
+    global _est_lib
+    if _est_lib is None:
+        lib()                                      # libref_core.so first (the estimator library links it)
+        L = C.CDLL(REF_EST)
+        L.ref_est_create.restype = C.c_void_p
+        L.ref_est_create.argtypes = [C.c_void_p]
+        L.ref_est_destroy.argtypes = [C.c_void_p]
+        L.ref_est_process.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_est_map.restype = C.c_void_p
+        L.ref_est_map.argtypes = [C.c_void_p]
+        _est_lib = L
+    return _est_lib
+
+
+class Estimator:
+    """processing::Estimator itself (loop detection and pose-graph optimisation switched off): process() = process_frame on one scan."""
+
+    def __init__(self, cfg=None):
+        self.cfg = cfg or orc.default_pipe_cfg()
+        self.h = C.c_void_p(_est().ref_est_create(C.byref(self.cfg)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            _est().ref_est_destroy(self.h)
+            self.h = None
+
+    def process(self, scan):
+        s = f32(scan)
+        pose = np.zeros(16, np.float32); flags = C.c_int(0); nf = C.c_int(0)
+        ok = _est().ref_est_process(self.h, _p(s), s.shape[0], s.shape[1], _p(pose), C.byref(flags), C.byref(nf))
+        return dict(ok=bool(ok), pose=pose.reshape(4, 4).copy(), keyframe=bool(flags.value & 1), n_features=nf.value)
+
+    def map(self):
+        m = VoxelMap.__new__(VoxelMap)
+        m.h = C.c_void_p(_est().ref_est_map(self.h)); m.owned = False; m._est = self   # borrowed: the estimator owns it
+        return m

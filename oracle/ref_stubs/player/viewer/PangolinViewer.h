@@ -1,5 +1,5 @@
 // ORACLE - TEST INFRASTRUCTURE ONLY.  Stand-in for /root/reference/src/viewer/PangolinViewer.h (Pangolin / OpenGL: absent here); see
-// oracle/ref_stubs/processing/Estimator.h.  Every member the player touches exists and does nothing.
+// oracle/ref_stubs/player/processing/Estimator.h.  Every member the player touches exists and does nothing.
 #pragma once
 namespace lidar_slam {
 namespace viewer {

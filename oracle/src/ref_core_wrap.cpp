@@ -355,6 +355,7 @@ struct RefPipe {
     vmap->UpdateVoxelMap(f->get_feature_cloud_global(), sensor, cfg.max_range * 1.2, true);
     if (!cfg.icp.use_surfel_correspondence) vmap->RebuildKdTree();
     f->set_local_map(vmap->GetPointCloud());
+    f->set_keyframe_id(n_keyframes);             // :376 - from now on get_pose() of this frame is its stored pose
     last_keyframe = f;
     last_keyframe_pose = f->get_pose();
     ++n_keyframes;
@@ -412,6 +413,10 @@ struct RefPipe {
     T_wl = result;
     velocity = previous->get_pose().Inverse() * T_wl;                  // :177
     frame->set_pose(T_wl);
+    if (last_keyframe) {                                               // :186-191: a non-keyframe's get_pose() is keyframe pose * relative pose
+      frame->set_previous_keyframe(last_keyframe);
+      frame->set_relative_pose(last_keyframe->get_stored_pose().Inverse() * T_wl);
+    }
     bool kf = n_keyframes == 0;                                        // should_create_keyframe :349-368
     if (!kf) {
       Eigen::Vector3f d = T_wl.Translation() - last_keyframe_pose.Translation();

@@ -2,7 +2,7 @@
 // /root/reference/app/player/ply_player.cpp (PLYPlayer::parse_ply_header / load_ply_point_cloud, :267-461) compiled by oracle/Makefile
 // into oracle/_ref/libref_ply.so.  That translation unit also holds the player's run loop, which names processing::Estimator and
 // viewer::PangolinViewer; their headers (OpenCV, Pangolin, the pose-graph solver) are replaced by the do-nothing stand-ins of
-// oracle/ref_stubs/ found first on the include path, and Eigen::Quaternionf (trajectory writer only) comes from the force-included
+// oracle/ref_stubs/player/ found first on the include path, and Eigen::Quaternionf (trajectory writer only) comes from the force-included
 // oracle/ref_stubs/eigen_quaternion.h.  Nothing of that is executed here: the wrapper only calls the two reader functions
 // (private members: this file alone is compiled with -fno-access-control) so that tests/test_reference_core.py can compare
 // oracle/include/orc_ingest.hpp with them on the same files.

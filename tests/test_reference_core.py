@@ -505,3 +505,32 @@ def test_ply_reader_matches_the_reference_player(orc, ref, tmp_path):
         else:
             assert want.shape[0] == 0, name     # whatever the product refuses, the reference loads nothing from
     assert n_loaded >= 10   # the comparison is not vacuous: most images load
+
+
+@pytest.mark.parametrize("mid360", [False, True])
+def test_oracle_pipeline_matches_the_reference_estimator(orc, ref, mid360):
+    """orc::Pipeline (the restated process_frame control flow over the restated classes) against processing::Estimator::process_frame ITSELF:
+    the unmodified src/processing/Estimator.cpp (oracle/_ref/libref_estimator.so; loop detection and pose graph switched off, their classes
+    replaced by no-ops).  KITTI configuration: poses bit for bit, scan after scan - including the scans after a non-keyframe, whose
+    previous pose the reference re-composes from the last keyframe (LidarFrame::get_pose).  MID360 / KDTree configuration (few keyframes,
+    two different SVD algorithms in the plane fit): poses within 1e-6."""
+    if not ref.estimator_available():
+        pytest.skip("oracle/_ref/libref_estimator.so not built")
+    from lidar_odometry_b200 import synth
+    if mid360:
+        scans, _ = synth.mid360_sequence(n_scans=8, seed=3)
+    else:
+        scans, _ = synth.kitti_sequence(n_scans=8, seed=7, n_rings=64, n_az=600)
+    cfg = orc.default_pipe_cfg(mid360=mid360)
+    a, b = orc.Pipeline(cfg), ref.Estimator(cfg)
+    kfs = []
+    for k, s in enumerate(scans):
+        ra, rb = a.process(s), b.process(s)
+        assert ra["ok"] == rb["ok"] and ra["keyframe"] == rb["keyframe"] and ra["n_features"] == rb["n_features"], k
+        if mid360:
+            assert np.abs(ra["pose"].astype(np.float64) - rb["pose"]).max() < 1e-6, k
+        else:
+            assert np.array_equal(ra["pose"].view(np.uint32), rb["pose"].view(np.uint32)), k
+        kfs.append(ra["keyframe"])
+    assert not all(kfs) and any(kfs[1:]) or mid360      # the KITTI run holds a non-keyframe followed by keyframes: the re-composed pose is exercised
+    assert a.map().counts() == b.map().counts()
