@@ -118,7 +118,7 @@ def run_reference(args, rank, world):
 
 CPU_ARMS_NOTE = ("'reference' = the reference's own translation units (VoxelMap.cpp, IterativeClosestPointOptimizer.cpp, AdaptiveMEstimator.cpp, MathUtils.cpp, "
                  "PointCloudUtils.cpp, LidarFrame.cpp) compiled with the reference's own flags (-O3 -DNDEBUG, CMakeLists.txt:12,19-21) into oracle/_ref/libref_core.so against oracle/eigen_compat (Eigen is absent from the image; the stand-in "
-                 "evaluates eagerly, so this build is somewhat slower than one against real Eigen), driven in Estimator::process_frame order; 'port' = the oracle restatement "
+                 "evaluates eagerly, so this build is somewhat slower than one against real Eigen), driven by the reference's own processing::Estimator::process_frame (the unmodified Estimator.cpp, loop detection and pose graph switched off); 'port' = the oracle restatement "
                  "(bit-identical poses, plain loops).  `value` is the FASTER of the two, so the GPU / CPU ratio is never flattered by the stand-in.")
 
 
@@ -129,8 +129,10 @@ def cpu_arms(scans, K, W, S=1, T=1, stage=None):
     from oracle import orc, ref
     orc.build()
     makers = {"port": orc.Pipeline}
-    if ref.available():
-        makers["reference"] = ref.Pipeline
+    if ref.estimator_available():
+        makers["reference"] = ref.Estimator      # processing::Estimator::process_frame itself (the unmodified Estimator.cpp)
+    elif ref.available():
+        makers["reference"] = ref.Pipeline       # the same control flow over the reference's classes
     out = {}
     for kind, make in makers.items():
         pipes = [make() for _ in range(S)]
@@ -145,7 +147,7 @@ def cpu_arms(scans, K, W, S=1, T=1, stage=None):
             bar.wait()
             for s in scans[W:W + K]:
                 for pp in mine:
-                    st[t] += pp.process(s)["times_ms"]
+                    st[t] += pp.process(s).get("times_ms", 0.0)
             bar.wait()
 
         th = [threading.Thread(target=work, args=(t,)) for t in range(T)]
