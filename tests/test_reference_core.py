@@ -534,3 +534,26 @@ def test_oracle_pipeline_matches_the_reference_estimator(orc, ref, mid360):
         kfs.append(ra["keyframe"])
     assert not all(kfs) and any(kfs[1:]) or mid360      # the KITTI run holds a non-keyframe followed by keyframes: the re-composed pose is exercised
     assert a.map().counts() == b.map().counts()
+
+
+def test_oracle_pipeline_matches_the_reference_estimator_on_degenerate_scans(orc, ref):
+    """Scans that yield no features (all points non-finite: process_frame returns false and changes nothing) or too few correspondences
+    (a tiny far-away cloud: estimate_motion_dual_frame keeps the motion-model guess), in the middle of a sequence and as its very first
+    frame: the restated driver follows processing::Estimator::process_frame bit for bit through all of them."""
+    if not ref.estimator_available():
+        pytest.skip("oracle/_ref/libref_estimator.so not built")
+    from lidar_odometry_b200 import synth
+    scans, _ = synth.kitti_sequence(n_scans=6, seed=7, n_rings=64, n_az=600)
+    nan_scan = np.full((5000, 4), np.nan, np.float32)
+    far = np.zeros((4000, 4), np.float32)
+    far[:, :3] = np.random.default_rng(5).normal(0, 0.3, (4000, 3)).astype(np.float32) + np.array([900.0, 900.0, 50.0], np.float32)
+    for seq in ([scans[0], scans[1], nan_scan, scans[2], far, scans[3], scans[4]], [nan_scan, scans[0], scans[1], scans[2]]):
+        a, b = orc.Pipeline(), ref.Estimator()
+        oks = []
+        for k, s in enumerate(seq):
+            ra, rb = a.process(s), b.process(s)
+            assert (ra["ok"], ra["keyframe"], ra["n_features"]) == (rb["ok"], rb["keyframe"], rb["n_features"]), k
+            assert np.array_equal(ra["pose"].view(np.uint32), rb["pose"].view(np.uint32)), k
+            oks.append(ra["ok"])
+        assert not all(oks) and any(oks)
+        assert a.map().counts() == b.map().counts()
