@@ -338,25 +338,57 @@ def _est():
     return _est_lib
 
 
-class Estimator:
-    """processing::Estimator itself (loop detection and pose-graph optimisation switched off): process() = process_frame on one scan."""
+REF_EST_GPU = os.path.join(HERE, "_ref", "libref_estimator_gpu.so")
+_est_gpu_lib = None
 
-    def __init__(self, cfg=None):
+
+def estimator_gpu_available():
+    return os.path.exists(REF_EST_GPU)
+
+
+def _est_gpu():
+    """The same Estimator.cpp compiled against the drop-in shim and linked with libb2lo.so (needs a GPU to run)."""
+    global _est_gpu_lib
+    if _est_gpu_lib is None:
+        L = C.CDLL(REF_EST_GPU)
+        L.ref_est_create.restype = C.c_void_p
+        L.ref_est_create.argtypes = [C.c_void_p]
+        L.ref_est_destroy.argtypes = [C.c_void_p]
+        L.ref_est_process.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_est_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _est_gpu_lib = L
+    return _est_gpu_lib
+
+
+class Estimator:
+    """processing::Estimator itself (loop detection and pose-graph optimisation switched off): process() = process_frame on one scan.
+    gpu=True: the build in which database/VoxelMap.h and optimization/IterativeClosestPointOptimizer.h are the drop-in shim
+    (oracle/_ref/libref_estimator_gpu.so) - the reference's own driver running the CUDA engine."""
+
+    def __init__(self, cfg=None, gpu=False):
         self.cfg = cfg or orc.default_pipe_cfg()
-        self.h = C.c_void_p(_est().ref_est_create(C.byref(self.cfg)))
+        self._L = _est_gpu() if gpu else _est()
+        self.gpu = gpu
+        self.h = C.c_void_p(self._L.ref_est_create(C.byref(self.cfg)))
 
     def __del__(self):
         if getattr(self, "h", None):
-            _est().ref_est_destroy(self.h)
+            self._L.ref_est_destroy(self.h)
             self.h = None
+
+    def counts(self):
+        a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        self._L.ref_est_counts(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
 
     def process(self, scan):
         s = f32(scan)
         pose = np.zeros(16, np.float32); flags = C.c_int(0); nf = C.c_int(0)
-        ok = _est().ref_est_process(self.h, _p(s), s.shape[0], s.shape[1], _p(pose), C.byref(flags), C.byref(nf))
+        ok = self._L.ref_est_process(self.h, _p(s), s.shape[0], s.shape[1], _p(pose), C.byref(flags), C.byref(nf))
         return dict(ok=bool(ok), pose=pose.reshape(4, 4).copy(), keyframe=bool(flags.value & 1), n_features=nf.value)
 
     def map(self):
         m = VoxelMap.__new__(VoxelMap)
+        assert not self.gpu, "the GPU build's map is the shim's class: use counts()"
         m.h = C.c_void_p(_est().ref_est_map(self.h)); m.owned = False; m._est = self   # borrowed: the estimator owns it
         return m

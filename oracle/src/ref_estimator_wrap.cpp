@@ -7,6 +7,11 @@
 // translation units are not built: the eleven members Estimator.cpp references are defined below as no-ops, and the driver is run with
 // loop detection and pose-graph optimisation switched off (SystemConfig::loop_enable_loop_detection / pgo_enable_pgo = false), which is
 // also the configuration of the hot path this repository accelerates.  Nothing below touches the arithmetic of a scan.
+//
+// The same file is built a second time into oracle/_ref/libref_estimator_gpu.so: there Estimator.cpp is compiled through a header
+// OVERLAY (oracle/_ref/overlay: symlinks to the reference tree, except database/VoxelMap.h and
+// optimization/IterativeClosestPointOptimizer.h, which are the one-line `#include "b2lo_dropin.h"` of INTEGRATION.md) and linked with
+// libb2lo.so - the reference's own, unmodified Estimator driving the CUDA engine through the drop-in shim.
 #include <cstring>
 #include <memory>
 #include "database/LidarFrame.h"
@@ -92,6 +97,11 @@ int ref_est_process(void* h, const float* xyz, size_t n, size_t stride_floats, f
   if (n_features) *n_features = (int)r->n_features;
   return ok ? 1 : 0;
 }
-// the estimator's voxel map (a lidar_slam::map::VoxelMap of libref_core.so: usable with the ref_map_* entry points)
+// the estimator's voxel map (a lidar_slam::map::VoxelMap of libref_core.so: usable with the ref_map_* entry points; in the
+// libref_estimator_gpu.so build it is the drop-in shim's class and only the counts below are meaningful across the boundary)
 void* ref_est_map(void* h) { return static_cast<RefEstimator*>(h)->est->get_voxel_map(); }
+void ref_est_counts(void* h, size_t* l0, size_t* l1, size_t* surfels) {
+  auto* m = static_cast<RefEstimator*>(h)->est->get_voxel_map();
+  *l0 = m->GetVoxelCount(); *l1 = m->GetL1VoxelCount(); *surfels = m->GetSurfelCount();
+}
 }

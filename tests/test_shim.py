@@ -70,3 +70,32 @@ def test_dropin_with_the_reference_types_runs_the_call_sequence():
         pytest.skip("oracle/_ref/dropin_realhdr was not built (no reference tree where the repository was built)")
     r = subprocess.run([REALHDR], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "DROPIN-REALHDR PASS" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_the_reference_estimator_runs_the_cuda_engine_through_the_shim():
+    """The strongest form of the drop-in claim: the reference's OWN, unmodified src/processing/Estimator.cpp, compiled through a header
+    overlay in which exactly the two headers INTEGRATION.md names are `#include "b2lo_dropin.h"` and linked with libb2lo.so
+    (oracle/_ref/libref_estimator_gpu.so, built by oracle/Makefile where the reference tree exists), processes a sequence on the GPU.
+    Against the CPU oracle pipeline (itself bit-identical to the CPU build of the same Estimator.cpp): same keyframe decisions and
+    feature counts, poses within the north-star's 0.1 % drift."""
+    import numpy as np
+    from oracle import orc, ref
+    from lidar_odometry_b200 import synth
+    if not ref.estimator_gpu_available():
+        pytest.skip("oracle/_ref/libref_estimator_gpu.so was not built (no reference tree where the repository was built)")
+    orc.build()
+    scans, _ = synth.kitti_sequence(n_scans=8, seed=7, n_rings=64, n_az=600)
+    cpu, gpu = orc.Pipeline(), ref.Estimator(gpu=True)
+    path = 0.0
+    prev = np.zeros(3)
+    for k, s in enumerate(scans):
+        a, b = cpu.process(s), gpu.process(s)
+        assert a["ok"] == b["ok"] and a["n_features"] == b["n_features"], (k, a, b)
+        assert a["keyframe"] == b["keyframe"], k
+        path += float(np.linalg.norm(a["pose"][:3, 3] - prev)); prev = a["pose"][:3, 3].astype(np.float64)
+        assert np.linalg.norm(a["pose"][:3, 3].astype(np.float64) - b["pose"][:3, 3]) < 1e-3 + 1e-3 * path, (k, a["pose"], b["pose"])
+        assert np.abs(a["pose"][:3, :3].astype(np.float64) - b["pose"][:3, :3]).max() < 1e-3, k
+    l0, l1, _ = gpu.counts()
+    o0, o1, _ = cpu.map().counts()
+    assert abs(l0 - o0) <= 0.01 * o0 + 2 and abs(l1 - o1) <= 0.01 * o1 + 2
