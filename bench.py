@@ -286,6 +286,38 @@ def run_point_sharded(args, rank, world, local, api, torch, dist):
     return point_sharded_leg(args, rank, world, local, api, torch, dist, standalone=True)
 
 
+def dropin_estimator_leg(scans, K, W):
+    """The reference's OWN driver on the CUDA engine: the unmodified src/processing/Estimator.cpp, compiled with database/VoxelMap.h and
+    optimization/IterativeClosestPointOptimizer.h replaced by the drop-in shim and linked with libb2lo.so (oracle/_ref/libref_estimator_gpu.so,
+    built where the reference tree exists).  Wall clock per process_frame call in a child process (tools/estimator_gpu_bench.py); includes
+    what the reference does around the hot path (cloud copies, keyframe bookkeeping, sliding-window cleanup)."""
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.abspath(__file__))
+    if not os.path.exists(os.path.join(root, "oracle", "_ref", "libref_estimator_gpu.so")):
+        return {"unavailable": "oracle/_ref/libref_estimator_gpu.so was not built (no reference tree where the repository was built)"}
+    with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
+        for s in scans[:W + K]:
+            a = np.ascontiguousarray(s[:, :4], np.float32)
+            f.write(np.uint32(a.shape[0]).tobytes()); f.write(a.tobytes())
+        path = f.name
+    try:
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "estimator_gpu_bench.py"), path, str(W)], capture_output=True, text=True, timeout=300)
+    except Exception as e:      # timeout etc.
+        return {"unavailable": f"child failed: {e}"}
+    finally:
+        os.unlink(path)
+    if r.returncode != 0:
+        return {"unavailable": "child exited with " + str(r.returncode) + ": " + (r.stderr or r.stdout)[-300:]}
+    try:
+        out = json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception:
+        return {"unavailable": "child printed no JSON: " + r.stdout[-200:]}
+    out.update({"unit": UNIT, "value": out["scans_per_s"], "driver": "processing::Estimator::process_frame of the unmodified Estimator.cpp over b2lo_dropin.h + libb2lo.so",
+                "timing": "host wall clock per scan in a child process; pageable clouds; loop detection and pose graph off"})
+    return out
+
+
 def mid360_leg(ctx, api, capi, flush, torch):
     """BASELINE.json configs[2]: KDTree-mode correspondence (exact 5-NN over the L0 hash + per-query plane fit) on MID360-shaped
     non-repetitive scans (20 k points, stride 4, 0.4 m voxels), whole scan-to-map pipeline, next to the CPU oracle on the same scans."""
@@ -841,6 +873,8 @@ def main():
                "ms_per_scan": 1e3 / v, "stage_ms_per_scan": stage_cpu[kind], "stage_ms_per_scan_all": stage_cpu}
 
     dropin = dropin_leg(scans, K, W) if world == 1 else None
+    if dropin is not None:
+        dropin["reference_estimator"] = dropin_estimator_leg(scans, K, W)
 
     conc = None
     if world == 1 and args.concurrent:

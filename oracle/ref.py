@@ -381,6 +381,15 @@ class Estimator:
         self._L.ref_est_counts(self.h, C.byref(a), C.byref(b), C.byref(c))
         return a.value, b.value, c.value
 
+    def last_process_ms(self):
+        """Wall time of the last process_frame call alone (without the binding's cloud conversion); None with an older library."""
+        f = getattr(self._L, "ref_est_last_process_ms", None)
+        if f is None:
+            return None
+        f.restype = C.c_double
+        f.argtypes = [C.c_void_p]
+        return float(f(self.h))
+
     def process(self, scan):
         s = f32(scan)
         pose = np.zeros(16, np.float32); flags = C.c_int(0); nf = C.c_int(0)

@@ -12,6 +12,7 @@
 // OVERLAY (oracle/_ref/overlay: symlinks to the reference tree, except database/VoxelMap.h and
 // optimization/IterativeClosestPointOptimizer.h, which are the one-line `#include "b2lo_dropin.h"` of INTEGRATION.md) and linked with
 // libb2lo.so - the reference's own, unmodified Estimator driving the CUDA engine through the drop-in shim.
+#include <chrono>
 #include <cstring>
 #include <memory>
 #include "database/LidarFrame.h"
@@ -50,6 +51,7 @@ struct RefEstimator {
   int next_id = 0;
   size_t n_features = 0;
   bool last_kf = false;
+  double last_ms = 0.0;   // wall time of the last process_frame call alone (the cloud conversion around it is the player's job)
 };
 util::SystemConfig to_system_config(const orc_pipe_cfg* c) {   // the fields Estimator.cpp:30-105 reads, from the oracle's pipeline config
   util::SystemConfig s;
@@ -88,7 +90,9 @@ int ref_est_process(void* h, const float* xyz, size_t n, size_t stride_floats, f
   for (size_t i = 0; i < n; ++i) { util::Point3D p; p.x = xyz[i * stride_floats]; p.y = xyz[i * stride_floats + 1]; p.z = xyz[i * stride_floats + 2]; raw->push_back(p); }
   auto frame = std::make_shared<database::LidarFrame>(r->next_id++, 0.1 * r->next_id, raw);
   const size_t kf_before = r->est->get_keyframe_count();
+  const auto t0 = std::chrono::steady_clock::now();
   const bool ok = r->est->process_frame(frame);
+  r->last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   r->last_kf = r->est->get_keyframe_count() > kf_before;
   auto fc = frame->get_feature_cloud();
   r->n_features = fc ? fc->size() : 0;
@@ -100,6 +104,7 @@ int ref_est_process(void* h, const float* xyz, size_t n, size_t stride_floats, f
 // the estimator's voxel map (a lidar_slam::map::VoxelMap of libref_core.so: usable with the ref_map_* entry points; in the
 // libref_estimator_gpu.so build it is the drop-in shim's class and only the counts below are meaningful across the boundary)
 void* ref_est_map(void* h) { return static_cast<RefEstimator*>(h)->est->get_voxel_map(); }
+double ref_est_last_process_ms(void* h) { return static_cast<RefEstimator*>(h)->last_ms; }
 void ref_est_counts(void* h, size_t* l0, size_t* l1, size_t* surfels) {
   auto* m = static_cast<RefEstimator*>(h)->est->get_voxel_map();
   *l0 = m->GetVoxelCount(); *l1 = m->GetL1VoxelCount(); *surfels = m->GetSurfelCount();
