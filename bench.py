@@ -290,7 +290,9 @@ def dropin_estimator_leg(scans, K, W):
     """The reference's OWN driver on the CUDA engine: the unmodified src/processing/Estimator.cpp, compiled with database/VoxelMap.h and
     optimization/IterativeClosestPointOptimizer.h replaced by the drop-in shim and linked with libb2lo.so (oracle/_ref/libref_estimator_gpu.so,
     built where the reference tree exists).  Wall clock per process_frame call in a child process (tools/estimator_gpu_bench.py); includes
-    what the reference does around the hot path (cloud copies, keyframe bookkeeping, sliding-window cleanup)."""
+    what the reference does around the hot path (cloud copies, keyframe bookkeeping, sliding-window cleanup).
+    (oracle/_ref is only where compiled reference code lives: here the REFERENCE is the caller and libb2lo.so does every bit of the
+    hot-path arithmetic on the GPU - the product does not route through the oracle; the number is informational, next to dropin_e2e.)"""
     import subprocess
     import tempfile
     root = os.path.dirname(os.path.abspath(__file__))
