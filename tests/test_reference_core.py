@@ -388,6 +388,13 @@ def golden_run(orc, be):
     rs = [pipe.process(s) for s in scans]
     out.update(pipe_pose=[r["pose"] for r in rs], pipe_flags=[[int(r["keyframe"]), int(r["icp_ok"]), r["n_features"], r["n_corr"], r["n_iters"]] for r in rs],
                pipe_map_counts=list(pipe.map().counts()))
+    # the same through processing::Estimator::process_frame ITSELF (the unmodified Estimator.cpp) when `be` is the reference, on a
+    # sequence that holds a non-keyframe (the next scan then reads a re-composed previous pose, LidarFrame::get_pose)
+    from lidar_odometry_b200 import synth
+    seq, _ = synth.kitti_sequence(n_scans=6, seed=7, n_rings=64, n_az=600)
+    est = be.Estimator() if (hasattr(be, "Estimator") and be.estimator_available()) else be.Pipeline()
+    rs = [est.process(s) for s in seq]
+    out.update(est_pose=[r["pose"] for r in rs], est_flags=[[int(r["ok"]), int(r["keyframe"]), r["n_features"]] for r in rs], est_map_counts=list(est.map().counts()))
     return {k: np.array(v) for k, v in out.items()}
 
 
